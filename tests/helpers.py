@@ -1,0 +1,60 @@
+"""Shared helpers for the parity tests: rebuild the seeded golden-case inputs and check their hashes."""
+import hashlib
+import json
+import os
+
+import numpy as np
+
+from digat_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+# must match oracle/make_golden.py::CASES
+CASES = {
+    'default_n3_L3': (3, 2, 3, 6, True, 0.3),
+    'code_default_n5_L2': (5, 2, 2, 4, False, 0.3),
+    'wide_n8_L7': (8, 2, 7, 2, False, 0.3),
+    'unit_normal_n3_L3': (3, 2, 3, 4, False, 1.0),
+}
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def case_inputs(name):
+    """Same construction as oracle/make_golden.py::case_inputs (kept separate: tests must not need /root/reference)."""
+    N, hops, L, rows, keep, scale = CASES[name]
+    cfg = synth.make_config(SAG_neighbors=N, SAG_hops=hops, graph_depth=L)
+    sd = synth.make_state_dict(cfg, seed=11)
+    corpus = synth.make_corpus(cfg, n_news=300, n_behaviors=12, mean_candidates=3.0, seed=5, emb_scale=scale)
+    rng = np.random.Generator(np.random.PCG64(99))
+    ids = rng.choice(corpus.pair_behavior.shape[0], size=rows, replace=False)
+    empty = np.nonzero(~corpus.user_category_mask.any(axis=1))[0]
+    if len(empty):
+        hit = np.nonzero(corpus.pair_behavior == empty[0])[0]
+        if len(hit):
+            ids[0] = hit[0]
+    batch = synth.make_batch(corpus, np.sort(ids))
+    return cfg, sd, corpus, batch
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN, 'encoder_%s.npz' % name))
+    meta = json.loads(bytes(z['meta']).decode())
+    return z, meta
+
+
+def check_hashes(meta, sd, batch):
+    for k, v in sd.items():
+        assert meta['w:' + k] == sha(v.numpy()), 'synthetic weight %s drifted from the golden fixture' % k
+    for k, v in batch.items():
+        assert meta['x:' + k] == sha(v.numpy()), 'synthetic input %s drifted from the golden fixture' % k
+
+
+def rel_err(a, b):
+    """max |a-b| / max|b| -- relative to the tensor's scale (logits can be individually near zero)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
