@@ -1,0 +1,74 @@
+"""ctypes binding of libdigat_sm100.so (include/digat_sm100.h).  There is no fallback: if the library is missing,
+or the device is not sm_100, every compute entry point raises RuntimeError."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libdigat_sm100.so')
+
+c_void_p, c_int, c_int64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
+
+# name -> argument ctypes (all return int).  Must list EVERY symbol declared in include/digat_sm100.h.
+SIGNATURES = {
+    'digat_abi_version': [],
+    'digat_device_check': [c_void_p],
+    'digat_linear_f32': [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    'digat_graph_layer_fwd': [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_int, c_int, c_int, c_void_p],
+    'digat_attention_pool_fwd': [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                 c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    'digat_news_gate_fwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
+    'digat_topic_segment_fwd': [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_int, c_int, c_int, c_int, c_void_p],
+    'digat_gather_rows_i32': [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p],
+    'digat_gather_sag_i32': [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p],
+    'digat_build_user_nodes': [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                               c_void_p, c_void_p],
+    'digat_logits': [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
+    'digat_add_inplace': [c_void_p, c_void_p, c_int64, c_void_p],
+}
+
+_lib = None
+_device_ok = {}
+
+
+def load():
+    """Loads the shared library (no GPU needed) and binds every entry point."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError('libdigat_sm100.so not found at %s -- build it with `python -c "import __graft_entry__ as g; '
+                               'g.build()"` (there is no CPU/PyTorch fallback)' % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = argtypes
+            fn.restype = c_int
+        lib.digat_last_error.argtypes = []
+        lib.digat_last_error.restype = ctypes.c_char_p
+        _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    return load().digat_last_error().decode(errors='replace')
+
+
+def require_device(device_index: int):
+    """Raises unless the given CUDA device is an sm_100 part (checked once per device)."""
+    if _device_ok.get(device_index):
+        return
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError('digat_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
+    with torch.cuda.device(device_index):
+        rc = load().digat_device_check(None)
+    if rc != 0:
+        raise RuntimeError('digat_device_check failed: ' + last_error())
+    _device_ok[device_index] = True
+
+
+def call(name, *args):
+    rc = getattr(load(), name)(*args)
+    if rc != 0:
+        raise RuntimeError('%s failed (%d): %s' % (name, rc, last_error()))

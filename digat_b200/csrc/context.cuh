@@ -1,0 +1,278 @@
+// Context kernels of the DIGAT encoder: masked single-query attention pooling (reference layers.py:199-206),
+// the news-graph gate (graphEncoders.py:112-113) and the topic-level segment softmax / segment sum of the user
+// history (graphEncoders.py:128-130, torch_scatter.scatter_softmax + scatter_sum).
+//
+// All three are HBM-bound: every feature row is read once from DRAM (the value pass re-reads it from L1/L2), so
+// the roofline is bytes(F) / HBM bandwidth.  One CTA of kCtxThreads threads per batch row; a thread owns one or
+// more float4 feature quads, dot products are reduced with warp shuffles + one smem hop.
+#pragma once
+#include "common.cuh"
+
+namespace digat {
+
+constexpr int kCtxThreads = 128;
+constexpr int kCtxWarps = kCtxThreads / 32;
+constexpr int kCtxMaxItems = 128;     // max features per pooled set (graph nodes / topics / history length)
+constexpr int kCtxMaxQuads = 2;       // D <= 4 * kCtxThreads * kCtxMaxQuads = 1024
+
+// scores[k] = (F'_k . v) / sqrt(D) for k in [0,m), F' = F or relu(F)+resid.  Result in s_score (smem, all threads sync'd).
+template <bool kResid>
+__device__ __forceinline__ void ctx_scores(const float* __restrict__ F, int ldf, const float* __restrict__ Rs, int ldr,
+                                           const float* __restrict__ v, int m, int D, float inv_scale_div,
+                                           float (*s_part)[kCtxWarps], float* s_score) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nq = D >> 2;
+    float4 vq[kCtxMaxQuads];
+#pragma unroll
+    for (int c = 0; c < kCtxMaxQuads; ++c) {
+        const int q = tid + c * kCtxThreads;
+        vq[c] = q < nq ? reinterpret_cast<const float4*>(v)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int k = 0; k < m; ++k) {
+        float part = 0.f;
+#pragma unroll
+        for (int c = 0; c < kCtxMaxQuads; ++c) {
+            const int q = tid + c * kCtxThreads;
+            if (q < nq) {
+                float4 f = reinterpret_cast<const float4*>(F + (size_t)k * ldf)[q];
+                if (kResid) {
+                    const float4 t = reinterpret_cast<const float4*>(Rs + (size_t)k * ldr)[q];
+                    f.x = fmaxf(f.x, 0.f) + t.x; f.y = fmaxf(f.y, 0.f) + t.y;
+                    f.z = fmaxf(f.z, 0.f) + t.z; f.w = fmaxf(f.w, 0.f) + t.w;
+                }
+                part = fmaf(f.x, vq[c].x, part);
+                part = fmaf(f.y, vq[c].y, part);
+                part = fmaf(f.z, vq[c].z, part);
+                part = fmaf(f.w, vq[c].w, part);
+            }
+        }
+        part = warp_sum(part);
+        if (lane == 0) s_part[k][warp] = part;
+    }
+    __syncthreads();
+    if (tid < m) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kCtxWarps; ++w) s += s_part[tid][w];
+        s_score[tid] = s / inv_scale_div;
+    }
+    __syncthreads();
+}
+
+struct PoolArgs {
+    const float* F; int64_t strideF; int ldf;
+    const float* resid;                 // same strides as F (may be null)
+    const float* v;                     // [B, D]
+    const uint8_t* mask;                // [B, m]
+    float* out; int ldo;                // [B, ldo]
+    const float* add_in;                // optional [B, ldo]: out = add_in + pooled (may alias out)
+    float* first_out;                   // optional [B, ldo]: copy of F[b, 0, :]
+    float* alpha_out;                   // optional [B, m]
+    int B, m, D;
+};
+
+template <bool kResid>
+__global__ void __launch_bounds__(kCtxThreads)
+attention_pool_fwd_kernel(PoolArgs p) {
+    __shared__ float s_part[kCtxMaxItems][kCtxWarps];
+    __shared__ float s_score[kCtxMaxItems];
+    __shared__ float s_red[kCtxWarps];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m = p.m, D = p.D, nq = D >> 2;
+    const float* F = p.F + (size_t)b * p.strideF;
+    const float* Rs = kResid ? p.resid + (size_t)b * p.strideF : nullptr;
+    ctx_scores<kResid>(F, p.ldf, Rs, p.ldf, p.v + (size_t)b * D, m, D, sqrtf((float)D), s_part, s_score);
+
+    // masked softmax over the m scores (m <= 128 = one value per thread)
+    float val = -INFINITY;
+    if (tid < m) val = p.mask[(size_t)b * m + tid] != 0 ? s_score[tid] : kNegFill;
+    float mx = warp_max(val);
+    if (lane == 0) s_red[warp] = mx;
+    __syncthreads();
+    mx = s_red[0];
+#pragma unroll
+    for (int w = 1; w < kCtxWarps; ++w) mx = fmaxf(mx, s_red[w]);
+    __syncthreads();
+    const float e = tid < m ? expf(val - mx) : 0.f;
+    float sum = warp_sum(e);
+    if (lane == 0) s_red[warp] = sum;
+    __syncthreads();
+    sum = s_red[0];
+#pragma unroll
+    for (int w = 1; w < kCtxWarps; ++w) sum += s_red[w];
+    if (tid < m) {
+        const float al = e / sum;
+        s_score[tid] = al;
+        if (p.alpha_out != nullptr) p.alpha_out[(size_t)b * m + tid] = al;
+    }
+    __syncthreads();
+
+    // value pass: out = sum_k alpha_k F'_k  (k ascending, like bmm's reduction over the feature axis)
+#pragma unroll
+    for (int c = 0; c < kCtxMaxQuads; ++c) {
+        const int q = tid + c * kCtxThreads;
+        if (q >= nq) continue;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < m; ++k) {
+            float4 f = reinterpret_cast<const float4*>(F + (size_t)k * p.ldf)[q];
+            if (kResid) {
+                const float4 t = reinterpret_cast<const float4*>(Rs + (size_t)k * p.ldf)[q];
+                f.x = fmaxf(f.x, 0.f) + t.x; f.y = fmaxf(f.y, 0.f) + t.y;
+                f.z = fmaxf(f.z, 0.f) + t.z; f.w = fmaxf(f.w, 0.f) + t.w;
+            }
+            const float al = s_score[k];
+            acc.x = fmaf(al, f.x, acc.x); acc.y = fmaf(al, f.y, acc.y);
+            acc.z = fmaf(al, f.z, acc.z); acc.w = fmaf(al, f.w, acc.w);
+        }
+        if (p.add_in != nullptr) {
+            const float4 c = reinterpret_cast<const float4*>(p.add_in + (size_t)b * p.ldo)[q];
+            acc.x = c.x + acc.x; acc.y = c.y + acc.y; acc.z = c.z + acc.z; acc.w = c.w + acc.w;
+        }
+        reinterpret_cast<float4*>(p.out + (size_t)b * p.ldo)[q] = acc;
+        if (p.first_out != nullptr)
+            reinterpret_cast<float4*>(p.first_out + (size_t)b * p.ldo)[q] = reinterpret_cast<const float4*>(F)[q];
+    }
+}
+
+inline int launch_attention_pool_fwd(const float* F, int64_t strideF, int ldf, const float* resid, const float* v,
+                                     const uint8_t* mask, const float* add_in, float* out, int ldo, float* first_out,
+                                     float* alpha_out, int B, int m, int D, cudaStream_t st) {
+    DIGAT_REQUIRE(F && v && mask && out, "digat_attention_pool_fwd: null pointer");
+    DIGAT_REQUIRE(m >= 1 && m <= kCtxMaxItems, "digat_attention_pool_fwd: m=%d outside [1,%d]", m, kCtxMaxItems);
+    DIGAT_REQUIRE(D >= 4 && (D & 3) == 0 && D <= 4 * kCtxThreads * kCtxMaxQuads, "digat_attention_pool_fwd: bad D=%d", D);
+    DIGAT_REQUIRE((ldf & 3) == 0 && (ldo & 3) == 0 && (strideF & 3) == 0 && ldf >= D && ldo >= D,
+                  "digat_attention_pool_fwd: strides must be multiples of 4 and >= D");
+    DIGAT_REQUIRE(aligned16(F) && aligned16(v) && aligned16(out) && (!resid || aligned16(resid)) &&
+                  (!first_out || aligned16(first_out)), "digat_attention_pool_fwd: pointers must be 16-byte aligned");
+    if (B <= 0) return DIGAT_OK;
+    PoolArgs a{F, strideF, ldf, resid, v, mask, out, ldo, add_in, first_out, alpha_out, B, m, D};
+    if (resid) attention_pool_fwd_kernel<true><<<B, kCtxThreads, 0, st>>>(a);
+    else       attention_pool_fwd_kernel<false><<<B, kCtxThreads, 0, st>>>(a);
+    return check_launch("digat_attention_pool_fwd");
+}
+
+// ---------------------------------------------------------------------------------------------- news gate
+__global__ void news_gate_fwd_kernel(const float4* __restrict__ z, const float4* __restrict__ lg,
+                                     const float4* ctx_in, float4* ctx_out, int B, int Dq) {   // ctx_in may alias ctx_out
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * Dq) return;
+    const int b = (int)(i / Dq), q = (int)(i % Dq);
+    const float4 zz = z[i];
+    const float4 l = lg[(size_t)b * 2 * Dq + q];
+    const float4 g = lg[(size_t)b * 2 * Dq + Dq + q];
+    float4 o = ctx_in != nullptr ? ctx_in[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    auto mix = [](float zv, float lv, float gv) {
+        const float gate = 1.f / (1.f + expf(-zv));
+        return gate * lv + (1.f - gate) * gv;
+    };
+    o.x += mix(zz.x, l.x, g.x); o.y += mix(zz.y, l.y, g.y);
+    o.z += mix(zz.z, l.z, g.z); o.w += mix(zz.w, l.w, g.w);
+    ctx_out[i] = o;
+}
+
+inline int launch_news_gate_fwd(const float* z, const float* lg, const float* ctx_in, float* ctx_out, int B, int D,
+                                cudaStream_t st) {
+    DIGAT_REQUIRE(z && lg && ctx_out, "digat_news_gate_fwd: null pointer");
+    DIGAT_REQUIRE(D >= 4 && (D & 3) == 0, "digat_news_gate_fwd: D must be a multiple of 4");
+    DIGAT_REQUIRE(aligned16(z) && aligned16(lg) && aligned16(ctx_out) && (!ctx_in || aligned16(ctx_in)),
+                  "digat_news_gate_fwd: pointers must be 16-byte aligned");
+    if (B <= 0) return DIGAT_OK;
+    const int64_t total = (int64_t)B * (D / 4);
+    news_gate_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<const float4*>(z), reinterpret_cast<const float4*>(lg),
+        reinterpret_cast<const float4*>(ctx_in), reinterpret_cast<float4*>(ctx_out), B, D / 4);
+    return check_launch("digat_news_gate_fwd");
+}
+
+// ---------------------------------------------------------------------------------------------- topic segments
+struct SegArgs {
+    const float* Xu; int64_t strideX;     // [B, n_u, D], first H rows are the history
+    const float* v;                       // [B, D]
+    const int64_t* cidx;                  // [B, H]
+    float* T;                             // [B, n_seg, D]
+    float* alpha_out;                     // optional [B, H]
+    int B, H, n_seg, D;
+    int* err_flag;                        // device int, set to 1 when a segment id is out of range
+};
+
+__global__ void __launch_bounds__(kCtxThreads)
+topic_segment_fwd_kernel(SegArgs p) {
+    __shared__ float s_part[kCtxMaxItems][kCtxWarps];
+    __shared__ float s_score[kCtxMaxItems];
+    __shared__ float s_alpha[kCtxMaxItems];
+    __shared__ int s_seg[kCtxMaxItems];
+    __shared__ int s_order[kCtxMaxItems];      // history slots sorted by (segment, slot): a stable counting sort
+    __shared__ int s_start[kCtxMaxItems + 1];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int H = p.H, D = p.D, nq = D >> 2, n_seg = p.n_seg;
+    const float* Xh = p.Xu + (size_t)b * p.strideX;
+    if (tid < H) {
+        const int64_t c = p.cidx[(size_t)b * H + tid];
+        int ci = (int)c;
+        if (c < 0 || c >= n_seg) { ci = n_seg - 1; if (p.err_flag) atomicExch(p.err_flag, 1); }
+        s_seg[tid] = ci;
+    }
+    ctx_scores<false>(Xh, D, nullptr, 0, p.v + (size_t)b * D, H, D, sqrtf((float)D), s_part, s_score);
+
+    // segment softmax: every slot recomputes its segment's max and (ascending-order) sum -- H^2 <= 16K flops per row
+    if (tid < H) {
+        const int me = s_seg[tid];
+        float mx = -INFINITY;
+        for (int t = 0; t < H; ++t)
+            if (s_seg[t] == me) mx = fmaxf(mx, s_score[t]);
+        float sum = 0.f;
+        for (int t = 0; t < H; ++t)
+            if (s_seg[t] == me) sum += expf(s_score[t] - mx);
+        const float al = expf(s_score[tid] - mx) / sum;
+        s_alpha[tid] = al;
+        if (p.alpha_out != nullptr) p.alpha_out[(size_t)b * H + tid] = al;
+    }
+    // stable counting sort of the slots by segment (thread k handles segment k)
+    for (int k = tid; k <= n_seg; k += kCtxThreads) {
+        int cnt = 0;
+        for (int t = 0; t < H; ++t) cnt += (s_seg[t] < k);
+        s_start[k] = cnt;
+    }
+    __syncthreads();
+    for (int k = tid; k < n_seg; k += kCtxThreads) {
+        int pos = s_start[k];
+        for (int t = 0; t < H; ++t)
+            if (s_seg[t] == k) s_order[pos++] = t;
+    }
+    __syncthreads();
+
+    // segment sum, slots in ascending order inside a segment (the order of a CPU scatter_add)
+#pragma unroll
+    for (int c = 0; c < kCtxMaxQuads; ++c) {
+        const int q = tid + c * kCtxThreads;
+        if (q >= nq) continue;
+        for (int k = 0; k < n_seg; ++k) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int pos = s_start[k]; pos < s_start[k + 1]; ++pos) {
+                const int t = s_order[pos];
+                const float al = s_alpha[t];
+                const float4 x = reinterpret_cast<const float4*>(Xh + (size_t)t * D)[q];
+                // alpha * x is rounded before the add in the reference (alpha * X then scatter_add): no fma here
+                acc.x = __fadd_rn(acc.x, __fmul_rn(al, x.x)); acc.y = __fadd_rn(acc.y, __fmul_rn(al, x.y));
+                acc.z = __fadd_rn(acc.z, __fmul_rn(al, x.z)); acc.w = __fadd_rn(acc.w, __fmul_rn(al, x.w));
+            }
+            reinterpret_cast<float4*>(p.T + ((size_t)b * n_seg + k) * D)[q] = acc;
+        }
+    }
+}
+
+inline int launch_topic_segment_fwd(const float* Xu, int64_t strideX, const float* v, const int64_t* cidx, float* T,
+                                    float* alpha_out, int32_t* err_flag, int B, int H, int n_seg, int D, cudaStream_t st) {
+    DIGAT_REQUIRE(Xu && v && cidx && T, "digat_topic_segment_fwd: null pointer");
+    DIGAT_REQUIRE(H >= 1 && H <= kCtxMaxItems && n_seg >= 1 && n_seg <= kCtxMaxItems,
+                  "digat_topic_segment_fwd: H=%d / n_seg=%d outside [1,%d]", H, n_seg, kCtxMaxItems);
+    DIGAT_REQUIRE(D >= 4 && (D & 3) == 0 && D <= 4 * kCtxThreads * kCtxMaxQuads, "digat_topic_segment_fwd: bad D=%d", D);
+    DIGAT_REQUIRE((strideX & 3) == 0 && aligned16(Xu) && aligned16(v) && aligned16(T),
+                  "digat_topic_segment_fwd: pointers/strides must be 16-byte aligned");
+    if (B <= 0) return DIGAT_OK;
+    SegArgs a{Xu, strideX, v, cidx, T, alpha_out, B, H, n_seg, D, err_flag};
+    topic_segment_fwd_kernel<<<B, kCtxThreads, 0, st>>>(a);
+    return check_launch("digat_topic_segment_fwd");
+}
+
+}  // namespace digat

@@ -1,0 +1,121 @@
+// libdigat_sm100.so -- the C ABI (include/digat_sm100.h) over the hand-written sm_100a kernels.
+// One translation unit: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "pair_attention.cuh"
+#include "context.cuh"
+#include "gather.cuh"
+
+using namespace digat;
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+int digat_abi_version(void) { return DIGAT_ABI_VERSION; }
+
+const char* digat_last_error(void) { return g_last_error; }
+
+int digat_device_check(int* sm_count) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(DIGAT_E_CUDA, "no CUDA device: %s", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    const DeviceInfo* di = device_info();
+    if (!di) return fail(DIGAT_E_CUDA, "cannot query the current CUDA device");
+    if (di->cc_major != 10)
+        return fail(DIGAT_E_UNSUPPORTED, "libdigat_sm100 is built for sm_100a only; device is compute capability %d.x",
+                    di->cc_major);
+    if (sm_count) *sm_count = di->sm_count;
+    return DIGAT_OK;
+}
+
+int digat_linear_f32(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc,
+                     int M, int N, int K, int relu, void* stream) {
+    return launch_linear_f32(A, lda, W, ldw, bias, C, ldc, M, N, K, relu, as_stream(stream));
+}
+
+int digat_graph_layer_fwd(const float* P, int ldp, const float* k3, const float* a, const uint8_t* adj,
+                          const float* X, float* Y, float* alpha_out, int B, int n, int D, void* stream) {
+    return launch_graph_layer_fwd(P, ldp, k3, a, adj, X, Y, alpha_out, B, n, D, as_stream(stream));
+}
+
+int digat_attention_pool_fwd(const float* F, int64_t strideF, int ldf, const float* resid_F, const float* v,
+                             const uint8_t* mask, const float* add_in, float* out, int ldo, float* first_out,
+                             float* alpha_out, int B, int m, int D, void* stream) {
+    return launch_attention_pool_fwd(F, strideF, ldf, resid_F, v, mask, add_in, out, ldo, first_out, alpha_out, B, m, D,
+                                     as_stream(stream));
+}
+
+int digat_news_gate_fwd(const float* z, const float* lg, const float* ctx_in, float* ctx_out, int B, int D,
+                        void* stream) {
+    return launch_news_gate_fwd(z, lg, ctx_in, ctx_out, B, D, as_stream(stream));
+}
+
+int digat_topic_segment_fwd(const float* Xu, int64_t strideX, const float* v, const int64_t* cidx, float* T,
+                            float* alpha_out, int32_t* err_flag, int B, int H, int n_seg, int D, void* stream) {
+    return launch_topic_segment_fwd(Xu, strideX, v, cidx, T, alpha_out, err_flag, B, H, n_seg, D, as_stream(stream));
+}
+
+int digat_gather_rows_i32(const float* table, int64_t n_table, const int32_t* idx, float* out, int64_t ldo,
+                          int64_t rows, int D, int32_t* err_flag, void* stream) {
+    DIGAT_REQUIRE(table && idx && out, "digat_gather_rows_i32: null pointer");
+    DIGAT_REQUIRE(D >= 4 && (D & 3) == 0 && (ldo & 3) == 0 && ldo >= D, "digat_gather_rows_i32: D, ldo must be multiples of 4");
+    DIGAT_REQUIRE(aligned16(table) && aligned16(out), "digat_gather_rows_i32: pointers must be 16-byte aligned");
+    if (rows <= 0) return DIGAT_OK;
+    const DeviceInfo* di = device_info();
+    if (!di) return fail(DIGAT_E_CUDA, "digat_gather_rows_i32: no CUDA device");
+    gather_rows_kernel<<<gather_grid(rows, di->sm_count), kGatherThreads, 0, as_stream(stream)>>>(
+        table, n_table, idx, nullptr, 1, out, ldo, rows, D / 4, err_flag);
+    return check_launch("digat_gather_rows_i32");
+}
+
+int digat_gather_sag_i32(const float* table, int64_t n_table, const int32_t* node_id, int n_nodes,
+                         const int32_t* news, float* out, int64_t rows, int D, int32_t* err_flag, void* stream) {
+    DIGAT_REQUIRE(table && node_id && news && out, "digat_gather_sag_i32: null pointer");
+    DIGAT_REQUIRE(n_nodes >= 1 && D >= 4 && (D & 3) == 0, "digat_gather_sag_i32: bad n_nodes / D");
+    DIGAT_REQUIRE(aligned16(table) && aligned16(out), "digat_gather_sag_i32: pointers must be 16-byte aligned");
+    if (rows <= 0) return DIGAT_OK;
+    const DeviceInfo* di = device_info();
+    if (!di) return fail(DIGAT_E_CUDA, "digat_gather_sag_i32: no CUDA device");
+    const int64_t total = rows * n_nodes;
+    gather_rows_kernel<<<gather_grid(total, di->sm_count), kGatherThreads, 0, as_stream(stream)>>>(
+        table, n_table, news, node_id, n_nodes, out, D, total, D / 4, err_flag);
+    return check_launch("digat_gather_sag_i32");
+}
+
+int digat_build_user_nodes(const float* table, int64_t n_table, const int32_t* hist_idx, const float* hist,
+                           const float* topic_emb, float* Xu, int B, int H, int C, int D, int32_t* err_flag,
+                           void* stream) {
+    DIGAT_REQUIRE(topic_emb && Xu && ((table && hist_idx) || hist), "digat_build_user_nodes: null pointer");
+    DIGAT_REQUIRE(H >= 1 && C >= 0 && D >= 4 && (D & 3) == 0, "digat_build_user_nodes: bad H / C / D");
+    DIGAT_REQUIRE(aligned16(Xu) && aligned16(topic_emb) && (!table || aligned16(table)) && (!hist || aligned16(hist)),
+                  "digat_build_user_nodes: pointers must be 16-byte aligned");
+    if (B <= 0) return DIGAT_OK;
+    const DeviceInfo* di = device_info();
+    if (!di) return fail(DIGAT_E_CUDA, "digat_build_user_nodes: no CUDA device");
+    const int64_t rows = (int64_t)B * (H + C);
+    build_user_nodes_kernel<<<gather_grid(rows, di->sm_count), kGatherThreads, 0, as_stream(stream)>>>(
+        table, n_table, hist_idx, hist, topic_emb, Xu, rows, H, C, D / 4, err_flag);
+    return check_launch("digat_build_user_nodes");
+}
+
+int digat_logits(const float* news_ctx, const float* user_ctx, float* logits, int B, int D, void* stream) {
+    DIGAT_REQUIRE(news_ctx && user_ctx && logits, "digat_logits: null pointer");
+    DIGAT_REQUIRE(D >= 4 && (D & 3) == 0 && aligned16(news_ctx) && aligned16(user_ctx), "digat_logits: bad D / alignment");
+    if (B <= 0) return DIGAT_OK;
+    const int warps_per_cta = kGatherThreads / 32;
+    logits_kernel<<<(B + warps_per_cta - 1) / warps_per_cta, kGatherThreads, 0, as_stream(stream)>>>(
+        news_ctx, user_ctx, logits, B, D / 4);
+    return check_launch("digat_logits");
+}
+
+int digat_add_inplace(const float* x, float* y, int64_t count, void* stream) {
+    DIGAT_REQUIRE(x && y && aligned16(x) && aligned16(y), "digat_add_inplace: null or misaligned pointer");
+    if (count <= 0) return DIGAT_OK;
+    const int64_t threads = (count + 3) / 4;
+    add_inplace_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, as_stream(stream)>>>(x, y, count);
+    return check_launch("digat_add_inplace");
+}
+
+}  // extern "C"

@@ -1,0 +1,342 @@
+"""Drop-in for reference graphEncoders.py (``--graph_encoder=DIGAT``): same class names, constructor, parameter
+names/shapes (so reference checkpoints ``load_state_dict``), and the same public methods -- but every arithmetic
+step runs in the hand-written sm_100a kernels of libdigat_sm100.so (include/digat_sm100.h).
+
+Reference interface mirrored here (paths relative to /root/reference):
+  GraphEncoder.__init__/initialize                 graphEncoders.py:10-45
+  DIGAT.__init__/initialize                        graphEncoders.py:48-101
+  DIGAT.compute_news_graph_context(X, mask)        graphEncoders.py:109-114   (also called by util.py:43)
+  DIGAT.compute_user_graph_context(...)            graphEncoders.py:123-134
+  DIGAT.compute_news/user_graph_embeddings(...)    graphEncoders.py:143-174   (Eq. (8) at :150/:170)
+  DIGAT.forward / DIGAT.inference                  graphEncoders.py:177-198
+
+There is no PyTorch fallback: CPU tensors, a missing library or a non-sm_100 device raise RuntimeError.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _f32c(t, name):
+    if not t.is_cuda:
+        raise RuntimeError('%s must be a CUDA tensor (digat_b200 has no CPU fallback)' % name)
+    if t.dtype != torch.float32:
+        raise RuntimeError('%s must be float32, got %s' % (name, t.dtype))
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _boolc(t, name):
+    if not t.is_cuda:
+        raise RuntimeError('%s must be a CUDA tensor (digat_b200 has no CPU fallback)' % name)
+    if t.dtype not in (torch.bool, torch.uint8):
+        raise RuntimeError('%s must be bool, got %s' % (name, t.dtype))
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------- thin op wrappers
+def linear(A, W, bias=None, relu=False, M=None, K=None, lda=None, out=None):
+    """out[M,N] = A[M,K] W[N,K]^T (+bias).  ``A`` may be a strided row view (pass M, K, lda explicitly)."""
+    N = W.shape[0]
+    if K is None:
+        K = W.shape[1]
+    if M is None:
+        M = A.numel() // K
+    if lda is None:
+        lda = K
+    if out is None:
+        out = torch.empty((M, N), device=A.device, dtype=torch.float32)
+    _lib.call('digat_linear_f32', A.data_ptr(), lda, W.data_ptr(), W.stride(0), _ptr(bias), out.data_ptr(),
+              out.stride(0), M, N, K, 1 if relu else 0, _stream())
+    return out
+
+
+def graph_layer_fwd(P, k3, a, adj, X, alpha_out=None):
+    B, n, D = X.shape
+    Y = torch.empty_like(X)
+    _lib.call('digat_graph_layer_fwd', P.data_ptr(), P.stride(0), k3.data_ptr(), a.data_ptr(), adj.data_ptr(),
+              X.data_ptr(), Y.data_ptr(), _ptr(alpha_out), B, n, D, _stream())
+    return Y
+
+
+def attention_pool_fwd(F, v, mask, resid=None, add_in=None, out=None, ldo=None, first_out=None, alpha_out=None):
+    B, m, D = F.shape
+    if out is None:
+        out = torch.empty((B, D), device=F.device, dtype=torch.float32)
+        ldo = D
+    _lib.call('digat_attention_pool_fwd', F.data_ptr(), m * D, D, _ptr(resid), v.data_ptr(), mask.data_ptr(),
+              _ptr(add_in), out.data_ptr(), ldo, _ptr(first_out), _ptr(alpha_out), B, m, D, _stream())
+    return out
+
+
+class ScaledDotProductAttention(nn.Module):
+    """Parameter container with the names of reference layers.py:181-191 (``K.weight``, ``Q.weight``, ``Q.bias``).
+    The arithmetic (layers.py:199-206) is done by digat_attention_pool_fwd after folding K into the query."""
+
+    def __init__(self, feature_dim: int, query_dim: int, attention_dim: int):
+        super().__init__()
+        self.K = nn.Linear(feature_dim, attention_dim, bias=False)
+        self.Q = nn.Linear(query_dim, attention_dim, bias=True)
+        self.attention_scalar = math.sqrt(float(attention_dim))
+
+    def initialize(self):
+        nn.init.xavier_uniform_(self.K.weight)
+        nn.init.xavier_uniform_(self.Q.weight)
+        nn.init.zeros_(self.Q.bias)
+
+
+class GraphEncoder(nn.Module):
+    def __init__(self, config, news_embedding_dim: int):
+        super().__init__()
+        self.news_graph_size = config.news_graph_size
+        self.user_graph_size = config.max_history_num + config.category_num
+        self.max_history_num = config.max_history_num
+        self.category_num = config.category_num + 1
+        self.news_embedding_dim = news_embedding_dim
+        self.graph_depth = config.graph_depth
+        self.attention_scalar = math.sqrt(float(self.news_embedding_dim))
+        self.dropout_rate = float(config.dropout_rate)
+        self.topic_node_embedding = nn.Parameter(torch.zeros([config.category_num, self.news_embedding_dim]))
+
+    def initialize(self):
+        nn.init.zeros_(self.topic_node_embedding)
+
+    def forward(self, news_graph_embeddings, news_graph, news_graph_mask, user_news_embedding, user_graph,
+                user_category_mask, user_category_indices):
+        raise Exception('Function forward must be implemented at sub-class')
+
+    def inference(self, news_graph_embeddings, news_graph, news_graph_mask, user_news_embedding, user_graph,
+                  user_category_mask, user_category_indices, news_graph_context):
+        raise Exception('Function inference must be implemented at sub-class')
+
+
+class DIGAT(GraphEncoder):
+    def __init__(self, config, news_embedding_dim: int):
+        super().__init__(config, news_embedding_dim)
+        D, L = self.news_embedding_dim, self.graph_depth
+        if D % 4 != 0:
+            raise Exception('news_embedding_dim must be a multiple of 4 for the sm_100a kernels')
+        self.candidate_attention = ScaledDotProductAttention(D, D, D)
+        self.news_graph_W = nn.Linear(D * 2, D, bias=True)
+        self.user_news_K = nn.Linear(D, D, bias=False)
+        self.user_news_Q = nn.Linear(D, D, bias=True)
+        self.featureAffine = nn.Linear(D, D, bias=True)
+        self.userAttention = ScaledDotProductAttention(D, D, D)
+        for g in ('news', 'user'):
+            setattr(self, g + '_graph_attention_W', nn.ModuleList([nn.Linear(D, D, bias=True) for _ in range(L)]))
+            setattr(self, g + '_graph_attention_ffn1', nn.ModuleList([nn.Linear(D, D, bias=False) for _ in range(L)]))
+            setattr(self, g + '_graph_attention_ffn2', nn.ModuleList([nn.Linear(D, D, bias=False) for _ in range(L)]))
+            setattr(self, g + '_graph_attention_ffn3', nn.ModuleList([nn.Linear(D, D, bias=True) for _ in range(L)]))
+            setattr(self, g + '_graph_attention_a', nn.ModuleList([nn.Linear(D, 1, bias=False) for _ in range(L)]))
+        self._packed = None
+        self._packed_key = None
+
+    def initialize(self):
+        super().initialize()
+        relu_gain = nn.init.calculate_gain('relu')
+        leaky_gain = nn.init.calculate_gain('leaky_relu', 0.2)
+        for g in ('news', 'user'):
+            for i in range(self.graph_depth):
+                W = getattr(self, g + '_graph_attention_W')[i]
+                nn.init.xavier_uniform_(W.weight)
+                nn.init.zeros_(W.bias)
+                nn.init.xavier_uniform_(getattr(self, g + '_graph_attention_a')[i].weight, gain=leaky_gain)
+                for f in ('ffn1', 'ffn2', 'ffn3'):
+                    nn.init.xavier_uniform_(getattr(self, g + '_graph_attention_' + f)[i].weight, gain=relu_gain)
+                nn.init.zeros_(getattr(self, g + '_graph_attention_ffn3')[i].bias)
+        self.candidate_attention.initialize()
+        nn.init.xavier_uniform_(self.news_graph_W.weight)
+        nn.init.zeros_(self.news_graph_W.bias)
+        nn.init.xavier_uniform_(self.user_news_K.weight)
+        nn.init.xavier_uniform_(self.user_news_Q.weight)
+        nn.init.zeros_(self.user_news_Q.bias)
+        nn.init.xavier_uniform_(self.featureAffine.weight, gain=relu_gain)
+        nn.init.zeros_(self.featureAffine.bias)
+        self.userAttention.initialize()
+
+    # ---------------------------------------------------------------------------------- packed weights
+    def _weights(self):
+        """Kernel-side weight layout, rebuilt only when a parameter changed (optimizer step / load_state_dict):
+        * per layer and graph: [W; ffn1; ffn2] stacked to [3D, D] so h, K1, K2 come out of ONE projection GEMM;
+        * attention K matrices transposed, so the folded query v = K^T (Q q + b) is a plain linear;
+        * [user_news_Q; userAttention.Q] stacked: both queries of the user context come from one GEMM on c_n."""
+        params = list(self.parameters())
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if self._packed is not None and key == self._packed_key:
+            return self._packed
+        dev = params[0].device
+        if dev.type != 'cuda':
+            raise RuntimeError('DIGAT parameters must live on a CUDA device (digat_b200 has no CPU fallback)')
+        _lib.require_device(dev.index if dev.index is not None else torch.cuda.current_device())
+        D = self.news_embedding_dim
+        with torch.no_grad():
+            w = {}
+            for g in ('news', 'user'):
+                for i in range(self.graph_depth):
+                    W = getattr(self, g + '_graph_attention_W')[i]
+                    f1 = getattr(self, g + '_graph_attention_ffn1')[i]
+                    f2 = getattr(self, g + '_graph_attention_ffn2')[i]
+                    f3 = getattr(self, g + '_graph_attention_ffn3')[i]
+                    av = getattr(self, g + '_graph_attention_a')[i]
+                    w[g, i, 'Wcat'] = torch.cat([W.weight, f1.weight, f2.weight], 0).float().contiguous()
+                    w[g, i, 'bcat'] = torch.cat([W.bias, torch.zeros(2 * D, device=dev)], 0).float().contiguous()
+                    w[g, i, 'W3'] = f3.weight.detach().float().contiguous()
+                    w[g, i, 'b3'] = f3.bias.detach().float().contiguous()
+                    w[g, i, 'a'] = av.weight.detach().float().reshape(D).contiguous()
+            w['cand_Q'] = self.candidate_attention.Q.weight.detach().float().contiguous()
+            w['cand_Qb'] = self.candidate_attention.Q.bias.detach().float().contiguous()
+            w['cand_Kt'] = self.candidate_attention.K.weight.detach().float().t().contiguous()
+            w['gate_W'] = self.news_graph_W.weight.detach().float().contiguous()
+            w['gate_b'] = self.news_graph_W.bias.detach().float().contiguous()
+            w['uq_W'] = torch.cat([self.user_news_Q.weight, self.userAttention.Q.weight], 0).float().contiguous()
+            w['uq_b'] = torch.cat([self.user_news_Q.bias, self.userAttention.Q.bias], 0).float().contiguous()
+            w['unK_t'] = self.user_news_K.weight.detach().float().t().contiguous()
+            w['uaK_t'] = self.userAttention.K.weight.detach().float().t().contiguous()
+            w['fa_W'] = self.featureAffine.weight.detach().float().contiguous()
+            w['fa_b'] = self.featureAffine.bias.detach().float().contiguous()
+            w['topic'] = self.topic_node_embedding.detach().float().contiguous()
+        self._packed, self._packed_key = w, key
+        return w
+
+    # ---------------------------------------------------------------------------------- kernels, no autograd
+    def _news_ctx(self, w, X, mask, ctx_in=None):
+        B, n, D = X.shape
+        q = linear(X, w['cand_Q'], w['cand_Qb'], M=B, K=D, lda=n * D)            # Q(l), l = X[:,0,:]
+        v = linear(q, w['cand_Kt'])                                               # K^T q
+        lg = torch.empty((B, 2 * D), device=X.device, dtype=torch.float32)
+        attention_pool_fwd(X, v, mask, out=lg[:, D:], ldo=2 * D, first_out=lg)    # lg = [l | g]
+        z = linear(lg, w['gate_W'], w['gate_b'])
+        out = torch.empty((B, D), device=X.device, dtype=torch.float32)
+        _lib.call('digat_news_gate_fwd', z.data_ptr(), lg.data_ptr(), _ptr(ctx_in), out.data_ptr(), B, D, _stream())
+        return out
+
+    def _user_ctx(self, w, Xu, cmask, cidx, c_n, ctx_in=None):
+        B, nu, D = Xu.shape
+        H, S = self.max_history_num, self.category_num
+        qq = linear(c_n, w['uq_W'], w['uq_b'])                                    # [B,2D] = [user_news_Q c | userAttention.Q c]
+        v1 = linear(qq, w['unK_t'], M=B, K=D, lda=2 * D)
+        v2 = linear(qq[:, D:], w['uaK_t'], M=B, K=D, lda=2 * D)
+        T = torch.empty((B, S, D), device=Xu.device, dtype=torch.float32)
+        _lib.call('digat_topic_segment_fwd', Xu.data_ptr(), nu * D, v1.data_ptr(), cidx.data_ptr(), T.data_ptr(), 0,
+                  self._err_flag(Xu.device).data_ptr(), B, H, S, D, _stream())
+        Fa = linear(T, w['fa_W'], w['fa_b'])                                      # featureAffine(T)  [B*S, D]
+        return attention_pool_fwd(Fa.view(B, S, D), v2, cmask, resid=T, add_in=ctx_in)
+
+    def _layer(self, w, g, i, X, adj, ctx_other):
+        B, n, D = X.shape
+        P = linear(X, w[g, i, 'Wcat'], w[g, i, 'bcat'])                           # [B*n, 3D] = h | K1 | K2
+        k3 = linear(ctx_other, w[g, i, 'W3'], w[g, i, 'b3'])
+        return graph_layer_fwd(P, k3, w[g, i, 'a'], adj, X)
+
+    def _err_flag(self, device):
+        f = getattr(self, '_err', None)
+        if f is None or f.device != device:
+            f = torch.zeros(1, dtype=torch.int32, device=device)
+            self._err = f
+        return f
+
+    def check_index_errors(self):
+        """Raises if a kernel saw an out-of-range category index since the last check (synchronises)."""
+        f = getattr(self, '_err', None)
+        if f is not None and int(f.item()) != 0:
+            f.zero_()
+            raise RuntimeError('index out of range in user_category_indices (reference: torch_scatter raises)')
+
+    def _user_nodes(self, w, user_news_embedding):
+        B, H, D = user_news_embedding.shape
+        C = w['topic'].shape[0]
+        Xu = torch.empty((B, H + C, D), device=user_news_embedding.device, dtype=torch.float32)
+        _lib.call('digat_build_user_nodes', 0, 0, 0, user_news_embedding.data_ptr(), w['topic'].data_ptr(),
+                  Xu.data_ptr(), B, H, C, D, 0, _stream())
+        return Xu
+
+    def _check_inputs(self, news_graph_embeddings, news_graph, news_graph_mask, user_news_embedding, user_graph,
+                      user_category_mask, user_category_indices):
+        Xn = _f32c(news_graph_embeddings, 'news_graph_embeddings')
+        Xh = _f32c(user_news_embedding, 'user_news_embedding')
+        An = _boolc(news_graph, 'news_graph')
+        Au = _boolc(user_graph, 'user_graph')
+        Mn = _boolc(news_graph_mask, 'news_graph_mask')
+        Mc = _boolc(user_category_mask, 'user_category_mask')
+        if user_category_indices.dtype != torch.int64 or not user_category_indices.is_cuda:
+            raise RuntimeError('user_category_indices must be a CUDA int64 tensor')
+        ci = user_category_indices.contiguous()
+        B = Xn.shape[0]
+        if Xn.shape[1:] != (self.news_graph_size, self.news_embedding_dim) or \
+           Xh.shape != (B, self.max_history_num, self.news_embedding_dim) or \
+           An.shape != (B, self.news_graph_size, self.news_graph_size) or \
+           Au.shape != (B, self.user_graph_size, self.user_graph_size) or \
+           Mn.shape != (B, self.news_graph_size) or Mc.shape != (B, self.category_num) or \
+           ci.shape != (B, self.max_history_num):
+            raise RuntimeError('DIGAT: inconsistent input shapes')
+        return Xn, An, Mn, Xh, Au, Mc, ci
+
+    # ---------------------------------------------------------------------------------- reference API
+    def compute_news_graph_context(self, news_graph_embeddings, news_graph_mask):
+        w = self._weights()
+        with torch.no_grad():
+            return self._news_ctx(w, _f32c(news_graph_embeddings, 'news_graph_embeddings'),
+                                  _boolc(news_graph_mask, 'news_graph_mask'))
+
+    def compute_user_graph_context(self, user_graph_embeddings, user_category_mask, user_category_indices,
+                                   news_graph_context):
+        w = self._weights()
+        with torch.no_grad():
+            return self._user_ctx(w, _f32c(user_graph_embeddings, 'user_graph_embeddings'),
+                                  _boolc(user_category_mask, 'user_category_mask'), user_category_indices.contiguous(),
+                                  _f32c(news_graph_context, 'news_graph_context'))
+
+    def compute_news_graph_embeddings(self, index, news_graph_embeddings, news_graph, user_graph_context):
+        w = self._weights()
+        with torch.no_grad():
+            return self._layer(w, 'news', index, _f32c(news_graph_embeddings, 'news_graph_embeddings'),
+                               _boolc(news_graph, 'news_graph'), _f32c(user_graph_context, 'user_graph_context'))
+
+    def compute_user_graph_embeddings(self, index, user_graph_embeddings, user_graph, news_graph_context):
+        w = self._weights()
+        with torch.no_grad():
+            return self._layer(w, 'user', index, _f32c(user_graph_embeddings, 'user_graph_embeddings'),
+                               _boolc(user_graph, 'user_graph'), _f32c(news_graph_context, 'news_graph_context'))
+
+    def _encode(self, w, Xn, An, Mn, Xh, Au, Mc, ci, c_n):
+        Xu = self._user_nodes(w, Xh)
+        if c_n is None:
+            c_n = self._news_ctx(w, Xn, Mn)
+        c_u = self._user_ctx(w, Xu, Mc, ci, c_n)
+        for i in range(self.graph_depth):
+            Xn_new = self._layer(w, 'news', i, Xn, An, c_u)
+            Xu = self._layer(w, 'user', i, Xu, Au, c_n)
+            Xn = Xn_new
+            c_n = self._news_ctx(w, Xn, Mn, ctx_in=c_n)
+            c_u = self._user_ctx(w, Xu, Mc, ci, c_n, ctx_in=c_u)
+        return c_n, c_u
+
+    def inference(self, news_graph_embeddings, news_graph, news_graph_mask, user_news_embedding, user_graph,
+                  user_category_mask, user_category_indices, news_graph_context):
+        w = self._weights()
+        args = self._check_inputs(news_graph_embeddings, news_graph, news_graph_mask, user_news_embedding, user_graph,
+                                  user_category_mask, user_category_indices)
+        with torch.no_grad():
+            return self._encode(w, *args, _f32c(news_graph_context, 'news_graph_context'))
+
+    def forward(self, news_graph_embeddings, news_graph, news_graph_mask, user_news_embedding, user_graph,
+                user_category_mask, user_category_indices):
+        w = self._weights()
+        args = self._check_inputs(news_graph_embeddings, news_graph, news_graph_mask, user_news_embedding, user_graph,
+                                  user_category_mask, user_category_indices)
+        if torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters())
+                                        or news_graph_embeddings.requires_grad or user_news_embedding.requires_grad):
+            from . import autograd_ops   # training path: autograd.Functions over the backward kernels
+            return autograd_ops.encode_with_grad(self, *args)
+        with torch.no_grad():
+            return self._encode(w, *args, None)

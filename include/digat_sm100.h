@@ -1,0 +1,121 @@
+/*
+ * digat_sm100.h -- C ABI of libdigat_sm100.so: hand-written sm_100a kernels for the DIGAT dual-graph
+ * interaction encoder (reference: Veason-silverbullet/DIGAT, graphEncoders.py:48-198).
+ *
+ * The reference has no native code at all: every entry point below replaces a group of
+ * PyTorch/torch_scatter library calls on the hot path; the reference lines each one replaces are cited.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer into memory owned by the caller (PyTorch allocates inputs, outputs and
+ *     workspaces); the library owns nothing but cached TMA descriptors;
+ *   - all matrices are row-major fp32, 16-byte aligned, leading dimensions in ELEMENTS and multiples of 4;
+ *   - graphs / masks are 1 byte per element (torch.bool), non-zero = edge / valid;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); every call is asynchronous;
+ *   - return value: 0 on success, <0 on failure (DIGAT_E_*); digat_last_error() gives the message of the
+ *     last failure on the calling thread.  Nothing throws or exits across this boundary.
+ *   - entry points are re-entrant; there is no CPU fallback: without an sm_100 device every compute call fails.
+ */
+#ifndef DIGAT_SM100_H
+#define DIGAT_SM100_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DIGAT_OK             0
+#define DIGAT_E_INVALID     -1   /* bad argument (null pointer, misaligned, unsupported size) */
+#define DIGAT_E_CUDA        -2   /* a CUDA runtime/driver call or a launch failed */
+#define DIGAT_E_UNSUPPORTED -3   /* device is not sm_100 */
+
+#define DIGAT_ABI_VERSION 1
+
+int         digat_abi_version(void);
+const char* digat_last_error(void);
+/* Checks that the current device is compute capability 10.x; fills sm_count if non-null. */
+int         digat_device_check(int* sm_count);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Dense projections (replace nn.Linear: graphEncoders.py:146-149,166-169,112,126-127,131; layers.py:200)
+ * C[M,N] = A[M,K] * W[N,K]^T (+ bias[N]) (optionally relu), W in nn.Linear layout.
+ * --------------------------------------------------------------------------------------------------------- */
+
+/* Exact-fp32 CUDA-core GEMM (FFMA, fp32 accumulate).  Any M,N; K % 4 == 0. */
+int digat_linear_f32(const float* A, int lda, const float* W, int ldw, const float* bias,
+                     float* C, int ldc, int M, int N, int K, int relu, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Fused Eq. (8) graph-attention layer (replaces graphEncoders.py:150-153 / 170-173).
+ *   P    [B*n, ldp]  node projections of this layer: columns [0,D) = h (bias included), [D,2D) = K1, [2D,3D) = K2
+ *   k3   [B, D]      ffn3(context of the other graph) + bias          (graphEncoders.py:149 / 169)
+ *   a    [D]         attention vector                                  (news/user_graph_attention_a[i].weight)
+ *   adj  [B, n, n]   bool adjacency, row i = query node, column j = neighbour
+ *   X    [B, n, D]   layer input (residual)
+ *   Y    [B, n, D]   out: relu(softmax_j(mask(leaky_relu(a . relu((k3 + K1_j) + K2_i)))) * h) + X
+ *   alpha_out [B,n,n] optional (may be NULL): the softmax weights, saved for the backward pass.
+ * The [B,n,n,D] broadcast tensor of the reference is never materialised.  n <= 128, D % 4 == 0, D <= 1024.
+ * --------------------------------------------------------------------------------------------------------- */
+int digat_graph_layer_fwd(const float* P, int ldp, const float* k3, const float* a, const uint8_t* adj,
+                          const float* X, float* Y, float* alpha_out, int B, int n, int D, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Masked single-query attention pooling (replaces layers.py:199-206 after folding W_K into the query:
+ * a_k = F_k . v / sqrt(D) with v = W_K^T (W_Q q + b_Q)):
+ *   out[b] = sum_k softmax_k(mask(F[b,k] . v[b] / sqrt(D))) F[b,k]
+ *   F [B, m, D] with row stride ldf and batch stride strideF (elements); mask [B,m] bool; v [B,D].
+ * If resid_F != NULL the pooled features are F' = relu(F) + resid_F (graphEncoders.py:131, featureAffine output
+ * in F, topic embeddings in resid_F).  out has leading dimension ldo (so it can land inside a [B,2D] buffer).
+ * add_in [B, ldo] optional: out = add_in + pooled (context accumulation, graphEncoders.py:186/197; may alias out).
+ * first_out [B, ldo] optional: receives a copy of F[b,0,:] (the "local" context l of graphEncoders.py:110, so
+ * that [l | g] lands in one [B,2D] buffer for the gate projection).  alpha_out [B,m] optional.
+ * --------------------------------------------------------------------------------------------------------- */
+int digat_attention_pool_fwd(const float* F, int64_t strideF, int ldf, const float* resid_F,
+                             const float* v, const uint8_t* mask, const float* add_in, float* out, int ldo,
+                             float* first_out, float* alpha_out, int B, int m, int D, void* stream);
+
+/* News-graph gate (graphEncoders.py:112-113): ctx_out = ctx_in + sigmoid(z) * l + (1 - sigmoid(z)) * g
+ *   z [B,D] = news_graph_W([l;g]) (+bias, from digat_linear_*), lg [B, 2D] = [l | g].  ctx_in may be NULL
+ *   (first context, graphEncoders.py:180) and may alias ctx_out. */
+int digat_news_gate_fwd(const float* z, const float* lg, const float* ctx_in, float* ctx_out,
+                        int B, int D, void* stream);
+
+/* Topic-level aggregation of the user history (replaces torch_scatter.scatter_softmax + scatter_sum,
+ * graphEncoders.py:128-130; torch_scatter is an un-vendored third-party dependency, see oracle/scatter_shim.py):
+ *   a_t   = Xh[b,t] . v[b] / sqrt(D),                 t in [0,H)      (v = user_news_K^T (user_news_Q c_n + b))
+ *   alpha = softmax of a_t inside each segment {t : cidx[b,t] = k}
+ *   T[b,k] = sum_{t in segment k, ascending t} alpha_t Xh[b,t],  k in [0, n_seg); empty segments are 0.
+ *   Xh = first H rows of X_u [B, n_u, D] (batch stride strideX elements); cidx int64 [B,H] in [0,n_seg).
+ * alpha_out [B,H] optional.  err_flag: see the gathers below. */
+int digat_topic_segment_fwd(const float* Xu, int64_t strideX, const float* v, const int64_t* cidx,
+                            float* T, float* alpha_out, int32_t* err_flag, int B, int H, int n_seg, int D,
+                            void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Gathers (replace index_select at util.py:34-36 and util.py:65-67) and small glue.
+ * --------------------------------------------------------------------------------------------------------- */
+/* Index errors: the reference's index_select / scatter raise on an out-of-range index.  A kernel cannot raise, so
+ * every indexed entry point takes `err_flag` (device int32, may be NULL): it is set to 1 when an index is out of
+ * range (the offending row then reads row 0 / the last segment); the host wrapper checks it and raises. */
+/* out[r, :] = table[idx[r], :] for r in [0,rows); idx int32; D % 4 == 0; out row stride ldo. */
+int digat_gather_rows_i32(const float* table, int64_t n_table, const int32_t* idx, float* out, int64_t ldo,
+                          int64_t rows, int D, int32_t* err_flag, void* stream);
+/* Two-level gather for SAG node embeddings: out[r, s, :] = table[node_id[news[r], s], :]  (util.py:35 + :66
+ * without materialising the [N_news, n_n, D] cache). */
+int digat_gather_sag_i32(const float* table, int64_t n_table, const int32_t* node_id, int n_nodes,
+                         const int32_t* news, float* out, int64_t rows, int D, int32_t* err_flag,
+                         void* stream);
+/* X_u[b] = [ hist[b] (H rows, gathered from table through hist_idx or copied from `hist` if table==NULL) ;
+ *            topic_emb (C rows) ]   (graphEncoders.py:179/191: cat(user_news_embedding, topic_node_embedding)) */
+int digat_build_user_nodes(const float* table, int64_t n_table, const int32_t* hist_idx, const float* hist,
+                           const float* topic_emb, float* Xu, int B, int H, int C, int D, int32_t* err_flag,
+                           void* stream);
+/* logits[b] = sum_d news_ctx[b,d] * user_ctx[b,d]   (model.py:76,89) */
+int digat_logits(const float* news_ctx, const float* user_ctx, float* logits, int B, int D, void* stream);
+/* y = x + y (fp32, count elements) -- context accumulation (graphEncoders.py:185-186,196-197) */
+int digat_add_inplace(const float* x, float* y, int64_t count, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIGAT_SM100_H */
