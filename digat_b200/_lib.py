@@ -68,7 +68,45 @@ def require_device(device_index: int):
     _device_ok[device_index] = True
 
 
+_NON_KERNEL = ('digat_abi_version', 'digat_device_check')
+_launches = 0
+_profile = None      # list of (name, args, start_event, end_event) while bench.py's per-kernel pass is running
+
+
+def reset_launch_count():
+    global _launches
+    _launches = 0
+
+
+def launch_count() -> int:
+    """Kernel launches issued through the C ABI since the last reset (every compute entry point = 1 launch)."""
+    return _launches
+
+
+def start_profile():
+    global _profile
+    _profile = []
+    return _profile
+
+
+def stop_profile():
+    """-> [(entry point, args, milliseconds)]; call after torch.cuda.synchronize()."""
+    global _profile
+    rec, _profile = _profile or [], None
+    return [(n, a, s.elapsed_time(e)) for (n, a, s, e) in rec]
+
+
 def call(name, *args):
-    rc = getattr(load(), name)(*args)
+    global _launches
+    if _profile is not None:
+        import torch
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        rc = getattr(load(), name)(*args)
+        e.record()
+        _profile.append((name, args, s, e))
+    else:
+        rc = getattr(load(), name)(*args)
+    _launches += 1
     if rc != 0:
         raise RuntimeError('%s failed (%d): %s' % (name, rc, last_error()))

@@ -308,8 +308,9 @@ class DIGAT(GraphEncoder):
             return self._layer(w, 'user', index, _f32c(user_graph_embeddings, 'user_graph_embeddings'),
                                _boolc(user_graph, 'user_graph'), _f32c(news_graph_context, 'news_graph_context'))
 
-    def _encode(self, w, Xn, An, Mn, Xh, Au, Mc, ci, c_n):
-        Xu = self._user_nodes(w, Xh)
+    def _encode(self, w, Xn, An, Mn, Xu, Au, Mc, ci, c_n):
+        """The L-layer dual-graph schedule of graphEncoders.py:180-198 on prebuilt node tensors.
+        Xu [B, H+C, D] already holds [history ; topic nodes]; c_n None = compute the initial news context."""
         if c_n is None:
             c_n = self._news_ctx(w, Xn, Mn)
         c_u = self._user_ctx(w, Xu, Mc, ci, c_n)
@@ -326,8 +327,10 @@ class DIGAT(GraphEncoder):
         w = self._weights()
         args = self._check_inputs(news_graph_embeddings, news_graph, news_graph_mask, user_news_embedding, user_graph,
                                   user_category_mask, user_category_indices)
+        Xn, An, Mn, Xh, Au, Mc, ci = args
         with torch.no_grad():
-            return self._encode(w, *args, _f32c(news_graph_context, 'news_graph_context'))
+            return self._encode(w, Xn, An, Mn, self._user_nodes(w, Xh), Au, Mc, ci,
+                                _f32c(news_graph_context, 'news_graph_context'))
 
     def forward(self, news_graph_embeddings, news_graph, news_graph_mask, user_news_embedding, user_graph,
                 user_category_mask, user_category_indices):
@@ -338,5 +341,6 @@ class DIGAT(GraphEncoder):
                                         or news_graph_embeddings.requires_grad or user_news_embedding.requires_grad):
             from . import autograd_ops   # training path: autograd.Functions over the backward kernels
             return autograd_ops.encode_with_grad(self, *args)
+        Xn, An, Mn, Xh, Au, Mc, ci = args
         with torch.no_grad():
-            return self._encode(w, *args, None)
+            return self._encode(w, Xn, An, Mn, self._user_nodes(w, Xh), Au, Mc, ci, None)

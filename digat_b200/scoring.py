@@ -1,0 +1,140 @@
+"""Scoring driver over the sm_100a DIGAT encoder: the device-side part of reference util.compute_scores
+(util.py:34-69) -- SAG neighbour gather, the cached initial news-graph context c_n0, and the per-batch gathers +
+Model.inference -- with every gather done by the kernels of libdigat_sm100.so.
+
+Two ways in:
+* ``score_host_batch``  takes the HOST tensors the reference DataLoader yields (util.py:56: user_title_index,
+  user_graph, user_category_mask, user_category_indices, news_ID, news_graph, news_graph_mask), copies them to the
+  device and scores them: the end-to-end ("e2e") path of bench.py;
+* ``score_resident``    takes only (behaviour index, news id) per pair; graphs, masks and tables stay resident in HBM.
+Pairs are independent, so multi-GPU inference shards the pair list with no communication (``shard_range``).
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from .model import logits
+
+
+def shard_range(n_items: int, rank: int, world_size: int):
+    """Contiguous shard [lo, hi) of an ordered pair list (scores are concatenated in rank order afterwards)."""
+    per = (n_items + world_size - 1) // world_size
+    lo = min(rank * per, n_items)
+    return lo, min(lo + per, n_items)
+
+
+class Scorer:
+    def __init__(self, encoder, corpus, device):
+        """encoder: digat_b200.graphEncoders.DIGAT on `device`; corpus: digat_b200.synth.Corpus (host numpy)."""
+        self.enc = encoder.eval()
+        self.dev = torch.device(device)
+        _lib.require_device(self.dev.index if self.dev.index is not None else torch.cuda.current_device())
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.dev)
+        self.table = t(corpus.news_embeddings)                  # [N,D]   cached news representations (util.py:20-33)
+        self.node_id = t(corpus.news_node_ID)                   # [N,n_n] int32 (util.py:34)
+        self.news_graph = t(corpus.news_graph)                  # [N,n_n,n_n] bool
+        self.news_mask = t(corpus.news_graph_mask)              # [N,n_n] bool (util.py:35)
+        self.history = t(corpus.history)                        # [Nb,H] int32
+        self.user_graph = t(corpus.user_graph)                  # [Nb,nu,nu] bool
+        self.cmask = t(corpus.user_category_mask)
+        self.cidx = t(corpus.user_category_indices)
+        self.n_news, self.D = self.table.shape
+        self.n_n = self.node_id.shape[1]
+        self.err = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.c_n0 = None
+
+    def _st(self):
+        return torch.cuda.current_stream().cuda_stream
+
+    def gather_sag(self, news_idx):
+        """[B] int32 news ids -> [B, n_n, D] SAG node embeddings (util.py:35-36 + :66 without the [N,n_n,D] cache)."""
+        B = news_idx.shape[0]
+        out = torch.empty((B, self.n_n, self.D), device=self.dev, dtype=torch.float32)
+        _lib.call('digat_gather_sag_i32', self.table.data_ptr(), self.n_news, self.node_id.data_ptr(), self.n_n,
+                  news_idx.data_ptr(), out.data_ptr(), B, self.D, self.err.data_ptr(), self._st())
+        return out
+
+    def gather_rows(self, table, idx):
+        rows = idx.numel()
+        out = torch.empty((rows, table.shape[1]), device=self.dev, dtype=torch.float32)
+        _lib.call('digat_gather_rows_i32', table.data_ptr(), table.shape[0], idx.data_ptr(), out.data_ptr(),
+                  table.shape[1], rows, table.shape[1], self.err.data_ptr(), self._st())
+        return out
+
+    def user_nodes(self, hist_idx):
+        """[B,H] int32 history ids -> X_u [B, H+C, D] = [gathered history ; topic nodes] (util.py:65 + graphEncoders.py:191)."""
+        w = self.enc._weights()
+        B, H = hist_idx.shape
+        C = w['topic'].shape[0]
+        Xu = torch.empty((B, H + C, self.D), device=self.dev, dtype=torch.float32)
+        _lib.call('digat_build_user_nodes', self.table.data_ptr(), self.n_news, hist_idx.data_ptr(), 0,
+                  w['topic'].data_ptr(), Xu.data_ptr(), B, H, C, self.D, self.err.data_ptr(), self._st())
+        return Xu
+
+    def cache_news_context(self, batch_size=1024):
+        """c_n0 for every news (util.py:37-44), in chunks of batch_size news."""
+        w = self.enc._weights()
+        c = torch.empty((self.n_news, self.D), device=self.dev, dtype=torch.float32)
+        with torch.no_grad():
+            for lo in range(0, self.n_news, batch_size):
+                hi = min(lo + batch_size, self.n_news)
+                ids = torch.arange(lo, hi, device=self.dev, dtype=torch.int32)
+                c[lo:hi] = self.enc._news_ctx(w, self.gather_sag(ids), self.news_mask[lo:hi])
+        self.c_n0 = c
+        return c
+
+    def _score(self, hist_idx, Au, Mc, ci, news_idx, An, Mn):
+        w = self.enc._weights()
+        if self.c_n0 is None:
+            self.cache_news_context()
+        with torch.no_grad():
+            Xn = self.gather_sag(news_idx)
+            Xu = self.user_nodes(hist_idx)
+            c0 = self.gather_rows(self.c_n0, news_idx)
+            cn, cu = self.enc._encode(w, Xn, An, Mn, Xu, Au, Mc, ci, c0)
+            return logits(cn, cu)
+
+    def score_resident(self, beh_idx, news_idx):
+        """beh_idx, news_idx: [B] device tensors (any integer dtype).  Everything else is already in HBM."""
+        b = beh_idx.long()
+        nl = news_idx.long()
+        return self._score(self.history.index_select(0, b), self.user_graph.index_select(0, b),
+                           self.cmask.index_select(0, b), self.cidx.index_select(0, b), news_idx.to(torch.int32),
+                           self.news_graph.index_select(0, nl), self.news_mask.index_select(0, nl))
+
+    def score_host_batch(self, user_title_index, user_graph, user_category_mask, user_category_indices, news_ID,
+                         news_graph, news_graph_mask):
+        """The reference hot loop body (util.py:56-68) on HOST tensors (pinned for async copies)."""
+        d = lambda x: x.to(self.dev, non_blocking=True)
+        return self._score(d(user_title_index).to(torch.int32), d(user_graph), d(user_category_mask),
+                           d(user_category_indices), d(news_ID).to(torch.int32), d(news_graph), d(news_graph_mask))
+
+    def check_index_errors(self):
+        if int(self.err.item()) != 0:
+            self.err.zero_()
+            raise RuntimeError('index out of range in a gather (reference: index_select raises)')
+        self.enc.check_index_errors()
+
+
+def host_batch(corpus, pair_ids, pin=False):
+    """The 7 host tensors the reference's MIND_DevTest_Dataset + DataLoader yield for these pairs (MIND_dataset.py:97-102)."""
+    b = corpus.pair_behavior[pair_ids]
+    nid = corpus.pair_news[pair_ids]
+    out = (torch.from_numpy(corpus.history[b]), torch.from_numpy(corpus.user_graph[b]),
+           torch.from_numpy(corpus.user_category_mask[b]), torch.from_numpy(corpus.user_category_indices[b]),
+           torch.from_numpy(nid.astype(np.int64)), torch.from_numpy(corpus.news_graph[nid]),
+           torch.from_numpy(corpus.news_graph_mask[nid]))
+    if pin:
+        out = tuple(x.pin_memory() for x in out)
+    return out
+
+
+def compute_scores(scorer: Scorer, corpus, batch_size: int, rank: int = 0, world_size: int = 1):
+    """Scores this rank's shard of the ordered pair list through the host-batch path; returns a numpy array."""
+    lo, hi = shard_range(corpus.pair_behavior.shape[0], rank, world_size)
+    out = torch.empty(hi - lo, device=scorer.dev, dtype=torch.float32)
+    for s in range(lo, hi, batch_size):
+        e = min(s + batch_size, hi)
+        out[s - lo:e - lo] = scorer.score_host_batch(*host_batch(corpus, np.arange(s, e)))
+    scorer.check_index_errors()
+    return out.cpu().numpy()
