@@ -284,7 +284,7 @@ def summarize_kernels(records, hbm_peak, tensor_peak):
             key = '%s[n=%d]' % (name, n)
             work, bound = B * (5 * n * Dd * 4 + n * n + Dd * 4), 'hbm'
         elif name == 'digat_linear_f32' or name == 'digat_linear_tf32x3':
-            M, N, K = a[7], a[8], a[9]
+            M, N, K = (a[7], a[8], a[9]) if name == 'digat_linear_f32' else (a[8], a[9], a[10])
             key = '%s[N=%d,K=%d,%s]' % (name, N, K, 'M>2048' if M > 2048 else 'M<=2048')
             work, bound = 2.0 * M * N * K, 'tensor'
         elif name == 'digat_attention_pool_fwd':

@@ -13,6 +13,9 @@ SIGNATURES = {
     'digat_abi_version': [],
     'digat_device_check': [c_void_p],
     'digat_linear_f32': [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    'digat_split_tf32': [c_void_p, c_void_p, c_void_p, c_int64, c_void_p],
+    'digat_linear_tf32x3': [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    'digat_debug_set_gemm_variant': [c_int],
     'digat_graph_layer_fwd': [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_int, c_int, c_int, c_void_p],
     'digat_attention_pool_fwd': [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
@@ -68,7 +71,7 @@ def require_device(device_index: int):
     _device_ok[device_index] = True
 
 
-_NON_KERNEL = ('digat_abi_version', 'digat_device_check')
+_NON_KERNEL = ('digat_abi_version', 'digat_device_check', 'digat_debug_set_gemm_variant')
 _launches = 0
 _profile = None      # list of (name, args, start_event, end_event) while bench.py's per-kernel pass is running
 

@@ -2,6 +2,7 @@
 // One translation unit: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_tcgen05.cuh"
 #include "pair_attention.cuh"
 #include "context.cuh"
 #include "gather.cuh"
@@ -33,6 +34,23 @@ int digat_device_check(int* sm_count) {
 int digat_linear_f32(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc,
                      int M, int N, int K, int relu, void* stream) {
     return launch_linear_f32(A, lda, W, ldw, bias, C, ldc, M, N, K, relu, as_stream(stream));
+}
+
+int digat_split_tf32(const float* W, float* W_hi, float* W_lo, int64_t count, void* stream) {
+    DIGAT_REQUIRE(W && W_hi && W_lo, "digat_split_tf32: null pointer");
+    if (count <= 0) return DIGAT_OK;
+    split_tf32_kernel<<<(unsigned)((count + 255) / 256), 256, 0, as_stream(stream)>>>(W, W_hi, W_lo, count);
+    return check_launch("digat_split_tf32");
+}
+
+int digat_linear_tf32x3(const float* A, int lda, const float* W_hi, const float* W_lo, int ldw, const float* bias,
+                        float* C, int ldc, int M, int N, int K, void* stream) {
+    return launch_linear_tf32x3(A, lda, W_hi, W_lo, ldw, bias, C, ldc, M, N, K, as_stream(stream));
+}
+
+int digat_debug_set_gemm_variant(int variant) {
+    g_tc_variant = variant;
+    return DIGAT_OK;
 }
 
 int digat_graph_layer_fwd(const float* P, int ldp, const float* k3, const float* a, const uint8_t* adj,

@@ -1,0 +1,369 @@
+// tcgen05 tensor-core GEMM with fp32-level accuracy (3xTF32 error compensation), TMA-fed, accumulators in TMEM.
+//
+//   C[M,N] = A[M,K] * W[N,K]^T (+ bias)        A fp32 (split on the fly), W pre-split into two TF32 planes
+//   A = A_hi + A_lo  (A_hi = rna_tf32(A), A_lo = rna_tf32(A - A_hi));  W = W_hi + W_lo likewise
+//   C = A_hi*W_hi + A_lo*W_hi + A_hi*W_lo      (the dropped A_lo*W_lo term is ~2^-22 relative)
+//
+// This is the projection GEMM of the DIGAT layer: h | K1 | K2 = X * [W; ffn1; ffn2]^T (reference
+// graphEncoders.py:146-148 / 166-168), M = batch*nodes, N = 3D = 1200, K = D = 400.
+//
+// CTA = 192 threads, one output tile of (MH*128) x BN:
+//   warp 0      TMA producer: per k-block (16 fp32 = one 64-byte swizzle row) loads the raw A tile and both W planes
+//   warps 2..5  operand transform: split the raw fp32 A tile in smem into A_hi (in place) and A_lo, fence to the
+//               async proxy, signal the MMA warp; after the main loop the same warps run the epilogue
+//               (tcgen05.ld TMEM -> registers, + bias, 128-bit global stores)
+//   warp 1      MMA issuer (one elected lane): 3 x tcgen05.mma.kind::tf32 per 8-wide k-step and 128-row half, commit
+//               to the stage's "empty" barrier; owns the TMEM allocation (MH*BN fp32 columns).
+// Pipeline: full[s] (TMA bytes landed) -> ready[s] (A split done) -> MMA -> empty[s] (tcgen05.commit) -> TMA.
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+
+namespace digat {
+
+constexpr int kTcBK = 16;                       // fp32 elements per k-block = 64 bytes = SWIZZLE_64B span
+constexpr int kTcThreads = 192;
+constexpr int kTcTransformThreads = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Bounded spin: a barrier that never completes traps (CUDA error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    for (uint32_t spin = 0; ; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return;
+        if (spin > (1u << 24)) {
+            printf("digat gemm_tcgen05: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+            __trap();
+        }
+    }
+}
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+
+// K-major operand tile, SWIZZLE_64B: rows of 64 bytes, 8-row groups of 512 bytes (SBO), version 1 (sm_100).
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);        // start address  [0,14)
+    d |= (uint64_t)1 << 16;                             // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(512 >> 4) << 32;                    // stride byte offset [32,46)
+    d |= (uint64_t)1 << 46;                             // descriptor version
+    d |= (uint64_t)4 << 61;                             // SWIZZLE_64B
+    return d;
+}
+
+// kind::tf32, fp32 accumulate, both operands K-major, M=128, N=BN.
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                 :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float to_tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// SPLIT: the correction products (A_lo*W_hi + A_hi*W_lo, ~2^-11 of the main term) get their own TMEM accumulator.
+// The tensor core adds into the fp32 accumulator with truncation, aligned to the accumulator's exponent; keeping the
+// small terms out of the large accumulator removes most of that error (measured: see profiles/ and DESIGN.md).
+template <int BN, int MH, bool SPLIT>
+struct TcCfg {
+    static constexpr int BM = 128 * MH;
+    static constexpr int A_BYTES = BM * kTcBK * 4;             // one plane of the A tile
+    static constexpr int W_BYTES = BN * kTcBK * 4;
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
+    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
+    static constexpr int ACC_COLS = MH * BN * (SPLIT ? 2 : 1);
+    static constexpr int TMEM_COLS = (ACC_COLS <= 32) ? 32 : (ACC_COLS <= 64) ? 64 : (ACC_COLS <= 128) ? 128
+                                     : (ACC_COLS <= 256) ? 256 : 512;
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
+    static_assert(BN % 16 == 0 && BN <= 256, "invalid UMMA N");
+    static_assert(A_BYTES % 1024 == 0 && W_BYTES % 1024 == 0, "operand tiles must keep 1024-byte alignment");
+    static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
+};
+
+template <int BN, int MH, bool SPLIT>
+__global__ void __launch_bounds__(kTcThreads, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_whi,
+                   const __grid_constant__ CUtensorMap map_wlo, const float* __restrict__ bias,
+                   float* __restrict__ C, int ldc, int M, int N, int K) {
+    using Cfg = TcCfg<BN, MH, SPLIT>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full = bars;                       // [STAGES] TMA bytes landed
+    uint64_t* ready = bars + Cfg::STAGES;        // [STAGES] A split into hi/lo
+    uint64_t* empty = bars + 2 * Cfg::STAGES;    // [STAGES] MMAs reading the stage have completed
+    uint64_t* accum_full = bars + 3 * Cfg::STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * Cfg::STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * Cfg::BM;
+    const int nkb = (K + kTcBK - 1) / kTcBK;
+
+    auto a_hi = [&](int s) { return smem + (size_t)s * Cfg::STAGE_BYTES; };
+    auto a_lo = [&](int s) { return smem + (size_t)s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
+    auto w_hi = [&](int s) { return smem + (size_t)s * Cfg::STAGE_BYTES + 2 * Cfg::A_BYTES; };
+    auto w_lo = [&](int s) { return smem + (size_t)s * Cfg::STAGE_BYTES + 2 * Cfg::A_BYTES + Cfg::W_BYTES; };
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(&map_whi)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(&map_wlo)) : "memory");
+        for (int s = 0; s < Cfg::STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&ready[s], kTcTransformThreads);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(accum_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {   // TMEM allocation (whole warp), address lands in smem
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % Cfg::STAGES;
+                const uint32_t ph = (kb / Cfg::STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                mbar_arrive_expect_tx(&full[s], Cfg::A_BYTES + 2 * Cfg::W_BYTES);
+                tma_load_2d(a_hi(s), &map_a, &full[s], kb * kTcBK, m0);
+                tma_load_2d(w_hi(s), &map_whi, &full[s], kb * kTcBK, n0);
+                tma_load_2d(w_lo(s), &map_wlo, &full[s], kb * kTcBK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(128, BN);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % Cfg::STAGES;
+                const uint32_t ph = (kb / Cfg::STAGES) & 1;
+                mbar_wait(&ready[s], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint64_t d_whi = umma_desc_sw64(smem_u32(w_hi(s)));
+                const uint64_t d_wlo = umma_desc_sw64(smem_u32(w_lo(s)));
+#pragma unroll
+                for (int h = 0; h < MH; ++h) {
+                    const uint64_t d_ahi = umma_desc_sw64(smem_u32(a_hi(s) + h * 128 * kTcBK * 4));
+                    const uint64_t d_alo = umma_desc_sw64(smem_u32(a_lo(s) + h * 128 * kTcBK * 4));
+                    const uint32_t d_main = tmem_base + (uint32_t)(h * BN);
+                    const uint32_t d_corr = SPLIT ? tmem_base + (uint32_t)((MH + h) * BN) : d_main;
+#pragma unroll
+                    for (int k = 0; k < kTcBK / 8; ++k) {
+                        const uint64_t koff = (uint64_t)((k * 8 * 4) >> 4);       // 32 bytes per k-step, in 16-byte units
+                        const uint32_t first = (kb > 0 || k > 0) ? 1u : 0u;
+                        umma_tf32(d_main, d_ahi + koff, d_whi + koff, idesc, first);
+                        umma_tf32(d_corr, d_alo + koff, d_whi + koff, idesc, SPLIT ? first : 1u);
+                        umma_tf32(d_corr, d_ahi + koff, d_wlo + koff, idesc, 1u);
+                    }
+                }
+                umma_commit(&empty[s]);            // frees the smem stage once these MMAs retire
+            }
+            umma_commit(accum_full);               // accumulators complete
+        }
+    } else {
+        // ------------------------------------------------------------------ operand transform, then epilogue
+        const int t = threadIdx.x - 64;            // 0..127
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % Cfg::STAGES;
+            const uint32_t ph = (kb / Cfg::STAGES) & 1;
+            mbar_wait(&full[s], ph);
+            float4* hi = reinterpret_cast<float4*>(a_hi(s));
+            float4* lo = reinterpret_cast<float4*>(a_lo(s));
+#pragma unroll
+            for (int i = 0; i < Cfg::A_BYTES / 16 / kTcTransformThreads; ++i) {
+                const int idx = t + i * kTcTransformThreads;     // elementwise: the swizzle pattern is irrelevant
+                const float4 v = hi[idx];
+                float4 vh, vl;
+                vh.x = to_tf32_rna(v.x); vh.y = to_tf32_rna(v.y); vh.z = to_tf32_rna(v.z); vh.w = to_tf32_rna(v.w);
+                vl.x = to_tf32_rna(v.x - vh.x); vl.y = to_tf32_rna(v.y - vh.y);
+                vl.z = to_tf32_rna(v.z - vh.z); vl.w = to_tf32_rna(v.w - vh.w);
+                hi[idx] = vh;
+                lo[idx] = vl;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
+            mbar_arrive(&ready[s]);
+        }
+        // epilogue: this warp may touch TMEM lanes [32*(warp%4), +32)
+        mbar_wait(accum_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3;
+#pragma unroll
+        for (int h = 0; h < MH; ++h) {
+            const int m = m0 + h * 128 + q * 32 + lane;
+            float* crow = C + (size_t)m * ldc + n0;
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 16) {
+                uint32_t r[16];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * BN + c);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                    : "r"(taddr));
+                if (SPLIT) {
+                    uint32_t r2[16];
+                    const uint32_t taddr2 = taddr + (uint32_t)(MH * BN);
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                        : "=r"(r2[0]), "=r"(r2[1]), "=r"(r2[2]), "=r"(r2[3]), "=r"(r2[4]), "=r"(r2[5]), "=r"(r2[6]), "=r"(r2[7]),
+                          "=r"(r2[8]), "=r"(r2[9]), "=r"(r2[10]), "=r"(r2[11]), "=r"(r2[12]), "=r"(r2[13]), "=r"(r2[14]), "=r"(r2[15])
+                        : "r"(taddr2));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
+                }
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (m < M) {
+#pragma unroll
+                    for (int v4 = 0; v4 < 4; ++v4) {
+                        float4 o;
+                        o.x = __uint_as_float(r[v4 * 4 + 0]); o.y = __uint_as_float(r[v4 * 4 + 1]);
+                        o.z = __uint_as_float(r[v4 * 4 + 2]); o.w = __uint_as_float(r[v4 * 4 + 3]);
+                        if (bias != nullptr) {
+                            const float4 bv = *reinterpret_cast<const float4*>(bias + n0 + c + v4 * 4);
+                            o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+                        }
+                        *reinterpret_cast<float4*>(crow + c + v4 * 4) = o;
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
+                     :: "r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+__global__ void split_tf32_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const float x = w[i];
+        const float h = to_tf32_rna(x);
+        hi[i] = h;
+        lo[i] = to_tf32_rna(x - h);
+    }
+}
+
+typedef CUresult (*PFN_tensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                             const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                             CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                             CUtensorMapFloatOOBfill);
+
+inline PFN_tensorMapEncodeTiled tensor_map_encoder() {
+    static PFN_tensorMapEncodeTiled fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_tensorMapEncodeTiled>(p);
+    }
+    return fn;
+}
+
+// 2-D fp32 row-major [rows, cols] with row pitch ld elements; box = [box_rows, 16 cols], SWIZZLE_64B, OOB -> 0.
+inline int make_map_2d(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    PFN_tensorMapEncodeTiled enc = tensor_map_encoder();
+    if (!enc) return fail(DIGAT_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)kTcBK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(DIGAT_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return DIGAT_OK;
+}
+
+template <int BN, int MH, bool SPLIT>
+inline int launch_tf32x3_cfg(const float* A, int lda, const float* W_hi, const float* W_lo, int ldw, const float* bias,
+                             float* C, int ldc, int M, int N, int K, cudaStream_t st) {
+    using Cfg = TcCfg<BN, MH, SPLIT>;
+    CUtensorMap ma, mh, ml;
+    int rc;
+    if ((rc = make_map_2d(&ma, A, M, K, lda, Cfg::BM)) != DIGAT_OK) return rc;
+    if ((rc = make_map_2d(&mh, W_hi, N, K, ldw, BN)) != DIGAT_OK) return rc;
+    if ((rc = make_map_2d(&ml, W_lo, N, K, ldw, BN)) != DIGAT_OK) return rc;
+    DIGAT_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, MH, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    dim3 grid(N / BN, (M + Cfg::BM - 1) / Cfg::BM);
+    gemm_tf32x3_kernel<BN, MH, SPLIT><<<grid, kTcThreads, Cfg::SMEM, st>>>(ma, mh, ml, bias, C, ldc, M, N, K);
+    return check_launch("digat_linear_tf32x3");
+}
+
+static int g_tc_variant = 0;   // experiment switch (digat_debug_set_gemm_variant)
+
+inline int launch_linear_tf32x3(const float* A, int lda, const float* W_hi, const float* W_lo, int ldw, const float* bias,
+                                float* C, int ldc, int M, int N, int K, cudaStream_t st) {
+    DIGAT_REQUIRE(A && W_hi && W_lo && C, "digat_linear_tf32x3: null pointer");
+    DIGAT_REQUIRE(M >= 0 && N > 0 && K > 0, "digat_linear_tf32x3: bad shape M=%d N=%d K=%d", M, N, K);
+    DIGAT_REQUIRE((K & 3) == 0 && (lda & 3) == 0 && (ldw & 3) == 0 && (ldc & 3) == 0,
+                  "digat_linear_tf32x3: K, lda, ldw, ldc must be multiples of 4");
+    DIGAT_REQUIRE(lda >= K && ldw >= K && ldc >= N, "digat_linear_tf32x3: leading dimension too small");
+    DIGAT_REQUIRE(aligned16(A) && aligned16(W_hi) && aligned16(W_lo) && aligned16(C) && (!bias || aligned16(bias)),
+                  "digat_linear_tf32x3: pointers must be 16-byte aligned");
+    DIGAT_REQUIRE(N % 80 == 0, "digat_linear_tf32x3: N=%d must be a multiple of 80 (tile widths 80/160/240)", N);
+    if (M == 0) return DIGAT_OK;
+    // variant 0 (default): one 128-row half per CTA, separate main / correction accumulators (most accurate);
+    // variant 1: two halves per CTA for M > 16384, single accumulator (half the W traffic per flop, less accurate).
+    const int variant = g_tc_variant;
+    const bool big = M > 16384;
+#define DIGAT_TC_DISPATCH(BN_)                                                                                      \
+    do {                                                                                                            \
+        if (variant == 1 && big) return launch_tf32x3_cfg<BN_, 2, false>(A, lda, W_hi, W_lo, ldw, bias, C, ldc, M, N, K, st); \
+        if (variant == 1) return launch_tf32x3_cfg<BN_, 1, false>(A, lda, W_hi, W_lo, ldw, bias, C, ldc, M, N, K, st);        \
+        return launch_tf32x3_cfg<BN_, 1, true>(A, lda, W_hi, W_lo, ldw, bias, C, ldc, M, N, K, st);                 \
+    } while (0)
+    if (N % 240 == 0) DIGAT_TC_DISPATCH(240);
+    if (N % 160 == 0) DIGAT_TC_DISPATCH(160);
+    DIGAT_TC_DISPATCH(80);
+#undef DIGAT_TC_DISPATCH
+}
+
+}  // namespace digat

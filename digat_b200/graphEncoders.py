@@ -45,19 +45,44 @@ def _boolc(t, name):
 
 
 # ------------------------------------------------------------------------------------------- thin op wrappers
+class PackedWeight:
+    """A projection weight in kernel layout: fp32 [N,K] (nn.Linear layout) plus, when the tcgen05 GEMM can take it
+    (N % 80 == 0), its two TF32 planes hi = rna_tf32(W), lo = rna_tf32(W - hi) (digat_split_tf32)."""
+    __slots__ = ('w', 'hi', 'lo')
+
+    def __init__(self, w):
+        self.w = w.detach().float().contiguous()
+        self.hi = self.lo = None
+        if self.w.shape[0] % 80 == 0 and self.w.shape[1] % 4 == 0:
+            self.hi, self.lo = torch.empty_like(self.w), torch.empty_like(self.w)
+            _lib.call('digat_split_tf32', self.w.data_ptr(), self.hi.data_ptr(), self.lo.data_ptr(), self.w.numel(),
+                      _stream())
+
+
+# rows below which the exact-fp32 CUDA-core GEMM is used (a 128-row tensor-core tile would be mostly padding)
+TENSOR_CORE_MIN_ROWS = 256
+
+
 def linear(A, W, bias=None, relu=False, M=None, K=None, lda=None, out=None):
-    """out[M,N] = A[M,K] W[N,K]^T (+bias).  ``A`` may be a strided row view (pass M, K, lda explicitly)."""
-    N = W.shape[0]
+    """out[M,N] = A[M,K] W[N,K]^T (+bias).  ``A`` may be a strided row view (pass M, K, lda explicitly).
+    W: PackedWeight (tcgen05 3xTF32 GEMM when it has TF32 planes and M is large enough) or a plain fp32 tensor
+    (exact-fp32 CUDA-core GEMM)."""
+    w = W.w if isinstance(W, PackedWeight) else W
+    N = w.shape[0]
     if K is None:
-        K = W.shape[1]
+        K = w.shape[1]
     if M is None:
         M = A.numel() // K
     if lda is None:
         lda = K
     if out is None:
         out = torch.empty((M, N), device=A.device, dtype=torch.float32)
-    _lib.call('digat_linear_f32', A.data_ptr(), lda, W.data_ptr(), W.stride(0), _ptr(bias), out.data_ptr(),
-              out.stride(0), M, N, K, 1 if relu else 0, _stream())
+    if isinstance(W, PackedWeight) and W.hi is not None and M >= TENSOR_CORE_MIN_ROWS and not relu:
+        _lib.call('digat_linear_tf32x3', A.data_ptr(), lda, W.hi.data_ptr(), W.lo.data_ptr(), w.stride(0), _ptr(bias),
+                  out.data_ptr(), out.stride(0), M, N, K, _stream())
+    else:
+        _lib.call('digat_linear_f32', A.data_ptr(), lda, w.data_ptr(), w.stride(0), _ptr(bias), out.data_ptr(),
+                  out.stride(0), M, N, K, 1 if relu else 0, _stream())
     return out
 
 
@@ -188,21 +213,21 @@ class DIGAT(GraphEncoder):
                     f2 = getattr(self, g + '_graph_attention_ffn2')[i]
                     f3 = getattr(self, g + '_graph_attention_ffn3')[i]
                     av = getattr(self, g + '_graph_attention_a')[i]
-                    w[g, i, 'Wcat'] = torch.cat([W.weight, f1.weight, f2.weight], 0).float().contiguous()
+                    w[g, i, 'Wcat'] = PackedWeight(torch.cat([W.weight, f1.weight, f2.weight], 0).float().contiguous())
                     w[g, i, 'bcat'] = torch.cat([W.bias, torch.zeros(2 * D, device=dev)], 0).float().contiguous()
-                    w[g, i, 'W3'] = f3.weight.detach().float().contiguous()
+                    w[g, i, 'W3'] = PackedWeight(f3.weight.detach().float().contiguous())
                     w[g, i, 'b3'] = f3.bias.detach().float().contiguous()
                     w[g, i, 'a'] = av.weight.detach().float().reshape(D).contiguous()
-            w['cand_Q'] = self.candidate_attention.Q.weight.detach().float().contiguous()
+            w['cand_Q'] = PackedWeight(self.candidate_attention.Q.weight.detach().float().contiguous())
             w['cand_Qb'] = self.candidate_attention.Q.bias.detach().float().contiguous()
-            w['cand_Kt'] = self.candidate_attention.K.weight.detach().float().t().contiguous()
-            w['gate_W'] = self.news_graph_W.weight.detach().float().contiguous()
+            w['cand_Kt'] = PackedWeight(self.candidate_attention.K.weight.detach().float().t().contiguous())
+            w['gate_W'] = PackedWeight(self.news_graph_W.weight.detach().float().contiguous())
             w['gate_b'] = self.news_graph_W.bias.detach().float().contiguous()
-            w['uq_W'] = torch.cat([self.user_news_Q.weight, self.userAttention.Q.weight], 0).float().contiguous()
+            w['uq_W'] = PackedWeight(torch.cat([self.user_news_Q.weight, self.userAttention.Q.weight], 0).float().contiguous())
             w['uq_b'] = torch.cat([self.user_news_Q.bias, self.userAttention.Q.bias], 0).float().contiguous()
-            w['unK_t'] = self.user_news_K.weight.detach().float().t().contiguous()
-            w['uaK_t'] = self.userAttention.K.weight.detach().float().t().contiguous()
-            w['fa_W'] = self.featureAffine.weight.detach().float().contiguous()
+            w['unK_t'] = PackedWeight(self.user_news_K.weight.detach().float().t().contiguous())
+            w['uaK_t'] = PackedWeight(self.userAttention.K.weight.detach().float().t().contiguous())
+            w['fa_W'] = PackedWeight(self.featureAffine.weight.detach().float().contiguous())
             w['fa_b'] = self.featureAffine.bias.detach().float().contiguous()
             w['topic'] = self.topic_node_embedding.detach().float().contiguous()
         self._packed, self._packed_key = w, key

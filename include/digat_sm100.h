@@ -45,6 +45,20 @@ int         digat_device_check(int* sm_count);
 int digat_linear_f32(const float* A, int lda, const float* W, int ldw, const float* bias,
                      float* C, int ldc, int M, int N, int K, int relu, void* stream);
 
+/* Splits W into the two TF32 planes used by digat_linear_tf32x3: hi = rna_tf32(W), lo = rna_tf32(W - hi). */
+int digat_split_tf32(const float* W, float* W_hi, float* W_lo, int64_t count, void* stream);
+
+/* tcgen05 tensor-core GEMM, operands fed by TMA, fp32 accumulators in TMEM, fp32-level accuracy by 3xTF32 error
+ * compensation: C = A_hi*W_hi + A_lo*W_hi + A_hi*W_lo (+ bias).  A is plain fp32 and is split into its TF32 planes
+ * on the fly inside the kernel; W_hi / W_lo come from digat_split_tf32 (same ldw).
+ * Requires K % 4 == 0, N % 80 == 0, lda/ldw/ldc % 4 == 0.  Replaces the three node projections h, K1, K2 of one
+ * layer as ONE GEMM against the stacked [3D, D] weight (graphEncoders.py:146-148 / 166-168). */
+int digat_linear_tf32x3(const float* A, int lda, const float* W_hi, const float* W_lo, int ldw,
+                        const float* bias, float* C, int ldc, int M, int N, int K, void* stream);
+
+/* Tuning/experiment switch for digat_linear_tf32x3 tile variants (0 = default).  Not part of the reference path. */
+int digat_debug_set_gemm_variant(int variant);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Fused Eq. (8) graph-attention layer (replaces graphEncoders.py:150-153 / 170-173).
  *   P    [B*n, ldp]  node projections of this layer: columns [0,D) = h (bias included), [D,2D) = K1, [2D,3D) = K2

@@ -1,0 +1,71 @@
+"""GPU tests of the tcgen05 3xTF32 projection GEMM against fp64 (and against the exact-fp32 CUDA-core GEMM)."""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _split(W):
+    from digat_b200 import _lib
+    hi, lo = torch.empty_like(W), torch.empty_like(W)
+    _lib.call('digat_split_tf32', W.data_ptr(), hi.data_ptr(), lo.data_ptr(), W.numel(),
+              torch.cuda.current_stream().cuda_stream)
+    return hi, lo
+
+
+def _tf32x3(A, W, bias, lda=None):
+    from digat_b200 import _lib
+    M, K = A.shape
+    N = W.shape[0]
+    hi, lo = _split(W)
+    C = torch.full((M, N), float('nan'), device=A.device)
+    _lib.call('digat_linear_tf32x3', A.data_ptr(), lda or A.stride(0), hi.data_ptr(), lo.data_ptr(), W.stride(0),
+              0 if bias is None else bias.data_ptr(), C.data_ptr(), N, M, N, K, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return C
+
+
+def test_split_planes_are_exact_tf32():
+    g = torch.Generator().manual_seed(0)
+    W = (torch.randn(1200, 400, generator=g) * 0.1).cuda()
+    hi, lo = _split(W)
+    torch.cuda.synchronize()
+    assert int((hi.view(torch.int32) & 0x1FFF).abs().max()) == 0 and int((lo.view(torch.int32) & 0x1FFF).abs().max()) == 0
+    # hi + lo reproduces W to 2^-22 relative
+    assert float(((hi.double() + lo.double() - W.double()).abs() / W.double().abs().clamp_min(1e-30)).max()) < 2 ** -21
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 240, 16), (128, 80, 400), (256, 1200, 400), (1000, 400, 400),
+                                   (4096, 400, 800), (20000, 1200, 400), (69632, 1200, 400), (16385, 800, 400)])
+def test_tf32x3_matches_fp64(M, N, K):
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g)
+    W = torch.randn(N, K, generator=g) * 0.05
+    bias = torch.randn(N, generator=g)
+    C = _tf32x3(A.cuda(), W.cuda(), bias.cuda()).cpu()
+    assert torch.isfinite(C).all()
+    # row-sampled fp64 reference (full fp64 GEMM of the largest case is slow on the host)
+    rows = torch.randperm(M, generator=g)[:min(M, 512)]
+    rows = torch.cat([rows, torch.tensor([0, M - 1])])
+    ref = A[rows].double() @ W.double().t() + bias.double()
+    e = rel_err(C[rows].numpy(), ref.numpy())
+    ref32 = (A[rows] @ W.t() + bias)
+    e32 = rel_err(ref32.numpy(), ref.numpy())
+    assert e < 4e-6, "tf32x3 rel err %.3e (torch fp32 on CPU: %.3e)" % (e, e32)
+
+
+def test_tf32x3_strided_A_and_no_bias():
+    g = torch.Generator().manual_seed(4)
+    X = torch.randn(300, 10, 400, generator=g).cuda()       # A = X[:, 0, :] with lda = 10*400
+    W = (torch.randn(400, 400, generator=g) * 0.05).cuda()
+    from digat_b200 import _lib
+    hi, lo = _split(W)
+    C = torch.empty(300, 400, device='cuda')
+    _lib.call('digat_linear_tf32x3', X.data_ptr(), 4000, hi.data_ptr(), lo.data_ptr(), 400, 0, C.data_ptr(), 400,
+              300, 400, 400, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    ref = X[:, 0, :].double().cpu() @ W.double().cpu().t()
+    assert rel_err(C.cpu().numpy(), ref.numpy()) < 2e-6
