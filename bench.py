@@ -280,7 +280,7 @@ def summarize_kernels(records, hbm_peak, tensor_peak):
     agg = {}
     for name, a, ms in records:
         if name == 'digat_graph_layer_fwd':
-            B, n, Dd = a[8], a[9], a[10]
+            B, n, Dd = a[6], a[7], a[8]
             key = '%s[n=%d]' % (name, n)
             work, bound = B * (5 * n * Dd * 4 + n * n + Dd * 4), 'hbm'
         elif name == 'digat_linear_f32' or name == 'digat_linear_tf32x3':

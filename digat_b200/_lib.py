@@ -12,12 +12,14 @@ c_void_p, c_int, c_int64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
 SIGNATURES = {
     'digat_abi_version': [],
     'digat_device_check': [c_void_p],
-    'digat_linear_f32': [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    'digat_linear_f32': [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                         c_void_p, c_int, c_int, c_int, c_void_p],
     'digat_split_tf32': [c_void_p, c_void_p, c_void_p, c_int64, c_void_p],
-    'digat_linear_tf32x3': [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    'digat_linear_tf32x3': [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                            c_void_p, c_int, c_int, c_int, c_void_p],
     'digat_debug_set_gemm_variant': [c_int],
-    'digat_graph_layer_fwd': [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                              c_int, c_int, c_int, c_void_p],
+    'digat_graph_layer_fwd': [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                              c_void_p, ctypes.c_float, c_void_p, c_void_p, c_void_p, c_void_p],
     'digat_attention_pool_fwd': [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                  c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     'digat_news_gate_fwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
@@ -27,6 +29,16 @@ SIGNATURES = {
     'digat_gather_sag_i32': [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p],
     'digat_build_user_nodes': [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                c_void_p, c_void_p],
+    'digat_graph_layer_bwd': [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_float, c_void_p,
+                              c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p],
+    'digat_attention_pool_bwd': [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                 c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    'digat_topic_segment_bwd': [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_int, c_int, c_int, c_int, c_int, c_void_p],
+    'digat_reduce_workspace_floats': [c_int, c_int, c_int, c_void_p],
+    'digat_linear_wgrad': [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    'digat_colsum': [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p],
+    'digat_groupsum': [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     'digat_logits': [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
     'digat_add_inplace': [c_void_p, c_void_p, c_int64, c_void_p],
 }
@@ -71,7 +83,8 @@ def require_device(device_index: int):
     _device_ok[device_index] = True
 
 
-_NON_KERNEL = ('digat_abi_version', 'digat_device_check', 'digat_debug_set_gemm_variant')
+_NON_KERNEL = ('digat_abi_version', 'digat_device_check', 'digat_debug_set_gemm_variant',
+               'digat_reduce_workspace_floats')
 _launches = 0
 _profile = None      # list of (name, args, start_event, end_event) while bench.py's per-kernel pass is running
 
@@ -110,6 +123,7 @@ def call(name, *args):
         _profile.append((name, args, s, e))
     else:
         rc = getattr(load(), name)(*args)
-    _launches += 1
+    if name not in _NON_KERNEL:
+        _launches += 1
     if rc != 0:
         raise RuntimeError('%s failed (%d): %s' % (name, rc, last_error()))

@@ -1,0 +1,221 @@
+"""Training path of the sm_100a DIGAT encoder: torch.autograd.Functions whose forward AND backward are the kernels of
+libdigat_sm100.so, plus ``encode_with_grad`` -- reference DIGAT.forward (graphEncoders.py:177-187) including its
+dropout sites.  PyTorch only provides the autograd graph, the dropout random numbers (elementwise masks) and
+trivial glue (cat / slicing / the [B,D] gate arithmetic); every contraction, the fused Eq. (8) layer and the
+segment / pooling ops run in the hand-written kernels, forward and backward.
+
+Works under DistributedDataParallel (reference trainer.py:19): parameters receive ordinary ``.grad`` tensors, so DDP's
+bucketed NCCL all-reduce overlaps with this backward exactly as it does with PyTorch's own.
+"""
+import torch
+import torch.nn.functional as F
+from torch.autograd import Function
+
+from . import _lib
+from .graphEncoders import PackedWeight, _ptr, _stream, attention_pool_fwd, graph_layer_fwd, linear
+
+
+def _workspace(M, N, K, device):
+    n = torch.zeros(1, dtype=torch.int64)
+    _lib.call('digat_reduce_workspace_floats', M, N, K, n.data_ptr())
+    return torch.empty(int(n.item()), device=device, dtype=torch.float32)
+
+
+def colsum(x2d):
+    M, N = x2d.shape
+    out = torch.empty(N, device=x2d.device, dtype=torch.float32)
+    if M == 0:
+        return out.zero_()
+    ws = _workspace(M, N, 1, x2d.device)
+    _lib.call('digat_colsum', x2d.data_ptr(), x2d.stride(0), out.data_ptr(), ws.data_ptr(), M, N, _stream())
+    return out
+
+
+class LinearFn(Function):
+    """out = A W^T (+bias) (+row-group bias); dA by the tcgen05 GEMM against W^T, dW by the exact-fp32 wgrad GEMM."""
+
+    @staticmethod
+    def forward(ctx, A, W, bias, group_bias, group_rows, group_col0):
+        A = A.contiguous()
+        W = W.contiguous()
+        ctx.save_for_backward(A, W)
+        ctx.has_bias = bias is not None
+        ctx.group = None if group_bias is None else (group_rows, group_col0, group_bias.shape[1])
+        return linear(A, PackedWeight(W), None if bias is None else bias.contiguous(),
+                      group_bias=None if group_bias is None else group_bias.contiguous(), group_rows=group_rows,
+                      group_col0=group_col0)
+
+    @staticmethod
+    def backward(ctx, dC):
+        A, W = ctx.saved_tensors
+        dC = dC.contiguous()
+        M, K = A.shape
+        N = W.shape[0]
+        dA = dW = db = dg = None
+        if ctx.needs_input_grad[0]:
+            dA = linear(dC, PackedWeight(W.t().contiguous()))
+        if ctx.needs_input_grad[1]:
+            dW = torch.empty_like(W)
+            ws = _workspace(M, N, K, A.device)
+            _lib.call('digat_linear_wgrad', dC.data_ptr(), dC.stride(0), A.data_ptr(), A.stride(0), dW.data_ptr(),
+                      ws.data_ptr(), M, N, K, _stream())
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = colsum(dC)
+        if ctx.group is not None and ctx.needs_input_grad[3]:
+            rows, col0, cols = ctx.group
+            dg = torch.empty((M // rows, cols), device=A.device, dtype=torch.float32)
+            _lib.call('digat_groupsum', dC.data_ptr(), dC.stride(0), dg.data_ptr(), M // rows, rows, col0, cols, _stream())
+        return dA, dW, db, dg, None, None
+
+
+def lin(A, W, bias=None, group_bias=None, group_rows=1, group_col0=0):
+    return LinearFn.apply(A, W, bias, group_bias, group_rows, group_col0)
+
+
+class GraphLayerFn(Function):
+    """Fused Eq. (8) layer; backward recomputes the [n,n,D] relu mask instead of storing it (digat_graph_layer_bwd)."""
+
+    @staticmethod
+    def forward(ctx, P, a, adj, X, drop_keep, drop_scale):
+        B, n, D = X.shape
+        P, a, X = P.contiguous(), a.contiguous(), X.contiguous()
+        score = torch.empty((B, n, n), device=X.device, dtype=torch.float32)
+        alpha = torch.empty((B, n, n), device=X.device, dtype=torch.float32)
+        rmask = torch.empty((B, n, D), device=X.device, dtype=torch.uint8)
+        Y = graph_layer_fwd(P, a, adj, X, drop_keep=drop_keep, drop_scale=drop_scale, score_out=score,
+                            alpha_out=alpha, relu_mask_out=rmask)
+        ctx.save_for_backward(P, a, adj, score, alpha, rmask)
+        ctx.drop = (drop_keep, float(drop_scale))
+        return Y
+
+    @staticmethod
+    def backward(ctx, dY):
+        P, a, adj, score, alpha, rmask = ctx.saved_tensors
+        keep, scale = ctx.drop
+        B, n, D = rmask.shape
+        dY = dY.contiguous()
+        G = dY * rmask                                    # dZ = dY * 1[Z > 0]
+        dP = torch.empty_like(P)
+        da_part = torch.empty((B, D), device=P.device, dtype=torch.float32)
+        _lib.call('digat_graph_layer_bwd', P.data_ptr(), P.stride(0), a.data_ptr(), adj.data_ptr(), score.data_ptr(),
+                  alpha.data_ptr(), _ptr(keep), scale, G.data_ptr(), dP.data_ptr(), dP.stride(0), da_part.data_ptr(),
+                  B, n, D, _stream())
+        return dP, colsum(da_part), None, dY, None, None
+
+
+class AttentionPoolFn(Function):
+    @staticmethod
+    def forward(ctx, Fm, v, mask, resid):
+        Fm, v = Fm.contiguous(), v.contiguous()
+        resid = None if resid is None else resid.contiguous()
+        B, m, D = Fm.shape
+        alpha = torch.empty((B, m), device=Fm.device, dtype=torch.float32)
+        out = attention_pool_fwd(Fm, v, mask, resid=resid, alpha_out=alpha)
+        ctx.save_for_backward(Fm, v, mask, alpha, *(() if resid is None else (resid,)))
+        ctx.has_resid = resid is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        Fm, v, mask, alpha = ctx.saved_tensors[:4]
+        resid = ctx.saved_tensors[4] if ctx.has_resid else None
+        B, m, D = Fm.shape
+        dout = dout.contiguous()
+        dF = torch.empty_like(Fm)
+        dres = torch.empty_like(Fm) if resid is not None else None
+        dv = torch.empty_like(v)
+        _lib.call('digat_attention_pool_bwd', Fm.data_ptr(), m * D, D, _ptr(resid), v.data_ptr(), mask.data_ptr(),
+                  alpha.data_ptr(), dout.data_ptr(), dout.stride(0), dF.data_ptr(), _ptr(dres), dv.data_ptr(), B, m, D,
+                  _stream())
+        return dF, dv, None, dres
+
+
+class TopicSegmentFn(Function):
+    @staticmethod
+    def forward(ctx, Xu, v, cidx, H, S, err_flag):
+        Xu, v = Xu.contiguous(), v.contiguous()
+        B, nu, D = Xu.shape
+        T = torch.empty((B, S, D), device=Xu.device, dtype=torch.float32)
+        alpha = torch.empty((B, H), device=Xu.device, dtype=torch.float32)
+        _lib.call('digat_topic_segment_fwd', Xu.data_ptr(), nu * D, v.data_ptr(), cidx.data_ptr(), T.data_ptr(),
+                  alpha.data_ptr(), err_flag.data_ptr(), B, H, S, D, _stream())
+        ctx.save_for_backward(Xu, v, cidx, alpha)
+        ctx.dims = (H, S)
+        return T
+
+    @staticmethod
+    def backward(ctx, dT):
+        Xu, v, cidx, alpha = ctx.saved_tensors
+        H, S = ctx.dims
+        B, nu, D = Xu.shape
+        dT = dT.contiguous()
+        dXu = torch.empty_like(Xu)
+        dv = torch.empty_like(v)
+        _lib.call('digat_topic_segment_bwd', Xu.data_ptr(), nu * D, v.data_ptr(), cidx.data_ptr(), alpha.data_ptr(),
+                  dT.data_ptr(), dXu.data_ptr(), dv.data_ptr(), B, H, S, nu, D, _stream())
+        return dXu, dv, None, None, None, None
+
+
+def encode_with_grad(enc, Xn, An, Mn, Xh, Au, Mc, ci):
+    """Reference DIGAT.forward (graphEncoders.py:177-187) with autograd; dropout active iff enc.training."""
+    D, L, H, S = enc.news_embedding_dim, enc.graph_depth, enc.max_history_num, enc.category_num
+    p = enc.dropout_rate if enc.training else 0.0
+    B = Xn.shape[0]
+    dev = Xn.device
+    _lib.require_device(dev.index if dev.index is not None else torch.cuda.current_device())
+    err = enc._err_flag(dev)
+
+    def drop(x, rate):
+        return F.dropout(x, rate, True) if rate > 0 else x
+
+    # differentiable packing of the parameters (same layout as DIGAT._weights)
+    cand, ua = enc.candidate_attention, enc.userAttention
+    cand_Kt, ua_Kt, un_Kt = cand.K.weight.t(), ua.K.weight.t(), enc.user_news_K.weight.t()
+    uq_W = torch.cat([enc.user_news_Q.weight, ua.Q.weight], 0)
+    uq_b = torch.cat([enc.user_news_Q.bias, ua.Q.bias], 0)
+    zeros2D = torch.zeros(2 * D, device=dev)
+
+    def news_ctx(X):
+        l = X[:, 0, :]
+        q = lin(l, cand.Q.weight, cand.Q.bias)
+        v = lin(q, cand_Kt)
+        g = AttentionPoolFn.apply(X, v, Mn, None)
+        z = drop(lin(torch.cat([l, g], 1), enc.news_graph_W.weight, enc.news_graph_W.bias), p / 2)
+        gate = torch.sigmoid(z)
+        return gate * l + (1 - gate) * g
+
+    def user_ctx(Xu, c_n):
+        qq = lin(c_n, uq_W, uq_b)
+        v1 = lin(qq[:, :D], un_Kt)
+        v2 = lin(qq[:, D:], ua_Kt)
+        T = TopicSegmentFn.apply(Xu, v1, ci, H, S, err)
+        Fa = lin(T.reshape(B * S, D), enc.featureAffine.weight, enc.featureAffine.bias).view(B, S, D)
+        if p > 0:
+            return AttentionPoolFn.apply(drop(torch.relu(Fa) + T, p), v2, Mc, None)
+        return AttentionPoolFn.apply(Fa, v2, Mc, T)
+
+    def layer(g, i, X, adj, ctx_other):
+        n = X.shape[1]
+        W = getattr(enc, g + '_graph_attention_W')[i]
+        f1 = getattr(enc, g + '_graph_attention_ffn1')[i]
+        f2 = getattr(enc, g + '_graph_attention_ffn2')[i]
+        f3 = getattr(enc, g + '_graph_attention_ffn3')[i]
+        av = getattr(enc, g + '_graph_attention_a')[i]
+        Xd = drop(X, p / 2)                                        # the residual uses the DROPPED input (:145,153)
+        k3 = lin(ctx_other, f3.weight, f3.bias)
+        P = lin(Xd.reshape(B * n, D), torch.cat([W.weight, f1.weight, f2.weight], 0), torch.cat([W.bias, zeros2D], 0),
+                group_bias=k3, group_rows=n, group_col0=D)
+        keep = (torch.rand((B, n, n), device=dev) >= p) if p > 0 else None
+        return GraphLayerFn.apply(P, av.weight.reshape(D), adj, Xd, keep, 1.0 / (1.0 - p) if p > 0 else 1.0)
+
+    topic = drop(enc.topic_node_embedding.unsqueeze(0).expand(B, -1, -1), p / 2)
+    Xu = torch.cat([Xh, topic], 1)
+    c_n = news_ctx(Xn)
+    c_u = user_ctx(Xu, c_n)
+    for i in range(L):
+        Xn_new = layer('news', i, Xn, An, c_u)
+        Xu = layer('user', i, Xu, Au, c_n)
+        Xn = Xn_new
+        c_n = c_n + news_ctx(Xn)
+        c_u = c_u + user_ctx(Xu, c_n)
+    return c_n, c_u

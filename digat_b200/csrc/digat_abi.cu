@@ -6,6 +6,9 @@
 #include "pair_attention.cuh"
 #include "context.cuh"
 #include "gather.cuh"
+#include "pair_attention_bwd.cuh"
+#include "context_bwd.cuh"
+#include "gemm_wgrad.cuh"
 
 using namespace digat;
 
@@ -32,8 +35,10 @@ int digat_device_check(int* sm_count) {
 }
 
 int digat_linear_f32(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc,
-                     int M, int N, int K, int relu, void* stream) {
-    return launch_linear_f32(A, lda, W, ldw, bias, C, ldc, M, N, K, relu, as_stream(stream));
+                     int M, int N, int K, int relu, const float* group_bias, int group_rows, int group_col0,
+                     int group_cols, void* stream) {
+    return launch_linear_f32(A, lda, W, ldw, bias, C, ldc, M, N, K, relu,
+                             GroupBias{group_bias, group_rows, group_col0, group_cols}, as_stream(stream));
 }
 
 int digat_split_tf32(const float* W, float* W_hi, float* W_lo, int64_t count, void* stream) {
@@ -44,8 +49,10 @@ int digat_split_tf32(const float* W, float* W_hi, float* W_lo, int64_t count, vo
 }
 
 int digat_linear_tf32x3(const float* A, int lda, const float* W_hi, const float* W_lo, int ldw, const float* bias,
-                        float* C, int ldc, int M, int N, int K, void* stream) {
-    return launch_linear_tf32x3(A, lda, W_hi, W_lo, ldw, bias, C, ldc, M, N, K, as_stream(stream));
+                        float* C, int ldc, int M, int N, int K, const float* group_bias, int group_rows,
+                        int group_col0, int group_cols, void* stream) {
+    return launch_linear_tf32x3(A, lda, W_hi, W_lo, ldw, bias, C, ldc, M, N, K,
+                                GroupBias{group_bias, group_rows, group_col0, group_cols}, as_stream(stream));
 }
 
 int digat_debug_set_gemm_variant(int variant) {
@@ -53,9 +60,11 @@ int digat_debug_set_gemm_variant(int variant) {
     return DIGAT_OK;
 }
 
-int digat_graph_layer_fwd(const float* P, int ldp, const float* k3, const float* a, const uint8_t* adj,
-                          const float* X, float* Y, float* alpha_out, int B, int n, int D, void* stream) {
-    return launch_graph_layer_fwd(P, ldp, k3, a, adj, X, Y, alpha_out, B, n, D, as_stream(stream));
+int digat_graph_layer_fwd(const float* P, int ldp, const float* a, const uint8_t* adj, const float* X, float* Y,
+                          int B, int n, int D, const uint8_t* drop_keep, float drop_scale, float* score_out,
+                          float* alpha_out, uint8_t* relu_mask_out, void* stream) {
+    return launch_graph_layer_fwd(P, ldp, a, adj, X, Y, B, n, D, drop_keep, drop_scale, score_out, alpha_out,
+                                  relu_mask_out, as_stream(stream));
 }
 
 int digat_attention_pool_fwd(const float* F, int64_t strideF, int ldf, const float* resid_F, const float* v,
@@ -134,6 +143,46 @@ int digat_add_inplace(const float* x, float* y, int64_t count, void* stream) {
     const int64_t threads = (count + 3) / 4;
     add_inplace_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, as_stream(stream)>>>(x, y, count);
     return check_launch("digat_add_inplace");
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+int digat_graph_layer_bwd(const float* P, int ldp, const float* a, const uint8_t* adj, const float* score,
+                          const float* alpha, const uint8_t* drop_keep, float drop_scale, const float* G, float* dP,
+                          int lddp, float* da_partial, int B, int n, int D, void* stream) {
+    return launch_graph_layer_bwd(P, ldp, a, adj, score, alpha, drop_keep, drop_scale, G, dP, lddp, da_partial, B, n, D,
+                                  as_stream(stream));
+}
+
+int digat_attention_pool_bwd(const float* F, int64_t strideF, int ldf, const float* resid_F, const float* v,
+                             const uint8_t* mask, const float* alpha, const float* dout, int ldg, float* dF,
+                             float* dresid, float* dv, int B, int m, int D, void* stream) {
+    return launch_attention_pool_bwd(F, strideF, ldf, resid_F, v, mask, alpha, dout, ldg, dF, dresid, dv, B, m, D,
+                                     as_stream(stream));
+}
+
+int digat_topic_segment_bwd(const float* Xu, int64_t strideX, const float* v, const int64_t* cidx, const float* alpha,
+                            const float* dT, float* dXu, float* dv, int B, int H, int n_seg, int n_u, int D,
+                            void* stream) {
+    return launch_topic_segment_bwd(Xu, strideX, v, cidx, alpha, dT, dXu, dv, B, H, n_seg, n_u, D, as_stream(stream));
+}
+
+int digat_reduce_workspace_floats(int M, int N, int K, int64_t* floats) {
+    DIGAT_REQUIRE(floats != nullptr && M >= 0 && N > 0 && K > 0, "digat_reduce_workspace_floats: bad argument");
+    *floats = wgrad_workspace_floats(M, N, K);
+    return DIGAT_OK;
+}
+
+int digat_linear_wgrad(const float* dC, int lddc, const float* A, int lda, float* dW, float* workspace, int M, int N,
+                       int K, void* stream) {
+    return launch_linear_wgrad(dC, lddc, A, lda, dW, workspace, M, N, K, as_stream(stream));
+}
+
+int digat_colsum(const float* in, int ld, float* out, float* workspace, int M, int N, void* stream) {
+    return launch_colsum(in, ld, out, workspace, M, N, as_stream(stream));
+}
+
+int digat_groupsum(const float* in, int ld, float* out, int groups, int rows, int col0, int cols, void* stream) {
+    return launch_groupsum(in, ld, out, groups, rows, col0, cols, as_stream(stream));
 }
 
 }  // extern "C"

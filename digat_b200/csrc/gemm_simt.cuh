@@ -6,10 +6,19 @@
 
 namespace digat {
 
+// Row-group bias: C[m, col0 + c] += ptr[(m / rows) * cols + c] for c in [0, cols).  Used to fold the per-graph
+// context projection k3 into the K1 block of the node projections: U = fl(k3 + K1), the first broadcast add of
+// Eq. (8) (reference graphEncoders.py:150), with the reference's rounding.
+struct GroupBias {
+    const float* ptr;
+    int rows, col0, cols;
+};
+
 template <int BM, int BN, int BK, int TM, int TN>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 gemm_tn_f32_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
-                   const float* __restrict__ bias, float* __restrict__ C, int ldc, int M, int N, int K, int relu) {
+                   const float* __restrict__ bias, float* __restrict__ C, int ldc, int M, int N, int K, int relu,
+                   GroupBias gb) {
     constexpr int NT = (BM / TM) * (BN / TN);
     constexpr int KQ = BK / 4;               // float4 per tile row
     static_assert((BM * BK / 4) % NT == 0 && (BN * BK / 4) % NT == 0, "tile/loader mismatch");
@@ -111,6 +120,8 @@ gemm_tn_f32_kernel(const float* __restrict__ A, int lda, const float* __restrict
                 for (int jj = 0; jj < 4; ++jj) {
                     float v = acc[gi * 4 + ii][gj * 4 + jj];
                     if (bias != nullptr && gn + jj < N) v += bias[gn + jj];
+                    if (gb.ptr != nullptr && gn + jj >= gb.col0 && gn + jj < gb.col0 + gb.cols)
+                        v += gb.ptr[(size_t)(gm / gb.rows) * gb.cols + (gn + jj - gb.col0)];
                     if (relu) v = fmaxf(v, 0.f);
                     o[jj] = v;
                 }
@@ -127,22 +138,24 @@ gemm_tn_f32_kernel(const float* __restrict__ A, int lda, const float* __restrict
 }
 
 inline int launch_linear_f32(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc,
-                             int M, int N, int K, int relu, cudaStream_t st) {
+                             int M, int N, int K, int relu, GroupBias gb, cudaStream_t st) {
     DIGAT_REQUIRE(A && W && C, "digat_linear_f32: null pointer");
     DIGAT_REQUIRE(M >= 0 && N > 0 && K > 0, "digat_linear_f32: bad shape M=%d N=%d K=%d", M, N, K);
     DIGAT_REQUIRE((K & 3) == 0 && (lda & 3) == 0 && (ldw & 3) == 0, "digat_linear_f32: K, lda, ldw must be multiples of 4");
     DIGAT_REQUIRE(aligned16(A) && aligned16(W) && aligned16(C), "digat_linear_f32: pointers must be 16-byte aligned");
     DIGAT_REQUIRE(lda >= K && ldw >= K && ldc >= N, "digat_linear_f32: leading dimension too small");
+    DIGAT_REQUIRE(gb.ptr == nullptr || (gb.rows > 0 && gb.col0 >= 0 && gb.cols > 0 && gb.col0 + gb.cols <= N),
+                  "digat_linear_f32: bad row-group bias");
     if (M == 0) return DIGAT_OK;
     if (M <= 2048) {
         // skinny: smaller tiles so that the grid covers the 148 SMs
         constexpr int BM = 64, BN = 64;
         dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
-        gemm_tn_f32_kernel<BM, BN, 16, 4, 4><<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, C, ldc, M, N, K, relu);
+        gemm_tn_f32_kernel<BM, BN, 16, 4, 4><<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, C, ldc, M, N, K, relu, gb);
     } else {
         constexpr int BM = 128, BN = 128;
         dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
-        gemm_tn_f32_kernel<BM, BN, 8, 8, 8><<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, C, ldc, M, N, K, relu);
+        gemm_tn_f32_kernel<BM, BN, 8, 8, 8><<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, C, ldc, M, N, K, relu, gb);
     }
     return check_launch("digat_linear_f32");
 }

@@ -16,49 +16,15 @@
 //               to the stage's "empty" barrier; owns the TMEM allocation (MH*BN fp32 columns).
 // Pipeline: full[s] (TMA bytes landed) -> ready[s] (A split done) -> MMA -> empty[s] (tcgen05.commit) -> TMA.
 #pragma once
-#include <cuda.h>
 #include "common.cuh"
+#include "tma.cuh"
+#include "gemm_simt.cuh"   // GroupBias
 
 namespace digat {
 
 constexpr int kTcBK = 16;                       // fp32 elements per k-block = 64 bytes = SWIZZLE_64B span
 constexpr int kTcThreads = 192;
 constexpr int kTcTransformThreads = 128;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// Bounded spin: a barrier that never completes traps (CUDA error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    uint32_t done = 0;
-    for (uint32_t spin = 0; ; ++spin) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-        if (done) return;
-        if (spin > (1u << 24)) {
-            printf("digat gemm_tcgen05: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
-            __trap();
-        }
-    }
-}
-
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
 
 // K-major operand tile, SWIZZLE_64B: rows of 64 bytes, 8-row groups of 512 bytes (SBO), version 1 (sm_100).
 __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
@@ -117,10 +83,10 @@ template <int BN, int MH, bool SPLIT>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_whi,
                    const __grid_constant__ CUtensorMap map_wlo, const float* __restrict__ bias,
-                   float* __restrict__ C, int ldc, int M, int N, int K) {
+                   float* __restrict__ C, int ldc, int M, int N, int K, GroupBias gb) {
     using Cfg = TcCfg<BN, MH, SPLIT>;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) uint8_t smem_raw[];   // SWIZZLE_64B operand tiles: keep 1024-byte alignment
+    uint8_t* smem = smem_raw;                               // stays a __shared__ pointer (LDS/STS in the transform warps)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES);
     uint64_t* full = bars;                       // [STAGES] TMA bytes landed
     uint64_t* ready = bars + Cfg::STAGES;        // [STAGES] A split into hi/lo
@@ -233,6 +199,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         for (int h = 0; h < MH; ++h) {
             const int m = m0 + h * 128 + q * 32 + lane;
             float* crow = C + (size_t)m * ldc + n0;
+            const float* grow = gb.ptr != nullptr ? gb.ptr + (size_t)(m / gb.rows) * gb.cols - gb.col0 + n0 : nullptr;
 #pragma unroll 1
             for (int c = 0; c < BN; c += 16) {
                 uint32_t r[16];
@@ -265,6 +232,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                             const float4 bv = *reinterpret_cast<const float4*>(bias + n0 + c + v4 * 4);
                             o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
                         }
+                        const int col = n0 + c + v4 * 4;      // col0 and cols are multiples of 4: a quad is in or out
+                        if (grow != nullptr && col >= gb.col0 && col < gb.col0 + gb.cols) {
+                            const float4 gv = *reinterpret_cast<const float4*>(grow + c + v4 * 4);
+                            o.x += gv.x; o.y += gv.y; o.z += gv.z; o.w += gv.w;
+                        }
                         *reinterpret_cast<float4*>(crow + c + v4 * 4) = o;
                     }
                 }
@@ -290,58 +262,29 @@ __global__ void split_tf32_kernel(const float* __restrict__ w, float* __restrict
     }
 }
 
-typedef CUresult (*PFN_tensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                             const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                             CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                             CUtensorMapFloatOOBfill);
-
-inline PFN_tensorMapEncodeTiled tensor_map_encoder() {
-    static PFN_tensorMapEncodeTiled fn = nullptr;
-    if (fn == nullptr) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<PFN_tensorMapEncodeTiled>(p);
-    }
-    return fn;
-}
-
-// 2-D fp32 row-major [rows, cols] with row pitch ld elements; box = [box_rows, 16 cols], SWIZZLE_64B, OOB -> 0.
-inline int make_map_2d(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
-    PFN_tensorMapEncodeTiled enc = tensor_map_encoder();
-    if (!enc) return fail(DIGAT_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)kTcBK, (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(DIGAT_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-    return DIGAT_OK;
-}
-
 template <int BN, int MH, bool SPLIT>
 inline int launch_tf32x3_cfg(const float* A, int lda, const float* W_hi, const float* W_lo, int ldw, const float* bias,
-                             float* C, int ldc, int M, int N, int K, cudaStream_t st) {
+                             float* C, int ldc, int M, int N, int K, GroupBias gb, cudaStream_t st) {
     using Cfg = TcCfg<BN, MH, SPLIT>;
     CUtensorMap ma, mh, ml;
     int rc;
-    if ((rc = make_map_2d(&ma, A, M, K, lda, Cfg::BM)) != DIGAT_OK) return rc;
-    if ((rc = make_map_2d(&mh, W_hi, N, K, ldw, BN)) != DIGAT_OK) return rc;
-    if ((rc = make_map_2d(&ml, W_lo, N, K, ldw, BN)) != DIGAT_OK) return rc;
+    if ((rc = make_tensor_map_2d(&ma, A, M, K, lda, Cfg::BM, kTcBK, CU_TENSOR_MAP_SWIZZLE_64B)) != DIGAT_OK) return rc;
+    if ((rc = make_tensor_map_2d(&mh, W_hi, N, K, ldw, BN, kTcBK, CU_TENSOR_MAP_SWIZZLE_64B)) != DIGAT_OK) return rc;
+    if ((rc = make_tensor_map_2d(&ml, W_lo, N, K, ldw, BN, kTcBK, CU_TENSOR_MAP_SWIZZLE_64B)) != DIGAT_OK) return rc;
     DIGAT_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, MH, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     dim3 grid(N / BN, (M + Cfg::BM - 1) / Cfg::BM);
-    gemm_tf32x3_kernel<BN, MH, SPLIT><<<grid, kTcThreads, Cfg::SMEM, st>>>(ma, mh, ml, bias, C, ldc, M, N, K);
+    gemm_tf32x3_kernel<BN, MH, SPLIT><<<grid, kTcThreads, Cfg::SMEM, st>>>(ma, mh, ml, bias, C, ldc, M, N, K, gb);
     return check_launch("digat_linear_tf32x3");
 }
 
 static int g_tc_variant = 0;   // experiment switch (digat_debug_set_gemm_variant)
 
 inline int launch_linear_tf32x3(const float* A, int lda, const float* W_hi, const float* W_lo, int ldw, const float* bias,
-                                float* C, int ldc, int M, int N, int K, cudaStream_t st) {
+                                float* C, int ldc, int M, int N, int K, GroupBias gb, cudaStream_t st) {
     DIGAT_REQUIRE(A && W_hi && W_lo && C, "digat_linear_tf32x3: null pointer");
+    DIGAT_REQUIRE(gb.ptr == nullptr || (gb.rows > 0 && gb.col0 >= 0 && gb.cols > 0 && gb.col0 + gb.cols <= N &&
+                                        (gb.col0 & 3) == 0 && (gb.cols & 3) == 0 && aligned16(gb.ptr)),
+                  "digat_linear_tf32x3: bad row-group bias (col0/cols must be multiples of 4)");
     DIGAT_REQUIRE(M >= 0 && N > 0 && K > 0, "digat_linear_tf32x3: bad shape M=%d N=%d K=%d", M, N, K);
     DIGAT_REQUIRE((K & 3) == 0 && (lda & 3) == 0 && (ldw & 3) == 0 && (ldc & 3) == 0,
                   "digat_linear_tf32x3: K, lda, ldw, ldc must be multiples of 4");
@@ -356,9 +299,9 @@ inline int launch_linear_tf32x3(const float* A, int lda, const float* W_hi, cons
     const bool big = M > 16384;
 #define DIGAT_TC_DISPATCH(BN_)                                                                                      \
     do {                                                                                                            \
-        if (variant == 1 && big) return launch_tf32x3_cfg<BN_, 2, false>(A, lda, W_hi, W_lo, ldw, bias, C, ldc, M, N, K, st); \
-        if (variant == 1) return launch_tf32x3_cfg<BN_, 1, false>(A, lda, W_hi, W_lo, ldw, bias, C, ldc, M, N, K, st);        \
-        return launch_tf32x3_cfg<BN_, 1, true>(A, lda, W_hi, W_lo, ldw, bias, C, ldc, M, N, K, st);                 \
+        if (variant == 1 && big) return launch_tf32x3_cfg<BN_, 2, false>(A, lda, W_hi, W_lo, ldw, bias, C, ldc, M, N, K, gb, st); \
+        if (variant == 1) return launch_tf32x3_cfg<BN_, 1, false>(A, lda, W_hi, W_lo, ldw, bias, C, ldc, M, N, K, gb, st);        \
+        return launch_tf32x3_cfg<BN_, 1, true>(A, lda, W_hi, W_lo, ldw, bias, C, ldc, M, N, K, gb, st);                 \
     } while (0)
     if (N % 240 == 0) DIGAT_TC_DISPATCH(240);
     if (N % 160 == 0) DIGAT_TC_DISPATCH(160);

@@ -1,0 +1,186 @@
+// Weight-gradient GEMM and the small reductions of the backward pass (exact fp32, CUDA cores, deterministic):
+//   dW[N,K] = dC[M,N]^T * A[M,K]          (wgrad of C = A W^T; contraction over the M rows, split over gridDim.z)
+//   colsum  : out[n]     = sum_m in[m, n]                                   (bias gradients)
+//   groupsum: out[b, c]  = sum_{r < rows} in[b*rows + r, col0 + c]          (gradient of the GEMM's row-group bias = dk3)
+// Partials of the split reductions are written to a workspace and summed in a fixed order (no float atomics).
+#pragma once
+#include "common.cuh"
+
+namespace digat {
+
+constexpr int kWgTile = 128, kWgBK = 8, kWgThreads = 256;
+
+// part[z][N][K] = sum over the z-th slice of rows of dC^T A
+__global__ void __launch_bounds__(kWgThreads)
+gemm_wgrad_kernel(const float* __restrict__ dC, int lddc, const float* __restrict__ A, int lda,
+                  float* __restrict__ part, int M, int N, int K, int rows_per_split) {
+    __shared__ __align__(16) float Ds[2][kWgBK][kWgTile];
+    __shared__ __align__(16) float As[2][kWgBK][kWgTile];
+    const int tid = threadIdx.x;
+    const int n0 = blockIdx.y * kWgTile, k0 = blockIdx.x * kWgTile;
+    const int m_lo = blockIdx.z * rows_per_split, m_hi = min(M, m_lo + rows_per_split);
+    const int tx = tid & 15, ty = tid >> 4;
+    const int lrow = tid >> 5, lq = (tid & 31) * 4;            // loader: 8 rows x 32 float4
+    float4 rd, ra;
+    auto gload = [&](int m0) {
+        const int m = m0 + lrow;
+        rd = (m < m_hi && n0 + lq < N) ? *reinterpret_cast<const float4*>(dC + (size_t)m * lddc + n0 + lq)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+        ra = (m < m_hi && k0 + lq < K) ? *reinterpret_cast<const float4*>(A + (size_t)m * lda + k0 + lq)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    auto sstore = [&](int buf) {
+        *reinterpret_cast<float4*>(&Ds[buf][lrow][lq]) = rd;
+        *reinterpret_cast<float4*>(&As[buf][lrow][lq]) = ra;
+    };
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    const int steps = (m_hi - m_lo + kWgBK - 1) / kWgBK;
+    if (steps > 0) {
+        gload(m_lo);
+        sstore(0);
+    }
+    __syncthreads();
+    for (int s = 0; s < steps; ++s) {
+        const int buf = s & 1;
+        if (s + 1 < steps) gload(m_lo + (s + 1) * kWgBK);
+#pragma unroll
+        for (int kk = 0; kk < kWgBK; ++kk) {
+            float d[8], a[8];
+#pragma unroll
+            for (int gI = 0; gI < 2; ++gI) {
+                const float4 v = *reinterpret_cast<const float4*>(&Ds[buf][kk][ty * 4 + gI * 64]);
+                d[gI * 4 + 0] = v.x; d[gI * 4 + 1] = v.y; d[gI * 4 + 2] = v.z; d[gI * 4 + 3] = v.w;
+                const float4 w = *reinterpret_cast<const float4*>(&As[buf][kk][tx * 4 + gI * 64]);
+                a[gI * 4 + 0] = w.x; a[gI * 4 + 1] = w.y; a[gI * 4 + 2] = w.z; a[gI * 4 + 3] = w.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(d[i], a[j], acc[i][j]);
+        }
+        if (s + 1 < steps) {
+            sstore(buf ^ 1);
+            __syncthreads();
+        }
+    }
+    float* out = part + (size_t)blockIdx.z * N * K;
+#pragma unroll
+    for (int gi = 0; gi < 2; ++gi)
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) {
+            const int nrow = n0 + ty * 4 + gi * 64 + ii;
+            if (nrow >= N) continue;
+#pragma unroll
+            for (int gj = 0; gj < 2; ++gj) {
+                const int kc = k0 + tx * 4 + gj * 64;
+                if (kc < K)       // K % 4 == 0: a quad is entirely inside or outside
+                    *reinterpret_cast<float4*>(out + (size_t)nrow * K + kc) =
+                        make_float4(acc[gi * 4 + ii][gj * 4 + 0], acc[gi * 4 + ii][gj * 4 + 1],
+                                    acc[gi * 4 + ii][gj * 4 + 2], acc[gi * 4 + ii][gj * 4 + 3]);
+            }
+        }
+}
+
+// out[i] = sum_s part[s][i]   (fixed order: deterministic)
+__global__ void reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out, int splits, int64_t len) {
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= len) return;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int z = 0; z < splits; ++z) {
+        const float4 v = *reinterpret_cast<const float4*>(part + (size_t)z * len + i);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    *reinterpret_cast<float4*>(out + i) = s;
+}
+
+// part[z][n] = sum over the z-th slice of rows of in[m, n]
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ in, int ld, float* __restrict__ part, int M, int N, int rows_per_split) {
+    __shared__ float4 s_acc[8][32];
+    const int cq = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int col = (blockIdx.x * 32 + cq) * 4;
+    const int m_lo = blockIdx.y * rows_per_split, m_hi = min(M, m_lo + rows_per_split);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col < N)
+        for (int m = m_lo + rl; m < m_hi; m += 8) {
+            const float4 v = *reinterpret_cast<const float4*>(in + (size_t)m * ld + col);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+    s_acc[rl][cq] = s;
+    __syncthreads();
+    if (rl == 0 && col < N) {
+#pragma unroll
+        for (int r = 1; r < 8; ++r) {
+            const float4 v = s_acc[r][cq];
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        *reinterpret_cast<float4*>(part + (size_t)blockIdx.y * N + col) = s;
+    }
+}
+
+// out[b, c] = sum_{r < rows} in[(b*rows + r) * ld + col0 + c]
+__global__ void groupsum_kernel(const float* __restrict__ in, int ld, float* __restrict__ out, int groups, int rows,
+                                int col0, int cols) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int cq = cols >> 2;
+    if (i >= (int64_t)groups * cq) return;
+    const int b = (int)(i / cq), q = (int)(i % cq);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* base = in + (size_t)b * rows * ld + col0 + 4 * q;
+    for (int r = 0; r < rows; ++r) {
+        const float4 v = *reinterpret_cast<const float4*>(base + (size_t)r * ld);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    *reinterpret_cast<float4*>(out + (size_t)b * cols + 4 * q) = s;
+}
+
+inline int wgrad_splits(int M) {
+    int s = (M + 2047) / 2048;
+    return s < 1 ? 1 : (s > 64 ? 64 : s);
+}
+
+// workspace floats needed by launch_linear_wgrad / launch_colsum
+inline int64_t wgrad_workspace_floats(int M, int N, int K) { return (int64_t)wgrad_splits(M) * N * K; }
+
+inline int launch_linear_wgrad(const float* dC, int lddc, const float* A, int lda, float* dW, float* workspace,
+                               int M, int N, int K, cudaStream_t st) {
+    DIGAT_REQUIRE(dC && A && dW && workspace, "digat_linear_wgrad: null pointer");
+    DIGAT_REQUIRE(M > 0 && N > 0 && K > 0 && (N & 3) == 0 && (K & 3) == 0 && (lddc & 3) == 0 && (lda & 3) == 0,
+                  "digat_linear_wgrad: N, K, lddc, lda must be multiples of 4");
+    DIGAT_REQUIRE(aligned16(dC) && aligned16(A) && aligned16(dW) && aligned16(workspace),
+                  "digat_linear_wgrad: pointers must be 16-byte aligned");
+    const int splits = wgrad_splits(M);
+    const int rows = ((M + splits - 1) / splits + kWgBK - 1) / kWgBK * kWgBK;
+    dim3 grid((K + kWgTile - 1) / kWgTile, (N + kWgTile - 1) / kWgTile, splits);
+    gemm_wgrad_kernel<<<grid, kWgThreads, 0, st>>>(dC, lddc, A, lda, workspace, M, N, K, rows);
+    const int64_t len = (int64_t)N * K;
+    reduce_partials_kernel<<<(unsigned)((len / 4 + 255) / 256), 256, 0, st>>>(workspace, dW, splits, len);
+    return check_launch("digat_linear_wgrad");
+}
+
+inline int launch_colsum(const float* in, int ld, float* out, float* workspace, int M, int N, cudaStream_t st) {
+    DIGAT_REQUIRE(in && out && workspace, "digat_colsum: null pointer");
+    DIGAT_REQUIRE(M > 0 && N > 0 && (N & 3) == 0 && (ld & 3) == 0 && aligned16(in) && aligned16(out) && aligned16(workspace),
+                  "digat_colsum: N, ld must be multiples of 4 and pointers 16-byte aligned");
+    const int splits = wgrad_splits(M);
+    const int rows = (M + splits - 1) / splits;
+    dim3 grid((N / 4 + 31) / 32, splits);
+    colsum_kernel<<<grid, 256, 0, st>>>(in, ld, workspace, M, N, rows);
+    reduce_partials_kernel<<<(unsigned)((N / 4 + 255) / 256), 256, 0, st>>>(workspace, out, splits, N);
+    return check_launch("digat_colsum");
+}
+
+inline int launch_groupsum(const float* in, int ld, float* out, int groups, int rows, int col0, int cols, cudaStream_t st) {
+    DIGAT_REQUIRE(in && out, "digat_groupsum: null pointer");
+    DIGAT_REQUIRE(groups > 0 && rows > 0 && cols > 0 && (cols & 3) == 0 && (col0 & 3) == 0 && (ld & 3) == 0 &&
+                  aligned16(in) && aligned16(out), "digat_groupsum: bad shape / alignment");
+    const int64_t total = (int64_t)groups * (cols / 4);
+    groupsum_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, ld, out, groups, rows, col0, cols);
+    return check_launch("digat_groupsum");
+}
+
+}  // namespace digat

@@ -1,129 +1,185 @@
 // Fused Eq. (8) graph-attention layer, forward (replaces reference graphEncoders.py:150-153 / 170-173).
 //
-//   s_ij = sum_d a_d * relu((k3_d + K1_jd) + K2_id)      -- the [B,n,n,D] broadcast tensor is never materialised
+//   s_ij = sum_d a_d * relu(U_jd + K2_id),  U = k3 + K1   -- the [B,n,n,D] broadcast tensor is never materialised
 //   e_ij = leaky_relu(s_ij, 0.2);  m_ij = adj_ij ? e_ij : -1e9;  alpha_i: = softmax_j(m_i:)
 //   Y_i  = relu(sum_j alpha_ij h_j) + X_i
 //
-// One CTA owns R whole graphs (batch rows).  Three phases share one shared-memory arena:
-//   phase 1  D is streamed in chunks: U = k3 + K1 and K2 chunks are staged in smem ([node][d], padded rows);
-//            every thread owns a 4x4 set of (i,j) pairs (rows interleaved by nt so that consecutive lanes read
-//            consecutive smem rows -> conflict-free LDS.128) and keeps the 16 partial dot products in registers;
-//   phase 2  one warp per query node i: leaky-relu, mask, max / sum by warp shuffles, exp, normalise; the weights
-//            stay in smem, transposed (St[j][i]) so that phase 3 reads 4 query rows per LDS.128;
-//   phase 3  h is streamed in chunks; a thread owns 8 query rows x 4 features and accumulates alpha * h over j,
-//            then applies relu + residual and writes Y with streaming 128-bit stores.
-// HBM traffic per graph: read P (3nD) + X (nD) + adj (n^2 bytes) + k3, write Y (nD): 5nD*4 + n^2 bytes.
+// U = fl(k3 + K1) is produced by the projection GEMM's epilogue (row-group bias), rounded exactly like the
+// reference's first broadcast add, so this kernel only streams tiles of P = [h | U | K2].
+//
+// One CTA owns R whole graphs (batch rows).  The feature dimension is streamed through a 2-deep TMA pipeline
+// (cp.async.bulk.tensor.2d -> mbarrier); all three phases share the two shared-memory buffers:
+//   phase 1  per chunk of `dc` features: U and K2 tiles [R*n][dc] (dense rows; dc/4 odd -> consecutive rows start
+//            4 banks apart, so the row-interleaved LDS.128 pattern is conflict-free).  Every thread owns a 4x4 set
+//            of (i,j) pairs and keeps 16 x 2 partial dot products in registers; the inner loop is packed fp32x2
+//            (FADD2 / FFMA2) with scalar FMNMX for the relu: 2 issue slots per (i,j,d) instead of 3;
+//   phase 2  one warp per query node: leaky-relu, mask, max / sum by warp shuffles, exp, normalise; the weights stay
+//            in smem, transposed (St[j][i]) so that phase 3 reads 8 query rows with two LDS.128;
+//   phase 3  h streamed in chunks of 2*dc features; a thread owns 8 query rows x 4 features, accumulates
+//            alpha * h over j (FFMA2), applies relu + residual and writes Y with streaming 128-bit stores.
+// The loads of the next chunk (and of the first h chunks during phase 2) overlap the math of the current one.
+// HBM traffic per graph: read P (3nD) + X (nD) + adj (n^2 bytes), write Y (nD): 5nD*4 + n^2 bytes.
 #pragma once
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace digat {
 
-constexpr int kPairThreads = 320;   // 10 warps: 289 pair tiles of a 68-node user graph fit in one pass
+constexpr int kPairThreads = 320;   // 10 warps: the 289 pair tiles of a 68-node user graph fit in one pass
 constexpr int kPairMaxNodes = 128;
 
 struct PairAttnGeom {
-    int R;        // graphs per CTA
-    int nt;       // pair tiles per dimension = ceil(n/4)
-    int dc1;      // phase-1 feature chunk (multiple of 4)
-    int ld1;      // smem row stride of the phase-1 chunk (dc1 + 4 floats; odd multiple of 4 -> conflict-free)
-    int dc3;      // phase-3 feature chunk
-    int ld3;      // dc3 + 4
-    int lds;      // leading dim of the transposed score matrix St[j][i] (multiple of 8, >= n)
-    int arena;    // floats of the chunk arena per graph
-    size_t smem;  // dynamic shared memory bytes
+    int R;           // graphs per CTA
+    int nt;          // pair tiles per dimension = ceil(n/4)
+    int dc;          // phase-1 feature chunk (multiple of 4; dc/4 odd when possible)
+    int nch1;        // phase-1 chunks = ceil(D/dc)
+    int dc3;         // phase-3 feature chunk = 2*dc
+    int nch3;        // phase-3 chunks = ceil(D/dc3)
+    int lds;         // leading dim of the transposed score matrix St[j][i] (multiple of 4, >= 8*ceil(n/8))
+    int tile_floats; // floats of one [R*n][dc] tile, rounded up to 128 bytes
+    size_t smem;     // dynamic shared memory bytes
 };
 
 struct PairAttnArgs {
     const float* P; int ldp;
-    const float* k3; const float* a; const uint8_t* adj; const float* X;
-    float* Y; float* alpha_out;
+    const float* a; const uint8_t* adj; const float* X;
+    float* Y;
     int B, n, D;
+    // training extras (all optional): dropout on the attention weights (reference graphEncoders.py:152/172) with a
+    // caller-provided keep mask, and the tensors the backward pass needs
+    const uint8_t* drop_keep;   // [B,n,n] 1 = keep; alpha~ = alpha * keep * drop_scale
+    float drop_scale;           // 1 / (1 - p)
+    float* score_out;           // [B,n,n] raw Eq.(8) scores s_ij (their sign selects the leaky-relu slope)
+    float* alpha_out;           // [B,n,n] softmax weights BEFORE dropout
+    uint8_t* relu_mask_out;     // [B,n,D] 1 where (alpha~ h) > 0
 };
+
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {      // two IEEE fp32 adds in one issue slot
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
 
 template <bool kSingleTile>
 __global__ void __launch_bounds__(kPairThreads, 2)
-graph_layer_fwd_kernel(PairAttnArgs p, PairAttnGeom g) {
-    extern __shared__ __align__(16) float smem[];
+graph_layer_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map3,
+                       PairAttnArgs p, PairAttnGeom g) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];   // TMA destinations need 128-byte alignment
+    uint8_t* sbase = smem_raw;                              // (keep it a __shared__ pointer: LDS/STS, not generic LD/ST)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = p.n, D = p.D, R = g.R;
     const int b0 = blockIdx.x * R;
     const int Rv = min(R, p.B - b0);                 // graphs actually present in this CTA
+    const int rows = R * n;                          // rows of a staged tile (TMA zero-fills rows past B*n)
 
-    float* a_s = smem;                                // [D]
-    float* k3_s = a_s + D;                            // [R][D]
-    float* St = k3_s + (size_t)R * D;                 // [R][n][lds]   St[r][j*lds + i]
-    float* arena = St + (size_t)R * n * g.lds;        // [R][arena]
+    const int half = 2 * g.tile_floats;              // floats per pipeline buffer
+    float* buf0 = reinterpret_cast<float*>(sbase);   // [2][half]   (128-byte aligned: TMA destination)
+    float* a_s = buf0 + 2 * half;                    // [D]
+    float* St = a_s + D;                             // [R][n][lds]   St[r][j*lds + i]
+    uint64_t* full = reinterpret_cast<uint64_t*>(St + (size_t)R * n * g.lds);   // [2] TMA barriers (8-byte aligned)
 
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     for (int i = tid; i < D / 4; i += kPairThreads)
         reinterpret_cast<float4*>(a_s)[i] = reinterpret_cast<const float4*>(p.a)[i];
-    for (int i = tid; i < Rv * (D / 4); i += kPairThreads) {
-        int r = i / (D / 4), q = i % (D / 4);
-        reinterpret_cast<float4*>(k3_s + (size_t)r * D)[q] =
-            reinterpret_cast<const float4*>(p.k3 + (size_t)(b0 + r) * D)[q];
-    }
     __syncthreads();
+
+    // unified load schedule: loads 0..nch1-1 are phase-1 chunks (U + K2 tiles), nch1.. are phase-3 chunks (h tile);
+    // load l lands in buffer l&1 and completes phase (l>>1)&1 of that buffer's barrier.
+    const int n_loads = g.nch1 + g.nch3;
+    auto issue = [&](int l) {
+        float* dst = buf0 + (l & 1) * half;
+        if (l < g.nch1) {
+            mbar_arrive_expect_tx(&full[l & 1], 2u * rows * g.dc * 4u);
+            tma_load_2d(dst, &map1, &full[l & 1], D + l * g.dc, b0 * n);                       // U  = k3 + K1
+            tma_load_2d(dst + g.tile_floats, &map1, &full[l & 1], 2 * D + l * g.dc, b0 * n);   // K2
+        } else {
+            mbar_arrive_expect_tx(&full[l & 1], (uint32_t)rows * g.dc3 * 4u);
+            tma_load_2d(dst, &map3, &full[l & 1], (l - g.nch1) * g.dc3, b0 * n);               // h
+        }
+    };
+    if (tid == 0) {
+        issue(0);
+        if (n_loads > 1) issue(1);
+    }
 
     // ------------------------------------------------------------------ phase 1: pair scores
     const int nt = g.nt, tiles_per_graph = nt * nt, tiles = Rv * tiles_per_graph;
-    float acc[4][4];
+    uint64_t acc[4][4];
 #pragma unroll
     for (int x = 0; x < 4; ++x)
 #pragma unroll
-        for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
+        for (int y = 0; y < 4; ++y) acc[x][y] = 0ull;
 
-    for (int c0 = 0; c0 < D; c0 += g.dc1) {
-        const int w = min(g.dc1, D - c0), wq = w >> 2;
-        // stage U = k3 + K1 (rounded exactly like the reference's first add) and K2
-        for (int it = tid; it < Rv * n * wq; it += kPairThreads) {
-            const int q = it % wq, node = (it / wq) % n, r = it / (wq * n);
-            const float* prow = p.P + ((size_t)(b0 + r) * n + node) * p.ldp + c0 + 4 * q;
-            float4 k1 = ldg_stream(reinterpret_cast<const float4*>(prow + D));
-            float4 k2 = ldg_stream(reinterpret_cast<const float4*>(prow + 2 * D));
-            const float4 kk = *reinterpret_cast<const float4*>(k3_s + (size_t)r * D + c0 + 4 * q);
-            k1.x = kk.x + k1.x; k1.y = kk.y + k1.y; k1.z = kk.z + k1.z; k1.w = kk.w + k1.w;
-            float* base = arena + (size_t)r * g.arena;
-            *reinterpret_cast<float4*>(base + node * g.ld1 + 4 * q) = k1;                    // U  [n][ld1]
-            *reinterpret_cast<float4*>(base + (n + node) * g.ld1 + 4 * q) = k2;              // K2 [n][ld1]
-        }
-        __syncthreads();
+    for (int l = 0; l < g.nch1; ++l) {
+        const int c0 = l * g.dc;
+        const int wq = min(g.dc, D - c0) >> 2;
+        mbar_wait(&full[l & 1], (uint32_t)(l >> 1) & 1u);
         for (int t = tid; t < tiles; t += kPairThreads) {
-            const int r = t / tiles_per_graph, tt = t % tiles_per_graph;
-            const int ti = tt / nt, tj = tt % nt;
-            const float* Us = arena + (size_t)r * g.arena;
-            const float* K2s = Us + n * g.ld1;
-            int io[4], jo[4];
+            const int r = t / tiles_per_graph, tt = t - r * tiles_per_graph;
+            const int ti = tt / nt, tj = tt - ti * nt;
+            // byte offsets (from the start of dynamic smem) of this thread's 4 K2 rows and 4 U rows
+            const uint32_t buf_off = (uint32_t)((l & 1) * half) * 4u;
+            uint32_t ko[4], uo[4];
 #pragma unroll
             for (int x = 0; x < 4; ++x) {
-                io[x] = min(ti + nt * x, n - 1) * g.ld1;
-                jo[x] = min(tj + nt * x, n - 1) * g.ld1;
+                ko[x] = buf_off + (uint32_t)(g.tile_floats + (r * n + min(ti + nt * x, n - 1)) * g.dc) * 4u;
+                uo[x] = buf_off + (uint32_t)((r * n + min(tj + nt * x, n - 1)) * g.dc) * 4u;
             }
             if (!kSingleTile) {
 #pragma unroll
                 for (int x = 0; x < 4; ++x)
 #pragma unroll
-                    for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
+                    for (int y = 0; y < 4; ++y) acc[x][y] = 0ull;
             }
-            const float4* a4 = reinterpret_cast<const float4*>(a_s + c0);
-#pragma unroll 2
+            const uint32_t ao = (uint32_t)(2 * half + c0) * 4u;
+#pragma unroll 1
             for (int q = 0; q < wq; ++q) {
-                const float4 av = a4[q];
-                float4 k2[4], u[4];
+                const uint32_t qo = (uint32_t)q * 16u;
+                const float4 av = *reinterpret_cast<const float4*>(smem_raw + ao + qo);
+                const uint64_t a01 = pack2(av.x, av.y), a23 = pack2(av.z, av.w);
+                uint64_t u01[4], u23[4];
 #pragma unroll
-                for (int x = 0; x < 4; ++x) {
-                    k2[x] = *reinterpret_cast<const float4*>(K2s + io[x] + 4 * q);
-                    u[x] = *reinterpret_cast<const float4*>(Us + jo[x] + 4 * q);
+                for (int y = 0; y < 4; ++y) {
+                    const float4 u = *reinterpret_cast<const float4*>(smem_raw + uo[y] + qo);
+                    u01[y] = pack2(u.x, u.y);
+                    u23[y] = pack2(u.z, u.w);
                 }
 #pragma unroll
-                for (int x = 0; x < 4; ++x)
+                for (int x = 0; x < 4; ++x) {
+                    const float4 k2 = *reinterpret_cast<const float4*>(smem_raw + ko[x] + qo);
+                    const uint64_t k01 = pack2(k2.x, k2.y), k23 = pack2(k2.z, k2.w);
+                    // 8 independent add -> relu -> fma chains per x: staged so the scheduler can interleave them
+                    float s[16];
 #pragma unroll
                     for (int y = 0; y < 4; ++y) {
-                        float s = acc[x][y];
-                        s = fmaf(av.x, fmaxf(u[y].x + k2[x].x, 0.f), s);
-                        s = fmaf(av.y, fmaxf(u[y].y + k2[x].y, 0.f), s);
-                        s = fmaf(av.z, fmaxf(u[y].z + k2[x].z, 0.f), s);
-                        s = fmaf(av.w, fmaxf(u[y].w + k2[x].w, 0.f), s);
-                        acc[x][y] = s;
+                        unpack2(add2(u01[y], k01), s[4 * y + 0], s[4 * y + 1]);
+                        unpack2(add2(u23[y], k23), s[4 * y + 2], s[4 * y + 3]);
                     }
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) s[e] = fmaxf(s[e], 0.f);
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) {
+                        acc[x][y] = fma2(a01, pack2(s[4 * y + 0], s[4 * y + 1]), acc[x][y]);
+                        acc[x][y] = fma2(a23, pack2(s[4 * y + 2], s[4 * y + 3]), acc[x][y]);
+                    }
+                }
             }
             if (!kSingleTile) {
                 float* S = St + (size_t)r * n * g.lds;
@@ -133,31 +189,38 @@ graph_layer_fwd_kernel(PairAttnArgs p, PairAttnGeom g) {
                     for (int y = 0; y < 4; ++y) {
                         const int i = ti + nt * x, j = tj + nt * y;
                         if (i < n && j < n) {
+                            float e, o;
+                            unpack2(acc[x][y], e, o);
                             float* dst = S + j * g.lds + i;
-                            *dst = (c0 == 0 ? 0.f : *dst) + acc[x][y];
+                            *dst = (l == 0 ? 0.f : *dst) + (e + o);
                         }
                     }
             }
         }
-        __syncthreads();
+        __syncthreads();                              // everyone is done with buffer l&1
+        if (tid == 0 && l + 2 < n_loads) issue(l + 2);
     }
     if (kSingleTile && tid < tiles) {
-        const int r = tid / tiles_per_graph, tt = tid % tiles_per_graph;
-        const int ti = tt / nt, tj = tt % nt;
+        const int r = tid / tiles_per_graph, tt = tid - r * tiles_per_graph;
+        const int ti = tt / nt, tj = tt - ti * nt;
         float* S = St + (size_t)r * n * g.lds;
 #pragma unroll
         for (int x = 0; x < 4; ++x)
 #pragma unroll
             for (int y = 0; y < 4; ++y) {
                 const int i = ti + nt * x, j = tj + nt * y;
-                if (i < n && j < n) S[j * g.lds + i] = acc[x][y];
+                if (i < n && j < n) {
+                    float e, o;
+                    unpack2(acc[x][y], e, o);
+                    S[j * g.lds + i] = e + o;
+                }
             }
     }
     __syncthreads();
 
     // ------------------------------------------------------------------ phase 2: masked softmax per query node
     for (int row = warp; row < Rv * n; row += kPairThreads / 32) {
-        const int r = row / n, i = row % n;
+        const int r = row / n, i = row - r * n;
         float* S = St + (size_t)r * n * g.lds;
         const uint8_t* adj = p.adj + ((size_t)(b0 + r) * n + i) * n;
         float v[kPairMaxNodes / 32];
@@ -168,6 +231,7 @@ graph_layer_fwd_kernel(PairAttnArgs p, PairAttnGeom g) {
             float m = -INFINITY;
             if (j < n) {
                 const float s = S[j * g.lds + i];
+                if (p.score_out != nullptr) p.score_out[((size_t)(b0 + r) * n + i) * n + j] = s;
                 const float e = s > 0.f ? s : s * kLeakySlope;
                 m = adj[j] != 0 ? e : kNegFill;
             }
@@ -187,52 +251,54 @@ graph_layer_fwd_kernel(PairAttnArgs p, PairAttnGeom g) {
         for (int k = 0; k < kPairMaxNodes / 32; ++k) {
             const int j = lane + 32 * k;
             if (j < n) {
-                const float al = v[k] / sum;
+                float al = v[k] / sum;
+                const size_t o = ((size_t)(b0 + r) * n + i) * n + j;
+                if (p.alpha_out != nullptr) p.alpha_out[o] = al;
+                if (p.drop_keep != nullptr) al = p.drop_keep[o] != 0 ? al * p.drop_scale : 0.f;
                 S[j * g.lds + i] = al;
-                if (p.alpha_out != nullptr) p.alpha_out[((size_t)(b0 + r) * n + i) * n + j] = al;
             }
         }
     }
     // padding columns i in [n, lds) are read (and discarded) by phase 3: keep them finite
-    for (int it = tid; it < Rv * n * (g.lds - n); it += kPairThreads) {
+    {
         const int pad = g.lds - n;
-        const int i = n + it % pad, j = (it / pad) % n, r = it / (pad * n);
-        St[(size_t)r * n * g.lds + j * g.lds + i] = 0.f;
+        for (int it = tid; it < Rv * n * pad; it += kPairThreads) {
+            const int i = n + it % pad, j = (it / pad) % n, r = it / (pad * n);
+            St[(size_t)r * n * g.lds + j * g.lds + i] = 0.f;
+        }
     }
     __syncthreads();
 
     // ------------------------------------------------------------------ phase 3: Y = relu(alpha * h) + X
     const int nit = (n + 7) >> 3;
-    for (int c0 = 0; c0 < D; c0 += g.dc3) {
-        const int w = min(g.dc3, D - c0), wq = w >> 2;
-        for (int it = tid; it < Rv * n * wq; it += kPairThreads) {
-            const int q = it % wq, node = (it / wq) % n, r = it / (wq * n);
-            const float4 h = ldg_stream(reinterpret_cast<const float4*>(
-                p.P + ((size_t)(b0 + r) * n + node) * p.ldp + c0 + 4 * q));
-            *reinterpret_cast<float4*>(arena + (size_t)r * g.arena + node * g.ld3 + 4 * q) = h;
-        }
-        __syncthreads();
+    for (int l = g.nch1; l < n_loads; ++l) {
+        const int c0 = (l - g.nch1) * g.dc3;
+        const int wq = min(g.dc3, D - c0) >> 2;
+        const float* Hs0 = buf0 + (l & 1) * half;
+        mbar_wait(&full[l & 1], (uint32_t)(l >> 1) & 1u);
         const int items = Rv * nit * wq;
         for (int it = tid; it < items; it += kPairThreads) {
             const int q = it % wq, ib = (it / wq) % nit, r = it / (wq * nit);
             const int i0 = ib * 8;
-            const float* Hs = arena + (size_t)r * g.arena + 4 * q;
+            const float* Hs = Hs0 + (size_t)r * n * g.dc3 + 4 * q;
             const float* S = St + (size_t)r * n * g.lds + i0;
-            float4 o[8];
+            uint64_t o[8][2];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) o[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int k = 0; k < 8; ++k) o[k][0] = o[k][1] = 0ull;
 #pragma unroll 2
             for (int j = 0; j < n; ++j) {
-                const float4 h = *reinterpret_cast<const float4*>(Hs + j * g.ld3);
-                const float4 al0 = *reinterpret_cast<const float4*>(S + j * g.lds);
-                const float4 al1 = *reinterpret_cast<const float4*>(S + j * g.lds + 4);
+                const float4 h = *reinterpret_cast<const float4*>(Hs);
+                const float4 al0 = *reinterpret_cast<const float4*>(S);
+                const float4 al1 = *reinterpret_cast<const float4*>(S + 4);
+                Hs += g.dc3;
+                S += g.lds;
+                const uint64_t h01 = pack2(h.x, h.y), h23 = pack2(h.z, h.w);
                 const float al[8] = {al0.x, al0.y, al0.z, al0.w, al1.x, al1.y, al1.z, al1.w};
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    o[k].x = fmaf(al[k], h.x, o[k].x);
-                    o[k].y = fmaf(al[k], h.y, o[k].y);
-                    o[k].z = fmaf(al[k], h.z, o[k].z);
-                    o[k].w = fmaf(al[k], h.w, o[k].w);
+                    const uint64_t aa = pack2(al[k], al[k]);
+                    o[k][0] = fma2(aa, h01, o[k][0]);
+                    o[k][1] = fma2(aa, h23, o[k][1]);
                 }
             }
 #pragma unroll
@@ -242,61 +308,52 @@ graph_layer_fwd_kernel(PairAttnArgs p, PairAttnGeom g) {
                     const size_t off = ((size_t)(b0 + r) * n + i) * D + c0 + 4 * q;
                     const float4 x = ldg_stream(reinterpret_cast<const float4*>(p.X + off));
                     float4 y;
-                    y.x = fmaxf(o[k].x, 0.f) + x.x;
-                    y.y = fmaxf(o[k].y, 0.f) + x.y;
-                    y.z = fmaxf(o[k].z, 0.f) + x.z;
-                    y.w = fmaxf(o[k].w, 0.f) + x.w;
+                    unpack2(o[k][0], y.x, y.y);
+                    unpack2(o[k][1], y.z, y.w);
+                    if (p.relu_mask_out != nullptr)
+                        *reinterpret_cast<uchar4*>(p.relu_mask_out + off) =
+                            make_uchar4(y.x > 0.f, y.y > 0.f, y.z > 0.f, y.w > 0.f);
+                    y.x = fmaxf(y.x, 0.f) + x.x;
+                    y.y = fmaxf(y.y, 0.f) + x.y;
+                    y.z = fmaxf(y.z, 0.f) + x.z;
+                    y.w = fmaxf(y.w, 0.f) + x.w;
                     stg_stream(reinterpret_cast<float4*>(p.Y + off), y);
                 }
             }
         }
         __syncthreads();
+        if (tid == 0 && l + 2 < n_loads) issue(l + 2);
     }
 }
 
 // Host-side geometry: graphs per CTA and chunk widths for (n, D) under a shared-memory budget.
-inline bool pair_attn_geometry(int n, int D, int B, PairAttnGeom* g) {
+inline void pair_attn_geometry(int n, int D, int B, PairAttnGeom* g) {
     const int nt = (n + 3) / 4;
     const int tiles = nt * nt;
-    int dc1 = 80;
-    if (dc1 > D) dc1 = D;
-    const int ld1 = dc1 + 4;
-    const int lds = ((n + 7) / 8) * 8 + 4;        // multiple of 4; +4 shifts consecutive j by 4 banks
-    const int arena = 2 * n * ld1;
-    const size_t per_graph = (size_t)(D + n * lds + arena) * sizeof(float);
-    const size_t budget = 72 * 1024;               // keeps 3 CTAs per SM for the 68-node user graph
+    int dc = 68;                                   // 68/4 = 17 (odd): consecutive dense rows start 4 banks apart
+    if (dc > D) dc = D;
+    const int lds = ((n + 7) / 8) * 8 + 4;         // multiple of 4; +4 shifts consecutive j by 4 banks
+    auto tile_floats = [&](int R) { return ((R * n * dc * 4 + 127) / 128) * 128 / 4; };
+    auto smem_of = [&](int R) {
+        return (size_t)128 + (size_t)4 * tile_floats(R) * 4 + (size_t)D * 4 + (size_t)R * n * lds * 4 + 16;
+    };
+    const size_t budget = 110 * 1024;              // two CTAs per SM
     int R = kPairThreads / tiles;
     if (R < 1) R = 1;
-    while (R > 1 && (size_t)D * 4 + R * per_graph > budget) --R;
+    while (R > 1 && (smem_of(R) > budget || R * n > 256)) --R;      // TMA box: at most 256 rows
     if (R > B) R = B > 0 ? B : 1;
-    // phase-3 chunk: widest multiple of 4 that fits the arena and maximises lane utilisation
-    const int nit = (n + 7) / 8;
-    const int max_dc3 = (arena / n) - 4;
-    int best = 4; double best_eff = -1.0;
-    for (int dc3 = 16; dc3 <= max_dc3 && dc3 <= D; dc3 += 4) {
-        long busy = 0, slots = 0;
-        for (int c0 = 0; c0 < D; c0 += dc3) {
-            const int w = (D - c0 < dc3) ? D - c0 : dc3;
-            const long items = (long)R * nit * (w / 4);
-            busy += items;
-            slots += ((items + kPairThreads - 1) / kPairThreads) * kPairThreads + 64;   // +64: per-chunk sync cost
-        }
-        const double eff = (double)busy / (double)slots;
-        if (eff > best_eff) { best_eff = eff; best = dc3; }
-    }
-    g->R = R; g->nt = nt; g->dc1 = dc1; g->ld1 = ld1; g->dc3 = best; g->ld3 = best + 4; g->lds = lds;
-    g->arena = arena;
-    g->smem = (size_t)D * 4 + (size_t)R * per_graph;
-    return true;
+    g->R = R; g->nt = nt; g->dc = dc; g->nch1 = (D + dc - 1) / dc; g->dc3 = 2 * dc;
+    g->nch3 = (D + 2 * dc - 1) / (2 * dc); g->lds = lds; g->tile_floats = tile_floats(R); g->smem = smem_of(R);
 }
 
-inline int launch_graph_layer_fwd(const float* P, int ldp, const float* k3, const float* a, const uint8_t* adj,
-                                  const float* X, float* Y, float* alpha_out, int B, int n, int D, cudaStream_t st) {
-    DIGAT_REQUIRE(P && k3 && a && adj && X && Y, "digat_graph_layer_fwd: null pointer");
+inline int launch_graph_layer_fwd(const float* P, int ldp, const float* a, const uint8_t* adj, const float* X, float* Y,
+                                  int B, int n, int D, const uint8_t* drop_keep, float drop_scale, float* score_out,
+                                  float* alpha_out, uint8_t* relu_mask_out, cudaStream_t st) {
+    DIGAT_REQUIRE(P && a && adj && X && Y, "digat_graph_layer_fwd: null pointer");
     DIGAT_REQUIRE(B >= 0 && n >= 1 && n <= kPairMaxNodes, "digat_graph_layer_fwd: n=%d outside [1,%d]", n, kPairMaxNodes);
     DIGAT_REQUIRE(D >= 4 && (D & 3) == 0 && D <= 1024, "digat_graph_layer_fwd: D=%d must be a multiple of 4 in [4,1024]", D);
     DIGAT_REQUIRE((ldp & 3) == 0 && ldp >= 3 * D, "digat_graph_layer_fwd: ldp=%d must be a multiple of 4 and >= 3D", ldp);
-    DIGAT_REQUIRE(aligned16(P) && aligned16(k3) && aligned16(a) && aligned16(X) && aligned16(Y),
+    DIGAT_REQUIRE(aligned16(P) && aligned16(a) && aligned16(X) && aligned16(Y),
                   "digat_graph_layer_fwd: pointers must be 16-byte aligned");
     if (B == 0) return DIGAT_OK;
     PairAttnGeom g;
@@ -304,15 +361,19 @@ inline int launch_graph_layer_fwd(const float* P, int ldp, const float* k3, cons
     const DeviceInfo* di = device_info();
     if (!di) return fail(DIGAT_E_CUDA, "digat_graph_layer_fwd: no CUDA device");
     DIGAT_REQUIRE(g.smem <= (size_t)di->max_smem_optin, "digat_graph_layer_fwd: needs %zu B shared memory", g.smem);
-    PairAttnArgs args{P, ldp, k3, a, adj, X, Y, alpha_out, B, n, D};
+    CUtensorMap map1, map3;
+    int rc;
+    if ((rc = make_tensor_map_2d(&map1, P, (int64_t)B * n, 3 * D, ldp, g.R * n, g.dc, CU_TENSOR_MAP_SWIZZLE_NONE)) != DIGAT_OK) return rc;
+    if ((rc = make_tensor_map_2d(&map3, P, (int64_t)B * n, 3 * D, ldp, g.R * n, g.dc3, CU_TENSOR_MAP_SWIZZLE_NONE)) != DIGAT_OK) return rc;
+    PairAttnArgs args{P, ldp, a, adj, X, Y, B, n, D, drop_keep, drop_scale, score_out, alpha_out, relu_mask_out};
     const int grid = (B + g.R - 1) / g.R;
     const bool single = g.R * g.nt * g.nt <= kPairThreads;
     if (single) {
         DIGAT_CUDA(cudaFuncSetAttribute(graph_layer_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
-        graph_layer_fwd_kernel<true><<<grid, kPairThreads, g.smem, st>>>(args, g);
+        graph_layer_fwd_kernel<true><<<grid, kPairThreads, g.smem, st>>>(map1, map3, args, g);
     } else {
         DIGAT_CUDA(cudaFuncSetAttribute(graph_layer_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
-        graph_layer_fwd_kernel<false><<<grid, kPairThreads, g.smem, st>>>(args, g);
+        graph_layer_fwd_kernel<false><<<grid, kPairThreads, g.smem, st>>>(map1, map3, args, g);
     }
     return check_launch("digat_graph_layer_fwd");
 }

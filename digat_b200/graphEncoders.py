@@ -63,10 +63,11 @@ class PackedWeight:
 TENSOR_CORE_MIN_ROWS = 256
 
 
-def linear(A, W, bias=None, relu=False, M=None, K=None, lda=None, out=None):
+def linear(A, W, bias=None, relu=False, M=None, K=None, lda=None, out=None, group_bias=None, group_rows=1,
+           group_col0=0):
     """out[M,N] = A[M,K] W[N,K]^T (+bias).  ``A`` may be a strided row view (pass M, K, lda explicitly).
     W: PackedWeight (tcgen05 3xTF32 GEMM when it has TF32 planes and M is large enough) or a plain fp32 tensor
-    (exact-fp32 CUDA-core GEMM)."""
+    (exact-fp32 CUDA-core GEMM).  group_bias [M/group_rows, cols]: out[m, group_col0 + c] += group_bias[m // group_rows, c]."""
     w = W.w if isinstance(W, PackedWeight) else W
     N = w.shape[0]
     if K is None:
@@ -77,20 +78,23 @@ def linear(A, W, bias=None, relu=False, M=None, K=None, lda=None, out=None):
         lda = K
     if out is None:
         out = torch.empty((M, N), device=A.device, dtype=torch.float32)
+    gcols = 0 if group_bias is None else group_bias.shape[1]
     if isinstance(W, PackedWeight) and W.hi is not None and M >= TENSOR_CORE_MIN_ROWS and not relu:
         _lib.call('digat_linear_tf32x3', A.data_ptr(), lda, W.hi.data_ptr(), W.lo.data_ptr(), w.stride(0), _ptr(bias),
-                  out.data_ptr(), out.stride(0), M, N, K, _stream())
+                  out.data_ptr(), out.stride(0), M, N, K, _ptr(group_bias), group_rows, group_col0, gcols, _stream())
     else:
         _lib.call('digat_linear_f32', A.data_ptr(), lda, w.data_ptr(), w.stride(0), _ptr(bias), out.data_ptr(),
-                  out.stride(0), M, N, K, 1 if relu else 0, _stream())
+                  out.stride(0), M, N, K, 1 if relu else 0, _ptr(group_bias), group_rows, group_col0, gcols, _stream())
     return out
 
 
-def graph_layer_fwd(P, k3, a, adj, X, alpha_out=None):
+def graph_layer_fwd(P, a, adj, X, drop_keep=None, drop_scale=1.0, score_out=None, alpha_out=None, relu_mask_out=None):
+    """P [B*n, 3D] = h | U | K2 with U = k3 + K1 (row-group bias of the projection GEMM)."""
     B, n, D = X.shape
     Y = torch.empty_like(X)
-    _lib.call('digat_graph_layer_fwd', P.data_ptr(), P.stride(0), k3.data_ptr(), a.data_ptr(), adj.data_ptr(),
-              X.data_ptr(), Y.data_ptr(), _ptr(alpha_out), B, n, D, _stream())
+    _lib.call('digat_graph_layer_fwd', P.data_ptr(), P.stride(0), a.data_ptr(), adj.data_ptr(), X.data_ptr(),
+              Y.data_ptr(), B, n, D, _ptr(drop_keep), float(drop_scale), _ptr(score_out), _ptr(alpha_out),
+              _ptr(relu_mask_out), _stream())
     return Y
 
 
@@ -259,9 +263,9 @@ class DIGAT(GraphEncoder):
 
     def _layer(self, w, g, i, X, adj, ctx_other):
         B, n, D = X.shape
-        P = linear(X, w[g, i, 'Wcat'], w[g, i, 'bcat'])                           # [B*n, 3D] = h | K1 | K2
-        k3 = linear(ctx_other, w[g, i, 'W3'], w[g, i, 'b3'])
-        return graph_layer_fwd(P, k3, w[g, i, 'a'], adj, X)
+        k3 = linear(ctx_other, w[g, i, 'W3'], w[g, i, 'b3'])                      # [B, D]
+        P = linear(X, w[g, i, 'Wcat'], w[g, i, 'bcat'], group_bias=k3, group_rows=n, group_col0=D)   # h | k3+K1 | K2
+        return graph_layer_fwd(P, w[g, i, 'a'], adj, X)
 
     def _err_flag(self, device):
         f = getattr(self, '_err', None)

@@ -41,9 +41,15 @@ int         digat_device_check(int* sm_count);
  * C[M,N] = A[M,K] * W[N,K]^T (+ bias[N]) (optionally relu), W in nn.Linear layout.
  * --------------------------------------------------------------------------------------------------------- */
 
+/* Optional row-group bias of both GEMMs (group_bias may be NULL):
+ *   C[m, group_col0 + c] += group_bias[(m / group_rows) * group_cols + c],  c in [0, group_cols)
+ * It folds k3 = ffn3(context) + b3 (graphEncoders.py:149/169, one row per graph) into the K1 block of the node
+ * projections, so the GEMM emits U = fl(k3 + K1): the first broadcast add of Eq. (8) with the reference's rounding. */
+
 /* Exact-fp32 CUDA-core GEMM (FFMA, fp32 accumulate).  Any M,N; K % 4 == 0. */
 int digat_linear_f32(const float* A, int lda, const float* W, int ldw, const float* bias,
-                     float* C, int ldc, int M, int N, int K, int relu, void* stream);
+                     float* C, int ldc, int M, int N, int K, int relu,
+                     const float* group_bias, int group_rows, int group_col0, int group_cols, void* stream);
 
 /* Splits W into the two TF32 planes used by digat_linear_tf32x3: hi = rna_tf32(W), lo = rna_tf32(W - hi). */
 int digat_split_tf32(const float* W, float* W_hi, float* W_lo, int64_t count, void* stream);
@@ -54,24 +60,31 @@ int digat_split_tf32(const float* W, float* W_hi, float* W_lo, int64_t count, vo
  * Requires K % 4 == 0, N % 80 == 0, lda/ldw/ldc % 4 == 0.  Replaces the three node projections h, K1, K2 of one
  * layer as ONE GEMM against the stacked [3D, D] weight (graphEncoders.py:146-148 / 166-168). */
 int digat_linear_tf32x3(const float* A, int lda, const float* W_hi, const float* W_lo, int ldw,
-                        const float* bias, float* C, int ldc, int M, int N, int K, void* stream);
+                        const float* bias, float* C, int ldc, int M, int N, int K,
+                        const float* group_bias, int group_rows, int group_col0, int group_cols, void* stream);
 
 /* Tuning/experiment switch for digat_linear_tf32x3 tile variants (0 = default).  Not part of the reference path. */
 int digat_debug_set_gemm_variant(int variant);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Fused Eq. (8) graph-attention layer (replaces graphEncoders.py:150-153 / 170-173).
- *   P    [B*n, ldp]  node projections of this layer: columns [0,D) = h (bias included), [D,2D) = K1, [2D,3D) = K2
- *   k3   [B, D]      ffn3(context of the other graph) + bias          (graphEncoders.py:149 / 169)
+ *   P    [B*n, ldp]  node projections of this layer: columns [0,D) = h (bias included), [D,2D) = U = k3 + K1
+ *                    (k3 = ffn3(context of the other graph) + bias, folded in by the GEMM's row-group bias),
+ *                    [2D,3D) = K2
  *   a    [D]         attention vector                                  (news/user_graph_attention_a[i].weight)
  *   adj  [B, n, n]   bool adjacency, row i = query node, column j = neighbour
  *   X    [B, n, D]   layer input (residual)
- *   Y    [B, n, D]   out: relu(softmax_j(mask(leaky_relu(a . relu((k3 + K1_j) + K2_i)))) * h) + X
- *   alpha_out [B,n,n] optional (may be NULL): the softmax weights, saved for the backward pass.
- * The [B,n,n,D] broadcast tensor of the reference is never materialised.  n <= 128, D % 4 == 0, D <= 1024.
+ *   Y    [B, n, D]   out: relu(softmax_j(mask(leaky_relu(a . relu(U_j + K2_i)))) * h) + X
+ * Training extras (each may be NULL): drop_keep [B,n,n] bool keep-mask of the dropout on the attention weights
+ * (graphEncoders.py:152/172; the weights are multiplied by keep * drop_scale, drop_scale = 1/(1-p)); outputs saved
+ * for digat_graph_layer_bwd: score_out [B,n,n] raw scores s_ij, alpha_out [B,n,n] softmax weights before dropout,
+ * relu_mask_out [B,n,D] bool, 1 where the aggregated message (alpha~ h) is positive.
+ * The [B,n,n,D] broadcast tensor of the reference is never materialised: P tiles are streamed through shared memory
+ * by TMA (2-deep pipeline).  n <= 128, D % 4 == 0, D <= 1024.
  * --------------------------------------------------------------------------------------------------------- */
-int digat_graph_layer_fwd(const float* P, int ldp, const float* k3, const float* a, const uint8_t* adj,
-                          const float* X, float* Y, float* alpha_out, int B, int n, int D, void* stream);
+int digat_graph_layer_fwd(const float* P, int ldp, const float* a, const uint8_t* adj, const float* X, float* Y,
+                          int B, int n, int D, const uint8_t* drop_keep, float drop_scale, float* score_out,
+                          float* alpha_out, uint8_t* relu_mask_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Masked single-query attention pooling (replaces layers.py:199-206 after folding W_K into the query:
@@ -128,6 +141,43 @@ int digat_build_user_nodes(const float* table, int64_t n_table, const int32_t* h
 int digat_logits(const float* news_ctx, const float* user_ctx, float* logits, int B, int D, void* stream);
 /* y = x + y (fp32, count elements) -- context accumulation (graphEncoders.py:185-186,196-197) */
 int digat_add_inplace(const float* x, float* y, int64_t count, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Backward kernels (training; replace PyTorch autograd of the forward ops above).  The reference's autograd saves
+ * the [B,n,n,D] relu output of Eq. (8) per layer and graph; here its mask is recomputed from P.
+ * --------------------------------------------------------------------------------------------------------- */
+
+/* Backward of digat_graph_layer_fwd.
+ *   in : P, a, adj as in the forward; score, alpha (saved by the forward); drop_keep/drop_scale as in the forward;
+ *        G [B,n,D] = dY * relu_mask (the caller applies the saved relu mask; dX of the residual is dY itself)
+ *   out: dP [B*n, lddp] = dh | dU | dK2  (dk3 = sum over a graph's rows of dU: digat_groupsum);
+ *        da_partial [B, D] per-graph partial of the attention-vector gradient (digat_colsum over B finishes it). */
+int digat_graph_layer_bwd(const float* P, int ldp, const float* a, const uint8_t* adj, const float* score,
+                          const float* alpha, const uint8_t* drop_keep, float drop_scale, const float* G,
+                          float* dP, int lddp, float* da_partial, int B, int n, int D, void* stream);
+
+/* Backward of digat_attention_pool_fwd.  alpha [B,m] saved by the forward; dout [B, ldg].
+ * out: dF [B,m,D] dense (w.r.t. F; masked by F > 0 when resid_F is given), dresid [B,m,D] (only with resid_F),
+ *      dv [B,D]. */
+int digat_attention_pool_bwd(const float* F, int64_t strideF, int ldf, const float* resid_F, const float* v,
+                             const uint8_t* mask, const float* alpha, const float* dout, int ldg,
+                             float* dF, float* dresid, float* dv, int B, int m, int D, void* stream);
+
+/* Backward of digat_topic_segment_fwd.  alpha [B,H] saved by the forward; dT [B,n_seg,D].
+ * out: dXu [B,n_u,D] (rows >= H are written as zeros: topic nodes are not pooled), dv [B,D]. */
+int digat_topic_segment_bwd(const float* Xu, int64_t strideX, const float* v, const int64_t* cidx,
+                            const float* alpha, const float* dT, float* dXu, float* dv,
+                            int B, int H, int n_seg, int n_u, int D, void* stream);
+
+/* Weight gradient of C = A W^T: dW[N,K] = dC[M,N]^T A[M,K] (exact fp32, deterministic split reduction over M).
+ * workspace: digat_reduce_workspace_floats(M, N, K) floats. */
+int digat_reduce_workspace_floats(int M, int N, int K, int64_t* floats);
+int digat_linear_wgrad(const float* dC, int lddc, const float* A, int lda, float* dW, float* workspace,
+                       int M, int N, int K, void* stream);
+/* out[n] = sum_m in[m, n] (bias gradients); workspace: digat_reduce_workspace_floats(M, N, 1) floats. */
+int digat_colsum(const float* in, int ld, float* out, float* workspace, int M, int N, void* stream);
+/* out[g, c] = sum_{r < rows} in[(g*rows + r), col0 + c] -- gradient of the GEMMs' row-group bias (dk3). */
+int digat_groupsum(const float* in, int ld, float* out, int groups, int rows, int col0, int cols, void* stream);
 
 #ifdef __cplusplus
 }

@@ -23,7 +23,8 @@ def _tf32x3(A, W, bias, lda=None):
     hi, lo = _split(W)
     C = torch.full((M, N), float('nan'), device=A.device)
     _lib.call('digat_linear_tf32x3', A.data_ptr(), lda or A.stride(0), hi.data_ptr(), lo.data_ptr(), W.stride(0),
-              0 if bias is None else bias.data_ptr(), C.data_ptr(), N, M, N, K, torch.cuda.current_stream().cuda_stream)
+              0 if bias is None else bias.data_ptr(), C.data_ptr(), N, M, N, K, 0, 1, 0, 0,
+              torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     return C
 
@@ -65,7 +66,25 @@ def test_tf32x3_strided_A_and_no_bias():
     hi, lo = _split(W)
     C = torch.empty(300, 400, device='cuda')
     _lib.call('digat_linear_tf32x3', X.data_ptr(), 4000, hi.data_ptr(), lo.data_ptr(), 400, 0, C.data_ptr(), 400,
-              300, 400, 400, torch.cuda.current_stream().cuda_stream)
+              300, 400, 400, 0, 1, 0, 0, torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     ref = X[:, 0, :].double().cpu() @ W.double().cpu().t()
     assert rel_err(C.cpu().numpy(), ref.numpy()) < 2e-6
+
+
+@pytest.mark.parametrize('M,n', [(680, 68), (100, 10), (5440, 68)])
+def test_group_bias_folds_k3_into_K1_block(M, n):
+    """U = fl(k3 + K1): the row-group bias of both GEMMs (tensor-core path for M >= 256, CUDA-core path below)."""
+    from digat_b200.graphEncoders import PackedWeight, linear
+    g = torch.Generator().manual_seed(M)
+    D = 400
+    X = torch.randn(M, D, generator=g).cuda()
+    W = (torch.randn(3 * D, D, generator=g) * 0.05).cuda()
+    bias = torch.randn(3 * D, generator=g).cuda()
+    k3 = torch.randn(M // n, D, generator=g).cuda()
+    base = linear(X, PackedWeight(W), bias)
+    out = linear(X, PackedWeight(W), bias, group_bias=k3, group_rows=n, group_col0=D)
+    torch.cuda.synchronize()
+    expect = base.clone()
+    expect[:, D:2 * D] = base[:, D:2 * D] + k3.repeat_interleave(n, 0)       # exactly one fp32 add
+    assert torch.equal(out, expect)
