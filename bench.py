@@ -134,11 +134,16 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--cpu-budget', type=float, default=12.0, help='seconds of CPU-oracle timing for cpu_baseline')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--mode', default='score', choices=['score', 'train'],
+                    help="'score' = the headline metric; 'train' = fwd+bwd(+DDP all-reduce)+Adam step, samples/s")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
 
     if args.impl == 'reference':
         run_reference_arm(args)
+        return
+    if args.mode == 'train':
+        run_train(args)
         return
 
     rank = int(os.environ.get('RANK', '0'))
@@ -271,6 +276,106 @@ def main():
                                     'sample': '%d calls x 64 pairs of the same workload (%.1f s of CPU work), '
                                               'oracle/digat_oracle.py inference, torch CPU fp32' % (n, n * sec)}
         print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def run_train(args):
+    """BASELINE.json configs[2]: DIGAT training fwd+bwd on synthetic MIND-shaped batches, per-GPU batch = 64 behaviours
+    x (1 + 4 negatives) = 320 rows (reference config.py:31,34), dropout 0.2, DDP gradient all-reduce over NCCL when
+    launched with N>1 ranks, clip-norm 1 + Adam step as reference trainer.py:98-105.  News-encoder excluded."""
+    import torch.nn.functional as F
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        torch.distributed.init_process_group('nccl', device_id=dev)
+    from digat_b200 import _lib, synth
+    from digat_b200.graphEncoders import DIGAT
+    from digat_b200.model import Model
+    _lib.require_device(local_rank)
+    N, hops, L = WORKLOADS[args.workload][:3]
+    cfg = synth.make_config(SAG_neighbors=N, SAG_hops=hops, graph_depth=L, dropout_rate=0.2)
+    sd = synth.make_state_dict(cfg, D=D, seed=0)
+    corpus = synth.make_corpus(cfg, D=D, n_news=20000, n_behaviors=4096, mean_candidates=8.0, seed=rank)
+    model = Model(cfg, D)
+    model.graph_encoder.load_state_dict(sd)
+    model = model.to(dev).train()
+    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank]) if world > 1 else model
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    bs, news_num = 64, 5
+    rng = np.random.Generator(np.random.PCG64(rank))
+    emb = torch.from_numpy(corpus.news_embeddings).to(dev)
+    node = torch.from_numpy(corpus.news_node_ID.astype(np.int64)).to(dev)
+    ng, nm = torch.from_numpy(corpus.news_graph).to(dev), torch.from_numpy(corpus.news_graph_mask).to(dev)
+    hist = torch.from_numpy(corpus.history.astype(np.int64)).to(dev)
+    ug, cm, ci = (torch.from_numpy(x).to(dev) for x in (corpus.user_graph, corpus.user_category_mask, corpus.user_category_indices))
+
+    def make_step_inputs():
+        beh = torch.from_numpy(rng.integers(0, hist.shape[0], size=bs)).to(dev)
+        cand = torch.from_numpy(rng.integers(1, emb.shape[0], size=(bs, news_num))).to(dev)
+        return (emb[hist[beh]], ug[beh], cm[beh], ci[beh], emb[node[cand]], ng[cand], nm[cand])
+
+    def step(inp):
+        logits = net.forward_embeddings(*inp) if world == 1 else net.module.forward_embeddings(*inp)
+        loss = (-F.log_softmax(logits, dim=1).select(1, 0)).mean()
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        return loss
+
+    if world > 1:
+        # DDP hooks fire on the wrapped module's forward: route forward_embeddings through it
+        class _Fwd(torch.nn.Module):
+            def __init__(self, m):
+                super().__init__()
+                self.m = m
+
+            def forward(self, *a):
+                return self.m.forward_embeddings(*a)
+        fwd = torch.nn.parallel.DistributedDataParallel(_Fwd(model), device_ids=[local_rank])
+
+        def step(inp):  # noqa: F811
+            logits = fwd(*inp)
+            loss = (-F.log_softmax(logits, dim=1).select(1, 0)).mean()
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+            opt.step()
+            return loss
+
+    inputs = [make_step_inputs() for _ in range(args.warmup + args.steps)]
+    for s_ in range(args.warmup):
+        step(inputs[s_])
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    _lib.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s_ in range(args.warmup, args.warmup + args.steps):
+        loss = step(inputs[s_])
+    e1.record()
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t.item())
+    if rank == 0:
+        print(json.dumps({
+            'metric': 'train_samples_per_sec', 'value': world * args.steps * bs / (ms * 1e-3), 'unit': 'samples/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': args.workload + ':train', 'behaviours_per_gpu': bs, 'candidates': news_num,
+                       'rows_per_gpu': bs * news_num, 'dropout': 0.2, 'optimizer': 'Adam + clip_grad_norm 1',
+                       'parallelism': 'DDP x%d, NCCL gradient all-reduce' % world},
+            'gpu_launches': _lib.launch_count(), 'final_loss': float(loss)}))
     if world > 1:
         torch.distributed.destroy_process_group()
 
