@@ -68,7 +68,10 @@ struct TcCfg {
     static constexpr int A_BYTES = BM * kTcBK * 4;             // one plane of the A tile
     static constexpr int W_BYTES = BN * kTcBK * 4;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
-    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
+    // BN = 128 is the two-CTAs-per-SM configuration (256 TMEM columns and <= 110 KB of smem each): one CTA's prologue /
+    // epilogue overlaps the other's main loop.  The other widths own the SM (up to 512 TMEM columns, ~200 KB).
+    static constexpr int SMEM_BUDGET = (BN == 128 ? 108 : 200) * 1024;
+    static constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES > 6 ? 6 : SMEM_BUDGET / STAGE_BYTES;
     static constexpr int ACC_COLS = MH * BN * (SPLIT ? 2 : 1);
     static constexpr int TMEM_COLS = (ACC_COLS <= 32) ? 32 : (ACC_COLS <= 64) ? 64 : (ACC_COLS <= 128) ? 128
                                      : (ACC_COLS <= 256) ? 256 : 512;
@@ -80,7 +83,7 @@ struct TcCfg {
 };
 
 template <int BN, int MH, bool SPLIT>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kTcThreads, BN == 128 ? 2 : 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_whi,
                    const __grid_constant__ CUtensorMap map_wlo, const float* __restrict__ bias,
                    float* __restrict__ C, int ldc, int M, int N, int K, GroupBias gb) {
@@ -97,6 +100,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * BN, m0 = blockIdx.y * Cfg::BM;
     const int nkb = (K + kTcBK - 1) / kTcBK;
+    __shared__ float bias_s[BN];
+    for (int i = threadIdx.x; i < BN; i += kTcThreads) bias_s[i] = (bias != nullptr && n0 + i < N) ? bias[n0 + i] : 0.f;
 
     auto a_hi = [&](int s) { return smem + (size_t)s * Cfg::STAGE_BYTES; };
     auto a_lo = [&](int s) { return smem + (size_t)s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
@@ -191,54 +196,64 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
             mbar_arrive(&ready[s]);
         }
-        // epilogue: this warp may touch TMEM lanes [32*(warp%4), +32)
+        // epilogue: this warp may touch TMEM lanes [32*(warp%4), +32).  Software-pipelined over 16-column groups: the
+        // TMEM loads (and the row-group-bias loads) of group c+1 are in flight while group c is finished and stored.
         mbar_wait(accum_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q = warp & 3;
+        const bool has_gb = gb.ptr != nullptr;
 #pragma unroll
         for (int h = 0; h < MH; ++h) {
             const int m = m0 + h * 128 + q * 32 + lane;
+            const bool row_ok = m < M;
             float* crow = C + (size_t)m * ldc + n0;
-            const float* grow = gb.ptr != nullptr ? gb.ptr + (size_t)(m / gb.rows) * gb.cols - gb.col0 + n0 : nullptr;
-#pragma unroll 1
-            for (int c = 0; c < BN; c += 16) {
-                uint32_t r[16];
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * BN + c);
+            const float* grow = (has_gb && row_ok) ? gb.ptr + (size_t)(m / gb.rows) * gb.cols - gb.col0 + n0 : nullptr;
+            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * BN);
+            uint32_t rm[16], rc[16];
+            float4 gq[4];
+            auto issue_group = [&](int c) {
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                    : "r"(taddr));
+                    : "=r"(rm[0]), "=r"(rm[1]), "=r"(rm[2]), "=r"(rm[3]), "=r"(rm[4]), "=r"(rm[5]), "=r"(rm[6]), "=r"(rm[7]),
+                      "=r"(rm[8]), "=r"(rm[9]), "=r"(rm[10]), "=r"(rm[11]), "=r"(rm[12]), "=r"(rm[13]), "=r"(rm[14]), "=r"(rm[15])
+                    : "r"(tbase + (uint32_t)c));
                 if (SPLIT) {
-                    uint32_t r2[16];
-                    const uint32_t taddr2 = taddr + (uint32_t)(MH * BN);
                     asm volatile(
                         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                        : "=r"(r2[0]), "=r"(r2[1]), "=r"(r2[2]), "=r"(r2[3]), "=r"(r2[4]), "=r"(r2[5]), "=r"(r2[6]), "=r"(r2[7]),
-                          "=r"(r2[8]), "=r"(r2[9]), "=r"(r2[10]), "=r"(r2[11]), "=r"(r2[12]), "=r"(r2[13]), "=r"(r2[14]), "=r"(r2[15])
-                        : "r"(taddr2));
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
+                        : "=r"(rc[0]), "=r"(rc[1]), "=r"(rc[2]), "=r"(rc[3]), "=r"(rc[4]), "=r"(rc[5]), "=r"(rc[6]), "=r"(rc[7]),
+                          "=r"(rc[8]), "=r"(rc[9]), "=r"(rc[10]), "=r"(rc[11]), "=r"(rc[12]), "=r"(rc[13]), "=r"(rc[14]), "=r"(rc[15])
+                        : "r"(tbase + (uint32_t)(MH * BN + c)));
                 }
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (m < M) {
 #pragma unroll
-                    for (int v4 = 0; v4 < 4; ++v4) {
-                        float4 o;
-                        o.x = __uint_as_float(r[v4 * 4 + 0]); o.y = __uint_as_float(r[v4 * 4 + 1]);
-                        o.z = __uint_as_float(r[v4 * 4 + 2]); o.w = __uint_as_float(r[v4 * 4 + 3]);
-                        if (bias != nullptr) {
-                            const float4 bv = *reinterpret_cast<const float4*>(bias + n0 + c + v4 * 4);
-                            o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
-                        }
-                        const int col = n0 + c + v4 * 4;      // col0 and cols are multiples of 4: a quad is in or out
-                        if (grow != nullptr && col >= gb.col0 && col < gb.col0 + gb.cols) {
-                            const float4 gv = *reinterpret_cast<const float4*>(grow + c + v4 * 4);
-                            o.x += gv.x; o.y += gv.y; o.z += gv.z; o.w += gv.w;
-                        }
-                        *reinterpret_cast<float4*>(crow + c + v4 * 4) = o;
-                    }
+                for (int v4 = 0; v4 < 4; ++v4) {
+                    const int col = n0 + c + v4 * 4;       // col0 / cols are multiples of 4: a quad is entirely in or out
+                    gq[v4] = (grow != nullptr && col >= gb.col0 && col < gb.col0 + gb.cols)
+                                 ? *reinterpret_cast<const float4*>(grow + c + v4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            };
+            issue_group(0);
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 16) {
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                float o[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float v = __uint_as_float(rm[i]);
+                    if (SPLIT) v += __uint_as_float(rc[i]);          // main + correction accumulators (IEEE add)
+                    o[i] = v + bias_s[c + i];
+                }
+#pragma unroll
+                for (int v4 = 0; v4 < 4; ++v4) {
+                    o[v4 * 4 + 0] += gq[v4].x; o[v4 * 4 + 1] += gq[v4].y;
+                    o[v4 * 4 + 2] += gq[v4].z; o[v4 * 4 + 3] += gq[v4].w;
+                }
+                if (c + 16 < BN) issue_group(c + 16);                // next group's loads overlap these stores
+                if (row_ok) {
+#pragma unroll
+                    for (int v4 = 0; v4 < 4; ++v4)
+                        if (n0 + c + v4 * 4 < N)             // N % 4 == 0; the last N tile may be partial (TMA zero-fills W)
+                            *reinterpret_cast<float4*>(crow + c + v4 * 4) =
+                            make_float4(o[v4 * 4 + 0], o[v4 * 4 + 1], o[v4 * 4 + 2], o[v4 * 4 + 3]);
                 }
             }
         }
@@ -272,7 +287,7 @@ inline int launch_tf32x3_cfg(const float* A, int lda, const float* W_hi, const f
     if ((rc = make_tensor_map_2d(&mh, W_hi, N, K, ldw, BN, kTcBK, CU_TENSOR_MAP_SWIZZLE_64B)) != DIGAT_OK) return rc;
     if ((rc = make_tensor_map_2d(&ml, W_lo, N, K, ldw, BN, kTcBK, CU_TENSOR_MAP_SWIZZLE_64B)) != DIGAT_OK) return rc;
     DIGAT_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, MH, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-    dim3 grid(N / BN, (M + Cfg::BM - 1) / Cfg::BM);
+    dim3 grid((N + BN - 1) / BN, (M + Cfg::BM - 1) / Cfg::BM);
     gemm_tf32x3_kernel<BN, MH, SPLIT><<<grid, kTcThreads, Cfg::SMEM, st>>>(ma, mh, ml, bias, C, ldc, M, N, K, gb);
     return check_launch("digat_linear_tf32x3");
 }
@@ -291,12 +306,16 @@ inline int launch_linear_tf32x3(const float* A, int lda, const float* W_hi, cons
     DIGAT_REQUIRE(lda >= K && ldw >= K && ldc >= N, "digat_linear_tf32x3: leading dimension too small");
     DIGAT_REQUIRE(aligned16(A) && aligned16(W_hi) && aligned16(W_lo) && aligned16(C) && (!bias || aligned16(bias)),
                   "digat_linear_tf32x3: pointers must be 16-byte aligned");
-    DIGAT_REQUIRE(N % 80 == 0, "digat_linear_tf32x3: N=%d must be a multiple of 80 (tile widths 80/160/240)", N);
+    DIGAT_REQUIRE(N % 16 == 0, "digat_linear_tf32x3: N=%d must be a multiple of 16", N);
     if (M == 0) return DIGAT_OK;
     // variant 0 (default): one 128-row half per CTA, separate main / correction accumulators (most accurate);
     // variant 1: two halves per CTA for M > 16384, single accumulator (half the W traffic per flop, less accurate).
     const int variant = g_tc_variant;
     const bool big = M > 16384;
+    // small problems (few tiles) and odd widths: 128-wide tiles, two CTAs per SM (measured 1.45x faster at M = 4096);
+    // the last N tile may be partial.  Large M keeps the 240-wide tile (fewer re-reads of A: measured 185 vs 158 TFLOP/s).
+    if (variant == 2 || N % 80 != 0 || (variant == 0 && !big))
+        return launch_tf32x3_cfg<128, 1, true>(A, lda, W_hi, W_lo, ldw, bias, C, ldc, M, N, K, gb, st);
 #define DIGAT_TC_DISPATCH(BN_)                                                                                      \
     do {                                                                                                            \
         if (variant == 1 && big) return launch_tf32x3_cfg<BN_, 2, false>(A, lda, W_hi, W_lo, ldw, bias, C, ldc, M, N, K, gb, st); \
