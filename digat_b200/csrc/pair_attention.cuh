@@ -282,9 +282,12 @@ graph_layer_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
             const int i0 = ib * 8;
             const float* Hs = Hs0 + (size_t)r * n * g.dc3 + 4 * q;
             const float* S = St + (size_t)r * n * g.lds + i0;
-            uint64_t o[8][2];
+            // outer product alpha[8 rows] x h[4 features] with packed fp32x2 FMAs and only 4 register moves per j:
+            // row pair (a_k, a_k+1) times the feature pair (h0,h1) gives o[k][0], o[k+1][1]; times the SWAPPED pair
+            // (h1,h0) it gives o[k][1], o[k+1][0].  od = "diagonal" accumulators, ox = "crossed" accumulators.
+            uint64_t od[4][2], ox[4][2];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) o[k][0] = o[k][1] = 0ull;
+            for (int k = 0; k < 4; ++k) od[k][0] = od[k][1] = ox[k][0] = ox[k][1] = 0ull;
 #pragma unroll 2
             for (int j = 0; j < n; ++j) {
                 const float4 h = *reinterpret_cast<const float4*>(Hs);
@@ -293,31 +296,40 @@ graph_layer_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
                 Hs += g.dc3;
                 S += g.lds;
                 const uint64_t h01 = pack2(h.x, h.y), h23 = pack2(h.z, h.w);
-                const float al[8] = {al0.x, al0.y, al0.z, al0.w, al1.x, al1.y, al1.z, al1.w};
+                const uint64_t h10 = pack2(h.y, h.x), h32 = pack2(h.w, h.z);
+                const uint64_t ap[4] = {pack2(al0.x, al0.y), pack2(al0.z, al0.w), pack2(al1.x, al1.y), pack2(al1.z, al1.w)};
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const uint64_t aa = pack2(al[k], al[k]);
-                    o[k][0] = fma2(aa, h01, o[k][0]);
-                    o[k][1] = fma2(aa, h23, o[k][1]);
+                for (int k = 0; k < 4; ++k) {
+                    od[k][0] = fma2(ap[k], h01, od[k][0]);      // (a_2k   h0, a_2k+1 h1)
+                    ox[k][0] = fma2(ap[k], h10, ox[k][0]);      // (a_2k   h1, a_2k+1 h0)
+                    od[k][1] = fma2(ap[k], h23, od[k][1]);      // (a_2k   h2, a_2k+1 h3)
+                    ox[k][1] = fma2(ap[k], h32, ox[k][1]);      // (a_2k   h3, a_2k+1 h2)
                 }
             }
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int i = i0 + k;
-                if (i < n) {
-                    const size_t off = ((size_t)(b0 + r) * n + i) * D + c0 + 4 * q;
-                    const float4 x = ldg_stream(reinterpret_cast<const float4*>(p.X + off));
-                    float4 y;
-                    unpack2(o[k][0], y.x, y.y);
-                    unpack2(o[k][1], y.z, y.w);
-                    if (p.relu_mask_out != nullptr)
-                        *reinterpret_cast<uchar4*>(p.relu_mask_out + off) =
-                            make_uchar4(y.x > 0.f, y.y > 0.f, y.z > 0.f, y.w > 0.f);
-                    y.x = fmaxf(y.x, 0.f) + x.x;
-                    y.y = fmaxf(y.y, 0.f) + x.y;
-                    y.z = fmaxf(y.z, 0.f) + x.z;
-                    y.w = fmaxf(y.w, 0.f) + x.w;
-                    stg_stream(reinterpret_cast<float4*>(p.Y + off), y);
+            for (int k = 0; k < 4; ++k) {
+                float d0, d1, d2, d3, x0, x1, x2, x3;
+                unpack2(od[k][0], d0, d1);      // row 2k: h0 ; row 2k+1: h1
+                unpack2(ox[k][0], x0, x1);      // row 2k: h1 ; row 2k+1: h0
+                unpack2(od[k][1], d2, d3);      // row 2k: h2 ; row 2k+1: h3
+                unpack2(ox[k][1], x2, x3);      // row 2k: h3 ; row 2k+1: h2
+                const float4 rowv[2] = {make_float4(d0, x0, d2, x2), make_float4(x1, d1, x3, d3)};
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int i = i0 + 2 * k + e;
+                    if (i < n) {
+                        const size_t off = ((size_t)(b0 + r) * n + i) * D + c0 + 4 * q;
+                        const float4 x = ldg_stream(reinterpret_cast<const float4*>(p.X + off));
+                        float4 y = rowv[e];
+                        if (p.relu_mask_out != nullptr)
+                            *reinterpret_cast<uchar4*>(p.relu_mask_out + off) =
+                                make_uchar4(y.x > 0.f, y.y > 0.f, y.z > 0.f, y.w > 0.f);
+                        y.x = fmaxf(y.x, 0.f) + x.x;
+                        y.y = fmaxf(y.y, 0.f) + x.y;
+                        y.z = fmaxf(y.z, 0.f) + x.z;
+                        y.w = fmaxf(y.w, 0.f) + x.w;
+                        stg_stream(reinterpret_cast<float4*>(p.Y + off), y);
+                    }
                 }
             }
         }
