@@ -193,6 +193,7 @@ struct SegArgs {
     float* alpha_out;                     // optional [B, H]
     int B, H, n_seg, D;
     int* err_flag;                        // device int, set to 1 when a segment id is out of range
+    const int32_t* src_index;             // optional [B]: row b reads Xu and cidx of row src_index[b] (shared user graphs)
 };
 
 __global__ void __launch_bounds__(kCtxThreads)
@@ -205,9 +206,10 @@ topic_segment_fwd_kernel(SegArgs p) {
     __shared__ int s_start[kCtxMaxItems + 1];
     const int b = blockIdx.x, tid = threadIdx.x;
     const int H = p.H, D = p.D, nq = D >> 2, n_seg = p.n_seg;
-    const float* Xh = p.Xu + (size_t)b * p.strideX;
+    const size_t src = p.src_index != nullptr ? (size_t)p.src_index[b] : (size_t)b;
+    const float* Xh = p.Xu + src * p.strideX;
     if (tid < H) {
-        const int64_t c = p.cidx[(size_t)b * H + tid];
+        const int64_t c = p.cidx[src * H + tid];
         int ci = (int)c;
         if (c < 0 || c >= n_seg) { ci = n_seg - 1; if (p.err_flag) atomicExch(p.err_flag, 1); }
         s_seg[tid] = ci;
@@ -262,7 +264,8 @@ topic_segment_fwd_kernel(SegArgs p) {
 }
 
 inline int launch_topic_segment_fwd(const float* Xu, int64_t strideX, const float* v, const int64_t* cidx, float* T,
-                                    float* alpha_out, int32_t* err_flag, int B, int H, int n_seg, int D, cudaStream_t st) {
+                                    float* alpha_out, int32_t* err_flag, const int32_t* src_index, int B, int H, int n_seg, int D,
+                                    cudaStream_t st) {
     DIGAT_REQUIRE(Xu && v && cidx && T, "digat_topic_segment_fwd: null pointer");
     DIGAT_REQUIRE(H >= 1 && H <= kCtxMaxItems && n_seg >= 1 && n_seg <= kCtxMaxItems,
                   "digat_topic_segment_fwd: H=%d / n_seg=%d outside [1,%d]", H, n_seg, kCtxMaxItems);
@@ -270,7 +273,7 @@ inline int launch_topic_segment_fwd(const float* Xu, int64_t strideX, const floa
     DIGAT_REQUIRE((strideX & 3) == 0 && aligned16(Xu) && aligned16(v) && aligned16(T),
                   "digat_topic_segment_fwd: pointers/strides must be 16-byte aligned");
     if (B <= 0) return DIGAT_OK;
-    SegArgs a{Xu, strideX, v, cidx, T, alpha_out, B, H, n_seg, D, err_flag};
+    SegArgs a{Xu, strideX, v, cidx, T, alpha_out, B, H, n_seg, D, err_flag, src_index};
     topic_segment_fwd_kernel<<<B, kCtxThreads, 0, st>>>(a);
     return check_launch("digat_topic_segment_fwd");
 }

@@ -62,9 +62,10 @@ int digat_debug_set_gemm_variant(int variant) {
 
 int digat_graph_layer_fwd(const float* P, int ldp, const float* a, const uint8_t* adj, const float* X, float* Y,
                           int B, int n, int D, const uint8_t* drop_keep, float drop_scale, float* score_out,
-                          float* alpha_out, uint8_t* relu_mask_out, void* stream) {
+                          float* alpha_out, uint8_t* relu_mask_out, const int32_t* px_index, int n_src,
+                          const int32_t* adj_index, const float* k3, void* stream) {
     return launch_graph_layer_fwd(P, ldp, a, adj, X, Y, B, n, D, drop_keep, drop_scale, score_out, alpha_out,
-                                  relu_mask_out, as_stream(stream));
+                                  relu_mask_out, px_index, n_src, adj_index, k3, as_stream(stream));
 }
 
 int digat_attention_pool_fwd(const float* F, int64_t strideF, int ldf, const float* resid_F, const float* v,
@@ -80,8 +81,10 @@ int digat_news_gate_fwd(const float* z, const float* lg, const float* ctx_in, fl
 }
 
 int digat_topic_segment_fwd(const float* Xu, int64_t strideX, const float* v, const int64_t* cidx, float* T,
-                            float* alpha_out, int32_t* err_flag, int B, int H, int n_seg, int D, void* stream) {
-    return launch_topic_segment_fwd(Xu, strideX, v, cidx, T, alpha_out, err_flag, B, H, n_seg, D, as_stream(stream));
+                            float* alpha_out, int32_t* err_flag, const int32_t* src_index, int B, int H, int n_seg,
+                            int D, void* stream) {
+    return launch_topic_segment_fwd(Xu, strideX, v, cidx, T, alpha_out, err_flag, src_index, B, H, n_seg, D,
+                                    as_stream(stream));
 }
 
 int digat_gather_rows_i32(const float* table, int64_t n_table, const int32_t* idx, float* out, int64_t ldo,

@@ -52,6 +52,11 @@ struct PairAttnArgs {
     float* score_out;           // [B,n,n] raw Eq.(8) scores s_ij (their sign selects the leaky-relu slope)
     float* alpha_out;           // [B,n,n] softmax weights BEFORE dropout
     uint8_t* relu_mask_out;     // [B,n,D] 1 where (alpha~ h) > 0
+    // de-duplicated scoring (all optional): many pairs of one impression share the user graph, so layer 0 of the
+    // user graph is projected once per behaviour and every pair reads it through an index
+    const int32_t* px_index;    // [B] graph b reads P and X of graph px_index[b] (P then holds K1 WITHOUT k3)
+    const int32_t* adj_index;   // [B] graph b reads adj of graph adj_index[b]
+    const float* k3;            // [B,D] added to the staged U tile in-kernel: U = fl(K1 + k3), same rounding as the GEMM path
 };
 
 __device__ __forceinline__ uint64_t pack2(float lo, float hi) {
@@ -84,11 +89,13 @@ graph_layer_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
     const int b0 = blockIdx.x * R;
     const int Rv = min(R, p.B - b0);                 // graphs actually present in this CTA
     const int rows = R * n;                          // rows of a staged tile (TMA zero-fills rows past B*n)
+    const int src0 = p.px_index != nullptr ? p.px_index[b0] : b0;      // indexed mode runs with R == 1
 
     const int half = 2 * g.tile_floats;              // floats per pipeline buffer
     float* buf0 = reinterpret_cast<float*>(sbase);   // [2][half]   (128-byte aligned: TMA destination)
     float* a_s = buf0 + 2 * half;                    // [D]
-    float* St = a_s + D;                             // [R][n][lds]   St[r][j*lds + i]
+    float* k3_s = a_s + D;                           // [D] (indexed mode only; zero-sized region otherwise is still reserved)
+    float* St = k3_s + D;                            // [R][n][lds]   St[r][j*lds + i]
     uint64_t* full = reinterpret_cast<uint64_t*>(St + (size_t)R * n * g.lds);   // [2] TMA barriers (8-byte aligned)
 
     if (tid == 0) {
@@ -96,8 +103,11 @@ graph_layer_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
         mbar_init(&full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < D / 4; i += kPairThreads)
+    for (int i = tid; i < D / 4; i += kPairThreads) {
         reinterpret_cast<float4*>(a_s)[i] = reinterpret_cast<const float4*>(p.a)[i];
+        if (p.k3 != nullptr)
+            reinterpret_cast<float4*>(k3_s)[i] = reinterpret_cast<const float4*>(p.k3 + (size_t)b0 * D)[i];
+    }
     __syncthreads();
 
     // unified load schedule: loads 0..nch1-1 are phase-1 chunks (U + K2 tiles), nch1.. are phase-3 chunks (h tile);
@@ -107,11 +117,11 @@ graph_layer_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
         float* dst = buf0 + (l & 1) * half;
         if (l < g.nch1) {
             mbar_arrive_expect_tx(&full[l & 1], 2u * rows * g.dc * 4u);
-            tma_load_2d(dst, &map1, &full[l & 1], D + l * g.dc, b0 * n);                       // U  = k3 + K1
-            tma_load_2d(dst + g.tile_floats, &map1, &full[l & 1], 2 * D + l * g.dc, b0 * n);   // K2
+            tma_load_2d(dst, &map1, &full[l & 1], D + l * g.dc, src0 * n);                     // U  = k3 + K1
+            tma_load_2d(dst + g.tile_floats, &map1, &full[l & 1], 2 * D + l * g.dc, src0 * n); // K2
         } else {
             mbar_arrive_expect_tx(&full[l & 1], (uint32_t)rows * g.dc3 * 4u);
-            tma_load_2d(dst, &map3, &full[l & 1], (l - g.nch1) * g.dc3, b0 * n);               // h
+            tma_load_2d(dst, &map3, &full[l & 1], (l - g.nch1) * g.dc3, src0 * n);             // h
         }
     };
     if (tid == 0) {
@@ -131,6 +141,18 @@ graph_layer_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
         const int c0 = l * g.dc;
         const int wq = min(g.dc, D - c0) >> 2;
         mbar_wait(&full[l & 1], (uint32_t)(l >> 1) & 1u);
+        if (p.k3 != nullptr) {                        // indexed mode: the shared K1 tile becomes this pair's U tile
+            float* Ut = buf0 + (l & 1) * half;
+            for (int it = tid; it < n * wq; it += kPairThreads) {
+                const int row = it / wq, q = it - row * wq;
+                float4* u = reinterpret_cast<float4*>(Ut + row * g.dc + 4 * q);
+                const float4 k = *reinterpret_cast<const float4*>(k3_s + c0 + 4 * q);
+                float4 v = *u;
+                v.x = k.x + v.x; v.y = k.y + v.y; v.z = k.z + v.z; v.w = k.w + v.w;
+                *u = v;
+            }
+            __syncthreads();
+        }
         for (int t = tid; t < tiles; t += kPairThreads) {
             const int r = t / tiles_per_graph, tt = t - r * tiles_per_graph;
             const int ti = tt / nt, tj = tt - ti * nt;
@@ -222,7 +244,8 @@ graph_layer_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
     for (int row = warp; row < Rv * n; row += kPairThreads / 32) {
         const int r = row / n, i = row - r * n;
         float* S = St + (size_t)r * n * g.lds;
-        const uint8_t* adj = p.adj + ((size_t)(b0 + r) * n + i) * n;
+        const size_t ag = p.adj_index != nullptr ? (size_t)p.adj_index[b0 + r] : (size_t)(b0 + r);
+        const uint8_t* adj = p.adj + (ag * n + i) * n;
         float v[kPairMaxNodes / 32];
         float mx = -INFINITY;
 #pragma unroll
@@ -319,7 +342,8 @@ graph_layer_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
                     const int i = i0 + 2 * k + e;
                     if (i < n) {
                         const size_t off = ((size_t)(b0 + r) * n + i) * D + c0 + 4 * q;
-                        const float4 x = ldg_stream(reinterpret_cast<const float4*>(p.X + off));
+                        const size_t xoff = p.px_index != nullptr ? ((size_t)src0 * n + i) * D + c0 + 4 * q : off;
+                        const float4 x = ldg_stream(reinterpret_cast<const float4*>(p.X + xoff));
                         float4 y = rowv[e];
                         if (p.relu_mask_out != nullptr)
                             *reinterpret_cast<uchar4*>(p.relu_mask_out + off) =
@@ -339,7 +363,7 @@ graph_layer_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
 }
 
 // Host-side geometry: graphs per CTA and chunk widths for (n, D) under a shared-memory budget.
-inline void pair_attn_geometry(int n, int D, int B, PairAttnGeom* g) {
+inline void pair_attn_geometry(int n, int D, int B, bool indexed, PairAttnGeom* g) {
     const int nt = (n + 3) / 4;
     const int tiles = nt * nt;
     int dc = 68;                                   // 68/4 = 17 (odd): consecutive dense rows start 4 banks apart
@@ -347,11 +371,11 @@ inline void pair_attn_geometry(int n, int D, int B, PairAttnGeom* g) {
     const int lds = ((n + 7) / 8) * 8 + 4;         // multiple of 4; +4 shifts consecutive j by 4 banks
     auto tile_floats = [&](int R) { return ((R * n * dc * 4 + 127) / 128) * 128 / 4; };
     auto smem_of = [&](int R) {
-        return (size_t)128 + (size_t)4 * tile_floats(R) * 4 + (size_t)D * 4 + (size_t)R * n * lds * 4 + 16;
+        return (size_t)4 * tile_floats(R) * 4 + (size_t)2 * D * 4 + (size_t)R * n * lds * 4 + 16;
     };
     const size_t budget = 110 * 1024;              // two CTAs per SM
     int R = kPairThreads / tiles;
-    if (R < 1) R = 1;
+    if (R < 1 || indexed) R = 1;
     while (R > 1 && (smem_of(R) > budget || R * n > 256)) --R;      // TMA box: at most 256 rows
     if (R > B) R = B > 0 ? B : 1;
     g->R = R; g->nt = nt; g->dc = dc; g->nch1 = (D + dc - 1) / dc; g->dc3 = 2 * dc;
@@ -360,24 +384,30 @@ inline void pair_attn_geometry(int n, int D, int B, PairAttnGeom* g) {
 
 inline int launch_graph_layer_fwd(const float* P, int ldp, const float* a, const uint8_t* adj, const float* X, float* Y,
                                   int B, int n, int D, const uint8_t* drop_keep, float drop_scale, float* score_out,
-                                  float* alpha_out, uint8_t* relu_mask_out, cudaStream_t st) {
+                                  float* alpha_out, uint8_t* relu_mask_out, const int32_t* px_index, int n_src,
+                                  const int32_t* adj_index, const float* k3, cudaStream_t st) {
     DIGAT_REQUIRE(P && a && adj && X && Y, "digat_graph_layer_fwd: null pointer");
     DIGAT_REQUIRE(B >= 0 && n >= 1 && n <= kPairMaxNodes, "digat_graph_layer_fwd: n=%d outside [1,%d]", n, kPairMaxNodes);
     DIGAT_REQUIRE(D >= 4 && (D & 3) == 0 && D <= 1024, "digat_graph_layer_fwd: D=%d must be a multiple of 4 in [4,1024]", D);
     DIGAT_REQUIRE((ldp & 3) == 0 && ldp >= 3 * D, "digat_graph_layer_fwd: ldp=%d must be a multiple of 4 and >= 3D", ldp);
     DIGAT_REQUIRE(aligned16(P) && aligned16(a) && aligned16(X) && aligned16(Y),
                   "digat_graph_layer_fwd: pointers must be 16-byte aligned");
+    DIGAT_REQUIRE((px_index == nullptr) == (k3 == nullptr) && (px_index == nullptr || n_src > 0),
+                  "digat_graph_layer_fwd: px_index, k3 and n_src go together");
+    DIGAT_REQUIRE(k3 == nullptr || aligned16(k3), "digat_graph_layer_fwd: k3 must be 16-byte aligned");
     if (B == 0) return DIGAT_OK;
     PairAttnGeom g;
-    pair_attn_geometry(n, D, B, &g);
+    pair_attn_geometry(n, D, B, px_index != nullptr, &g);
+    const int64_t src_graphs = px_index != nullptr ? n_src : B;
     const DeviceInfo* di = device_info();
     if (!di) return fail(DIGAT_E_CUDA, "digat_graph_layer_fwd: no CUDA device");
     DIGAT_REQUIRE(g.smem <= (size_t)di->max_smem_optin, "digat_graph_layer_fwd: needs %zu B shared memory", g.smem);
     CUtensorMap map1, map3;
     int rc;
-    if ((rc = make_tensor_map_2d(&map1, P, (int64_t)B * n, 3 * D, ldp, g.R * n, g.dc, CU_TENSOR_MAP_SWIZZLE_NONE)) != DIGAT_OK) return rc;
-    if ((rc = make_tensor_map_2d(&map3, P, (int64_t)B * n, 3 * D, ldp, g.R * n, g.dc3, CU_TENSOR_MAP_SWIZZLE_NONE)) != DIGAT_OK) return rc;
-    PairAttnArgs args{P, ldp, a, adj, X, Y, B, n, D, drop_keep, drop_scale, score_out, alpha_out, relu_mask_out};
+    if ((rc = make_tensor_map_2d(&map1, P, src_graphs * n, 3 * D, ldp, g.R * n, g.dc, CU_TENSOR_MAP_SWIZZLE_NONE)) != DIGAT_OK) return rc;
+    if ((rc = make_tensor_map_2d(&map3, P, src_graphs * n, 3 * D, ldp, g.R * n, g.dc3, CU_TENSOR_MAP_SWIZZLE_NONE)) != DIGAT_OK) return rc;
+    PairAttnArgs args{P, ldp, a, adj, X, Y, B, n, D, drop_keep, drop_scale, score_out, alpha_out, relu_mask_out,
+                      px_index, adj_index, k3};
     const int grid = (B + g.R - 1) / g.R;
     const bool single = g.R * g.nt * g.nt <= kPairThreads;
     if (single) {

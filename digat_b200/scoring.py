@@ -94,13 +94,33 @@ class Scorer:
             cn, cu = self.enc._encode(w, Xn, An, Mn, Xu, Au, Mc, ci, c0)
             return logits(cn, cu)
 
-    def score_resident(self, beh_idx, news_idx):
-        """beh_idx, news_idx: [B] device tensors (any integer dtype).  Everything else is already in HBM."""
-        b = beh_idx.long()
+    def score_resident(self, beh_idx, news_idx, share_user_graphs=True):
+        """beh_idx, news_idx: [B] device tensors (any integer dtype).  Everything else is already in HBM.
+
+        share_user_graphs: the pairs of one impression are consecutive in the reference's pair list
+        (MIND_corpus.py:295-297) and share the user graph.  Its node build, its layer-0 projection GEMM and its
+        adjacency are then computed / read once per distinct behaviour and indexed per pair (bit-identical results:
+        the same rows go through the same kernels; tests/test_gpu_scoring.py)."""
         nl = news_idx.long()
-        return self._score(self.history.index_select(0, b), self.user_graph.index_select(0, b),
-                           self.cmask.index_select(0, b), self.cidx.index_select(0, b), news_idx.to(torch.int32),
-                           self.news_graph.index_select(0, nl), self.news_mask.index_select(0, nl))
+        news_i32 = news_idx.to(torch.int32)
+        An, Mn = self.news_graph.index_select(0, nl), self.news_mask.index_select(0, nl)
+        if not share_user_graphs:
+            b = beh_idx.long()
+            return self._score(self.history.index_select(0, b), self.user_graph.index_select(0, b),
+                               self.cmask.index_select(0, b), self.cidx.index_select(0, b), news_i32, An, Mn)
+        ub, inv = torch.unique_consecutive(beh_idx.long(), return_inverse=True)
+        share = inv.to(torch.int32)
+        w = self.enc._weights()
+        if self.c_n0 is None:
+            self.cache_news_context()
+        with torch.no_grad():
+            Xn = self.gather_sag(news_i32)
+            Xu_b = self.user_nodes(self.history.index_select(0, ub))             # one node tensor per behaviour
+            c0 = self.gather_rows(self.c_n0, news_i32)
+            cn, cu = self.enc._encode(w, Xn, An, Mn, Xu_b, self.user_graph.index_select(0, ub),
+                                      self.cmask.index_select(0, beh_idx.long()), self.cidx.index_select(0, ub), c0,
+                                      share=share)
+            return logits(cn, cu)
 
     def score_host_batch(self, user_title_index, user_graph, user_category_mask, user_category_indices, news_ID,
                          news_graph, news_graph_mask):

@@ -81,10 +81,16 @@ int digat_debug_set_gemm_variant(int variant);
  * relu_mask_out [B,n,D] bool, 1 where the aggregated message (alpha~ h) is positive.
  * The [B,n,n,D] broadcast tensor of the reference is never materialised: P tiles are streamed through shared memory
  * by TMA (2-deep pipeline).  n <= 128, D % 4 == 0, D <= 1024.
+ * De-duplicated scoring (each may be NULL): the ~37 candidate pairs of one impression share the user graph, so its
+ * layer-0 projection is computed once per behaviour: px_index [B] makes graph b read P and X of graph px_index[b]
+ * (tables with n_src graphs; P then holds K1 WITHOUT k3) and k3 [B,D] is added to the staged K1 tile in-kernel
+ * (same fp32 add as the GEMM's row-group bias, so results are bit-identical to the expanded path); adj_index [B]
+ * makes graph b read adj of graph adj_index[b] (per-behaviour user graphs, no per-pair copy).
  * --------------------------------------------------------------------------------------------------------- */
 int digat_graph_layer_fwd(const float* P, int ldp, const float* a, const uint8_t* adj, const float* X, float* Y,
                           int B, int n, int D, const uint8_t* drop_keep, float drop_scale, float* score_out,
-                          float* alpha_out, uint8_t* relu_mask_out, void* stream);
+                          float* alpha_out, uint8_t* relu_mask_out, const int32_t* px_index, int n_src,
+                          const int32_t* adj_index, const float* k3, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Masked single-query attention pooling (replaces layers.py:199-206 after folding W_K into the query:
@@ -113,10 +119,11 @@ int digat_news_gate_fwd(const float* z, const float* lg, const float* ctx_in, fl
  *   alpha = softmax of a_t inside each segment {t : cidx[b,t] = k}
  *   T[b,k] = sum_{t in segment k, ascending t} alpha_t Xh[b,t],  k in [0, n_seg); empty segments are 0.
  *   Xh = first H rows of X_u [B, n_u, D] (batch stride strideX elements); cidx int64 [B,H] in [0,n_seg).
- * alpha_out [B,H] optional.  err_flag: see the gathers below. */
+ * alpha_out [B,H] optional.  err_flag: see the gathers below.  src_index [B] optional: row b reads Xu and cidx of
+ * row src_index[b] (user graphs shared by the pairs of one impression). */
 int digat_topic_segment_fwd(const float* Xu, int64_t strideX, const float* v, const int64_t* cidx,
-                            float* T, float* alpha_out, int32_t* err_flag, int B, int H, int n_seg, int D,
-                            void* stream);
+                            float* T, float* alpha_out, int32_t* err_flag, const int32_t* src_index,
+                            int B, int H, int n_seg, int D, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Gathers (replace index_select at util.py:34-36 and util.py:65-67) and small glue.
