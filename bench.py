@@ -393,11 +393,11 @@ def summarize_kernels(records, hbm_peak, tensor_peak):
             key = '%s[N=%d,K=%d,%s]' % (name, N, K, 'M>2048' if M > 2048 else 'M<=2048')
             work, bound = 2.0 * M * N * K, 'tensor'
         elif name == 'digat_attention_pool_fwd':
-            B, m, Dd = a[11], a[12], a[13]
+            B, m, Dd = a[12], a[13], a[14]
             key = '%s[m=%d]' % (name, m)
             work, bound = B * (m * Dd * 4 * (2 if a[3] else 1) + 2 * Dd * 4), 'hbm'
         elif name == 'digat_topic_segment_fwd':
-            B, H, S, Dd = a[8], a[9], a[10], a[11]
+            B, H, S, Dd = a[9], a[10], a[11], a[12]
             key, work, bound = name, B * (H * Dd * 4 + S * Dd * 4 + Dd * 4 + H * 8), 'hbm'
         elif name in ('digat_gather_sag_i32',):
             key, work, bound = name, a[6] * a[3] * a[7] * 4 * 2, 'hbm'

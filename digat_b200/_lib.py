@@ -13,18 +13,18 @@ SIGNATURES = {
     'digat_abi_version': [],
     'digat_device_check': [c_void_p],
     'digat_linear_f32': [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                         c_void_p, c_int, c_int, c_int, c_void_p],
+                         c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     'digat_split_tf32': [c_void_p, c_void_p, c_void_p, c_int64, c_void_p],
     'digat_linear_tf32x3': [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
-                            c_void_p, c_int, c_int, c_int, c_void_p],
+                            c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     'digat_debug_set_gemm_variant': [c_int],
     'digat_graph_layer_fwd': [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                               c_void_p, ctypes.c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
-                              c_void_p],
-    'digat_attention_pool_fwd': [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                              c_int, c_void_p],
+    'digat_attention_pool_fwd': [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                  c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     'digat_news_gate_fwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
-    'digat_topic_segment_fwd': [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+    'digat_topic_segment_fwd': [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_int, c_int, c_int, c_int, c_void_p],
     'digat_gather_rows_i32': [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p],
     'digat_gather_sag_i32': [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p],

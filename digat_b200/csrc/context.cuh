@@ -62,7 +62,7 @@ __device__ __forceinline__ void ctx_scores(const float* __restrict__ F, int ldf,
 struct PoolArgs {
     const float* F; int64_t strideF; int ldf;
     const float* resid;                 // same strides as F (may be null)
-    const float* v;                     // [B, D]
+    const float* v; int ldv;            // [B, ldv] query-side vector (row b at v + b*ldv)
     const uint8_t* mask;                // [B, m]
     float* out; int ldo;                // [B, ldo]
     const float* add_in;                // optional [B, ldo]: out = add_in + pooled (may alias out)
@@ -81,7 +81,7 @@ attention_pool_fwd_kernel(PoolArgs p) {
     const int m = p.m, D = p.D, nq = D >> 2;
     const float* F = p.F + (size_t)b * p.strideF;
     const float* Rs = kResid ? p.resid + (size_t)b * p.strideF : nullptr;
-    ctx_scores<kResid>(F, p.ldf, Rs, p.ldf, p.v + (size_t)b * D, m, D, sqrtf((float)D), s_part, s_score);
+    ctx_scores<kResid>(F, p.ldf, Rs, p.ldf, p.v + (size_t)b * p.ldv, m, D, sqrtf((float)D), s_part, s_score);
 
     // masked softmax over the m scores (m <= 128 = one value per thread)
     float val = -INFINITY;
@@ -135,7 +135,7 @@ attention_pool_fwd_kernel(PoolArgs p) {
 }
 
 inline int launch_attention_pool_fwd(const float* F, int64_t strideF, int ldf, const float* resid, const float* v,
-                                     const uint8_t* mask, const float* add_in, float* out, int ldo, float* first_out,
+                                     int ldv, const uint8_t* mask, const float* add_in, float* out, int ldo, float* first_out,
                                      float* alpha_out, int B, int m, int D, cudaStream_t st) {
     DIGAT_REQUIRE(F && v && mask && out, "digat_attention_pool_fwd: null pointer");
     DIGAT_REQUIRE(m >= 1 && m <= kCtxMaxItems, "digat_attention_pool_fwd: m=%d outside [1,%d]", m, kCtxMaxItems);
@@ -145,7 +145,8 @@ inline int launch_attention_pool_fwd(const float* F, int64_t strideF, int ldf, c
     DIGAT_REQUIRE(aligned16(F) && aligned16(v) && aligned16(out) && (!resid || aligned16(resid)) &&
                   (!first_out || aligned16(first_out)), "digat_attention_pool_fwd: pointers must be 16-byte aligned");
     if (B <= 0) return DIGAT_OK;
-    PoolArgs a{F, strideF, ldf, resid, v, mask, out, ldo, add_in, first_out, alpha_out, B, m, D};
+    DIGAT_REQUIRE((ldv & 3) == 0 && ldv >= D, "digat_attention_pool_fwd: ldv must be a multiple of 4 and >= D");
+    PoolArgs a{F, strideF, ldf, resid, v, ldv, mask, out, ldo, add_in, first_out, alpha_out, B, m, D};
     if (resid) attention_pool_fwd_kernel<true><<<B, kCtxThreads, 0, st>>>(a);
     else       attention_pool_fwd_kernel<false><<<B, kCtxThreads, 0, st>>>(a);
     return check_launch("digat_attention_pool_fwd");
@@ -187,7 +188,7 @@ inline int launch_news_gate_fwd(const float* z, const float* lg, const float* ct
 // ---------------------------------------------------------------------------------------------- topic segments
 struct SegArgs {
     const float* Xu; int64_t strideX;     // [B, n_u, D], first H rows are the history
-    const float* v;                       // [B, D]
+    const float* v; int ldv;              // [B, ldv]
     const int64_t* cidx;                  // [B, H]
     float* T;                             // [B, n_seg, D]
     float* alpha_out;                     // optional [B, H]
@@ -214,7 +215,7 @@ topic_segment_fwd_kernel(SegArgs p) {
         if (c < 0 || c >= n_seg) { ci = n_seg - 1; if (p.err_flag) atomicExch(p.err_flag, 1); }
         s_seg[tid] = ci;
     }
-    ctx_scores<false>(Xh, D, nullptr, 0, p.v + (size_t)b * D, H, D, sqrtf((float)D), s_part, s_score);
+    ctx_scores<false>(Xh, D, nullptr, 0, p.v + (size_t)b * p.ldv, H, D, sqrtf((float)D), s_part, s_score);
 
     // segment softmax: every slot recomputes its segment's max and (ascending-order) sum -- H^2 <= 16K flops per row
     if (tid < H) {
@@ -263,7 +264,7 @@ topic_segment_fwd_kernel(SegArgs p) {
     }
 }
 
-inline int launch_topic_segment_fwd(const float* Xu, int64_t strideX, const float* v, const int64_t* cidx, float* T,
+inline int launch_topic_segment_fwd(const float* Xu, int64_t strideX, const float* v, int ldv, const int64_t* cidx, float* T,
                                     float* alpha_out, int32_t* err_flag, const int32_t* src_index, int B, int H, int n_seg, int D,
                                     cudaStream_t st) {
     DIGAT_REQUIRE(Xu && v && cidx && T, "digat_topic_segment_fwd: null pointer");
@@ -273,7 +274,8 @@ inline int launch_topic_segment_fwd(const float* Xu, int64_t strideX, const floa
     DIGAT_REQUIRE((strideX & 3) == 0 && aligned16(Xu) && aligned16(v) && aligned16(T),
                   "digat_topic_segment_fwd: pointers/strides must be 16-byte aligned");
     if (B <= 0) return DIGAT_OK;
-    SegArgs a{Xu, strideX, v, cidx, T, alpha_out, B, H, n_seg, D, err_flag, src_index};
+    DIGAT_REQUIRE((ldv & 3) == 0 && ldv >= D, "digat_topic_segment_fwd: ldv must be a multiple of 4 and >= D");
+    SegArgs a{Xu, strideX, v, ldv, cidx, T, alpha_out, B, H, n_seg, D, err_flag, src_index};
     topic_segment_fwd_kernel<<<B, kCtxThreads, 0, st>>>(a);
     return check_launch("digat_topic_segment_fwd");
 }

@@ -36,9 +36,9 @@ int digat_device_check(int* sm_count) {
 
 int digat_linear_f32(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc,
                      int M, int N, int K, int relu, const float* group_bias, int group_rows, int group_col0,
-                     int group_cols, void* stream) {
+                     int group_cols, int group_ld, void* stream) {
     return launch_linear_f32(A, lda, W, ldw, bias, C, ldc, M, N, K, relu,
-                             GroupBias{group_bias, group_rows, group_col0, group_cols}, as_stream(stream));
+                             GroupBias{group_bias, group_rows, group_col0, group_cols, group_ld}, as_stream(stream));
 }
 
 int digat_split_tf32(const float* W, float* W_hi, float* W_lo, int64_t count, void* stream) {
@@ -50,9 +50,9 @@ int digat_split_tf32(const float* W, float* W_hi, float* W_lo, int64_t count, vo
 
 int digat_linear_tf32x3(const float* A, int lda, const float* W_hi, const float* W_lo, int ldw, const float* bias,
                         float* C, int ldc, int M, int N, int K, const float* group_bias, int group_rows,
-                        int group_col0, int group_cols, void* stream) {
+                        int group_col0, int group_cols, int group_ld, void* stream) {
     return launch_linear_tf32x3(A, lda, W_hi, W_lo, ldw, bias, C, ldc, M, N, K,
-                                GroupBias{group_bias, group_rows, group_col0, group_cols}, as_stream(stream));
+                                GroupBias{group_bias, group_rows, group_col0, group_cols, group_ld}, as_stream(stream));
 }
 
 int digat_debug_set_gemm_variant(int variant) {
@@ -63,15 +63,15 @@ int digat_debug_set_gemm_variant(int variant) {
 int digat_graph_layer_fwd(const float* P, int ldp, const float* a, const uint8_t* adj, const float* X, float* Y,
                           int B, int n, int D, const uint8_t* drop_keep, float drop_scale, float* score_out,
                           float* alpha_out, uint8_t* relu_mask_out, const int32_t* px_index, int n_src,
-                          const int32_t* adj_index, const float* k3, void* stream) {
+                          const int32_t* adj_index, const float* k3, int ldk3, void* stream) {
     return launch_graph_layer_fwd(P, ldp, a, adj, X, Y, B, n, D, drop_keep, drop_scale, score_out, alpha_out,
-                                  relu_mask_out, px_index, n_src, adj_index, k3, as_stream(stream));
+                                  relu_mask_out, px_index, n_src, adj_index, k3, ldk3, as_stream(stream));
 }
 
 int digat_attention_pool_fwd(const float* F, int64_t strideF, int ldf, const float* resid_F, const float* v,
-                             const uint8_t* mask, const float* add_in, float* out, int ldo, float* first_out,
+                             int ldv, const uint8_t* mask, const float* add_in, float* out, int ldo, float* first_out,
                              float* alpha_out, int B, int m, int D, void* stream) {
-    return launch_attention_pool_fwd(F, strideF, ldf, resid_F, v, mask, add_in, out, ldo, first_out, alpha_out, B, m, D,
+    return launch_attention_pool_fwd(F, strideF, ldf, resid_F, v, ldv, mask, add_in, out, ldo, first_out, alpha_out, B, m, D,
                                      as_stream(stream));
 }
 
@@ -80,10 +80,10 @@ int digat_news_gate_fwd(const float* z, const float* lg, const float* ctx_in, fl
     return launch_news_gate_fwd(z, lg, ctx_in, ctx_out, B, D, as_stream(stream));
 }
 
-int digat_topic_segment_fwd(const float* Xu, int64_t strideX, const float* v, const int64_t* cidx, float* T,
+int digat_topic_segment_fwd(const float* Xu, int64_t strideX, const float* v, int ldv, const int64_t* cidx, float* T,
                             float* alpha_out, int32_t* err_flag, const int32_t* src_index, int B, int H, int n_seg,
                             int D, void* stream) {
-    return launch_topic_segment_fwd(Xu, strideX, v, cidx, T, alpha_out, err_flag, src_index, B, H, n_seg, D,
+    return launch_topic_segment_fwd(Xu, strideX, v, ldv, cidx, T, alpha_out, err_flag, src_index, B, H, n_seg, D,
                                     as_stream(stream));
 }
 

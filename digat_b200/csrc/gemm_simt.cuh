@@ -11,7 +11,7 @@ namespace digat {
 // Eq. (8) (reference graphEncoders.py:150), with the reference's rounding.
 struct GroupBias {
     const float* ptr;
-    int rows, col0, cols;
+    int rows, col0, cols, ld;      // ld = row pitch of ptr in elements (>= cols)
 };
 
 template <int BM, int BN, int BK, int TM, int TN>
@@ -121,7 +121,7 @@ gemm_tn_f32_kernel(const float* __restrict__ A, int lda, const float* __restrict
                     float v = acc[gi * 4 + ii][gj * 4 + jj];
                     if (bias != nullptr && gn + jj < N) v += bias[gn + jj];
                     if (gb.ptr != nullptr && gn + jj >= gb.col0 && gn + jj < gb.col0 + gb.cols)
-                        v += gb.ptr[(size_t)(gm / gb.rows) * gb.cols + (gn + jj - gb.col0)];
+                        v += gb.ptr[(size_t)(gm / gb.rows) * gb.ld + (gn + jj - gb.col0)];
                     if (relu) v = fmaxf(v, 0.f);
                     o[jj] = v;
                 }
@@ -144,7 +144,7 @@ inline int launch_linear_f32(const float* A, int lda, const float* W, int ldw, c
     DIGAT_REQUIRE((K & 3) == 0 && (lda & 3) == 0 && (ldw & 3) == 0, "digat_linear_f32: K, lda, ldw must be multiples of 4");
     DIGAT_REQUIRE(aligned16(A) && aligned16(W) && aligned16(C), "digat_linear_f32: pointers must be 16-byte aligned");
     DIGAT_REQUIRE(lda >= K && ldw >= K && ldc >= N, "digat_linear_f32: leading dimension too small");
-    DIGAT_REQUIRE(gb.ptr == nullptr || (gb.rows > 0 && gb.col0 >= 0 && gb.cols > 0 && gb.col0 + gb.cols <= N),
+    DIGAT_REQUIRE(gb.ptr == nullptr || (gb.rows > 0 && gb.col0 >= 0 && gb.cols > 0 && gb.col0 + gb.cols <= N && gb.ld >= gb.cols),
                   "digat_linear_f32: bad row-group bias");
     if (M == 0) return DIGAT_OK;
     if (M <= 2048) {

@@ -207,7 +207,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             const int m = m0 + h * 128 + q * 32 + lane;
             const bool row_ok = m < M;
             float* crow = C + (size_t)m * ldc + n0;
-            const float* grow = (has_gb && row_ok) ? gb.ptr + (size_t)(m / gb.rows) * gb.cols - gb.col0 + n0 : nullptr;
+            const float* grow = (has_gb && row_ok) ? gb.ptr + (size_t)(m / gb.rows) * gb.ld - gb.col0 + n0 : nullptr;
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * BN);
             uint32_t rm[16], rc[16];
             float4 gq[4];
@@ -298,7 +298,8 @@ inline int launch_linear_tf32x3(const float* A, int lda, const float* W_hi, cons
                                 float* C, int ldc, int M, int N, int K, GroupBias gb, cudaStream_t st) {
     DIGAT_REQUIRE(A && W_hi && W_lo && C, "digat_linear_tf32x3: null pointer");
     DIGAT_REQUIRE(gb.ptr == nullptr || (gb.rows > 0 && gb.col0 >= 0 && gb.cols > 0 && gb.col0 + gb.cols <= N &&
-                                        (gb.col0 & 3) == 0 && (gb.cols & 3) == 0 && aligned16(gb.ptr)),
+                                        (gb.col0 & 3) == 0 && (gb.cols & 3) == 0 && (gb.ld & 3) == 0 && gb.ld >= gb.cols &&
+                                        aligned16(gb.ptr)),
                   "digat_linear_tf32x3: bad row-group bias (col0/cols must be multiples of 4)");
     DIGAT_REQUIRE(M >= 0 && N > 0 && K > 0, "digat_linear_tf32x3: bad shape M=%d N=%d K=%d", M, N, K);
     DIGAT_REQUIRE((K & 3) == 0 && (lda & 3) == 0 && (ldw & 3) == 0 && (ldc & 3) == 0,

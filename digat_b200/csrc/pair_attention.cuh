@@ -56,7 +56,7 @@ struct PairAttnArgs {
     // user graph is projected once per behaviour and every pair reads it through an index
     const int32_t* px_index;    // [B] graph b reads P and X of graph px_index[b] (P then holds K1 WITHOUT k3)
     const int32_t* adj_index;   // [B] graph b reads adj of graph adj_index[b]
-    const float* k3;            // [B,D] added to the staged U tile in-kernel: U = fl(K1 + k3), same rounding as the GEMM path
+    const float* k3; int ldk3;  // [B,ldk3] added to the staged U tile in-kernel: U = fl(K1 + k3), same rounding as the GEMM path
 };
 
 __device__ __forceinline__ uint64_t pack2(float lo, float hi) {
@@ -106,7 +106,7 @@ graph_layer_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
     for (int i = tid; i < D / 4; i += kPairThreads) {
         reinterpret_cast<float4*>(a_s)[i] = reinterpret_cast<const float4*>(p.a)[i];
         if (p.k3 != nullptr)
-            reinterpret_cast<float4*>(k3_s)[i] = reinterpret_cast<const float4*>(p.k3 + (size_t)b0 * D)[i];
+            reinterpret_cast<float4*>(k3_s)[i] = reinterpret_cast<const float4*>(p.k3 + (size_t)b0 * p.ldk3)[i];
     }
     __syncthreads();
 
@@ -385,7 +385,7 @@ inline void pair_attn_geometry(int n, int D, int B, bool indexed, PairAttnGeom* 
 inline int launch_graph_layer_fwd(const float* P, int ldp, const float* a, const uint8_t* adj, const float* X, float* Y,
                                   int B, int n, int D, const uint8_t* drop_keep, float drop_scale, float* score_out,
                                   float* alpha_out, uint8_t* relu_mask_out, const int32_t* px_index, int n_src,
-                                  const int32_t* adj_index, const float* k3, cudaStream_t st) {
+                                  const int32_t* adj_index, const float* k3, int ldk3, cudaStream_t st) {
     DIGAT_REQUIRE(P && a && adj && X && Y, "digat_graph_layer_fwd: null pointer");
     DIGAT_REQUIRE(B >= 0 && n >= 1 && n <= kPairMaxNodes, "digat_graph_layer_fwd: n=%d outside [1,%d]", n, kPairMaxNodes);
     DIGAT_REQUIRE(D >= 4 && (D & 3) == 0 && D <= 1024, "digat_graph_layer_fwd: D=%d must be a multiple of 4 in [4,1024]", D);
@@ -394,7 +394,8 @@ inline int launch_graph_layer_fwd(const float* P, int ldp, const float* a, const
                   "digat_graph_layer_fwd: pointers must be 16-byte aligned");
     DIGAT_REQUIRE((px_index == nullptr) == (k3 == nullptr) && (px_index == nullptr || n_src > 0),
                   "digat_graph_layer_fwd: px_index, k3 and n_src go together");
-    DIGAT_REQUIRE(k3 == nullptr || aligned16(k3), "digat_graph_layer_fwd: k3 must be 16-byte aligned");
+    DIGAT_REQUIRE(k3 == nullptr || (aligned16(k3) && (ldk3 & 3) == 0 && ldk3 >= D),
+                  "digat_graph_layer_fwd: k3 must be 16-byte aligned with ldk3 a multiple of 4 and >= D");
     if (B == 0) return DIGAT_OK;
     PairAttnGeom g;
     pair_attn_geometry(n, D, B, px_index != nullptr, &g);
@@ -407,7 +408,7 @@ inline int launch_graph_layer_fwd(const float* P, int ldp, const float* a, const
     if ((rc = make_tensor_map_2d(&map1, P, src_graphs * n, 3 * D, ldp, g.R * n, g.dc, CU_TENSOR_MAP_SWIZZLE_NONE)) != DIGAT_OK) return rc;
     if ((rc = make_tensor_map_2d(&map3, P, src_graphs * n, 3 * D, ldp, g.R * n, g.dc3, CU_TENSOR_MAP_SWIZZLE_NONE)) != DIGAT_OK) return rc;
     PairAttnArgs args{P, ldp, a, adj, X, Y, B, n, D, drop_keep, drop_scale, score_out, alpha_out, relu_mask_out,
-                      px_index, adj_index, k3};
+                      px_index, adj_index, k3, ldk3};
     const int grid = (B + g.R - 1) / g.R;
     const bool single = g.R * g.nt * g.nt <= kPairThreads;
     if (single) {

@@ -79,12 +79,13 @@ def linear(A, W, bias=None, relu=False, M=None, K=None, lda=None, out=None, grou
     if out is None:
         out = torch.empty((M, N), device=A.device, dtype=torch.float32)
     gcols = 0 if group_bias is None else group_bias.shape[1]
+    gld = 0 if group_bias is None else group_bias.stride(0)
     if isinstance(W, PackedWeight) and W.hi is not None and M >= TENSOR_CORE_MIN_ROWS and not relu:
         _lib.call('digat_linear_tf32x3', A.data_ptr(), lda, W.hi.data_ptr(), W.lo.data_ptr(), w.stride(0), _ptr(bias),
-                  out.data_ptr(), out.stride(0), M, N, K, _ptr(group_bias), group_rows, group_col0, gcols, _stream())
+                  out.data_ptr(), out.stride(0), M, N, K, _ptr(group_bias), group_rows, group_col0, gcols, gld, _stream())
     else:
         _lib.call('digat_linear_f32', A.data_ptr(), lda, w.data_ptr(), w.stride(0), _ptr(bias), out.data_ptr(),
-                  out.stride(0), M, N, K, 1 if relu else 0, _ptr(group_bias), group_rows, group_col0, gcols, _stream())
+                  out.stride(0), M, N, K, 1 if relu else 0, _ptr(group_bias), group_rows, group_col0, gcols, gld, _stream())
     return out
 
 
@@ -98,7 +99,8 @@ def graph_layer_fwd(P, a, adj, X, drop_keep=None, drop_scale=1.0, score_out=None
     Y = torch.empty((B, n, D), device=X.device, dtype=torch.float32)
     _lib.call('digat_graph_layer_fwd', P.data_ptr(), P.stride(0), a.data_ptr(), adj.data_ptr(), X.data_ptr(),
               Y.data_ptr(), B, n, D, _ptr(drop_keep), float(drop_scale), _ptr(score_out), _ptr(alpha_out),
-              _ptr(relu_mask_out), _ptr(px_index), n_src, _ptr(adj_index), _ptr(k3), _stream())
+              _ptr(relu_mask_out), _ptr(px_index), n_src, _ptr(adj_index), _ptr(k3),
+              0 if k3 is None else k3.stride(0), _stream())
     return Y
 
 
@@ -107,7 +109,7 @@ def attention_pool_fwd(F, v, mask, resid=None, add_in=None, out=None, ldo=None, 
     if out is None:
         out = torch.empty((B, D), device=F.device, dtype=torch.float32)
         ldo = D
-    _lib.call('digat_attention_pool_fwd', F.data_ptr(), m * D, D, _ptr(resid), v.data_ptr(), mask.data_ptr(),
+    _lib.call('digat_attention_pool_fwd', F.data_ptr(), m * D, D, _ptr(resid), v.data_ptr(), v.stride(0), mask.data_ptr(),
               _ptr(add_in), out.data_ptr(), ldo, _ptr(first_out), _ptr(alpha_out), B, m, D, _stream())
     return out
 
@@ -226,15 +228,27 @@ class DIGAT(GraphEncoder):
                     w[g, i, 'W3'] = PackedWeight(f3.weight.detach().float().contiguous())
                     w[g, i, 'b3'] = f3.bias.detach().float().contiguous()
                     w[g, i, 'a'] = av.weight.detach().float().reshape(D).contiguous()
-            w['cand_Q'] = PackedWeight(self.candidate_attention.Q.weight.detach().float().contiguous())
-            w['cand_Qb'] = self.candidate_attention.Q.bias.detach().float().contiguous()
-            w['cand_Kt'] = PackedWeight(self.candidate_attention.K.weight.detach().float().t().contiguous())
+            # attention key folded into the query: a_k = F_k . v / sqrt(D), v = K^T (Q q + b) = (K^T Q) q + K^T b.
+            # The [D,D] product is formed once in fp64 and rounded to fp32 (one GEMM per context instead of two).
+            def fold(K, Q):
+                Kd = K.weight.detach().double()
+                return (Kd.t() @ Q.weight.detach().double()).float().contiguous(), \
+                       (Kd.t() @ Q.bias.detach().double()).float().contiguous()
+            cand_M, cand_m = fold(self.candidate_attention.K, self.candidate_attention.Q)
+            w['cand_M'], w['cand_m'] = PackedWeight(cand_M), cand_m
             w['gate_W'] = PackedWeight(self.news_graph_W.weight.detach().float().contiguous())
             w['gate_b'] = self.news_graph_W.bias.detach().float().contiguous()
-            w['uq_W'] = PackedWeight(torch.cat([self.user_news_Q.weight, self.userAttention.Q.weight], 0).float().contiguous())
-            w['uq_b'] = torch.cat([self.user_news_Q.bias, self.userAttention.Q.bias], 0).float().contiguous()
-            w['unK_t'] = PackedWeight(self.user_news_K.weight.detach().float().t().contiguous())
-            w['uaK_t'] = PackedWeight(self.userAttention.K.weight.detach().float().t().contiguous())
+            # everything the user side needs from c_n comes out of ONE GEMM: [v_topic | v_user | k3 of the next user layer]
+            un_M, un_m = fold(self.user_news_K, self.user_news_Q)
+            ua_M, ua_m = fold(self.userAttention.K, self.userAttention.Q)
+            for j in range(self.graph_depth + 1):
+                Ws, bs = [un_M, ua_M], [un_m, ua_m]
+                if j < self.graph_depth:
+                    f3 = self.user_graph_attention_ffn3[j]
+                    Ws.append(f3.weight.detach().float())
+                    bs.append(f3.bias.detach().float())
+                w['uctx_W', j] = PackedWeight(torch.cat(Ws, 0).contiguous())
+                w['uctx_b', j] = torch.cat(bs, 0).contiguous()
             w['fa_W'] = PackedWeight(self.featureAffine.weight.detach().float().contiguous())
             w['fa_b'] = self.featureAffine.bias.detach().float().contiguous()
             w['topic'] = self.topic_node_embedding.detach().float().contiguous()
@@ -244,8 +258,7 @@ class DIGAT(GraphEncoder):
     # ---------------------------------------------------------------------------------- kernels, no autograd
     def _news_ctx(self, w, X, mask, ctx_in=None):
         B, n, D = X.shape
-        q = linear(X, w['cand_Q'], w['cand_Qb'], M=B, K=D, lda=n * D)            # Q(l), l = X[:,0,:]
-        v = linear(q, w['cand_Kt'])                                               # K^T q
+        v = linear(X, w['cand_M'], w['cand_m'], M=B, K=D, lda=n * D)             # K^T (Q l + b), l = X[:,0,:]
         lg = torch.empty((B, 2 * D), device=X.device, dtype=torch.float32)
         attention_pool_fwd(X, v, mask, out=lg[:, D:], ldo=2 * D, first_out=lg)    # lg = [l | g]
         z = linear(lg, w['gate_W'], w['gate_b'])
@@ -253,25 +266,28 @@ class DIGAT(GraphEncoder):
         _lib.call('digat_news_gate_fwd', z.data_ptr(), lg.data_ptr(), _ptr(ctx_in), out.data_ptr(), B, D, _stream())
         return out
 
-    def _user_ctx(self, w, Xu, cmask, cidx, c_n, ctx_in=None, src_index=None):
-        """src_index [B] int32: Xu / cidx are per-behaviour tables and row b uses entry src_index[b]."""
+    def _user_ctx(self, w, Xu, cmask, cidx, c_n, j, ctx_in=None, src_index=None):
+        """j = index of this call (0 = initial context, i+1 = after layer i).  Returns (context, k3 of user layer j or
+        None).  src_index [B] int32: Xu / cidx are per-behaviour tables and row b uses entry src_index[b]."""
         nu, D = Xu.shape[1], Xu.shape[2]
         B = c_n.shape[0]
         H, S = self.max_history_num, self.category_num
-        qq = linear(c_n, w['uq_W'], w['uq_b'])                                    # [B,2D] = [user_news_Q c | userAttention.Q c]
-        v1 = linear(qq, w['unK_t'], M=B, K=D, lda=2 * D)
-        v2 = linear(qq[:, D:], w['uaK_t'], M=B, K=D, lda=2 * D)
+        vv = linear(c_n, w['uctx_W', j], w['uctx_b', j])                          # [B, 2D or 3D]
+        v1, v2 = vv[:, :D], vv[:, D:2 * D]
+        k3_next = vv[:, 2 * D:] if vv.shape[1] > 2 * D else None
         T = torch.empty((B, S, D), device=Xu.device, dtype=torch.float32)
-        _lib.call('digat_topic_segment_fwd', Xu.data_ptr(), nu * D, v1.data_ptr(), cidx.data_ptr(), T.data_ptr(), 0,
-                  self._err_flag(Xu.device).data_ptr(), _ptr(src_index), B, H, S, D, _stream())
+        _lib.call('digat_topic_segment_fwd', Xu.data_ptr(), nu * D, v1.data_ptr(), vv.stride(0), cidx.data_ptr(),
+                  T.data_ptr(), 0, self._err_flag(Xu.device).data_ptr(), _ptr(src_index), B, H, S, D, _stream())
         Fa = linear(T, w['fa_W'], w['fa_b'])                                      # featureAffine(T)  [B*S, D]
-        return attention_pool_fwd(Fa.view(B, S, D), v2, cmask, resid=T, add_in=ctx_in)
+        return attention_pool_fwd(Fa.view(B, S, D), v2, cmask, resid=T, add_in=ctx_in), k3_next
 
-    def _layer(self, w, g, i, X, adj, ctx_other, share=None, adj_index=None):
-        """share [B] int32 (layer 0 of the scoring path): X [n_src,n,D] holds one graph per BEHAVIOUR and pair b uses
+    def _layer(self, w, g, i, X, adj, ctx_other, k3=None, share=None, adj_index=None):
+        """k3 [B,D] (possibly a column view): ffn3(context of the other graph) + bias, computed here when None.
+        share [B] int32 (layer 0 of the scoring path): X [n_src,n,D] holds one graph per BEHAVIOUR and pair b uses
         graph share[b]; the projection then runs once per behaviour and k3 is added inside the fused kernel."""
         n, D = X.shape[1], X.shape[2]
-        k3 = linear(ctx_other, w[g, i, 'W3'], w[g, i, 'b3'])                      # [B, D]
+        if k3 is None:
+            k3 = linear(ctx_other, w[g, i, 'W3'], w[g, i, 'b3'])                  # [B, D]
         if share is not None:
             P = linear(X, w[g, i, 'Wcat'], w[g, i, 'bcat'])                       # h | K1 | K2 per behaviour
             return graph_layer_fwd(P, w[g, i, 'a'], adj, X, px_index=share, adj_index=share, k3=k3, B=k3.shape[0])
@@ -334,7 +350,7 @@ class DIGAT(GraphEncoder):
         with torch.no_grad():
             return self._user_ctx(w, _f32c(user_graph_embeddings, 'user_graph_embeddings'),
                                   _boolc(user_category_mask, 'user_category_mask'), user_category_indices.contiguous(),
-                                  _f32c(news_graph_context, 'news_graph_context'))
+                                  _f32c(news_graph_context, 'news_graph_context'), self.graph_depth)[0]
 
     def compute_news_graph_embeddings(self, index, news_graph_embeddings, news_graph, user_graph_context):
         w = self._weights()
@@ -355,242 +371,17 @@ class DIGAT(GraphEncoder):
         user graph's layer-0 projection and node build then run once per behaviour (results are bit-identical)."""
         if c_n is None:
             c_n = self._news_ctx(w, Xn, Mn)
-        c_u = self._user_ctx(w, Xu, Mc, ci, c_n, src_index=share)
+        c_u, k3u = self._user_ctx(w, Xu, Mc, ci, c_n, 0, src_index=share)
         if share is not None:
             ci = ci.index_select(0, share.long())      # [B,H] int64: from layer 1 on every pair owns its user nodes
         for i in range(self.graph_depth):
             Xn_new = self._layer(w, 'news', i, Xn, An, c_u)
-            Xu = self._layer(w, 'user', i, Xu, Au, c_n, share=share if i == 0 else None,
+            Xu = self._layer(w, 'user', i, Xu, Au, c_n, k3=k3u, share=share if i == 0 else None,
                              adj_index=share if i > 0 else None)
             Xn = Xn_new
             c_n = self._news_ctx(w, Xn, Mn, ctx_in=c_n)
-            c_u = self._user_ctx(w, Xu, Mc, ci, c_n, ctx_in=c_u)
+            c_u, k3u = self._user_ctx(w, Xu, Mc, ci, c_n, i + 1, ctx_in=c_u)
         return c_n, c_u
-
-    def inference(self, news_graph_embeddings, news_graph, news_graph_mask, user_news_embedding, user_graph,
-                  user_category_mask, user_category_indices, news_graph_context):
-        raise Exception('Function inference must be implemented at sub-class')
-
-
-class DIGAT(GraphEncoder):
-    def __init__(self, config, news_embedding_dim: int):
-        super().__init__(config, news_embedding_dim)
-        D, L = self.news_embedding_dim, self.graph_depth
-        if D % 4 != 0:
-            raise Exception('news_embedding_dim must be a multiple of 4 for the sm_100a kernels')
-        self.candidate_attention = ScaledDotProductAttention(D, D, D)
-        self.news_graph_W = nn.Linear(D * 2, D, bias=True)
-        self.user_news_K = nn.Linear(D, D, bias=False)
-        self.user_news_Q = nn.Linear(D, D, bias=True)
-        self.featureAffine = nn.Linear(D, D, bias=True)
-        self.userAttention = ScaledDotProductAttention(D, D, D)
-        for g in ('news', 'user'):
-            setattr(self, g + '_graph_attention_W', nn.ModuleList([nn.Linear(D, D, bias=True) for _ in range(L)]))
-            setattr(self, g + '_graph_attention_ffn1', nn.ModuleList([nn.Linear(D, D, bias=False) for _ in range(L)]))
-            setattr(self, g + '_graph_attention_ffn2', nn.ModuleList([nn.Linear(D, D, bias=False) for _ in range(L)]))
-            setattr(self, g + '_graph_attention_ffn3', nn.ModuleList([nn.Linear(D, D, bias=True) for _ in range(L)]))
-            setattr(self, g + '_graph_attention_a', nn.ModuleList([nn.Linear(D, 1, bias=False) for _ in range(L)]))
-        self._packed = None
-        self._packed_key = None
-
-    def initialize(self):
-        super().initialize()
-        relu_gain = nn.init.calculate_gain('relu')
-        leaky_gain = nn.init.calculate_gain('leaky_relu', 0.2)
-        for g in ('news', 'user'):
-            for i in range(self.graph_depth):
-                W = getattr(self, g + '_graph_attention_W')[i]
-                nn.init.xavier_uniform_(W.weight)
-                nn.init.zeros_(W.bias)
-                nn.init.xavier_uniform_(getattr(self, g + '_graph_attention_a')[i].weight, gain=leaky_gain)
-                for f in ('ffn1', 'ffn2', 'ffn3'):
-                    nn.init.xavier_uniform_(getattr(self, g + '_graph_attention_' + f)[i].weight, gain=relu_gain)
-                nn.init.zeros_(getattr(self, g + '_graph_attention_ffn3')[i].bias)
-        self.candidate_attention.initialize()
-        nn.init.xavier_uniform_(self.news_graph_W.weight)
-        nn.init.zeros_(self.news_graph_W.bias)
-        nn.init.xavier_uniform_(self.user_news_K.weight)
-        nn.init.xavier_uniform_(self.user_news_Q.weight)
-        nn.init.zeros_(self.user_news_Q.bias)
-        nn.init.xavier_uniform_(self.featureAffine.weight, gain=relu_gain)
-        nn.init.zeros_(self.featureAffine.bias)
-        self.userAttention.initialize()
-
-    # ---------------------------------------------------------------------------------- packed weights
-    def _weights(self):
-        """Kernel-side weight layout, rebuilt only when a parameter changed (optimizer step / load_state_dict):
-        * per layer and graph: [W; ffn1; ffn2] stacked to [3D, D] so h, K1, K2 come out of ONE projection GEMM;
-        * attention K matrices transposed, so the folded query v = K^T (Q q + b) is a plain linear;
-        * [user_news_Q; userAttention.Q] stacked: both queries of the user context come from one GEMM on c_n."""
-        params = list(self.parameters())
-        key = tuple((p.data_ptr(), p._version) for p in params)
-        if self._packed is not None and key == self._packed_key:
-            return self._packed
-        dev = params[0].device
-        if dev.type != 'cuda':
-            raise RuntimeError('DIGAT parameters must live on a CUDA device (digat_b200 has no CPU fallback)')
-        _lib.require_device(dev.index if dev.index is not None else torch.cuda.current_device())
-        D = self.news_embedding_dim
-        with torch.no_grad():
-            w = {}
-            for g in ('news', 'user'):
-                for i in range(self.graph_depth):
-                    W = getattr(self, g + '_graph_attention_W')[i]
-                    f1 = getattr(self, g + '_graph_attention_ffn1')[i]
-                    f2 = getattr(self, g + '_graph_attention_ffn2')[i]
-                    f3 = getattr(self, g + '_graph_attention_ffn3')[i]
-                    av = getattr(self, g + '_graph_attention_a')[i]
-                    w[g, i, 'Wcat'] = PackedWeight(torch.cat([W.weight, f1.weight, f2.weight], 0).float().contiguous())
-                    w[g, i, 'bcat'] = torch.cat([W.bias, torch.zeros(2 * D, device=dev)], 0).float().contiguous()
-                    w[g, i, 'W3'] = PackedWeight(f3.weight.detach().float().contiguous())
-                    w[g, i, 'b3'] = f3.bias.detach().float().contiguous()
-                    w[g, i, 'a'] = av.weight.detach().float().reshape(D).contiguous()
-            w['cand_Q'] = PackedWeight(self.candidate_attention.Q.weight.detach().float().contiguous())
-            w['cand_Qb'] = self.candidate_attention.Q.bias.detach().float().contiguous()
-            w['cand_Kt'] = PackedWeight(self.candidate_attention.K.weight.detach().float().t().contiguous())
-            w['gate_W'] = PackedWeight(self.news_graph_W.weight.detach().float().contiguous())
-            w['gate_b'] = self.news_graph_W.bias.detach().float().contiguous()
-            w['uq_W'] = PackedWeight(torch.cat([self.user_news_Q.weight, self.userAttention.Q.weight], 0).float().contiguous())
-            w['uq_b'] = torch.cat([self.user_news_Q.bias, self.userAttention.Q.bias], 0).float().contiguous()
-            w['unK_t'] = PackedWeight(self.user_news_K.weight.detach().float().t().contiguous())
-            w['uaK_t'] = PackedWeight(self.userAttention.K.weight.detach().float().t().contiguous())
-            w['fa_W'] = PackedWeight(self.featureAffine.weight.detach().float().contiguous())
-            w['fa_b'] = self.featureAffine.bias.detach().float().contiguous()
-            w['topic'] = self.topic_node_embedding.detach().float().contiguous()
-        self._packed, self._packed_key = w, key
-        return w
-
-    # ---------------------------------------------------------------------------------- kernels, no autograd
-    def _news_ctx(self, w, X, mask, ctx_in=None):
-        B, n, D = X.shape
-        q = linear(X, w['cand_Q'], w['cand_Qb'], M=B, K=D, lda=n * D)            # Q(l), l = X[:,0,:]
-        v = linear(q, w['cand_Kt'])                                               # K^T q
-        lg = torch.empty((B, 2 * D), device=X.device, dtype=torch.float32)
-        attention_pool_fwd(X, v, mask, out=lg[:, D:], ldo=2 * D, first_out=lg)    # lg = [l | g]
-        z = linear(lg, w['gate_W'], w['gate_b'])
-        out = torch.empty((B, D), device=X.device, dtype=torch.float32)
-        _lib.call('digat_news_gate_fwd', z.data_ptr(), lg.data_ptr(), _ptr(ctx_in), out.data_ptr(), B, D, _stream())
-        return out
-
-    def _user_ctx(self, w, Xu, cmask, cidx, c_n, ctx_in=None, src_index=None):
-        """src_index [B] int32: Xu / cidx are per-behaviour tables and row b uses entry src_index[b]."""
-        nu, D = Xu.shape[1], Xu.shape[2]
-        B = c_n.shape[0]
-        H, S = self.max_history_num, self.category_num
-        qq = linear(c_n, w['uq_W'], w['uq_b'])                                    # [B,2D] = [user_news_Q c | userAttention.Q c]
-        v1 = linear(qq, w['unK_t'], M=B, K=D, lda=2 * D)
-        v2 = linear(qq[:, D:], w['uaK_t'], M=B, K=D, lda=2 * D)
-        T = torch.empty((B, S, D), device=Xu.device, dtype=torch.float32)
-        _lib.call('digat_topic_segment_fwd', Xu.data_ptr(), nu * D, v1.data_ptr(), cidx.data_ptr(), T.data_ptr(), 0,
-                  self._err_flag(Xu.device).data_ptr(), _ptr(src_index), B, H, S, D, _stream())
-        Fa = linear(T, w['fa_W'], w['fa_b'])                                      # featureAffine(T)  [B*S, D]
-        return attention_pool_fwd(Fa.view(B, S, D), v2, cmask, resid=T, add_in=ctx_in)
-
-    def _layer(self, w, g, i, X, adj, ctx_other, share=None, adj_index=None):
-        """share [B] int32 (layer 0 of the scoring path): X [n_src,n,D] holds one graph per BEHAVIOUR and pair b uses
-        graph share[b]; the projection then runs once per behaviour and k3 is added inside the fused kernel."""
-        n, D = X.shape[1], X.shape[2]
-        k3 = linear(ctx_other, w[g, i, 'W3'], w[g, i, 'b3'])                      # [B, D]
-        if share is not None:
-            P = linear(X, w[g, i, 'Wcat'], w[g, i, 'bcat'])                       # h | K1 | K2 per behaviour
-            return graph_layer_fwd(P, w[g, i, 'a'], adj, X, px_index=share, adj_index=share, k3=k3, B=k3.shape[0])
-        P = linear(X, w[g, i, 'Wcat'], w[g, i, 'bcat'], group_bias=k3, group_rows=n, group_col0=D)   # h | k3+K1 | K2
-        return graph_layer_fwd(P, w[g, i, 'a'], adj, X, adj_index=adj_index)
-
-    def _err_flag(self, device):
-        f = getattr(self, '_err', None)
-        if f is None or f.device != device:
-            f = torch.zeros(1, dtype=torch.int32, device=device)
-            self._err = f
-        return f
-
-    def check_index_errors(self):
-        """Raises if a kernel saw an out-of-range category index since the last check (synchronises)."""
-        f = getattr(self, '_err', None)
-        if f is not None and int(f.item()) != 0:
-            f.zero_()
-            raise RuntimeError('index out of range in user_category_indices (reference: torch_scatter raises)')
-
-    def _user_nodes(self, w, user_news_embedding):
-        B, H, D = user_news_embedding.shape
-        C = w['topic'].shape[0]
-        Xu = torch.empty((B, H + C, D), device=user_news_embedding.device, dtype=torch.float32)
-        _lib.call('digat_build_user_nodes', 0, 0, 0, user_news_embedding.data_ptr(), w['topic'].data_ptr(),
-                  Xu.data_ptr(), B, H, C, D, 0, _stream())
-        return Xu
-
-    def _check_inputs(self, news_graph_embeddings, news_graph, news_graph_mask, user_news_embedding, user_graph,
-                      user_category_mask, user_category_indices):
-        Xn = _f32c(news_graph_embeddings, 'news_graph_embeddings')
-        Xh = _f32c(user_news_embedding, 'user_news_embedding')
-        An = _boolc(news_graph, 'news_graph')
-        Au = _boolc(user_graph, 'user_graph')
-        Mn = _boolc(news_graph_mask, 'news_graph_mask')
-        Mc = _boolc(user_category_mask, 'user_category_mask')
-        if user_category_indices.dtype != torch.int64 or not user_category_indices.is_cuda:
-            raise RuntimeError('user_category_indices must be a CUDA int64 tensor')
-        ci = user_category_indices.contiguous()
-        B = Xn.shape[0]
-        if Xn.shape[1:] != (self.news_graph_size, self.news_embedding_dim) or \
-           Xh.shape != (B, self.max_history_num, self.news_embedding_dim) or \
-           An.shape != (B, self.news_graph_size, self.news_graph_size) or \
-           Au.shape != (B, self.user_graph_size, self.user_graph_size) or \
-           Mn.shape != (B, self.news_graph_size) or Mc.shape != (B, self.category_num) or \
-           ci.shape != (B, self.max_history_num):
-            raise RuntimeError('DIGAT: inconsistent input shapes')
-        return Xn, An, Mn, Xh, Au, Mc, ci
-
-    # ---------------------------------------------------------------------------------- reference API
-    def compute_news_graph_context(self, news_graph_embeddings, news_graph_mask):
-        w = self._weights()
-        with torch.no_grad():
-            return self._news_ctx(w, _f32c(news_graph_embeddings, 'news_graph_embeddings'),
-                                  _boolc(news_graph_mask, 'news_graph_mask'))
-
-    def compute_user_graph_context(self, user_graph_embeddings, user_category_mask, user_category_indices,
-                                   news_graph_context):
-        w = self._weights()
-        with torch.no_grad():
-            return self._user_ctx(w, _f32c(user_graph_embeddings, 'user_graph_embeddings'),
-                                  _boolc(user_category_mask, 'user_category_mask'), user_category_indices.contiguous(),
-                                  _f32c(news_graph_context, 'news_graph_context'))
-
-    def compute_news_graph_embeddings(self, index, news_graph_embeddings, news_graph, user_graph_context):
-        w = self._weights()
-        with torch.no_grad():
-            return self._layer(w, 'news', index, _f32c(news_graph_embeddings, 'news_graph_embeddings'),
-                               _boolc(news_graph, 'news_graph'), _f32c(user_graph_context, 'user_graph_context'))
-
-    def compute_user_graph_embeddings(self, index, user_graph_embeddings, user_graph, news_graph_context):
-        w = self._weights()
-        with torch.no_grad():
-            return self._layer(w, 'user', index, _f32c(user_graph_embeddings, 'user_graph_embeddings'),
-                               _boolc(user_graph, 'user_graph'), _f32c(news_graph_context, 'news_graph_context'))
-
-    def _encode(self, w, Xn, An, Mn, Xu, Au, Mc, ci, c_n, share=None):
-        """The L-layer dual-graph schedule of graphEncoders.py:180-198 on prebuilt node tensors.
-        Xu [B, H+C, D] already holds [history ; topic nodes]; c_n None = compute the initial news context.
-        share [B] int32 (scoring path): Xu / Au / ci are per-BEHAVIOUR tables and pair b uses entry share[b]; the
-        user graph's layer-0 projection and node build then run once per behaviour (results are bit-identical)."""
-        if c_n is None:
-            c_n = self._news_ctx(w, Xn, Mn)
-        c_u = self._user_ctx(w, Xu, Mc, ci, c_n, src_index=share)
-        for i in range(self.graph_depth):
-            Xn_new = self._layer(w, 'news', i, Xn, An, c_u)
-            Xu = self._layer(w, 'user', i, Xu, Au, c_n, share=share if i == 0 else None,
-                             adj_index=share if i > 0 else None)
-            Xn = Xn_new
-            c_n = self._news_ctx(w, Xn, Mn, ctx_in=c_n)
-            # from layer 1 on every pair owns its user-node tensor; only the (integer) category ids stay shared
-            c_u = self._user_ctx_after(w, Xu, Mc, ci, c_n, c_u, share)
-        return c_n, c_u
-
-    def _user_ctx_after(self, w, Xu, Mc, ci, c_n, c_u, share):
-        if share is None:
-            return self._user_ctx(w, Xu, Mc, ci, c_n, ctx_in=c_u)
-        if getattr(self, '_ci_pairs', None) is None or self._ci_pairs[0] is not share:
-            self._ci_pairs = (share, ci.index_select(0, share.long()))          # [B,H] int64 gather once per batch
-        return self._user_ctx(w, Xu, Mc, self._ci_pairs[1], c_n, ctx_in=c_u)
 
     def inference(self, news_graph_embeddings, news_graph, news_graph_mask, user_news_embedding, user_graph,
                   user_category_mask, user_category_indices, news_graph_context):

@@ -123,11 +123,34 @@ class Scorer:
             return logits(cn, cu)
 
     def score_host_batch(self, user_title_index, user_graph, user_category_mask, user_category_indices, news_ID,
-                         news_graph, news_graph_mask):
-        """The reference hot loop body (util.py:56-68) on HOST tensors (pinned for async copies)."""
+                         news_graph, news_graph_mask, share_user_graphs=True):
+        """The reference hot loop body (util.py:56-68) on HOST tensors (pinned for async copies).
+
+        The DataLoader repeats the user tensors for every candidate of an impression (MIND_dataset.py:97-102).
+        Consecutive rows with the same clicked-news history have the same user graph / category tensors (they are
+        functions of the history, MIND_corpus.py:143-176), so they are detected on the device and encoded through the
+        shared-user-graph path (bit-identical results)."""
         d = lambda x: x.to(self.dev, non_blocking=True)
-        return self._score(d(user_title_index).to(torch.int32), d(user_graph), d(user_category_mask),
-                           d(user_category_indices), d(news_ID).to(torch.int32), d(news_graph), d(news_graph_mask))
+        hist = d(user_title_index).to(torch.int32)
+        Au, Mc, ci = d(user_graph), d(user_category_mask), d(user_category_indices)
+        news_i32 = d(news_ID).to(torch.int32)
+        An, Mn = d(news_graph), d(news_graph_mask)
+        if not share_user_graphs or hist.shape[0] < 2:
+            return self._score(hist, Au, Mc, ci, news_i32, An, Mn)
+        first = torch.ones(hist.shape[0], dtype=torch.bool, device=self.dev)
+        first[1:] = (hist[1:] != hist[:-1]).any(dim=1)
+        share = (torch.cumsum(first, 0) - 1).to(torch.int32)
+        rows = first.nonzero(as_tuple=True)[0]
+        w = self.enc._weights()
+        if self.c_n0 is None:
+            self.cache_news_context()
+        with torch.no_grad():
+            Xn = self.gather_sag(news_i32)
+            Xu_b = self.user_nodes(hist.index_select(0, rows))
+            c0 = self.gather_rows(self.c_n0, news_i32)
+            cn, cu = self.enc._encode(w, Xn, An, Mn, Xu_b, Au.index_select(0, rows), Mc, ci.index_select(0, rows), c0,
+                                      share=share)
+            return logits(cn, cu)
 
     def check_index_errors(self):
         if int(self.err.item()) != 0:

@@ -42,14 +42,15 @@ int         digat_device_check(int* sm_count);
  * --------------------------------------------------------------------------------------------------------- */
 
 /* Optional row-group bias of both GEMMs (group_bias may be NULL):
- *   C[m, group_col0 + c] += group_bias[(m / group_rows) * group_cols + c],  c in [0, group_cols)
+ *   C[m, group_col0 + c] += group_bias[(m / group_rows) * group_ld + c],  c in [0, group_cols)
  * It folds k3 = ffn3(context) + b3 (graphEncoders.py:149/169, one row per graph) into the K1 block of the node
  * projections, so the GEMM emits U = fl(k3 + K1): the first broadcast add of Eq. (8) with the reference's rounding. */
 
 /* Exact-fp32 CUDA-core GEMM (FFMA, fp32 accumulate).  Any M,N; K % 4 == 0. */
 int digat_linear_f32(const float* A, int lda, const float* W, int ldw, const float* bias,
                      float* C, int ldc, int M, int N, int K, int relu,
-                     const float* group_bias, int group_rows, int group_col0, int group_cols, void* stream);
+                     const float* group_bias, int group_rows, int group_col0, int group_cols, int group_ld,
+                     void* stream);
 
 /* Splits W into the two TF32 planes used by digat_linear_tf32x3: hi = rna_tf32(W), lo = rna_tf32(W - hi). */
 int digat_split_tf32(const float* W, float* W_hi, float* W_lo, int64_t count, void* stream);
@@ -61,7 +62,8 @@ int digat_split_tf32(const float* W, float* W_hi, float* W_lo, int64_t count, vo
  * layer as ONE GEMM against the stacked [3D, D] weight (graphEncoders.py:146-148 / 166-168). */
 int digat_linear_tf32x3(const float* A, int lda, const float* W_hi, const float* W_lo, int ldw,
                         const float* bias, float* C, int ldc, int M, int N, int K,
-                        const float* group_bias, int group_rows, int group_col0, int group_cols, void* stream);
+                        const float* group_bias, int group_rows, int group_col0, int group_cols, int group_ld,
+                     void* stream);
 
 /* Tuning/experiment switch for digat_linear_tf32x3 tile variants (0 = default).  Not part of the reference path. */
 int digat_debug_set_gemm_variant(int variant);
@@ -83,20 +85,20 @@ int digat_debug_set_gemm_variant(int variant);
  * by TMA (2-deep pipeline).  n <= 128, D % 4 == 0, D <= 1024.
  * De-duplicated scoring (each may be NULL): the ~37 candidate pairs of one impression share the user graph, so its
  * layer-0 projection is computed once per behaviour: px_index [B] makes graph b read P and X of graph px_index[b]
- * (tables with n_src graphs; P then holds K1 WITHOUT k3) and k3 [B,D] is added to the staged K1 tile in-kernel
+ * (tables with n_src graphs; P then holds K1 WITHOUT k3) and k3 [B,ldk3] is added to the staged K1 tile in-kernel
  * (same fp32 add as the GEMM's row-group bias, so results are bit-identical to the expanded path); adj_index [B]
  * makes graph b read adj of graph adj_index[b] (per-behaviour user graphs, no per-pair copy).
  * --------------------------------------------------------------------------------------------------------- */
 int digat_graph_layer_fwd(const float* P, int ldp, const float* a, const uint8_t* adj, const float* X, float* Y,
                           int B, int n, int D, const uint8_t* drop_keep, float drop_scale, float* score_out,
                           float* alpha_out, uint8_t* relu_mask_out, const int32_t* px_index, int n_src,
-                          const int32_t* adj_index, const float* k3, void* stream);
+                          const int32_t* adj_index, const float* k3, int ldk3, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Masked single-query attention pooling (replaces layers.py:199-206 after folding W_K into the query:
  * a_k = F_k . v / sqrt(D) with v = W_K^T (W_Q q + b_Q)):
  *   out[b] = sum_k softmax_k(mask(F[b,k] . v[b] / sqrt(D))) F[b,k]
- *   F [B, m, D] with row stride ldf and batch stride strideF (elements); mask [B,m] bool; v [B,D].
+ *   F [B, m, D] with row stride ldf and batch stride strideF (elements); mask [B,m] bool; v [B,D] with row pitch ldv.
  * If resid_F != NULL the pooled features are F' = relu(F) + resid_F (graphEncoders.py:131, featureAffine output
  * in F, topic embeddings in resid_F).  out has leading dimension ldo (so it can land inside a [B,2D] buffer).
  * add_in [B, ldo] optional: out = add_in + pooled (context accumulation, graphEncoders.py:186/197; may alias out).
@@ -104,7 +106,7 @@ int digat_graph_layer_fwd(const float* P, int ldp, const float* a, const uint8_t
  * that [l | g] lands in one [B,2D] buffer for the gate projection).  alpha_out [B,m] optional.
  * --------------------------------------------------------------------------------------------------------- */
 int digat_attention_pool_fwd(const float* F, int64_t strideF, int ldf, const float* resid_F,
-                             const float* v, const uint8_t* mask, const float* add_in, float* out, int ldo,
+                             const float* v, int ldv, const uint8_t* mask, const float* add_in, float* out, int ldo,
                              float* first_out, float* alpha_out, int B, int m, int D, void* stream);
 
 /* News-graph gate (graphEncoders.py:112-113): ctx_out = ctx_in + sigmoid(z) * l + (1 - sigmoid(z)) * g
@@ -121,7 +123,7 @@ int digat_news_gate_fwd(const float* z, const float* lg, const float* ctx_in, fl
  *   Xh = first H rows of X_u [B, n_u, D] (batch stride strideX elements); cidx int64 [B,H] in [0,n_seg).
  * alpha_out [B,H] optional.  err_flag: see the gathers below.  src_index [B] optional: row b reads Xu and cidx of
  * row src_index[b] (user graphs shared by the pairs of one impression). */
-int digat_topic_segment_fwd(const float* Xu, int64_t strideX, const float* v, const int64_t* cidx,
+int digat_topic_segment_fwd(const float* Xu, int64_t strideX, const float* v, int ldv, const int64_t* cidx,
                             float* T, float* alpha_out, int32_t* err_flag, const int32_t* src_index,
                             int B, int H, int n_seg, int D, void* stream);
 

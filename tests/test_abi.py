@@ -42,14 +42,14 @@ def test_invalid_arguments_return_error_codes():
     """Argument validation happens before any CUDA call, so it can be exercised without a GPU."""
     from digat_b200 import _lib
     lib = _lib.load()
-    assert lib.digat_linear_f32(None, 4, None, 4, None, None, 4, 1, 1, 4, 0, None, 1, 0, 0, None) == -1
+    assert lib.digat_linear_f32(None, 4, None, 4, None, None, 4, 1, 1, 4, 0, None, 1, 0, 0, 0, None) == -1
     assert 'null' in _lib.last_error()
     buf = (ctypes.c_float * 64)()
     p = ctypes.addressof(buf)
     p = (p + 15) & ~15
-    assert lib.digat_linear_f32(p, 6, p, 8, None, p, 8, 1, 1, 6, 0, None, 1, 0, 0, None) == -1        # K not multiple of 4
-    assert lib.digat_graph_layer_fwd(p, 12, p, p, p, p, 1, 500, 4, None, 1.0, None, None, None, None, 0, None, None, None) == -1   # n too large
-    assert lib.digat_attention_pool_fwd(p, 8, 8, None, p, p, None, p, 8, None, None, 1, 1000, 8, None) == -1
+    assert lib.digat_linear_f32(p, 6, p, 8, None, p, 8, 1, 1, 6, 0, None, 1, 0, 0, 0, None) == -1        # K not multiple of 4
+    assert lib.digat_graph_layer_fwd(p, 12, p, p, p, p, 1, 500, 4, None, 1.0, None, None, None, None, 0, None, None, 0, None) == -1   # n too large
+    assert lib.digat_attention_pool_fwd(p, 8, 8, None, p, 8, p, None, p, 8, None, None, 1, 1000, 8, None) == -1
 
 
 def test_state_dict_names_match_reference_layout():
