@@ -311,6 +311,13 @@ graph_layer_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
             uint64_t od[4][2], ox[4][2];
 #pragma unroll
             for (int k = 0; k < 4; ++k) od[k][0] = od[k][1] = ox[k][0] = ox[k][1] = 0ull;
+            {   // the residual rows are needed only after the j loop: pull them into L2 now (no registers held)
+                const size_t xrow0 = (p.px_index != nullptr ? (size_t)src0 : (size_t)(b0 + r)) * n + i0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (i0 + k < n)
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"(p.X + (xrow0 + k) * D + c0 + 4 * q));
+            }
 #pragma unroll 2
             for (int j = 0; j < n; ++j) {
                 const float4 h = *reinterpret_cast<const float4*>(Hs);
