@@ -4,6 +4,7 @@
 #include "gemm_simt.cuh"
 #include "gemm_tcgen05.cuh"
 #include "pair_attention.cuh"
+#include "pair_attention_sparse.cuh"
 #include "context.cuh"
 #include "gather.cuh"
 #include "pair_attention_bwd.cuh"
@@ -53,6 +54,11 @@ int digat_linear_tf32x3(const float* A, int lda, const float* W_hi, const float*
                         int group_col0, int group_cols, int group_ld, void* stream) {
     return launch_linear_tf32x3(A, lda, W_hi, W_lo, ldw, bias, C, ldc, M, N, K,
                                 GroupBias{group_bias, group_rows, group_col0, group_cols, group_ld}, as_stream(stream));
+}
+
+int digat_debug_set_layer_mode(int mode) {
+    g_layer_mode = mode;
+    return DIGAT_OK;
 }
 
 int digat_debug_set_gemm_variant(int variant) {

@@ -389,6 +389,10 @@ inline void pair_attn_geometry(int n, int D, int B, bool indexed, PairAttnGeom* 
     g->nch3 = (D + 2 * dc - 1) / (2 * dc); g->lds = lds; g->tile_floats = tile_floats(R); g->smem = smem_of(R);
 }
 
+struct PairAttnArgs;
+int launch_graph_layer_fwd_sparse(const PairAttnArgs& args, int n_src, cudaStream_t st);    // pair_attention_sparse.cuh
+static int g_layer_mode = 0;   // 0 = auto (edge-driven kernel for single-graph CTAs at inference), 1 = dense, 2 = edge-driven
+
 inline int launch_graph_layer_fwd(const float* P, int ldp, const float* a, const uint8_t* adj, const float* X, float* Y,
                                   int B, int n, int D, const uint8_t* drop_keep, float drop_scale, float* score_out,
                                   float* alpha_out, uint8_t* relu_mask_out, const int32_t* px_index, int n_src,
@@ -416,6 +420,9 @@ inline int launch_graph_layer_fwd(const float* P, int ldp, const float* a, const
     if ((rc = make_tensor_map_2d(&map3, P, src_graphs * n, 3 * D, ldp, g.R * n, g.dc3, CU_TENSOR_MAP_SWIZZLE_NONE)) != DIGAT_OK) return rc;
     PairAttnArgs args{P, ldp, a, adj, X, Y, B, n, D, drop_keep, drop_scale, score_out, alpha_out, relu_mask_out,
                       px_index, adj_index, k3, ldk3};
+    const bool inference = !drop_keep && !score_out && !alpha_out && !relu_mask_out;
+    if (inference && g_layer_mode != 1 && (g.R == 1 || g_layer_mode == 2))
+        return launch_graph_layer_fwd_sparse(args, n_src, st);
     const int grid = (B + g.R - 1) / g.R;
     const bool single = g.R * g.nt * g.nt <= kPairThreads;
     if (single) {

@@ -67,6 +67,9 @@ int digat_linear_tf32x3(const float* A, int lda, const float* W_hi, const float*
 
 /* Tuning/experiment switch for digat_linear_tf32x3 tile variants (0 = default).  Not part of the reference path. */
 int digat_debug_set_gemm_variant(int variant);
+/* digat_graph_layer_fwd kernel choice: 0 = auto (edge-driven kernel when a CTA owns one graph and no training extras are
+ * requested, dense kernel otherwise), 1 = always dense, 2 = always edge-driven (inference).  For tests / profiling. */
+int digat_debug_set_layer_mode(int mode);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Fused Eq. (8) graph-attention layer (replaces graphEncoders.py:150-153 / 170-173).
