@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tcgen05.cuh"
+#include "gemm_tcgen05_pair.cuh"
 #include "pair_attention.cuh"
 #include "pair_attention_sparse.cuh"
 #include "context.cuh"
