@@ -25,6 +25,7 @@ namespace digat {
 constexpr int kTcBK = 16;                       // fp32 elements per k-block = 64 bytes = SWIZZLE_64B span
 constexpr int kTcThreads = 192;
 constexpr int kTcTransformThreads = 128;
+constexpr int kTcPrefetchBlocks = 40;          // M blocks between a CTA and the block whose A rows it prefetches into L2
 
 // K-major operand tile, SWIZZLE_64B: rows of 64 bytes, 8-row groups of 512 bytes (SBO), version 1 (sm_100).
 __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
@@ -52,6 +53,9 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
                  :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float tf32_trunc(float x) {      // what the tensor core sees of an fp32 operand
+    return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
 }
 __device__ __forceinline__ float to_tf32_rna(float x) {
     uint32_t r;
@@ -129,10 +133,23 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+#ifdef DIGAT_TC_TIMING
+    const long long t_start = clock64();
+#endif
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
+            // A is touched first by the CTAs of one M block, all at the same time: every one of them would wait for DRAM.
+            // The first N tile of each M block therefore pulls the A rows of a LATER M block (one that starts roughly a
+            // wave from now) into L2, so that the loads of the main loop see L2 latency instead of DRAM latency.
+            if (blockIdx.x == 0) {
+                const int ahead = (int)blockIdx.y + kTcPrefetchBlocks;
+                if (ahead < (int)gridDim.y)
+                    for (int kb = 0; kb < nkb; ++kb)
+                        asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
+                                     :: "l"(reinterpret_cast<uint64_t>(&map_a)), "r"(kb * kTcBK), "r"(ahead * Cfg::BM) : "memory");
+            }
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % Cfg::STAGES;
                 const uint32_t ph = (kb / Cfg::STAGES) & 1;
@@ -145,33 +162,65 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
+        // The tensor core reads only the upper 19 bits of an fp32 operand (TF32 = truncation), so the RAW A tile is the
+        // "hi" operand as it lands from TMA: the main product and the A_hi*W_lo correction are issued as soon as the
+        // stage is full, and only the A_lo*W_hi correction waits for the transform warps -- one stage later, so the
+        // split of stage s is hidden behind the four independent MMAs of stage s+1.
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_tf32(128, BN);
-            for (int kb = 0; kb < nkb; ++kb) {
+            auto issue_raw = [&](int kb) {                        // products that need no transformed operand
                 const int s = kb % Cfg::STAGES;
-                const uint32_t ph = (kb / Cfg::STAGES) & 1;
-                mbar_wait(&ready[s], ph);
+                mbar_wait(&full[s], (kb / Cfg::STAGES) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint64_t d_whi = umma_desc_sw64(smem_u32(w_hi(s)));
-                const uint64_t d_wlo = umma_desc_sw64(smem_u32(w_lo(s)));
+                const uint64_t d_whi = umma_desc_sw64(smem_u32(w_hi(s))), d_wlo = umma_desc_sw64(smem_u32(w_lo(s)));
 #pragma unroll
                 for (int h = 0; h < MH; ++h) {
                     const uint64_t d_ahi = umma_desc_sw64(smem_u32(a_hi(s) + h * 128 * kTcBK * 4));
-                    const uint64_t d_alo = umma_desc_sw64(smem_u32(a_lo(s) + h * 128 * kTcBK * 4));
                     const uint32_t d_main = tmem_base + (uint32_t)(h * BN);
                     const uint32_t d_corr = SPLIT ? tmem_base + (uint32_t)((MH + h) * BN) : d_main;
 #pragma unroll
                     for (int k = 0; k < kTcBK / 8; ++k) {
-                        const uint64_t koff = (uint64_t)((k * 8 * 4) >> 4);       // 32 bytes per k-step, in 16-byte units
+                        const uint64_t koff = (uint64_t)((k * 8 * 4) >> 4);   // 32 bytes per k-step, in 16-byte units
                         const uint32_t first = (kb > 0 || k > 0) ? 1u : 0u;
                         umma_tf32(d_main, d_ahi + koff, d_whi + koff, idesc, first);
-                        umma_tf32(d_corr, d_alo + koff, d_whi + koff, idesc, SPLIT ? first : 1u);
-                        umma_tf32(d_corr, d_ahi + koff, d_wlo + koff, idesc, 1u);
+                        umma_tf32(d_corr, d_ahi + koff, d_wlo + koff, idesc, SPLIT ? first : 1u);
                     }
                 }
-                umma_commit(&empty[s]);            // frees the smem stage once these MMAs retire
+            };
+            auto issue_lo = [&](int kb) {                         // A_lo * W_hi, then release the stage
+                const int s = kb % Cfg::STAGES;
+                mbar_wait(&ready[s], (kb / Cfg::STAGES) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint64_t d_whi = umma_desc_sw64(smem_u32(w_hi(s)));
+#pragma unroll
+                for (int h = 0; h < MH; ++h) {
+                    const uint64_t d_alo = umma_desc_sw64(smem_u32(a_lo(s) + h * 128 * kTcBK * 4));
+                    const uint32_t d_corr = SPLIT ? tmem_base + (uint32_t)((MH + h) * BN) : tmem_base + (uint32_t)(h * BN);
+#pragma unroll
+                    for (int k = 0; k < kTcBK / 8; ++k) {
+                        const uint64_t koff = (uint64_t)((k * 8 * 4) >> 4);
+                        umma_tf32(d_corr, d_alo + koff, d_whi + koff, idesc, 1u);
+                    }
+                }
+                umma_commit(&empty[s]);            // frees the smem stage once every MMA issued so far has retired
+            };
+            issue_raw(0);
+#ifdef DIGAT_TC_TIMING
+            const long long t_first = clock64();
+#endif
+            for (int kb = 0; kb < nkb; ++kb) {
+                if (kb + 1 < nkb) issue_raw(kb + 1);
+                issue_lo(kb);
             }
             umma_commit(accum_full);               // accumulators complete
+#ifdef DIGAT_TC_TIMING
+            const long long t_issued = clock64();
+            mbar_wait(accum_full, 0);
+            const long long t_done = clock64();
+            if (blockIdx.x == 2 && (blockIdx.y % 997) == 5)
+                printf("tile(%d,%d): first MMA issued +%lld, all issued +%lld, accum done +%lld\n", blockIdx.x, blockIdx.y,
+                       t_first - t_start, t_issued - t_start, t_done - t_start);
+#endif
         }
     } else {
         // ------------------------------------------------------------------ operand transform, then epilogue
@@ -185,12 +234,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 #pragma unroll
             for (int i = 0; i < Cfg::A_BYTES / 16 / kTcTransformThreads; ++i) {
                 const int idx = t + i * kTcTransformThreads;     // elementwise: the swizzle pattern is irrelevant
+                // the raw tile stays untouched (the tensor core truncates it to TF32 itself); lo = rna_tf32(A - trunc(A))
                 const float4 v = hi[idx];
-                float4 vh, vl;
-                vh.x = to_tf32_rna(v.x); vh.y = to_tf32_rna(v.y); vh.z = to_tf32_rna(v.z); vh.w = to_tf32_rna(v.w);
-                vl.x = to_tf32_rna(v.x - vh.x); vl.y = to_tf32_rna(v.y - vh.y);
-                vl.z = to_tf32_rna(v.z - vh.z); vl.w = to_tf32_rna(v.w - vh.w);
-                hi[idx] = vh;
+                float4 vl;
+                vl.x = to_tf32_rna(v.x - tf32_trunc(v.x)); vl.y = to_tf32_rna(v.y - tf32_trunc(v.y));
+                vl.z = to_tf32_rna(v.z - tf32_trunc(v.z)); vl.w = to_tf32_rna(v.w - tf32_trunc(v.w));
                 lo[idx] = vl;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
@@ -202,11 +250,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q = warp & 3;
         const bool has_gb = gb.ptr != nullptr;
+        float* stage = reinterpret_cast<float*>(smem) + q * (32 * 20);     // per-warp 32 x (16+4) staging block
 #pragma unroll
         for (int h = 0; h < MH; ++h) {
             const int m = m0 + h * 128 + q * 32 + lane;
             const bool row_ok = m < M;
-            float* crow = C + (size_t)m * ldc + n0;
             const float* grow = (has_gb && row_ok) ? gb.ptr + (size_t)(m / gb.rows) * gb.ld - gb.col0 + n0 : nullptr;
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * BN);
             uint32_t rm[16], rc[16];
@@ -248,16 +296,31 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     o[v4 * 4 + 2] += gq[v4].z; o[v4 * 4 + 3] += gq[v4].w;
                 }
                 if (c + 16 < BN) issue_group(c + 16);                // next group's loads overlap these stores
-                if (row_ok) {
+                // A thread owns one ROW of the tile, so direct stores would scatter 16-byte pieces over 32 rows per
+                // instruction (measured: the epilogue was LSU-transaction-bound, 10.5k of 36k cycles per tile).  Stage the
+                // 32 x 16 block through shared memory (the pipeline stages are idle now) and write 64-byte row segments:
+                // 4 lanes per row, 8 rows per instruction.
+                __syncwarp();
 #pragma unroll
-                    for (int v4 = 0; v4 < 4; ++v4)
-                        if (n0 + c + v4 * 4 < N)             // N % 4 == 0; the last N tile may be partial (TMA zero-fills W)
-                            *reinterpret_cast<float4*>(crow + c + v4 * 4) =
-                            make_float4(o[v4 * 4 + 0], o[v4 * 4 + 1], o[v4 * 4 + 2], o[v4 * 4 + 3]);
+                for (int v4 = 0; v4 < 4; ++v4)
+                    *reinterpret_cast<float4*>(stage + lane * 20 + v4 * 4) =
+                        make_float4(o[v4 * 4 + 0], o[v4 * 4 + 1], o[v4 * 4 + 2], o[v4 * 4 + 3]);
+                __syncwarp();
+#pragma unroll
+                for (int t4 = 0; t4 < 4; ++t4) {
+                    const int f = t4 * 32 + lane, row = f >> 2, cq = f & 3;
+                    const int mr = m0 + h * 128 + q * 32 + row;
+                    if (mr < M && n0 + c + cq * 4 < N)          // N % 4 == 0; the last N tile may be partial
+                        *reinterpret_cast<float4*>(C + (size_t)mr * ldc + n0 + c + cq * 4) =
+                            *reinterpret_cast<const float4*>(stage + row * 20 + cq * 4);
                 }
             }
         }
     }
+#ifdef DIGAT_TC_TIMING
+    if (threadIdx.x == 64 && blockIdx.x == 2 && (blockIdx.y % 997) == 5)
+        printf("tile(%d,%d): epilogue done +%lld\n", blockIdx.x, blockIdx.y, clock64() - t_start);
+#endif
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
