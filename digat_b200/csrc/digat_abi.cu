@@ -4,6 +4,7 @@
 #include "gemm_simt.cuh"
 #include "gemm_tcgen05.cuh"
 #include "gemm_tcgen05_pair.cuh"
+#include "gemm_tcgen05_persistent.cuh"
 #include "pair_attention.cuh"
 #include "pair_attention_sparse.cuh"
 #include "context.cuh"

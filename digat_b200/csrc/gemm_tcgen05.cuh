@@ -360,6 +360,9 @@ static int g_tc_variant = 0;   // experiment switch (digat_debug_set_gemm_varian
 template <int BN>
 int launch_tf32x3_pair(const float* A, int lda, const float* W_hi, const float* W_lo, int ldw, const float* bias,
                        float* C, int ldc, int M, int N, int K, GroupBias gb, cudaStream_t st);   // gemm_tcgen05_pair.cuh
+template <int BN>
+int launch_tf32x3_persistent(const float* A, int lda, const float* W_hi, const float* W_lo, int ldw, const float* bias,
+                             float* C, int ldc, int M, int N, int K, GroupBias gb, cudaStream_t st);   // gemm_tcgen05_persistent.cuh
 
 inline int launch_linear_tf32x3(const float* A, int lda, const float* W_hi, const float* W_lo, int ldw, const float* bias,
                                 float* C, int ldc, int M, int N, int K, GroupBias gb, cudaStream_t st) {
@@ -380,11 +383,13 @@ inline int launch_linear_tf32x3(const float* A, int lda, const float* W_hi, cons
     // variant 1: two halves per CTA for M > 16384, single accumulator (half the W traffic per flop, less accurate).
     const int variant = g_tc_variant;
     const bool big = M > 16384;
+    if (variant == 0 && big && N % 240 == 0 && N <= 1280) // persistent 128 x 240 tiles (variant 4 = one tile per CTA)
+        return launch_tf32x3_persistent<240>(A, lda, W_hi, W_lo, ldw, bias, C, ldc, M, N, K, gb, st);
     if (variant == 3 && N % 240 == 0)                    // 2-CTA (cta_group::2) 256 x 240 tiles
         return launch_tf32x3_pair<240>(A, lda, W_hi, W_lo, ldw, bias, C, ldc, M, N, K, gb, st);
     // small problems (few tiles) and odd widths: 128-wide tiles, two CTAs per SM (measured 1.45x faster at M = 4096);
     // the last N tile may be partial.  Large M keeps the 240-wide tile (fewer re-reads of A: measured 185 vs 158 TFLOP/s).
-    if (variant == 2 || N % 80 != 0 || (variant == 0 && (!big || (N % 240 != 0 && N % 160 != 0))))
+    if (variant == 2 || N % 80 != 0 || ((variant == 0 || variant == 4) && (!big || (N % 240 != 0 && N % 160 != 0))))
         return launch_tf32x3_cfg<128, 1, true>(A, lda, W_hi, W_lo, ldw, bias, C, ldc, M, N, K, gb, st);
 #define DIGAT_TC_DISPATCH(BN_)                                                                                      \
     do {                                                                                                            \

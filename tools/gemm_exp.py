@@ -5,9 +5,9 @@ def split(W):
     hi, lo = torch.empty_like(W), torch.empty_like(W)
     _lib.call('digat_split_tf32', W.data_ptr(), hi.data_ptr(), lo.data_ptr(), W.numel(), 0); return hi, lo
 st=0
-for variant in (0,):
+for variant in (4,0):
     _lib.call('digat_debug_set_gemm_variant', variant)
-    for (M,N,K) in [(300,240,64),(4096,1200,400),(40960,1200,400),(278528,1200,400),(77824,400,400)]:
+    for (M,N,K) in [(16500,240,64),(20000,1200,400),(40960,1200,400),(278528,1200,400)]:
         g=torch.Generator().manual_seed(1)
         A=torch.randn(M,K,generator=g).cuda(); W=(torch.randn(N,K,generator=g)*0.05).cuda(); b=torch.randn(N,generator=g).cuda()
         hi,lo=split(W); C=torch.empty(M,N,device='cuda')
