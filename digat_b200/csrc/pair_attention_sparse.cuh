@@ -3,18 +3,22 @@
 // The reference evaluates s_ij for all n^2 pairs and then overwrites the non-edges with -1e9
 // (graphEncoders.py:150-152).  A masked pair contributes exp(-1e9 - max) == 0.0f to the softmax of any row that has at
 // least one edge, so its score is never observable: this kernel computes s_ij ONLY on the edges of the adjacency and
-// aggregates over neighbours only -- bit-for-bit the same alpha and Y as the dense evaluation, with E instead of n^2
-// pair evaluations (MIND-shaped user graphs: E ~ 300-650 of 4624; SAG trees: ~2n of n^2).  A row without any edge
-// (cannot happen in the reference's data: the diagonal is always set) is handled like the reference: every entry is
-// -1e9, the softmax is uniform 1/n over ALL nodes.
+// aggregates over neighbours only -- the same alpha and Y as the dense evaluation, with E instead of n^2 pair
+// evaluations (MIND-shaped user graphs: E ~ 300-650 of 4624; SAG trees: ~2n of n^2).  A row without any edge (cannot
+// happen in the reference's data: the diagonal is always set) is handled like the reference: every entry is -1e9, the
+// softmax is uniform 1/n over ALL nodes.
 //
-// Structure (same 2-deep TMA pipeline and smem tiles as the dense kernel, pair_attention.cuh):
-//   setup    adjacency bytes -> CSR (row pointers, uint8 columns) with warp ballots + one warp scan
-//   phase 1  work item = (row i, up to 4 neighbours): K2_i quad in registers, U_j quads from smem, packed
-//            FADD2 / FMNMX / FFMA2; partial dot products accumulate into score[e] in smem once per feature chunk
-//   phase 2  one warp per row: leaky-relu, max/sum by shuffles over the row's CSR segment, exp, normalise
-//   phase 3  work item = (row i, feature quad): loop over the neighbours, FFMA2; relu + residual, streaming store
-// HBM traffic per graph is unchanged (P is still streamed once); the kernel moves from fp32-pipe-bound to HBM-bound.
+// With the pair work gone the kernel is bound by how fast P can be streamed in, so it is organised around the loads:
+//   warp 10   TMA producer: walks the load schedule (13 U|K2 units of 32 features, then 7 h units of 64 features)
+//             through a 4-deep ring of shared-memory buffers, waiting only on per-buffer "empty" mbarriers;
+//   warps 0-9 consumers: no CTA-wide barrier inside the streaming loops -- a warp waits on "full[buf]", does its share
+//             and arrives on "empty[buf]"; fast warps run up to 4 units ahead of slow ones.
+//   setup     adjacency bytes -> CSR (row pointers, uint8 row / column per edge) with warp ballots + one warp scan
+//   phase 1   one EDGE per thread: U_j and K2_i quads from smem, packed FADD2 / FMNMX / FFMA2, score[e] += partial
+//   phase 2   one warp per row: leaky-relu, max/sum by shuffles over the row's CSR segment, exp, normalise
+//   phase 3   half a warp per row, one lane per feature quad: loop over the row's neighbours (FFMA2), relu + residual
+// In indexed (de-duplicated) mode the shared K1 tile becomes this pair's U in registers: fl(fl(K1 + k3) + K2), the
+// reference's rounding.  HBM traffic per graph is unchanged: 5nD*4 + n^2 bytes.
 #pragma once
 #include "common.cuh"
 #include "tma.cuh"
@@ -22,75 +26,87 @@
 
 namespace digat {
 
-constexpr int kSparseItemEdges = 4;
+constexpr int kSparseConsumers = 320;                     // warps 0..9
+constexpr int kSparseThreads = kSparseConsumers + 32;     // + producer warp
+constexpr int kSparseBufs = 4;
+constexpr int kSparseDc1 = 32, kSparseDc3 = 64;
 
 struct SparseGeom {
-    int dc, nch1, dc3, nch3;
-    int tile_floats;       // floats of one [n][dc] tile rounded up to 128 bytes
-    int max_items;         // upper bound of phase-1 work items: sum_i ceil(deg_i / 4) <= n * ceil(n/4)
+    int nch1, nch3;
+    int tile_floats;       // floats of one [n][32] tile rounded up to 1024 bytes (SWIZZLE_128B atoms stay aligned)
+    int unit_floats;       // floats of one ring buffer = 2 tiles (>= the [n][64] h tile)
     size_t smem;
 };
 
-template <int kDummy>
-__global__ void __launch_bounds__(kPairThreads, 2)
+__device__ __forceinline__ void consumer_sync() {         // named barrier over the 10 consumer warps only
+    asm volatile("bar.sync 1, %0;" :: "n"(kSparseConsumers) : "memory");
+}
+
+template <bool kIndexed>
+__global__ void __launch_bounds__(kSparseThreads, 2)
 graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map3,
                               PairAttnArgs p, SparseGeom g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = p.n, D = p.D;
     const int b = blockIdx.x;
-    const int src0 = p.px_index != nullptr ? p.px_index[b] : b;
-    const int half = 2 * g.tile_floats;
+    const int src0 = kIndexed ? p.px_index[b] : b;
 
-    float* buf0 = reinterpret_cast<float*>(smem_raw);             // [2][half]   (multiple of 128 bytes)
-    uint64_t* full = reinterpret_cast<uint64_t*>(buf0 + 2 * half); // [2] TMA barriers
-    float* a_s = reinterpret_cast<float*>(full + 2);               // [D]
+    float* ring = reinterpret_cast<float*>(smem_raw);              // [kSparseBufs][unit_floats]
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring + kSparseBufs * g.unit_floats);   // [kSparseBufs]
+    uint64_t* empty = full + kSparseBufs;                          // [kSparseBufs]
+    float* a_s = reinterpret_cast<float*>(empty + kSparseBufs);    // [D]
     float* k3_s = a_s + D;                                         // [D]
     float* score = k3_s + D;                                       // [n*n] per-edge score, later alpha~
-    int* rowptr = reinterpret_cast<int*>(score + n * n);           // [n+1]
-    int* itemptr = rowptr + (n + 1);                               // [n+1] first phase-1 item of each row
-    int* items = itemptr + (n + 1);                                // [max_items] (row << 16) | first edge offset in row
-    uint8_t* col = reinterpret_cast<uint8_t*>(items + g.max_items); // [n*n] neighbour index of each edge
-    uint8_t* adj_s = col + n * n;                                  // [n*n] adjacency bytes
+    int* rowptr = reinterpret_cast<int*>(score + n * n);           // [n+2]
+    uint8_t* col = reinterpret_cast<uint8_t*>(rowptr + (n + 2));   // [n*n] neighbour (column) index of each edge
+    uint8_t* erow = col + n * n;                                   // [n*n] query (row) index of each edge
+    uint8_t* adj_s = erow + n * n;                                 // [n*n] adjacency bytes
     uint8_t* uniform_row = adj_s + n * n;                          // [n] 1 = row without edges (uniform softmax)
 
     if (tid == 0) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
+        for (int i = 0; i < kSparseBufs; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], kSparseConsumers / 32);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < D / 4; i += kPairThreads) {
+    __syncthreads();
+    const int n_loads = g.nch1 + g.nch3;
+
+    if (warp == kSparseConsumers / 32) {
+        // ------------------------------------------------------------------ producer warp
+        if (lane == 0) {
+            for (int l = 0; l < n_loads; ++l) {
+                const int buf = l % kSparseBufs;
+                float* dst = ring + buf * g.unit_floats;
+                mbar_wait(&empty[buf], ((uint32_t)(l / kSparseBufs) & 1u) ^ 1u);
+                if (l < g.nch1) {
+                    mbar_arrive_expect_tx(&full[buf], 2u * n * kSparseDc1 * 4u);
+                    tma_load_2d(dst, &map1, &full[buf], D + l * kSparseDc1, src0 * n);                     // U (or K1)
+                    tma_load_2d(dst + g.tile_floats, &map1, &full[buf], 2 * D + l * kSparseDc1, src0 * n);  // K2
+                } else {
+                    mbar_arrive_expect_tx(&full[buf], (uint32_t)n * kSparseDc3 * 4u);
+                    tma_load_2d(dst, &map3, &full[buf], (l - g.nch1) * kSparseDc3, src0 * n);              // h
+                }
+            }
+        }
+        return;                                                    // consumers synchronise among themselves (barrier 1)
+    }
+
+    // ---------------------------------------------------------------------- consumers: setup (overlaps the first loads)
+    for (int i = tid; i < D / 4; i += kSparseConsumers) {
         reinterpret_cast<float4*>(a_s)[i] = reinterpret_cast<const float4*>(p.a)[i];
-        if (p.k3 != nullptr)
-            reinterpret_cast<float4*>(k3_s)[i] = reinterpret_cast<const float4*>(p.k3 + (size_t)b * p.ldk3)[i];
+        if (kIndexed) reinterpret_cast<float4*>(k3_s)[i] = reinterpret_cast<const float4*>(p.k3 + (size_t)b * p.ldk3)[i];
     }
     {
         const size_t ag = p.adj_index != nullptr ? (size_t)p.adj_index[b] : (size_t)b;
         const uint8_t* srcp = p.adj + ag * n * n;
-        for (int i = tid; i < n * n; i += kPairThreads) adj_s[i] = srcp[i];
+        for (int i = tid; i < n * n; i += kSparseConsumers) adj_s[i] = srcp[i];
     }
-    __syncthreads();
-
-    const int n_loads = g.nch1 + g.nch3;
-    auto issue = [&](int l) {
-        float* dst = buf0 + (l & 1) * half;
-        if (l < g.nch1) {
-            mbar_arrive_expect_tx(&full[l & 1], 2u * n * g.dc * 4u);
-            tma_load_2d(dst, &map1, &full[l & 1], D + l * g.dc, src0 * n);
-            tma_load_2d(dst + g.tile_floats, &map1, &full[l & 1], 2 * D + l * g.dc, src0 * n);
-        } else {
-            mbar_arrive_expect_tx(&full[l & 1], (uint32_t)n * g.dc3 * 4u);
-            tma_load_2d(dst, &map3, &full[l & 1], (l - g.nch1) * g.dc3, src0 * n);
-        }
-    };
-    if (tid == 0) {
-        issue(0);
-        if (n_loads > 1) issue(1);
-    }
-
-    // ------------------------------------------------------------------ CSR of the adjacency (overlaps the first TMA loads)
-    // pass A: degrees (a row without edges becomes a full row with uniform weights)
-    for (int i = warp; i < n; i += kPairThreads / 32) {
+    consumer_sync();
+    // CSR pass A: degrees (a row without edges becomes a full row with uniform weights)
+    for (int i = warp; i < n; i += kSparseConsumers / 32) {
         int deg = 0;
         for (int k = 0; k < (n + 31) / 32; ++k) {
             const int j = lane + 32 * k;
@@ -98,31 +114,28 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
         }
         if (lane == 0) {
             uniform_row[i] = deg == 0;
-            if (deg == 0) deg = n;
-            rowptr[i + 1] = deg;                                   // degrees for now, scanned below
-            itemptr[i + 1] = (deg + kSparseItemEdges - 1) / kSparseItemEdges;
+            rowptr[i + 1] = deg == 0 ? n : deg;                    // degrees for now, scanned below
         }
     }
-    __syncthreads();
+    consumer_sync();
     if (warp == 0) {                                               // inclusive scan of <= 128 entries by one warp
-        int run_e = 0, run_i = 0;
+        int run_e = 0;
         for (int base = 0; base < n; base += 32) {
             const int i = base + lane;
-            int ve = i < n ? rowptr[i + 1] : 0, vi = i < n ? itemptr[i + 1] : 0;
+            int ve = i < n ? rowptr[i + 1] : 0;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const int te = __shfl_up_sync(0xffffffffu, ve, o), ti = __shfl_up_sync(0xffffffffu, vi, o);
-                if (lane >= o) { ve += te; vi += ti; }
+                const int te = __shfl_up_sync(0xffffffffu, ve, o);
+                if (lane >= o) ve += te;
             }
-            if (i < n) { rowptr[i + 1] = run_e + ve; itemptr[i + 1] = run_i + vi; }
+            if (i < n) rowptr[i + 1] = run_e + ve;
             run_e += __shfl_sync(0xffffffffu, ve, 31);
-            run_i += __shfl_sync(0xffffffffu, vi, 31);
         }
-        if (lane == 0) { rowptr[0] = 0; itemptr[0] = 0; }
+        if (lane == 0) rowptr[0] = 0;
     }
-    __syncthreads();
-    // pass B: columns, phase-1 items, zeroed scores
-    for (int i = warp; i < n; i += kPairThreads / 32) {
+    consumer_sync();
+    // CSR pass B: column / row index of every edge, zeroed scores
+    for (int i = warp; i < n; i += kSparseConsumers / 32) {
         const int e0 = rowptr[i];
         const bool uni = uniform_row[i] != 0;
         int filled = 0;
@@ -130,84 +143,66 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
             const int j = lane + 32 * k;
             const bool on = j < n && (uni || adj_s[i * n + j] != 0);
             const unsigned m = __ballot_sync(0xffffffffu, on);
-            if (on) col[e0 + filled + __popc(m & ((1u << lane) - 1u))] = (uint8_t)j;
+            if (on) {
+                const int e = e0 + filled + __popc(m & ((1u << lane) - 1u));
+                col[e] = (uint8_t)j;
+                erow[e] = (uint8_t)i;
+            }
             filled += __popc(m);
         }
-        const int it0 = itemptr[i], nit = itemptr[i + 1] - it0;
-        for (int t = lane; t < nit; t += 32) items[it0 + t] = (i << 16) | (t * kSparseItemEdges);
     }
-    const int E = rowptr[n], n_items = itemptr[n];
-    for (int e = tid; e < E; e += kPairThreads) score[e] = 0.f;
-    __syncthreads();
+    const int E = rowptr[n];
+    for (int e = tid; e < E; e += kSparseConsumers) score[e] = 0.f;
+    consumer_sync();
 
-    // ------------------------------------------------------------------ phase 1: scores on the edges only
+    // ---------------------------------------------------------------------- phase 1: scores on the edges only
+    const uint32_t a_off = (uint32_t)(reinterpret_cast<uint8_t*>(a_s) - smem_raw);
+    const uint32_t k3_off = (uint32_t)(reinterpret_cast<uint8_t*>(k3_s) - smem_raw);
     for (int l = 0; l < g.nch1; ++l) {
-        const int c0 = l * g.dc;
-        const int wq = min(g.dc, D - c0) >> 2;
-        float* Ut = buf0 + (l & 1) * half;
-        mbar_wait(&full[l & 1], (uint32_t)(l >> 1) & 1u);
-        if (p.k3 != nullptr) {                                     // indexed mode: shared K1 tile -> this pair's U tile
-            for (int it = tid; it < n * wq; it += kPairThreads) {
-                const int row = it / wq, q = it - row * wq;
-                float4* u = reinterpret_cast<float4*>(Ut + row * g.dc + 4 * q);
-                const float4 k = *reinterpret_cast<const float4*>(k3_s + c0 + 4 * q);
-                float4 v = *u;
-                v.x = k.x + v.x; v.y = k.y + v.y; v.z = k.z + v.z; v.w = k.w + v.w;
-                *u = v;
-            }
-            __syncthreads();
-        }
-        const uint32_t uoff = (uint32_t)((l & 1) * half) * 4u;
+        const int buf = l % kSparseBufs;
+        const int c0 = l * kSparseDc1;
+        const int wq = min(kSparseDc1, D - c0) >> 2;
+        const uint32_t uoff = (uint32_t)(buf * g.unit_floats) * 4u;            // the ring starts at dynamic smem offset 0
         const uint32_t koff = uoff + (uint32_t)g.tile_floats * 4u;
-        const uint32_t aoff = (uint32_t)(2 * half + 4 + c0) * 4u;     // a_s sits after the two 8-byte barriers
-        for (int it = tid; it < n_items; it += kPairThreads) {
-            const int packed = items[it];
-            const int i = packed >> 16, eo = packed & 0xffff;
-            const int e0 = rowptr[i] + eo;
-            const int cnt = min(kSparseItemEdges, rowptr[i + 1] - e0);
-            uint32_t uo[kSparseItemEdges];
-#pragma unroll
-            for (int m = 0; m < kSparseItemEdges; ++m)
-                uo[m] = uoff + (uint32_t)(col[e0 + min(m, cnt - 1)] * g.dc) * 4u;      // clamp: idle slots redo the last edge
-            const uint32_t ko = koff + (uint32_t)(i * g.dc) * 4u;
-            uint64_t acc[kSparseItemEdges];
-#pragma unroll
-            for (int m = 0; m < kSparseItemEdges; ++m) acc[m] = 0ull;
-#pragma unroll 1
+        const uint32_t aoff = a_off + (uint32_t)c0 * 4u, k3off = k3_off + (uint32_t)c0 * 4u;
+        mbar_wait(&full[buf], (uint32_t)(l / kSparseBufs) & 1u);
+        for (int e = tid; e < E; e += kSparseConsumers) {          // one edge per thread: all lanes busy for E >= 320
+            // rows are 128 bytes (all rows would start in bank 0): the tiles are loaded with SWIZZLE_128B, i.e. the 16-byte
+            // chunk q of the 128-byte line L sits at chunk q ^ (L & 7) -- threads on different rows hit different banks
+            const uint32_t uo = uoff + (uint32_t)(col[e] * kSparseDc1) * 4u;
+            const uint32_t ko = koff + (uint32_t)(erow[e] * kSparseDc1) * 4u;
+            const uint32_t ukey = ((uo >> 7) & 7u) << 4, kkey = ((ko >> 7) & 7u) << 4;
+            uint64_t acc0 = 0ull, acc1 = 0ull;
+#pragma unroll 2
             for (int q = 0; q < wq; ++q) {
                 const uint32_t qo = (uint32_t)q * 16u;
                 const float4 av = *reinterpret_cast<const float4*>(smem_raw + aoff + qo);
-                const float4 k2 = *reinterpret_cast<const float4*>(smem_raw + ko + qo);
-                const uint64_t a01 = pack2(av.x, av.y), a23 = pack2(av.z, av.w);
-                const uint64_t k01 = pack2(k2.x, k2.y), k23 = pack2(k2.z, k2.w);
-                float s[4 * kSparseItemEdges];
-#pragma unroll
-                for (int m = 0; m < kSparseItemEdges; ++m) {
-                    const float4 u = *reinterpret_cast<const float4*>(smem_raw + uo[m] + qo);
-                    unpack2(add2(pack2(u.x, u.y), k01), s[4 * m + 0], s[4 * m + 1]);
-                    unpack2(add2(pack2(u.z, u.w), k23), s[4 * m + 2], s[4 * m + 3]);
+                const float4 k2 = *reinterpret_cast<const float4*>(smem_raw + ko + (qo ^ kkey));
+                const float4 u = *reinterpret_cast<const float4*>(smem_raw + uo + (qo ^ ukey));
+                uint64_t u01 = pack2(u.x, u.y), u23 = pack2(u.z, u.w);
+                if (kIndexed) {                                     // the staged tile is K1: U = fl(k3 + K1)
+                    const float4 kk = *reinterpret_cast<const float4*>(smem_raw + k3off + qo);
+                    u01 = add2(pack2(kk.x, kk.y), u01);
+                    u23 = add2(pack2(kk.z, kk.w), u23);
                 }
-#pragma unroll
-                for (int e = 0; e < 4 * kSparseItemEdges; ++e) s[e] = fmaxf(s[e], 0.f);
-#pragma unroll
-                for (int m = 0; m < kSparseItemEdges; ++m) acc[m] = fma2(a01, pack2(s[4 * m + 0], s[4 * m + 1]), acc[m]);
-#pragma unroll
-                for (int m = 0; m < kSparseItemEdges; ++m) acc[m] = fma2(a23, pack2(s[4 * m + 2], s[4 * m + 3]), acc[m]);
+                float s0, s1, s2, s3;
+                unpack2(add2(u01, pack2(k2.x, k2.y)), s0, s1);
+                unpack2(add2(u23, pack2(k2.z, k2.w)), s2, s3);
+                acc0 = fma2(pack2(av.x, av.y), pack2(fmaxf(s0, 0.f), fmaxf(s1, 0.f)), acc0);
+                acc1 = fma2(pack2(av.z, av.w), pack2(fmaxf(s2, 0.f), fmaxf(s3, 0.f)), acc1);
             }
-#pragma unroll
-            for (int m = 0; m < kSparseItemEdges; ++m)
-                if (m < cnt) {
-                    float lo, hi;
-                    unpack2(acc[m], lo, hi);
-                    score[e0 + m] += lo + hi;                      // each edge is owned by exactly one thread
-                }
+            float a0, a1, b0, b1;
+            unpack2(acc0, a0, a1);
+            unpack2(acc1, b0, b1);
+            score[e] += (a0 + a1) + (b0 + b1);                     // each edge is owned by exactly one thread
         }
-        __syncthreads();
-        if (tid == 0 && l + 2 < n_loads) issue(l + 2);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[buf]);                   // this warp is done with the buffer
     }
+    consumer_sync();                                               // every edge score is complete
 
-    // ------------------------------------------------------------------ phase 2: softmax over each row's edges
-    for (int i = warp; i < n; i += kPairThreads / 32) {
+    // ---------------------------------------------------------------------- phase 2: softmax over each row's edges
+    for (int i = warp; i < n; i += kSparseConsumers / 32) {
         const int e0 = rowptr[i], deg = rowptr[i + 1] - e0;
         const bool uni = uniform_row[i] != 0;
         float v[kPairMaxNodes / 32];
@@ -238,51 +233,56 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
             if (t < deg) score[e0 + t] = v[k] / sum;
         }
     }
-    __syncthreads();
+    consumer_sync();
 
-    // ------------------------------------------------------------------ phase 3: Y = relu(sum_{j in N(i)} alpha_ij h_j) + X
+    // ---------------------------------------------------------------------- phase 3: Y = relu(sum_{j in N(i)} alpha_ij h_j) + X
+    const int half_lane = lane & 15, sub = lane >> 4;              // two rows per warp pass, 16 feature quads each
     for (int l = g.nch1; l < n_loads; ++l) {
-        const int c0 = (l - g.nch1) * g.dc3;
-        const int wq = min(g.dc3, D - c0) >> 2;
-        const float* Hs0 = buf0 + (l & 1) * half;
-        mbar_wait(&full[l & 1], (uint32_t)(l >> 1) & 1u);
-        for (int it = tid; it < n * wq; it += kPairThreads) {
-            const int i = it / wq, q = it - i * wq;
-            const size_t yoff = ((size_t)b * n + i) * D + c0 + 4 * q;
-            const size_t xoff = ((size_t)src0 * n + i) * D + c0 + 4 * q;
-            const float4 x = ldg_stream(reinterpret_cast<const float4*>(p.X + xoff));      // consumed after the loop
-            const float* Hs = Hs0 + 4 * q;
-            uint64_t o01 = 0ull, o23 = 0ull;
-            const int e1 = rowptr[i + 1];
-            for (int e = rowptr[i]; e < e1; ++e) {
-                const float al = score[e];
-                const float4 h = *reinterpret_cast<const float4*>(Hs + col[e] * g.dc3);
-                const uint64_t aa = pack2(al, al);
-                o01 = fma2(aa, pack2(h.x, h.y), o01);
-                o23 = fma2(aa, pack2(h.z, h.w), o23);
+        const int buf = l % kSparseBufs;
+        const int c0 = (l - g.nch1) * kSparseDc3;
+        const int wq = min(kSparseDc3, D - c0) >> 2;
+        const float* Hs0 = ring + buf * g.unit_floats;
+        mbar_wait(&full[buf], (uint32_t)(l / kSparseBufs) & 1u);
+        for (int rp = warp; 2 * rp < n; rp += kSparseConsumers / 32) {
+            const int i = 2 * rp + sub;
+            if (i < n && half_lane < wq) {
+                const int q = half_lane;
+                const size_t yoff = ((size_t)b * n + i) * D + c0 + 4 * q;
+                const size_t xoff = ((size_t)src0 * n + i) * D + c0 + 4 * q;
+                const float4 x = ldg_stream(reinterpret_cast<const float4*>(p.X + xoff));   // consumed after the loop
+                const float* Hs = Hs0 + 4 * q;
+                uint64_t o01 = 0ull, o23 = 0ull;
+                const int e1 = rowptr[i + 1];
+#pragma unroll 2
+                for (int e = rowptr[i]; e < e1; ++e) {
+                    const float al = score[e];                                              // broadcast within the half warp
+                    const float4 h = *reinterpret_cast<const float4*>(Hs + col[e] * kSparseDc3);
+                    const uint64_t aa = pack2(al, al);
+                    o01 = fma2(aa, pack2(h.x, h.y), o01);
+                    o23 = fma2(aa, pack2(h.z, h.w), o23);
+                }
+                float4 y;
+                unpack2(o01, y.x, y.y);
+                unpack2(o23, y.z, y.w);
+                y.x = fmaxf(y.x, 0.f) + x.x;
+                y.y = fmaxf(y.y, 0.f) + x.y;
+                y.z = fmaxf(y.z, 0.f) + x.z;
+                y.w = fmaxf(y.w, 0.f) + x.w;
+                stg_stream(reinterpret_cast<float4*>(p.Y + yoff), y);
             }
-            float4 y;
-            unpack2(o01, y.x, y.y);
-            unpack2(o23, y.z, y.w);
-            y.x = fmaxf(y.x, 0.f) + x.x;
-            y.y = fmaxf(y.y, 0.f) + x.y;
-            y.z = fmaxf(y.z, 0.f) + x.z;
-            y.w = fmaxf(y.w, 0.f) + x.w;
-            stg_stream(reinterpret_cast<float4*>(p.Y + yoff), y);
         }
-        __syncthreads();
-        if (tid == 0 && l + 2 < n_loads) issue(l + 2);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[buf]);
     }
 }
 
 inline void sparse_geometry(int n, int D, SparseGeom* g) {
-    int dc = 68;
-    if (dc > D) dc = D;
-    g->dc = dc; g->nch1 = (D + dc - 1) / dc; g->dc3 = 2 * dc; g->nch3 = (D + 2 * dc - 1) / (2 * dc);
-    g->tile_floats = ((n * dc * 4 + 127) / 128) * 128 / 4;
-    g->max_items = n * ((n + kSparseItemEdges - 1) / kSparseItemEdges);
-    g->smem = (size_t)4 * g->tile_floats * 4 + 16 + (size_t)2 * D * 4 + (size_t)n * n * 4 + (size_t)2 * (n + 1) * 4 +
-              (size_t)g->max_items * 4 + (size_t)2 * n * n + (size_t)n + 16;
+    g->nch1 = (D + kSparseDc1 - 1) / kSparseDc1;
+    g->nch3 = (D + kSparseDc3 - 1) / kSparseDc3;
+    g->tile_floats = ((n * kSparseDc1 * 4 + 1023) / 1024) * 1024 / 4;
+    g->unit_floats = 2 * g->tile_floats;
+    g->smem = (size_t)kSparseBufs * g->unit_floats * 4 + (size_t)2 * kSparseBufs * 8 + (size_t)2 * D * 4 +
+              (size_t)n * n * 4 + (size_t)(n + 2) * 4 + (size_t)3 * n * n + (size_t)n + 16;
 }
 
 int launch_graph_layer_fwd_sparse(const PairAttnArgs& args, int n_src, cudaStream_t st) {
@@ -293,11 +293,17 @@ int launch_graph_layer_fwd_sparse(const PairAttnArgs& args, int n_src, cudaStrea
     DIGAT_REQUIRE(g.smem <= (size_t)di->max_smem_optin, "digat_graph_layer_fwd(sparse): needs %zu B shared memory", g.smem);
     CUtensorMap map1, map3;
     int rc;
-    const int64_t src_graphs = args.px_index != nullptr ? n_src : args.B;
-    if ((rc = make_tensor_map_2d(&map1, args.P, src_graphs * args.n, 3 * args.D, args.ldp, args.n, g.dc, CU_TENSOR_MAP_SWIZZLE_NONE)) != DIGAT_OK) return rc;
-    if ((rc = make_tensor_map_2d(&map3, args.P, src_graphs * args.n, 3 * args.D, args.ldp, args.n, g.dc3, CU_TENSOR_MAP_SWIZZLE_NONE)) != DIGAT_OK) return rc;
-    DIGAT_CUDA(cudaFuncSetAttribute(graph_layer_fwd_sparse_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
-    graph_layer_fwd_sparse_kernel<0><<<args.B, kPairThreads, g.smem, st>>>(map1, map3, args, g);
+    const bool indexed = args.px_index != nullptr;
+    const int64_t src_graphs = indexed ? n_src : args.B;
+    if ((rc = make_tensor_map_2d(&map1, args.P, src_graphs * args.n, 3 * args.D, args.ldp, args.n, kSparseDc1, CU_TENSOR_MAP_SWIZZLE_128B)) != DIGAT_OK) return rc;
+    if ((rc = make_tensor_map_2d(&map3, args.P, src_graphs * args.n, 3 * args.D, args.ldp, args.n, kSparseDc3, CU_TENSOR_MAP_SWIZZLE_NONE)) != DIGAT_OK) return rc;
+    if (indexed) {
+        DIGAT_CUDA(cudaFuncSetAttribute(graph_layer_fwd_sparse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+        graph_layer_fwd_sparse_kernel<true><<<args.B, kSparseThreads, g.smem, st>>>(map1, map3, args, g);
+    } else {
+        DIGAT_CUDA(cudaFuncSetAttribute(graph_layer_fwd_sparse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+        graph_layer_fwd_sparse_kernel<false><<<args.B, kSparseThreads, g.smem, st>>>(map1, map3, args, g);
+    }
     return check_launch("digat_graph_layer_fwd(sparse)");
 }
 
