@@ -95,6 +95,9 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
     }
 
     // ---------------------------------------------------------------------- consumers: setup (overlaps the first loads)
+#ifdef DIGAT_TC_TIMING
+    const long long t0 = clock64();
+#endif
     for (int i = tid; i < D / 4; i += kSparseConsumers) {
         reinterpret_cast<float4*>(a_s)[i] = reinterpret_cast<const float4*>(p.a)[i];
         if (kIndexed) reinterpret_cast<float4*>(k3_s)[i] = reinterpret_cast<const float4*>(p.k3 + (size_t)b * p.ldk3)[i];
@@ -155,6 +158,9 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
     for (int e = tid; e < E; e += kSparseConsumers) score[e] = 0.f;
     consumer_sync();
 
+#ifdef DIGAT_TC_TIMING
+    const long long t1 = clock64();
+#endif
     // ---------------------------------------------------------------------- phase 1: scores on the edges only
     const uint32_t a_off = (uint32_t)(reinterpret_cast<uint8_t*>(a_s) - smem_raw);
     const uint32_t k3_off = (uint32_t)(reinterpret_cast<uint8_t*>(k3_s) - smem_raw);
@@ -200,6 +206,9 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
         if (lane == 0) mbar_arrive(&empty[buf]);                   // this warp is done with the buffer
     }
     consumer_sync();                                               // every edge score is complete
+#ifdef DIGAT_TC_TIMING
+    const long long t2 = clock64();
+#endif
 
     // ---------------------------------------------------------------------- phase 2: softmax over each row's edges
     for (int i = warp; i < n; i += kSparseConsumers / 32) {
@@ -235,21 +244,49 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
     }
     consumer_sync();
 
+#ifdef DIGAT_TC_TIMING
+    const long long t3 = clock64();
+#endif
     // ---------------------------------------------------------------------- phase 3: Y = relu(sum_{j in N(i)} alpha_ij h_j) + X
     const int half_lane = lane & 15, sub = lane >> 4;              // two rows per warp pass, 16 feature quads each
+    // Residual rows: a pass over a row's few neighbours is far shorter than a DRAM round trip, so the x values of a
+    // whole unit (up to kXSlots passes of this warp) are requested one unit AHEAD and sit in registers meanwhile.
+    constexpr int kXSlots = 4;
+    constexpr int kRowPairStep = kSparseConsumers / 32;
+    auto load_x = [&](int unit, int slot) {
+        const int c0_ = unit * kSparseDc3;
+        const int i_ = 2 * (warp + slot * kRowPairStep) + sub;
+        return (unit < g.nch3 && i_ < n && c0_ + 4 * half_lane < D)
+                   ? ldg_stream(reinterpret_cast<const float4*>(p.X + ((size_t)src0 * n + i_) * D + c0_ + 4 * half_lane))
+                   : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    float4 xq[kXSlots];
+#pragma unroll
+    for (int sl = 0; sl < kXSlots; ++sl) xq[sl] = load_x(0, sl);
     for (int l = g.nch1; l < n_loads; ++l) {
         const int buf = l % kSparseBufs;
-        const int c0 = (l - g.nch1) * kSparseDc3;
+        const int unit = l - g.nch1;
+        const int c0 = unit * kSparseDc3;
         const int wq = min(kSparseDc3, D - c0) >> 2;
         const float* Hs0 = ring + buf * g.unit_floats;
+        float4 xcur[kXSlots];
+#pragma unroll
+        for (int sl = 0; sl < kXSlots; ++sl) {
+            xcur[sl] = xq[sl];
+            xq[sl] = load_x(unit + 1, sl);                          // next unit's rows: in flight during this unit
+        }
         mbar_wait(&full[buf], (uint32_t)(l / kSparseBufs) & 1u);
-        for (int rp = warp; 2 * rp < n; rp += kSparseConsumers / 32) {
+#pragma unroll
+        for (int sl = 0; sl < kXSlots + 3; ++sl) {                  // n <= 128: at most 7 passes; slots >= kXSlots load directly
+            const int rp = warp + sl * kRowPairStep;
+            if (2 * rp >= n) break;
             const int i = 2 * rp + sub;
             if (i < n && half_lane < wq) {
                 const int q = half_lane;
                 const size_t yoff = ((size_t)b * n + i) * D + c0 + 4 * q;
-                const size_t xoff = ((size_t)src0 * n + i) * D + c0 + 4 * q;
-                const float4 x = ldg_stream(reinterpret_cast<const float4*>(p.X + xoff));   // consumed after the loop
+                float4 x;
+                if (sl < kXSlots) x = xcur[sl < kXSlots ? sl : 0];
+                else x = ldg_stream(reinterpret_cast<const float4*>(p.X + ((size_t)src0 * n + i) * D + c0 + 4 * q));
                 const float* Hs = Hs0 + 4 * q;
                 uint64_t o01 = 0ull, o23 = 0ull;
                 const int e1 = rowptr[i + 1];
@@ -274,6 +311,10 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[buf]);
     }
+#ifdef DIGAT_TC_TIMING
+    if (tid == 0 && (b % 1000) == 7)
+        printf("graph %d E=%d: setup %lld, phase1 %lld, softmax %lld, phase3 %lld\n", b, E, t1 - t0, t2 - t1, t3 - t2, clock64() - t3);
+#endif
 }
 
 inline void sparse_geometry(int n, int D, SparseGeom* g) {
