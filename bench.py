@@ -247,8 +247,15 @@ def main():
         top = table[0] if table else None
         roofline = None
         if top:
+            traffic, traffic_note = None, None
+            tj = os.path.join(ROOT, 'profiles', 'r1_traffic.json')      # DRAM bytes per launch from the ncu --set full captures
+            if os.path.isfile(tj):
+                ent = json.load(open(tj)).get(top['kernel'])
+                if ent:
+                    traffic, traffic_note = ent['bytes'], ent['launch'] + ' / ' + ent['capture']
             roofline = {'kernel': top['kernel'], 'bound': top['bound'], 'achieved': top['achieved'], 'peak': top['peak'],
-                        'unit': top['unit'], 'frac': top['achieved'] / top['peak'], 'traffic': None,
+                        'unit': top['unit'], 'frac': top['achieved'] / top['peak'], 'traffic': traffic,
+                        'traffic_note': traffic_note,
                         'share_of_step': top['share'], 'peak_source': peak_src, 'avg_launch_ms': top['avg_ms']}
         line = {
             'metric': 'impressions_scored_per_sec', 'value': value, 'unit': 'pairs/s', 'n_gpus': world,
