@@ -137,6 +137,7 @@ attention_pool_fwd_kernel(PoolArgs p) {
 inline int launch_attention_pool_fwd(const float* F, int64_t strideF, int ldf, const float* resid, const float* v,
                                      int ldv, const uint8_t* mask, const float* add_in, float* out, int ldo, float* first_out,
                                      float* alpha_out, int B, int m, int D, cudaStream_t st) {
+    if (B <= 0) return DIGAT_OK;
     DIGAT_REQUIRE(F && v && mask && out, "digat_attention_pool_fwd: null pointer");
     DIGAT_REQUIRE(m >= 1 && m <= kCtxMaxItems, "digat_attention_pool_fwd: m=%d outside [1,%d]", m, kCtxMaxItems);
     DIGAT_REQUIRE(D >= 4 && (D & 3) == 0 && D <= 4 * kCtxThreads * kCtxMaxQuads, "digat_attention_pool_fwd: bad D=%d", D);
@@ -173,6 +174,7 @@ __global__ void news_gate_fwd_kernel(const float4* __restrict__ z, const float4*
 
 inline int launch_news_gate_fwd(const float* z, const float* lg, const float* ctx_in, float* ctx_out, int B, int D,
                                 cudaStream_t st) {
+    if (B <= 0) return DIGAT_OK;
     DIGAT_REQUIRE(z && lg && ctx_out, "digat_news_gate_fwd: null pointer");
     DIGAT_REQUIRE(D >= 4 && (D & 3) == 0, "digat_news_gate_fwd: D must be a multiple of 4");
     DIGAT_REQUIRE(aligned16(z) && aligned16(lg) && aligned16(ctx_out) && (!ctx_in || aligned16(ctx_in)),
@@ -267,6 +269,7 @@ topic_segment_fwd_kernel(SegArgs p) {
 inline int launch_topic_segment_fwd(const float* Xu, int64_t strideX, const float* v, int ldv, const int64_t* cidx, float* T,
                                     float* alpha_out, int32_t* err_flag, const int32_t* src_index, int B, int H, int n_seg, int D,
                                     cudaStream_t st) {
+    if (B <= 0) return DIGAT_OK;
     DIGAT_REQUIRE(Xu && v && cidx && T, "digat_topic_segment_fwd: null pointer");
     DIGAT_REQUIRE(H >= 1 && H <= kCtxMaxItems && n_seg >= 1 && n_seg <= kCtxMaxItems,
                   "digat_topic_segment_fwd: H=%d / n_seg=%d outside [1,%d]", H, n_seg, kCtxMaxItems);

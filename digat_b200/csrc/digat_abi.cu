@@ -97,6 +97,7 @@ int digat_topic_segment_fwd(const float* Xu, int64_t strideX, const float* v, in
 
 int digat_gather_rows_i32(const float* table, int64_t n_table, const int32_t* idx, float* out, int64_t ldo,
                           int64_t rows, int D, int32_t* err_flag, void* stream) {
+    if (rows <= 0) return DIGAT_OK;
     DIGAT_REQUIRE(table && idx && out, "digat_gather_rows_i32: null pointer");
     DIGAT_REQUIRE(D >= 4 && (D & 3) == 0 && (ldo & 3) == 0 && ldo >= D, "digat_gather_rows_i32: D, ldo must be multiples of 4");
     DIGAT_REQUIRE(aligned16(table) && aligned16(out), "digat_gather_rows_i32: pointers must be 16-byte aligned");
@@ -110,6 +111,7 @@ int digat_gather_rows_i32(const float* table, int64_t n_table, const int32_t* id
 
 int digat_gather_sag_i32(const float* table, int64_t n_table, const int32_t* node_id, int n_nodes,
                          const int32_t* news, float* out, int64_t rows, int D, int32_t* err_flag, void* stream) {
+    if (rows <= 0) return DIGAT_OK;
     DIGAT_REQUIRE(table && node_id && news && out, "digat_gather_sag_i32: null pointer");
     DIGAT_REQUIRE(n_nodes >= 1 && D >= 4 && (D & 3) == 0, "digat_gather_sag_i32: bad n_nodes / D");
     DIGAT_REQUIRE(aligned16(table) && aligned16(out), "digat_gather_sag_i32: pointers must be 16-byte aligned");
@@ -125,6 +127,7 @@ int digat_gather_sag_i32(const float* table, int64_t n_table, const int32_t* nod
 int digat_build_user_nodes(const float* table, int64_t n_table, const int32_t* hist_idx, const float* hist,
                            const float* topic_emb, float* Xu, int B, int H, int C, int D, int32_t* err_flag,
                            void* stream) {
+    if (B <= 0) return DIGAT_OK;
     DIGAT_REQUIRE(topic_emb && Xu && ((table && hist_idx) || hist), "digat_build_user_nodes: null pointer");
     DIGAT_REQUIRE(H >= 1 && C >= 0 && D >= 4 && (D & 3) == 0, "digat_build_user_nodes: bad H / C / D");
     DIGAT_REQUIRE(aligned16(Xu) && aligned16(topic_emb) && (!table || aligned16(table)) && (!hist || aligned16(hist)),
@@ -139,6 +142,7 @@ int digat_build_user_nodes(const float* table, int64_t n_table, const int32_t* h
 }
 
 int digat_logits(const float* news_ctx, const float* user_ctx, float* logits, int B, int D, void* stream) {
+    if (B <= 0) return DIGAT_OK;
     DIGAT_REQUIRE(news_ctx && user_ctx && logits, "digat_logits: null pointer");
     DIGAT_REQUIRE(D >= 4 && (D & 3) == 0 && aligned16(news_ctx) && aligned16(user_ctx), "digat_logits: bad D / alignment");
     if (B <= 0) return DIGAT_OK;

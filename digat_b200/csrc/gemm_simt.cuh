@@ -139,6 +139,7 @@ gemm_tn_f32_kernel(const float* __restrict__ A, int lda, const float* __restrict
 
 inline int launch_linear_f32(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc,
                              int M, int N, int K, int relu, GroupBias gb, cudaStream_t st) {
+    if (M == 0) return DIGAT_OK;                        // empty batch: nothing to do (pointers of empty tensors are null)
     DIGAT_REQUIRE(A && W && C, "digat_linear_f32: null pointer");
     DIGAT_REQUIRE(M >= 0 && N > 0 && K > 0, "digat_linear_f32: bad shape M=%d N=%d K=%d", M, N, K);
     DIGAT_REQUIRE((K & 3) == 0 && (lda & 3) == 0 && (ldw & 3) == 0, "digat_linear_f32: K, lda, ldw must be multiples of 4");

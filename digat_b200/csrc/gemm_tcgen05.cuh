@@ -366,6 +366,7 @@ int launch_tf32x3_persistent(const float* A, int lda, const float* W_hi, const f
 
 inline int launch_linear_tf32x3(const float* A, int lda, const float* W_hi, const float* W_lo, int ldw, const float* bias,
                                 float* C, int ldc, int M, int N, int K, GroupBias gb, cudaStream_t st) {
+    if (M == 0) return DIGAT_OK;
     DIGAT_REQUIRE(A && W_hi && W_lo && C, "digat_linear_tf32x3: null pointer");
     DIGAT_REQUIRE(gb.ptr == nullptr || (gb.rows > 0 && gb.col0 >= 0 && gb.cols > 0 && gb.col0 + gb.cols <= N &&
                                         (gb.col0 & 3) == 0 && (gb.cols & 3) == 0 && (gb.ld & 3) == 0 && gb.ld >= gb.cols &&

@@ -391,12 +391,14 @@ inline void pair_attn_geometry(int n, int D, int B, bool indexed, PairAttnGeom* 
 
 struct PairAttnArgs;
 int launch_graph_layer_fwd_sparse(const PairAttnArgs& args, int n_src, cudaStream_t st);    // pair_attention_sparse.cuh
+size_t graph_layer_fwd_sparse_smem(int n, int D);                                            // pair_attention_sparse.cuh
 static int g_layer_mode = 0;   // 0 = auto (edge-driven kernel for single-graph CTAs at inference), 1 = dense, 2 = edge-driven
 
 inline int launch_graph_layer_fwd(const float* P, int ldp, const float* a, const uint8_t* adj, const float* X, float* Y,
                                   int B, int n, int D, const uint8_t* drop_keep, float drop_scale, float* score_out,
                                   float* alpha_out, uint8_t* relu_mask_out, const int32_t* px_index, int n_src,
                                   const int32_t* adj_index, const float* k3, int ldk3, cudaStream_t st) {
+    if (B == 0) return DIGAT_OK;
     DIGAT_REQUIRE(P && a && adj && X && Y, "digat_graph_layer_fwd: null pointer");
     DIGAT_REQUIRE(B >= 0 && n >= 1 && n <= kPairMaxNodes, "digat_graph_layer_fwd: n=%d outside [1,%d]", n, kPairMaxNodes);
     DIGAT_REQUIRE(D >= 4 && (D & 3) == 0 && D <= 1024, "digat_graph_layer_fwd: D=%d must be a multiple of 4 in [4,1024]", D);
@@ -407,7 +409,6 @@ inline int launch_graph_layer_fwd(const float* P, int ldp, const float* a, const
                   "digat_graph_layer_fwd: px_index, k3 and n_src go together");
     DIGAT_REQUIRE(k3 == nullptr || (aligned16(k3) && (ldk3 & 3) == 0 && ldk3 >= D),
                   "digat_graph_layer_fwd: k3 must be 16-byte aligned with ldk3 a multiple of 4 and >= D");
-    if (B == 0) return DIGAT_OK;
     PairAttnGeom g;
     pair_attn_geometry(n, D, B, px_index != nullptr, &g);
     const int64_t src_graphs = px_index != nullptr ? n_src : B;
@@ -421,7 +422,9 @@ inline int launch_graph_layer_fwd(const float* P, int ldp, const float* a, const
     PairAttnArgs args{P, ldp, a, adj, X, Y, B, n, D, drop_keep, drop_scale, score_out, alpha_out, relu_mask_out,
                       px_index, adj_index, k3, ldk3};
     const bool inference = !drop_keep && !score_out && !alpha_out && !relu_mask_out;
-    if (inference && g_layer_mode != 1 && (g.R == 1 || g_layer_mode == 2))
+    // auto mode keeps the dense kernel for graphs whose edge-driven working set does not fit one CTA (n > ~100 at D = 400)
+    const bool sparse_fits = graph_layer_fwd_sparse_smem(n, D) <= (size_t)di->max_smem_optin;
+    if (inference && g_layer_mode != 1 && ((g.R == 1 && sparse_fits) || g_layer_mode == 2))
         return launch_graph_layer_fwd_sparse(args, n_src, st);
     const int grid = (B + g.R - 1) / g.R;
     const bool single = g.R * g.nt * g.nt <= kPairThreads;

@@ -330,6 +330,7 @@ inline void pair_bwd_geometry(int n, int D, PairBwdGeom* g) {
 inline int launch_graph_layer_bwd(const float* P, int ldp, const float* a, const uint8_t* adj, const float* score,
                                   const float* alpha, const uint8_t* drop_keep, float drop_scale, const float* G,
                                   float* dP, int lddp, float* da_partial, int B, int n, int D, cudaStream_t st) {
+    if (B == 0) return DIGAT_OK;
     DIGAT_REQUIRE(P && a && adj && score && alpha && G && dP && da_partial, "digat_graph_layer_bwd: null pointer");
     DIGAT_REQUIRE(B >= 0 && n >= 1 && n <= kPairMaxNodes, "digat_graph_layer_bwd: n=%d outside [1,%d]", n, kPairMaxNodes);
     DIGAT_REQUIRE(D >= 4 && (D & 3) == 0 && D <= 1024, "digat_graph_layer_bwd: D=%d must be a multiple of 4 in [4,1024]", D);

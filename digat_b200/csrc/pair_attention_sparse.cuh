@@ -326,6 +326,12 @@ inline void sparse_geometry(int n, int D, SparseGeom* g) {
               (size_t)n * n * 4 + (size_t)(n + 2) * 4 + (size_t)3 * n * n + (size_t)n + 16;
 }
 
+size_t graph_layer_fwd_sparse_smem(int n, int D) {
+    SparseGeom g;
+    sparse_geometry(n, D, &g);
+    return g.smem;
+}
+
 int launch_graph_layer_fwd_sparse(const PairAttnArgs& args, int n_src, cudaStream_t st) {
     SparseGeom g;
     sparse_geometry(args.n, args.D, &g);

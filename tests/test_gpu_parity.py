@@ -263,3 +263,60 @@ def test_edge_driven_layer_kernel_matches_dense(n, B):
     Yref = torch.relu(torch.bmm(al, h)) + X.double()
     assert rel_err(Ys.cpu().numpy(), Yref.cpu().numpy()) < 2e-6
     assert rel_err(Yd.cpu().numpy(), Yref.cpu().numpy()) < 2e-6
+
+
+@pytest.mark.parametrize('B', [1, 2, 3])
+def test_tiny_batches_and_single_row(B):
+    """Ragged / tiny batches: B smaller than any tile, both GEMM paths (CUDA-core below 256 rows), B=1."""
+    from digat_b200 import synth
+    from digat_b200.model import logits
+    cfg = synth.make_config(SAG_neighbors=3, SAG_hops=2, graph_depth=2)
+    sd = synth.make_state_dict(cfg, seed=8)
+    corpus, batch = _oracle_batch(cfg, sd, 6, seed=4)
+    batch = {k: v[:B].contiguous() for k, v in batch.items()}
+    m = _module(cfg, sd)
+    b = _to(batch)
+    order = ('news_graph_embeddings', 'news_graph', 'news_graph_mask', 'user_news_embedding', 'user_graph',
+             'user_category_mask', 'user_category_indices')
+    with torch.no_grad():
+        fn, fu = m.forward(*[b[k] for k in order])
+        lg = logits(fn, fu).cpu().numpy()
+    on, ou = O.forward(O.cast_params(sd), *[batch[k] for k in order])
+    assert lg.shape == (B,)
+    assert rel_err(lg, O.logits(on, ou).numpy()) < LOGIT_TOL
+
+
+def test_empty_batch_is_a_no_op():
+    from digat_b200 import _lib
+    from digat_b200.graphEncoders import graph_layer_fwd, linear
+    dev = _dev()
+    st = torch.cuda.current_stream().cuda_stream
+    P = torch.empty(0, 1200, device=dev)
+    a = torch.zeros(400, device=dev)
+    X = torch.empty(0, 10, 400, device=dev)
+    adj = torch.empty(0, 10, 10, dtype=torch.bool, device=dev)
+    assert graph_layer_fwd(P, a, adj, X).shape == (0, 10, 400)
+    assert linear(torch.empty(0, 400, device=dev), torch.zeros(400, 400, device=dev)).shape == (0, 400)
+    _lib.call('digat_logits', 0, 0, 0, 0, 400, st)
+    _lib.call('digat_gather_rows_i32', torch.zeros(4, 400, device=dev).data_ptr(), 4, torch.zeros(1, dtype=torch.int32, device=dev).data_ptr(),
+              torch.zeros(1, 400, device=dev).data_ptr(), 400, 0, 400, 0, st)
+    torch.cuda.synchronize()
+
+
+def test_single_node_graph_and_max_nodes():
+    """n = 1 (a news with no SAG neighbours in a 1-node graph) and n = 128 (the kernels' maximum)."""
+    from digat_b200.graphEncoders import graph_layer_fwd
+    for n, B in ((1, 5), (128, 3)):
+        g = torch.Generator().manual_seed(n)
+        D = 400
+        P = (torch.randn(B * n, 3 * D, generator=g) * 0.5).cuda()
+        a = (torch.randn(D, generator=g) * 0.1).cuda()
+        X = torch.randn(B, n, D, generator=g).cuda()
+        adj = ((torch.rand(B, n, n, generator=g) < 0.05) | torch.eye(n, dtype=torch.bool)).cuda()
+        Y = graph_layer_fwd(P, a, adj, X)
+        torch.cuda.synchronize()
+        h, U, K2 = P.view(B, n, 3 * D).double().split(D, dim=2)
+        s = (torch.relu(U.unsqueeze(1) + K2.unsqueeze(2)) * a.double()).sum(-1)
+        al = torch.softmax(torch.nn.functional.leaky_relu(s, 0.2).masked_fill(~adj, -1e9), dim=2)
+        Yref = torch.relu(torch.bmm(al, h)) + X.double()
+        assert rel_err(Y.cpu().numpy(), Yref.cpu().numpy()) < 2e-6, n
