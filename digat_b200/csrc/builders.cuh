@@ -1,0 +1,289 @@
+// Integer / byte builders either side of the encoder: all results bit-exact.
+//   user_graph_kernel       reference MIND_corpus.py:143-176  (user-history graph, category mask, segment ids)
+//   sag_bfs_kernel          reference construct_SAG.py:449-485 (semantic-augmented graph: BFS over similar news)
+//   rank_impressions_kernel reference util.py:70-80           (per-impression rank of every pair, stable descending)
+//   impression_metrics_kernel reference evaluate.py:32-89     (AUC / MRR / nDCG@5 / nDCG@10 of score = 1/rank)
+// These are HBM-bound byte kernels (the user-graph builder writes 4.6 KB per behaviour from 200 B of input);
+// nothing here is GEMM-shaped.
+#pragma once
+#include "common.cuh"
+
+namespace digat {
+
+constexpr int kBuilderThreads = 256;
+constexpr int kBuilderMaxH = 512;      // history slots kept in shared memory
+constexpr int kBuilderMaxC = 256;      // categories
+
+// One CTA per behaviour.  Element (i, j) of the [n_u, n_u] graph, n_u = H + C (nodes 0..H-1 clicked news, H.. topics):
+//   i == j                      -> 1                                     (np.identity, MIND_corpus.py:145)
+//   both news                   -> both valid and same category         (:168-170)
+//   news i, topic c             -> i valid and category(i) == c         (:163-164)
+//   topic c, topic c'           -> both categories present              (:171-173; distinct categories only: c != c')
+// kWord: n_u^2 is a multiple of 4, so a thread produces 4 consecutive bytes with one 32-bit store.
+template <bool kWord>
+__global__ void __launch_bounds__(kBuilderThreads)
+user_graph_kernel(const int32_t* __restrict__ hist_cat, const int32_t* __restrict__ hist_len, uint8_t* __restrict__ graph,
+                  uint8_t* __restrict__ cmask, int64_t* __restrict__ cidx, int H, int C, int32_t* __restrict__ err_flag) {
+    __shared__ int cat_s[kBuilderMaxH];          // category of slot t, C for padding
+    __shared__ int present_s[kBuilderMaxC + 1];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int n_u = H + C;
+    int len = hist_len[b];
+    if (len < 0 || len > H) {
+        if (tid == 0 && err_flag) atomicOr(err_flag, 1);
+        len = min(max(len, 0), H);
+    }
+    for (int c = tid; c <= C; c += kBuilderThreads) present_s[c] = 0;
+    __syncthreads();
+    for (int t = tid; t < H; t += kBuilderThreads) {
+        int c = C;
+        if (t < len) {
+            c = hist_cat[(size_t)b * H + t];
+            if (c < 0 || c >= C) {                 // the reference would raise IndexError on cmask[c]
+                if (err_flag) atomicOr(err_flag, 1);
+                c = C;
+            } else {
+                present_s[c] = 1;                  // benign race: every writer stores 1
+            }
+        }
+        cat_s[t] = c;
+        cidx[(size_t)b * H + t] = c;
+    }
+    __syncthreads();
+    for (int c = tid; c <= C; c += kBuilderThreads) cmask[(size_t)b * (C + 1) + c] = (c < C && present_s[c]) ? 1 : 0;
+
+    auto element = [&](int i, int j) -> uint32_t {
+        if (i == j) return 1u;
+        if (i < H && j < H) return (cat_s[i] == cat_s[j] && cat_s[i] < C) ? 1u : 0u;
+        if (i < H) return cat_s[i] == j - H ? 1u : 0u;            // padding slots hold C, never equal to a topic id < C
+        if (j < H) return cat_s[j] == i - H ? 1u : 0u;
+        return (present_s[i - H] && present_s[j - H]) ? 1u : 0u;
+    };
+    const int n2 = n_u * n_u;
+    uint8_t* g = graph + (size_t)b * n2;
+    if (kWord) {
+        uint32_t* g4 = reinterpret_cast<uint32_t*>(g);
+        for (int w = tid; w < n2 / 4; w += kBuilderThreads) {
+            int i = (4 * w) / n_u, j = 4 * w - i * n_u;
+            uint32_t v = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                v |= element(i, j) << (8 * k);
+                if (++j == n_u) { j = 0; ++i; }
+            }
+            g4[w] = v;
+        }
+    } else {
+        for (int e = tid; e < n2; e += kBuilderThreads) {
+            const int i = e / n_u;
+            g[e] = (uint8_t)element(i, e - i * n_u);
+        }
+    }
+}
+
+inline int launch_build_user_graphs(const int32_t* hist_cat, const int32_t* hist_len, uint8_t* graph, uint8_t* cmask,
+                                    int64_t* cidx, int64_t N, int H, int C, int32_t* err_flag, cudaStream_t st) {
+    if (N <= 0) return DIGAT_OK;
+    DIGAT_REQUIRE(hist_cat && hist_len && graph && cmask && cidx, "digat_build_user_graphs: null pointer");
+    DIGAT_REQUIRE(H >= 1 && H <= kBuilderMaxH && C >= 1 && C <= kBuilderMaxC,
+                  "digat_build_user_graphs: H=%d must be in [1,%d], C=%d in [1,%d]", H, kBuilderMaxH, C, kBuilderMaxC);
+    DIGAT_REQUIRE(N <= 0x7fffffff, "digat_build_user_graphs: too many behaviours for one launch");
+    const int n2 = (H + C) * (H + C);
+    if ((n2 & 3) == 0 && (reinterpret_cast<uintptr_t>(graph) & 3) == 0)
+        user_graph_kernel<true><<<(unsigned)N, kBuilderThreads, 0, st>>>(hist_cat, hist_len, graph, cmask, cidx, H, C, err_flag);
+    else
+        user_graph_kernel<false><<<(unsigned)N, kBuilderThreads, 0, st>>>(hist_cat, hist_len, graph, cmask, cidx, H, C, err_flag);
+    return check_launch("digat_build_user_graphs");
+}
+
+// ---------------------------------------------------------------------------------------------------- SAG BFS
+// One warp per news.  The queue (node ids, depths) and the n x n adjacency live in shared memory; the similar-news
+// lists come as CSR (offsets, neighbour index, cosine as double: the reference compares python floats).
+// The BFS itself is sequential (construct_SAG.py:459-484): lane 0 walks the neighbour list, all lanes search the
+// queue for "already present" with ballots.
+constexpr int kSagWarps = 4;
+constexpr int kSagMaxNodes = 128;
+
+__global__ void __launch_bounds__(kSagWarps * 32)
+sag_bfs_kernel(const int64_t* __restrict__ sim_off, const int32_t* __restrict__ sim_idx, const double* __restrict__ sim_cos,
+               int32_t* __restrict__ node_id, uint8_t* __restrict__ graph, uint8_t* __restrict__ mask, int n_news,
+               int top_M, int hop, int n, double threshold, int32_t* __restrict__ err_flag) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n2 = n * n;
+    const int g_bytes = (n2 + 15) & ~15;
+    uint8_t* g_s = smem_raw + (size_t)warp * g_bytes;
+    int* node_s = reinterpret_cast<int*>(smem_raw + (size_t)kSagWarps * g_bytes) + warp * 2 * kSagMaxNodes;
+    int* depth_s = node_s + kSagMaxNodes;
+    const int news = blockIdx.x * kSagWarps + warp;
+    if (news >= n_news) return;
+
+    for (int e = lane; e < g_bytes / 4; e += 32) reinterpret_cast<uint32_t*>(g_s)[e] = 0u;
+    for (int e = lane; e < n; e += 32) { node_s[e] = 0; depth_s[e] = 0; }
+    __syncwarp();
+    int rear = 0;
+    if (news >= 1) {                                   // row 0 is the padding news: all zero except mask[0,0]
+        if (lane == 0) node_s[0] = news;
+        __syncwarp();
+        rear = 1;
+        for (int head = 0; head < rear; ++head) {
+            const int d = depth_s[head];
+            if (d == hop) continue;
+            const int cur = node_s[head];
+            const int64_t lo = sim_off[cur], hi = sim_off[cur + 1];
+            for (int64_t k = lo; k < hi; ++k) {
+                const double cs = sim_cos[k];
+                if (d > 0 && (cs < threshold || (int)(k - lo) == top_M - 1)) break;
+                const int other = sim_idx[k];
+                if (other < 0 || other >= n_news) {
+                    if (lane == 0 && err_flag) atomicOr(err_flag, 1);
+                    continue;
+                }
+                int pos = -1;
+                for (int base = 0; base < rear; base += 32) {
+                    const unsigned hit = __ballot_sync(0xffffffffu, base + lane < rear && node_s[base + lane] == other);
+                    if (hit) { pos = base + __ffs(hit) - 1; break; }
+                }
+                if (pos < 0) {
+                    if (rear >= n) {                   // the reference would raise IndexError
+                        if (lane == 0 && err_flag) atomicOr(err_flag, 2);
+                        continue;
+                    }
+                    pos = rear;
+                    if (lane == 0) { node_s[rear] = other; depth_s[rear] = d + 1; }
+                    ++rear;
+                }
+                if (lane == 0) { g_s[head * n + pos] = 1; g_s[pos * n + head] = 1; }
+                __syncwarp();
+            }
+        }
+    }
+    __syncwarp();
+    // coalesced write-out
+    for (int e = lane; e < n; e += 32) {
+        node_id[(size_t)news * n + e] = node_s[e];
+        mask[(size_t)news * n + e] = (e == 0 || e < rear) ? 1 : 0;
+    }
+    uint8_t* g = graph + (size_t)news * n2;
+    for (int e = lane; e < n2; e += 32) g[e] = g_s[e];
+}
+
+inline int launch_sag_bfs(const int64_t* sim_off, const int32_t* sim_idx, const double* sim_cos, int32_t* node_id,
+                          uint8_t* graph, uint8_t* mask, int n_news, int top_M, int hop, int n_nodes, double threshold,
+                          int32_t* err_flag, cudaStream_t st) {
+    if (n_news <= 0) return DIGAT_OK;
+    DIGAT_REQUIRE(sim_off && node_id && graph && mask, "digat_sag_bfs: null pointer");
+    DIGAT_REQUIRE(n_nodes >= 1 && n_nodes <= kSagMaxNodes, "digat_sag_bfs: n_nodes=%d outside [1,%d]", n_nodes, kSagMaxNodes);
+    DIGAT_REQUIRE(top_M >= 1 && hop >= 0, "digat_sag_bfs: bad top_M / hop");
+    const size_t smem = (size_t)kSagWarps * (((size_t)n_nodes * n_nodes + 15) & ~(size_t)15) +
+                        (size_t)kSagWarps * 2 * kSagMaxNodes * sizeof(int);
+    DIGAT_CUDA(cudaFuncSetAttribute(sag_bfs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sag_bfs_kernel<<<(n_news + kSagWarps - 1) / kSagWarps, kSagWarps * 32, smem, st>>>(
+        sim_off, sim_idx, sim_cos, node_id, graph, mask, n_news, top_M, hop, n_nodes, threshold, err_flag);
+    return check_launch("digat_sag_bfs");
+}
+
+// ---------------------------------------------------------------------------------------------------- ranking
+// rank_i = 1 + #{j : s_j > s_i} + #{j < i : s_j == s_i}: the position of pair i in a STABLE descending sort of its
+// impression (util.py:72-76 sorts [score, index] rows with a stable list sort keyed on -score).  One warp per impression.
+constexpr int kRankWarps = 8;
+
+__global__ void __launch_bounds__(kRankWarps * 32)
+rank_impressions_kernel(const float* __restrict__ scores, const int64_t* __restrict__ offsets, int32_t* __restrict__ ranks,
+                        int64_t n_imp) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t imp = (int64_t)blockIdx.x * kRankWarps + warp;
+    if (imp >= n_imp) return;
+    const int64_t lo = offsets[imp];
+    const int m = (int)(offsets[imp + 1] - lo);
+    const float* s = scores + lo;
+    for (int base = 0; base < m; base += 32) {
+        const int i = base + lane;
+        const float si = i < m ? s[i] : 0.f;
+        int r = 1;
+        for (int j0 = 0; j0 < m; j0 += 32) {
+            const float mine = j0 + lane < m ? s[j0 + lane] : 0.f;
+            const int cnt = min(32, m - j0);
+            for (int k = 0; k < cnt; ++k) {
+                const float sj = __shfl_sync(0xffffffffu, mine, k);
+                const int j = j0 + k;
+                r += (sj > si || (sj == si && j < i)) ? 1 : 0;
+            }
+        }
+        if (i < m) ranks[lo + i] = r;
+    }
+}
+
+inline int launch_rank_impressions(const float* scores, const int64_t* offsets, int32_t* ranks, int64_t n_imp,
+                                   cudaStream_t st) {
+    if (n_imp <= 0) return DIGAT_OK;
+    DIGAT_REQUIRE(scores && offsets && ranks, "digat_rank_impressions: null pointer");
+    rank_impressions_kernel<<<(unsigned)((n_imp + kRankWarps - 1) / kRankWarps), kRankWarps * 32, 0, st>>>(
+        scores, offsets, ranks, n_imp);
+    return check_launch("digat_rank_impressions");
+}
+
+// Per-impression metrics of y_score = 1/rank (evaluate.py:73-80).  Ranks are a permutation of 1..m, so there are no
+// ties: AUC = #{(pos, neg) : rank_pos < rank_neg} / (n_pos n_neg) (integer count, one division),
+// MRR = sum_pos 1/rank / n_pos, nDCG@k = sum_{pos, rank <= k} 1/log2(rank + 1) / sum_{t < min(k, n_pos)} 1/log2(t + 2).
+// out[imp] = {auc, mrr, ndcg5, ndcg10} in double; valid[imp] = 0 for an empty impression (skipped by the reference,
+// evaluate.py:70) and 2 when only one class is present (roc_auc_score raises) -- the caller turns 2 into an error.
+__global__ void __launch_bounds__(kRankWarps * 32)
+impression_metrics_kernel(const int32_t* __restrict__ ranks, const uint8_t* __restrict__ labels,
+                          const int64_t* __restrict__ offsets, double* __restrict__ out, uint8_t* __restrict__ valid,
+                          int64_t n_imp) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t imp = (int64_t)blockIdx.x * kRankWarps + warp;
+    if (imp >= n_imp) return;
+    const int64_t lo = offsets[imp];
+    const int m = (int)(offsets[imp + 1] - lo);
+    long long n_pos = 0, below = 0;                   // below = sum over positives of (m - rank)
+    double rr = 0.0, d5 = 0.0, d10 = 0.0;
+    for (int i = lane; i < m; i += 32) {
+        if (labels[lo + i] != 0) {
+            const int r = ranks[lo + i];
+            ++n_pos;
+            below += m - r;
+            rr += 1.0 / (double)r;
+            const double g = 1.0 / log2((double)r + 1.0);
+            if (r <= 5) d5 += g;
+            if (r <= 10) d10 += g;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_pos += __shfl_xor_sync(0xffffffffu, n_pos, o);
+        below += __shfl_xor_sync(0xffffffffu, below, o);
+        rr += __shfl_xor_sync(0xffffffffu, rr, o);
+        d5 += __shfl_xor_sync(0xffffffffu, d5, o);
+        d10 += __shfl_xor_sync(0xffffffffu, d10, o);
+    }
+    if (lane != 0) return;
+    double* o4 = out + 4 * imp;
+    const long long n_neg = m - n_pos;
+    if (m == 0) { valid[imp] = 0; o4[0] = o4[1] = o4[2] = o4[3] = 0.0; return; }
+    if (n_pos == 0 || n_neg == 0) { valid[imp] = 2; o4[0] = o4[1] = o4[2] = o4[3] = 0.0; return; }
+    double i5 = 0.0, i10 = 0.0;
+    for (int t = 0; t < 10 && t < n_pos; ++t) {
+        const double g = 1.0 / log2((double)t + 2.0);
+        if (t < 5) i5 += g;
+        i10 += g;
+    }
+    const long long wins = below - n_pos * (n_pos - 1) / 2;      // negatives ranked below each positive, summed
+    o4[0] = (double)wins / ((double)n_pos * (double)n_neg);
+    o4[1] = rr / (double)n_pos;
+    o4[2] = d5 / i5;
+    o4[3] = d10 / i10;
+    valid[imp] = 1;
+}
+
+inline int launch_impression_metrics(const int32_t* ranks, const uint8_t* labels, const int64_t* offsets, double* out,
+                                     uint8_t* valid, int64_t n_imp, cudaStream_t st) {
+    if (n_imp <= 0) return DIGAT_OK;
+    DIGAT_REQUIRE(ranks && labels && offsets && out && valid, "digat_impression_metrics: null pointer");
+    impression_metrics_kernel<<<(unsigned)((n_imp + kRankWarps - 1) / kRankWarps), kRankWarps * 32, 0, st>>>(
+        ranks, labels, offsets, out, valid, n_imp);
+    return check_launch("digat_impression_metrics");
+}
+
+}  // namespace digat

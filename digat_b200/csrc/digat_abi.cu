@@ -12,6 +12,7 @@
 #include "pair_attention_bwd.cuh"
 #include "context_bwd.cuh"
 #include "gemm_wgrad.cuh"
+#include "builders.cuh"
 
 using namespace digat;
 
@@ -198,6 +199,27 @@ int digat_colsum(const float* in, int ld, float* out, float* workspace, int M, i
 
 int digat_groupsum(const float* in, int ld, float* out, int groups, int rows, int col0, int cols, void* stream) {
     return launch_groupsum(in, ld, out, groups, rows, col0, cols, as_stream(stream));
+}
+
+int digat_build_user_graphs(const int32_t* hist_cat, const int32_t* hist_len, uint8_t* graph, uint8_t* cmask,
+                            int64_t* cidx, int64_t N, int H, int C, int32_t* err_flag, void* stream) {
+    return launch_build_user_graphs(hist_cat, hist_len, graph, cmask, cidx, N, H, C, err_flag, as_stream(stream));
+}
+
+int digat_sag_bfs(const int64_t* sim_off, const int32_t* sim_idx, const double* sim_cos, int32_t* node_id,
+                  uint8_t* graph, uint8_t* mask, int n_news, int top_M, int hop, int n_nodes, double threshold,
+                  int32_t* err_flag, void* stream) {
+    return launch_sag_bfs(sim_off, sim_idx, sim_cos, node_id, graph, mask, n_news, top_M, hop, n_nodes, threshold,
+                          err_flag, as_stream(stream));
+}
+
+int digat_rank_impressions(const float* scores, const int64_t* offsets, int32_t* ranks, int64_t n_imp, void* stream) {
+    return launch_rank_impressions(scores, offsets, ranks, n_imp, as_stream(stream));
+}
+
+int digat_impression_metrics(const int32_t* ranks, const uint8_t* labels, const int64_t* offsets, double* out,
+                             uint8_t* valid, int64_t n_imp, void* stream) {
+    return launch_impression_metrics(ranks, labels, offsets, out, valid, n_imp, as_stream(stream));
 }
 
 }  // extern "C"

@@ -62,3 +62,50 @@ def metrics(ranks, labels_per_impression):
         n5.append(_dcg(y_true, y_score, 5) / _dcg(y_true, y_true, 5))
         n10.append(_dcg(y_true, y_score, 10) / _dcg(y_true, y_true, 10))
     return float(np.mean(aucs)), float(np.mean(mrrs)), float(np.mean(n5)), float(np.mean(n10))
+
+
+# ----------------------------------------------------------------------------------------------- device versions
+def impression_offsets(impression_of_pair: np.ndarray):
+    """[P] non-decreasing impression id per pair -> [n_imp+1] int64 offsets into the ordered pair list."""
+    imp = np.asarray(impression_of_pair)
+    n_imp = int(imp[-1]) + 1 if len(imp) else 0
+    off = np.zeros(n_imp + 1, dtype=np.int64)
+    np.cumsum(np.bincount(imp, minlength=n_imp), out=off[1:])
+    return off
+
+
+def rank_pairs_device(scores, offsets):
+    """scores [P] fp32 CUDA tensor, offsets [n_imp+1] int64 CUDA tensor -> ranks [P] int32 CUDA tensor: the rank lists of
+    ``rank_lists`` (reference util.py:70-80) concatenated in pair order, computed by rank_impressions_kernel."""
+    import torch
+    from . import _lib
+    dev = scores.device
+    _lib.require_device(dev.index if dev.index is not None else torch.cuda.current_device())
+    assert scores.dtype == torch.float32 and offsets.dtype == torch.int64 and scores.is_contiguous()
+    ranks = torch.empty(scores.shape[0], dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call('digat_rank_impressions', scores.data_ptr(), offsets.data_ptr(), ranks.data_ptr(),
+                  offsets.shape[0] - 1, torch.cuda.current_stream().cuda_stream)
+    return ranks
+
+
+def metrics_device(ranks, labels, offsets):
+    """ranks [P] int32, labels [P] (0/1, any integer/bool dtype), offsets [n_imp+1] int64, all CUDA tensors ->
+    (AUC, MRR, nDCG@5, nDCG@10) averaged over the non-empty impressions, as reference evaluate.py:66-89.
+    Per-impression values come from impression_metrics_kernel in double; the mean is taken on the host in impression
+    order.  Raises ValueError if an impression has a single class (sklearn's roc_auc_score raises there)."""
+    import torch
+    from . import _lib
+    dev = ranks.device
+    n_imp = offsets.shape[0] - 1
+    lab = labels.to(torch.uint8).contiguous()
+    out = torch.empty((n_imp, 4), dtype=torch.float64, device=dev)
+    valid = torch.empty(n_imp, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call('digat_impression_metrics', ranks.data_ptr(), lab.data_ptr(), offsets.data_ptr(), out.data_ptr(),
+                  valid.data_ptr(), n_imp, torch.cuda.current_stream().cuda_stream)
+    v = valid.cpu().numpy()
+    if (v == 2).any():
+        raise ValueError('Only one class present in y_true. ROC AUC score is not defined in that case.')
+    o = out.cpu().numpy()[v == 1]
+    return tuple(float(np.mean(o[:, k])) for k in range(4))

@@ -24,8 +24,12 @@ def shard_range(n_items: int, rank: int, world_size: int):
 
 
 class Scorer:
-    def __init__(self, encoder, corpus, device):
-        """encoder: digat_b200.graphEncoders.DIGAT on `device`; corpus: digat_b200.synth.Corpus (host numpy)."""
+    def __init__(self, encoder, corpus, device, build_user_graphs_on_device=False):
+        """encoder: digat_b200.graphEncoders.DIGAT on `device`; corpus: digat_b200.synth.Corpus (host numpy).
+
+        build_user_graphs_on_device: derive user_graph / category mask / segment ids from the [N_beh,H] category table
+        with the CUDA builder (graphs.build_user_graphs_device; bit-identical to MIND_corpus.py:143-176) instead of
+        uploading the [N_beh,n_u,n_u] bool array (4.6 KB per behaviour vs 200 B)."""
         self.enc = encoder.eval()
         self.dev = torch.device(device)
         _lib.require_device(self.dev.index if self.dev.index is not None else torch.cuda.current_device())
@@ -35,9 +39,16 @@ class Scorer:
         self.news_graph = t(corpus.news_graph)                  # [N,n_n,n_n] bool
         self.news_mask = t(corpus.news_graph_mask)              # [N,n_n] bool (util.py:35)
         self.history = t(corpus.history)                        # [Nb,H] int32
-        self.user_graph = t(corpus.user_graph)                  # [Nb,nu,nu] bool
-        self.cmask = t(corpus.user_category_mask)
-        self.cidx = t(corpus.user_category_indices)
+        if build_user_graphs_on_device:
+            from . import graphs
+            H = corpus.history.shape[1]
+            C = encoder.category_num - 1 if hasattr(encoder, 'category_num') else corpus.user_category_mask.shape[1] - 1
+            cat = t(corpus.history_category)
+            self.user_graph, self.cmask, self.cidx = graphs.build_user_graphs_device(cat, (cat < C).sum(dim=1), H, C)
+        else:
+            self.user_graph = t(corpus.user_graph)              # [Nb,nu,nu] bool
+            self.cmask = t(corpus.user_category_mask)
+            self.cidx = t(corpus.user_category_indices)
         self.n_news, self.D = self.table.shape
         self.n_n = self.node_id.shape[1]
         self.err = torch.zeros(1, dtype=torch.int32, device=self.dev)
@@ -181,3 +192,28 @@ def compute_scores(scorer: Scorer, corpus, batch_size: int, rank: int = 0, world
         out[s - lo:e - lo] = scorer.score_host_batch(*host_batch(corpus, np.arange(s, e)))
     scorer.check_index_errors()
     return out.cpu().numpy()
+
+
+def evaluate_resident(scorer: Scorer, corpus, batch_size: int = 4096, rank: int = 0, world_size: int = 1):
+    """Device-resident replacement of the reference's evaluation loop (util.compute_scores, util.py:51-80, followed by
+    evaluate.scoring): pairs are (behaviour index, news id) only, graphs and tables stay in HBM, and the per-impression
+    ranking and metrics run on the GPU (csrc/builders.cuh).  Shards whole impressions across ranks (no communication).
+
+    Returns dict(scores [P_local] f32 tensor, ranks [P_local] i32 tensor, offsets, metrics (auc, mrr, ndcg5, ndcg10))."""
+    from . import evaluate
+    off_all = evaluate.impression_offsets(corpus.pair_behavior)
+    n_imp = off_all.shape[0] - 1
+    i_lo, i_hi = shard_range(n_imp, rank, world_size)
+    lo, hi = int(off_all[i_lo]), int(off_all[i_hi])
+    dev = scorer.dev
+    beh = torch.from_numpy(corpus.pair_behavior[lo:hi]).to(dev)
+    news = torch.from_numpy(corpus.pair_news[lo:hi]).to(dev)
+    scores = torch.empty(hi - lo, device=dev, dtype=torch.float32)
+    for s in range(0, hi - lo, batch_size):
+        e = min(s + batch_size, hi - lo)
+        scores[s:e] = scorer.score_resident(beh[s:e], news[s:e])
+    scorer.check_index_errors()
+    off = torch.from_numpy(off_all[i_lo:i_hi + 1] - lo).to(dev)
+    ranks = evaluate.rank_pairs_device(scores, off)
+    m = evaluate.metrics_device(ranks, torch.from_numpy(corpus.labels[lo:hi]).to(dev), off)
+    return dict(scores=scores, ranks=ranks, offsets=off, metrics=m)

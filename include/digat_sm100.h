@@ -191,6 +191,32 @@ int digat_colsum(const float* in, int ld, float* out, float* workspace, int M, i
 /* out[g, c] = sum_{r < rows} in[(g*rows + r), col0 + c] -- gradient of the GEMMs' row-group bias (dk3). */
 int digat_groupsum(const float* in, int ld, float* out, int groups, int rows, int col0, int cols, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Integer builders and ranking either side of the encoder; every output is bit-exact.
+ * --------------------------------------------------------------------------------------------------------- */
+
+/* User-history graphs (reference MIND_corpus.py:143-176, its O(H^2) Python loops per behaviour).
+ *   in : hist_cat [N,H] int32 category id of history slot t (ignored for t >= hist_len[n]); hist_len [N] int32
+ *   out: graph [N,H+C,H+C] u8 (bool), cmask [N,C+1] u8 (bool), cidx [N,H] int64 (padding bucket C)
+ * err_flag (optional): bit 0 set on a category outside [0,C) or a length outside [0,H] (the reference raises). */
+int digat_build_user_graphs(const int32_t* hist_cat, const int32_t* hist_len, uint8_t* graph, uint8_t* cmask,
+                            int64_t* cidx, int64_t N, int H, int C, int32_t* err_flag, void* stream);
+/* Semantic-augmented graphs by BFS over the similar-news lists (reference construct_SAG.py:449-485).
+ *   in : CSR lists sim_off [n_news+1] int64, sim_idx [nnz] int32, sim_cos [nnz] f64, ordered as in the reference's
+ *        similarity dict (most similar first); top_M, hop, threshold as construct_SAG.py:15-17,468
+ *   out: node_id [n_news,n_nodes] int32, graph [n_news,n_nodes,n_nodes] u8, mask [n_news,n_nodes] u8 (mask[:,0]=1)
+ * err_flag (optional): bit 0 = neighbour id out of range, bit 1 = more than n_nodes nodes (the reference raises). */
+int digat_sag_bfs(const int64_t* sim_off, const int32_t* sim_idx, const double* sim_cos, int32_t* node_id,
+                  uint8_t* graph, uint8_t* mask, int n_news, int top_M, int hop, int n_nodes, double threshold,
+                  int32_t* err_flag, void* stream);
+/* ranks[p] = 1-based position of pair p inside its impression under a STABLE descending sort of the scores
+ * (reference util.py:70-80).  offsets [n_imp+1] int64 delimit the impressions in the ordered pair list. */
+int digat_rank_impressions(const float* scores, const int64_t* offsets, int32_t* ranks, int64_t n_imp, void* stream);
+/* Per-impression AUC, MRR, nDCG@5, nDCG@10 of y_score = 1/rank (reference evaluate.py:32-89): out [n_imp,4] f64;
+ * valid [n_imp] u8: 1 = scored, 0 = empty impression (skipped, evaluate.py:70), 2 = one class only (sklearn raises). */
+int digat_impression_metrics(const int32_t* ranks, const uint8_t* labels, const int64_t* offsets, double* out,
+                             uint8_t* valid, int64_t n_imp, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
