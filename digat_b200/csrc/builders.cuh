@@ -96,6 +96,58 @@ inline int launch_build_user_graphs(const int32_t* hist_cat, const int32_t* hist
     return check_launch("digat_build_user_graphs");
 }
 
+// Node pruning for the user graph (inference): active[g, i] = 0 iff nothing can observe the layer output of node i:
+//   * no OTHER node attends to it (column i of the adjacency is empty off the diagonal), and
+//   * no context reads it: i >= H (topic nodes are never pooled, graphEncoders.py:125), or its history slot belongs to a
+//     bucket c = cidx[g,i] whose topic embedding is masked out of the user-level attention (cmask[g,c] == 0; in MIND data
+//     the padding bucket S-1) -- unless EVERY bucket is masked: the -1e9 fill then gives a uniform softmax over all S
+//     buckets (layers.py:202), which reads them all (users with an empty history).
+// A graph with an edge-less row keeps every node (that row's softmax is uniform over ALL nodes).
+// For MIND-shaped graphs the inactive nodes are the padded history slots and the categories the user never clicked.
+__global__ void __launch_bounds__(128)
+user_active_rows_kernel(const uint8_t* __restrict__ adj, const int32_t* __restrict__ adj_index,
+                        const int64_t* __restrict__ cidx, const uint8_t* __restrict__ cmask, uint8_t* __restrict__ active,
+                        int n, int H, int S) {
+    __shared__ int col_used[128];
+    __shared__ int any_empty, any_bucket;
+    const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t src = adj_index != nullptr ? (size_t)adj_index[g] : (size_t)g;
+    const uint8_t* a = adj + src * n * n;
+    if (tid < n) col_used[tid] = 0;
+    if (tid == 0) { any_empty = 0; any_bucket = 0; }
+    __syncthreads();
+    for (int c = tid; c < S; c += 128)
+        if (cmask[(size_t)g * S + c] != 0) any_bucket = 1;
+    for (int i = warp; i < n; i += 4) {
+        bool row_any = false;
+        for (int j = lane; j < n; j += 32) {
+            const bool on = a[i * n + j] != 0;
+            row_any |= on;
+            if (on && j != i) col_used[j] = 1;          // benign race: every writer stores 1
+        }
+        if (!__any_sync(0xffffffffu, row_any) && lane == 0) any_empty = 1;
+    }
+    __syncthreads();
+    if (tid < n) {
+        bool pooled = false;                                // does a context read this node's output?
+        if (tid < H) {
+            const int64_t c = cidx[src * H + tid];
+            pooled = !any_bucket || c < 0 || c >= S || cmask[(size_t)g * S + c] != 0;   // bad ids: leave to the segment kernel
+        }
+        active[(size_t)g * n + tid] = (any_empty || col_used[tid] || pooled) ? 1 : 0;
+    }
+}
+
+inline int launch_user_active_rows(const uint8_t* adj, const int32_t* adj_index, const int64_t* cidx, const uint8_t* cmask,
+                                   uint8_t* active, int64_t G, int n, int H, int S, cudaStream_t st) {
+    if (G <= 0) return DIGAT_OK;
+    DIGAT_REQUIRE(adj && cidx && cmask && active, "digat_user_active_rows: null pointer");
+    DIGAT_REQUIRE(n >= 1 && n <= 128 && H >= 0 && H <= n && S >= 1, "digat_user_active_rows: bad n / H / S");
+    DIGAT_REQUIRE(G <= 0x7fffffff, "digat_user_active_rows: too many graphs for one launch");
+    user_active_rows_kernel<<<(unsigned)G, 128, 0, st>>>(adj, adj_index, cidx, cmask, active, n, H, S);
+    return check_launch("digat_user_active_rows");
+}
+
 // ---------------------------------------------------------------------------------------------------- SAG BFS
 // One warp per news.  The queue (node ids, depths) and the n x n adjacency live in shared memory; the similar-news
 // lists come as CSR (offsets, neighbour index, cosine as double: the reference compares python floats).

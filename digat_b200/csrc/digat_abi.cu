@@ -54,9 +54,10 @@ int digat_split_tf32(const float* W, float* W_hi, float* W_lo, int64_t count, vo
 
 int digat_linear_tf32x3(const float* A, int lda, const float* W_hi, const float* W_lo, int ldw, const float* bias,
                         float* C, int ldc, int M, int N, int K, const float* group_bias, int group_rows,
-                        int group_col0, int group_cols, int group_ld, void* stream) {
+                        int group_col0, int group_cols, int group_ld, const int32_t* c_row_index, void* stream) {
     return launch_linear_tf32x3(A, lda, W_hi, W_lo, ldw, bias, C, ldc, M, N, K,
-                                GroupBias{group_bias, group_rows, group_col0, group_cols, group_ld}, as_stream(stream));
+                                GroupBias{group_bias, group_rows, group_col0, group_cols, group_ld, c_row_index},
+                                as_stream(stream));
 }
 
 int digat_debug_set_layer_mode(int mode) {
@@ -72,9 +73,10 @@ int digat_debug_set_gemm_variant(int variant) {
 int digat_graph_layer_fwd(const float* P, int ldp, const float* a, const uint8_t* adj, const float* X, float* Y,
                           int B, int n, int D, const uint8_t* drop_keep, float drop_scale, float* score_out,
                           float* alpha_out, uint8_t* relu_mask_out, const int32_t* px_index, int n_src,
-                          const int32_t* adj_index, const float* k3, int ldk3, void* stream) {
+                          const int32_t* adj_index, const float* k3, int ldk3, const uint8_t* row_active,
+                          void* stream) {
     return launch_graph_layer_fwd(P, ldp, a, adj, X, Y, B, n, D, drop_keep, drop_scale, score_out, alpha_out,
-                                  relu_mask_out, px_index, n_src, adj_index, k3, ldk3, as_stream(stream));
+                                  relu_mask_out, px_index, n_src, adj_index, k3, ldk3, row_active, as_stream(stream));
 }
 
 int digat_attention_pool_fwd(const float* F, int64_t strideF, int ldf, const float* resid_F, const float* v,
@@ -205,6 +207,13 @@ int digat_build_user_graphs(const int32_t* hist_cat, const int32_t* hist_len, ui
                             int64_t* cidx, int64_t N, int H, int C, int32_t* err_flag, void* stream) {
     return launch_build_user_graphs(hist_cat, hist_len, graph, cmask, cidx, N, H, C, err_flag, as_stream(stream));
 }
+
+int digat_user_active_rows(const uint8_t* adj, const int32_t* adj_index, const int64_t* cidx, const uint8_t* cmask,
+                           uint8_t* active, int64_t G, int n, int H, int S, void* stream) {
+    return launch_user_active_rows(adj, adj_index, cidx, cmask, active, G, n, H, S, as_stream(stream));
+}
+
+int digat_graph_layer_supports_row_active(int n, int D, int B) { return graph_layer_supports_row_active(n, D, B); }
 
 int digat_sag_bfs(const int64_t* sim_off, const int32_t* sim_idx, const double* sim_cos, int32_t* node_id,
                   uint8_t* graph, uint8_t* mask, int n_news, int top_M, int hop, int n_nodes, double threshold,

@@ -12,6 +12,10 @@ namespace digat {
 struct GroupBias {
     const float* ptr;
     int rows, col0, cols, ld;      // ld = row pitch of ptr in elements (>= cols)
+    // Row scatter (tcgen05 persistent GEMM only): product row m is written to row out_rows[m] of C and takes the
+    // row-group bias of THAT row.  A holds only the rows worth computing (digat_b200/graphEncoders.py: nodes whose
+    // output can reach a context), C keeps the dense [graphs * n] layout the fused layer kernel streams with TMA.
+    const int32_t* out_rows = nullptr;
 };
 
 template <int BM, int BN, int BK, int TM, int TN>

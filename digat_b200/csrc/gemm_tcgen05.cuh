@@ -380,12 +380,21 @@ inline int launch_linear_tf32x3(const float* A, int lda, const float* W_hi, cons
                   "digat_linear_tf32x3: pointers must be 16-byte aligned");
     DIGAT_REQUIRE(N % 16 == 0, "digat_linear_tf32x3: N=%d must be a multiple of 16", N);
     if (M == 0) return DIGAT_OK;
+    if (gb.out_rows != nullptr) {                         // row scatter lives in the persistent kernel's epilogue only
+        DIGAT_REQUIRE(N <= 1280, "digat_linear_tf32x3: c_row_index needs N <= 1280 (N=%d)", N);
+        if (N % 240 == 0) return launch_tf32x3_persistent<240>(A, lda, W_hi, W_lo, ldw, bias, C, ldc, M, N, K, gb, st);
+        return launch_tf32x3_persistent<208>(A, lda, W_hi, W_lo, ldw, bias, C, ldc, M, N, K, gb, st);
+    }
     // variant 0 (default): one 128-row half per CTA, separate main / correction accumulators (most accurate);
     // variant 1: two halves per CTA for M > 16384, single accumulator (half the W traffic per flop, less accurate).
     const int variant = g_tc_variant;
     const bool big = M > 16384;
     if (variant == 0 && big && N % 240 == 0 && N <= 1280) // persistent 128 x 240 tiles (variant 4 = one tile per CTA)
         return launch_tf32x3_persistent<240>(A, lda, W_hi, W_lo, ldw, bias, C, ldc, M, N, K, gb, st);
+    // widths that 240 does not divide (N = 400: featureAffine): 208-wide persistent tiles when they waste < 10 % of the
+    // MMA columns (400 -> 2 x 208 = 4 %; the 128-wide fallback below computes 512 columns = 28 %)
+    if (variant == 0 && big && N <= 1280 && ((N + 207) / 208) * 208 * 10 < N * 11)
+        return launch_tf32x3_persistent<208>(A, lda, W_hi, W_lo, ldw, bias, C, ldc, M, N, K, gb, st);
     if (variant == 3 && N % 240 == 0)                    // 2-CTA (cta_group::2) 256 x 240 tiles
         return launch_tf32x3_pair<240>(A, lda, W_hi, W_lo, ldw, bias, C, ldc, M, N, K, gb, st);
     // small problems (few tiles) and odd widths: 128-wide tiles, two CTAs per SM (measured 1.45x faster at M = 4096);

@@ -202,10 +202,12 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
             const int mb = tile / n_tiles_n, m0 = mb * 128, n0 = (tile - mb * n_tiles_n) * BN;
             const int m = m0 + q * 32 + lane;
+            const int32_t* orow = gb.out_rows;                             // ascending row scatter, or null
+            const int mo = orow != nullptr ? orow[min(m, M - 1)] : m;      // row of C (and of the row-group bias)
             // Row-group bias of this tile: its few distinct rows (128 / group_rows + 2 groups) are staged in smem NOW,
             // while the MMA main loop of this tile is still running, so the epilogue proper never waits on L2.
-            const int g0 = has_gb ? m0 / gb.rows : 0;
-            const int g1 = has_gb ? min(m0 + 127, M - 1) / gb.rows : 0;
+            const int g0 = has_gb ? (orow != nullptr ? orow[m0] : m0) / gb.rows : 0;
+            const int g1 = has_gb ? (orow != nullptr ? orow[min(m0 + 127, M - 1)] : min(m0 + 127, M - 1)) / gb.rows : 0;
             const bool gb_tile = has_gb && n0 < gb.col0 + gb.cols && n0 + BN > gb.col0;      // tile overlaps the bias columns
             const bool gb_smem = gb_tile && (g1 - g0 + 1) <= Cfg::GB_GROUPS;
             if (gb_smem) {
@@ -221,8 +223,8 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
                 }
                 asm volatile("bar.sync 1, %0;" :: "n"(kTcEpiWarps * 32) : "memory");
             }
-            const float* grow = (gb_tile && !gb_smem && m < M) ? gb.ptr + (size_t)(m / gb.rows) * gb.ld - gb.col0 + n0 : nullptr;
-            const float* gsrow = gb_smem ? gb_s + (min(m, M - 1) / gb.rows - g0) * BN : nullptr;
+            const float* grow = (gb_tile && !gb_smem && m < M) ? gb.ptr + (size_t)(mo / gb.rows) * gb.ld - gb.col0 + n0 : nullptr;
+            const float* gsrow = gb_smem ? gb_s + ((orow != nullptr ? mo : min(m, M - 1)) / gb.rows - g0) * BN : nullptr;
 #ifdef DIGAT_TC_TIMING
             const long long e0 = clock64();
 #endif
@@ -288,8 +290,9 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
                 for (int t4 = 0; t4 < 4; ++t4) {
                     const int f = t4 * 32 + lane, row = f >> 2, cq = f & 3;
                     const int mr = m0 + q * 32 + row;
+                    const int mc = __shfl_sync(0xffffffffu, mo, row);         // C row of tile row `row` (== mr without scatter)
                     if (mr < M && n0 + c + cq * 4 < N)
-                        *reinterpret_cast<float4*>(C + (size_t)mr * ldc + n0 + c + cq * 4) =
+                        *reinterpret_cast<float4*>(C + (size_t)mc * ldc + n0 + c + cq * 4) =
                             *reinterpret_cast<const float4*>(stage + row * 20 + cq * 4);
                 }
             }

@@ -57,6 +57,10 @@ struct PairAttnArgs {
     const int32_t* px_index;    // [B] graph b reads P and X of graph px_index[b] (P then holds K1 WITHOUT k3)
     const int32_t* adj_index;   // [B] graph b reads adj of graph adj_index[b]
     const float* k3; int ldk3;  // [B,ldk3] added to the staged U tile in-kernel: U = fl(K1 + k3), same rounding as the GEMM path
+    // node pruning (edge-driven kernel only, optional): row_active [B,n] 0 = node whose output cannot reach any context
+    // (digat_user_active_rows): its P row was never computed (may hold anything), no edge of it is evaluated and its
+    // output row is Y = X.  No active node may have an edge to an inactive one.
+    const uint8_t* row_active;
 };
 
 __device__ __forceinline__ uint64_t pack2(float lo, float hi) {
@@ -397,7 +401,8 @@ static int g_layer_mode = 0;   // 0 = auto (edge-driven kernel for single-graph 
 inline int launch_graph_layer_fwd(const float* P, int ldp, const float* a, const uint8_t* adj, const float* X, float* Y,
                                   int B, int n, int D, const uint8_t* drop_keep, float drop_scale, float* score_out,
                                   float* alpha_out, uint8_t* relu_mask_out, const int32_t* px_index, int n_src,
-                                  const int32_t* adj_index, const float* k3, int ldk3, cudaStream_t st) {
+                                  const int32_t* adj_index, const float* k3, int ldk3, const uint8_t* row_active,
+                                  cudaStream_t st) {
     if (B == 0) return DIGAT_OK;
     DIGAT_REQUIRE(P && a && adj && X && Y, "digat_graph_layer_fwd: null pointer");
     DIGAT_REQUIRE(B >= 0 && n >= 1 && n <= kPairMaxNodes, "digat_graph_layer_fwd: n=%d outside [1,%d]", n, kPairMaxNodes);
@@ -420,12 +425,15 @@ inline int launch_graph_layer_fwd(const float* P, int ldp, const float* a, const
     if ((rc = make_tensor_map_2d(&map1, P, src_graphs * n, 3 * D, ldp, g.R * n, g.dc, CU_TENSOR_MAP_SWIZZLE_NONE)) != DIGAT_OK) return rc;
     if ((rc = make_tensor_map_2d(&map3, P, src_graphs * n, 3 * D, ldp, g.R * n, g.dc3, CU_TENSOR_MAP_SWIZZLE_NONE)) != DIGAT_OK) return rc;
     PairAttnArgs args{P, ldp, a, adj, X, Y, B, n, D, drop_keep, drop_scale, score_out, alpha_out, relu_mask_out,
-                      px_index, adj_index, k3, ldk3};
+                      px_index, adj_index, k3, ldk3, row_active};
     const bool inference = !drop_keep && !score_out && !alpha_out && !relu_mask_out;
     // auto mode keeps the dense kernel for graphs whose edge-driven working set does not fit one CTA (n > ~100 at D = 400)
     const bool sparse_fits = graph_layer_fwd_sparse_smem(n, D) <= (size_t)di->max_smem_optin;
     if (inference && g_layer_mode != 1 && ((g.R == 1 && sparse_fits) || g_layer_mode == 2))
         return launch_graph_layer_fwd_sparse(args, n_src, st);
+    if (row_active != nullptr)
+        return fail(DIGAT_E_UNSUPPORTED, "digat_graph_layer_fwd: row_active needs the edge-driven kernel (inference, one graph "
+                    "per CTA); query digat_graph_layer_supports_row_active first");
     const int grid = (B + g.R - 1) / g.R;
     const bool single = g.R * g.nt * g.nt <= kPairThreads;
     if (single) {
@@ -436,6 +444,17 @@ inline int launch_graph_layer_fwd(const float* P, int ldp, const float* a, const
         graph_layer_fwd_kernel<false><<<grid, kPairThreads, g.smem, st>>>(map1, map3, args, g);
     }
     return check_launch("digat_graph_layer_fwd");
+}
+
+// 1 when launch_graph_layer_fwd would take the edge-driven kernel for an inference call with these sizes (the only
+// kernel that honours row_active): one graph per CTA (not indexed) and its working set fits the SM.
+inline int graph_layer_supports_row_active(int n, int D, int B) {
+    if (n < 1 || n > kPairMaxNodes || D < 4 || (D & 3) != 0 || D > 1024 || B < 1 || g_layer_mode == 1) return 0;
+    const DeviceInfo* di = device_info();
+    if (!di) return 0;
+    PairAttnGeom g;
+    pair_attn_geometry(n, D, B, false, &g);
+    return (g.R == 1 || g_layer_mode == 2) && graph_layer_fwd_sparse_smem(n, D) <= (size_t)di->max_smem_optin ? 1 : 0;
 }
 
 }  // namespace digat

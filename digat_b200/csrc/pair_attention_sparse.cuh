@@ -63,6 +63,7 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
     uint8_t* erow = col + n * n;                                   // [n*n] query (row) index of each edge
     uint8_t* adj_s = erow + n * n;                                 // [n*n] adjacency bytes
     uint8_t* uniform_row = adj_s + n * n;                          // [n] 1 = row without edges (uniform softmax)
+    uint8_t* dead_row = uniform_row + n;                           // [n] 1 = pruned node (row_active == 0): no edges, Y = X
 
     if (tid == 0) {
         for (int i = 0; i < kSparseBufs; ++i) {
@@ -106,6 +107,8 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
         const size_t ag = p.adj_index != nullptr ? (size_t)p.adj_index[b] : (size_t)b;
         const uint8_t* srcp = p.adj + ag * n * n;
         for (int i = tid; i < n * n; i += kSparseConsumers) adj_s[i] = srcp[i];
+        for (int i = tid; i < n; i += kSparseConsumers)
+            dead_row[i] = (p.row_active != nullptr && p.row_active[(size_t)b * n + i] == 0) ? 1 : 0;
     }
     consumer_sync();
     // CSR pass A: degrees (a row without edges becomes a full row with uniform weights)
@@ -116,8 +119,9 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
             deg += __popc(__ballot_sync(0xffffffffu, j < n && adj_s[i * n + j] != 0));
         }
         if (lane == 0) {
-            uniform_row[i] = deg == 0;
-            rowptr[i + 1] = deg == 0 ? n : deg;                    // degrees for now, scanned below
+            const bool dead = dead_row[i] != 0;
+            uniform_row[i] = deg == 0 && !dead;
+            rowptr[i + 1] = dead ? 0 : (deg == 0 ? n : deg);       // degrees for now, scanned below
         }
     }
     consumer_sync();
@@ -141,6 +145,7 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
     for (int i = warp; i < n; i += kSparseConsumers / 32) {
         const int e0 = rowptr[i];
         const bool uni = uniform_row[i] != 0;
+        if (dead_row[i] != 0) continue;
         int filled = 0;
         for (int k = 0; k < (n + 31) / 32; ++k) {
             const int j = lane + 32 * k;
@@ -323,7 +328,7 @@ inline void sparse_geometry(int n, int D, SparseGeom* g) {
     g->tile_floats = ((n * kSparseDc1 * 4 + 1023) / 1024) * 1024 / 4;
     g->unit_floats = 2 * g->tile_floats;
     g->smem = (size_t)kSparseBufs * g->unit_floats * 4 + (size_t)2 * kSparseBufs * 8 + (size_t)2 * D * 4 +
-              (size_t)n * n * 4 + (size_t)(n + 2) * 4 + (size_t)3 * n * n + (size_t)n + 16;
+              (size_t)n * n * 4 + (size_t)(n + 2) * 4 + (size_t)3 * n * n + (size_t)2 * n + 16;
 }
 
 size_t graph_layer_fwd_sparse_smem(int n, int D) {

@@ -64,10 +64,12 @@ TENSOR_CORE_MIN_ROWS = 256
 
 
 def linear(A, W, bias=None, relu=False, M=None, K=None, lda=None, out=None, group_bias=None, group_rows=1,
-           group_col0=0):
+           group_col0=0, c_rows=None):
     """out[M,N] = A[M,K] W[N,K]^T (+bias).  ``A`` may be a strided row view (pass M, K, lda explicitly).
     W: PackedWeight (tcgen05 3xTF32 GEMM when it has TF32 planes and M is large enough) or a plain fp32 tensor
-    (exact-fp32 CUDA-core GEMM).  group_bias [M/group_rows, cols]: out[m, group_col0 + c] += group_bias[m // group_rows, c]."""
+    (exact-fp32 CUDA-core GEMM).  group_bias [M/group_rows, cols]: out[m, group_col0 + c] += group_bias[m // group_rows, c].
+    c_rows [M] int32 ascending (tensor-core path only, ``out`` required): product row m lands in out[c_rows[m]] and takes
+    the group bias of that row; the other rows of ``out`` are left untouched."""
     w = W.w if isinstance(W, PackedWeight) else W
     N = w.shape[0]
     if K is None:
@@ -80,9 +82,16 @@ def linear(A, W, bias=None, relu=False, M=None, K=None, lda=None, out=None, grou
         out = torch.empty((M, N), device=A.device, dtype=torch.float32)
     gcols = 0 if group_bias is None else group_bias.shape[1]
     gld = 0 if group_bias is None else group_bias.stride(0)
-    if isinstance(W, PackedWeight) and W.hi is not None and M >= TENSOR_CORE_MIN_ROWS and not relu:
+    if c_rows is not None:
+        if not (isinstance(W, PackedWeight) and W.hi is not None) or relu:
+            raise RuntimeError('linear: c_rows needs a PackedWeight with TF32 planes and no relu')
         _lib.call('digat_linear_tf32x3', A.data_ptr(), lda, W.hi.data_ptr(), W.lo.data_ptr(), w.stride(0), _ptr(bias),
-                  out.data_ptr(), out.stride(0), M, N, K, _ptr(group_bias), group_rows, group_col0, gcols, gld, _stream())
+                  out.data_ptr(), out.stride(0), M, N, K, _ptr(group_bias), group_rows, group_col0, gcols, gld,
+                  c_rows.data_ptr(), _stream())
+    elif isinstance(W, PackedWeight) and W.hi is not None and M >= TENSOR_CORE_MIN_ROWS and not relu:
+        _lib.call('digat_linear_tf32x3', A.data_ptr(), lda, W.hi.data_ptr(), W.lo.data_ptr(), w.stride(0), _ptr(bias),
+                  out.data_ptr(), out.stride(0), M, N, K, _ptr(group_bias), group_rows, group_col0, gcols, gld, 0,
+                  _stream())
     else:
         _lib.call('digat_linear_f32', A.data_ptr(), lda, w.data_ptr(), w.stride(0), _ptr(bias), out.data_ptr(),
                   out.stride(0), M, N, K, 1 if relu else 0, _ptr(group_bias), group_rows, group_col0, gcols, gld, _stream())
@@ -90,7 +99,7 @@ def linear(A, W, bias=None, relu=False, M=None, K=None, lda=None, out=None, grou
 
 
 def graph_layer_fwd(P, a, adj, X, drop_keep=None, drop_scale=1.0, score_out=None, alpha_out=None, relu_mask_out=None,
-                    px_index=None, adj_index=None, k3=None, B=None):
+                    px_index=None, adj_index=None, k3=None, B=None, row_active=None):
     """P [B*n, 3D] = h | U | K2 with U = k3 + K1 (row-group bias of the projection GEMM).
     Indexed mode (px_index, k3): P / X are per-behaviour tables shared by B pairs, k3 [B,D] is added in-kernel."""
     n_src, n, D = X.shape
@@ -100,7 +109,7 @@ def graph_layer_fwd(P, a, adj, X, drop_keep=None, drop_scale=1.0, score_out=None
     _lib.call('digat_graph_layer_fwd', P.data_ptr(), P.stride(0), a.data_ptr(), adj.data_ptr(), X.data_ptr(),
               Y.data_ptr(), B, n, D, _ptr(drop_keep), float(drop_scale), _ptr(score_out), _ptr(alpha_out),
               _ptr(relu_mask_out), _ptr(px_index), n_src, _ptr(adj_index), _ptr(k3),
-              0 if k3 is None else k3.stride(0), _stream())
+              0 if k3 is None else k3.stride(0), _ptr(row_active), _stream())
     return Y
 
 
@@ -281,18 +290,51 @@ class DIGAT(GraphEncoder):
         Fa = linear(T, w['fa_W'], w['fa_b'])                                      # featureAffine(T)  [B*S, D]
         return attention_pool_fwd(Fa.view(B, S, D), v2, cmask, resid=T, add_in=ctx_in), k3_next
 
-    def _layer(self, w, g, i, X, adj, ctx_other, k3=None, share=None, adj_index=None):
+    def _layer(self, w, g, i, X, adj, ctx_other, k3=None, share=None, adj_index=None, prune=None):
         """k3 [B,D] (possibly a column view): ffn3(context of the other graph) + bias, computed here when None.
         share [B] int32 (layer 0 of the scoring path): X [n_src,n,D] holds one graph per BEHAVIOUR and pair b uses
-        graph share[b]; the projection then runs once per behaviour and k3 is added inside the fused kernel."""
+        graph share[b]; the projection then runs once per behaviour and k3 is added inside the fused kernel.
+        prune = (row_active [B,n] uint8, rows [M_act] int32) from _active_user_rows: only the listed node rows are
+        projected (gathered, multiplied, scattered back into the dense P) and evaluated by the layer kernel."""
         n, D = X.shape[1], X.shape[2]
         if k3 is None:
             k3 = linear(ctx_other, w[g, i, 'W3'], w[g, i, 'b3'])                  # [B, D]
+        act = None if prune is None else prune[0]
         if share is not None:
             P = linear(X, w[g, i, 'Wcat'], w[g, i, 'bcat'])                       # h | K1 | K2 per behaviour
-            return graph_layer_fwd(P, w[g, i, 'a'], adj, X, px_index=share, adj_index=share, k3=k3, B=k3.shape[0])
+            return graph_layer_fwd(P, w[g, i, 'a'], adj, X, px_index=share, adj_index=share, k3=k3, B=k3.shape[0],
+                                   row_active=act)
+        if prune is not None:
+            rows = prune[1]
+            M = rows.shape[0]
+            A = torch.empty((M, D), device=X.device, dtype=torch.float32)
+            _lib.call('digat_gather_rows_i32', X.data_ptr(), X.shape[0] * n, rows.data_ptr(), A.data_ptr(), D, M, D,
+                      self._err_flag(X.device).data_ptr(), _stream())
+            P = torch.empty((X.shape[0] * n, w[g, i, 'Wcat'].w.shape[0]), device=X.device, dtype=torch.float32)
+            linear(A, w[g, i, 'Wcat'], w[g, i, 'bcat'], out=P, group_bias=k3, group_rows=n, group_col0=D, c_rows=rows)
+            return graph_layer_fwd(P, w[g, i, 'a'], adj, X, adj_index=adj_index, row_active=act)
         P = linear(X, w[g, i, 'Wcat'], w[g, i, 'bcat'], group_bias=k3, group_rows=n, group_col0=D)   # h | k3+K1 | K2
         return graph_layer_fwd(P, w[g, i, 'a'], adj, X, adj_index=adj_index)
+
+    prune_user_nodes = True      # inference only; switch off to evaluate every node of every user graph
+
+    def _active_user_rows(self, Au, Mc, ci, share):
+        """Node pruning of the user graph at inference (digat_user_active_rows): nodes that no other node attends to and
+        no context pools -- in MIND-shaped data the padded history slots and the categories a user never clicked, about
+        half of the 68 nodes -- cannot influence (news_ctx, user_ctx); their rows are neither projected nor evaluated.
+        Returns (row_active [B,n] uint8, flat row ids int32 [M_act]) or None when unsupported / nothing to prune.
+        The nonzero() is a host synchronisation: M_act is a launch parameter of the projection GEMM."""
+        B, n = Mc.shape[0], Au.shape[1]
+        if not self.prune_user_nodes or B * n < TENSOR_CORE_MIN_ROWS or \
+           not _lib.load().digat_graph_layer_supports_row_active(n, self.news_embedding_dim, B):
+            return None          # (small batches stay on the exact-fp32 GEMM, which has no row scatter)
+        act = torch.empty((B, n), dtype=torch.uint8, device=Au.device)
+        _lib.call('digat_user_active_rows', Au.data_ptr(), _ptr(share), ci.data_ptr(), Mc.data_ptr(), act.data_ptr(), B, n,
+                  self.max_history_num, self.category_num, _stream())
+        rows = act.view(-1).nonzero().squeeze(1).to(torch.int32)
+        if rows.shape[0] == B * n:
+            return None
+        return act, rows
 
     def _err_flag(self, device):
         f = getattr(self, '_err', None)
@@ -372,12 +414,13 @@ class DIGAT(GraphEncoder):
         if c_n is None:
             c_n = self._news_ctx(w, Xn, Mn)
         c_u, k3u = self._user_ctx(w, Xu, Mc, ci, c_n, 0, src_index=share)
+        prune = self._active_user_rows(Au, Mc, ci, share)
         if share is not None:
             ci = ci.index_select(0, share.long())      # [B,H] int64: from layer 1 on every pair owns its user nodes
         for i in range(self.graph_depth):
             Xn_new = self._layer(w, 'news', i, Xn, An, c_u)
             Xu = self._layer(w, 'user', i, Xu, Au, c_n, k3=k3u, share=share if i == 0 else None,
-                             adj_index=share if i > 0 else None)
+                             adj_index=share if i > 0 else None, prune=prune)
             Xn = Xn_new
             c_n = self._news_ctx(w, Xn, Mn, ctx_in=c_n)
             c_u, k3u = self._user_ctx(w, Xu, Mc, ci, c_n, i + 1, ctx_in=c_u)

@@ -29,7 +29,7 @@ extern "C" {
 #define DIGAT_E_CUDA        -2   /* a CUDA runtime/driver call or a launch failed */
 #define DIGAT_E_UNSUPPORTED -3   /* device is not sm_100 */
 
-#define DIGAT_ABI_VERSION 1
+#define DIGAT_ABI_VERSION 2
 
 int         digat_abi_version(void);
 const char* digat_last_error(void);
@@ -59,11 +59,15 @@ int digat_split_tf32(const float* W, float* W_hi, float* W_lo, int64_t count, vo
  * compensation: C = A_hi*W_hi + A_lo*W_hi + A_hi*W_lo (+ bias).  A is plain fp32 and is split into its TF32 planes
  * on the fly inside the kernel; W_hi / W_lo come from digat_split_tf32 (same ldw).
  * Requires K % 4 == 0, N % 80 == 0, lda/ldw/ldc % 4 == 0.  Replaces the three node projections h, K1, K2 of one
- * layer as ONE GEMM against the stacked [3D, D] weight (graphEncoders.py:146-148 / 166-168). */
+ * layer as ONE GEMM against the stacked [3D, D] weight (graphEncoders.py:146-148 / 166-168).
+ * c_row_index (may be NULL; ascending int32 [M]): row scatter -- product row m is written to row c_row_index[m] of C
+ * and takes the row-group bias of that row.  A then holds only the node rows worth projecting (see
+ * digat_user_active_rows) while C keeps the dense [graphs * n] layout digat_graph_layer_fwd streams with TMA; the
+ * rows of C that are not listed are left untouched.  Needs N <= 1280. */
 int digat_linear_tf32x3(const float* A, int lda, const float* W_hi, const float* W_lo, int ldw,
                         const float* bias, float* C, int ldc, int M, int N, int K,
                         const float* group_bias, int group_rows, int group_col0, int group_cols, int group_ld,
-                     void* stream);
+                        const int32_t* c_row_index, void* stream);
 
 /* Tuning/experiment switch for digat_linear_tf32x3 tile variants (0 = default).  Not part of the reference path. */
 int digat_debug_set_gemm_variant(int variant);
@@ -91,11 +95,26 @@ int digat_debug_set_layer_mode(int mode);
  * (tables with n_src graphs; P then holds K1 WITHOUT k3) and k3 [B,ldk3] is added to the staged K1 tile in-kernel
  * (same fp32 add as the GEMM's row-group bias, so results are bit-identical to the expanded path); adj_index [B]
  * makes graph b read adj of graph adj_index[b] (per-behaviour user graphs, no per-pair copy).
+ * Node pruning (may be NULL; edge-driven kernel only, see digat_graph_layer_supports_row_active): row_active [B,n]
+ * bool, 0 = node whose output nothing can observe (digat_user_active_rows).  Its P row is never read for arithmetic
+ * (it may be uninitialised: digat_linear_tf32x3 with c_row_index skips it), none of its edges is evaluated and its
+ * output row is Y = X.  No active node may have an edge to an inactive one.
  * --------------------------------------------------------------------------------------------------------- */
 int digat_graph_layer_fwd(const float* P, int ldp, const float* a, const uint8_t* adj, const float* X, float* Y,
                           int B, int n, int D, const uint8_t* drop_keep, float drop_scale, float* score_out,
                           float* alpha_out, uint8_t* relu_mask_out, const int32_t* px_index, int n_src,
-                          const int32_t* adj_index, const float* k3, int ldk3, void* stream);
+                          const int32_t* adj_index, const float* k3, int ldk3, const uint8_t* row_active,
+                          void* stream);
+/* 1 if an inference call of digat_graph_layer_fwd with these sizes takes the kernel that honours row_active, else 0. */
+int digat_graph_layer_supports_row_active(int n, int D, int B);
+/* Node pruning flags for user graphs: active [G,n] = 0 iff node i's layer output is unobservable: no other node has
+ * an edge to it (column i of adj empty off the diagonal) AND no context reads it (i >= H: topic nodes are never
+ * pooled, graphEncoders.py:125; or history slot i belongs to a bucket c = cidx[i] with cmask[c] == 0 while some other
+ * bucket is unmasked -- with every bucket masked the softmax is uniform and reads them all).
+ * A graph with an edge-less row keeps every node.  adj [*,n,n] read through adj_index [G] when given (then cidx
+ * [*,H] int64 is read through the same index); cmask [G,S] is per graph. */
+int digat_user_active_rows(const uint8_t* adj, const int32_t* adj_index, const int64_t* cidx, const uint8_t* cmask,
+                           uint8_t* active, int64_t G, int n, int H, int S, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Masked single-query attention pooling (replaces layers.py:199-206 after folding W_K into the query:

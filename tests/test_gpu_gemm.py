@@ -23,7 +23,7 @@ def _tf32x3(A, W, bias, lda=None):
     hi, lo = _split(W)
     C = torch.full((M, N), float('nan'), device=A.device)
     _lib.call('digat_linear_tf32x3', A.data_ptr(), lda or A.stride(0), hi.data_ptr(), lo.data_ptr(), W.stride(0),
-              0 if bias is None else bias.data_ptr(), C.data_ptr(), N, M, N, K, 0, 1, 0, 0, 0,
+              0 if bias is None else bias.data_ptr(), C.data_ptr(), N, M, N, K, 0, 1, 0, 0, 0, 0,
               torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     return C
@@ -66,7 +66,7 @@ def test_tf32x3_strided_A_and_no_bias():
     hi, lo = _split(W)
     C = torch.empty(300, 400, device='cuda')
     _lib.call('digat_linear_tf32x3', X.data_ptr(), 4000, hi.data_ptr(), lo.data_ptr(), 400, 0, C.data_ptr(), 400,
-              300, 400, 400, 0, 1, 0, 0, 0, torch.cuda.current_stream().cuda_stream)
+              300, 400, 400, 0, 1, 0, 0, 0, 0, torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     ref = X[:, 0, :].double().cpu() @ W.double().cpu().t()
     assert rel_err(C.cpu().numpy(), ref.numpy()) < 2e-6

@@ -11,7 +11,7 @@ for variant in (4,0):
         g=torch.Generator().manual_seed(1)
         A=torch.randn(M,K,generator=g).cuda(); W=(torch.randn(N,K,generator=g)*0.05).cuda(); b=torch.randn(N,generator=g).cuda()
         hi,lo=split(W); C=torch.empty(M,N,device='cuda')
-        def run(): _lib.call('digat_linear_tf32x3', A.data_ptr(), K, hi.data_ptr(), lo.data_ptr(), K, b.data_ptr(), C.data_ptr(), N, M, N, K, 0, 1, 0, 0, 0, 0)
+        def run(): _lib.call('digat_linear_tf32x3', A.data_ptr(), K, hi.data_ptr(), lo.data_ptr(), K, b.data_ptr(), C.data_ptr(), N, M, N, K, 0, 1, 0, 0, 0, 0, 0)
         run(); torch.cuda.synchronize()
         rows=torch.arange(0,M,max(1,M//256))[:256].cuda()
         ref=A[rows].double()@W.double().t()+b.double()

@@ -9,5 +9,5 @@ hi, lo = torch.empty_like(W), torch.empty_like(W)
 _lib.call('digat_split_tf32', W.data_ptr(), hi.data_ptr(), lo.data_ptr(), W.numel(), 0)
 C = torch.empty(M, N, device='cuda')
 for _ in range(3):
-    _lib.call('digat_linear_tf32x3', A.data_ptr(), K, hi.data_ptr(), lo.data_ptr(), K, 0, C.data_ptr(), N, M, N, K, 0, 1, 0, 0, 0, 0)
+    _lib.call('digat_linear_tf32x3', A.data_ptr(), K, hi.data_ptr(), lo.data_ptr(), K, 0, C.data_ptr(), N, M, N, K, 0, 1, 0, 0, 0, 0, 0)
 torch.cuda.synchronize()
