@@ -404,7 +404,7 @@ def summarize_kernels(records, hbm_peak, tensor_peak):
             key = '%s[m=%d]' % (name, m)
             work, bound = B * (m * Dd * 4 * (2 if a[3] else 1) + 2 * Dd * 4), 'hbm'
         elif name == 'digat_topic_segment_fwd':
-            B, H, S, Dd = a[9], a[10], a[11], a[12]
+            B, H, S, Dd = a[10], a[11], a[12], a[13]
             key, work, bound = name, B * (H * Dd * 4 + S * Dd * 4 + Dd * 4 + H * 8), 'hbm'
         elif name in ('digat_gather_sag_i32',):
             key, work, bound = name, a[6] * a[3] * a[7] * 4 * 2, 'hbm'

@@ -16,10 +16,13 @@ constexpr int kCtxMaxItems = 128;     // max features per pooled set (graph node
 constexpr int kCtxMaxQuads = 2;       // D <= 4 * kCtxThreads * kCtxMaxQuads = 1024
 
 // scores[k] = (F'_k . v) / sqrt(D) for k in [0,m), F' = F or relu(F)+resid.  Result in s_score (smem, all threads sync'd).
+// Rows are processed four at a time so that four rows' loads are in flight per thread (the loop is latency-bound
+// otherwise: one 1600-byte row per DRAM round trip).  s_skip (smem, may be null): rows with s_skip[k] != 0 are not
+// read at all (their score is 0; the caller masks them).
 template <bool kResid>
 __device__ __forceinline__ void ctx_scores(const float* __restrict__ F, int ldf, const float* __restrict__ Rs, int ldr,
                                            const float* __restrict__ v, int m, int D, float inv_scale_div,
-                                           float (*s_part)[kCtxWarps], float* s_score) {
+                                           float (*s_part)[kCtxWarps], float* s_score, const uint8_t* s_skip = nullptr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nq = D >> 2;
     float4 vq[kCtxMaxQuads];
@@ -28,26 +31,48 @@ __device__ __forceinline__ void ctx_scores(const float* __restrict__ F, int ldf,
         const int q = tid + c * kCtxThreads;
         vq[c] = q < nq ? reinterpret_cast<const float4*>(v)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    for (int k = 0; k < m; ++k) {
-        float part = 0.f;
+    constexpr int kRows = 4;
+    for (int k0 = 0; k0 < m; k0 += kRows) {
+        float4 f[kRows][kCtxMaxQuads], t[kRows][kCtxMaxQuads];
 #pragma unroll
-        for (int c = 0; c < kCtxMaxQuads; ++c) {
-            const int q = tid + c * kCtxThreads;
-            if (q < nq) {
-                float4 f = reinterpret_cast<const float4*>(F + (size_t)k * ldf)[q];
-                if (kResid) {
-                    const float4 t = reinterpret_cast<const float4*>(Rs + (size_t)k * ldr)[q];
-                    f.x = fmaxf(f.x, 0.f) + t.x; f.y = fmaxf(f.y, 0.f) + t.y;
-                    f.z = fmaxf(f.z, 0.f) + t.z; f.w = fmaxf(f.w, 0.f) + t.w;
-                }
-                part = fmaf(f.x, vq[c].x, part);
-                part = fmaf(f.y, vq[c].y, part);
-                part = fmaf(f.z, vq[c].z, part);
-                part = fmaf(f.w, vq[c].w, part);
+        for (int u = 0; u < kRows; ++u) {
+            const int k = k0 + u;
+            const bool live = k < m && !(s_skip != nullptr && s_skip[k] != 0);
+#pragma unroll
+            for (int c = 0; c < kCtxMaxQuads; ++c) {
+                const int q = tid + c * kCtxThreads;
+                const bool on = live && q < nq;
+                f[u][c] = on ? reinterpret_cast<const float4*>(F + (size_t)k * ldf)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (kResid)
+                    t[u][c] = on ? reinterpret_cast<const float4*>(Rs + (size_t)k * ldr)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
-        part = warp_sum(part);
-        if (lane == 0) s_part[k][warp] = part;
+        float part[kRows];
+#pragma unroll
+        for (int u = 0; u < kRows; ++u) {
+            part[u] = 0.f;
+#pragma unroll
+            for (int c = 0; c < kCtxMaxQuads; ++c) {
+                float4 x = f[u][c];
+                if (kResid) {
+                    x.x = fmaxf(x.x, 0.f) + t[u][c].x; x.y = fmaxf(x.y, 0.f) + t[u][c].y;
+                    x.z = fmaxf(x.z, 0.f) + t[u][c].z; x.w = fmaxf(x.w, 0.f) + t[u][c].w;
+                }
+                part[u] = fmaf(x.x, vq[c].x, part[u]);
+                part[u] = fmaf(x.y, vq[c].y, part[u]);
+                part[u] = fmaf(x.z, vq[c].z, part[u]);
+                part[u] = fmaf(x.w, vq[c].w, part[u]);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int u = 0; u < kRows; ++u) part[u] += __shfl_xor_sync(0xffffffffu, part[u], o);
+        if (lane == 0) {
+#pragma unroll
+            for (int u = 0; u < kRows; ++u)
+                if (k0 + u < m) s_part[k0 + u][warp] = part[u];
+        }
     }
     __syncthreads();
     if (tid < m) {
@@ -81,7 +106,14 @@ attention_pool_fwd_kernel(PoolArgs p) {
     const int m = p.m, D = p.D, nq = D >> 2;
     const float* F = p.F + (size_t)b * p.strideF;
     const float* Rs = kResid ? p.resid + (size_t)b * p.strideF : nullptr;
-    ctx_scores<kResid>(F, p.ldf, Rs, p.ldf, p.v + (size_t)b * p.ldv, m, D, sqrtf((float)D), s_part, s_score);
+    // Masked rows get the -1e9 fill whatever their score is, and a softmax weight of exactly 0 unless EVERY row is
+    // masked (then the weights are uniform): they are not read at all when at least one row is unmasked.
+    __shared__ uint8_t s_skip[kCtxMaxItems];
+    const bool unmasked = tid < m && p.mask[(size_t)b * m + tid] != 0;
+    const int any_unmasked = __syncthreads_or(unmasked ? 1 : 0);
+    if (tid < m) s_skip[tid] = (any_unmasked && !unmasked) ? 1 : 0;
+    __syncthreads();
+    ctx_scores<kResid>(F, p.ldf, Rs, p.ldf, p.v + (size_t)b * p.ldv, m, D, sqrtf((float)D), s_part, s_score, s_skip);
 
     // masked softmax over the m scores (m <= 128 = one value per thread)
     float val = -INFINITY;
@@ -113,16 +145,29 @@ attention_pool_fwd_kernel(PoolArgs p) {
         const int q = tid + c * kCtxThreads;
         if (q >= nq) continue;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int k = 0; k < m; ++k) {
-            float4 f = reinterpret_cast<const float4*>(F + (size_t)k * p.ldf)[q];
-            if (kResid) {
-                const float4 t = reinterpret_cast<const float4*>(Rs + (size_t)k * p.ldf)[q];
-                f.x = fmaxf(f.x, 0.f) + t.x; f.y = fmaxf(f.y, 0.f) + t.y;
-                f.z = fmaxf(f.z, 0.f) + t.z; f.w = fmaxf(f.w, 0.f) + t.w;
+        constexpr int kRows = 4;                                   // four rows' loads in flight per thread
+        for (int k0 = 0; k0 < m; k0 += kRows) {
+            float4 f[kRows], t[kRows];
+            float al[kRows];
+#pragma unroll
+            for (int u = 0; u < kRows; ++u) {
+                const int k = k0 + u;
+                al[u] = k < m ? s_score[k] : 0.f;
+                const bool live = k < m && s_skip[k] == 0;         // skipped rows have weight 0: fma(0, 0, acc) == acc
+                f[u] = live ? reinterpret_cast<const float4*>(F + (size_t)k * p.ldf)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (kResid)
+                    t[u] = live ? reinterpret_cast<const float4*>(Rs + (size_t)k * p.ldf)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            const float al = s_score[k];
-            acc.x = fmaf(al, f.x, acc.x); acc.y = fmaf(al, f.y, acc.y);
-            acc.z = fmaf(al, f.z, acc.z); acc.w = fmaf(al, f.w, acc.w);
+#pragma unroll
+            for (int u = 0; u < kRows; ++u) {
+                float4 x = f[u];
+                if (kResid) {
+                    x.x = fmaxf(x.x, 0.f) + t[u].x; x.y = fmaxf(x.y, 0.f) + t[u].y;
+                    x.z = fmaxf(x.z, 0.f) + t[u].z; x.w = fmaxf(x.w, 0.f) + t[u].w;
+                }
+                acc.x = fmaf(al[u], x.x, acc.x); acc.y = fmaf(al[u], x.y, acc.y);
+                acc.z = fmaf(al[u], x.z, acc.z); acc.w = fmaf(al[u], x.w, acc.w);
+            }
         }
         if (p.add_in != nullptr) {
             const float4 c = reinterpret_cast<const float4*>(p.add_in + (size_t)b * p.ldo)[q];
@@ -197,17 +242,23 @@ struct SegArgs {
     int B, H, n_seg, D;
     int* err_flag;                        // device int, set to 1 when a segment id is out of range
     const int32_t* src_index;             // optional [B]: row b reads Xu and cidx of row src_index[b] (shared user graphs)
+    const uint8_t* cmask;                 // optional [B, n_seg]: segments masked out of the user-level attention are not
+                                          // evaluated (T = 0) unless every segment of the row is masked
 };
 
+// One CTA per (user, candidate) row.  The kernel is organised around a compact, segment-sorted list of the LIVE history
+// slots (slots of segments the user-level attention masks out are dropped up front): both streaming passes walk that
+// list four rows at a time, so per-row control work stays small next to the 1600-byte row it loads.
 __global__ void __launch_bounds__(kCtxThreads)
 topic_segment_fwd_kernel(SegArgs p) {
     __shared__ float s_part[kCtxMaxItems][kCtxWarps];
-    __shared__ float s_score[kCtxMaxItems];
+    __shared__ float s_score[kCtxMaxItems];    // per slot: score, then exp(score - segment max)
     __shared__ float s_alpha[kCtxMaxItems];
     __shared__ int s_seg[kCtxMaxItems];
-    __shared__ int s_order[kCtxMaxItems];      // history slots sorted by (segment, slot): a stable counting sort
-    __shared__ int s_start[kCtxMaxItems + 1];
-    const int b = blockIdx.x, tid = threadIdx.x;
+    __shared__ int s_order[kCtxMaxItems];      // live history slots sorted by (segment, slot): a stable counting sort
+    __shared__ int s_start[kCtxMaxItems + 1];  // segment k owns s_order[s_start[k] .. s_start[k+1])
+    __shared__ uint8_t s_segskip[kCtxMaxItems];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int H = p.H, D = p.D, nq = D >> 2, n_seg = p.n_seg;
     const size_t src = p.src_index != nullptr ? (size_t)p.src_index[b] : (size_t)b;
     const float* Xh = p.Xu + src * p.strideX;
@@ -217,58 +268,149 @@ topic_segment_fwd_kernel(SegArgs p) {
         if (c < 0 || c >= n_seg) { ci = n_seg - 1; if (p.err_flag) atomicExch(p.err_flag, 1); }
         s_seg[tid] = ci;
     }
-    ctx_scores<false>(Xh, D, nullptr, 0, p.v + (size_t)b * p.ldv, H, D, sqrtf((float)D), s_part, s_score);
-
-    // segment softmax: every slot recomputes its segment's max and (ascending-order) sum -- H^2 <= 16K flops per row
-    if (tid < H) {
-        const int me = s_seg[tid];
-        float mx = -INFINITY;
-        for (int t = 0; t < H; ++t)
-            if (s_seg[t] == me) mx = fmaxf(mx, s_score[t]);
-        float sum = 0.f;
-        for (int t = 0; t < H; ++t)
-            if (s_seg[t] == me) sum += expf(s_score[t] - mx);
-        const float al = expf(s_score[tid] - mx) / sum;
-        s_alpha[tid] = al;
-        if (p.alpha_out != nullptr) p.alpha_out[(size_t)b * H + tid] = al;
+    {
+        const bool unmasked = p.cmask != nullptr && tid < n_seg && p.cmask[(size_t)b * n_seg + tid] != 0;
+        const int any_unmasked = __syncthreads_or(unmasked ? 1 : 0);           // (also orders the s_seg writes)
+        if (tid < n_seg) s_segskip[tid] = (p.cmask != nullptr && any_unmasked && !unmasked) ? 1 : 0;
+        __syncthreads();
     }
-    // stable counting sort of the slots by segment (thread k handles segment k)
+    // stable counting sort of the live slots by segment (thread k handles segment k)
     for (int k = tid; k <= n_seg; k += kCtxThreads) {
         int cnt = 0;
-        for (int t = 0; t < H; ++t) cnt += (s_seg[t] < k);
+        for (int t = 0; t < H; ++t) {
+            const int sg = s_seg[t];
+            cnt += (sg < k && s_segskip[sg] == 0);
+        }
         s_start[k] = cnt;
     }
     __syncthreads();
     for (int k = tid; k < n_seg; k += kCtxThreads) {
+        if (s_segskip[k]) continue;
         int pos = s_start[k];
         for (int t = 0; t < H; ++t)
             if (s_seg[t] == k) s_order[pos++] = t;
     }
     __syncthreads();
+    const int n_live = s_start[n_seg];
 
-    // segment sum, slots in ascending order inside a segment (the order of a CPU scatter_add)
+    // ---- pass 1: scores of the live slots, a_t = Xh_t . v / sqrt(D)
+    float4 vq[kCtxMaxQuads];
+#pragma unroll
+    for (int c = 0; c < kCtxMaxQuads; ++c) {
+        const int q = tid + c * kCtxThreads;
+        vq[c] = q < nq ? reinterpret_cast<const float4*>(p.v + (size_t)b * p.ldv)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    constexpr int kRows = 4;
+    for (int e0 = 0; e0 < n_live; e0 += kRows) {
+        float4 x[kRows][kCtxMaxQuads];
+        int tt[kRows];
+#pragma unroll
+        for (int u = 0; u < kRows; ++u) {
+            tt[u] = s_order[min(e0 + u, n_live - 1)];                          // the tail repeats the last row (result unused)
+#pragma unroll
+            for (int c = 0; c < kCtxMaxQuads; ++c) {
+                const int q = tid + c * kCtxThreads;
+                x[u][c] = q < nq ? reinterpret_cast<const float4*>(Xh + (size_t)tt[u] * D)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        float part[kRows];
+#pragma unroll
+        for (int u = 0; u < kRows; ++u) {
+            part[u] = 0.f;
+#pragma unroll
+            for (int c = 0; c < kCtxMaxQuads; ++c) {
+                part[u] = fmaf(x[u][c].x, vq[c].x, part[u]);
+                part[u] = fmaf(x[u][c].y, vq[c].y, part[u]);
+                part[u] = fmaf(x[u][c].z, vq[c].z, part[u]);
+                part[u] = fmaf(x[u][c].w, vq[c].w, part[u]);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int u = 0; u < kRows; ++u) part[u] += __shfl_xor_sync(0xffffffffu, part[u], o);
+        if (lane == 0) {
+#pragma unroll
+            for (int u = 0; u < kRows; ++u)
+                if (e0 + u < n_live) s_part[tt[u]][warp] = part[u];
+        }
+    }
+    __syncthreads();
+    const bool live_slot = tid < H && s_segskip[s_seg[tid]] == 0;
+    const float inv_div = sqrtf((float)D);
+    if (live_slot) {
+        float sc = 0.f;
+#pragma unroll
+        for (int w = 0; w < kCtxWarps; ++w) sc += s_part[tid][w];
+        s_score[tid] = sc / inv_div;
+    }
+    __syncthreads();
+    // ---- segment softmax over the slot's own segment (its sorted range, ascending slots): max, exp once per slot, sum
+    int r0 = 0, r1 = 0;
+    float mx = 0.f;
+    if (live_slot) {
+        r0 = s_start[s_seg[tid]];
+        r1 = s_start[s_seg[tid] + 1];
+        mx = -INFINITY;
+        for (int e = r0; e < r1; ++e) mx = fmaxf(mx, s_score[s_order[e]]);
+    }
+    __syncthreads();
+    if (live_slot) s_score[tid] = expf(s_score[tid] - mx);
+    __syncthreads();
+    if (tid < H) {
+        float al = 0.f;
+        if (live_slot) {
+            float sum = 0.f;
+            for (int e = r0; e < r1; ++e) sum += s_score[s_order[e]];
+            al = s_score[tid] / sum;
+        }
+        s_alpha[tid] = al;
+        if (p.alpha_out != nullptr) p.alpha_out[(size_t)b * H + tid] = al;
+    }
+    __syncthreads();
+
+    // ---- pass 2: T[k] = sum over segment k (ascending slots) of alpha_t * Xh_t; segments without live slots are 0
 #pragma unroll
     for (int c = 0; c < kCtxMaxQuads; ++c) {
         const int q = tid + c * kCtxThreads;
         if (q >= nq) continue;
-        for (int k = 0; k < n_seg; ++k) {
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int pos = s_start[k]; pos < s_start[k + 1]; ++pos) {
-                const int t = s_order[pos];
-                const float al = s_alpha[t];
-                const float4 x = reinterpret_cast<const float4*>(Xh + (size_t)t * D)[q];
-                // alpha * x is rounded before the add in the reference (alpha * X then scatter_add): no fma here
-                acc.x = __fadd_rn(acc.x, __fmul_rn(al, x.x)); acc.y = __fadd_rn(acc.y, __fmul_rn(al, x.y));
-                acc.z = __fadd_rn(acc.z, __fmul_rn(al, x.z)); acc.w = __fadd_rn(acc.w, __fmul_rn(al, x.w));
+        float4* Tq = reinterpret_cast<float4*>(p.T + (size_t)b * n_seg * D) + q;
+        for (int k = 0; k < n_seg; ++k)
+            if (s_start[k + 1] == s_start[k]) Tq[(size_t)k * nq] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int cur = n_live > 0 ? s_seg[s_order[0]] : 0;
+        for (int e0 = 0; e0 < n_live; e0 += kRows) {
+            float4 x[kRows];
+            float al[kRows];
+            int sg[kRows];
+#pragma unroll
+            for (int u = 0; u < kRows; ++u) {
+                const int t = s_order[min(e0 + u, n_live - 1)];
+                sg[u] = s_seg[t];
+                al[u] = s_alpha[t];
+                x[u] = reinterpret_cast<const float4*>(Xh + (size_t)t * D)[q];
             }
-            reinterpret_cast<float4*>(p.T + ((size_t)b * n_seg + k) * D)[q] = acc;
+#pragma unroll
+            for (int u = 0; u < kRows; ++u) {
+                if (e0 + u < n_live) {                                        // CTA-uniform control flow (shared-memory data only)
+                    if (sg[u] != cur) {
+                        Tq[(size_t)cur * nq] = acc;
+                        acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                        cur = sg[u];
+                    }
+                    // alpha * x is rounded before the add in the reference (alpha * X then scatter_add): no fma here
+                    acc.x = __fadd_rn(acc.x, __fmul_rn(al[u], x[u].x)); acc.y = __fadd_rn(acc.y, __fmul_rn(al[u], x[u].y));
+                    acc.z = __fadd_rn(acc.z, __fmul_rn(al[u], x[u].z)); acc.w = __fadd_rn(acc.w, __fmul_rn(al[u], x[u].w));
+                }
+            }
         }
+        if (n_live > 0) Tq[(size_t)cur * nq] = acc;
     }
 }
 
 inline int launch_topic_segment_fwd(const float* Xu, int64_t strideX, const float* v, int ldv, const int64_t* cidx, float* T,
-                                    float* alpha_out, int32_t* err_flag, const int32_t* src_index, int B, int H, int n_seg, int D,
-                                    cudaStream_t st) {
+                                    float* alpha_out, int32_t* err_flag, const int32_t* src_index, const uint8_t* cmask,
+                                    int B, int H, int n_seg, int D, cudaStream_t st) {
     if (B <= 0) return DIGAT_OK;
     DIGAT_REQUIRE(Xu && v && cidx && T, "digat_topic_segment_fwd: null pointer");
     DIGAT_REQUIRE(H >= 1 && H <= kCtxMaxItems && n_seg >= 1 && n_seg <= kCtxMaxItems,
@@ -278,7 +420,7 @@ inline int launch_topic_segment_fwd(const float* Xu, int64_t strideX, const floa
                   "digat_topic_segment_fwd: pointers/strides must be 16-byte aligned");
     if (B <= 0) return DIGAT_OK;
     DIGAT_REQUIRE((ldv & 3) == 0 && ldv >= D, "digat_topic_segment_fwd: ldv must be a multiple of 4 and >= D");
-    SegArgs a{Xu, strideX, v, ldv, cidx, T, alpha_out, B, H, n_seg, D, err_flag, src_index};
+    SegArgs a{Xu, strideX, v, ldv, cidx, T, alpha_out, B, H, n_seg, D, err_flag, src_index, cmask};
     topic_segment_fwd_kernel<<<B, kCtxThreads, 0, st>>>(a);
     return check_launch("digat_topic_segment_fwd");
 }

@@ -92,9 +92,9 @@ int digat_news_gate_fwd(const float* z, const float* lg, const float* ctx_in, fl
 }
 
 int digat_topic_segment_fwd(const float* Xu, int64_t strideX, const float* v, int ldv, const int64_t* cidx, float* T,
-                            float* alpha_out, int32_t* err_flag, const int32_t* src_index, int B, int H, int n_seg,
-                            int D, void* stream) {
-    return launch_topic_segment_fwd(Xu, strideX, v, ldv, cidx, T, alpha_out, err_flag, src_index, B, H, n_seg, D,
+                            float* alpha_out, int32_t* err_flag, const int32_t* src_index, const uint8_t* cmask,
+                            int B, int H, int n_seg, int D, void* stream) {
+    return launch_topic_segment_fwd(Xu, strideX, v, ldv, cidx, T, alpha_out, err_flag, src_index, cmask, B, H, n_seg, D,
                                     as_stream(stream));
 }
 

@@ -26,9 +26,18 @@
 
 namespace digat {
 
-constexpr int kSparseConsumers = 320;                     // warps 0..9
+#ifndef DIGAT_SPARSE_WARPS
+#define DIGAT_SPARSE_WARPS 10
+#endif
+#ifndef DIGAT_SPARSE_BUFS
+#define DIGAT_SPARSE_BUFS 4
+#endif
+#ifndef DIGAT_SPARSE_MINCTAS
+#define DIGAT_SPARSE_MINCTAS 2
+#endif
+constexpr int kSparseConsumers = 32 * DIGAT_SPARSE_WARPS; // consumer warps 0..W-1
 constexpr int kSparseThreads = kSparseConsumers + 32;     // + producer warp
-constexpr int kSparseBufs = 4;
+constexpr int kSparseBufs = DIGAT_SPARSE_BUFS;
 constexpr int kSparseDc1 = 32, kSparseDc3 = 64;
 
 struct SparseGeom {
@@ -43,7 +52,7 @@ __device__ __forceinline__ void consumer_sync() {         // named barrier over 
 }
 
 template <bool kIndexed>
-__global__ void __launch_bounds__(kSparseThreads, 2)
+__global__ void __launch_bounds__(kSparseThreads, DIGAT_SPARSE_MINCTAS)
 graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map3,
                               PairAttnArgs p, SparseGeom g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -59,10 +68,9 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
     float* k3_s = a_s + D;                                         // [D]
     float* score = k3_s + D;                                       // [n*n] per-edge score, later alpha~
     int* rowptr = reinterpret_cast<int*>(score + n * n);           // [n+2]
-    uint8_t* col = reinterpret_cast<uint8_t*>(rowptr + (n + 2));   // [n*n] neighbour (column) index of each edge
-    uint8_t* erow = col + n * n;                                   // [n*n] query (row) index of each edge
-    uint8_t* adj_s = erow + n * n;                                 // [n*n] adjacency bytes
-    uint8_t* uniform_row = adj_s + n * n;                          // [n] 1 = row without edges (uniform softmax)
+    uint16_t* meta = reinterpret_cast<uint16_t*>(rowptr + (n + 2)); // [n*n] per edge: neighbour (column) | query row << 8
+    uint8_t* adj_s = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(meta + n * n) + 15) & ~(uintptr_t)15);   // [n*n], 16-byte aligned
+    uint8_t* uniform_row = adj_s + ((n * n + 15) & ~15);           // [n] 1 = row without edges (uniform softmax)
     uint8_t* dead_row = uniform_row + n;                           // [n] 1 = pruned node (row_active == 0): no edges, Y = X
 
     if (tid == 0) {
@@ -104,22 +112,32 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
         if (kIndexed) reinterpret_cast<float4*>(k3_s)[i] = reinterpret_cast<const float4*>(p.k3 + (size_t)b * p.ldk3)[i];
     }
     {
-        const size_t ag = p.adj_index != nullptr ? (size_t)p.adj_index[b] : (size_t)b;
-        const uint8_t* srcp = p.adj + ag * n * n;
-        for (int i = tid; i < n * n; i += kSparseConsumers) adj_s[i] = srcp[i];
+        // adjacency -> shared memory with independent 16-byte loads (one round trip) when the graph is 16-byte aligned
+        const uint8_t* adj_g = p.adj + (p.adj_index != nullptr ? (size_t)p.adj_index[b] : (size_t)b) * n * n;
+        const int n2 = n * n;
+        if (((n2 | (int)(reinterpret_cast<uintptr_t>(adj_g) & 15)) & 15) == 0) {
+            for (int i = tid; i < n2 / 16; i += kSparseConsumers)
+                reinterpret_cast<uint4*>(adj_s)[i] = __ldg(reinterpret_cast<const uint4*>(adj_g) + i);
+        } else {
+            for (int i = tid; i < n2; i += kSparseConsumers) adj_s[i] = adj_g[i];
+        }
         for (int i = tid; i < n; i += kSparseConsumers)
             dead_row[i] = (p.row_active != nullptr && p.row_active[(size_t)b * n + i] == 0) ? 1 : 0;
     }
     consumer_sync();
-    // CSR pass A: degrees (a row without edges becomes a full row with uniform weights)
+#ifdef DIGAT_TC_TIMING
+    const long long ta = clock64();
+#endif
+    // CSR pass A: degrees (a row without edges becomes a full row with uniform weights; a pruned row has no edges)
     for (int i = warp; i < n; i += kSparseConsumers / 32) {
+        const bool dead = dead_row[i] != 0;
         int deg = 0;
-        for (int k = 0; k < (n + 31) / 32; ++k) {
-            const int j = lane + 32 * k;
-            deg += __popc(__ballot_sync(0xffffffffu, j < n && adj_s[i * n + j] != 0));
-        }
+        if (!dead)
+            for (int k = 0; k < (n + 31) / 32; ++k) {
+                const int j = lane + 32 * k;
+                deg += __popc(__ballot_sync(0xffffffffu, j < n && adj_s[i * n + j] != 0));
+            }
         if (lane == 0) {
-            const bool dead = dead_row[i] != 0;
             uniform_row[i] = deg == 0 && !dead;
             rowptr[i + 1] = dead ? 0 : (deg == 0 ? n : deg);       // degrees for now, scanned below
         }
@@ -153,14 +171,13 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
             const unsigned m = __ballot_sync(0xffffffffu, on);
             if (on) {
                 const int e = e0 + filled + __popc(m & ((1u << lane) - 1u));
-                col[e] = (uint8_t)j;
-                erow[e] = (uint8_t)i;
+                meta[e] = (uint16_t)(j | (i << 8));
+                score[e] = 0.f;
             }
             filled += __popc(m);
         }
     }
     const int E = rowptr[n];
-    for (int e = tid; e < E; e += kSparseConsumers) score[e] = 0.f;
     consumer_sync();
 
 #ifdef DIGAT_TC_TIMING
@@ -180,8 +197,9 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
         for (int e = tid; e < E; e += kSparseConsumers) {          // one edge per thread: all lanes busy for E >= 320
             // rows are 128 bytes (all rows would start in bank 0): the tiles are loaded with SWIZZLE_128B, i.e. the 16-byte
             // chunk q of the 128-byte line L sits at chunk q ^ (L & 7) -- threads on different rows hit different banks
-            const uint32_t uo = uoff + (uint32_t)(col[e] * kSparseDc1) * 4u;
-            const uint32_t ko = koff + (uint32_t)(erow[e] * kSparseDc1) * 4u;
+            const uint32_t mt = meta[e];
+            const uint32_t uo = uoff + (mt & 255u) * (uint32_t)(kSparseDc1 * 4);
+            const uint32_t ko = koff + (mt >> 8) * (uint32_t)(kSparseDc1 * 4);
             const uint32_t ukey = ((uo >> 7) & 7u) << 4, kkey = ((ko >> 7) & 7u) << 4;
             uint64_t acc0 = 0ull, acc1 = 0ull;
 #pragma unroll 2
@@ -218,7 +236,20 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
     // ---------------------------------------------------------------------- phase 2: softmax over each row's edges
     for (int i = warp; i < n; i += kSparseConsumers / 32) {
         const int e0 = rowptr[i], deg = rowptr[i + 1] - e0;
+        if (deg == 0) continue;                                    // pruned row
         const bool uni = uniform_row[i] != 0;
+        if (deg <= 32) {                                           // the common case: one edge per lane
+            float m = -INFINITY;
+            if (lane < deg) {
+                const float s = score[e0 + lane];
+                m = uni ? kNegFill : (s > 0.f ? s : s * kLeakySlope);
+            }
+            const float mx1 = warp_max(m);
+            const float ex = lane < deg ? expf(m - mx1) : 0.f;
+            const float sum1 = warp_sum(ex);
+            if (lane < deg) score[e0 + lane] = ex / sum1;
+            continue;
+        }
         float v[kPairMaxNodes / 32];
         float mx = -INFINITY;
 #pragma unroll
@@ -281,8 +312,9 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
             xq[sl] = load_x(unit + 1, sl);                          // next unit's rows: in flight during this unit
         }
         mbar_wait(&full[buf], (uint32_t)(l / kSparseBufs) & 1u);
+        constexpr int kMaxPasses = (kPairMaxNodes / 2 + kRowPairStep - 1) / kRowPairStep;
 #pragma unroll
-        for (int sl = 0; sl < kXSlots + 3; ++sl) {                  // n <= 128: at most 7 passes; slots >= kXSlots load directly
+        for (int sl = 0; sl < kMaxPasses; ++sl) {                   // slots >= kXSlots load their residual directly
             const int rp = warp + sl * kRowPairStep;
             if (2 * rp >= n) break;
             const int i = 2 * rp + sub;
@@ -295,10 +327,25 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
                 const float* Hs = Hs0 + 4 * q;
                 uint64_t o01 = 0ull, o23 = 0ull;
                 const int e1 = rowptr[i + 1];
-#pragma unroll 2
-                for (int e = rowptr[i]; e < e1; ++e) {
-                    const float al = score[e];                                              // broadcast within the half warp
-                    const float4 h = *reinterpret_cast<const float4*>(Hs + col[e] * kSparseDc3);
+                int e = rowptr[i];
+                for (; e + 4 <= e1; e += 4) {                                               // 4 neighbours in flight
+                    float al[4];
+                    float4 h[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        al[u] = score[e + u];                                               // broadcast within the half warp
+                        h[u] = *reinterpret_cast<const float4*>(Hs + (meta[e + u] & 255u) * kSparseDc3);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint64_t aa = pack2(al[u], al[u]);
+                        o01 = fma2(aa, pack2(h[u].x, h[u].y), o01);
+                        o23 = fma2(aa, pack2(h[u].z, h[u].w), o23);
+                    }
+                }
+                for (; e < e1; ++e) {
+                    const float al = score[e];
+                    const float4 h = *reinterpret_cast<const float4*>(Hs + (meta[e] & 255u) * kSparseDc3);
                     const uint64_t aa = pack2(al, al);
                     o01 = fma2(aa, pack2(h.x, h.y), o01);
                     o23 = fma2(aa, pack2(h.z, h.w), o23);
@@ -318,7 +365,7 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
     }
 #ifdef DIGAT_TC_TIMING
     if (tid == 0 && (b % 1000) == 7)
-        printf("graph %d E=%d: setup %lld, phase1 %lld, softmax %lld, phase3 %lld\n", b, E, t1 - t0, t2 - t1, t3 - t2, clock64() - t3);
+        printf("graph %d E=%d: setup %lld (loads %lld), phase1 %lld, softmax %lld, phase3 %lld\n", b, E, t1 - t0, ta - t0, t2 - t1, t3 - t2, clock64() - t3);
 #endif
 }
 
@@ -328,7 +375,7 @@ inline void sparse_geometry(int n, int D, SparseGeom* g) {
     g->tile_floats = ((n * kSparseDc1 * 4 + 1023) / 1024) * 1024 / 4;
     g->unit_floats = 2 * g->tile_floats;
     g->smem = (size_t)kSparseBufs * g->unit_floats * 4 + (size_t)2 * kSparseBufs * 8 + (size_t)2 * D * 4 +
-              (size_t)n * n * 4 + (size_t)(n + 2) * 4 + (size_t)3 * n * n + (size_t)2 * n + 16;
+              (size_t)n * n * 4 + (size_t)(n + 2) * 4 + (size_t)2 * n * n + (size_t)((n * n + 15) & ~15) + (size_t)2 * n + 48;
 }
 
 size_t graph_layer_fwd_sparse_smem(int n, int D) {

@@ -286,7 +286,8 @@ class DIGAT(GraphEncoder):
         k3_next = vv[:, 2 * D:] if vv.shape[1] > 2 * D else None
         T = torch.empty((B, S, D), device=Xu.device, dtype=torch.float32)
         _lib.call('digat_topic_segment_fwd', Xu.data_ptr(), nu * D, v1.data_ptr(), vv.stride(0), cidx.data_ptr(),
-                  T.data_ptr(), 0, self._err_flag(Xu.device).data_ptr(), _ptr(src_index), B, H, S, D, _stream())
+                  T.data_ptr(), 0, self._err_flag(Xu.device).data_ptr(), _ptr(src_index),
+                  cmask.data_ptr() if self.prune_user_nodes else 0, B, H, S, D, _stream())
         Fa = linear(T, w['fa_W'], w['fa_b'])                                      # featureAffine(T)  [B*S, D]
         return attention_pool_fwd(Fa.view(B, S, D), v2, cmask, resid=T, add_in=ctx_in), k3_next
 

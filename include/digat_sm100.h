@@ -144,10 +144,13 @@ int digat_news_gate_fwd(const float* z, const float* lg, const float* ctx_in, fl
  *   T[b,k] = sum_{t in segment k, ascending t} alpha_t Xh[b,t],  k in [0, n_seg); empty segments are 0.
  *   Xh = first H rows of X_u [B, n_u, D] (batch stride strideX elements); cidx int64 [B,H] in [0,n_seg).
  * alpha_out [B,H] optional.  err_flag: see the gathers below.  src_index [B] optional: row b reads Xu and cidx of
- * row src_index[b] (user graphs shared by the pairs of one impression). */
+ * row src_index[b] (user graphs shared by the pairs of one impression).
+ * cmask [B,n_seg] bool optional (inference): the mask the user-level attention applies to T afterwards
+ * (graphEncoders.py:132).  Segments with cmask == 0 get a softmax weight of exactly 0 there, so their history rows are
+ * not read and T[b,k] = 0 -- unless every segment of row b is masked (uniform weights: everything is evaluated). */
 int digat_topic_segment_fwd(const float* Xu, int64_t strideX, const float* v, int ldv, const int64_t* cidx,
                             float* T, float* alpha_out, int32_t* err_flag, const int32_t* src_index,
-                            int B, int H, int n_seg, int D, void* stream);
+                            const uint8_t* cmask, int B, int H, int n_seg, int D, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Gathers (replace index_select at util.py:34-36 and util.py:65-67) and small glue.
