@@ -211,12 +211,12 @@ def main():
             for s in range(total_steps)]
     h2d = int(sum(t.numel() * t.element_size() for t in host[0]))
     res = torch.empty((total_steps, args.batch), dtype=torch.float32).pin_memory()
-    for s in range(args.warmup):
-        res[s].copy_(scorer.score_host_batch(*host[s]), non_blocking=True)
+    scoring.score_host_batches(scorer, host[:args.warmup], res[:args.warmup])
     barrier()
     e0.record()
-    for s in range(args.warmup, total_steps):
-        res[s].copy_(scorer.score_host_batch(*host[s]), non_blocking=True)
+    # the public pipelined call: every timed step's H2D copy and D2H read is issued inside the timed region
+    # (batch k+1's copies overlap batch k's kernels on a side stream)
+    scoring.score_host_batches(scorer, host[args.warmup:total_steps], res[args.warmup:total_steps])
     e1.record()
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))

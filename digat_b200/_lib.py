@@ -4,7 +4,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libdigat_sm100.so')
+LIB_PATH = os.environ.get('DIGAT_SM100_LIB') or os.path.join(_HERE, 'libdigat_sm100.so')   # (override: kernel experiments)
 
 c_void_p, c_int, c_int64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
 

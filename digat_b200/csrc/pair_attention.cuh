@@ -427,9 +427,10 @@ inline int launch_graph_layer_fwd(const float* P, int ldp, const float* a, const
     PairAttnArgs args{P, ldp, a, adj, X, Y, B, n, D, drop_keep, drop_scale, score_out, alpha_out, relu_mask_out,
                       px_index, adj_index, k3, ldk3, row_active};
     const bool inference = !drop_keep && !score_out && !alpha_out && !relu_mask_out;
-    // auto mode keeps the dense kernel for graphs whose edge-driven working set does not fit one CTA (n > ~100 at D = 400)
+    // Inference takes the edge-driven kernel (small graphs are batched several per CTA); the dense kernel stays for
+    // training and for graphs whose edge-driven working set does not fit one CTA (n > ~100 at D = 400).
     const bool sparse_fits = graph_layer_fwd_sparse_smem(n, D) <= (size_t)di->max_smem_optin;
-    if (inference && g_layer_mode != 1 && ((g.R == 1 && sparse_fits) || g_layer_mode == 2))
+    if (inference && g_layer_mode != 1 && (sparse_fits || g_layer_mode == 2))
         return launch_graph_layer_fwd_sparse(args, n_src, st);
     if (row_active != nullptr)
         return fail(DIGAT_E_UNSUPPORTED, "digat_graph_layer_fwd: row_active needs the edge-driven kernel (inference, one graph "
@@ -452,9 +453,7 @@ inline int graph_layer_supports_row_active(int n, int D, int B) {
     if (n < 1 || n > kPairMaxNodes || D < 4 || (D & 3) != 0 || D > 1024 || B < 1 || g_layer_mode == 1) return 0;
     const DeviceInfo* di = device_info();
     if (!di) return 0;
-    PairAttnGeom g;
-    pair_attn_geometry(n, D, B, false, &g);
-    return (g.R == 1 || g_layer_mode == 2) && graph_layer_fwd_sparse_smem(n, D) <= (size_t)di->max_smem_optin ? 1 : 0;
+    return graph_layer_fwd_sparse_smem(n, D) <= (size_t)di->max_smem_optin ? 1 : 0;
 }
 
 }  // namespace digat

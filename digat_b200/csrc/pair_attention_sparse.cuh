@@ -42,8 +42,9 @@ constexpr int kSparseDc1 = 32, kSparseDc3 = 64;
 
 struct SparseGeom {
     int nch1, nch3;
-    int tile_floats;       // floats of one [n][32] tile rounded up to 1024 bytes (SWIZZLE_128B atoms stay aligned)
-    int unit_floats;       // floats of one ring buffer = 2 tiles (>= the [n][64] h tile)
+    int G;                 // graphs per CTA: small graphs are batched into one block-diagonal graph of G*n nodes
+    int tile_floats;       // floats of one [G*n][32] tile rounded up to 1024 bytes (SWIZZLE_128B atoms stay aligned)
+    int unit_floats;       // floats of one ring buffer = 2 tiles (>= the [G*n][64] h tile)
     size_t smem;
 };
 
@@ -51,14 +52,17 @@ __device__ __forceinline__ void consumer_sync() {         // named barrier over 
     asm volatile("bar.sync 1, %0;" :: "n"(kSparseConsumers) : "memory");
 }
 
-template <bool kIndexed>
+// kMulti: several small graphs per CTA (block-diagonal); false keeps every index a function of n alone (one graph per CTA)
+template <bool kIndexed, bool kMulti>
 __global__ void __launch_bounds__(kSparseThreads, DIGAT_SPARSE_MINCTAS)
 graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map3,
                               PairAttnArgs p, SparseGeom g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = p.n, D = p.D;
-    const int b = blockIdx.x;
+    const int b = kMulti ? blockIdx.x * g.G : blockIdx.x;          // first graph of this CTA (G == 1 in indexed mode)
+    const int N = kMulti ? min(g.G, p.B - b) * n : n;              // nodes of the block-diagonal graph this CTA evaluates
+    const int NB = kMulti ? g.G * n : n;                           // rows of a TMA box
     const int src0 = kIndexed ? p.px_index[b] : b;
 
     float* ring = reinterpret_cast<float*>(smem_raw);              // [kSparseBufs][unit_floats]
@@ -66,12 +70,12 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
     uint64_t* empty = full + kSparseBufs;                          // [kSparseBufs]
     float* a_s = reinterpret_cast<float*>(empty + kSparseBufs);    // [D]
     float* k3_s = a_s + D;                                         // [D]
-    float* score = k3_s + D;                                       // [n*n] per-edge score, later alpha~
-    int* rowptr = reinterpret_cast<int*>(score + n * n);           // [n+2]
-    uint16_t* meta = reinterpret_cast<uint16_t*>(rowptr + (n + 2)); // [n*n] per edge: neighbour (column) | query row << 8
-    uint8_t* adj_s = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(meta + n * n) + 15) & ~(uintptr_t)15);   // [n*n], 16-byte aligned
-    uint8_t* uniform_row = adj_s + ((n * n + 15) & ~15);           // [n] 1 = row without edges (uniform softmax)
-    uint8_t* dead_row = uniform_row + n;                           // [n] 1 = pruned node (row_active == 0): no edges, Y = X
+    float* score = k3_s + D;                                       // [NB*n] per-edge score, later alpha~
+    int* rowptr = reinterpret_cast<int*>(score + NB * n);          // [NB+2]
+    uint16_t* meta = reinterpret_cast<uint16_t*>(rowptr + (NB + 2)); // [NB*n] per edge: neighbour (column) | query row << 8
+    uint8_t* adj_s = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(meta + NB * n) + 15) & ~(uintptr_t)15);   // [NB*n], 16-byte aligned
+    uint8_t* uniform_row = adj_s + ((NB * n + 15) & ~15);          // [NB] 1 = row without edges (uniform softmax)
+    uint8_t* dead_row = uniform_row + NB;                          // [NB] 1 = pruned node (row_active == 0): no edges, Y = X
 
     if (tid == 0) {
         for (int i = 0; i < kSparseBufs; ++i) {
@@ -91,11 +95,11 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
                 float* dst = ring + buf * g.unit_floats;
                 mbar_wait(&empty[buf], ((uint32_t)(l / kSparseBufs) & 1u) ^ 1u);
                 if (l < g.nch1) {
-                    mbar_arrive_expect_tx(&full[buf], 2u * n * kSparseDc1 * 4u);
+                    mbar_arrive_expect_tx(&full[buf], 2u * NB * kSparseDc1 * 4u);       // (rows past the tensor end arrive as zeros)
                     tma_load_2d(dst, &map1, &full[buf], D + l * kSparseDc1, src0 * n);                     // U (or K1)
                     tma_load_2d(dst + g.tile_floats, &map1, &full[buf], 2 * D + l * kSparseDc1, src0 * n);  // K2
                 } else {
-                    mbar_arrive_expect_tx(&full[buf], (uint32_t)n * kSparseDc3 * 4u);
+                    mbar_arrive_expect_tx(&full[buf], (uint32_t)NB * kSparseDc3 * 4u);
                     tma_load_2d(dst, &map3, &full[buf], (l - g.nch1) * kSparseDc3, src0 * n);              // h
                 }
             }
@@ -113,15 +117,16 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
     }
     {
         // adjacency -> shared memory with independent 16-byte loads (one round trip) when the graph is 16-byte aligned
+        // (the graphs of one CTA are consecutive in memory: several graphs per CTA only without adj_index)
         const uint8_t* adj_g = p.adj + (p.adj_index != nullptr ? (size_t)p.adj_index[b] : (size_t)b) * n * n;
-        const int n2 = n * n;
+        const int n2 = N * n;
         if (((n2 | (int)(reinterpret_cast<uintptr_t>(adj_g) & 15)) & 15) == 0) {
             for (int i = tid; i < n2 / 16; i += kSparseConsumers)
                 reinterpret_cast<uint4*>(adj_s)[i] = __ldg(reinterpret_cast<const uint4*>(adj_g) + i);
         } else {
             for (int i = tid; i < n2; i += kSparseConsumers) adj_s[i] = adj_g[i];
         }
-        for (int i = tid; i < n; i += kSparseConsumers)
+        for (int i = tid; i < N; i += kSparseConsumers)
             dead_row[i] = (p.row_active != nullptr && p.row_active[(size_t)b * n + i] == 0) ? 1 : 0;
     }
     consumer_sync();
@@ -129,7 +134,7 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
     const long long ta = clock64();
 #endif
     // CSR pass A: degrees (a row without edges becomes a full row with uniform weights; a pruned row has no edges)
-    for (int i = warp; i < n; i += kSparseConsumers / 32) {
+    for (int i = warp; i < N; i += kSparseConsumers / 32) {        // row i of the block-diagonal graph = adjacency row i, n columns
         const bool dead = dead_row[i] != 0;
         int deg = 0;
         if (!dead)
@@ -145,25 +150,26 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
     consumer_sync();
     if (warp == 0) {                                               // inclusive scan of <= 128 entries by one warp
         int run_e = 0;
-        for (int base = 0; base < n; base += 32) {
+        for (int base = 0; base < N; base += 32) {
             const int i = base + lane;
-            int ve = i < n ? rowptr[i + 1] : 0;
+            int ve = i < N ? rowptr[i + 1] : 0;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const int te = __shfl_up_sync(0xffffffffu, ve, o);
                 if (lane >= o) ve += te;
             }
-            if (i < n) rowptr[i + 1] = run_e + ve;
+            if (i < N) rowptr[i + 1] = run_e + ve;
             run_e += __shfl_sync(0xffffffffu, ve, 31);
         }
         if (lane == 0) rowptr[0] = 0;
     }
     consumer_sync();
     // CSR pass B: column / row index of every edge, zeroed scores
-    for (int i = warp; i < n; i += kSparseConsumers / 32) {
+    for (int i = warp; i < N; i += kSparseConsumers / 32) {
         const int e0 = rowptr[i];
         const bool uni = uniform_row[i] != 0;
         if (dead_row[i] != 0) continue;
+        const int node0 = kMulti ? (i / n) * n : 0;                // first node of row i's graph inside the CTA
         int filled = 0;
         for (int k = 0; k < (n + 31) / 32; ++k) {
             const int j = lane + 32 * k;
@@ -171,13 +177,13 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
             const unsigned m = __ballot_sync(0xffffffffu, on);
             if (on) {
                 const int e = e0 + filled + __popc(m & ((1u << lane) - 1u));
-                meta[e] = (uint16_t)(j | (i << 8));
+                meta[e] = (uint16_t)((node0 + j) | (i << 8));
                 score[e] = 0.f;
             }
             filled += __popc(m);
         }
     }
-    const int E = rowptr[n];
+    const int E = rowptr[N];
     consumer_sync();
 
 #ifdef DIGAT_TC_TIMING
@@ -234,7 +240,7 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
 #endif
 
     // ---------------------------------------------------------------------- phase 2: softmax over each row's edges
-    for (int i = warp; i < n; i += kSparseConsumers / 32) {
+    for (int i = warp; i < N; i += kSparseConsumers / 32) {
         const int e0 = rowptr[i], deg = rowptr[i + 1] - e0;
         if (deg == 0) continue;                                    // pruned row
         const bool uni = uniform_row[i] != 0;
@@ -292,7 +298,7 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
     auto load_x = [&](int unit, int slot) {
         const int c0_ = unit * kSparseDc3;
         const int i_ = 2 * (warp + slot * kRowPairStep) + sub;
-        return (unit < g.nch3 && i_ < n && c0_ + 4 * half_lane < D)
+        return (unit < g.nch3 && i_ < N && c0_ + 4 * half_lane < D)
                    ? ldg_stream(reinterpret_cast<const float4*>(p.X + ((size_t)src0 * n + i_) * D + c0_ + 4 * half_lane))
                    : make_float4(0.f, 0.f, 0.f, 0.f);
     };
@@ -316,9 +322,9 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
 #pragma unroll
         for (int sl = 0; sl < kMaxPasses; ++sl) {                   // slots >= kXSlots load their residual directly
             const int rp = warp + sl * kRowPairStep;
-            if (2 * rp >= n) break;
+            if (2 * rp >= N) break;
             const int i = 2 * rp + sub;
-            if (i < n && half_lane < wq) {
+            if (i < N && half_lane < wq) {
                 const int q = half_lane;
                 const size_t yoff = ((size_t)b * n + i) * D + c0 + 4 * q;
                 float4 x;
@@ -369,39 +375,64 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
 #endif
 }
 
-inline void sparse_geometry(int n, int D, SparseGeom* g) {
+inline void sparse_geometry(int n, int D, int G, SparseGeom* g) {
+    const int NB = G * n;
+    g->G = G;
     g->nch1 = (D + kSparseDc1 - 1) / kSparseDc1;
     g->nch3 = (D + kSparseDc3 - 1) / kSparseDc3;
-    g->tile_floats = ((n * kSparseDc1 * 4 + 1023) / 1024) * 1024 / 4;
+    g->tile_floats = ((NB * kSparseDc1 * 4 + 1023) / 1024) * 1024 / 4;
     g->unit_floats = 2 * g->tile_floats;
     g->smem = (size_t)kSparseBufs * g->unit_floats * 4 + (size_t)2 * kSparseBufs * 8 + (size_t)2 * D * 4 +
-              (size_t)n * n * 4 + (size_t)(n + 2) * 4 + (size_t)2 * n * n + (size_t)((n * n + 15) & ~15) + (size_t)2 * n + 48;
+              (size_t)NB * n * 4 + (size_t)(NB + 2) * 4 + (size_t)2 * NB * n + (size_t)((NB * n + 15) & ~15) + (size_t)2 * NB + 48;
 }
 
 size_t graph_layer_fwd_sparse_smem(int n, int D) {
     SparseGeom g;
-    sparse_geometry(n, D, &g);
+    sparse_geometry(n, D, 1, &g);
     return g.smem;
 }
 
+// Graphs per CTA for small graphs (not indexed): at most 128 nodes and the shared memory of DIGAT_SPARSE_MINCTAS CTAs per
+// SM; among those the G that minimises (waves of CTAs) x (G + fixed per-CTA cost).
+inline int sparse_graphs_per_cta(int n, int D, int B, int sm_count, size_t max_smem) {
+    const size_t budget = (size_t)(227 * 1024) / DIGAT_SPARSE_MINCTAS - 1024 < max_smem ? (size_t)(227 * 1024) / DIGAT_SPARSE_MINCTAS - 1024 : max_smem;
+    int best = 1;
+    long best_cost = -1;
+    for (int G = 1; G * n <= kPairMaxNodes && G <= B; ++G) {
+        SparseGeom g;
+        sparse_geometry(n, D, G, &g);
+        if (G > 1 && g.smem > budget) break;
+        const long ctas = (B + G - 1) / G, slots = (long)sm_count * DIGAT_SPARSE_MINCTAS;
+        const long cost = ((ctas + slots - 1) / slots) * (G * (long)n + 24);     // ~24 nodes' worth of fixed work per CTA
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = G; }
+    }
+    return best;
+}
+
 int launch_graph_layer_fwd_sparse(const PairAttnArgs& args, int n_src, cudaStream_t st) {
-    SparseGeom g;
-    sparse_geometry(args.n, args.D, &g);
     const DeviceInfo* di = device_info();
     if (!di) return fail(DIGAT_E_CUDA, "digat_graph_layer_fwd: no CUDA device");
+    const bool indexed = args.px_index != nullptr;
+    const int G = (indexed || args.adj_index != nullptr) ? 1
+                  : sparse_graphs_per_cta(args.n, args.D, args.B, di->sm_count, (size_t)di->max_smem_optin);
+    SparseGeom g;
+    sparse_geometry(args.n, args.D, G, &g);
     DIGAT_REQUIRE(g.smem <= (size_t)di->max_smem_optin, "digat_graph_layer_fwd(sparse): needs %zu B shared memory", g.smem);
     CUtensorMap map1, map3;
     int rc;
-    const bool indexed = args.px_index != nullptr;
     const int64_t src_graphs = indexed ? n_src : args.B;
-    if ((rc = make_tensor_map_2d(&map1, args.P, src_graphs * args.n, 3 * args.D, args.ldp, args.n, kSparseDc1, CU_TENSOR_MAP_SWIZZLE_128B)) != DIGAT_OK) return rc;
-    if ((rc = make_tensor_map_2d(&map3, args.P, src_graphs * args.n, 3 * args.D, args.ldp, args.n, kSparseDc3, CU_TENSOR_MAP_SWIZZLE_NONE)) != DIGAT_OK) return rc;
+    if ((rc = make_tensor_map_2d(&map1, args.P, src_graphs * args.n, 3 * args.D, args.ldp, G * args.n, kSparseDc1, CU_TENSOR_MAP_SWIZZLE_128B)) != DIGAT_OK) return rc;
+    if ((rc = make_tensor_map_2d(&map3, args.P, src_graphs * args.n, 3 * args.D, args.ldp, G * args.n, kSparseDc3, CU_TENSOR_MAP_SWIZZLE_NONE)) != DIGAT_OK) return rc;
+    const int grid = (args.B + G - 1) / G;
     if (indexed) {
-        DIGAT_CUDA(cudaFuncSetAttribute(graph_layer_fwd_sparse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
-        graph_layer_fwd_sparse_kernel<true><<<args.B, kSparseThreads, g.smem, st>>>(map1, map3, args, g);
+        DIGAT_CUDA(cudaFuncSetAttribute(graph_layer_fwd_sparse_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+        graph_layer_fwd_sparse_kernel<true, false><<<grid, kSparseThreads, g.smem, st>>>(map1, map3, args, g);
+    } else if (G == 1) {
+        DIGAT_CUDA(cudaFuncSetAttribute(graph_layer_fwd_sparse_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+        graph_layer_fwd_sparse_kernel<false, false><<<grid, kSparseThreads, g.smem, st>>>(map1, map3, args, g);
     } else {
-        DIGAT_CUDA(cudaFuncSetAttribute(graph_layer_fwd_sparse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
-        graph_layer_fwd_sparse_kernel<false><<<args.B, kSparseThreads, g.smem, st>>>(map1, map3, args, g);
+        DIGAT_CUDA(cudaFuncSetAttribute(graph_layer_fwd_sparse_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+        graph_layer_fwd_sparse_kernel<false, true><<<grid, kSparseThreads, g.smem, st>>>(map1, map3, args, g);
     }
     return check_launch("digat_graph_layer_fwd(sparse)");
 }

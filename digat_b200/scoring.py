@@ -141,11 +141,21 @@ class Scorer:
         Consecutive rows with the same clicked-news history have the same user graph / category tensors (they are
         functions of the history, MIND_corpus.py:143-176), so they are detected on the device and encoded through the
         shared-user-graph path (bit-identical results)."""
-        d = lambda x: x.to(self.dev, non_blocking=True)
-        hist = d(user_title_index).to(torch.int32)
-        Au, Mc, ci = d(user_graph), d(user_category_mask), d(user_category_indices)
-        news_i32 = d(news_ID).to(torch.int32)
-        An, Mn = d(news_graph), d(news_graph_mask)
+        return self.score_device_batch(*self.stage_host_batch(user_title_index, user_graph, user_category_mask,
+                                                              user_category_indices, news_ID, news_graph,
+                                                              news_graph_mask), share_user_graphs=share_user_graphs)
+
+    def stage_host_batch(self, *host_tensors):
+        """Host -> device copies of one DataLoader batch on the CURRENT stream (asynchronous for pinned tensors)."""
+        return tuple(x.to(self.dev, non_blocking=True) for x in host_tensors)
+
+    def score_device_batch(self, user_title_index, user_graph, user_category_mask, user_category_indices, news_ID,
+                           news_graph, news_graph_mask, share_user_graphs=True):
+        """score_host_batch after its copies: the same 7 tensors, already on the device."""
+        hist = user_title_index.to(torch.int32)
+        Au, Mc, ci = user_graph, user_category_mask, user_category_indices
+        news_i32 = news_ID.to(torch.int32)
+        An, Mn = news_graph, news_graph_mask
         if not share_user_graphs or hist.shape[0] < 2:
             return self._score(hist, Au, Mc, ci, news_i32, An, Mn)
         first = torch.ones(hist.shape[0], dtype=torch.bool, device=self.dev)
@@ -183,15 +193,53 @@ def host_batch(corpus, pair_ids, pin=False):
     return out
 
 
+def score_host_batches(scorer: Scorer, host_batches, results=None, share_user_graphs=True):
+    """The reference hot loop (util.py:56-69) over an iterable of HOST batches (7-tuples, ideally pinned), pipelined:
+    the copies of batch k+1 run on a side stream while batch k is encoded on the current stream, and the scores of
+    batch k go back to ``results[k]`` (pinned host tensors, optional) asynchronously.  Every batch's host->device copy
+    and device->host read happens inside this call.  Returns the list of device score tensors."""
+    main = torch.cuda.current_stream(scorer.dev)
+    side = getattr(scorer, '_copy_stream', None)
+    if side is None:
+        side = scorer._copy_stream = torch.cuda.Stream(device=scorer.dev)
+
+    def stage(hb):
+        side.wait_stream(main)                       # do not run ahead of work that may still read recycled staging memory
+        with torch.cuda.stream(side):
+            dev_t = scorer.stage_host_batch(*hb)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        for t in dev_t:
+            t.record_stream(main)                    # allocated on the side stream, consumed on the main one
+        return dev_t, ev
+
+    outs = []
+    it = iter(host_batches)
+    nxt = next(it, None)
+    staged = stage(nxt) if nxt is not None else None
+    k = 0
+    while staged is not None:
+        dev_t, ev = staged
+        nxt = next(it, None)
+        staged = stage(nxt) if nxt is not None else None          # copies of batch k+1 overlap the encoding of batch k
+        main.wait_event(ev)
+        scores = scorer.score_device_batch(*dev_t, share_user_graphs=share_user_graphs)
+        if results is not None:
+            results[k].copy_(scores, non_blocking=True)
+        outs.append(scores)
+        k += 1
+    return outs
+
+
 def compute_scores(scorer: Scorer, corpus, batch_size: int, rank: int = 0, world_size: int = 1):
-    """Scores this rank's shard of the ordered pair list through the host-batch path; returns a numpy array."""
+    """Scores this rank's shard of the ordered pair list through the (pipelined) host-batch path; returns a numpy array."""
     lo, hi = shard_range(corpus.pair_behavior.shape[0], rank, world_size)
-    out = torch.empty(hi - lo, device=scorer.dev, dtype=torch.float32)
-    for s in range(lo, hi, batch_size):
-        e = min(s + batch_size, hi)
-        out[s - lo:e - lo] = scorer.score_host_batch(*host_batch(corpus, np.arange(s, e)))
+    batches = (host_batch(corpus, np.arange(s, min(s + batch_size, hi)), pin=True) for s in range(lo, hi, batch_size))
+    outs = score_host_batches(scorer, batches)
     scorer.check_index_errors()
-    return out.cpu().numpy()
+    if not outs:
+        return np.zeros(0, dtype=np.float32)
+    return torch.cat(outs).cpu().numpy()
 
 
 def evaluate_resident(scorer: Scorer, corpus, batch_size: int = 4096, rank: int = 0, world_size: int = 1):

@@ -57,3 +57,27 @@ _lib.call('digat_debug_set_layer_mode', 1)
 Yd = graph_layer_fwd(P, a, adj, X)
 _lib.call('digat_debug_set_layer_mode', 0)
 print('max |sparse - dense| = %.3e' % float((Y0 - Yd).abs().max()))
+
+
+# ---- news graphs (n = 10): dense multi-graph kernel vs edge-driven kernel with several graphs per CTA
+nid = corpus.pair_news[:B].astype(np.int64)
+adj_n = torch.from_numpy(corpus.news_graph[nid]).to(dev)
+nn_ = adj_n.shape[1]
+Xn = torch.randn(B, nn_, D, device=dev, generator=g)
+Pn = torch.randn(B * nn_, 3 * D, device=dev, generator=g)
+res = {}
+for mode, name in ((1, 'dense'), (0, 'edge-driven')):
+    _lib.call('digat_debug_set_layer_mode', mode)
+    Yn = graph_layer_fwd(Pn, a, adj_n, Xn)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(10):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); graph_layer_fwd(Pn, a, adj_n, Xn); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    res[name] = Yn
+    algn = B * (5 * nn_ * D * 4 + nn_ * nn_ + D * 4)
+    print('news n=%d %-12s: %.4f ms  %.0f GB/s algorithmic' % (nn_, name, float(np.median(ts)), algn / float(np.median(ts)) / 1e6))
+_lib.call('digat_debug_set_layer_mode', 0)
+print('news max |sparse - dense| = %.3e' % float((res['dense'] - res['edge-driven']).abs().max()))
