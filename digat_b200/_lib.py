@@ -21,8 +21,9 @@ SIGNATURES = {
     'digat_debug_set_layer_mode': [c_int],
     'digat_graph_layer_fwd': [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                               c_void_p, ctypes.c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
-                              c_int, c_void_p, c_void_p],
+                              c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     'digat_graph_layer_supports_row_active': [c_int, c_int, c_int],
+    'digat_news_active_rows': [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p],
     'digat_user_active_rows': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p],
     'digat_attention_pool_fwd': [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                  c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],

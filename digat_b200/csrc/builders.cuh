@@ -138,6 +138,42 @@ user_active_rows_kernel(const uint8_t* __restrict__ adj, const int32_t* __restri
     }
 }
 
+// The same for news graphs (SAG): node i is observable iff another node attends to it, or the news context reads it:
+// i == 0 (the "local" context, graphEncoders.py:110), mask[g,i] != 0 (pooled by the candidate attention) or every mask
+// entry is 0 (uniform softmax over all nodes).  In SAG data the inactive nodes are the unused BFS slots.
+__global__ void __launch_bounds__(128)
+news_active_rows_kernel(const uint8_t* __restrict__ adj, const uint8_t* __restrict__ mask, uint8_t* __restrict__ active, int n) {
+    __shared__ int col_used[128];
+    __shared__ int any_empty, any_mask;
+    const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint8_t* a = adj + (size_t)g * n * n;
+    if (tid < n) col_used[tid] = 0;
+    if (tid == 0) { any_empty = 0; any_mask = 0; }
+    __syncthreads();
+    if (tid < n && mask[(size_t)g * n + tid] != 0) any_mask = 1;
+    for (int i = warp; i < n; i += 4) {
+        bool row_any = false;
+        for (int j = lane; j < n; j += 32) {
+            const bool on = a[i * n + j] != 0;
+            row_any |= on;
+            if (on && j != i) col_used[j] = 1;
+        }
+        if (!__any_sync(0xffffffffu, row_any) && lane == 0) any_empty = 1;
+    }
+    __syncthreads();
+    if (tid < n)
+        active[(size_t)g * n + tid] = (any_empty || col_used[tid] || tid == 0 || !any_mask || mask[(size_t)g * n + tid] != 0) ? 1 : 0;
+}
+
+inline int launch_news_active_rows(const uint8_t* adj, const uint8_t* mask, uint8_t* active, int64_t G, int n, cudaStream_t st) {
+    if (G <= 0) return DIGAT_OK;
+    DIGAT_REQUIRE(adj && mask && active, "digat_news_active_rows: null pointer");
+    DIGAT_REQUIRE(n >= 1 && n <= 128, "digat_news_active_rows: bad n");
+    DIGAT_REQUIRE(G <= 0x7fffffff, "digat_news_active_rows: too many graphs for one launch");
+    news_active_rows_kernel<<<(unsigned)G, 128, 0, st>>>(adj, mask, active, n);
+    return check_launch("digat_news_active_rows");
+}
+
 inline int launch_user_active_rows(const uint8_t* adj, const int32_t* adj_index, const int64_t* cidx, const uint8_t* cmask,
                                    uint8_t* active, int64_t G, int n, int H, int S, cudaStream_t st) {
     if (G <= 0) return DIGAT_OK;

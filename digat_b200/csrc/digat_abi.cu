@@ -74,9 +74,10 @@ int digat_graph_layer_fwd(const float* P, int ldp, const float* a, const uint8_t
                           int B, int n, int D, const uint8_t* drop_keep, float drop_scale, float* score_out,
                           float* alpha_out, uint8_t* relu_mask_out, const int32_t* px_index, int n_src,
                           const int32_t* adj_index, const float* k3, int ldk3, const uint8_t* row_active,
-                          void* stream) {
+                          float* Yc, const int32_t* row_pos, void* stream) {
     return launch_graph_layer_fwd(P, ldp, a, adj, X, Y, B, n, D, drop_keep, drop_scale, score_out, alpha_out,
-                                  relu_mask_out, px_index, n_src, adj_index, k3, ldk3, row_active, as_stream(stream));
+                                  relu_mask_out, px_index, n_src, adj_index, k3, ldk3, row_active, Yc, row_pos,
+                                  as_stream(stream));
 }
 
 int digat_attention_pool_fwd(const float* F, int64_t strideF, int ldf, const float* resid_F, const float* v,
@@ -211,6 +212,10 @@ int digat_build_user_graphs(const int32_t* hist_cat, const int32_t* hist_len, ui
 int digat_user_active_rows(const uint8_t* adj, const int32_t* adj_index, const int64_t* cidx, const uint8_t* cmask,
                            uint8_t* active, int64_t G, int n, int H, int S, void* stream) {
     return launch_user_active_rows(adj, adj_index, cidx, cmask, active, G, n, H, S, as_stream(stream));
+}
+
+int digat_news_active_rows(const uint8_t* adj, const uint8_t* mask, uint8_t* active, int64_t G, int n, void* stream) {
+    return launch_news_active_rows(adj, mask, active, G, n, as_stream(stream));
 }
 
 int digat_graph_layer_supports_row_active(int n, int D, int B) { return graph_layer_supports_row_active(n, D, B); }

@@ -61,6 +61,9 @@ struct PairAttnArgs {
     // (digat_user_active_rows): its P row was never computed (may hold anything), no edge of it is evaluated and its
     // output row is Y = X.  No active node may have an edge to an inactive one.
     const uint8_t* row_active;
+    // with row_active: Yc [M_act, D] also receives the output rows of the active nodes, row_pos [B*n] = position of node
+    // row r in that compact list -- the next layer's projection GEMM reads Yc directly (no gather pass)
+    float* Yc; const int32_t* row_pos;
 };
 
 __device__ __forceinline__ uint64_t pack2(float lo, float hi) {
@@ -402,8 +405,10 @@ inline int launch_graph_layer_fwd(const float* P, int ldp, const float* a, const
                                   int B, int n, int D, const uint8_t* drop_keep, float drop_scale, float* score_out,
                                   float* alpha_out, uint8_t* relu_mask_out, const int32_t* px_index, int n_src,
                                   const int32_t* adj_index, const float* k3, int ldk3, const uint8_t* row_active,
-                                  cudaStream_t st) {
+                                  float* Yc, const int32_t* row_pos, cudaStream_t st) {
     if (B == 0) return DIGAT_OK;
+    DIGAT_REQUIRE((Yc == nullptr) == (row_pos == nullptr) && (Yc == nullptr || (row_active != nullptr && aligned16(Yc))),
+                  "digat_graph_layer_fwd: Yc, row_pos and row_active go together");
     DIGAT_REQUIRE(P && a && adj && X && Y, "digat_graph_layer_fwd: null pointer");
     DIGAT_REQUIRE(B >= 0 && n >= 1 && n <= kPairMaxNodes, "digat_graph_layer_fwd: n=%d outside [1,%d]", n, kPairMaxNodes);
     DIGAT_REQUIRE(D >= 4 && (D & 3) == 0 && D <= 1024, "digat_graph_layer_fwd: D=%d must be a multiple of 4 in [4,1024]", D);
@@ -425,7 +430,7 @@ inline int launch_graph_layer_fwd(const float* P, int ldp, const float* a, const
     if ((rc = make_tensor_map_2d(&map1, P, src_graphs * n, 3 * D, ldp, g.R * n, g.dc, CU_TENSOR_MAP_SWIZZLE_NONE)) != DIGAT_OK) return rc;
     if ((rc = make_tensor_map_2d(&map3, P, src_graphs * n, 3 * D, ldp, g.R * n, g.dc3, CU_TENSOR_MAP_SWIZZLE_NONE)) != DIGAT_OK) return rc;
     PairAttnArgs args{P, ldp, a, adj, X, Y, B, n, D, drop_keep, drop_scale, score_out, alpha_out, relu_mask_out,
-                      px_index, adj_index, k3, ldk3, row_active};
+                      px_index, adj_index, k3, ldk3, row_active, Yc, row_pos};
     const bool inference = !drop_keep && !score_out && !alpha_out && !relu_mask_out;
     // Inference takes the edge-driven kernel (small graphs are batched several per CTA); the dense kernel stays for
     // training and for graphs whose edge-driven working set does not fit one CTA (n > ~100 at D = 400).

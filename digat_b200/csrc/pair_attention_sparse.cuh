@@ -76,6 +76,7 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
     uint8_t* adj_s = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(meta + NB * n) + 15) & ~(uintptr_t)15);   // [NB*n], 16-byte aligned
     uint8_t* uniform_row = adj_s + ((NB * n + 15) & ~15);          // [NB] 1 = row without edges (uniform softmax)
     uint8_t* dead_row = uniform_row + NB;                          // [NB] 1 = pruned node (row_active == 0): no edges, Y = X
+    int* pos_s = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(dead_row + NB) + 3) & ~(uintptr_t)3);   // [NB] compact row of each node
 
     if (tid == 0) {
         for (int i = 0; i < kSparseBufs; ++i) {
@@ -126,8 +127,10 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
         } else {
             for (int i = tid; i < n2; i += kSparseConsumers) adj_s[i] = adj_g[i];
         }
-        for (int i = tid; i < N; i += kSparseConsumers)
+        for (int i = tid; i < N; i += kSparseConsumers) {
             dead_row[i] = (p.row_active != nullptr && p.row_active[(size_t)b * n + i] == 0) ? 1 : 0;
+            if (p.Yc != nullptr) pos_s[i] = p.row_pos[(size_t)b * n + i];
+        }
     }
     consumer_sync();
 #ifdef DIGAT_TC_TIMING
@@ -364,6 +367,8 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
                 y.z = fmaxf(y.z, 0.f) + x.z;
                 y.w = fmaxf(y.w, 0.f) + x.w;
                 stg_stream(reinterpret_cast<float4*>(p.Y + yoff), y);
+                if (p.Yc != nullptr && dead_row[i] == 0)                    // compact copy for the next layer's projection
+                    *reinterpret_cast<float4*>(p.Yc + (size_t)pos_s[i] * D + c0 + 4 * q) = y;
             }
         }
         __syncwarp();
@@ -383,7 +388,7 @@ inline void sparse_geometry(int n, int D, int G, SparseGeom* g) {
     g->tile_floats = ((NB * kSparseDc1 * 4 + 1023) / 1024) * 1024 / 4;
     g->unit_floats = 2 * g->tile_floats;
     g->smem = (size_t)kSparseBufs * g->unit_floats * 4 + (size_t)2 * kSparseBufs * 8 + (size_t)2 * D * 4 +
-              (size_t)NB * n * 4 + (size_t)(NB + 2) * 4 + (size_t)2 * NB * n + (size_t)((NB * n + 15) & ~15) + (size_t)2 * NB + 48;
+              (size_t)NB * n * 4 + (size_t)(NB + 2) * 4 + (size_t)2 * NB * n + (size_t)((NB * n + 15) & ~15) + (size_t)2 * NB + (size_t)4 * NB + 64;
 }
 
 size_t graph_layer_fwd_sparse_smem(int n, int D) {

@@ -99,7 +99,7 @@ def linear(A, W, bias=None, relu=False, M=None, K=None, lda=None, out=None, grou
 
 
 def graph_layer_fwd(P, a, adj, X, drop_keep=None, drop_scale=1.0, score_out=None, alpha_out=None, relu_mask_out=None,
-                    px_index=None, adj_index=None, k3=None, B=None, row_active=None):
+                    px_index=None, adj_index=None, k3=None, B=None, row_active=None, compact_out=None, row_pos=None):
     """P [B*n, 3D] = h | U | K2 with U = k3 + K1 (row-group bias of the projection GEMM).
     Indexed mode (px_index, k3): P / X are per-behaviour tables shared by B pairs, k3 [B,D] is added in-kernel."""
     n_src, n, D = X.shape
@@ -109,7 +109,7 @@ def graph_layer_fwd(P, a, adj, X, drop_keep=None, drop_scale=1.0, score_out=None
     _lib.call('digat_graph_layer_fwd', P.data_ptr(), P.stride(0), a.data_ptr(), adj.data_ptr(), X.data_ptr(),
               Y.data_ptr(), B, n, D, _ptr(drop_keep), float(drop_scale), _ptr(score_out), _ptr(alpha_out),
               _ptr(relu_mask_out), _ptr(px_index), n_src, _ptr(adj_index), _ptr(k3),
-              0 if k3 is None else k3.stride(0), _ptr(row_active), _stream())
+              0 if k3 is None else k3.stride(0), _ptr(row_active), _ptr(compact_out), _ptr(row_pos), _stream())
     return Y
 
 
@@ -291,31 +291,39 @@ class DIGAT(GraphEncoder):
         Fa = linear(T, w['fa_W'], w['fa_b'])                                      # featureAffine(T)  [B*S, D]
         return attention_pool_fwd(Fa.view(B, S, D), v2, cmask, resid=T, add_in=ctx_in), k3_next
 
-    def _layer(self, w, g, i, X, adj, ctx_other, k3=None, share=None, adj_index=None, prune=None):
+    def _layer(self, w, g, i, X, adj, ctx_other, k3=None, share=None, adj_index=None, prune=None, A_c=None,
+               want_compact=False):
         """k3 [B,D] (possibly a column view): ffn3(context of the other graph) + bias, computed here when None.
         share [B] int32 (layer 0 of the scoring path): X [n_src,n,D] holds one graph per BEHAVIOUR and pair b uses
         graph share[b]; the projection then runs once per behaviour and k3 is added inside the fused kernel.
-        prune = (row_active [B,n] uint8, rows [M_act] int32) from _active_user_rows: only the listed node rows are
-        projected (gathered, multiplied, scattered back into the dense P) and evaluated by the layer kernel."""
+        prune = (row_active [B,n] uint8, rows [M_act] int32, row_pos [B*n] int32) from _active_*_rows: only the listed
+        node rows are projected (compact operand A_c, or gathered here when it is None; scattered back into the dense P)
+        and evaluated by the layer kernel.  want_compact: the layer kernel also writes the compact operand of the NEXT
+        layer.  Returns (Y [B,n,D], Yc [M_act,D] or None)."""
         n, D = X.shape[1], X.shape[2]
         if k3 is None:
             k3 = linear(ctx_other, w[g, i, 'W3'], w[g, i, 'b3'])                  # [B, D]
-        act = None if prune is None else prune[0]
+        act, rows, pos = (None, None, None) if prune is None else prune
+        Yc = None
+        if prune is not None and want_compact:
+            # capacity = every row (M_act changes from batch to batch: a fixed size lets the caching allocator reuse the block)
+            Yc = torch.empty((act.numel(), D), device=X.device, dtype=torch.float32)[:rows.shape[0]]
         if share is not None:
             P = linear(X, w[g, i, 'Wcat'], w[g, i, 'bcat'])                       # h | K1 | K2 per behaviour
             return graph_layer_fwd(P, w[g, i, 'a'], adj, X, px_index=share, adj_index=share, k3=k3, B=k3.shape[0],
-                                   row_active=act)
+                                   row_active=act, compact_out=Yc, row_pos=pos if Yc is not None else None), Yc
         if prune is not None:
-            rows = prune[1]
             M = rows.shape[0]
-            A = torch.empty((M, D), device=X.device, dtype=torch.float32)
-            _lib.call('digat_gather_rows_i32', X.data_ptr(), X.shape[0] * n, rows.data_ptr(), A.data_ptr(), D, M, D,
-                      self._err_flag(X.device).data_ptr(), _stream())
+            if A_c is None:                                                       # first layer: gather the active rows
+                A_c = torch.empty((act.numel(), D), device=X.device, dtype=torch.float32)[:M]
+                _lib.call('digat_gather_rows_i32', X.data_ptr(), X.shape[0] * n, rows.data_ptr(), A_c.data_ptr(), D, M, D,
+                          self._err_flag(X.device).data_ptr(), _stream())
             P = torch.empty((X.shape[0] * n, w[g, i, 'Wcat'].w.shape[0]), device=X.device, dtype=torch.float32)
-            linear(A, w[g, i, 'Wcat'], w[g, i, 'bcat'], out=P, group_bias=k3, group_rows=n, group_col0=D, c_rows=rows)
-            return graph_layer_fwd(P, w[g, i, 'a'], adj, X, adj_index=adj_index, row_active=act)
+            linear(A_c, w[g, i, 'Wcat'], w[g, i, 'bcat'], out=P, group_bias=k3, group_rows=n, group_col0=D, c_rows=rows)
+            return graph_layer_fwd(P, w[g, i, 'a'], adj, X, adj_index=adj_index, row_active=act, compact_out=Yc,
+                                   row_pos=pos if Yc is not None else None), Yc
         P = linear(X, w[g, i, 'Wcat'], w[g, i, 'bcat'], group_bias=k3, group_rows=n, group_col0=D)   # h | k3+K1 | K2
-        return graph_layer_fwd(P, w[g, i, 'a'], adj, X, adj_index=adj_index)
+        return graph_layer_fwd(P, w[g, i, 'a'], adj, X, adj_index=adj_index), None
 
     prune_user_nodes = True      # inference only; switch off to evaluate every node of every user graph
 
@@ -323,7 +331,8 @@ class DIGAT(GraphEncoder):
         """Node pruning of the user graph at inference (digat_user_active_rows): nodes that no other node attends to and
         no context pools -- in MIND-shaped data the padded history slots and the categories a user never clicked, about
         half of the 68 nodes -- cannot influence (news_ctx, user_ctx); their rows are neither projected nor evaluated.
-        Returns (row_active [B,n] uint8, flat row ids int32 [M_act]) or None when unsupported / nothing to prune.
+        Returns (row_active [B,n] uint8, flat row ids int32 [M_act], row_pos int32 [B*n]) or None when unsupported /
+        nothing to prune; row_pos[r] = position of node row r in the compact list (valid where active).
         The nonzero() is a host synchronisation: M_act is a launch parameter of the projection GEMM."""
         B, n = Mc.shape[0], Au.shape[1]
         if not self.prune_user_nodes or B * n < TENSOR_CORE_MIN_ROWS or \
@@ -332,10 +341,26 @@ class DIGAT(GraphEncoder):
         act = torch.empty((B, n), dtype=torch.uint8, device=Au.device)
         _lib.call('digat_user_active_rows', Au.data_ptr(), _ptr(share), ci.data_ptr(), Mc.data_ptr(), act.data_ptr(), B, n,
                   self.max_history_num, self.category_num, _stream())
-        rows = act.view(-1).nonzero().squeeze(1).to(torch.int32)
-        if rows.shape[0] == B * n:
+        return self._row_lists(act)
+
+    @staticmethod
+    def _row_lists(act):
+        flat = act.view(-1)
+        rows = flat.nonzero().squeeze(1).to(torch.int32)
+        if rows.shape[0] == flat.shape[0]:
             return None
-        return act, rows
+        return act, rows, torch.cumsum(flat, 0, dtype=torch.int32) - 1
+
+    def _active_news_rows(self, An, Mn):
+        """The same for the news graph (digat_news_active_rows): the unused BFS slots of a SAG (isolated, masked out of the
+        candidate attention) are not projected."""
+        B, n = Mn.shape
+        if not self.prune_user_nodes or B * n < TENSOR_CORE_MIN_ROWS or \
+           not _lib.load().digat_graph_layer_supports_row_active(n, self.news_embedding_dim, B):
+            return None
+        act = torch.empty((B, n), dtype=torch.uint8, device=An.device)
+        _lib.call('digat_news_active_rows', An.data_ptr(), Mn.data_ptr(), act.data_ptr(), B, n, _stream())
+        return self._row_lists(act)
 
     def _err_flag(self, device):
         f = getattr(self, '_err', None)
@@ -399,13 +424,13 @@ class DIGAT(GraphEncoder):
         w = self._weights()
         with torch.no_grad():
             return self._layer(w, 'news', index, _f32c(news_graph_embeddings, 'news_graph_embeddings'),
-                               _boolc(news_graph, 'news_graph'), _f32c(user_graph_context, 'user_graph_context'))
+                               _boolc(news_graph, 'news_graph'), _f32c(user_graph_context, 'user_graph_context'))[0]
 
     def compute_user_graph_embeddings(self, index, user_graph_embeddings, user_graph, news_graph_context):
         w = self._weights()
         with torch.no_grad():
             return self._layer(w, 'user', index, _f32c(user_graph_embeddings, 'user_graph_embeddings'),
-                               _boolc(user_graph, 'user_graph'), _f32c(news_graph_context, 'news_graph_context'))
+                               _boolc(user_graph, 'user_graph'), _f32c(news_graph_context, 'news_graph_context'))[0]
 
     def _encode(self, w, Xn, An, Mn, Xu, Au, Mc, ci, c_n, share=None):
         """The L-layer dual-graph schedule of graphEncoders.py:180-198 on prebuilt node tensors.
@@ -416,12 +441,15 @@ class DIGAT(GraphEncoder):
             c_n = self._news_ctx(w, Xn, Mn)
         c_u, k3u = self._user_ctx(w, Xu, Mc, ci, c_n, 0, src_index=share)
         prune = self._active_user_rows(Au, Mc, ci, share)
+        prune_n = self._active_news_rows(An, Mn)
         if share is not None:
             ci = ci.index_select(0, share.long())      # [B,H] int64: from layer 1 on every pair owns its user nodes
+        Ac_n = Ac_u = None                               # compact projection operands written by the previous layer
         for i in range(self.graph_depth):
-            Xn_new = self._layer(w, 'news', i, Xn, An, c_u)
-            Xu = self._layer(w, 'user', i, Xu, Au, c_n, k3=k3u, share=share if i == 0 else None,
-                             adj_index=share if i > 0 else None, prune=prune)
+            more = i + 1 < self.graph_depth
+            Xn_new, Ac_n = self._layer(w, 'news', i, Xn, An, c_u, prune=prune_n, A_c=Ac_n, want_compact=more)
+            Xu, Ac_u = self._layer(w, 'user', i, Xu, Au, c_n, k3=k3u, share=share if i == 0 else None,
+                                   adj_index=share if i > 0 else None, prune=prune, A_c=Ac_u, want_compact=more)
             Xn = Xn_new
             c_n = self._news_ctx(w, Xn, Mn, ctx_in=c_n)
             c_u, k3u = self._user_ctx(w, Xu, Mc, ci, c_n, i + 1, ctx_in=c_u)

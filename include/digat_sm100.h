@@ -98,13 +98,15 @@ int digat_debug_set_layer_mode(int mode);
  * Node pruning (may be NULL; edge-driven kernel only, see digat_graph_layer_supports_row_active): row_active [B,n]
  * bool, 0 = node whose output nothing can observe (digat_user_active_rows).  Its P row is never read for arithmetic
  * (it may be uninitialised: digat_linear_tf32x3 with c_row_index skips it), none of its edges is evaluated and its
- * output row is Y = X.  No active node may have an edge to an inactive one.
+ * output row is Y = X.  No active node may have an edge to an inactive one.  With row_active, Yc [M_act, D] and
+ * row_pos [B*n] int32 (both or neither): the output row of active node row r is ALSO written to Yc[row_pos[r]], the
+ * compact operand of the next layer's projection (digat_linear_tf32x3 with c_row_index), saving a gather pass.
  * --------------------------------------------------------------------------------------------------------- */
 int digat_graph_layer_fwd(const float* P, int ldp, const float* a, const uint8_t* adj, const float* X, float* Y,
                           int B, int n, int D, const uint8_t* drop_keep, float drop_scale, float* score_out,
                           float* alpha_out, uint8_t* relu_mask_out, const int32_t* px_index, int n_src,
                           const int32_t* adj_index, const float* k3, int ldk3, const uint8_t* row_active,
-                          void* stream);
+                          float* Yc, const int32_t* row_pos, void* stream);
 /* 1 if an inference call of digat_graph_layer_fwd with these sizes takes the kernel that honours row_active, else 0. */
 int digat_graph_layer_supports_row_active(int n, int D, int B);
 /* Node pruning flags for user graphs: active [G,n] = 0 iff node i's layer output is unobservable: no other node has
@@ -115,6 +117,10 @@ int digat_graph_layer_supports_row_active(int n, int D, int B);
  * [*,H] int64 is read through the same index); cmask [G,S] is per graph. */
 int digat_user_active_rows(const uint8_t* adj, const int32_t* adj_index, const int64_t* cidx, const uint8_t* cmask,
                            uint8_t* active, int64_t G, int n, int H, int S, void* stream);
+/* The same for news graphs: a node is kept iff another node has an edge to it, or the news context reads it
+ * (graphEncoders.py:109-114): node 0 (the local context), mask[g,i] != 0 (pooled by the candidate attention), or every
+ * mask entry of the graph is 0 (uniform softmax).  adj [G,n,n], mask [G,n], active [G,n]. */
+int digat_news_active_rows(const uint8_t* adj, const uint8_t* mask, uint8_t* active, int64_t G, int n, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Masked single-query attention pooling (replaces layers.py:199-206 after folding W_K into the query:

@@ -125,3 +125,28 @@ def test_scorer_identical_with_and_without_pruning():
     scorer.enc.prune_user_nodes = False
     b = scorer.score_resident(beh, news)
     assert torch.equal(a, b) and torch.equal(a2, b)
+
+
+def test_news_active_rows_kernel_matches_rule():
+    from digat_b200 import _lib, synth
+    rng = np.random.Generator(np.random.PCG64(4))
+    cfg = synth.make_config(SAG_neighbors=5, SAG_hops=2, graph_depth=1)
+    node, adj, mask = synth.make_sag(rng, 400, cfg.news_graph_size, 5, 2)
+    n = adj.shape[1]
+    adj[7, 3, :] = False                                  # an edge-less row -> keep everything
+    mask[8, :] = False                                    # every entry masked -> uniform softmax reads every node
+    adj[9, 2, n - 1] = True                               # node 2 attends to the (possibly unused) last slot
+    want = np.zeros((400, n), dtype=np.uint8)
+    for g in range(400):
+        if (~adj[g].any(axis=1)).any() or not mask[g].any():
+            want[g] = 1
+            continue
+        col_used = (adj[g] & ~np.eye(n, dtype=bool)).any(axis=0)
+        want[g] = col_used | mask[g] | (np.arange(n) == 0)
+    dev = torch.device('cuda:0')
+    adj_d, mask_d = torch.from_numpy(adj).to(dev), torch.from_numpy(mask).to(dev)
+    act = torch.empty((400, n), dtype=torch.uint8, device=dev)
+    _lib.call('digat_news_active_rows', adj_d.data_ptr(), mask_d.data_ptr(), act.data_ptr(), 400, n,
+              torch.cuda.current_stream().cuda_stream)
+    assert np.array_equal(act.cpu().numpy(), want)
+    assert want[9, n - 1] == 1 and 0.2 < want.mean() < 0.9
