@@ -29,7 +29,7 @@ SIGNATURES = {
                                  c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     'digat_news_gate_fwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
     'digat_topic_segment_fwd': [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+                                c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     'digat_gather_rows_i32': [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p],
     'digat_gather_sag_i32': [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p],
     'digat_build_user_nodes': [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,

@@ -138,7 +138,7 @@ class TopicSegmentFn(Function):
         T = torch.empty((B, S, D), device=Xu.device, dtype=torch.float32)
         alpha = torch.empty((B, H), device=Xu.device, dtype=torch.float32)
         _lib.call('digat_topic_segment_fwd', Xu.data_ptr(), nu * D, v.data_ptr(), D, cidx.data_ptr(), T.data_ptr(),
-                  alpha.data_ptr(), err_flag.data_ptr(), 0, 0, B, H, S, D, _stream())
+                  alpha.data_ptr(), err_flag.data_ptr(), 0, 0, 0, 0, B, H, S, D, _stream())
         ctx.save_for_backward(Xu, v, cidx, alpha)
         ctx.dims = (H, S)
         return T

@@ -244,6 +244,8 @@ struct SegArgs {
     const int32_t* src_index;             // optional [B]: row b reads Xu and cidx of row src_index[b] (shared user graphs)
     const uint8_t* cmask;                 // optional [B, n_seg]: segments masked out of the user-level attention are not
                                           // evaluated (T = 0) unless every segment of the row is masked
+    float* Tc; const int32_t* seg_pos;    // optional (with cmask): the evaluated segments are ALSO written to the compact
+                                          // list Tc[seg_pos[b*n_seg + k]] -- the operand of the pruned featureAffine GEMM
 };
 
 // One CTA per (user, candidate) row.  The kernel is organised around a compact, segment-sorted list of the LIVE history
@@ -375,8 +377,13 @@ topic_segment_fwd_kernel(SegArgs p) {
         const int q = tid + c * kCtxThreads;
         if (q >= nq) continue;
         float4* Tq = reinterpret_cast<float4*>(p.T + (size_t)b * n_seg * D) + q;
+        auto put = [&](int k, const float4& val) {                                // T[b,k] (+ its compact copy)
+            Tq[(size_t)k * nq] = val;
+            if (p.Tc != nullptr && s_segskip[k] == 0)
+                reinterpret_cast<float4*>(p.Tc + (size_t)p.seg_pos[(size_t)b * n_seg + k] * D)[q] = val;
+        };
         for (int k = 0; k < n_seg; ++k)
-            if (s_start[k + 1] == s_start[k]) Tq[(size_t)k * nq] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (s_start[k + 1] == s_start[k]) put(k, make_float4(0.f, 0.f, 0.f, 0.f));
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         int cur = n_live > 0 ? s_seg[s_order[0]] : 0;
         for (int e0 = 0; e0 < n_live; e0 += kRows) {
@@ -394,7 +401,7 @@ topic_segment_fwd_kernel(SegArgs p) {
             for (int u = 0; u < kRows; ++u) {
                 if (e0 + u < n_live) {                                        // CTA-uniform control flow (shared-memory data only)
                     if (sg[u] != cur) {
-                        Tq[(size_t)cur * nq] = acc;
+                        put(cur, acc);
                         acc = make_float4(0.f, 0.f, 0.f, 0.f);
                         cur = sg[u];
                     }
@@ -404,13 +411,13 @@ topic_segment_fwd_kernel(SegArgs p) {
                 }
             }
         }
-        if (n_live > 0) Tq[(size_t)cur * nq] = acc;
+        if (n_live > 0) put(cur, acc);
     }
 }
 
 inline int launch_topic_segment_fwd(const float* Xu, int64_t strideX, const float* v, int ldv, const int64_t* cidx, float* T,
                                     float* alpha_out, int32_t* err_flag, const int32_t* src_index, const uint8_t* cmask,
-                                    int B, int H, int n_seg, int D, cudaStream_t st) {
+                                    float* Tc, const int32_t* seg_pos, int B, int H, int n_seg, int D, cudaStream_t st) {
     if (B <= 0) return DIGAT_OK;
     DIGAT_REQUIRE(Xu && v && cidx && T, "digat_topic_segment_fwd: null pointer");
     DIGAT_REQUIRE(H >= 1 && H <= kCtxMaxItems && n_seg >= 1 && n_seg <= kCtxMaxItems,
@@ -420,7 +427,9 @@ inline int launch_topic_segment_fwd(const float* Xu, int64_t strideX, const floa
                   "digat_topic_segment_fwd: pointers/strides must be 16-byte aligned");
     if (B <= 0) return DIGAT_OK;
     DIGAT_REQUIRE((ldv & 3) == 0 && ldv >= D, "digat_topic_segment_fwd: ldv must be a multiple of 4 and >= D");
-    SegArgs a{Xu, strideX, v, ldv, cidx, T, alpha_out, B, H, n_seg, D, err_flag, src_index, cmask};
+    DIGAT_REQUIRE((Tc == nullptr) == (seg_pos == nullptr) && (Tc == nullptr || (cmask != nullptr && aligned16(Tc))),
+                  "digat_topic_segment_fwd: Tc, seg_pos and cmask go together");
+    SegArgs a{Xu, strideX, v, ldv, cidx, T, alpha_out, B, H, n_seg, D, err_flag, src_index, cmask, Tc, seg_pos};
     topic_segment_fwd_kernel<<<B, kCtxThreads, 0, st>>>(a);
     return check_launch("digat_topic_segment_fwd");
 }

@@ -94,9 +94,9 @@ int digat_news_gate_fwd(const float* z, const float* lg, const float* ctx_in, fl
 
 int digat_topic_segment_fwd(const float* Xu, int64_t strideX, const float* v, int ldv, const int64_t* cidx, float* T,
                             float* alpha_out, int32_t* err_flag, const int32_t* src_index, const uint8_t* cmask,
-                            int B, int H, int n_seg, int D, void* stream) {
-    return launch_topic_segment_fwd(Xu, strideX, v, ldv, cidx, T, alpha_out, err_flag, src_index, cmask, B, H, n_seg, D,
-                                    as_stream(stream));
+                            float* Tc, const int32_t* seg_pos, int B, int H, int n_seg, int D, void* stream) {
+    return launch_topic_segment_fwd(Xu, strideX, v, ldv, cidx, T, alpha_out, err_flag, src_index, cmask, Tc, seg_pos,
+                                    B, H, n_seg, D, as_stream(stream));
 }
 
 int digat_gather_rows_i32(const float* table, int64_t n_table, const int32_t* idx, float* out, int64_t ldo,

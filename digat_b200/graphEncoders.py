@@ -275,9 +275,11 @@ class DIGAT(GraphEncoder):
         _lib.call('digat_news_gate_fwd', z.data_ptr(), lg.data_ptr(), _ptr(ctx_in), out.data_ptr(), B, D, _stream())
         return out
 
-    def _user_ctx(self, w, Xu, cmask, cidx, c_n, j, ctx_in=None, src_index=None):
+    def _user_ctx(self, w, Xu, cmask, cidx, c_n, j, ctx_in=None, src_index=None, seg_prune=None):
         """j = index of this call (0 = initial context, i+1 = after layer i).  Returns (context, k3 of user layer j or
-        None).  src_index [B] int32: Xu / cidx are per-behaviour tables and row b uses entry src_index[b]."""
+        None).  src_index [B] int32: Xu / cidx are per-behaviour tables and row b uses entry src_index[b].
+        seg_prune = (rows [M_live] int32, pos [B*S] int32) from _live_segments: featureAffine runs on the topic
+        embeddings the user-level attention can see only (the segment kernel writes them compactly)."""
         nu, D = Xu.shape[1], Xu.shape[2]
         B = c_n.shape[0]
         H, S = self.max_history_num, self.category_num
@@ -285,11 +287,31 @@ class DIGAT(GraphEncoder):
         v1, v2 = vv[:, :D], vv[:, D:2 * D]
         k3_next = vv[:, 2 * D:] if vv.shape[1] > 2 * D else None
         T = torch.empty((B, S, D), device=Xu.device, dtype=torch.float32)
+        Tc = pos = None
+        if seg_prune is not None:
+            rows, pos = seg_prune
+            Tc = torch.empty((B * S, D), device=Xu.device, dtype=torch.float32)[:rows.shape[0]]
         _lib.call('digat_topic_segment_fwd', Xu.data_ptr(), nu * D, v1.data_ptr(), vv.stride(0), cidx.data_ptr(),
                   T.data_ptr(), 0, self._err_flag(Xu.device).data_ptr(), _ptr(src_index),
-                  cmask.data_ptr() if self.prune_user_nodes else 0, B, H, S, D, _stream())
-        Fa = linear(T, w['fa_W'], w['fa_b'])                                      # featureAffine(T)  [B*S, D]
+                  cmask.data_ptr() if self.prune_user_nodes else 0, _ptr(Tc), _ptr(pos), B, H, S, D, _stream())
+        if seg_prune is not None:                                                 # featureAffine on the visible topics only
+            Fa = torch.empty((B * S, D), device=Xu.device, dtype=torch.float32)
+            linear(Tc, w['fa_W'], w['fa_b'], out=Fa, c_rows=rows)                 # (the pooling never reads the other rows)
+        else:
+            Fa = linear(T, w['fa_W'], w['fa_b'])                                  # featureAffine(T)  [B*S, D]
         return attention_pool_fwd(Fa.view(B, S, D), v2, cmask, resid=T, add_in=ctx_in), k3_next
+
+    def _live_segments(self, Mc):
+        """Topic embeddings the user-level attention can see: cmask != 0, or every segment of a fully masked row (uniform
+        softmax).  Returns (flat ids int32 [M_live], pos int32 [B*S]) or None (small batch / pruning off / nothing to skip)."""
+        B, S = Mc.shape
+        if not self.prune_user_nodes or B * S < TENSOR_CORE_MIN_ROWS:
+            return None
+        live = (Mc | ~Mc.any(dim=1, keepdim=True)).view(-1)
+        rows = live.nonzero().squeeze(1).to(torch.int32)
+        if rows.shape[0] == B * S:
+            return None
+        return rows, torch.cumsum(live, 0, dtype=torch.int32) - 1
 
     def _layer(self, w, g, i, X, adj, ctx_other, k3=None, share=None, adj_index=None, prune=None, A_c=None,
                want_compact=False):
@@ -432,16 +454,22 @@ class DIGAT(GraphEncoder):
             return self._layer(w, 'user', index, _f32c(user_graph_embeddings, 'user_graph_embeddings'),
                                _boolc(user_graph, 'user_graph'), _f32c(news_graph_context, 'news_graph_context'))[0]
 
-    def _encode(self, w, Xn, An, Mn, Xu, Au, Mc, ci, c_n, share=None):
+    def _encode(self, w, Xn, An, Mn, Xu, Au, Mc, ci, c_n, share=None, lists=None):
         """The L-layer dual-graph schedule of graphEncoders.py:180-198 on prebuilt node tensors.
         Xu [B, H+C, D] already holds [history ; topic nodes]; c_n None = compute the initial news context.
         share [B] int32 (scoring path): Xu / Au / ci are per-BEHAVIOUR tables and pair b uses entry share[b]; the
-        user graph's layer-0 projection and node build then run once per behaviour (results are bit-identical)."""
+        user graph's layer-0 projection and node build then run once per behaviour (results are bit-identical).
+        lists = (prune, prune_n, seg_prune) when the caller prepared the pruning lists already (scoring.Scorer does, on a
+        side stream); otherwise they are computed here (three nonzero() host synchronisations)."""
         if c_n is None:
             c_n = self._news_ctx(w, Xn, Mn)
-        c_u, k3u = self._user_ctx(w, Xu, Mc, ci, c_n, 0, src_index=share)
-        prune = self._active_user_rows(Au, Mc, ci, share)
-        prune_n = self._active_news_rows(An, Mn)
+        if lists is not None:
+            prune, prune_n, seg_prune = lists
+        else:
+            seg_prune = self._live_segments(Mc)
+            prune = self._active_user_rows(Au, Mc, ci, share)
+            prune_n = self._active_news_rows(An, Mn)
+        c_u, k3u = self._user_ctx(w, Xu, Mc, ci, c_n, 0, src_index=share, seg_prune=seg_prune)
         if share is not None:
             ci = ci.index_select(0, share.long())      # [B,H] int64: from layer 1 on every pair owns its user nodes
         Ac_n = Ac_u = None                               # compact projection operands written by the previous layer
@@ -452,7 +480,7 @@ class DIGAT(GraphEncoder):
                                    adj_index=share if i > 0 else None, prune=prune, A_c=Ac_u, want_compact=more)
             Xn = Xn_new
             c_n = self._news_ctx(w, Xn, Mn, ctx_in=c_n)
-            c_u, k3u = self._user_ctx(w, Xu, Mc, ci, c_n, i + 1, ctx_in=c_u)
+            c_u, k3u = self._user_ctx(w, Xu, Mc, ci, c_n, i + 1, ctx_in=c_u, seg_prune=seg_prune)
         return c_n, c_u
 
     def inference(self, news_graph_embeddings, news_graph, news_graph_mask, user_news_embedding, user_graph,

@@ -94,15 +94,67 @@ class Scorer:
         self.c_n0 = c
         return c
 
-    def _score(self, hist_idx, Au, Mc, ci, news_idx, An, Mn):
+    # ------------------------------------------------------------------------------------------------------------
+    # A batch is scored in two steps.  prepare_* does everything that needs the HOST to look at device data (the
+    # impression boundaries and the pruning lists are nonzero() calls, i.e. stream synchronisations) and depends on the
+    # batch's integer/bool inputs only; score_prepared then launches the encoder without a single synchronisation.
+    # score_host_batches runs prepare for batch k+1 on a side stream while batch k is encoded.
+    def _prune_lists(self, prep):
+        enc = self.enc
+        with torch.no_grad():
+            prep['seg_prune'] = enc._live_segments(prep['Mc'])
+            prep['prune'] = enc._active_user_rows(prep['Au'], prep['Mc'], prep['ci'], prep['share'])
+            prep['prune_n'] = enc._active_news_rows(prep['An'], prep['Mn'])
+        return prep
+
+    def prepare_resident(self, beh_idx, news_idx, share_user_graphs=True):
+        """beh_idx, news_idx: [B] device tensors (any integer dtype).  Everything else is already in HBM."""
+        nl, bl = news_idx.long(), beh_idx.long()
+        prep = dict(news=news_idx.to(torch.int32), An=self.news_graph.index_select(0, nl),
+                    Mn=self.news_mask.index_select(0, nl), share=None)
+        if share_user_graphs and bl.shape[0] >= 2:
+            ub, inv = torch.unique_consecutive(bl, return_inverse=True)
+            prep['share'] = inv.to(torch.int32)
+            prep['Mc'] = self.cmask.index_select(0, bl)                  # masks stay per pair
+            bl = ub                                                      # node tables, graphs, segment ids: per behaviour
+        else:
+            prep['Mc'] = self.cmask.index_select(0, bl)
+        prep.update(hist=self.history.index_select(0, bl), Au=self.user_graph.index_select(0, bl),
+                    ci=self.cidx.index_select(0, bl))
+        return self._prune_lists(prep)
+
+    def prepare_device_batch(self, user_title_index, user_graph, user_category_mask, user_category_indices, news_ID,
+                             news_graph, news_graph_mask, share_user_graphs=True):
+        """The 7 tensors of one reference DataLoader batch (util.py:56), already on the device.
+
+        The DataLoader repeats the user tensors for every candidate of an impression (MIND_dataset.py:97-102).
+        Consecutive rows with the same clicked-news history have the same user graph / category tensors (they are
+        functions of the history, MIND_corpus.py:143-176), so they are detected here and encoded through the
+        shared-user-graph path (bit-identical results)."""
+        hist = user_title_index.to(torch.int32)
+        prep = dict(news=news_ID.to(torch.int32), An=news_graph, Mn=news_graph_mask, Mc=user_category_mask, share=None,
+                    hist=hist, Au=user_graph, ci=user_category_indices)
+        if share_user_graphs and hist.shape[0] >= 2:
+            first = torch.ones(hist.shape[0], dtype=torch.bool, device=hist.device)
+            first[1:] = (hist[1:] != hist[:-1]).any(dim=1)
+            prep['share'] = (torch.cumsum(first, 0) - 1).to(torch.int32)
+            rows = first.nonzero(as_tuple=True)[0]
+            prep.update(hist=hist.index_select(0, rows), Au=user_graph.index_select(0, rows),
+                        ci=user_category_indices.index_select(0, rows))
+        return self._prune_lists(prep)
+
+    def score_prepared(self, prep):
+        """Gathers + encoder + logits of a prepared batch: kernel launches only, no host synchronisation."""
         w = self.enc._weights()
         if self.c_n0 is None:
             self.cache_news_context()
         with torch.no_grad():
-            Xn = self.gather_sag(news_idx)
-            Xu = self.user_nodes(hist_idx)
-            c0 = self.gather_rows(self.c_n0, news_idx)
-            cn, cu = self.enc._encode(w, Xn, An, Mn, Xu, Au, Mc, ci, c0)
+            Xn = self.gather_sag(prep['news'])
+            Xu = self.user_nodes(prep['hist'])                           # one node tensor per behaviour when shared
+            c0 = self.gather_rows(self.c_n0, prep['news'])
+            cn, cu = self.enc._encode(w, Xn, prep['An'], prep['Mn'], Xu, prep['Au'], prep['Mc'], prep['ci'], c0,
+                                      share=prep['share'],
+                                      lists=(prep['prune'], prep['prune_n'], prep['seg_prune']))
             return logits(cn, cu)
 
     def score_resident(self, beh_idx, news_idx, share_user_graphs=True):
@@ -112,35 +164,11 @@ class Scorer:
         (MIND_corpus.py:295-297) and share the user graph.  Its node build, its layer-0 projection GEMM and its
         adjacency are then computed / read once per distinct behaviour and indexed per pair (bit-identical results:
         the same rows go through the same kernels; tests/test_gpu_scoring.py)."""
-        nl = news_idx.long()
-        news_i32 = news_idx.to(torch.int32)
-        An, Mn = self.news_graph.index_select(0, nl), self.news_mask.index_select(0, nl)
-        if not share_user_graphs:
-            b = beh_idx.long()
-            return self._score(self.history.index_select(0, b), self.user_graph.index_select(0, b),
-                               self.cmask.index_select(0, b), self.cidx.index_select(0, b), news_i32, An, Mn)
-        ub, inv = torch.unique_consecutive(beh_idx.long(), return_inverse=True)
-        share = inv.to(torch.int32)
-        w = self.enc._weights()
-        if self.c_n0 is None:
-            self.cache_news_context()
-        with torch.no_grad():
-            Xn = self.gather_sag(news_i32)
-            Xu_b = self.user_nodes(self.history.index_select(0, ub))             # one node tensor per behaviour
-            c0 = self.gather_rows(self.c_n0, news_i32)
-            cn, cu = self.enc._encode(w, Xn, An, Mn, Xu_b, self.user_graph.index_select(0, ub),
-                                      self.cmask.index_select(0, beh_idx.long()), self.cidx.index_select(0, ub), c0,
-                                      share=share)
-            return logits(cn, cu)
+        return self.score_prepared(self.prepare_resident(beh_idx, news_idx, share_user_graphs))
 
     def score_host_batch(self, user_title_index, user_graph, user_category_mask, user_category_indices, news_ID,
                          news_graph, news_graph_mask, share_user_graphs=True):
-        """The reference hot loop body (util.py:56-68) on HOST tensors (pinned for async copies).
-
-        The DataLoader repeats the user tensors for every candidate of an impression (MIND_dataset.py:97-102).
-        Consecutive rows with the same clicked-news history have the same user graph / category tensors (they are
-        functions of the history, MIND_corpus.py:143-176), so they are detected on the device and encoded through the
-        shared-user-graph path (bit-identical results)."""
+        """The reference hot loop body (util.py:56-68) on HOST tensors (pinned for async copies)."""
         return self.score_device_batch(*self.stage_host_batch(user_title_index, user_graph, user_category_mask,
                                                               user_category_indices, news_ID, news_graph,
                                                               news_graph_mask), share_user_graphs=share_user_graphs)
@@ -149,29 +177,9 @@ class Scorer:
         """Host -> device copies of one DataLoader batch on the CURRENT stream (asynchronous for pinned tensors)."""
         return tuple(x.to(self.dev, non_blocking=True) for x in host_tensors)
 
-    def score_device_batch(self, user_title_index, user_graph, user_category_mask, user_category_indices, news_ID,
-                           news_graph, news_graph_mask, share_user_graphs=True):
+    def score_device_batch(self, *device_tensors, share_user_graphs=True):
         """score_host_batch after its copies: the same 7 tensors, already on the device."""
-        hist = user_title_index.to(torch.int32)
-        Au, Mc, ci = user_graph, user_category_mask, user_category_indices
-        news_i32 = news_ID.to(torch.int32)
-        An, Mn = news_graph, news_graph_mask
-        if not share_user_graphs or hist.shape[0] < 2:
-            return self._score(hist, Au, Mc, ci, news_i32, An, Mn)
-        first = torch.ones(hist.shape[0], dtype=torch.bool, device=self.dev)
-        first[1:] = (hist[1:] != hist[:-1]).any(dim=1)
-        share = (torch.cumsum(first, 0) - 1).to(torch.int32)
-        rows = first.nonzero(as_tuple=True)[0]
-        w = self.enc._weights()
-        if self.c_n0 is None:
-            self.cache_news_context()
-        with torch.no_grad():
-            Xn = self.gather_sag(news_i32)
-            Xu_b = self.user_nodes(hist.index_select(0, rows))
-            c0 = self.gather_rows(self.c_n0, news_i32)
-            cn, cu = self.enc._encode(w, Xn, An, Mn, Xu_b, Au.index_select(0, rows), Mc, ci.index_select(0, rows), c0,
-                                      share=share)
-            return logits(cn, cu)
+        return self.score_prepared(self.prepare_device_batch(*device_tensors, share_user_graphs=share_user_graphs))
 
     def check_index_errors(self):
         if int(self.err.item()) != 0:
@@ -193,42 +201,68 @@ def host_batch(corpus, pair_ids, pin=False):
     return out
 
 
-def score_host_batches(scorer: Scorer, host_batches, results=None, share_user_graphs=True):
-    """The reference hot loop (util.py:56-69) over an iterable of HOST batches (7-tuples, ideally pinned), pipelined:
-    the copies of batch k+1 run on a side stream while batch k is encoded on the current stream, and the scores of
-    batch k go back to ``results[k]`` (pinned host tensors, optional) asynchronously.  Every batch's host->device copy
-    and device->host read happens inside this call.  Returns the list of device score tensors."""
+def _tensors_of(obj):
+    if torch.is_tensor(obj):
+        yield obj
+    elif isinstance(obj, dict):
+        for v in obj.values():
+            yield from _tensors_of(v)
+    elif isinstance(obj, (tuple, list)):
+        for v in obj:
+            yield from _tensors_of(v)
+
+
+def _pipelined(scorer: Scorer, items, prepare, results):
+    """Runs ``prepare(item)`` for item k+1 on a side stream (copies, index work and their host synchronisations) while
+    item k is encoded on the current stream."""
     main = torch.cuda.current_stream(scorer.dev)
     side = getattr(scorer, '_copy_stream', None)
     if side is None:
         side = scorer._copy_stream = torch.cuda.Stream(device=scorer.dev)
 
-    def stage(hb):
-        side.wait_stream(main)                       # do not run ahead of work that may still read recycled staging memory
+    def stage(item):
+        # No wait on the main stream here: staging depends on the batch's own inputs only, and its tensors are handed to
+        # the main stream with record_stream (the caching allocator recycles them only after the main stream is done).
         with torch.cuda.stream(side):
-            dev_t = scorer.stage_host_batch(*hb)
+            prep = prepare(item)
             ev = torch.cuda.Event()
             ev.record(side)
-        for t in dev_t:
+        for t in _tensors_of(prep):
             t.record_stream(main)                    # allocated on the side stream, consumed on the main one
-        return dev_t, ev
+        return prep, ev
 
     outs = []
-    it = iter(host_batches)
+    it = iter(items)
     nxt = next(it, None)
     staged = stage(nxt) if nxt is not None else None
     k = 0
     while staged is not None:
-        dev_t, ev = staged
-        nxt = next(it, None)
-        staged = stage(nxt) if nxt is not None else None          # copies of batch k+1 overlap the encoding of batch k
+        prep, ev = staged
         main.wait_event(ev)
-        scores = scorer.score_device_batch(*dev_t, share_user_graphs=share_user_graphs)
+        scores = scorer.score_prepared(prep)                      # launches only: returns long before the GPU is done
         if results is not None:
             results[k].copy_(scores, non_blocking=True)
         outs.append(scores)
+        nxt = next(it, None)
+        staged = stage(nxt) if nxt is not None else None          # batch k+1 is staged while batch k runs
         k += 1
     return outs
+
+
+def score_host_batches(scorer: Scorer, host_batches, results=None, share_user_graphs=True):
+    """The reference hot loop (util.py:56-69) over an iterable of HOST batches (7-tuples, ideally pinned), pipelined:
+    the copies and the index preparation of batch k+1 run on a side stream while batch k is encoded on the current
+    stream, and the scores of batch k go back to ``results[k]`` (pinned host tensors, optional) asynchronously.  Every
+    batch's host->device copy and device->host read happens inside this call.  Returns the device score tensors."""
+    return _pipelined(scorer, host_batches,
+                      lambda hb: scorer.prepare_device_batch(*scorer.stage_host_batch(*hb),
+                                                             share_user_graphs=share_user_graphs), results)
+
+
+def score_resident_batches(scorer: Scorer, index_batches, results=None, share_user_graphs=True):
+    """The same pipeline for the resident path: ``index_batches`` yields (behaviour index, news id) device tensors."""
+    return _pipelined(scorer, index_batches,
+                      lambda ib: scorer.prepare_resident(ib[0], ib[1], share_user_graphs=share_user_graphs), results)
 
 
 def compute_scores(scorer: Scorer, corpus, batch_size: int, rank: int = 0, world_size: int = 1):

@@ -153,10 +153,13 @@ int digat_news_gate_fwd(const float* z, const float* lg, const float* ctx_in, fl
  * row src_index[b] (user graphs shared by the pairs of one impression).
  * cmask [B,n_seg] bool optional (inference): the mask the user-level attention applies to T afterwards
  * (graphEncoders.py:132).  Segments with cmask == 0 get a softmax weight of exactly 0 there, so their history rows are
- * not read and T[b,k] = 0 -- unless every segment of row b is masked (uniform weights: everything is evaluated). */
+ * not read and T[b,k] = 0 -- unless every segment of row b is masked (uniform weights: everything is evaluated).
+ * Tc [M_live, D] + seg_pos [B*n_seg] int32 optional (with cmask): the evaluated segments (cmask != 0, or all of a
+ * fully masked row) are also written to Tc[seg_pos[b*n_seg + k]], the compact operand of the featureAffine GEMM. */
 int digat_topic_segment_fwd(const float* Xu, int64_t strideX, const float* v, int ldv, const int64_t* cidx,
                             float* T, float* alpha_out, int32_t* err_flag, const int32_t* src_index,
-                            const uint8_t* cmask, int B, int H, int n_seg, int D, void* stream);
+                            const uint8_t* cmask, float* Tc, const int32_t* seg_pos,
+                            int B, int H, int n_seg, int D, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Gathers (replace index_select at util.py:34-36 and util.py:65-67) and small glue.

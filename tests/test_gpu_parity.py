@@ -160,7 +160,7 @@ def test_topic_segments_bit_exact_membership():
     alpha = torch.empty(B, H, device=dev)
     err = torch.zeros(1, dtype=torch.int32, device=dev)
     _lib.call('digat_topic_segment_fwd', Xu.data_ptr(), (H + 18) * D, v.data_ptr(), D, cidx.to(dev).data_ptr(), T.data_ptr(),
-              alpha.data_ptr(), err.data_ptr(), 0, 0, B, H, S, D, torch.cuda.current_stream().cuda_stream)
+              alpha.data_ptr(), err.data_ptr(), 0, 0, 0, 0, B, H, S, D, torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     assert int(err.item()) == 0
     a = alpha.cpu()
@@ -181,7 +181,7 @@ def test_topic_segments_bit_exact_membership():
     # out-of-range segment id -> flagged
     bad = cidx.clone(); bad[2, 7] = 99
     _lib.call('digat_topic_segment_fwd', Xu.data_ptr(), (H + 18) * D, v.data_ptr(), D, bad.to(dev).data_ptr(), T.data_ptr(),
-              0, err.data_ptr(), 0, 0, B, H, S, D, torch.cuda.current_stream().cuda_stream)
+              0, err.data_ptr(), 0, 0, 0, 0, B, H, S, D, torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     assert int(err.item()) == 1
 
