@@ -59,7 +59,7 @@ struct PairAttnArgs {
     const float* k3; int ldk3;  // [B,ldk3] added to the staged U tile in-kernel: U = fl(K1 + k3), same rounding as the GEMM path
     // node pruning (edge-driven kernel only, optional): row_active [B,n] 0 = node whose output cannot reach any context
     // (digat_user_active_rows): its P row was never computed (may hold anything), no edge of it is evaluated and its
-    // output row is Y = X.  No active node may have an edge to an inactive one.
+    // output row is NOT written (nothing may read it).  No active node may have an edge to an inactive one.
     const uint8_t* row_active;
     // with row_active: Yc [M_act, D] also receives the output rows of the active nodes, row_pos [B*n] = position of node
     // row r in that compact list -- the next layer's projection GEMM reads Yc directly (no gather pass)

@@ -301,7 +301,7 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
     auto load_x = [&](int unit, int slot) {
         const int c0_ = unit * kSparseDc3;
         const int i_ = 2 * (warp + slot * kRowPairStep) + sub;
-        return (unit < g.nch3 && i_ < N && c0_ + 4 * half_lane < D)
+        return (unit < g.nch3 && i_ < N && dead_row[min(i_, N - 1)] == 0 && c0_ + 4 * half_lane < D)
                    ? ldg_stream(reinterpret_cast<const float4*>(p.X + ((size_t)src0 * n + i_) * D + c0_ + 4 * half_lane))
                    : make_float4(0.f, 0.f, 0.f, 0.f);
     };
@@ -327,7 +327,7 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
             const int rp = warp + sl * kRowPairStep;
             if (2 * rp >= N) break;
             const int i = 2 * rp + sub;
-            if (i < N && half_lane < wq) {
+            if (i < N && half_lane < wq && dead_row[i] == 0) {          // pruned rows are neither read nor written
                 const int q = half_lane;
                 const size_t yoff = ((size_t)b * n + i) * D + c0 + 4 * q;
                 float4 x;
@@ -367,7 +367,7 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
                 y.z = fmaxf(y.z, 0.f) + x.z;
                 y.w = fmaxf(y.w, 0.f) + x.w;
                 stg_stream(reinterpret_cast<float4*>(p.Y + yoff), y);
-                if (p.Yc != nullptr && dead_row[i] == 0)                    // compact copy for the next layer's projection
+                if (p.Yc != nullptr)                                        // compact copy for the next layer's projection
                     *reinterpret_cast<float4*>(p.Yc + (size_t)pos_s[i] * D + c0 + 4 * q) = y;
             }
         }

@@ -98,7 +98,9 @@ int digat_debug_set_layer_mode(int mode);
  * Node pruning (may be NULL; edge-driven kernel only, see digat_graph_layer_supports_row_active): row_active [B,n]
  * bool, 0 = node whose output nothing can observe (digat_user_active_rows).  Its P row is never read for arithmetic
  * (it may be uninitialised: digat_linear_tf32x3 with c_row_index skips it), none of its edges is evaluated and its
- * output row is Y = X.  No active node may have an edge to an inactive one.  With row_active, Yc [M_act, D] and
+ * output row is left untouched (neither X nor Y of that row is accessed; every later consumer -- the next layer with
+ * the same flags, the pooling kernels with their masks -- skips it too).  No active node may have an edge to an
+ * inactive one.  With row_active, Yc [M_act, D] and
  * row_pos [B*n] int32 (both or neither): the output row of active node row r is ALSO written to Yc[row_pos[r]], the
  * compact operand of the next layer's projection (digat_linear_tf32x3 with c_row_index), saving a gather pass.
  * --------------------------------------------------------------------------------------------------------- */
