@@ -7,7 +7,8 @@
 A step = one pass of the hot path over one batch of `--batch` (user behaviour, candidate news) pairs of the
 synthetic MIND-small-dev-sized corpus (BASELINE.json configs[1]).
   value : pairs/s with the corpus resident in HBM (pair = (behaviour index, news id); gathers + encoder + logits)
-  e2e   : pairs/s through Scorer.score_host_batch with HOST (pinned) per-pair tensors, H2D + D2H inside the timing
+  e2e   : pairs/s through scoring.score_host_batches with HOST (pinned) per-pair tensors, H2D + D2H inside the timing
+          (both drivers stage batch k+1 on a side stream while batch k is encoded)
 One JSON line on stdout (rank 0).
 """
 import argparse
