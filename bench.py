@@ -135,6 +135,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--cpu-budget', type=float, default=12.0, help='seconds of CPU-oracle timing for cpu_baseline')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--eager-train', action='store_true',
+                    help='train mode: run the step eagerly instead of replaying it as one CUDA graph')
     ap.add_argument('--mode', default='score', choices=['score', 'train'],
                     help="'score' = the headline metric; 'train' = fwd+bwd(+DDP all-reduce)+Adam step, samples/s")
     args = ap.parse_args()
@@ -316,7 +318,8 @@ def run_train(args):
     model.graph_encoder.load_state_dict(sd)
     model = model.to(dev).train()
     net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank]) if world > 1 else model
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    graphed = world == 1 and not args.eager_train      # whole-step CUDA graph (digat_b200/training.py); DDP runs eagerly
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=graphed)
     bs, news_num = 64, 5
     rng = np.random.Generator(np.random.PCG64(rank))
     emb = torch.from_numpy(corpus.news_embeddings).to(dev)
@@ -360,6 +363,11 @@ def run_train(args):
             return loss
 
     inputs = [make_step_inputs() for _ in range(args.warmup + args.steps)]
+    if graphed:
+        from digat_b200.training import GraphedTrainStep
+        eager_step = step
+        gstep = GraphedTrainStep(lambda *a: eager_step(a), inputs[0])
+        step = lambda inp: gstep(*inp)                      # noqa: E731
     for s_ in range(args.warmup):
         step(inputs[s_])
     if world > 1:
@@ -386,6 +394,7 @@ def run_train(args):
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': args.workload + ':train', 'behaviours_per_gpu': bs, 'candidates': news_num,
                        'rows_per_gpu': bs * news_num, 'dropout': 0.2, 'optimizer': 'Adam + clip_grad_norm 1',
+                       'execution': 'whole step replayed as one CUDA graph' if graphed else 'eager',
                        'parallelism': 'DDP x%d, NCCL gradient all-reduce' % world},
             'gpu_launches': _lib.launch_count(), 'final_loss': float(loss)}))
     if world > 1:

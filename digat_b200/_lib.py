@@ -17,6 +17,8 @@ SIGNATURES = {
     'digat_split_tf32': [c_void_p, c_void_p, c_void_p, c_int64, c_void_p],
     'digat_linear_tf32x3': [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                             c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    'digat_linear_tf32x3_splitk': [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                   c_int64, c_void_p],
     'digat_debug_set_gemm_variant': [c_int],
     'digat_debug_set_layer_mode': [c_int],
     'digat_graph_layer_fwd': [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,

@@ -31,6 +31,34 @@ def colsum(x2d):
     return out
 
 
+WGRAD_TC_MIN_ROWS = 256      # contraction lengths below this keep the exact-fp32 CUDA-core wgrad kernel
+WGRAD_SLICE = 512            # rows per split-K slice: 64 truncating accumulate steps per accumulator
+
+
+def wgrad(dC, A):
+    """dW[N,K] = dC[M,N]^T A[M,K].  Long contractions run on the tensor cores: both operands are transposed so that the
+    contraction index is contiguous (K-major), A^T is split into its TF32 planes, digat_linear_tf32x3_splitk writes one
+    partial product per slice of WGRAD_SLICE rows and digat_colsum adds the slabs in slice order (deterministic)."""
+    M, K = A.shape
+    N = dC.shape[1]
+    dW = torch.empty((N, K), device=A.device, dtype=torch.float32)
+    if M < WGRAD_TC_MIN_ROWS or (M & 3) != 0 or K > 1280 or (K & 15) != 0:
+        ws = _workspace(M, N, K, A.device)
+        _lib.call('digat_linear_wgrad', dC.data_ptr(), dC.stride(0), A.data_ptr(), A.stride(0), dW.data_ptr(),
+                  ws.data_ptr(), M, N, K, _stream())
+        return dW
+    dCt = dC.t().contiguous()                                    # [N, M]
+    At = PackedWeight(A.t().contiguous())                        # [K, M] + TF32 planes
+    S = (M + WGRAD_SLICE - 1) // WGRAD_SLICE
+    out = dW if S == 1 else torch.empty((S, N, K), device=A.device, dtype=torch.float32)
+    _lib.call('digat_linear_tf32x3_splitk', dCt.data_ptr(), M, At.hi.data_ptr(), At.lo.data_ptr(), M, out.data_ptr(), K,
+              N, K, M, S, N * K, _stream())
+    if S > 1:
+        ws = _workspace(S, N * K, 1, A.device)
+        _lib.call('digat_colsum', out.data_ptr(), N * K, dW.data_ptr(), ws.data_ptr(), S, N * K, _stream())
+    return dW
+
+
 class LinearFn(Function):
     """out = A W^T (+bias) (+row-group bias); dA by the tcgen05 GEMM against W^T, dW by the exact-fp32 wgrad GEMM."""
 
@@ -55,10 +83,7 @@ class LinearFn(Function):
         if ctx.needs_input_grad[0]:
             dA = linear(dC, PackedWeight(W.t().contiguous()))
         if ctx.needs_input_grad[1]:
-            dW = torch.empty_like(W)
-            ws = _workspace(M, N, K, A.device)
-            _lib.call('digat_linear_wgrad', dC.data_ptr(), dC.stride(0), A.data_ptr(), A.stride(0), dW.data_ptr(),
-                      ws.data_ptr(), M, N, K, _stream())
+            dW = wgrad(dC, A)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = colsum(dC)
         if ctx.group is not None and ctx.needs_input_grad[3]:

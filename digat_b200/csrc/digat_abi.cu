@@ -60,6 +60,16 @@ int digat_linear_tf32x3(const float* A, int lda, const float* W_hi, const float*
                                 as_stream(stream));
 }
 
+int digat_linear_tf32x3_splitk(const float* A, int lda, const float* W_hi, const float* W_lo, int ldw, float* C, int ldc,
+                               int M, int N, int K, int kbatches, int64_t c_batch_stride, void* stream) {
+    DIGAT_REQUIRE(kbatches >= 1 && (kbatches == 1 || c_batch_stride >= (int64_t)M * ldc),
+                  "digat_linear_tf32x3_splitk: bad kbatches / c_batch_stride");
+    GroupBias gb{nullptr, 1, 0, 0, 0};
+    gb.kbatches = kbatches;
+    gb.c_batch_stride = c_batch_stride;
+    return launch_linear_tf32x3(A, lda, W_hi, W_lo, ldw, nullptr, C, ldc, M, N, K, gb, as_stream(stream));
+}
+
 int digat_debug_set_layer_mode(int mode) {
     g_layer_mode = mode;
     return DIGAT_OK;

@@ -16,6 +16,12 @@ struct GroupBias {
     // row-group bias of THAT row.  A holds only the rows worth computing (digat_b200/graphEncoders.py: nodes whose
     // output can reach a context), C keeps the dense [graphs * n] layout the fused layer kernel streams with TMA.
     const int32_t* out_rows = nullptr;
+    // Split-K batches (persistent GEMM only; weight gradients contract over tens of thousands of rows): the contraction
+    // range is cut into kbatches slices, slice s writes its partial product to C + s * c_batch_stride (summed by the
+    // caller with exact fp32 adds).  More tiles than SMs for skinny outputs, and at most K/kbatches truncating
+    // accumulate steps per accumulator.
+    int kbatches = 1;
+    long long c_batch_stride = 0;
 };
 
 template <int BM, int BN, int BK, int TM, int TN>

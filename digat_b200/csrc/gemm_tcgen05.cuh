@@ -380,7 +380,8 @@ inline int launch_linear_tf32x3(const float* A, int lda, const float* W_hi, cons
                   "digat_linear_tf32x3: pointers must be 16-byte aligned");
     DIGAT_REQUIRE(N % 16 == 0, "digat_linear_tf32x3: N=%d must be a multiple of 16", N);
     if (M == 0) return DIGAT_OK;
-    if (gb.out_rows != nullptr) {                         // row scatter lives in the persistent kernel's epilogue only
+    DIGAT_REQUIRE(gb.kbatches >= 1, "digat_linear_tf32x3: bad split-K batch count");
+    if (gb.out_rows != nullptr || gb.kbatches > 1) {      // row scatter / split-K live in the persistent kernel only
         DIGAT_REQUIRE(N <= 1280, "digat_linear_tf32x3: c_row_index needs N <= 1280 (N=%d)", N);
         if (N % 240 == 0) return launch_tf32x3_persistent<240>(A, lda, W_hi, W_lo, ldw, bias, C, ldc, M, N, K, gb, st);
         return launch_tf32x3_persistent<208>(A, lda, W_hi, W_lo, ldw, bias, C, ldc, M, N, K, gb, st);

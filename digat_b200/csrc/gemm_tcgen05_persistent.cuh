@@ -52,9 +52,11 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
     float* gb_s = stage_base + kTcEpiWarps * 32 * 20;       // [GB_GROUPS][BN] row-group bias slice of the current tile
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nkb = (K + kTcBK - 1) / kTcBK;
+    const int nkb_all = (K + kTcBK - 1) / kTcBK;
+    const int nkb = (nkb_all + gb.kbatches - 1) / gb.kbatches;          // k-blocks per split-K slice (tail slices read zeros)
     const int n_tiles_n = (N + BN - 1) / BN, n_tiles_m = (M + 127) / 128;
-    const int n_tiles = n_tiles_n * n_tiles_m;
+    const int n_tiles_mn = n_tiles_n * n_tiles_m;
+    const int n_tiles = n_tiles_mn * gb.kbatches;                        // tile = slice * n_tiles_mn + (m block, n block)
 
     auto a_hi = [&](int s) { return smem + (size_t)s * Cfg::STAGE_BYTES; };
     auto a_lo = [&](int s) { return smem + (size_t)s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
@@ -90,8 +92,10 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
         if (lane == 0) {
             int it = 0;                                                    // k-blocks issued so far (all tiles)
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int mb = tile / n_tiles_n, m0 = mb * 128, n0 = (tile - mb * n_tiles_n) * BN;
-                if (n0 == 0) {                                             // pull a later M block's A rows into L2
+                const int slice = tile / n_tiles_mn, t_mn = tile - slice * n_tiles_mn;
+                const int mb = t_mn / n_tiles_n, m0 = mb * 128, n0 = (t_mn - mb * n_tiles_n) * BN;
+                const int kb0 = slice * nkb;                               // first k-block of this split-K slice
+                if (n0 == 0 && gb.kbatches == 1) {                         // pull a later M block's A rows into L2
                     const int ahead = mb + kTcPrefetchBlocks;
                     if (ahead < n_tiles_m)
                         for (int kb = 0; kb < nkb; ++kb)
@@ -102,9 +106,9 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
                     const int s = it % Cfg::STAGES;
                     mbar_wait(&empty[s], ((it / Cfg::STAGES) & 1) ^ 1);
                     mbar_arrive_expect_tx(&full[s], Cfg::A_BYTES + 2 * Cfg::W_BYTES);
-                    tma_load_2d(a_hi(s), &map_a, &full[s], kb * kTcBK, m0);
-                    tma_load_2d(w_hi(s), &map_whi, &full[s], kb * kTcBK, n0);
-                    tma_load_2d(w_lo(s), &map_wlo, &full[s], kb * kTcBK, n0);
+                    tma_load_2d(a_hi(s), &map_a, &full[s], (kb0 + kb) * kTcBK, m0);        // k past K arrives as zeros
+                    tma_load_2d(w_hi(s), &map_whi, &full[s], (kb0 + kb) * kTcBK, n0);
+                    tma_load_2d(w_lo(s), &map_wlo, &full[s], (kb0 + kb) * kTcBK, n0);
                 }
             }
         }
@@ -200,7 +204,9 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
         const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
         int j = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
-            const int mb = tile / n_tiles_n, m0 = mb * 128, n0 = (tile - mb * n_tiles_n) * BN;
+            const int slice = tile / n_tiles_mn, t_mn = tile - slice * n_tiles_mn;
+            const int mb = t_mn / n_tiles_n, m0 = mb * 128, n0 = (t_mn - mb * n_tiles_n) * BN;
+            float* __restrict__ Cs = C + (size_t)slice * (size_t)gb.c_batch_stride;       // this slice's output slab
             const int m = m0 + q * 32 + lane;
             const int32_t* orow = gb.out_rows;                             // ascending row scatter, or null
             const int mo = orow != nullptr ? orow[min(m, M - 1)] : m;      // row of C (and of the row-group bias)
@@ -264,7 +270,7 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
                 float o[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
-                    o[i] = (__uint_as_float(rm[i]) + __uint_as_float(rc[i])) + (n0 + c + i < N ? bias_s[n0 + c + i] : 0.f);
+                    o[i] = (__uint_as_float(rm[i]) + __uint_as_float(rc[i])) + ((n0 + c + i < N && slice == 0) ? bias_s[n0 + c + i] : 0.f);
 #pragma unroll
                 for (int v4 = 0; v4 < 4; ++v4) {
                     float4 gv = gq[v4];
@@ -292,7 +298,7 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
                     const int mr = m0 + q * 32 + row;
                     const int mc = __shfl_sync(0xffffffffu, mo, row);         // C row of tile row `row` (== mr without scatter)
                     if (mr < M && n0 + c + cq * 4 < N)
-                        *reinterpret_cast<float4*>(C + (size_t)mc * ldc + n0 + c + cq * 4) =
+                        *reinterpret_cast<float4*>(Cs + (size_t)mc * ldc + n0 + c + cq * 4) =
                             *reinterpret_cast<const float4*>(stage + row * 20 + cq * 4);
                 }
             }
@@ -323,7 +329,7 @@ int launch_tf32x3_persistent(const float* A, int lda, const float* W_hi, const f
     if ((rc = make_tensor_map_2d(&ml, W_lo, N, K, ldw, BN, kTcBK, CU_TENSOR_MAP_SWIZZLE_64B)) != DIGAT_OK) return rc;
     DIGAT_REQUIRE(N <= Cfg::MAX_N, "digat_linear_tf32x3(persistent): N=%d exceeds %d", N, Cfg::MAX_N);
     DIGAT_CUDA(cudaFuncSetAttribute(gemm_tf32x3_persistent_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-    const int tiles = ((N + BN - 1) / BN) * ((M + 127) / 128);
+    const int tiles = ((N + BN - 1) / BN) * ((M + 127) / 128) * gb.kbatches;
     const int grid = tiles < di->sm_count ? tiles : di->sm_count;
     gemm_tf32x3_persistent_kernel<BN><<<grid, kTcPersistThreads, Cfg::SMEM, st>>>(ma, mh, ml, bias, C, ldc, M, N, K, gb);
     return check_launch("digat_linear_tf32x3(persistent)");

@@ -69,6 +69,15 @@ int digat_linear_tf32x3(const float* A, int lda, const float* W_hi, const float*
                         const float* group_bias, int group_rows, int group_col0, int group_cols, int group_ld,
                         const int32_t* c_row_index, void* stream);
 
+/* Split-K form of digat_linear_tf32x3 (no bias): the contraction range [0,K) is cut into kbatches equal slices and slice
+ * s writes its partial product to C + s * c_batch_stride (elements); the caller sums the slabs (digat_colsum over a
+ * [kbatches, M*ldc] view: exact fp32 adds in slice order).  Used for weight gradients dW = dC^T A, whose contraction
+ * runs over all rows of a batch: more tiles than SMs for a skinny output, and few truncating tensor-core accumulate
+ * steps per accumulator.  N <= 1280. */
+int digat_linear_tf32x3_splitk(const float* A, int lda, const float* W_hi, const float* W_lo, int ldw,
+                               float* C, int ldc, int M, int N, int K, int kbatches, int64_t c_batch_stride,
+                               void* stream);
+
 /* Tuning/experiment switch for digat_linear_tf32x3 tile variants (0 = default).  Not part of the reference path. */
 int digat_debug_set_gemm_variant(int variant);
 /* digat_graph_layer_fwd kernel choice: 0 = auto (edge-driven kernel when a CTA owns one graph and no training extras are
