@@ -318,7 +318,9 @@ def run_train(args):
     model.graph_encoder.load_state_dict(sd)
     model = model.to(dev).train()
     net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank]) if world > 1 else model
-    graphed = world == 1 and not args.eager_train      # whole-step CUDA graph (digat_b200/training.py); DDP runs eagerly
+    # whole-step CUDA graph (digat_b200/training.py) on one GPU; the DDP step runs eagerly (capturing DDP's reducer +
+    # NCCL all-reduce failed in this PyTorch build: capture_end reported an invalidated capture from the backward)
+    graphed = world == 1 and not args.eager_train
     opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=graphed)
     bs, news_num = 64, 5
     rng = np.random.Generator(np.random.PCG64(rank))

@@ -17,6 +17,7 @@
 // Pipeline: full[s] (TMA bytes landed) -> ready[s] (A split done) -> MMA -> empty[s] (tcgen05.commit) -> TMA.
 #pragma once
 #include "common.cuh"
+#include <cuda_bf16.h>
 #include "tma.cuh"
 #include "gemm_simt.cuh"   // GroupBias
 
@@ -36,6 +37,28 @@ __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
     d |= (uint64_t)1 << 46;                             // descriptor version
     d |= (uint64_t)4 << 61;                             // SWIZZLE_64B
     return d;
+}
+
+// K-major bf16 operand tile of 16 elements per row, SWIZZLE_32B: rows of 32 bytes, 8-row groups of 256 bytes (SBO).
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(256 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)6 << 61;                             // SWIZZLE_32B
+    return d;
+}
+// kind::f16 with bf16 operands (K = 16 per instruction), fp32 accumulate, both operands K-major.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
 
 // kind::tf32, fp32 accumulate, both operands K-major, M=128, N=BN.
@@ -340,6 +363,19 @@ __global__ void split_tf32_kernel(const float* __restrict__ w, float* __restrict
     }
 }
 
+// bf16 planes of a weight for the correction products of the TF32+BF16 scheme (gemm_tcgen05_persistent.cuh):
+// hb = bf16(rna_tf32(W)) (stands in for W_hi in A_lo*W_hi), lb = bf16(W - rna_tf32(W)) (W_lo in A*W_lo).
+__global__ void split_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hb, __nv_bfloat16* __restrict__ lb,
+                                  int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const float x = w[i];
+        const float h = to_tf32_rna(x);
+        hb[i] = __float2bfloat16_rn(h);
+        lb[i] = __float2bfloat16_rn(x - h);
+    }
+}
+
 template <int BN, int MH, bool SPLIT>
 inline int launch_tf32x3_cfg(const float* A, int lda, const float* W_hi, const float* W_lo, int ldw, const float* bias,
                              float* C, int ldc, int M, int N, int K, GroupBias gb, cudaStream_t st) {
@@ -362,7 +398,8 @@ int launch_tf32x3_pair(const float* A, int lda, const float* W_hi, const float* 
                        float* C, int ldc, int M, int N, int K, GroupBias gb, cudaStream_t st);   // gemm_tcgen05_pair.cuh
 template <int BN>
 int launch_tf32x3_persistent(const float* A, int lda, const float* W_hi, const float* W_lo, int ldw, const float* bias,
-                             float* C, int ldc, int M, int N, int K, GroupBias gb, cudaStream_t st);   // gemm_tcgen05_persistent.cuh
+                             float* C, int ldc, int M, int N, int K, GroupBias gb, cudaStream_t st,
+                             const void* W_hb = nullptr, const void* W_lb = nullptr);   // gemm_tcgen05_persistent.cuh
 
 inline int launch_linear_tf32x3(const float* A, int lda, const float* W_hi, const float* W_lo, int ldw, const float* bias,
                                 float* C, int ldc, int M, int N, int K, GroupBias gb, cudaStream_t st) {

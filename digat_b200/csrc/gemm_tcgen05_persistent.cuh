@@ -32,10 +32,17 @@ struct TcPersistCfg {
     static_assert(STAGES >= 3, "not enough shared memory for the pipeline");
 };
 
-template <int BN>
+// kBf16: the TF32+BF16 scheme.  The two correction products are ~2^-11 of the result, so they only need ~9 good bits:
+//   C = A_hi*W_hi [kind::tf32, raw A]  +  bf16(A)*bf16(W_lo)  +  bf16(A_lo)*bf16(W_hi)   [kind::f16, K = 16 per MMA]
+// (relative error of the corrections 2^-9 * 2^-10..2^-12 = 2^-19..2^-21 of the result, below the accumulator's own
+// truncation error).  bf16 MMAs run at twice the TF32 rate: per 16-wide k-block the tensor pipe does 2 TF32 MMAs + 2 BF16
+// MMAs = 4 TF32-MMA times instead of 6.  The stage keeps its size: A_lo (tf32) becomes two bf16 tiles of half the size,
+// W_lo (tf32) becomes the two bf16 planes of W (map_w2 = bf16(W_hi), map_w3 = bf16(W_lo); SWIZZLE_32B tiles).
+template <int BN, bool kBf16>
 __global__ void __launch_bounds__(kTcPersistThreads, 1)
 gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_whi,
-                              const __grid_constant__ CUtensorMap map_wlo, const float* __restrict__ bias,
+                              const __grid_constant__ CUtensorMap map_wlo, const __grid_constant__ CUtensorMap map_w3,
+                              const float* __restrict__ bias,
                               float* __restrict__ C, int ldc, int M, int N, int K, GroupBias gb) {
     using Cfg = TcPersistCfg<BN>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -62,6 +69,9 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
     auto a_lo = [&](int s) { return smem + (size_t)s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
     auto w_hi = [&](int s) { return smem + (size_t)s * Cfg::STAGE_BYTES + 2 * Cfg::A_BYTES; };
     auto w_lo = [&](int s) { return smem + (size_t)s * Cfg::STAGE_BYTES + 2 * Cfg::A_BYTES + Cfg::W_BYTES; };
+    // kBf16: a_lo(s) holds bf16(A) [128x16] then bf16(A_lo); w_lo(s) holds bf16(W_hi) [BNx16] then bf16(W_lo)
+    auto a_b2 = [&](int s) { return a_lo(s) + Cfg::A_BYTES / 2; };
+    auto w_b3 = [&](int s) { return w_lo(s) + Cfg::W_BYTES / 2; };
 
     for (int i = threadIdx.x; i < N; i += kTcPersistThreads) bias_s[i] = bias != nullptr ? bias[i] : 0.f;
     if (warp == 0 && lane == 0) {
@@ -108,7 +118,8 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
                     mbar_arrive_expect_tx(&full[s], Cfg::A_BYTES + 2 * Cfg::W_BYTES);
                     tma_load_2d(a_hi(s), &map_a, &full[s], (kb0 + kb) * kTcBK, m0);        // k past K arrives as zeros
                     tma_load_2d(w_hi(s), &map_whi, &full[s], (kb0 + kb) * kTcBK, n0);
-                    tma_load_2d(w_lo(s), &map_wlo, &full[s], (kb0 + kb) * kTcBK, n0);
+                    tma_load_2d(w_lo(s), &map_wlo, &full[s], (kb0 + kb) * kTcBK, n0);      // kBf16: bf16(W_hi), half the bytes
+                    if (kBf16) tma_load_2d(w_b3(s), &map_w3, &full[s], (kb0 + kb) * kTcBK, n0);   // bf16(W_lo)
                 }
             }
         }
@@ -140,18 +151,26 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
                         const uint64_t koff = (uint64_t)((k * 8 * 4) >> 4);
                         const uint32_t first = (kb > 0 || k > 0) ? 1u : 0u;
                         umma_tf32(d_main, d_ahi + koff, d_whi + koff, idesc, first);
-                        umma_tf32(d_corr, d_ahi + koff, d_wlo + koff, idesc, first);
+                        if (!kBf16) umma_tf32(d_corr, d_ahi + koff, d_wlo + koff, idesc, first);
                     }
                 };
                 auto issue_lo = [&](int g) {
                     const int s = g % Cfg::STAGES;
                     mbar_wait(&ready[s], (g / Cfg::STAGES) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint64_t d_alo = umma_desc_sw64(smem_u32(a_lo(s))), d_whi = umma_desc_sw64(smem_u32(w_hi(s)));
+                    if (kBf16) {
+                        // one K=16 bf16 MMA per correction product: bf16(A) x bf16(W_lo), bf16(A_lo) x bf16(W_hi)
+                        constexpr uint32_t idesc16 = umma_idesc_bf16(128, BN);
+                        const uint32_t first = (g - it) > 0 ? 1u : 0u;                  // first k-block of the tile starts d_corr
+                        umma_bf16(d_corr, umma_desc_sw32(smem_u32(a_lo(s))), umma_desc_sw32(smem_u32(w_b3(s))), idesc16, first);
+                        umma_bf16(d_corr, umma_desc_sw32(smem_u32(a_b2(s))), umma_desc_sw32(smem_u32(w_lo(s))), idesc16, 1u);
+                    } else {
+                        const uint64_t d_alo = umma_desc_sw64(smem_u32(a_lo(s))), d_whi = umma_desc_sw64(smem_u32(w_hi(s)));
 #pragma unroll
-                    for (int k = 0; k < kTcBK / 8; ++k) {
-                        const uint64_t koff = (uint64_t)((k * 8 * 4) >> 4);
-                        umma_tf32(d_corr, d_alo + koff, d_whi + koff, idesc, 1u);
+                        for (int k = 0; k < kTcBK / 8; ++k) {
+                            const uint64_t koff = (uint64_t)((k * 8 * 4) >> 4);
+                            umma_tf32(d_corr, d_alo + koff, d_whi + koff, idesc, 1u);
+                        }
                     }
                     umma_commit(&empty[s]);
                 };
@@ -182,10 +201,25 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
                 for (int i = 0; i < Cfg::A_BYTES / 16 / kTcTransformThreads; ++i) {
                     const int idx = t + i * kTcTransformThreads;
                     const float4 v = hi[idx];
-                    float4 vl;
-                    vl.x = to_tf32_rna(v.x - tf32_trunc(v.x)); vl.y = to_tf32_rna(v.y - tf32_trunc(v.y));
-                    vl.z = to_tf32_rna(v.z - tf32_trunc(v.z)); vl.w = to_tf32_rna(v.w - tf32_trunc(v.w));
-                    lo[idx] = vl;
+                    if (kBf16) {
+                        // source: fp32 tile, SWIZZLE_64B (16-byte chunk c of row r sits at chunk c ^ ((r >> 1) & 3));
+                        // destinations: two bf16 tiles, SWIZZLE_32B (rows of 32 bytes, chunk cd at cd ^ ((r >> 2) & 1))
+                        const int r = idx >> 2, c = (idx & 3) ^ ((r >> 1) & 3);          // logical columns 4c .. 4c+3
+                        const uint32_t off = (uint32_t)(r * 32 + (((c >> 1) ^ ((r >> 2) & 1)) << 4) + ((c & 1) << 3));
+                        __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
+                        __nv_bfloat162 q0 = __floats2bfloat162_rn(v.x - tf32_trunc(v.x), v.y - tf32_trunc(v.y));
+                        __nv_bfloat162 q1 = __floats2bfloat162_rn(v.z - tf32_trunc(v.z), v.w - tf32_trunc(v.w));
+                        uint2 full_v, lo_v;
+                        full_v.x = *reinterpret_cast<uint32_t*>(&p0); full_v.y = *reinterpret_cast<uint32_t*>(&p1);
+                        lo_v.x = *reinterpret_cast<uint32_t*>(&q0); lo_v.y = *reinterpret_cast<uint32_t*>(&q1);
+                        *reinterpret_cast<uint2*>(a_lo(s) + off) = full_v;                // bf16(A)
+                        *reinterpret_cast<uint2*>(a_b2(s) + off) = lo_v;                  // bf16(A - trunc_tf32(A))
+                    } else {
+                        float4 vl;
+                        vl.x = to_tf32_rna(v.x - tf32_trunc(v.x)); vl.y = to_tf32_rna(v.y - tf32_trunc(v.y));
+                        vl.z = to_tf32_rna(v.z - tf32_trunc(v.z)); vl.w = to_tf32_rna(v.w - tf32_trunc(v.w));
+                        lo[idx] = vl;
+                    }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
@@ -318,7 +352,8 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
 
 template <int BN>
 int launch_tf32x3_persistent(const float* A, int lda, const float* W_hi, const float* W_lo, int ldw, const float* bias,
-                             float* C, int ldc, int M, int N, int K, GroupBias gb, cudaStream_t st) {
+                             float* C, int ldc, int M, int N, int K, GroupBias gb, cudaStream_t st,
+                             const void* W_hb, const void* W_lb) {
     using Cfg = TcPersistCfg<BN>;
     const DeviceInfo* di = device_info();
     if (!di) return fail(DIGAT_E_CUDA, "digat_linear_tf32x3: no CUDA device");
@@ -326,12 +361,24 @@ int launch_tf32x3_persistent(const float* A, int lda, const float* W_hi, const f
     int rc;
     if ((rc = make_tensor_map_2d(&ma, A, M, K, lda, 128, kTcBK, CU_TENSOR_MAP_SWIZZLE_64B)) != DIGAT_OK) return rc;
     if ((rc = make_tensor_map_2d(&mh, W_hi, N, K, ldw, BN, kTcBK, CU_TENSOR_MAP_SWIZZLE_64B)) != DIGAT_OK) return rc;
-    if ((rc = make_tensor_map_2d(&ml, W_lo, N, K, ldw, BN, kTcBK, CU_TENSOR_MAP_SWIZZLE_64B)) != DIGAT_OK) return rc;
+    const bool bf16c = W_hb != nullptr && W_lb != nullptr;
+    CUtensorMap m3 = mh;
+    if (bf16c) {
+        if ((rc = make_tensor_map_2d_bf16(&ml, W_hb, N, K, ldw, BN, kTcBK, CU_TENSOR_MAP_SWIZZLE_32B)) != DIGAT_OK) return rc;
+        if ((rc = make_tensor_map_2d_bf16(&m3, W_lb, N, K, ldw, BN, kTcBK, CU_TENSOR_MAP_SWIZZLE_32B)) != DIGAT_OK) return rc;
+    } else {
+        if ((rc = make_tensor_map_2d(&ml, W_lo, N, K, ldw, BN, kTcBK, CU_TENSOR_MAP_SWIZZLE_64B)) != DIGAT_OK) return rc;
+    }
     DIGAT_REQUIRE(N <= Cfg::MAX_N, "digat_linear_tf32x3(persistent): N=%d exceeds %d", N, Cfg::MAX_N);
-    DIGAT_CUDA(cudaFuncSetAttribute(gemm_tf32x3_persistent_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     const int tiles = ((N + BN - 1) / BN) * ((M + 127) / 128) * gb.kbatches;
     const int grid = tiles < di->sm_count ? tiles : di->sm_count;
-    gemm_tf32x3_persistent_kernel<BN><<<grid, kTcPersistThreads, Cfg::SMEM, st>>>(ma, mh, ml, bias, C, ldc, M, N, K, gb);
+    if (bf16c) {
+        DIGAT_CUDA(cudaFuncSetAttribute(gemm_tf32x3_persistent_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        gemm_tf32x3_persistent_kernel<BN, true><<<grid, kTcPersistThreads, Cfg::SMEM, st>>>(ma, mh, ml, m3, bias, C, ldc, M, N, K, gb);
+    } else {
+        DIGAT_CUDA(cudaFuncSetAttribute(gemm_tf32x3_persistent_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        gemm_tf32x3_persistent_kernel<BN, false><<<grid, kTcPersistThreads, Cfg::SMEM, st>>>(ma, mh, ml, m3, bias, C, ldc, M, N, K, gb);
+    }
     return check_launch("digat_linear_tf32x3(persistent)");
 }
 

@@ -74,4 +74,20 @@ inline int make_tensor_map_2d(CUtensorMap* map, const float* base, int64_t rows,
     return DIGAT_OK;
 }
 
+// [rows, cols] bf16 (2-byte elements), row pitch ld elements
+inline int make_tensor_map_2d_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                                   int box_cols, CUtensorMapSwizzle swizzle) {
+    PFN_tensorMapEncodeTiled enc = tensor_map_encoder();
+    if (!enc) return fail(DIGAT_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(DIGAT_E_CUDA, "cuTensorMapEncodeTiled(bf16) failed with CUresult %d", (int)r);
+    return DIGAT_OK;
+}
+
 }  // namespace digat

@@ -69,6 +69,18 @@ int digat_linear_tf32x3(const float* A, int lda, const float* W_hi, const float*
                         const float* group_bias, int group_rows, int group_col0, int group_cols, int group_ld,
                         const int32_t* c_row_index, void* stream);
 
+/* TF32 + BF16-correction form of the projection GEMM (large M; persistent tcgen05 kernel):
+ *   C = A_hi*W_hi [TF32 MMAs on the raw fp32 A]  +  bf16(A)*bf16(W_lo)  +  bf16(A_lo)*bf16(W_hi)  [BF16 MMAs]
+ * The two correction products are ~2^-11 of the result and need only ~9 good bits, so they run as BF16 MMAs at twice the
+ * TF32 rate: 4 instead of 6 TF32-MMA times per k-block at the same fp32-level accuracy (measured in tests/test_gpu_gemm.py).
+ * W_hi = rna_tf32(W) (digat_split_tf32); W_hb = bf16(W_hi), W_lb = bf16(W - W_hi) (digat_split_bf16), all with row pitch
+ * ldw elements.  Same bias / row-group bias / row scatter semantics as digat_linear_tf32x3.  K, ldw % 8 == 0, N <= 1280. */
+int digat_split_bf16(const float* W, void* W_hb, void* W_lb, int64_t count, void* stream);
+int digat_linear_tf32_bf16c(const float* A, int lda, const float* W_hi, const void* W_hb, const void* W_lb, int ldw,
+                            const float* bias, float* C, int ldc, int M, int N, int K,
+                            const float* group_bias, int group_rows, int group_col0, int group_cols, int group_ld,
+                            const int32_t* c_row_index, void* stream);
+
 /* Split-K form of digat_linear_tf32x3 (no bias): the contraction range [0,K) is cut into kbatches equal slices and slice
  * s writes its partial product to C + s * c_batch_stride (elements); the caller sums the slabs (digat_colsum over a
  * [kbatches, M*ldc] view: exact fp32 adds in slice order).  Used for weight gradients dW = dC^T A, whose contraction

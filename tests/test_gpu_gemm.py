@@ -88,3 +88,27 @@ def test_group_bias_folds_k3_into_K1_block(M, n):
     expect = base.clone()
     expect[:, D:2 * D] = base[:, D:2 * D] + k3.repeat_interleave(n, 0)       # exactly one fp32 add
     assert torch.equal(out, expect)
+
+
+def test_tf32_bf16_correction_gemm_matches_fp64():
+    """digat_linear_tf32_bf16c (experimental scheme: TF32 main product, BF16 correction products) keeps fp32-level
+    accuracy, with bias, row-group bias and a partial last N tile."""
+    from digat_b200 import _lib
+    g = torch.Generator().manual_seed(3)
+    for (M, N, K) in [(20000, 1200, 400), (5000, 400, 800), (300, 240, 64)]:
+        A = torch.randn(M, K, generator=g).cuda()
+        W = (torch.randn(N, K, generator=g) * 0.05).cuda()
+        b = torch.randn(N, generator=g).cuda()
+        gbias = torch.randn((M + 67) // 68, 400 if N >= 400 else 80, generator=g).cuda()
+        hi, lo = _split(W)
+        hb = torch.empty(W.shape, dtype=torch.bfloat16, device='cuda')
+        lb = torch.empty_like(hb)
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.call('digat_split_bf16', W.data_ptr(), hb.data_ptr(), lb.data_ptr(), W.numel(), st)
+        C = torch.full((M, N), float('nan'), device='cuda')
+        _lib.call('digat_linear_tf32_bf16c', A.data_ptr(), K, hi.data_ptr(), hb.data_ptr(), lb.data_ptr(), K, b.data_ptr(),
+                  C.data_ptr(), N, M, N, K, gbias.data_ptr(), 68, 0, gbias.shape[1], gbias.shape[1], 0, st)
+        torch.cuda.synchronize()
+        ref = A.double().cpu() @ W.double().cpu().t() + b.double().cpu()
+        ref[:, :gbias.shape[1]] += gbias.double().cpu().repeat_interleave(68, dim=0)[:M]
+        assert rel_err(C.cpu().numpy(), ref.numpy()) < 4e-6
