@@ -1,4 +1,4 @@
-// Fused Eq. (8) graph-attention layer, forward, EDGE-DRIVEN variant (inference; one graph per CTA).
+// Fused Eq. (8) graph-attention layer, forward, EDGE-DRIVEN variant (inference).
 //
 // The reference evaluates s_ij for all n^2 pairs and then overwrites the non-edges with -1e9
 // (graphEncoders.py:150-152).  A masked pair contributes exp(-1e9 - max) == 0.0f to the softmax of any row that has at
@@ -6,19 +6,24 @@
 // aggregates over neighbours only -- the same alpha and Y as the dense evaluation, with E instead of n^2 pair
 // evaluations (MIND-shaped user graphs: E ~ 300-650 of 4624; SAG trees: ~2n of n^2).  A row without any edge (cannot
 // happen in the reference's data: the diagonal is always set) is handled like the reference: every entry is -1e9, the
-// softmax is uniform 1/n over ALL nodes.
+// softmax is uniform 1/n over ALL nodes of its graph.
 //
-// With the pair work gone the kernel is bound by how fast P can be streamed in, so it is organised around the loads:
-//   warp 10   TMA producer: walks the load schedule (13 U|K2 units of 32 features, then 7 h units of 64 features)
-//             through a 4-deep ring of shared-memory buffers, waiting only on per-buffer "empty" mbarriers;
-//   warps 0-9 consumers: no CTA-wide barrier inside the streaming loops -- a warp waits on "full[buf]", does its share
-//             and arrives on "empty[buf]"; fast warps run up to 4 units ahead of slow ones.
-//   setup     adjacency bytes -> CSR (row pointers, uint8 row / column per edge) with warp ballots + one warp scan
+// A CTA owns one graph, or G small graphs treated as one block-diagonal graph of G*n <= 128 nodes (kMulti; the rows
+// of consecutive graphs are contiguous in P / X / Y / adj, so one TMA box covers them).  The kernel is organised around
+// the loads:
+//   producer  (last warp) walks the load schedule (13 U|K2 units of 32 features, then 7 h units of 64 features) through
+//             a ring of shared-memory buffers, waiting only on per-buffer "empty" mbarriers;
+//   consumers no CTA-wide barrier inside the streaming loops -- a warp waits on "full[buf]", does its share and arrives
+//             on "empty[buf]"; fast warps run up to a ring's depth ahead of slow ones.
+//   setup     adjacency bytes -> CSR (row pointers, one uint16 (column | row << 8) per edge) with warp ballots + one warp
+//             scan; nodes pruned by row_active get no CSR row
 //   phase 1   one EDGE per thread: U_j and K2_i quads from smem, packed FADD2 / FMNMX / FFMA2, score[e] += partial
 //   phase 2   one warp per row: leaky-relu, max/sum by shuffles over the row's CSR segment, exp, normalise
-//   phase 3   half a warp per row, one lane per feature quad: loop over the row's neighbours (FFMA2), relu + residual
+//   phase 3   half a warp per row, one lane per feature quad: loop over the row's neighbours (FFMA2, four neighbours in
+//             flight), relu + residual; pruned rows are neither read nor written; with Yc the row is also written to the
+//             compact operand of the next layer's projection
 // In indexed (de-duplicated) mode the shared K1 tile becomes this pair's U in registers: fl(fl(K1 + k3) + K2), the
-// reference's rounding.  HBM traffic per graph is unchanged: 5nD*4 + n^2 bytes.
+// reference's rounding.  HBM traffic per graph: 5nD*4 + n^2 bytes (pruned rows of P are still streamed by the TMA boxes).
 #pragma once
 #include "common.cuh"
 #include "tma.cuh"

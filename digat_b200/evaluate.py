@@ -89,11 +89,12 @@ def rank_pairs_device(scores, offsets):
     return ranks
 
 
-def metrics_device(ranks, labels, offsets):
+def metrics_device(ranks, labels, offsets, on_single_class='raise'):
     """ranks [P] int32, labels [P] (0/1, any integer/bool dtype), offsets [n_imp+1] int64, all CUDA tensors ->
     (AUC, MRR, nDCG@5, nDCG@10) averaged over the non-empty impressions, as reference evaluate.py:66-89.
     Per-impression values come from impression_metrics_kernel in double; the mean is taken on the host in impression
-    order.  Raises ValueError if an impression has a single class (sklearn's roc_auc_score raises there)."""
+    order.  Raises ValueError if an impression has a single class (sklearn's roc_auc_score raises there; MIND impressions
+    always hold both) unless on_single_class='skip' (synthetic corpora with one-candidate impressions)."""
     import torch
     from . import _lib
     dev = ranks.device
@@ -105,7 +106,7 @@ def metrics_device(ranks, labels, offsets):
         _lib.call('digat_impression_metrics', ranks.data_ptr(), lab.data_ptr(), offsets.data_ptr(), out.data_ptr(),
                   valid.data_ptr(), n_imp, torch.cuda.current_stream().cuda_stream)
     v = valid.cpu().numpy()
-    if (v == 2).any():
+    if (v == 2).any() and on_single_class != 'skip':
         raise ValueError('Only one class present in y_true. ROC AUC score is not defined in that case.')
     o = out.cpu().numpy()[v == 1]
     return tuple(float(np.mean(o[:, k])) for k in range(4))

@@ -276,7 +276,8 @@ def compute_scores(scorer: Scorer, corpus, batch_size: int, rank: int = 0, world
     return torch.cat(outs).cpu().numpy()
 
 
-def evaluate_resident(scorer: Scorer, corpus, batch_size: int = 4096, rank: int = 0, world_size: int = 1):
+def evaluate_resident(scorer: Scorer, corpus, batch_size: int = 4096, rank: int = 0, world_size: int = 1,
+                      on_single_class='raise'):
     """Device-resident replacement of the reference's evaluation loop (util.compute_scores, util.py:51-80, followed by
     evaluate.scoring): pairs are (behaviour index, news id) only, graphs and tables stay in HBM, and the per-impression
     ranking and metrics run on the GPU (csrc/builders.cuh).  Shards whole impressions across ranks (no communication).
@@ -290,12 +291,11 @@ def evaluate_resident(scorer: Scorer, corpus, batch_size: int = 4096, rank: int 
     dev = scorer.dev
     beh = torch.from_numpy(corpus.pair_behavior[lo:hi]).to(dev)
     news = torch.from_numpy(corpus.pair_news[lo:hi]).to(dev)
-    scores = torch.empty(hi - lo, device=dev, dtype=torch.float32)
-    for s in range(0, hi - lo, batch_size):
-        e = min(s + batch_size, hi - lo)
-        scores[s:e] = scorer.score_resident(beh[s:e], news[s:e])
+    outs = score_resident_batches(scorer, ((beh[s:s + batch_size], news[s:s + batch_size])
+                                           for s in range(0, hi - lo, batch_size)))
+    scores = torch.cat(outs) if outs else torch.empty(0, device=dev, dtype=torch.float32)
     scorer.check_index_errors()
     off = torch.from_numpy(off_all[i_lo:i_hi + 1] - lo).to(dev)
     ranks = evaluate.rank_pairs_device(scores, off)
-    m = evaluate.metrics_device(ranks, torch.from_numpy(corpus.labels[lo:hi]).to(dev), off)
+    m = evaluate.metrics_device(ranks, torch.from_numpy(corpus.labels[lo:hi]).to(dev), off, on_single_class)
     return dict(scores=scores, ranks=ranks, offsets=off, metrics=m)
