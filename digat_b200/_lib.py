@@ -29,7 +29,8 @@ SIGNATURES = {
                               c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     'digat_graph_layer_supports_row_active': [c_int, c_int, c_int],
     'digat_news_active_rows': [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p],
-    'digat_user_active_rows': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p],
+    'digat_user_active_rows': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
+                               c_void_p],
     'digat_attention_pool_fwd': [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                  c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     'digat_news_gate_fwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],

@@ -107,7 +107,7 @@ inline int launch_build_user_graphs(const int32_t* hist_cat, const int32_t* hist
 __global__ void __launch_bounds__(128)
 user_active_rows_kernel(const uint8_t* __restrict__ adj, const int32_t* __restrict__ adj_index,
                         const int64_t* __restrict__ cidx, const uint8_t* __restrict__ cmask, uint8_t* __restrict__ active,
-                        int n, int H, int S) {
+                        uint8_t* __restrict__ pooled_out, int n, int H, int S) {
     __shared__ int col_used[128];
     __shared__ int any_empty, any_bucket;
     const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -135,6 +135,7 @@ user_active_rows_kernel(const uint8_t* __restrict__ adj, const int32_t* __restri
             pooled = !any_bucket || c < 0 || c >= S || cmask[(size_t)g * S + c] != 0;   // bad ids: leave to the segment kernel
         }
         active[(size_t)g * n + tid] = (any_empty || col_used[tid] || pooled) ? 1 : 0;
+        if (pooled_out != nullptr) pooled_out[(size_t)g * n + tid] = pooled ? 1 : 0;   // rows a context reads directly
     }
 }
 
@@ -175,12 +176,12 @@ inline int launch_news_active_rows(const uint8_t* adj, const uint8_t* mask, uint
 }
 
 inline int launch_user_active_rows(const uint8_t* adj, const int32_t* adj_index, const int64_t* cidx, const uint8_t* cmask,
-                                   uint8_t* active, int64_t G, int n, int H, int S, cudaStream_t st) {
+                                   uint8_t* active, uint8_t* pooled_out, int64_t G, int n, int H, int S, cudaStream_t st) {
     if (G <= 0) return DIGAT_OK;
     DIGAT_REQUIRE(adj && cidx && cmask && active, "digat_user_active_rows: null pointer");
     DIGAT_REQUIRE(n >= 1 && n <= 128 && H >= 0 && H <= n && S >= 1, "digat_user_active_rows: bad n / H / S");
     DIGAT_REQUIRE(G <= 0x7fffffff, "digat_user_active_rows: too many graphs for one launch");
-    user_active_rows_kernel<<<(unsigned)G, 128, 0, st>>>(adj, adj_index, cidx, cmask, active, n, H, S);
+    user_active_rows_kernel<<<(unsigned)G, 128, 0, st>>>(adj, adj_index, cidx, cmask, active, pooled_out, n, H, S);
     return check_launch("digat_user_active_rows");
 }
 

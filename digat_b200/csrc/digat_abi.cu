@@ -248,8 +248,8 @@ int digat_build_user_graphs(const int32_t* hist_cat, const int32_t* hist_len, ui
 }
 
 int digat_user_active_rows(const uint8_t* adj, const int32_t* adj_index, const int64_t* cidx, const uint8_t* cmask,
-                           uint8_t* active, int64_t G, int n, int H, int S, void* stream) {
-    return launch_user_active_rows(adj, adj_index, cidx, cmask, active, G, n, H, S, as_stream(stream));
+                           uint8_t* active, uint8_t* pooled, int64_t G, int n, int H, int S, void* stream) {
+    return launch_user_active_rows(adj, adj_index, cidx, cmask, active, pooled, G, n, H, S, as_stream(stream));
 }
 
 int digat_news_active_rows(const uint8_t* adj, const uint8_t* mask, uint8_t* active, int64_t G, int n, void* stream) {

@@ -325,7 +325,10 @@ class DIGAT(GraphEncoder):
         n, D = X.shape[1], X.shape[2]
         if k3 is None:
             k3 = linear(ctx_other, w[g, i, 'W3'], w[g, i, 'b3'])                  # [B, D]
-        act, rows, pos = (None, None, None) if prune is None else prune
+        act, rows, pos = (None, None, None) if prune is None else prune[:3]
+        kernel_act = act
+        if prune is not None and len(prune) > 3 and not want_compact and share is None and i + 1 == self.graph_depth:
+            kernel_act = prune[3]         # last layer: only the rows a context pools are evaluated (the rest stay neighbours)
         Yc = None
         if prune is not None and want_compact:
             # capacity = every row (M_act changes from batch to batch: a fixed size lets the caching allocator reuse the block)
@@ -342,7 +345,7 @@ class DIGAT(GraphEncoder):
                           self._err_flag(X.device).data_ptr(), _stream())
             P = torch.empty((X.shape[0] * n, w[g, i, 'Wcat'].w.shape[0]), device=X.device, dtype=torch.float32)
             linear(A_c, w[g, i, 'Wcat'], w[g, i, 'bcat'], out=P, group_bias=k3, group_rows=n, group_col0=D, c_rows=rows)
-            return graph_layer_fwd(P, w[g, i, 'a'], adj, X, adj_index=adj_index, row_active=act, compact_out=Yc,
+            return graph_layer_fwd(P, w[g, i, 'a'], adj, X, adj_index=adj_index, row_active=kernel_act, compact_out=Yc,
                                    row_pos=pos if Yc is not None else None), Yc
         P = linear(X, w[g, i, 'Wcat'], w[g, i, 'bcat'], group_bias=k3, group_rows=n, group_col0=D)   # h | k3+K1 | K2
         return graph_layer_fwd(P, w[g, i, 'a'], adj, X, adj_index=adj_index), None
@@ -361,9 +364,12 @@ class DIGAT(GraphEncoder):
            not _lib.load().digat_graph_layer_supports_row_active(n, self.news_embedding_dim, B):
             return None          # (small batches stay on the exact-fp32 GEMM, which has no row scatter)
         act = torch.empty((B, n), dtype=torch.uint8, device=Au.device)
-        _lib.call('digat_user_active_rows', Au.data_ptr(), _ptr(share), ci.data_ptr(), Mc.data_ptr(), act.data_ptr(), B, n,
-                  self.max_history_num, self.category_num, _stream())
-        return self._row_lists(act)
+        pooled = torch.empty((B, n), dtype=torch.uint8, device=Au.device)
+        _lib.call('digat_user_active_rows', Au.data_ptr(), _ptr(share), ci.data_ptr(), Mc.data_ptr(), act.data_ptr(),
+                  pooled.data_ptr(), B, n, self.max_history_num, self.category_num, _stream())
+        lists = self._row_lists(act)
+        # 4th entry: the rows the user context pools -- all that the LAST layer has to produce
+        return None if lists is None else lists + (pooled,)
 
     @staticmethod
     def _row_lists(act):

@@ -120,8 +120,9 @@ int digat_debug_set_layer_mode(int mode);
  * bool, 0 = node whose output nothing can observe (digat_user_active_rows).  Its P row is never read for arithmetic
  * (it may be uninitialised: digat_linear_tf32x3 with c_row_index skips it), none of its edges is evaluated and its
  * output row is left untouched (neither X nor Y of that row is accessed; every later consumer -- the next layer with
- * the same flags, the pooling kernels with their masks -- skips it too).  No active node may have an edge to an
- * inactive one.  With row_active, Yc [M_act, D] and
+ * the same flags, the pooling kernels with their masks -- skips it too).  An inactive node that an active one has an
+ * edge to must have a valid P row (it is still a neighbour): that is the last-layer case, where only the rows a
+ * context pools are evaluated.  With row_active, Yc [M_act, D] and
  * row_pos [B*n] int32 (both or neither): the output row of active node row r is ALSO written to Yc[row_pos[r]], the
  * compact operand of the next layer's projection (digat_linear_tf32x3 with c_row_index), saving a gather pass.
  * --------------------------------------------------------------------------------------------------------- */
@@ -137,9 +138,12 @@ int digat_graph_layer_supports_row_active(int n, int D, int B);
  * pooled, graphEncoders.py:125; or history slot i belongs to a bucket c = cidx[i] with cmask[c] == 0 while some other
  * bucket is unmasked -- with every bucket masked the softmax is uniform and reads them all).
  * A graph with an edge-less row keeps every node.  adj [*,n,n] read through adj_index [G] when given (then cidx
- * [*,H] int64 is read through the same index); cmask [G,S] is per graph. */
+ * [*,H] int64 is read through the same index); cmask [G,S] is per graph.
+ * pooled [G,n] (optional): 1 = the user context pools this node's row directly.  After the LAST layer only those rows
+ * are consumed, so they can serve as that layer's row_active (the other active nodes are still projected: they are
+ * neighbours). */
 int digat_user_active_rows(const uint8_t* adj, const int32_t* adj_index, const int64_t* cidx, const uint8_t* cmask,
-                           uint8_t* active, int64_t G, int n, int H, int S, void* stream);
+                           uint8_t* active, uint8_t* pooled, int64_t G, int n, int H, int S, void* stream);
 /* The same for news graphs: a node is kept iff another node has an edge to it, or the news context reads it
  * (graphEncoders.py:109-114): node 0 (the local context), mask[g,i] != 0 (pooled by the candidate attention), or every
  * mask entry of the graph is 0 (uniform softmax).  adj [G,n,n], mask [G,n], active [G,n]. */

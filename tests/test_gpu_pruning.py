@@ -46,10 +46,16 @@ def test_active_rows_kernel_matches_rule():
     t = lambda x: torch.from_numpy(x).to(dev)
     act = torch.empty((G, H + C), dtype=torch.uint8, device=dev)
     adj_d, cidx_d, cmask_d = t(adj), t(cidx), t(cmask)            # keep the device tensors alive across the calls
+    pooled = torch.empty_like(act)
     _lib.call('digat_user_active_rows', adj_d.data_ptr(), 0, cidx_d.data_ptr(), cmask_d.data_ptr(), act.data_ptr(),
-              G, H + C, H, C + 1, torch.cuda.current_stream().cuda_stream)
+              pooled.data_ptr(), G, H + C, H, C + 1, torch.cuda.current_stream().cuda_stream)
     want = _active_rule(adj, cidx, cmask, H)
     assert np.array_equal(act.cpu().numpy(), want)
+    pl = pooled.cpu().numpy()                              # pooled rows: history slots of visible buckets; subset of active
+    assert not pl[:, H:].any() and (pl <= want).all()
+    for g_ in (0, 1, 2, 3, 7, 8, 20):
+        vis = cmask[g_].any()
+        assert np.array_equal(pl[g_, :H], np.array([(not vis) or cmask[g_, cidx[g_, i]] for i in range(H)], dtype=np.uint8))
     assert want[5].all() and want[6, 40] == 1 and want[7, :H].all() and want[8, :H].all()
     assert 0.2 < want.mean() < 0.8                       # MIND-shaped graphs: roughly half of the nodes are prunable
     # indexed form: graphs and segment ids per behaviour, masks per pair
@@ -57,7 +63,7 @@ def test_active_rows_kernel_matches_rule():
     act2 = torch.empty((333, H + C), dtype=torch.uint8, device=dev)
     cm2 = cmask_d[idx.long()].contiguous()
     _lib.call('digat_user_active_rows', adj_d.data_ptr(), idx.data_ptr(), cidx_d.data_ptr(), cm2.data_ptr(),
-              act2.data_ptr(), 333, H + C, H, C + 1, torch.cuda.current_stream().cuda_stream)
+              act2.data_ptr(), 0, 333, H + C, H, C + 1, torch.cuda.current_stream().cuda_stream)
     assert np.array_equal(act2.cpu().numpy(), want[idx.cpu().numpy()])
 
 

@@ -24,7 +24,7 @@ X = torch.randn(B, n, D, device=dev, generator=g)
 P = torch.randn(B * n, 3 * D, device=dev, generator=g)
 a = torch.randn(D, device=dev, generator=g) * 0.1
 act = torch.empty((B, n), dtype=torch.uint8, device=dev)
-_lib.call('digat_user_active_rows', adj.data_ptr(), 0, cidx.data_ptr(), cmask.data_ptr(), act.data_ptr(), B, n, 50, 19, 0)
+_lib.call('digat_user_active_rows', adj.data_ptr(), 0, cidx.data_ptr(), cmask.data_ptr(), act.data_ptr(), 0, B, n, 50, 19, 0)
 torch.cuda.synchronize()
 print('B=%d n=%d edges/graph %.0f active rows/graph %.1f active edges/graph %.0f' % (
     B, n, adj.sum().item() / B, act.sum().item() / B, (adj & (act[:, :, None] != 0)).sum().item() / B))
