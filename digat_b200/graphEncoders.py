@@ -45,6 +45,17 @@ def _boolc(t, name):
 
 
 # ------------------------------------------------------------------------------------------- thin op wrappers
+_PINNED = {}
+
+
+def _pinned_ints(n):
+    """A small reusable pinned int32 buffer (cudaHostAlloc per call would cost more than the copy it serves)."""
+    buf = _PINNED.get(n)
+    if buf is None:
+        buf = _PINNED[n] = torch.empty(n, dtype=torch.int32).pin_memory()
+    return buf
+
+
 class PackedWeight:
     """A projection weight in kernel layout: fp32 [N,K] (nn.Linear layout) plus, when the tcgen05 GEMM can take it
     (N % 80 == 0), its two TF32 planes hi = rna_tf32(W), lo = rna_tf32(W - hi) (digat_split_tf32)."""
@@ -278,7 +289,7 @@ class DIGAT(GraphEncoder):
     def _user_ctx(self, w, Xu, cmask, cidx, c_n, j, ctx_in=None, src_index=None, seg_prune=None):
         """j = index of this call (0 = initial context, i+1 = after layer i).  Returns (context, k3 of user layer j or
         None).  src_index [B] int32: Xu / cidx are per-behaviour tables and row b uses entry src_index[b].
-        seg_prune = (rows [M_live] int32, pos [B*S] int32) from _live_segments: featureAffine runs on the topic
+        seg_prune = (rows [M_live] int32, pos [B*S] int32) from _segment_flags / compact_flags: featureAffine runs on the topic
         embeddings the user-level attention can see only (the segment kernel writes them compactly)."""
         nu, D = Xu.shape[1], Xu.shape[2]
         B = c_n.shape[0]
@@ -301,24 +312,12 @@ class DIGAT(GraphEncoder):
             Fa = linear(T, w['fa_W'], w['fa_b'])                                  # featureAffine(T)  [B*S, D]
         return attention_pool_fwd(Fa.view(B, S, D), v2, cmask, resid=T, add_in=ctx_in), k3_next
 
-    def _live_segments(self, Mc):
-        """Topic embeddings the user-level attention can see: cmask != 0, or every segment of a fully masked row (uniform
-        softmax).  Returns (flat ids int32 [M_live], pos int32 [B*S]) or None (small batch / pruning off / nothing to skip)."""
-        B, S = Mc.shape
-        if not self.prune_user_nodes or B * S < TENSOR_CORE_MIN_ROWS:
-            return None
-        live = (Mc | ~Mc.any(dim=1, keepdim=True)).view(-1)
-        rows = live.nonzero().squeeze(1).to(torch.int32)
-        if rows.shape[0] == B * S:
-            return None
-        return rows, torch.cumsum(live, 0, dtype=torch.int32) - 1
-
     def _layer(self, w, g, i, X, adj, ctx_other, k3=None, share=None, adj_index=None, prune=None, A_c=None,
                want_compact=False):
         """k3 [B,D] (possibly a column view): ffn3(context of the other graph) + bias, computed here when None.
         share [B] int32 (layer 0 of the scoring path): X [n_src,n,D] holds one graph per BEHAVIOUR and pair b uses
         graph share[b]; the projection then runs once per behaviour and k3 is added inside the fused kernel.
-        prune = (row_active [B,n] uint8, rows [M_act] int32, row_pos [B*n] int32) from _active_*_rows: only the listed
+        prune = (row_active [B,n] uint8, rows [M_act] int32, row_pos [B*n] int32[, pooled]) from _lists: only the listed
         node rows are projected (compact operand A_c, or gathered here when it is None; scattered back into the dense P)
         and evaluated by the layer kernel.  want_compact: the layer kernel also writes the compact operand of the NEXT
         layer.  Returns (Y [B,n,D], Yc [M_act,D] or None)."""
@@ -352,34 +351,25 @@ class DIGAT(GraphEncoder):
 
     prune_user_nodes = True      # inference only; switch off to evaluate every node of every user graph
 
-    def _active_user_rows(self, Au, Mc, ci, share):
+    # ---- pruning lists.  The flags are computed by kernels (no synchronisation); compact_flags turns any number of flag
+    # arrays into index lists with ONE host synchronisation (a single nonzero() over their concatenation).
+    def _user_flags(self, Au, Mc, ci, adj_index):
         """Node pruning of the user graph at inference (digat_user_active_rows): nodes that no other node attends to and
         no context pools -- in MIND-shaped data the padded history slots and the categories a user never clicked, about
         half of the 68 nodes -- cannot influence (news_ctx, user_ctx); their rows are neither projected nor evaluated.
-        Returns (row_active [B,n] uint8, flat row ids int32 [M_act], row_pos int32 [B*n]) or None when unsupported /
-        nothing to prune; row_pos[r] = position of node row r in the compact list (valid where active).
-        The nonzero() is a host synchronisation: M_act is a launch parameter of the projection GEMM."""
+        Au / ci may be tables read through adj_index [B] int32.  Returns (active [B,n], pooled [B,n]) uint8 or None when
+        unsupported / switched off (small batches stay on the exact-fp32 GEMM, which has no row scatter)."""
         B, n = Mc.shape[0], Au.shape[1]
         if not self.prune_user_nodes or B * n < TENSOR_CORE_MIN_ROWS or \
            not _lib.load().digat_graph_layer_supports_row_active(n, self.news_embedding_dim, B):
-            return None          # (small batches stay on the exact-fp32 GEMM, which has no row scatter)
+            return None
         act = torch.empty((B, n), dtype=torch.uint8, device=Au.device)
         pooled = torch.empty((B, n), dtype=torch.uint8, device=Au.device)
-        _lib.call('digat_user_active_rows', Au.data_ptr(), _ptr(share), ci.data_ptr(), Mc.data_ptr(), act.data_ptr(),
+        _lib.call('digat_user_active_rows', Au.data_ptr(), _ptr(adj_index), ci.data_ptr(), Mc.data_ptr(), act.data_ptr(),
                   pooled.data_ptr(), B, n, self.max_history_num, self.category_num, _stream())
-        lists = self._row_lists(act)
-        # 4th entry: the rows the user context pools -- all that the LAST layer has to produce
-        return None if lists is None else lists + (pooled,)
+        return act, pooled
 
-    @staticmethod
-    def _row_lists(act):
-        flat = act.view(-1)
-        rows = flat.nonzero().squeeze(1).to(torch.int32)
-        if rows.shape[0] == flat.shape[0]:
-            return None
-        return act, rows, torch.cumsum(flat, 0, dtype=torch.int32) - 1
-
-    def _active_news_rows(self, An, Mn):
+    def _news_flags(self, An, Mn):
         """The same for the news graph (digat_news_active_rows): the unused BFS slots of a SAG (isolated, masked out of the
         candidate attention) are not projected."""
         B, n = Mn.shape
@@ -388,7 +378,57 @@ class DIGAT(GraphEncoder):
             return None
         act = torch.empty((B, n), dtype=torch.uint8, device=An.device)
         _lib.call('digat_news_active_rows', An.data_ptr(), Mn.data_ptr(), act.data_ptr(), B, n, _stream())
-        return self._row_lists(act)
+        return act
+
+    def _segment_flags(self, Mc):
+        """Topic embeddings the user-level attention can see: cmask != 0, or every segment of a fully masked row (uniform
+        softmax).  [B,S] bool, or None (small batch / pruning off)."""
+        B, S = Mc.shape
+        if not self.prune_user_nodes or B * S < TENSOR_CORE_MIN_ROWS:
+            return None
+        return Mc | ~Mc.any(dim=1, keepdim=True)
+
+    @staticmethod
+    def compact_flags(flag_list):
+        """[flags or None, ...] -> [(ids int32 [count], pos int32 [numel]) or None, ...]: ids = flat positions of the
+        nonzero flags, pos[r] = rank of position r among them (valid where the flag is set).  One nonzero() over the
+        concatenation = one host synchronisation for all lists; the counts travel in the same round trip."""
+        live = [f for f in flag_list if f is not None]
+        if not live:
+            return [None] * len(flag_list)
+        flat = [f.reshape(-1).to(torch.uint8) for f in live]
+        sizes = [f.shape[0] for f in flat]
+        allf = torch.cat(flat) if len(flat) > 1 else flat[0]
+        csum = torch.cumsum(allf, 0, dtype=torch.int32)
+        ends = torch.tensor([sum(sizes[:k + 1]) - 1 for k in range(len(sizes))], device=allf.device)
+        counts_host = _pinned_ints(len(sizes))
+        counts_host.copy_(csum.index_select(0, ends), non_blocking=True)        # lands before nonzero()'s own sync returns
+        idx = allf.nonzero().squeeze(1)                                          # the synchronisation
+        cum = counts_host.tolist()
+        out, k, lo_idx, lo_pos, base = [], 0, 0, 0, 0
+        for f in flag_list:
+            if f is None:
+                out.append(None)
+                continue
+            hi_idx = cum[k]
+            ids = (idx[lo_idx:hi_idx] - lo_pos).to(torch.int32)
+            pos = csum[lo_pos:lo_pos + sizes[k]] - (1 + base)
+            out.append((ids, pos))
+            base, lo_idx, lo_pos, k = hi_idx, hi_idx, lo_pos + sizes[k], k + 1
+        return out
+
+    def _lists(self, uf, nf, sf):
+        """(user flags (active, pooled) | None, news flags | None, segment flags | None) -> (prune, prune_n, seg_prune)
+        as consumed by _layer / _user_ctx; a list that would keep every row is dropped (None)."""
+        cu, cn, cs = self.compact_flags([None if uf is None else uf[0], nf, sf])
+        prune = prune_n = seg_prune = None
+        if cu is not None and cu[0].shape[0] < uf[0].numel():
+            prune = (uf[0], cu[0], cu[1], uf[1])        # 4th entry: the rows the user context pools (last layer)
+        if cn is not None and cn[0].shape[0] < nf.numel():
+            prune_n = (nf, cn[0], cn[1])
+        if cs is not None and cs[0].shape[0] < sf.numel():
+            seg_prune = cs
+        return prune, prune_n, seg_prune
 
     def _err_flag(self, device):
         f = getattr(self, '_err', None)
@@ -466,15 +506,14 @@ class DIGAT(GraphEncoder):
         share [B] int32 (scoring path): Xu / Au / ci are per-BEHAVIOUR tables and pair b uses entry share[b]; the
         user graph's layer-0 projection and node build then run once per behaviour (results are bit-identical).
         lists = (prune, prune_n, seg_prune) when the caller prepared the pruning lists already (scoring.Scorer does, on a
-        side stream); otherwise they are computed here (three nonzero() host synchronisations)."""
+        side stream); otherwise they are computed here (one nonzero() host synchronisation)."""
         if c_n is None:
             c_n = self._news_ctx(w, Xn, Mn)
         if lists is not None:
             prune, prune_n, seg_prune = lists
         else:
-            seg_prune = self._live_segments(Mc)
-            prune = self._active_user_rows(Au, Mc, ci, share)
-            prune_n = self._active_news_rows(An, Mn)
+            prune, prune_n, seg_prune = self._lists(self._user_flags(Au, Mc, ci, share), self._news_flags(An, Mn),
+                                                    self._segment_flags(Mc))
         c_u, k3u = self._user_ctx(w, Xu, Mc, ci, c_n, 0, src_index=share, seg_prune=seg_prune)
         if share is not None:
             ci = ci.index_select(0, share.long())      # [B,H] int64: from layer 1 on every pair owns its user nodes

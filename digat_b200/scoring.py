@@ -99,29 +99,41 @@ class Scorer:
     # impression boundaries and the pruning lists are nonzero() calls, i.e. stream synchronisations) and depends on the
     # batch's integer/bool inputs only; score_prepared then launches the encoder without a single synchronisation.
     # score_host_batches runs prepare for batch k+1 on a side stream while batch k is encoded.
-    def _prune_lists(self, prep):
-        enc = self.enc
-        with torch.no_grad():
-            prep['seg_prune'] = enc._live_segments(prep['Mc'])
-            prep['prune'] = enc._active_user_rows(prep['Au'], prep['Mc'], prep['ci'], prep['share'])
-            prep['prune_n'] = enc._active_news_rows(prep['An'], prep['Mn'])
-        return prep
-
     def prepare_resident(self, beh_idx, news_idx, share_user_graphs=True):
         """beh_idx, news_idx: [B] device tensors (any integer dtype).  Everything else is already in HBM."""
-        nl, bl = news_idx.long(), beh_idx.long()
-        prep = dict(news=news_idx.to(torch.int32), An=self.news_graph.index_select(0, nl),
-                    Mn=self.news_mask.index_select(0, nl), share=None)
-        if share_user_graphs and bl.shape[0] >= 2:
-            ub, inv = torch.unique_consecutive(bl, return_inverse=True)
-            prep['share'] = inv.to(torch.int32)
-            prep['Mc'] = self.cmask.index_select(0, bl)                  # masks stay per pair
-            bl = ub                                                      # node tables, graphs, segment ids: per behaviour
-        else:
-            prep['Mc'] = self.cmask.index_select(0, bl)
-        prep.update(hist=self.history.index_select(0, bl), Au=self.user_graph.index_select(0, bl),
-                    ci=self.cidx.index_select(0, bl))
-        return self._prune_lists(prep)
+        enc = self.enc
+        with torch.no_grad():
+            nl, bl = news_idx.long(), beh_idx.long()
+            prep = dict(news=news_idx.to(torch.int32), An=self.news_graph.index_select(0, nl),
+                        Mn=self.news_mask.index_select(0, nl), Mc=self.cmask.index_select(0, bl), share=None)
+            first = None
+            if share_user_graphs and bl.shape[0] >= 2:
+                first = torch.ones(bl.shape[0], dtype=torch.bool, device=bl.device)
+                first[1:] = bl[1:] != bl[:-1]                            # impression boundaries in the ordered pair list
+                prep['share'] = (torch.cumsum(first, 0) - 1).to(torch.int32)
+            # flags straight from the resident per-behaviour tables (read through the behaviour index): no sync yet
+            uf = enc._user_flags(self.user_graph, prep['Mc'], self.cidx, bl.to(torch.int32))
+            nf, sf = enc._news_flags(prep['An'], prep['Mn']), enc._segment_flags(prep['Mc'])
+            # ONE synchronisation for the impression boundaries and all three pruning lists
+            comp = enc.compact_flags([first, None if uf is None else uf[0], nf, sf])
+            if first is not None:
+                bl = bl.index_select(0, comp[0][0].long())               # one row per behaviour: node tables, graphs, segment ids
+            prep.update(hist=self.history.index_select(0, bl), Au=self.user_graph.index_select(0, bl),
+                        ci=self.cidx.index_select(0, bl))
+            prep['prune'], prep['prune_n'], prep['seg_prune'] = self._pack_lists(uf, nf, sf, comp[1:])
+        return prep
+
+    @staticmethod
+    def _pack_lists(uf, nf, sf, comp):
+        cu, cn, cs = comp
+        prune = prune_n = seg_prune = None
+        if cu is not None and cu[0].shape[0] < uf[0].numel():
+            prune = (uf[0], cu[0], cu[1], uf[1])
+        if cn is not None and cn[0].shape[0] < nf.numel():
+            prune_n = (nf, cn[0], cn[1])
+        if cs is not None and cs[0].shape[0] < sf.numel():
+            seg_prune = cs
+        return prune, prune_n, seg_prune
 
     def prepare_device_batch(self, user_title_index, user_graph, user_category_mask, user_category_indices, news_ID,
                              news_graph, news_graph_mask, share_user_graphs=True):
@@ -131,17 +143,25 @@ class Scorer:
         Consecutive rows with the same clicked-news history have the same user graph / category tensors (they are
         functions of the history, MIND_corpus.py:143-176), so they are detected here and encoded through the
         shared-user-graph path (bit-identical results)."""
-        hist = user_title_index.to(torch.int32)
-        prep = dict(news=news_ID.to(torch.int32), An=news_graph, Mn=news_graph_mask, Mc=user_category_mask, share=None,
-                    hist=hist, Au=user_graph, ci=user_category_indices)
-        if share_user_graphs and hist.shape[0] >= 2:
-            first = torch.ones(hist.shape[0], dtype=torch.bool, device=hist.device)
-            first[1:] = (hist[1:] != hist[:-1]).any(dim=1)
-            prep['share'] = (torch.cumsum(first, 0) - 1).to(torch.int32)
-            rows = first.nonzero(as_tuple=True)[0]
-            prep.update(hist=hist.index_select(0, rows), Au=user_graph.index_select(0, rows),
-                        ci=user_category_indices.index_select(0, rows))
-        return self._prune_lists(prep)
+        enc = self.enc
+        with torch.no_grad():
+            hist = user_title_index.to(torch.int32)
+            prep = dict(news=news_ID.to(torch.int32), An=news_graph, Mn=news_graph_mask, Mc=user_category_mask, share=None,
+                        hist=hist, Au=user_graph, ci=user_category_indices)
+            first = None
+            if share_user_graphs and hist.shape[0] >= 2:
+                first = torch.ones(hist.shape[0], dtype=torch.bool, device=hist.device)
+                first[1:] = (hist[1:] != hist[:-1]).any(dim=1)
+                prep['share'] = (torch.cumsum(first, 0) - 1).to(torch.int32)
+            uf = enc._user_flags(user_graph, user_category_mask, user_category_indices, None)     # per-pair graphs
+            nf, sf = enc._news_flags(news_graph, news_graph_mask), enc._segment_flags(user_category_mask)
+            comp = enc.compact_flags([first, None if uf is None else uf[0], nf, sf])              # the one synchronisation
+            if first is not None:
+                rows = comp[0][0].long()
+                prep.update(hist=hist.index_select(0, rows), Au=user_graph.index_select(0, rows),
+                            ci=user_category_indices.index_select(0, rows))
+            prep['prune'], prep['prune_n'], prep['seg_prune'] = self._pack_lists(uf, nf, sf, comp[1:])
+        return prep
 
     def score_prepared(self, prep):
         """Gathers + encoder + logits of a prepared batch: kernel launches only, no host synchronisation."""
@@ -218,7 +238,9 @@ def _pipelined(scorer: Scorer, items, prepare, results):
     main = torch.cuda.current_stream(scorer.dev)
     side = getattr(scorer, '_copy_stream', None)
     if side is None:
-        side = scorer._copy_stream = torch.cuda.Stream(device=scorer.dev)
+        # high priority: the staging kernels are tiny and the host waits for them (one nonzero() per batch); they must not
+        # queue behind the encoder's long kernels
+        side = scorer._copy_stream = torch.cuda.Stream(device=scorer.dev, priority=-1)
 
     def stage(item):
         # No wait on the main stream here: staging depends on the batch's own inputs only, and its tensors are handed to
