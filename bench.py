@@ -197,20 +197,29 @@ def main():
         return ((pair_beh[s * args.batch:(s + 1) * args.batch], pair_news[s * args.batch:(s + 1) * args.batch])
                 for s in range(s0, s1))
 
-    scoring.score_resident_batches(scorer, index_batches(0, args.warmup))
+    # The clock sampler (an nvidia-smi process) is started BEFORE the warm-up and must have delivered its first sample
+    # before the timed region begins: its start-up (NVML initialisation) stalls kernel launches for tens of milliseconds,
+    # which used to land inside the first timed steps every few runs (seen as 2-3x slower `value` at unchanged `e2e`).
     sampler = ClockSampler(local_rank)
     sampler.start()
+    scoring.score_resident_batches(scorer, index_batches(0, args.warmup))
+    t_wait = time.time()
+    while not sampler.rows and time.time() - t_wait < 10.0:
+        time.sleep(0.05)
     barrier()
     _lib.reset_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     # the public pipelined driver: batch k+1's index preparation (impression boundaries, pruning lists: the only host
     # synchronisations of a step) runs on a side stream while batch k is encoded
-    scoring.score_resident_batches(scorer, index_batches(args.warmup, total_steps))
+    step_events = []
+    scoring.score_resident_batches(scorer, index_batches(args.warmup, total_steps), events=step_events)
     e1.record()
     barrier()
     launches = _lib.launch_count()
     ms_resident = max_over_ranks(e0.elapsed_time(e1))
+    marks = [e0] + step_events
+    step_ms = sorted(marks[k].elapsed_time(marks[k + 1]) for k in range(len(marks) - 1))
     scorer.check_index_errors()
 
     # ---------------------------------------------------------------- end-to-end path (host buffers)
@@ -267,6 +276,7 @@ def main():
         line = {
             'metric': 'impressions_scored_per_sec', 'value': value, 'unit': 'pairs/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_resident / args.steps,
+            'step_ms': {'min': step_ms[0], 'median': step_ms[len(step_ms) // 2], 'max': step_ms[-1]},
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': args.workload, 'pairs_per_step_per_gpu': args.batch, 'SAG_neighbors': cfg.SAG_neighbors,
                        'SAG_hops': cfg.SAG_hops, 'news_graph_size': n_n, 'user_graph_size': n_u, 'graph_depth': L,

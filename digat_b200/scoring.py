@@ -232,7 +232,7 @@ def _tensors_of(obj):
             yield from _tensors_of(v)
 
 
-def _pipelined(scorer: Scorer, items, prepare, results):
+def _pipelined(scorer: Scorer, items, prepare, results, events=None):
     """Runs ``prepare(item)`` for item k+1 on a side stream (copies, index work and their host synchronisations) while
     item k is encoded on the current stream."""
     main = torch.cuda.current_stream(scorer.dev)
@@ -265,6 +265,10 @@ def _pipelined(scorer: Scorer, items, prepare, results):
         if results is not None:
             results[k].copy_(scores, non_blocking=True)
         outs.append(scores)
+        if events is not None:                                    # per-batch completion events (diagnostics)
+            ev_done = torch.cuda.Event(enable_timing=True)
+            ev_done.record(main)
+            events.append(ev_done)
         nxt = next(it, None)
         staged = stage(nxt) if nxt is not None else None          # batch k+1 is staged while batch k runs
         k += 1
@@ -281,10 +285,11 @@ def score_host_batches(scorer: Scorer, host_batches, results=None, share_user_gr
                                                              share_user_graphs=share_user_graphs), results)
 
 
-def score_resident_batches(scorer: Scorer, index_batches, results=None, share_user_graphs=True):
+def score_resident_batches(scorer: Scorer, index_batches, results=None, share_user_graphs=True, events=None):
     """The same pipeline for the resident path: ``index_batches`` yields (behaviour index, news id) device tensors."""
     return _pipelined(scorer, index_batches,
-                      lambda ib: scorer.prepare_resident(ib[0], ib[1], share_user_graphs=share_user_graphs), results)
+                      lambda ib: scorer.prepare_resident(ib[0], ib[1], share_user_graphs=share_user_graphs), results,
+                      events)
 
 
 def compute_scores(scorer: Scorer, corpus, batch_size: int, rank: int = 0, world_size: int = 1):
