@@ -46,14 +46,27 @@ def _boolc(t, name):
 
 # ------------------------------------------------------------------------------------------- thin op wrappers
 _PINNED = {}
+_ENDS = {}
 
 
 def _pinned_ints(n):
-    """A small reusable pinned int32 buffer (cudaHostAlloc per call would cost more than the copy it serves)."""
-    buf = _PINNED.get(n)
-    if buf is None:
-        buf = _PINNED[n] = torch.empty(n, dtype=torch.int32).pin_memory()
-    return buf
+    """A small pinned int32 buffer from a free list (cudaHostAlloc per call would cost more than the copy it serves;
+    several may be in flight: one per staged batch)."""
+    free = _PINNED.setdefault(n, [])
+    return free.pop() if free else torch.empty(n, dtype=torch.int32).pin_memory()
+
+
+def _release_pinned(buf):
+    _PINNED.setdefault(buf.shape[0], []).append(buf)
+
+
+def _ends_tensor(sizes, device):
+    """Device tensor of the last flat position of each list (cached per size tuple: building it is a host->device copy)."""
+    key = (sizes, str(device))
+    t = _ENDS.get(key)
+    if t is None:
+        t = _ENDS[key] = torch.tensor([sum(sizes[:k + 1]) - 1 for k in range(len(sizes))], device=device)
+    return t
 
 
 class PackedWeight:
@@ -389,33 +402,55 @@ class DIGAT(GraphEncoder):
         return Mc | ~Mc.any(dim=1, keepdim=True)
 
     @staticmethod
-    def compact_flags(flag_list):
-        """[flags or None, ...] -> [(ids int32 [count], pos int32 [numel]) or None, ...]: ids = flat positions of the
-        nonzero flags, pos[r] = rank of position r among them (valid where the flag is set).  One nonzero() over the
-        concatenation = one host synchronisation for all lists; the counts travel in the same round trip."""
+    def compact_begin(flag_list):
+        """First half of the flag compaction: enqueue (no host synchronisation) the prefix sums over the concatenated
+        flags and an asynchronous copy of the per-list counts to pinned memory, and record an event behind it.
+        Returns a state for compact_finish, or None when every entry is None."""
         live = [f for f in flag_list if f is not None]
         if not live:
-            return [None] * len(flag_list)
+            return None
         flat = [f.reshape(-1).to(torch.uint8) for f in live]
         sizes = [f.shape[0] for f in flat]
         allf = torch.cat(flat) if len(flat) > 1 else flat[0]
         csum = torch.cumsum(allf, 0, dtype=torch.int32)
-        ends = torch.tensor([sum(sizes[:k + 1]) - 1 for k in range(len(sizes))], device=allf.device)
+        ends = _ends_tensor(tuple(sizes), allf.device)
         counts_host = _pinned_ints(len(sizes))
-        counts_host.copy_(csum.index_select(0, ends), non_blocking=True)        # lands before nonzero()'s own sync returns
-        idx = allf.nonzero().squeeze(1)                                          # the synchronisation
-        cum = counts_host.tolist()
-        out, k, lo_idx, lo_pos, base = [], 0, 0, 0, 0
-        for f in flag_list:
+        counts_host.copy_(csum.index_select(0, ends), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return dict(flags=flag_list, sizes=sizes, allf=allf, csum=csum, counts=counts_host, event=ev)
+
+    @staticmethod
+    def compact_finish(state, n_lists=None):
+        """Second half: wait for the counts (the only host synchronisation: an event recorded right behind the prefix
+        sums, so it does not wait for anything enqueued afterwards) and build, with launches only,
+        [(ids int32 [count], pos int32 [numel]) or None, ...]: ids = flat positions of the nonzero flags, pos[r] = rank
+        of position r among them (valid where the flag is set)."""
+        if state is None:
+            return [None] * (n_lists or 0)
+        state['event'].synchronize()
+        cum = state['counts'].tolist()
+        _release_pinned(state['counts'])
+        allf, csum, sizes = state['allf'], state['csum'], state['sizes']
+        out, k, lo_pos, base = [], 0, 0, 0
+        for f in state['flags']:
             if f is None:
                 out.append(None)
                 continue
-            hi_idx = cum[k]
-            ids = (idx[lo_idx:hi_idx] - lo_pos).to(torch.int32)
-            pos = csum[lo_pos:lo_pos + sizes[k]] - (1 + base)
-            out.append((ids, pos))
-            base, lo_idx, lo_pos, k = hi_idx, hi_idx, lo_pos + sizes[k], k + 1
+            count, size = cum[k] - base, sizes[k]
+            pos = csum[lo_pos:lo_pos + size] - (1 + base)
+            # scatter r -> ids[pos[r]] for the set flags; the others go to a dump slot behind the list
+            dest = torch.where(allf[lo_pos:lo_pos + size] != 0, pos, count).long()
+            ids = torch.empty(count + 1, dtype=torch.int32, device=allf.device)
+            ids.scatter_(0, dest, torch.arange(size, dtype=torch.int32, device=allf.device))
+            out.append((ids[:count], pos))
+            base, lo_pos, k = cum[k], lo_pos + size, k + 1
         return out
+
+    @classmethod
+    def compact_flags(cls, flag_list):
+        """compact_begin + compact_finish back to back (one host synchronisation)."""
+        return cls.compact_finish(cls.compact_begin(flag_list), len(flag_list))
 
     def _lists(self, uf, nf, sf):
         """(user flags (active, pooled) | None, news flags | None, segment flags | None) -> (prune, prune_n, seg_prune)

@@ -99,8 +99,9 @@ class Scorer:
     # impression boundaries and the pruning lists are nonzero() calls, i.e. stream synchronisations) and depends on the
     # batch's integer/bool inputs only; score_prepared then launches the encoder without a single synchronisation.
     # score_host_batches runs prepare for batch k+1 on a side stream while batch k is encoded.
-    def prepare_resident(self, beh_idx, news_idx, share_user_graphs=True):
-        """beh_idx, news_idx: [B] device tensors (any integer dtype).  Everything else is already in HBM."""
+    def begin_resident(self, beh_idx, news_idx, share_user_graphs=True):
+        """First half of a batch's preparation: launches only.  beh_idx, news_idx: [B] device tensors (any integer
+        dtype); everything else is already in HBM."""
         enc = self.enc
         with torch.no_grad():
             nl, bl = news_idx.long(), beh_idx.long()
@@ -111,33 +112,15 @@ class Scorer:
                 first = torch.ones(bl.shape[0], dtype=torch.bool, device=bl.device)
                 first[1:] = bl[1:] != bl[:-1]                            # impression boundaries in the ordered pair list
                 prep['share'] = (torch.cumsum(first, 0) - 1).to(torch.int32)
-            # flags straight from the resident per-behaviour tables (read through the behaviour index): no sync yet
+            # flags straight from the resident per-behaviour tables (read through the behaviour index)
             uf = enc._user_flags(self.user_graph, prep['Mc'], self.cidx, bl.to(torch.int32))
             nf, sf = enc._news_flags(prep['An'], prep['Mn']), enc._segment_flags(prep['Mc'])
-            # ONE synchronisation for the impression boundaries and all three pruning lists
-            comp = enc.compact_flags([first, None if uf is None else uf[0], nf, sf])
-            if first is not None:
-                bl = bl.index_select(0, comp[0][0].long())               # one row per behaviour: node tables, graphs, segment ids
-            prep.update(hist=self.history.index_select(0, bl), Au=self.user_graph.index_select(0, bl),
-                        ci=self.cidx.index_select(0, bl))
-            prep['prune'], prep['prune_n'], prep['seg_prune'] = self._pack_lists(uf, nf, sf, comp[1:])
-        return prep
+            state = enc.compact_begin([first, None if uf is None else uf[0], nf, sf])
+        return dict(kind='resident', prep=prep, bl=bl, first=first, uf=uf, nf=nf, sf=sf, state=state)
 
-    @staticmethod
-    def _pack_lists(uf, nf, sf, comp):
-        cu, cn, cs = comp
-        prune = prune_n = seg_prune = None
-        if cu is not None and cu[0].shape[0] < uf[0].numel():
-            prune = (uf[0], cu[0], cu[1], uf[1])
-        if cn is not None and cn[0].shape[0] < nf.numel():
-            prune_n = (nf, cn[0], cn[1])
-        if cs is not None and cs[0].shape[0] < sf.numel():
-            seg_prune = cs
-        return prune, prune_n, seg_prune
-
-    def prepare_device_batch(self, user_title_index, user_graph, user_category_mask, user_category_indices, news_ID,
-                             news_graph, news_graph_mask, share_user_graphs=True):
-        """The 7 tensors of one reference DataLoader batch (util.py:56), already on the device.
+    def begin_device_batch(self, user_title_index, user_graph, user_category_mask, user_category_indices, news_ID,
+                           news_graph, news_graph_mask, share_user_graphs=True):
+        """The same for the 7 tensors of one reference DataLoader batch (util.py:56), already on the device.
 
         The DataLoader repeats the user tensors for every candidate of an impression (MIND_dataset.py:97-102).
         Consecutive rows with the same clicked-news history have the same user graph / category tensors (they are
@@ -155,13 +138,45 @@ class Scorer:
                 prep['share'] = (torch.cumsum(first, 0) - 1).to(torch.int32)
             uf = enc._user_flags(user_graph, user_category_mask, user_category_indices, None)     # per-pair graphs
             nf, sf = enc._news_flags(news_graph, news_graph_mask), enc._segment_flags(user_category_mask)
-            comp = enc.compact_flags([first, None if uf is None else uf[0], nf, sf])              # the one synchronisation
-            if first is not None:
+            state = enc.compact_begin([first, None if uf is None else uf[0], nf, sf])
+        return dict(kind='device', prep=prep, first=first, uf=uf, nf=nf, sf=sf, state=state)
+
+    def finish_prepare(self, begun):
+        """Second half: ONE host wait (an event recorded right behind the flag kernels, so nothing enqueued after
+        begin_* delays it) for the counts of the impression boundaries and of the three pruning lists; the rest is launches."""
+        enc, prep = self.enc, begun['prep']
+        with torch.no_grad():
+            comp = enc.compact_finish(begun['state'], 4)
+            if begun['kind'] == 'resident':
+                bl = begun['bl']
+                if begun['first'] is not None:
+                    bl = bl.index_select(0, comp[0][0].long())           # one row per behaviour: node tables, graphs, segment ids
+                prep.update(hist=self.history.index_select(0, bl), Au=self.user_graph.index_select(0, bl),
+                            ci=self.cidx.index_select(0, bl))
+            elif begun['first'] is not None:
                 rows = comp[0][0].long()
-                prep.update(hist=hist.index_select(0, rows), Au=user_graph.index_select(0, rows),
-                            ci=user_category_indices.index_select(0, rows))
-            prep['prune'], prep['prune_n'], prep['seg_prune'] = self._pack_lists(uf, nf, sf, comp[1:])
+                prep.update(hist=prep['hist'].index_select(0, rows), Au=prep['Au'].index_select(0, rows),
+                            ci=prep['ci'].index_select(0, rows))
+            prep['prune'], prep['prune_n'], prep['seg_prune'] = self._pack_lists(begun['uf'], begun['nf'], begun['sf'], comp[1:])
         return prep
+
+    def prepare_resident(self, beh_idx, news_idx, share_user_graphs=True):
+        return self.finish_prepare(self.begin_resident(beh_idx, news_idx, share_user_graphs))
+
+    def prepare_device_batch(self, *device_tensors, share_user_graphs=True):
+        return self.finish_prepare(self.begin_device_batch(*device_tensors, share_user_graphs=share_user_graphs))
+
+    @staticmethod
+    def _pack_lists(uf, nf, sf, comp):
+        cu, cn, cs = comp
+        prune = prune_n = seg_prune = None
+        if cu is not None and cu[0].shape[0] < uf[0].numel():
+            prune = (uf[0], cu[0], cu[1], uf[1])
+        if cn is not None and cn[0].shape[0] < nf.numel():
+            prune_n = (nf, cn[0], cn[1])
+        if cs is not None and cs[0].shape[0] < sf.numel():
+            seg_prune = cs
+        return prune, prune_n, seg_prune
 
     def score_prepared(self, prep):
         """Gathers + encoder + logits of a prepared batch: kernel launches only, no host synchronisation."""
@@ -221,47 +236,22 @@ def host_batch(corpus, pair_ids, pin=False):
     return out
 
 
-def _tensors_of(obj):
-    if torch.is_tensor(obj):
-        yield obj
-    elif isinstance(obj, dict):
-        for v in obj.values():
-            yield from _tensors_of(v)
-    elif isinstance(obj, (tuple, list)):
-        for v in obj:
-            yield from _tensors_of(v)
-
-
-def _pipelined(scorer: Scorer, items, prepare, results, events=None):
-    """Runs ``prepare(item)`` for item k+1 on a side stream (copies, index work and their host synchronisations) while
-    item k is encoded on the current stream."""
+def _pipelined(scorer: Scorer, items, begin, results, events=None):
+    """Software pipelining on ONE compute stream.  In stream order:  ... flags(k+1) | encoder(k) | lists(k+1), flags(k+2)
+    | encoder(k+1) ...  The host waits (once per batch) on an event recorded right behind flags(k+1), i.e. while the GPU is
+    entering encoder(k); it then enqueues the list building of batch k+1 and the next round.  The GPU never waits for the
+    host as long as a round's enqueue time (about 2 ms) is shorter than an encoder pass, and nothing depends on how the GPU
+    schedules concurrent streams (a staging stream that ran concurrently was starved for up to 100 ms every few runs)."""
     main = torch.cuda.current_stream(scorer.dev)
-    side = getattr(scorer, '_copy_stream', None)
-    if side is None:
-        # high priority: the staging kernels are tiny and the host waits for them (one nonzero() per batch); they must not
-        # queue behind the encoder's long kernels
-        side = scorer._copy_stream = torch.cuda.Stream(device=scorer.dev, priority=-1)
-
-    def stage(item):
-        # No wait on the main stream here: staging depends on the batch's own inputs only, and its tensors are handed to
-        # the main stream with record_stream (the caching allocator recycles them only after the main stream is done).
-        with torch.cuda.stream(side):
-            prep = prepare(item)
-            ev = torch.cuda.Event()
-            ev.record(side)
-        for t in _tensors_of(prep):
-            t.record_stream(main)                    # allocated on the side stream, consumed on the main one
-        return prep, ev
-
     outs = []
     it = iter(items)
     nxt = next(it, None)
-    staged = stage(nxt) if nxt is not None else None
+    prep = scorer.finish_prepare(begin(nxt)) if nxt is not None else None
     k = 0
-    while staged is not None:
-        prep, ev = staged
-        main.wait_event(ev)
-        scores = scorer.score_prepared(prep)                      # launches only: returns long before the GPU is done
+    while prep is not None:
+        nxt = next(it, None)
+        begun = begin(nxt) if nxt is not None else None           # flags of batch k+1: ahead of encoder(k) in the stream
+        scores = scorer.score_prepared(prep)                      # launches only
         if results is not None:
             results[k].copy_(scores, non_blocking=True)
         outs.append(scores)
@@ -269,27 +259,38 @@ def _pipelined(scorer: Scorer, items, prepare, results, events=None):
             ev_done = torch.cuda.Event(enable_timing=True)
             ev_done.record(main)
             events.append(ev_done)
-        nxt = next(it, None)
-        staged = stage(nxt) if nxt is not None else None          # batch k+1 is staged while batch k runs
+        prep = scorer.finish_prepare(begun) if begun is not None else None
         k += 1
     return outs
 
 
 def score_host_batches(scorer: Scorer, host_batches, results=None, share_user_graphs=True):
     """The reference hot loop (util.py:56-69) over an iterable of HOST batches (7-tuples, ideally pinned), pipelined:
-    the copies and the index preparation of batch k+1 run on a side stream while batch k is encoded on the current
-    stream, and the scores of batch k go back to ``results[k]`` (pinned host tensors, optional) asynchronously.  Every
-    batch's host->device copy and device->host read happens inside this call.  Returns the device score tensors."""
-    return _pipelined(scorer, host_batches,
-                      lambda hb: scorer.prepare_device_batch(*scorer.stage_host_batch(*hb),
-                                                             share_user_graphs=share_user_graphs), results)
+    the host->device copies of batch k+1 run on a copy stream and its index preparation is enqueued ahead of the encoder
+    pass of batch k; the scores of batch k go back to ``results[k]`` (pinned host tensors, optional) asynchronously.
+    Every batch's host->device copy and device->host read happens inside this call.  Returns the device score tensors."""
+    main = torch.cuda.current_stream(scorer.dev)
+    side = getattr(scorer, '_copy_stream', None)
+    if side is None:
+        side = scorer._copy_stream = torch.cuda.Stream(device=scorer.dev)
+
+    def begin(hb):
+        with torch.cuda.stream(side):                             # DMA copies only: they overlap the running encoder pass
+            dev_t = scorer.stage_host_batch(*hb)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        for t in dev_t:
+            t.record_stream(main)                                 # allocated on the copy stream, consumed on the main one
+        main.wait_event(ev)
+        return scorer.begin_device_batch(*dev_t, share_user_graphs=share_user_graphs)
+
+    return _pipelined(scorer, host_batches, begin, results)
 
 
 def score_resident_batches(scorer: Scorer, index_batches, results=None, share_user_graphs=True, events=None):
     """The same pipeline for the resident path: ``index_batches`` yields (behaviour index, news id) device tensors."""
     return _pipelined(scorer, index_batches,
-                      lambda ib: scorer.prepare_resident(ib[0], ib[1], share_user_graphs=share_user_graphs), results,
-                      events)
+                      lambda ib: scorer.begin_resident(ib[0], ib[1], share_user_graphs=share_user_graphs), results, events)
 
 
 def compute_scores(scorer: Scorer, corpus, batch_size: int, rank: int = 0, world_size: int = 1):
