@@ -185,6 +185,56 @@ inline int launch_user_active_rows(const uint8_t* adj, const int32_t* adj_index,
     return check_launch("digat_user_active_rows");
 }
 
+// Stream compaction of up to four flag lists laid out back to back in `flags` (their inclusive prefix sums in `csum`):
+// for list k covering flat positions [lo[k], lo[k] + size[k]) with base[k] set flags before it,
+//   pos_k[r] = csum[lo + r] - 1 - base        (rank of position r among the set flags of ITS list; valid where set)
+//   ids_k[pos_k[r]] = r                        for every set flag
+// One launch builds all lists; the counts are known to the host (it sized ids_k), so nothing here synchronises.
+struct CompactLists {
+    int n_lists;
+    int64_t lo[4], size[4];
+    int32_t base[4];
+    int32_t* ids[4];
+    int32_t* pos[4];      // may be null (list whose ranks nobody needs)
+};
+
+__global__ void compact_lists_kernel(const uint8_t* __restrict__ flags, const int32_t* __restrict__ csum, CompactLists c) {
+    const int64_t total = c.lo[c.n_lists - 1] + c.size[c.n_lists - 1];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int k = 0;
+#pragma unroll
+        for (int t = 1; t < 4; ++t)
+            if (t < c.n_lists && i >= c.lo[t]) k = t;
+        const int64_t r = i - c.lo[k];
+        const int32_t p = csum[i] - 1 - c.base[k];
+        if (c.pos[k] != nullptr) c.pos[k][r] = p;
+        if (flags[i] != 0) c.ids[k][p] = (int32_t)r;
+    }
+}
+
+inline int launch_compact_lists(const uint8_t* flags, const int32_t* csum, int n_lists, const int64_t* lo, const int64_t* size,
+                                const int32_t* base, int32_t* const* ids, int32_t* const* pos, cudaStream_t st) {
+    DIGAT_REQUIRE(flags && csum && lo && size && base && ids && pos, "digat_compact_lists: null pointer");
+    DIGAT_REQUIRE(n_lists >= 1 && n_lists <= 4, "digat_compact_lists: 1..4 lists");
+    CompactLists c;
+    c.n_lists = n_lists;
+    for (int k = 0; k < 4; ++k) {
+        const bool on = k < n_lists;
+        c.lo[k] = on ? lo[k] : 0; c.size[k] = on ? size[k] : 0; c.base[k] = on ? base[k] : 0;
+        c.ids[k] = on ? ids[k] : nullptr; c.pos[k] = on ? pos[k] : nullptr;
+        DIGAT_REQUIRE(!on || (size[k] >= 0 && (k == 0 ? lo[k] == 0 : lo[k] == lo[k - 1] + size[k - 1])),
+                      "digat_compact_lists: lists must be laid out back to back");
+        DIGAT_REQUIRE(!on || ids[k] != nullptr || size[k] == 0, "digat_compact_lists: null ids");
+    }
+    const int64_t total = c.lo[n_lists - 1] + c.size[n_lists - 1];
+    if (total <= 0) return DIGAT_OK;
+    const DeviceInfo* di = device_info();
+    if (!di) return fail(DIGAT_E_CUDA, "digat_compact_lists: no CUDA device");
+    const int64_t blocks = (total + 255) / 256;
+    compact_lists_kernel<<<(unsigned)(blocks < 8 * di->sm_count ? blocks : 8 * di->sm_count), 256, 0, st>>>(flags, csum, c);
+    return check_launch("digat_compact_lists");
+}
+
 // ---------------------------------------------------------------------------------------------------- SAG BFS
 // One warp per news.  The queue (node ids, depths) and the n x n adjacency live in shared memory; the similar-news
 // lists come as CSR (offsets, neighbour index, cosine as double: the reference compares python floats).

@@ -252,6 +252,11 @@ int digat_user_active_rows(const uint8_t* adj, const int32_t* adj_index, const i
     return launch_user_active_rows(adj, adj_index, cidx, cmask, active, pooled, G, n, H, S, as_stream(stream));
 }
 
+int digat_compact_lists(const uint8_t* flags, const int32_t* csum, int n_lists, const int64_t* lo, const int64_t* size,
+                        const int32_t* base, int32_t* const* ids, int32_t* const* pos, void* stream) {
+    return launch_compact_lists(flags, csum, n_lists, lo, size, base, ids, pos, as_stream(stream));
+}
+
 int digat_news_active_rows(const uint8_t* adj, const uint8_t* mask, uint8_t* active, int64_t G, int n, void* stream) {
     return launch_news_active_rows(adj, mask, active, G, n, as_stream(stream));
 }

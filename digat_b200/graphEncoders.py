@@ -12,6 +12,7 @@ Reference interface mirrored here (paths relative to /root/reference):
 
 There is no PyTorch fallback: CPU tensors, a missing library or a non-sm_100 device raise RuntimeError.
 """
+import ctypes
 import math
 
 import torch
@@ -423,7 +424,7 @@ class DIGAT(GraphEncoder):
     @staticmethod
     def compact_finish(state, n_lists=None):
         """Second half: wait for the counts (the only host synchronisation: an event recorded right behind the prefix
-        sums, so it does not wait for anything enqueued afterwards) and build, with launches only,
+        sums, so it does not wait for anything enqueued afterwards) and build, with ONE launch (digat_compact_lists),
         [(ids int32 [count], pos int32 [numel]) or None, ...]: ids = flat positions of the nonzero flags, pos[r] = rank
         of position r among them (valid where the flag is set)."""
         if state is None:
@@ -432,19 +433,29 @@ class DIGAT(GraphEncoder):
         cum = state['counts'].tolist()
         _release_pinned(state['counts'])
         allf, csum, sizes = state['allf'], state['csum'], state['sizes']
-        out, k, lo_pos, base = [], 0, 0, 0
+        dev = allf.device
+        total_set = cum[-1]
+        ids_all = torch.empty(max(total_set, 1), dtype=torch.int32, device=dev)      # the lists, back to back
+        pos_all = torch.empty(allf.shape[0], dtype=torch.int32, device=dev)
+        out, lo, size, base, ids_p, pos_p = [], [], [], [], [], []
+        k, lo_pos, b0 = 0, 0, 0
         for f in state['flags']:
             if f is None:
                 out.append(None)
                 continue
-            count, size = cum[k] - base, sizes[k]
-            pos = csum[lo_pos:lo_pos + size] - (1 + base)
-            # scatter r -> ids[pos[r]] for the set flags; the others go to a dump slot behind the list
-            dest = torch.where(allf[lo_pos:lo_pos + size] != 0, pos, count).long()
-            ids = torch.empty(count + 1, dtype=torch.int32, device=allf.device)
-            ids.scatter_(0, dest, torch.arange(size, dtype=torch.int32, device=allf.device))
-            out.append((ids[:count], pos))
-            base, lo_pos, k = cum[k], lo_pos + size, k + 1
+            count, sz = cum[k] - b0, sizes[k]
+            ids, pos = ids_all[b0:b0 + count], pos_all[lo_pos:lo_pos + sz]
+            out.append((ids, pos))
+            lo.append(lo_pos); size.append(sz); base.append(b0)
+            ids_p.append(ids_all.data_ptr() + 4 * b0); pos_p.append(pos.data_ptr())
+            b0, lo_pos, k = cum[k], lo_pos + sz, k + 1
+        n = len(lo)
+        if n > 4:
+            raise RuntimeError('compact_finish: at most four lists per call')
+        pad = lambda v: v + [0] * (4 - n)
+        _lib.call('digat_compact_lists', allf.data_ptr(), csum.data_ptr(), n, (ctypes.c_int64 * 4)(*pad(lo)),
+                  (ctypes.c_int64 * 4)(*pad(size)), (ctypes.c_int32 * 4)(*pad(base)), (ctypes.c_void_p * 4)(*pad(ids_p)),
+                  (ctypes.c_void_p * 4)(*pad(pos_p)), _stream())
         return out
 
     @classmethod

@@ -144,6 +144,13 @@ int digat_graph_layer_supports_row_active(int n, int D, int B);
  * neighbours). */
 int digat_user_active_rows(const uint8_t* adj, const int32_t* adj_index, const int64_t* cidx, const uint8_t* cmask,
                            uint8_t* active, uint8_t* pooled, int64_t G, int n, int H, int S, void* stream);
+/* Index lists from flags without a host round trip for the data: up to four flag lists laid out back to back in `flags`
+ * (uint8) with their inclusive int32 prefix sums in `csum`.  HOST arrays lo/size (flat range of list k), base (number of
+ * set flags before list k) and ids/pos (DEVICE output pointers per list; pos[k] may be NULL): ids_k receives the positions
+ * of the set flags of list k in ascending order, pos_k[r] the rank of position r (valid where the flag is set).  The
+ * caller sizes ids_k from the counts it read back (one event wait per batch, digat_b200/graphEncoders.py). */
+int digat_compact_lists(const uint8_t* flags, const int32_t* csum, int n_lists, const int64_t* lo, const int64_t* size,
+                        const int32_t* base, int32_t* const* ids, int32_t* const* pos, void* stream);
 /* The same for news graphs: a node is kept iff another node has an edge to it, or the news context reads it
  * (graphEncoders.py:109-114): node 0 (the local context), mask[g,i] != 0 (pooled by the candidate attention), or every
  * mask entry of the graph is 0 (uniform softmax).  adj [G,n,n], mask [G,n], active [G,n]. */
