@@ -128,3 +128,31 @@ def test_rank_kernel_large_impressions_and_ties():
     assert np.allclose(got, want_m, atol=1e-12)
     with pytest.raises(ValueError):                                                  # an impression with one class only
         evaluate.metrics_device(torch.from_numpy(ranks).to(dev), torch.ones(len(ranks), dtype=torch.int64, device=dev), off)
+
+
+def test_compact_lists_matches_numpy():
+    """DIGAT.compact_flags (digat_compact_lists under one event wait) against numpy nonzero / cumsum, with empty, full and
+    missing lists."""
+    from digat_b200.graphEncoders import DIGAT
+    rng = np.random.Generator(np.random.PCG64(8))
+    dev = torch.device('cuda:0')
+    cases = [
+        [rng.random(4096) < 0.03, rng.random((4096, 68)) < 0.5, None, rng.random((4096, 19)) < 0.4],
+        [None, np.zeros((300, 10), dtype=bool), np.ones((7, 3), dtype=bool), None],
+        [rng.random(1) < 2.0],
+        [None, None],
+    ]
+    for flags in cases:
+        got = DIGAT.compact_flags([None if f is None else torch.from_numpy(np.ascontiguousarray(f)).to(dev) for f in flags])
+        assert len(got) == len(flags)
+        for f, g in zip(flags, got):
+            if f is None:
+                assert g is None
+                continue
+            ids, pos = g
+            want = np.flatnonzero(f.reshape(-1))
+            assert ids.dtype == torch.int32 and pos.dtype == torch.int32
+            assert np.array_equal(ids.cpu().numpy(), want)
+            rank = np.cumsum(f.reshape(-1)) - 1
+            sel = f.reshape(-1)
+            assert np.array_equal(pos.cpu().numpy()[sel], rank[sel])
