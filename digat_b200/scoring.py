@@ -5,8 +5,12 @@ Model.inference -- with every gather done by the kernels of libdigat_sm100.so.
 Two ways in:
 * ``score_host_batch``  takes the HOST tensors the reference DataLoader yields (util.py:56: user_title_index,
   user_graph, user_category_mask, user_category_indices, news_ID, news_graph, news_graph_mask), copies them to the
-  device and scores them: the end-to-end ("e2e") path of bench.py;
-* ``score_resident``    takes only (behaviour index, news id) per pair; graphs, masks and tables stay resident in HBM.
+  device and scores them; ``score_host_batches`` does it for a whole DataLoader, pipelined (the end-to-end "e2e" path
+  of bench.py);
+* ``score_resident``    takes only (behaviour index, news id) per pair; graphs, masks and tables stay resident in HBM;
+  ``score_resident_batches`` / ``evaluate_resident`` are its pipelined drivers (scores, on-GPU ranks and metrics).
+A batch is prepared in two halves (``begin_*``: launches only; ``finish_prepare``: one event wait for four list lengths)
+so that the drivers can enqueue batch k+1's first half ahead of batch k's encoder pass (see ``_pipelined``).
 Pairs are independent, so multi-GPU inference shards the pair list with no communication (``shard_range``).
 """
 import numpy as np

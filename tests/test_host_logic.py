@@ -90,3 +90,18 @@ def test_bench_reference_arm_runs_on_cpu():
     import json
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line['impl'] == 'reference' and line['value'] > 0 and line['cpu_baseline']['kind'] == 'port'
+
+
+def test_similar_to_csr_and_impression_offsets():
+    from digat_b200 import evaluate, graphs
+    similar = [[], [(3, 0.9), (2, 0.5)], None, [(1, 0.75)]]
+    off, idx, cos = graphs.similar_to_csr(similar, 5)                  # news 4 has no entry at all
+    assert off.tolist() == [0, 0, 2, 2, 3, 3] and off.dtype == np.int64
+    assert idx.tolist() == [3, 2, 1] and idx.dtype == np.int32
+    assert cos.tolist() == [0.9, 0.5, 0.75] and cos.dtype == np.float64
+    imp = np.array([0, 0, 0, 1, 3, 3])                                # impression 2 is empty
+    assert evaluate.impression_offsets(imp).tolist() == [0, 3, 4, 4, 6]
+    assert evaluate.impression_offsets(np.array([], dtype=np.int64)).tolist() == [0]
+    # rank_lists / metrics on the same layout (host versions; the device versions are checked against them on the GPU)
+    ranks = evaluate.rank_lists(np.array([0.1, 0.3, 0.3, 1.0, -1.0, 2.0], dtype=np.float32), imp)
+    assert ranks == [[3, 1, 2], [1], [], [2, 1]]
