@@ -316,7 +316,7 @@ inline int launch_sag_bfs(const int64_t* sim_off, const int32_t* sim_idx, const 
     DIGAT_REQUIRE(top_M >= 1 && hop >= 0, "digat_sag_bfs: bad top_M / hop");
     const size_t smem = (size_t)kSagWarps * (((size_t)n_nodes * n_nodes + 15) & ~(size_t)15) +
                         (size_t)kSagWarps * 2 * kSagMaxNodes * sizeof(int);
-    DIGAT_CUDA(cudaFuncSetAttribute(sag_bfs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (int rc_ = ensure_dynamic_smem(sag_bfs_kernel, (size_t)(smem))) return rc_;
     sag_bfs_kernel<<<(n_news + kSagWarps - 1) / kSagWarps, kSagWarps * 32, smem, st>>>(
         sim_off, sim_idx, sim_cos, node_id, graph, mask, n_news, top_M, hop, n_nodes, threshold, err_flag);
     return check_launch("digat_sag_bfs");

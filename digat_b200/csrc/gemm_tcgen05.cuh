@@ -385,7 +385,7 @@ inline int launch_tf32x3_cfg(const float* A, int lda, const float* W_hi, const f
     if ((rc = make_tensor_map_2d(&ma, A, M, K, lda, Cfg::BM, kTcBK, CU_TENSOR_MAP_SWIZZLE_64B)) != DIGAT_OK) return rc;
     if ((rc = make_tensor_map_2d(&mh, W_hi, N, K, ldw, BN, kTcBK, CU_TENSOR_MAP_SWIZZLE_64B)) != DIGAT_OK) return rc;
     if ((rc = make_tensor_map_2d(&ml, W_lo, N, K, ldw, BN, kTcBK, CU_TENSOR_MAP_SWIZZLE_64B)) != DIGAT_OK) return rc;
-    DIGAT_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, MH, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    if (int rc_ = ensure_dynamic_smem(gemm_tf32x3_kernel<BN, MH, SPLIT>, (size_t)(Cfg::SMEM))) return rc_;
     dim3 grid((N + BN - 1) / BN, (M + Cfg::BM - 1) / Cfg::BM);
     gemm_tf32x3_kernel<BN, MH, SPLIT><<<grid, kTcThreads, Cfg::SMEM, st>>>(ma, mh, ml, bias, C, ldc, M, N, K, gb);
     return check_launch("digat_linear_tf32x3");

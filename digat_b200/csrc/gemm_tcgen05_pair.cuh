@@ -264,7 +264,7 @@ int launch_tf32x3_pair(const float* A, int lda, const float* W_hi, const float* 
     if ((rc = make_tensor_map_2d(&ma, A, M, K, lda, 128, kTcBK, CU_TENSOR_MAP_SWIZZLE_64B)) != DIGAT_OK) return rc;
     if ((rc = make_tensor_map_2d(&mh, W_hi, N, K, ldw, Cfg::WH_ROWS, kTcBK, CU_TENSOR_MAP_SWIZZLE_64B)) != DIGAT_OK) return rc;
     if ((rc = make_tensor_map_2d(&ml, W_lo, N, K, ldw, Cfg::WH_ROWS, kTcBK, CU_TENSOR_MAP_SWIZZLE_64B)) != DIGAT_OK) return rc;
-    DIGAT_CUDA(cudaFuncSetAttribute(gemm_tf32x3_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    if (int rc_ = ensure_dynamic_smem(gemm_tf32x3_pair_kernel<BN>, (size_t)(Cfg::SMEM))) return rc_;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * ((N + BN - 1) / BN), (M + 255) / 256);
     cfg.blockDim = dim3(kTcThreads);

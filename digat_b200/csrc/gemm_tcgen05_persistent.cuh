@@ -373,10 +373,10 @@ int launch_tf32x3_persistent(const float* A, int lda, const float* W_hi, const f
     const int tiles = ((N + BN - 1) / BN) * ((M + 127) / 128) * gb.kbatches;
     const int grid = tiles < di->sm_count ? tiles : di->sm_count;
     if (bf16c) {
-        DIGAT_CUDA(cudaFuncSetAttribute(gemm_tf32x3_persistent_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        if (int rc_ = ensure_dynamic_smem(gemm_tf32x3_persistent_kernel<BN, true>, (size_t)(Cfg::SMEM))) return rc_;
         gemm_tf32x3_persistent_kernel<BN, true><<<grid, kTcPersistThreads, Cfg::SMEM, st>>>(ma, mh, ml, m3, bias, C, ldc, M, N, K, gb);
     } else {
-        DIGAT_CUDA(cudaFuncSetAttribute(gemm_tf32x3_persistent_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        if (int rc_ = ensure_dynamic_smem(gemm_tf32x3_persistent_kernel<BN, false>, (size_t)(Cfg::SMEM))) return rc_;
         gemm_tf32x3_persistent_kernel<BN, false><<<grid, kTcPersistThreads, Cfg::SMEM, st>>>(ma, mh, ml, m3, bias, C, ldc, M, N, K, gb);
     }
     return check_launch("digat_linear_tf32x3(persistent)");

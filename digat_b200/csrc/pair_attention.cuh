@@ -443,10 +443,10 @@ inline int launch_graph_layer_fwd(const float* P, int ldp, const float* a, const
     const int grid = (B + g.R - 1) / g.R;
     const bool single = g.R * g.nt * g.nt <= kPairThreads;
     if (single) {
-        DIGAT_CUDA(cudaFuncSetAttribute(graph_layer_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+        if (int rc_ = ensure_dynamic_smem(graph_layer_fwd_kernel<true>, (size_t)(g.smem))) return rc_;
         graph_layer_fwd_kernel<true><<<grid, kPairThreads, g.smem, st>>>(map1, map3, args, g);
     } else {
-        DIGAT_CUDA(cudaFuncSetAttribute(graph_layer_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+        if (int rc_ = ensure_dynamic_smem(graph_layer_fwd_kernel<false>, (size_t)(g.smem))) return rc_;
         graph_layer_fwd_kernel<false><<<grid, kPairThreads, g.smem, st>>>(map1, map3, args, g);
     }
     return check_launch("digat_graph_layer_fwd");

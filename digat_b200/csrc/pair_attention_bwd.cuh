@@ -351,10 +351,10 @@ inline int launch_graph_layer_bwd(const float* P, int ldp, const float* a, const
     PairBwdArgs args{a, adj, score, alpha, drop_keep, drop_scale, dP, lddp, da_partial, B, n, D};
     const bool single = g.nt * g.nt <= kPairThreads;
     if (single) {
-        DIGAT_CUDA(cudaFuncSetAttribute(graph_layer_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+        if (int rc_ = ensure_dynamic_smem(graph_layer_bwd_kernel<true>, (size_t)(g.smem))) return rc_;
         graph_layer_bwd_kernel<true><<<B, kPairThreads, g.smem, st>>>(mapP, mapG, args, g);
     } else {
-        DIGAT_CUDA(cudaFuncSetAttribute(graph_layer_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+        if (int rc_ = ensure_dynamic_smem(graph_layer_bwd_kernel<false>, (size_t)(g.smem))) return rc_;
         graph_layer_bwd_kernel<false><<<B, kPairThreads, g.smem, st>>>(mapP, mapG, args, g);
     }
     return check_launch("digat_graph_layer_bwd");

@@ -435,13 +435,13 @@ int launch_graph_layer_fwd_sparse(const PairAttnArgs& args, int n_src, cudaStrea
     if ((rc = make_tensor_map_2d(&map3, args.P, src_graphs * args.n, 3 * args.D, args.ldp, G * args.n, kSparseDc3, CU_TENSOR_MAP_SWIZZLE_NONE)) != DIGAT_OK) return rc;
     const int grid = (args.B + G - 1) / G;
     if (indexed) {
-        DIGAT_CUDA(cudaFuncSetAttribute(graph_layer_fwd_sparse_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+        if (int rc_ = ensure_dynamic_smem(graph_layer_fwd_sparse_kernel<true, false>, (size_t)(g.smem))) return rc_;
         graph_layer_fwd_sparse_kernel<true, false><<<grid, kSparseThreads, g.smem, st>>>(map1, map3, args, g);
     } else if (G == 1) {
-        DIGAT_CUDA(cudaFuncSetAttribute(graph_layer_fwd_sparse_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+        if (int rc_ = ensure_dynamic_smem(graph_layer_fwd_sparse_kernel<false, false>, (size_t)(g.smem))) return rc_;
         graph_layer_fwd_sparse_kernel<false, false><<<grid, kSparseThreads, g.smem, st>>>(map1, map3, args, g);
     } else {
-        DIGAT_CUDA(cudaFuncSetAttribute(graph_layer_fwd_sparse_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+        if (int rc_ = ensure_dynamic_smem(graph_layer_fwd_sparse_kernel<false, true>, (size_t)(g.smem))) return rc_;
         graph_layer_fwd_sparse_kernel<false, true><<<grid, kSparseThreads, g.smem, st>>>(map1, map3, args, g);
     }
     return check_launch("digat_graph_layer_fwd(sparse)");

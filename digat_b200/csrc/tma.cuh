@@ -2,6 +2,8 @@
 // host-side tensor-map encoder (cuTensorMapEncodeTiled through the runtime's driver entry point: no -lcuda needed).
 #pragma once
 #include <cuda.h>
+#include <mutex>
+#include <unordered_map>
 #include "common.cuh"
 
 namespace digat {
@@ -58,35 +60,86 @@ inline PFN_tensorMapEncodeTiled tensor_map_encoder() {
     return fn;
 }
 
-// 2-D fp32 row-major [rows, cols] with row pitch ld elements; box = [box_rows, box_cols]; out-of-bounds reads give 0.
-inline int make_tensor_map_2d(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
-                              int box_cols, CUtensorMapSwizzle swizzle) {
+// Descriptor cache.  A CUtensorMap is a pure function of (base address, shape, pitch, box, swizzle, element type), so an
+// encoded descriptor can be reused for as long as the process lives, whatever happens to the memory behind it (a buffer
+// freed and reallocated at the same address with the same shape needs the very same descriptor).  PyTorch's caching
+// allocator hands the same blocks to the same call sites step after step, so in steady state no launch encodes anything
+// (the driver call costs ~1 us per descriptor, three to four per GEMM launch).  Mutex-guarded; bounded (cleared when full).
+struct TensorMapKey {
+    const void* base;
+    int64_t rows, cols, ld;
+    int box_rows, box_cols, swizzle, dtype;
+    bool operator==(const TensorMapKey& o) const {
+        return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows &&
+               box_cols == o.box_cols && swizzle == o.swizzle && dtype == o.dtype;
+    }
+};
+struct TensorMapKeyHash {
+    size_t operator()(const TensorMapKey& k) const {
+        uint64_t h = reinterpret_cast<uintptr_t>(k.base) * 0x9E3779B97F4A7C15ull;
+        auto mix = [&](uint64_t v) { h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); };
+        mix((uint64_t)k.rows); mix((uint64_t)k.cols); mix((uint64_t)k.ld);
+        mix(((uint64_t)k.box_rows << 32) | (uint32_t)k.box_cols); mix(((uint64_t)k.swizzle << 8) | (uint32_t)k.dtype);
+        return (size_t)h;
+    }
+};
+
+inline int make_tensor_map_2d_any(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                                  int box_cols, CUtensorMapSwizzle swizzle, CUtensorMapDataType dtype, int elem_bytes) {
+    static std::mutex mu;
+    static std::unordered_map<TensorMapKey, CUtensorMap, TensorMapKeyHash> cache;
+    const TensorMapKey key{base, rows, cols, ld, box_rows, box_cols, (int)swizzle, (int)dtype};
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) {
+            *map = it->second;
+            return DIGAT_OK;
+        }
+    }
     PFN_tensorMapEncodeTiled enc = tensor_map_encoder();
     if (!enc) return fail(DIGAT_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * (cuuint64_t)elem_bytes};
     cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(map, dtype, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(DIGAT_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    std::lock_guard<std::mutex> lock(mu);
+    if (cache.size() >= 4096) cache.clear();
+    cache.emplace(key, *map);
     return DIGAT_OK;
+}
+
+// 2-D fp32 row-major [rows, cols] with row pitch ld elements; box = [box_rows, box_cols]; out-of-bounds reads give 0.
+inline int make_tensor_map_2d(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                              int box_cols, CUtensorMapSwizzle swizzle) {
+    return make_tensor_map_2d_any(map, base, rows, cols, ld, box_rows, box_cols, swizzle, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4);
 }
 
 // [rows, cols] bf16 (2-byte elements), row pitch ld elements
 inline int make_tensor_map_2d_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
                                    int box_cols, CUtensorMapSwizzle swizzle) {
-    PFN_tensorMapEncodeTiled enc = tensor_map_encoder();
-    if (!enc) return fail(DIGAT_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(DIGAT_E_CUDA, "cuTensorMapEncodeTiled(bf16) failed with CUresult %d", (int)r);
+    return make_tensor_map_2d_any(map, base, rows, cols, ld, box_rows, box_cols, swizzle, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel instantiation, device) instead of once per launch.
+template <typename Kernel>
+inline int ensure_dynamic_smem(Kernel kernel, size_t bytes) {
+    static std::mutex mu;
+    static std::unordered_map<uint64_t, size_t> done;          // (kernel address ^ device) -> largest size set
+    int dev = 0;
+    DIGAT_CUDA(cudaGetDevice(&dev));
+    const uint64_t key = (uint64_t)reinterpret_cast<uintptr_t>(reinterpret_cast<const void*>(kernel)) * 31u + (uint64_t)dev;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = done.find(key);
+        if (it != done.end() && it->second >= bytes) return DIGAT_OK;
+    }
+    if (int rc_ = ensure_dynamic_smem(kernel, (size_t)(bytes))) return rc_;
+    std::lock_guard<std::mutex> lock(mu);
+    done[key] = bytes;
     return DIGAT_OK;
 }
 

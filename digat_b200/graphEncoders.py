@@ -25,6 +25,15 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def _same_device(t, name):
+    """Kernels are launched on the CURRENT device's current stream: a tensor on another device would hand the kernel a
+    foreign pointer.  (One process per GPU: call torch.cuda.set_device first, as reference config.py:85-89 does.)"""
+    if t.device.index != torch.cuda.current_device():
+        raise RuntimeError('%s lives on %s but the current CUDA device is cuda:%d -- call torch.cuda.set_device(%d) '
+                           '(digat_b200 launches on the current device)' % (name, t.device, torch.cuda.current_device(),
+                                                                            t.device.index))
+
+
 def _ptr(t):
     return 0 if t is None else t.data_ptr()
 
@@ -34,6 +43,7 @@ def _f32c(t, name):
         raise RuntimeError('%s must be a CUDA tensor (digat_b200 has no CPU fallback)' % name)
     if t.dtype != torch.float32:
         raise RuntimeError('%s must be float32, got %s' % (name, t.dtype))
+    _same_device(t, name)
     return t if t.is_contiguous() else t.contiguous()
 
 
@@ -42,6 +52,7 @@ def _boolc(t, name):
         raise RuntimeError('%s must be a CUDA tensor (digat_b200 has no CPU fallback)' % name)
     if t.dtype not in (torch.bool, torch.uint8):
         raise RuntimeError('%s must be bool, got %s' % (name, t.dtype))
+    _same_device(t, name)
     return t if t.is_contiguous() else t.contiguous()
 
 
@@ -72,13 +83,13 @@ def _ends_tensor(sizes, device):
 
 class PackedWeight:
     """A projection weight in kernel layout: fp32 [N,K] (nn.Linear layout) plus, when the tcgen05 GEMM can take it
-    (N % 80 == 0), its two TF32 planes hi = rna_tf32(W), lo = rna_tf32(W - hi) (digat_split_tf32)."""
+    (N % 16 == 0, K % 4 == 0), its two TF32 planes hi = rna_tf32(W), lo = rna_tf32(W - hi) (digat_split_tf32)."""
     __slots__ = ('w', 'hi', 'lo')
 
     def __init__(self, w):
         self.w = w.detach().float().contiguous()
         self.hi = self.lo = None
-        if self.w.shape[0] % 80 == 0 and self.w.shape[1] % 4 == 0:
+        if self.w.shape[0] % 16 == 0 and self.w.shape[1] % 4 == 0:
             self.hi, self.lo = torch.empty_like(self.w), torch.empty_like(self.w)
             _lib.call('digat_split_tf32', self.w.data_ptr(), self.hi.data_ptr(), self.lo.data_ptr(), self.w.numel(),
                       _stream())
@@ -209,6 +220,19 @@ class DIGAT(GraphEncoder):
             setattr(self, g + '_graph_attention_a', nn.ModuleList([nn.Linear(D, 1, bias=False) for _ in range(L)]))
         self._packed = None
         self._packed_key = None
+
+    def invalidate_packed(self):
+        """Drops the kernel-layout copy of the weights (DIGAT._weights).  The copy is keyed on (data_ptr, _version) of every
+        parameter, which misses updates that do not bump ``_version``: a CUDA-graph replay of the optimizer step
+        (training.GraphedTrainStep), ``param.data`` writes, NCCL broadcasts into parameter storage.  ``train()`` / ``eval()``
+        call this on every mode switch, GraphedTrainStep after every replay; call it yourself after any other in-place
+        update made behind autograd's back."""
+        self._packed = None
+        self._packed_key = None
+
+    def train(self, mode: bool = True):
+        self.invalidate_packed()          # eval after training must never see the packed weights of an earlier eval
+        return super().train(mode)
 
     def initialize(self):
         super().initialize()
@@ -586,7 +610,6 @@ class DIGAT(GraphEncoder):
 
     def forward(self, news_graph_embeddings, news_graph, news_graph_mask, user_news_embedding, user_graph,
                 user_category_mask, user_category_indices):
-        w = self._weights()
         args = self._check_inputs(news_graph_embeddings, news_graph, news_graph_mask, user_news_embedding, user_graph,
                                   user_category_mask, user_category_indices)
         if torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters())
@@ -594,5 +617,6 @@ class DIGAT(GraphEncoder):
             from . import autograd_ops   # training path: autograd.Functions over the backward kernels
             return autograd_ops.encode_with_grad(self, *args)
         Xn, An, Mn, Xh, Au, Mc, ci = args
+        w = self._weights()               # (inference branch only: the training path packs its own, differentiable, layout)
         with torch.no_grad():
             return self._encode(w, Xn, An, Mn, self._user_nodes(w, Xh), Au, Mc, ci, None)

@@ -36,6 +36,9 @@ class Scorer:
         uploading the [N_beh,n_u,n_u] bool array (4.6 KB per behaviour vs 200 B)."""
         self.enc = encoder.eval()
         self.dev = torch.device(device)
+        if self.dev.type == 'cuda' and self.dev.index is not None and self.dev.index != torch.cuda.current_device():
+            raise RuntimeError('Scorer(device=%s): kernels launch on the current device (cuda:%d) -- call '
+                               'torch.cuda.set_device first' % (self.dev, torch.cuda.current_device()))
         _lib.require_device(self.dev.index if self.dev.index is not None else torch.cuda.current_device())
         t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.dev)
         self.table = t(corpus.news_embeddings)                  # [N,D]   cached news representations (util.py:20-33)
@@ -57,6 +60,7 @@ class Scorer:
         self.n_n = self.node_id.shape[1]
         self.err = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.c_n0 = None
+        self._c_n0_weights = None                               # the packed-weight generation c_n0 was computed with
 
     def _st(self):
         return torch.cuda.current_stream().cuda_stream
@@ -95,7 +99,7 @@ class Scorer:
                 hi = min(lo + batch_size, self.n_news)
                 ids = torch.arange(lo, hi, device=self.dev, dtype=torch.int32)
                 c[lo:hi] = self.enc._news_ctx(w, self.gather_sag(ids), self.news_mask[lo:hi])
-        self.c_n0 = c
+        self.c_n0, self._c_n0_weights = c, w
         return c
 
     # ------------------------------------------------------------------------------------------------------------
@@ -185,8 +189,8 @@ class Scorer:
     def score_prepared(self, prep):
         """Gathers + encoder + logits of a prepared batch: kernel launches only, no host synchronisation."""
         w = self.enc._weights()
-        if self.c_n0 is None:
-            self.cache_news_context()
+        if self.c_n0 is None or self._c_n0_weights is not w:     # the reference recomputes it per compute_scores call
+            self.cache_news_context()                            # (util.py:37-44); here: whenever the weights were repacked
         with torch.no_grad():
             Xn = self.gather_sag(prep['news'])
             Xu = self.user_nodes(prep['hist'])                           # one node tensor per behaviour when shared

@@ -10,9 +10,12 @@ import torch
 
 
 class GraphedTrainStep:
-    def __init__(self, step_fn, example_inputs, warmup: int = 3):
+    def __init__(self, step_fn, example_inputs, warmup: int = 3, modules=()):
         """step_fn(*inputs) -> loss tensor; it must do zero_grad / backward / optimizer.step itself.
-        NOTE: the ``warmup`` eager calls and the capture itself are real training steps on ``example_inputs``."""
+        NOTE: the ``warmup`` eager calls and the capture itself are real training steps on ``example_inputs``.
+        modules: nn.Modules whose DIGAT encoders keep a packed copy of the weights for inference -- a replayed optimizer
+        step does not bump ``param._version``, so every replay invalidates those copies (DIGAT.invalidate_packed)."""
+        self._encoders = [m for mod in modules for m in mod.modules() if hasattr(m, 'invalidate_packed')]
         self.static_inputs = [x.clone() for x in example_inputs]
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
@@ -30,4 +33,6 @@ class GraphedTrainStep:
         for dst, src in zip(self.static_inputs, inputs):
             dst.copy_(src, non_blocking=True)
         self.graph.replay()
+        for m in self._encoders:
+            m.invalidate_packed()
         return self.static_loss

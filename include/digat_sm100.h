@@ -13,7 +13,9 @@
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); every call is asynchronous;
  *   - return value: 0 on success, <0 on failure (DIGAT_E_*); digat_last_error() gives the message of the
  *     last failure on the calling thread.  Nothing throws or exits across this boundary.
- *   - entry points are re-entrant; there is no CPU fallback: without an sm_100 device every compute call fails.
+ *   - entry points are re-entrant (process-wide mutable state: cached device properties, a mutex-guarded TMA
+ *     descriptor cache, and the digat_debug_set_* experiment switches, which nothing on the reference path sets);
+ *     there is no CPU fallback: without an sm_100 device every compute call fails.
  */
 #ifndef DIGAT_SM100_H
 #define DIGAT_SM100_H

@@ -58,3 +58,37 @@ def rel_err(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
+
+
+def ulp_distance(a, b):
+    """Distance between two fp32 arrays in units in the last place (ordered-integer view of the IEEE bit patterns)."""
+    def key(x):
+        u = np.ascontiguousarray(np.asarray(x, dtype=np.float32)).view(np.int32).astype(np.int64)
+        return np.where(u < 0, -(u & 0x7FFFFFFF), u)
+    return np.abs(key(a) - key(b))
+
+
+def err_stats(got, ref, terms=None, floor_frac=1e-3):
+    """Error of ``got`` against ``ref`` reported three ways (tests gate on 'max_norm'; the others are printed and, where a
+    test says so, gated too):
+      max_norm : max|got-ref| / max|ref|                                  (the scale of the tensor)
+      per_elem : max over elements of |got-ref| / max(|ref|, floor),  floor = floor_frac * max|ref|   (per-logit error;
+                 the floor is stated because a single logit may be arbitrarily close to zero)
+      cond     : max over elements of |got-ref| / terms,  terms[i] = sum_d |x_d * y_d| of the dot product that forms
+                 element i (the magnitude fp32 rounding acts on: |logit| <= terms); only when ``terms`` is given
+      max_ulp  : largest distance in fp32 units in the last place."""
+    g = np.asarray(got, dtype=np.float64)
+    r = np.asarray(ref, dtype=np.float64)
+    scale = max(float(np.max(np.abs(r))), 1e-30)
+    d = np.abs(g - r)
+    out = {'max_norm': float(d.max() / scale),
+           'per_elem': float(np.max(d / np.maximum(np.abs(r), floor_frac * scale))),
+           'floor': floor_frac * scale,
+           'max_ulp': int(ulp_distance(got, ref).max())}
+    if terms is not None:
+        out['cond'] = float(np.max(d / np.maximum(np.asarray(terms, dtype=np.float64), 1e-30)))
+    return out
+
+
+def fmt_stats(s):
+    return ', '.join('%s %s' % (k, ('%d' % v) if k == 'max_ulp' else ('%.2e' % v)) for k, v in s.items())

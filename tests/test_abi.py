@@ -82,3 +82,35 @@ def test_state_dict_names_match_imported_reference():
     for k in rs:
         assert rs[k].shape == os_[k].shape
     ours.load_state_dict(rs)
+
+
+def _header_param_count(name):
+    src = open(os.path.join(ROOT, 'include', 'digat_sm100.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    m = re.search(r'\b%s\s*\(([^)]*)\)\s*;' % re.escape(name), src)
+    assert m, name + ' is not declared in the header'
+    params = m.group(1).strip()
+    return 0 if params in ('', 'void') else len(params.split(','))
+
+
+def test_ctypes_signatures_have_the_arity_of_the_header():
+    from digat_b200 import _lib
+    for name, argtypes in _lib.SIGNATURES.items():
+        assert len(argtypes) == _header_param_count(name), name
+
+
+def test_documented_ctypes_stub_matches_header():
+    """INTEGRATION.md shows the binding a maintainer would write for digat_graph_layer_fwd: its argtypes list and its
+    example call must have exactly the parameters the header declares (a stale stub is undefined behaviour)."""
+    doc = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    block = re.search(r'lib\.digat_graph_layer_fwd\.argtypes = \[(.*?)\]', doc, flags=re.S).group(1)
+    block = re.sub(r'#[^\n]*', '', block)
+    n_types = len([t for t in block.replace('\n', ' ').split(',') if t.strip()])
+    call = re.search(r'rc = lib\.digat_graph_layer_fwd\((.*?)\)\nif rc', doc, flags=re.S).group(1)
+    depth, n_args = 0, 1
+    for ch in call:
+        depth += ch in '([' 
+        depth -= ch in ')]'
+        n_args += ch == ',' and depth == 0
+    want = _header_param_count('digat_graph_layer_fwd')
+    assert n_types == want and n_args == want, (n_types, n_args, want)

@@ -11,7 +11,7 @@ from tests.helpers import rel_err
 pytestmark = pytest.mark.gpu
 ORDER = ('news_graph_embeddings', 'news_graph', 'news_graph_mask', 'user_news_embedding', 'user_graph',
          'user_category_mask', 'user_category_indices')
-GRAD_TOL = 2e-4     # gradients, relative to the largest magnitude of the tensor
+GRAD_TOL = 2e-5     # gradients vs the fp64 oracle autograd, relative to the largest magnitude of the tensor
 
 
 def _batch(cfg, rows, seed, scale=0.3):
@@ -63,14 +63,17 @@ def test_encoder_gradients_match_oracle(N, L, rows):
     ours['in:news'] = b['news_graph_embeddings'].grad
     ours['in:hist'] = b['user_news_embedding'].grad
     assert set(ours) == set(ref32)
-    worst = 0.0
+    worst, bad = 0.0, []
     for k in sorted(ref32):
         assert ours[k] is not None, 'no gradient for ' + k
         e64 = rel_err(ours[k].cpu().numpy(), ref64[k].numpy())
         eref = rel_err(ref32[k].numpy(), ref64[k].numpy())
         worst = max(worst, e64)
-        assert e64 < GRAD_TOL, 'grad %s: rel err vs fp64 %.3e (fp32 oracle vs fp64: %.3e)' % (k, e64, eref)
+        print('grad %-45s ours vs fp64 %.2e   oracle fp32 vs fp64 %.2e' % (k, e64, eref))
+        if e64 >= GRAD_TOL:
+            bad.append((k, e64, eref))
     print('worst gradient rel err vs fp64: %.3e' % worst)
+    assert not bad, 'gradients beyond %.0e of the fp64 oracle: %s' % (GRAD_TOL, bad)
 
 
 def test_graph_layer_dropout_mask_injection():

@@ -112,3 +112,35 @@ def test_tf32_bf16_correction_gemm_matches_fp64():
         ref = A.double().cpu() @ W.double().cpu().t() + b.double().cpu()
         ref[:, :gbias.shape[1]] += gbias.double().cpu().repeat_interleave(68, dim=0)[:M]
         assert rel_err(C.cpu().numpy(), ref.numpy()) < 4e-6
+
+
+@pytest.mark.parametrize('M,N,K', [(300, 64, 64), (1000, 256, 256), (20000, 512, 128), (40000, 128, 512), (700, 48, 32)])
+def test_tf32x3_widths_that_80_does_not_divide(M, N, K):
+    """news_embedding_dim values such as 64 / 128 / 256 / 512: partial last N tiles on every tile variant."""
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g)
+    W = torch.randn(N, K, generator=g) * 0.05
+    bias = torch.randn(N, generator=g)
+    C = _tf32x3(A.cuda(), W.cuda(), bias.cuda()).cpu()
+    ref = A.double() @ W.double().t() + bias.double()
+    assert torch.isfinite(C).all()
+    assert rel_err(C.numpy(), ref.numpy()) < 4e-6
+
+
+@pytest.mark.parametrize('M,D', [(512, 64), (1000, 256), (300, 128)])
+def test_linear_backward_other_embedding_dims(M, D):
+    """Weight gradients on the split-K tensor-core path for D not a multiple of 80 (used to crash: no TF32 planes)."""
+    from digat_b200.autograd_ops import lin
+    g = torch.Generator().manual_seed(M + D)
+    A = torch.randn(M, D, generator=g)
+    W = torch.randn(3 * D, D, generator=g) * 0.05
+    bias = torch.randn(3 * D, generator=g)
+    dC = torch.randn(M, 3 * D, generator=g)
+    A64, W64, b64 = (t.double().requires_grad_(True) for t in (A, W, bias))
+    (A64 @ W64.t() + b64).backward(dC.double())
+    Ac, Wc, bc = (t.cuda().requires_grad_(True) for t in (A, W, bias))
+    lin(Ac, Wc, bc).backward(dC.cuda())
+    torch.cuda.synchronize()
+    assert rel_err(Ac.grad.cpu().numpy(), A64.grad.numpy()) < 5e-6
+    assert rel_err(Wc.grad.cpu().numpy(), W64.grad.numpy()) < 5e-6
+    assert rel_err(bc.grad.cpu().numpy(), b64.grad.numpy()) < 2e-6
