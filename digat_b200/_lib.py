@@ -27,6 +27,7 @@ SIGNATURES = {
     'digat_graph_layer_fwd': [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                               c_void_p, ctypes.c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                               c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    'digat_gat_layer_fwd': [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     'digat_graph_layer_supports_row_active': [c_int, c_int, c_int],
     'digat_compact_lists': [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     'digat_news_active_rows': [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p],

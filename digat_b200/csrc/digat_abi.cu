@@ -118,6 +118,11 @@ int digat_graph_layer_fwd(const float* P, int ldp, const float* a, const uint8_t
                                   as_stream(stream));
 }
 
+int digat_gat_layer_fwd(const float* Hm, int ldh, const float* s12, const uint8_t* adj, const float* X, float* Y,
+                        int B, int n, int D, void* stream) {
+    return launch_gat_layer_fwd(Hm, ldh, s12, adj, X, Y, B, n, D, as_stream(stream));
+}
+
 int digat_attention_pool_fwd(const float* F, int64_t strideF, int ldf, const float* resid_F, const float* v,
                              int ldv, const uint8_t* mask, const float* add_in, float* out, int ldo, float* first_out,
                              float* alpha_out, int B, int m, int D, void* stream) {

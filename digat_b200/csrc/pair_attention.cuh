@@ -64,6 +64,9 @@ struct PairAttnArgs {
     // with row_active: Yc [M_act, D] also receives the output rows of the active nodes, row_pos [B*n] = position of node
     // row r in that compact list -- the next layer's projection GEMM reads Yc directly (no gather pass)
     float* Yc; const int32_t* row_pos;
+    // vanilla-GAT scores (ablation encoders, reference graphEncoders.py:498-500 / 515-517; edge-driven kernel only):
+    // gat_s [B*n, 2], s_ij = gat_s[j][0] + gat_s[i][1] (= a1 . h_j + a2 . h_i).  P then holds h only (ldp >= D) and `a` is unused.
+    const float* gat_s = nullptr;
 };
 
 __device__ __forceinline__ uint64_t pack2(float lo, float hi) {

@@ -117,8 +117,9 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
 #ifdef DIGAT_TC_TIMING
     const long long t0 = clock64();
 #endif
+    const float* __restrict__ gat_s = p.gat_s;                     // vanilla-GAT scores: no phase-1 loads (g.nch1 == 0)
     for (int i = tid; i < D / 4; i += kSparseConsumers) {
-        reinterpret_cast<float4*>(a_s)[i] = reinterpret_cast<const float4*>(p.a)[i];
+        if (gat_s == nullptr) reinterpret_cast<float4*>(a_s)[i] = reinterpret_cast<const float4*>(p.a)[i];
         if (kIndexed) reinterpret_cast<float4*>(k3_s)[i] = reinterpret_cast<const float4*>(p.k3 + (size_t)b * p.ldk3)[i];
     }
     {
@@ -186,7 +187,9 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
             if (on) {
                 const int e = e0 + filled + __popc(m & ((1u << lane) - 1u));
                 meta[e] = (uint16_t)((node0 + j) | (i << 8));
-                score[e] = 0.f;
+                // Eq. (8) scores are accumulated in phase 1; a vanilla-GAT score is complete here: fl(a1.h_j + a2.h_i)
+                score[e] = gat_s == nullptr ? 0.f
+                                            : gat_s[((size_t)b * n + node0 + j) * 2] + gat_s[((size_t)b * n + i) * 2 + 1];
             }
             filled += __popc(m);
         }
@@ -388,7 +391,7 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
 inline void sparse_geometry(int n, int D, int G, SparseGeom* g) {
     const int NB = G * n;
     g->G = G;
-    g->nch1 = (D + kSparseDc1 - 1) / kSparseDc1;
+    g->nch1 = (D + kSparseDc1 - 1) / kSparseDc1;                 // (the launcher zeroes it for vanilla-GAT scores)
     g->nch3 = (D + kSparseDc3 - 1) / kSparseDc3;
     g->tile_floats = ((NB * kSparseDc1 * 4 + 1023) / 1024) * 1024 / 4;
     g->unit_floats = 2 * g->tile_floats;
@@ -431,8 +434,10 @@ int launch_graph_layer_fwd_sparse(const PairAttnArgs& args, int n_src, cudaStrea
     CUtensorMap map1, map3;
     int rc;
     const int64_t src_graphs = indexed ? n_src : args.B;
-    if ((rc = make_tensor_map_2d(&map1, args.P, src_graphs * args.n, 3 * args.D, args.ldp, G * args.n, kSparseDc1, CU_TENSOR_MAP_SWIZZLE_128B)) != DIGAT_OK) return rc;
-    if ((rc = make_tensor_map_2d(&map3, args.P, src_graphs * args.n, 3 * args.D, args.ldp, G * args.n, kSparseDc3, CU_TENSOR_MAP_SWIZZLE_NONE)) != DIGAT_OK) return rc;
+    const int p_cols = args.gat_s != nullptr ? args.D : 3 * args.D;     // vanilla GAT: P = h only, no U | K2 loads
+    if (args.gat_s != nullptr) g.nch1 = 0;
+    if ((rc = make_tensor_map_2d(&map1, args.P, src_graphs * args.n, p_cols, args.ldp, G * args.n, kSparseDc1, CU_TENSOR_MAP_SWIZZLE_128B)) != DIGAT_OK) return rc;
+    if ((rc = make_tensor_map_2d(&map3, args.P, src_graphs * args.n, p_cols, args.ldp, G * args.n, kSparseDc3, CU_TENSOR_MAP_SWIZZLE_NONE)) != DIGAT_OK) return rc;
     const int grid = (args.B + G - 1) / G;
     if (indexed) {
         if (int rc_ = ensure_dynamic_smem(graph_layer_fwd_sparse_kernel<true, false>, (size_t)(g.smem))) return rc_;
@@ -445,6 +450,28 @@ int launch_graph_layer_fwd_sparse(const PairAttnArgs& args, int n_src, cudaStrea
         graph_layer_fwd_sparse_kernel<false, true><<<grid, kSparseThreads, g.smem, st>>>(map1, map3, args, g);
     }
     return check_launch("digat_graph_layer_fwd(sparse)");
+}
+
+// Vanilla-GAT layer of the ablation encoders (reference graphEncoders.py:494-503 / 511-520 and the two mixed variants):
+//   e_ij = leaky_relu(a1 . h_j + a2 . h_i);  alpha = softmax_j(mask(e));  Y = relu(alpha h) + X
+// on the edge-driven kernel: the score of an edge is one add of two precomputed dot products (gat_s), so the kernel
+// streams h only.
+inline int launch_gat_layer_fwd(const float* Hm, int ldh, const float* s12, const uint8_t* adj, const float* X, float* Y,
+                                int B, int n, int D, cudaStream_t st) {
+    if (B == 0) return DIGAT_OK;
+    DIGAT_REQUIRE(Hm && s12 && adj && X && Y, "digat_gat_layer_fwd: null pointer");
+    DIGAT_REQUIRE(B >= 0 && n >= 1 && n <= kPairMaxNodes, "digat_gat_layer_fwd: n=%d outside [1,%d]", n, kPairMaxNodes);
+    DIGAT_REQUIRE(D >= 4 && (D & 3) == 0 && D <= 1024, "digat_gat_layer_fwd: D=%d must be a multiple of 4 in [4,1024]", D);
+    DIGAT_REQUIRE((ldh & 3) == 0 && ldh >= D, "digat_gat_layer_fwd: ldh=%d must be a multiple of 4 and >= D", ldh);
+    DIGAT_REQUIRE(aligned16(Hm) && aligned16(X) && aligned16(Y), "digat_gat_layer_fwd: pointers must be 16-byte aligned");
+    const DeviceInfo* di = device_info();
+    if (!di) return fail(DIGAT_E_CUDA, "digat_gat_layer_fwd: no CUDA device");
+    DIGAT_REQUIRE(graph_layer_fwd_sparse_smem(n, D) <= (size_t)di->max_smem_optin,
+                  "digat_gat_layer_fwd: a graph of %d nodes x %d features does not fit one CTA", n, D);
+    PairAttnArgs args{Hm, ldh, nullptr, adj, X, Y, B, n, D, nullptr, 1.f, nullptr, nullptr, nullptr,
+                      nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr};
+    args.gat_s = s12;
+    return launch_graph_layer_fwd_sparse(args, B, st);
 }
 
 }  // namespace digat

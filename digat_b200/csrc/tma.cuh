@@ -2,6 +2,8 @@
 // host-side tensor-map encoder (cuTensorMapEncodeTiled through the runtime's driver entry point: no -lcuda needed).
 #pragma once
 #include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 #include <mutex>
 #include <unordered_map>
 #include "common.cuh"
@@ -43,12 +45,31 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
         :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
 
+#ifdef DIGAT_FAKE_TMA_ENCODER
+inline int& fake_encode_calls() { static int n = 0; return n; }
+#endif
 typedef CUresult (*PFN_tensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                              CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                              CUtensorMapFloatOOBfill);
 
+#ifdef DIGAT_FAKE_TMA_ENCODER   // host-only test harness of the descriptor cache (tests/cache_harness.cu): no driver needed
+inline CUresult fake_tensor_map_encode(CUtensorMap* m, CUtensorMapDataType, cuuint32_t, void* base, const cuuint64_t* gdim,
+                                       const cuuint64_t* gstride, const cuuint32_t* box, const cuuint32_t*,
+                                       CUtensorMapInterleave, CUtensorMapSwizzle sw, CUtensorMapL2promotion,
+                                       CUtensorMapFloatOOBfill) {
+    uint64_t* w = reinterpret_cast<uint64_t*>(m);
+    for (int i = 0; i < 16; ++i) w[i] = 0;
+    w[0] = reinterpret_cast<uintptr_t>(base); w[1] = gdim[0]; w[2] = gdim[1]; w[3] = gstride[0]; w[4] = box[0]; w[5] = box[1]; w[6] = sw;
+    ++fake_encode_calls();
+    return CUDA_SUCCESS;
+}
+#endif
+
 inline PFN_tensorMapEncodeTiled tensor_map_encoder() {
+#ifdef DIGAT_FAKE_TMA_ENCODER
+    return &fake_tensor_map_encode;
+#endif
     static PFN_tensorMapEncodeTiled fn = nullptr;
     if (fn == nullptr) {
         void* p = nullptr;
@@ -86,14 +107,16 @@ struct TensorMapKeyHash {
 
 inline int make_tensor_map_2d_any(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
                                   int box_cols, CUtensorMapSwizzle swizzle, CUtensorMapDataType dtype, int elem_bytes) {
+    static const bool no_cache = getenv("DIGAT_NO_DESC_CACHE") != nullptr;          // debugging aid
+    struct Blob { unsigned char bytes[sizeof(CUtensorMap)]; };   // plain bytes: CUtensorMap is alignas(64), map nodes need not be
     static std::mutex mu;
-    static std::unordered_map<TensorMapKey, CUtensorMap, TensorMapKeyHash> cache;
+    static std::unordered_map<TensorMapKey, Blob, TensorMapKeyHash> cache;
     const TensorMapKey key{base, rows, cols, ld, box_rows, box_cols, (int)swizzle, (int)dtype};
-    {
+    if (!no_cache) {
         std::lock_guard<std::mutex> lock(mu);
         auto it = cache.find(key);
         if (it != cache.end()) {
-            *map = it->second;
+            memcpy(map, it->second.bytes, sizeof(CUtensorMap));
             return DIGAT_OK;
         }
     }
@@ -106,9 +129,12 @@ inline int make_tensor_map_2d_any(CUtensorMap* map, const void* base, int64_t ro
     CUresult r = enc(map, dtype, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(DIGAT_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    if (no_cache) return DIGAT_OK;
+    Blob blob;
+    memcpy(blob.bytes, map, sizeof(CUtensorMap));
     std::lock_guard<std::mutex> lock(mu);
     if (cache.size() >= 4096) cache.clear();
-    cache.emplace(key, *map);
+    cache.emplace(key, blob);
     return DIGAT_OK;
 }
 
@@ -137,7 +163,7 @@ inline int ensure_dynamic_smem(Kernel kernel, size_t bytes) {
         auto it = done.find(key);
         if (it != done.end() && it->second >= bytes) return DIGAT_OK;
     }
-    if (int rc_ = ensure_dynamic_smem(kernel, (size_t)(bytes))) return rc_;
+    DIGAT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     std::lock_guard<std::mutex> lock(mu);
     done[key] = bytes;
     return DIGAT_OK;

@@ -31,7 +31,7 @@ extern "C" {
 #define DIGAT_E_CUDA        -2   /* a CUDA runtime/driver call or a launch failed */
 #define DIGAT_E_UNSUPPORTED -3   /* device is not sm_100 */
 
-#define DIGAT_ABI_VERSION 2
+#define DIGAT_ABI_VERSION 3
 
 int         digat_abi_version(void);
 const char* digat_last_error(void);
@@ -133,6 +133,14 @@ int digat_graph_layer_fwd(const float* P, int ldp, const float* a, const uint8_t
                           float* alpha_out, uint8_t* relu_mask_out, const int32_t* px_index, int n_src,
                           const int32_t* adj_index, const float* k3, int ldk3, const uint8_t* row_active,
                           float* Yc, const int32_t* row_pos, void* stream);
+/* Vanilla-GAT layer of the reference's ablation encoders (graphEncoders.py:494-503, 511-520, 640-649, 807-816:
+ * wo_interaction, news_graph_wo_inter, user_graph_wo_inter), inference:
+ *   Y = relu(softmax_j(mask(leaky_relu(a1 . h_j + a2 . h_i))) * h) + X
+ *   Hm [B*n, ldh] = h = W x + b;  s12 [B*n, 2]: s12[r][0] = a1 . h_r (neighbour term), s12[r][1] = a2 . h_r (query term),
+ *   both from digat_linear_* ; adj [B,n,n]; X, Y [B,n,D].  Same edge-driven kernel as digat_graph_layer_fwd: an edge's score
+ *   is one fp32 add, only h is streamed. */
+int digat_gat_layer_fwd(const float* Hm, int ldh, const float* s12, const uint8_t* adj, const float* X, float* Y,
+                        int B, int n, int D, void* stream);
 /* 1 if an inference call of digat_graph_layer_fwd with these sizes takes the kernel that honours row_active, else 0. */
 int digat_graph_layer_supports_row_active(int n, int D, int B);
 /* Node pruning flags for user graphs: active [G,n] = 0 iff node i's layer output is unobservable: no other node has
