@@ -620,3 +620,8 @@ class DIGAT(GraphEncoder):
         w = self._weights()               # (inference branch only: the training path packs its own, differentiable, layout)
         with torch.no_grad():
             return self._encode(w, Xn, An, Mn, self._user_nodes(w, Xh), Au, Mc, ci, None)
+
+
+# The reference keeps its five ablation encoders in the same module (graphEncoders.py:201-842) and model.py:20-29 looks
+# them up here by name: re-export them so that `from digat_b200 import graphEncoders` stays a one-line swap.
+from .ablation_encoders import (News_graph_wo_inter, Seq_SA, User_graph_wo_inter, wo_interaction, wo_SA)  # noqa: E402,F401

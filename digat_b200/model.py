@@ -11,9 +11,10 @@ from . import _lib, graphEncoders
 class Model(nn.Module):
     def __init__(self, config, news_embedding_dim: int = 400):
         super().__init__()
-        if config.graph_encoder != 'DIGAT':
+        from .ablation_encoders import ENCODERS                                 # the string dispatch of model.py:18-31
+        if config.graph_encoder not in ENCODERS:
             raise Exception(config.graph_encoder + ' is not implemented')      # same wording as model.py:31
-        self.graph_encoder = graphEncoders.DIGAT(config, news_embedding_dim)
+        self.graph_encoder = ENCODERS[config.graph_encoder](config, news_embedding_dim)
         self.model_name = getattr(config, 'news_encoder', 'MSA') + '-' + config.graph_encoder
         self.max_history_num = config.max_history_num
         self.category_num = config.category_num + 1

@@ -46,7 +46,7 @@ class Scorer:
         self.news_graph = t(corpus.news_graph)                  # [N,n_n,n_n] bool
         self.news_mask = t(corpus.news_graph_mask)              # [N,n_n] bool (util.py:35)
         self.history = t(corpus.history)                        # [Nb,H] int32
-        if build_user_graphs_on_device:
+        if build_user_graphs_on_device or corpus.user_graph is None:
             from . import graphs
             H = corpus.history.shape[1]
             C = encoder.category_num - 1 if hasattr(encoder, 'category_num') else corpus.user_category_mask.shape[1] - 1
@@ -231,12 +231,20 @@ class Scorer:
         self.enc.check_index_errors()
 
 
-def host_batch(corpus, pair_ids, pin=False):
-    """The 7 host tensors the reference's MIND_DevTest_Dataset + DataLoader yield for these pairs (MIND_dataset.py:97-102)."""
+def host_batch(corpus, pair_ids, pin=False, config=None):
+    """The 7 host tensors the reference's MIND_DevTest_Dataset + DataLoader yield for these pairs (MIND_dataset.py:97-102).
+    config: needed only for a corpus made without host user graphs (synth.make_corpus(build_user_graph=False))."""
     b = corpus.pair_behavior[pair_ids]
     nid = corpus.pair_news[pair_ids]
-    out = (torch.from_numpy(corpus.history[b]), torch.from_numpy(corpus.user_graph[b]),
-           torch.from_numpy(corpus.user_category_mask[b]), torch.from_numpy(corpus.user_category_indices[b]),
+    if corpus.user_graph is None:
+        from . import synth
+        ub, inv = np.unique(b, return_inverse=True)
+        g, cm, ci = synth.user_graphs_of(corpus, config, ub)
+        ug, ucm, uci = g[inv], cm[inv], ci[inv]
+    else:
+        ug, ucm, uci = corpus.user_graph[b], corpus.user_category_mask[b], corpus.user_category_indices[b]
+    out = (torch.from_numpy(corpus.history[b]), torch.from_numpy(ug),
+           torch.from_numpy(ucm), torch.from_numpy(uci),
            torch.from_numpy(nid.astype(np.int64)), torch.from_numpy(corpus.news_graph[nid]),
            torch.from_numpy(corpus.news_graph_mask[nid]))
     if pin:

@@ -29,12 +29,12 @@ def sag_size(neighbors: int, hops: int) -> int:
 
 
 def make_config(SAG_neighbors=3, SAG_hops=2, graph_depth=3, max_history_num=50, category_num=18,
-                dropout_rate=0.2, **extra):
+                dropout_rate=0.2, graph_encoder='DIGAT', news_encoder='MSA', **extra):
     """Duck-typed stand-in for reference config.Config (which needs a GPU and the datasets, config.py:84)."""
     return SimpleNamespace(SAG_neighbors=SAG_neighbors, SAG_hops=SAG_hops,
                            news_graph_size=sag_size(SAG_neighbors, SAG_hops), graph_depth=graph_depth,
                            max_history_num=max_history_num, category_num=category_num,
-                           dropout_rate=dropout_rate, graph_encoder='DIGAT', news_encoder='MSA', **extra)
+                           dropout_rate=dropout_rate, graph_encoder=graph_encoder, news_encoder=news_encoder, **extra)
 
 
 def _xavier(rng, out_f, in_f, gain=1.0):
@@ -78,6 +78,54 @@ def make_state_dict(config, D=400, seed=0, trained_like=True):
             sd[p + 'ffn3.%d.weight' % i] = _xavier(rng, D, D, relu_gain)
             sd[p + 'ffn3.%d.bias' % i] = bias(D)
             sd[p + 'a.%d.weight' % i] = _xavier(rng, 1, D, leaky_gain)
+    return {k: torch.from_numpy(v) for k, v in sd.items()}
+
+
+# graph_encoder name -> (has news context, news layer kind, user layer kind); reference graphEncoders.py:201-842
+ABLATIONS = {
+    'wo_SA': (False, None, 'digat'),
+    'Seq_SA': (True, None, 'digat'),
+    'wo_interaction': (True, 'gat', 'gat'),
+    'news_graph_wo_inter': (True, 'gat', 'digat'),
+    'user_graph_wo_inter': (True, 'digat', 'gat'),
+}
+
+
+def make_ablation_state_dict(kind, config, D=400, seed=0):
+    """Seeded trained-like state_dict of one ablation encoder (parameter names/shapes of reference
+    graphEncoders.py:201-842; biases and topic nodes non-zero so that every code path matters)."""
+    has_ctx, news_kind, user_kind = ABLATIONS[kind]
+    rng = np.random.Generator(np.random.PCG64(seed + 77))
+    relu_gain, leaky_gain = np.sqrt(2.0), np.sqrt(2.0 / (1 + 0.2 ** 2))
+    bias = lambda n: rng.normal(0, 0.05, size=n).astype(np.float32)          # noqa: E731
+    sd = {'topic_node_embedding': rng.normal(0, 0.1, size=(config.category_num, D)).astype(np.float32)}
+    atts = (['candidate_attention'] if has_ctx else []) + ['userAttention']
+    for att in atts:
+        sd[att + '.K.weight'] = _xavier(rng, D, D)
+        sd[att + '.Q.weight'] = _xavier(rng, D, D)
+        sd[att + '.Q.bias'] = bias(D)
+    if has_ctx:
+        sd['news_graph_W.weight'] = _xavier(rng, D, 2 * D)
+        sd['news_graph_W.bias'] = bias(D)
+    sd['user_news_K.weight'] = _xavier(rng, D, D)
+    sd['user_news_Q.weight'] = _xavier(rng, D, D)
+    sd['user_news_Q.bias'] = bias(D)
+    sd['featureAffine.weight'] = _xavier(rng, D, D, relu_gain)
+    sd['featureAffine.bias'] = bias(D)
+    for g, k in (('news', news_kind), ('user', user_kind)):
+        p = '%s_graph_attention_' % g
+        for i in range(config.graph_depth if k else 0):
+            sd[p + 'W.%d.weight' % i] = _xavier(rng, D, D)
+            sd[p + 'W.%d.bias' % i] = bias(D)
+            if k == 'digat':
+                sd[p + 'ffn1.%d.weight' % i] = _xavier(rng, D, D, relu_gain)
+                sd[p + 'ffn2.%d.weight' % i] = _xavier(rng, D, D, relu_gain)
+                sd[p + 'ffn3.%d.weight' % i] = _xavier(rng, D, D, relu_gain)
+                sd[p + 'ffn3.%d.bias' % i] = bias(D)
+                sd[p + 'a.%d.weight' % i] = _xavier(rng, 1, D, leaky_gain)
+            else:
+                sd[p + 'a1.%d.weight' % i] = _xavier(rng, 1, D, leaky_gain)
+                sd[p + 'a2.%d.weight' % i] = _xavier(rng, 1, D, leaky_gain)
     return {k: torch.from_numpy(v) for k, v in sd.items()}
 
 
@@ -138,7 +186,12 @@ def make_sag(rng, n_news, n_n, neighbors, hops):
 
 
 def make_corpus(config, D=400, n_news=2000, n_behaviors=64, mean_candidates=8.0, seed=0, emb_scale=0.3,
-                nonneg=False) -> Corpus:
+                nonneg=False, behavior_seed=None, build_user_graph=True) -> Corpus:
+    """behavior_seed: draw the behaviours / pairs from their own generator (ranks of a sharded run then hold the SAME news
+    side and DIFFERENT behaviour shards); None keeps the single generator sequence the golden fixtures were made with.
+    build_user_graph=False leaves user_graph / user_category_mask / user_category_indices as None (at MIND-large size the
+    [N_beh, 68, 68] array is 11 GB on the host): build them on the device (Scorer(build_user_graphs_on_device=True)) or per
+    batch (user_graphs_of)."""
     rng = np.random.Generator(np.random.PCG64(seed + 1000))
     H, C, n_n = config.max_history_num, config.category_num, config.news_graph_size
     emb = rng.normal(0, emb_scale, size=(n_news, D)).astype(np.float32)
@@ -146,12 +199,14 @@ def make_corpus(config, D=400, n_news=2000, n_behaviors=64, mean_candidates=8.0,
         emb = np.maximum(emb, 0)
     news_cat = _zipf_categories(rng, n_news, C)
     node, adj, mask = make_sag(rng, n_news, n_n, config.SAG_neighbors, config.SAG_hops)
+    if behavior_seed is not None:
+        rng = np.random.Generator(np.random.PCG64(behavior_seed + 5000))
     hist_len = rng.integers(0, H + 1, size=n_behaviors)
     hist_len[rng.random(n_behaviors) < 0.03] = 0
     history = rng.integers(1, n_news, size=(n_behaviors, H)).astype(np.int32)
     history[np.arange(H)[None, :] >= hist_len[:, None]] = 0
     hist_cat = np.where(np.arange(H)[None, :] < hist_len[:, None], news_cat[history], C).astype(np.int64)
-    ug, cmask, cidx = graphs.build_user_graphs(hist_cat, hist_len, H, C)
+    ug, cmask, cidx = graphs.build_user_graphs(hist_cat, hist_len, H, C) if build_user_graph else (None, None, None)
     n_cand = np.maximum(1, rng.geometric(1.0 / mean_candidates, size=n_behaviors))
     pair_beh = np.repeat(np.arange(n_behaviors, dtype=np.int32), n_cand)
     pair_news = rng.integers(1, n_news, size=pair_beh.shape[0]).astype(np.int32)
@@ -161,6 +216,16 @@ def make_corpus(config, D=400, n_news=2000, n_behaviors=64, mean_candidates=8.0,
     two = n_cand >= 2
     labels[first[two] + 1] = 0                                   # ... and, when it can, a negative (AUC defined)
     return Corpus(emb, node, adj, mask, history, hist_cat, ug, cmask, cidx, pair_beh, pair_news, labels)
+
+
+def user_graphs_of(corpus: Corpus, config, behaviors: np.ndarray):
+    """(user_graph, category_mask, category_indices) of the given behaviours: slices of the corpus arrays, or built on the
+    fly from the history categories when the corpus was made with build_user_graph=False."""
+    if corpus.user_graph is not None:
+        return corpus.user_graph[behaviors], corpus.user_category_mask[behaviors], corpus.user_category_indices[behaviors]
+    H, C = config.max_history_num, config.category_num
+    cat = corpus.history_category[behaviors]
+    return graphs.build_user_graphs(cat, (cat < C).sum(axis=1), H, C)
 
 
 def _zipf_categories(rng, n, C):

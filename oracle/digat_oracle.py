@@ -11,6 +11,7 @@ Each function cites the reference lines it follows (paths relative to /root/refe
 * ``graph_layer``        -- graphEncoders.py:143-154 / 163-174   (Eq. (8) at :150 / :170)
 * ``inference``          -- graphEncoders.py:189-198  + model.py:87-90 (logits)
 * ``forward``            -- graphEncoders.py:177-187  + model.py:73-77 (eval / p=0 semantics, dropout omitted)
+* ``gat_layer`` / ``ablation_inference`` / ``ablation_forward`` -- the five ablation encoders, graphEncoders.py:201-842
 * ``gather_*``           -- util.py:34-36, 65-67
 * ``rank_lists`` / ``metrics`` -- util.py:70-80 + evaluate.py:32-89
 * ``user_graph_loops``   -- MIND_corpus.py:143-176 (literal loops; integer oracle)
@@ -129,6 +130,59 @@ def forward(P, news_graph_embeddings, news_graph, news_graph_mask, user_news_emb
 
 def logits(news_ctx, user_ctx):
     return (user_ctx * news_ctx).sum(dim=1)
+
+
+# ----------------------------------------------------------------------------- ablation encoders (graphEncoders.py:201-842)
+def gat_layer(P, g, i, X, adj):
+    """Vanilla-GAT layer of wo_interaction / News_graph_wo_inter / User_graph_wo_inter (graphEncoders.py:494-503, 511-520,
+    640-649, 807-816): a1 broadcasts over rows (neighbour term), a2 over columns (query term)."""
+    p = '%s_graph_attention_' % g
+    B, n, _ = X.shape
+    h = _lin(X, P[p + 'W.%d.weight' % i], P[p + 'W.%d.bias' % i])
+    a1 = _lin(h, P[p + 'a1.%d.weight' % i]).view(B, 1, n)
+    a2 = _lin(h, P[p + 'a2.%d.weight' % i])
+    e = F.leaky_relu(a1 + a2, LEAKY_SLOPE)
+    alpha = F.softmax(e.masked_fill(adj == 0, NEG_FILL), dim=2)
+    return F.relu(torch.bmm(alpha, h)) + X
+
+
+ABLATION_LAYERS = {            # name -> (news layer kind, user layer kind)
+    'wo_interaction': ('gat', 'gat'), 'news_graph_wo_inter': ('gat', 'digat'), 'user_graph_wo_inter': ('digat', 'gat'),
+}
+
+
+def ablation_inference(kind, P, news_graph_embeddings, news_graph, news_graph_mask, user_news_embedding, user_graph,
+                       user_category_mask, user_category_indices, news_graph_context_0):
+    """``inference`` of the five ablation encoders; same argument order as the reference."""
+    H = user_news_embedding.shape[1]
+    X_n, X_u = news_graph_embeddings, _user_nodes(P, user_news_embedding)
+    L = 1 + max(int(k.split('.')[1]) for k in P if k.startswith('user_graph_attention_W.'))
+    if kind == 'wo_SA':                                                       # graphEncoders.py:288-295
+        cand = X_n.select(1, 0)
+        for i in range(L):
+            X_u = graph_layer(P, 'user', i, X_u, user_graph, cand)
+        return cand, user_graph_context(P, X_u, user_category_mask, user_category_indices, cand, H)
+    c_n = news_graph_context_0
+    c_u = user_graph_context(P, X_u, user_category_mask, user_category_indices, c_n, H)
+    if kind == 'Seq_SA':                                                      # graphEncoders.py:400-407
+        for i in range(L):
+            X_u = graph_layer(P, 'user', i, X_u, user_graph, c_n)
+            c_u = c_u + user_graph_context(P, X_u, user_category_mask, user_category_indices, c_n, H)
+        return c_n, c_u
+    news_kind, user_kind = ABLATION_LAYERS[kind]                              # graphEncoders.py:537-548, 685-695, 832-842
+    for i in range(L):
+        X_n_new = gat_layer(P, 'news', i, X_n, news_graph) if news_kind == 'gat' else graph_layer(P, 'news', i, X_n, news_graph, c_u)
+        X_u = gat_layer(P, 'user', i, X_u, user_graph) if user_kind == 'gat' else graph_layer(P, 'user', i, X_u, user_graph, c_n)
+        X_n = X_n_new
+        c_n = c_n + news_graph_context(P, X_n, news_graph_mask)
+        c_u = c_u + user_graph_context(P, X_u, user_category_mask, user_category_indices, c_n, H)
+    return c_n, c_u
+
+
+def ablation_forward(kind, P, news_graph_embeddings, news_graph, news_graph_mask, *user_args):
+    """``forward`` (eval / p=0): the initial news context is computed instead of read from the cache."""
+    c_n0 = None if kind == 'wo_SA' else news_graph_context(P, news_graph_embeddings, news_graph_mask)
+    return ablation_inference(kind, P, news_graph_embeddings, news_graph, news_graph_mask, *user_args, c_n0)
 
 
 # ----------------------------------------------------------------------------- gathers (util.py:34-36, 65-67)

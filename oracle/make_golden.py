@@ -101,6 +101,58 @@ def make_encoder_cases(ge):
         print(name, {k: v.shape for k, v in payload.items() if k != 'meta'})
 
 
+ABLATION_CLASSES = {'wo_SA': 'wo_SA', 'Seq_SA': 'Seq_SA', 'wo_interaction': 'wo_interaction',
+                    'news_graph_wo_inter': 'News_graph_wo_inter', 'user_graph_wo_inter': 'User_graph_wo_inter'}
+# name -> (SAG_neighbors, SAG_hops, depth, rows)
+ABLATION_CASES = {'n3_L2': (3, 2, 2, 5), 'n5_L3': (5, 2, 3, 3)}
+
+
+def ablation_inputs(kind, case):
+    N, hops, L, rows = ABLATION_CASES[case]
+    cfg = synth.make_config(SAG_neighbors=N, SAG_hops=hops, graph_depth=L, graph_encoder=kind)
+    sd = synth.make_ablation_state_dict(kind, cfg, seed=13)
+    corpus = synth.make_corpus(cfg, n_news=300, n_behaviors=12, mean_candidates=3.0, seed=6)
+    rng = np.random.Generator(np.random.PCG64(98))
+    ids = rng.choice(corpus.pair_behavior.shape[0], size=rows, replace=False)
+    empty = np.nonzero(~corpus.user_category_mask.any(axis=1))[0]
+    if len(empty):
+        hit = np.nonzero(corpus.pair_behavior == empty[0])[0]
+        if len(hit):
+            ids[0] = hit[0]
+    return cfg, sd, synth.make_batch(corpus, np.sort(ids))
+
+
+def make_ablation_cases(ge):
+    """The five ablation encoders of the unmodified reference (graphEncoders.py:201-842): inference, forward (eval) and
+    the first user/news layer outputs."""
+    for kind, cls in ABLATION_CLASSES.items():
+        for case in ABLATION_CASES:
+            cfg, sd, batch = ablation_inputs(kind, case)
+            payload = {'meta': np.frombuffer(json.dumps(input_hashes(sd, batch)).encode(), dtype=np.uint8)}
+            for tag, dt in (('ref32_', torch.float32), ('ref64_', torch.float64)):
+                m = getattr(ge, cls)(cfg, 400)
+                m.load_state_dict(sd)
+                m = m.to(dt).eval()
+                b = {k: (v.to(dt) if v.is_floating_point() else v) for k, v in batch.items()}
+                args = (b['news_graph_embeddings'], b['news_graph'], b['news_graph_mask'], b['user_news_embedding'],
+                        b['user_graph'], b['user_category_mask'], b['user_category_indices'])
+                with torch.no_grad():
+                    if kind == 'wo_SA':
+                        c_n0 = torch.zeros(args[0].shape[0], 400, dtype=dt)
+                    elif kind == 'Seq_SA':
+                        c_n0 = m.compute_news_sequence_context(args[0], args[2])
+                    else:
+                        c_n0 = m.compute_news_graph_context(args[0], args[2])
+                    cn, cu = m.inference(*args, c_n0)
+                    fn, fu = m.forward(*args)
+                    out = {'c_n0': c_n0, 'news_ctx': cn, 'user_ctx': cu, 'fwd_news_ctx': fn, 'fwd_user_ctx': fu,
+                           'logits': (cu * cn).sum(dim=1)}
+                for k, v in out.items():
+                    payload[tag + k] = v.numpy()
+            np.savez_compressed(os.path.join(GOLDEN, 'ablation_%s_%s.npz' % (kind, case)), **payload)
+            print(kind, case, {k: v.shape for k, v in payload.items() if k != 'meta'})
+
+
 def make_sag_case(sag):
     """construct_SAG.generate_news_graph on a seeded similarity table (integer golden vectors)."""
     rng = np.random.Generator(np.random.PCG64(7))
@@ -160,6 +212,12 @@ if __name__ == '__main__':
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(1)   # fixed reduction partitioning inside MKL/ATen -> reproducible fp32 vectors
     ge, layers, ev, sag = load_reference()
-    make_encoder_cases(ge)
-    make_sag_case(sag)
-    make_metric_case(ev)
+    which = sys.argv[1:] or ['encoder', 'ablation', 'sag', 'metrics']
+    if 'encoder' in which:
+        make_encoder_cases(ge)
+    if 'ablation' in which:
+        make_ablation_cases(ge)
+    if 'sag' in which:
+        make_sag_case(sag)
+    if 'metrics' in which:
+        make_metric_case(ev)

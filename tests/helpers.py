@@ -92,3 +92,29 @@ def err_stats(got, ref, terms=None, floor_frac=1e-3):
 
 def fmt_stats(s):
     return ', '.join('%s %s' % (k, ('%d' % v) if k == 'max_ulp' else ('%.2e' % v)) for k, v in s.items())
+
+
+# must match oracle/make_golden.py::ABLATION_CASES
+ABLATION_KINDS = ('wo_SA', 'Seq_SA', 'wo_interaction', 'news_graph_wo_inter', 'user_graph_wo_inter')
+ABLATION_CASES = {'n3_L2': (3, 2, 2, 5), 'n5_L3': (5, 2, 3, 3)}
+
+
+def ablation_inputs(kind, case):
+    """Same construction as oracle/make_golden.py::ablation_inputs."""
+    N, hops, L, rows = ABLATION_CASES[case]
+    cfg = synth.make_config(SAG_neighbors=N, SAG_hops=hops, graph_depth=L, graph_encoder=kind)
+    sd = synth.make_ablation_state_dict(kind, cfg, seed=13)
+    corpus = synth.make_corpus(cfg, n_news=300, n_behaviors=12, mean_candidates=3.0, seed=6)
+    rng = np.random.Generator(np.random.PCG64(98))
+    ids = rng.choice(corpus.pair_behavior.shape[0], size=rows, replace=False)
+    empty = np.nonzero(~corpus.user_category_mask.any(axis=1))[0]
+    if len(empty):
+        hit = np.nonzero(corpus.pair_behavior == empty[0])[0]
+        if len(hit):
+            ids[0] = hit[0]
+    return cfg, sd, synth.make_batch(corpus, np.sort(ids))
+
+
+def load_ablation_golden(kind, case):
+    z = np.load(os.path.join(GOLDEN, 'ablation_%s_%s.npz' % (kind, case)))
+    return z, json.loads(bytes(z['meta']).decode())

@@ -1,0 +1,67 @@
+"""GPU parity of the five ablation graph encoders (reference graphEncoders.py:201-842; ``--graph_encoder`` = wo_SA, Seq_SA,
+wo_interaction, news_graph_wo_inter, user_graph_wo_inter) against golden vectors of the UNMODIFIED reference classes
+(tests/golden/ablation_*.npz, oracle/make_golden.py) -- as given (small batches: exact-fp32 GEMMs) and replicated x64 (all
+projections on the tcgen05 GEMM, several graphs per CTA in the vanilla-GAT layer kernel)."""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import ABLATION_CASES, ABLATION_KINDS, ablation_inputs, check_hashes, load_ablation_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+ORDER = ('news_graph_embeddings', 'news_graph', 'news_graph_mask', 'user_news_embedding', 'user_graph',
+         'user_category_mask', 'user_category_indices')
+TOL = 1e-5
+
+
+@pytest.mark.parametrize('rep', [1, 64])
+@pytest.mark.parametrize('case', list(ABLATION_CASES))
+@pytest.mark.parametrize('kind', ABLATION_KINDS)
+def test_ablation_encoder_matches_reference_golden(kind, case, rep):
+    from digat_b200.ablation_encoders import ENCODERS
+    from digat_b200.model import Model, logits
+    cfg, sd, batch = ablation_inputs(kind, case)
+    z, meta = load_ablation_golden(kind, case)
+    check_hashes(meta, sd, batch)
+    model = Model(cfg, 400)                                   # the graph_encoder string dispatch (reference model.py:18-31)
+    assert type(model.graph_encoder) is ENCODERS[kind]
+    model.graph_encoder.load_state_dict(sd)
+    enc = model.graph_encoder.cuda().eval()
+    B = batch['news_graph'].shape[0]
+    b = {k: v.cuda().repeat(rep, *([1] * (v.dim() - 1))) for k, v in batch.items()}
+    args = [b[k] for k in ORDER]
+    c_n0 = torch.from_numpy(z['ref32_c_n0']).cuda().repeat(rep, 1)
+    with torch.no_grad():
+        if kind == 'Seq_SA':
+            c0 = enc.compute_news_sequence_context(b['news_graph_embeddings'], b['news_graph_mask'])
+        elif kind != 'wo_SA':
+            c0 = enc.compute_news_graph_context(b['news_graph_embeddings'], b['news_graph_mask'])
+        else:
+            c0 = None
+        cn, cu = enc.inference(*args, c_n0)
+        fn, fu = enc(*args)
+        lg = logits(cn.contiguous(), cu)
+        lm = model.inference(b['user_news_embedding'], b['user_graph'], b['user_category_mask'], b['user_category_indices'],
+                             b['news_graph_embeddings'], b['news_graph'], b['news_graph_mask'], c_n0)
+    torch.cuda.synchronize()
+    enc.check_index_errors()
+    got = {'news_ctx': cn, 'user_ctx': cu, 'fwd_news_ctx': fn, 'fwd_user_ctx': fu, 'logits': lg}
+    if c0 is not None:
+        got['c_n0'] = c0
+    for k, v in got.items():
+        v = v.cpu().numpy()
+        for r in (0, rep - 1):
+            e = rel_err(v[r * B:(r + 1) * B], z['ref32_' + k])
+            assert e < TOL, '%s/%s/%s x%d: rel err vs fp32 reference %.3e' % (kind, case, k, rep, e)
+    assert torch.equal(lm, lg)
+
+
+def test_ablation_encoders_refuse_to_train():
+    from digat_b200 import synth
+    from digat_b200.ablation_encoders import wo_interaction
+    cfg, sd, batch = ablation_inputs('wo_interaction', 'n3_L2')
+    enc = wo_interaction(cfg, 400)
+    enc.load_state_dict(sd)
+    enc = enc.cuda().train()
+    with pytest.raises(RuntimeError):
+        enc(*[batch[k].cuda() for k in ORDER])

@@ -103,3 +103,27 @@ def test_user_graph_vectorised_builder_bit_exact():
         g0, cm0, ci0 = O.user_graph_loops(cats[n], int(lens[n]), H, C)
         assert np.array_equal(g[n], g0) and np.array_equal(cm[n], cm0) and np.array_equal(ci[n], ci0)
     assert g.dtype == bool and cm.dtype == bool and ci.dtype == np.int64
+
+
+@pytest.mark.parametrize('case', ['n3_L2', 'n5_L3'])
+@pytest.mark.parametrize('kind', ['wo_SA', 'Seq_SA', 'wo_interaction', 'news_graph_wo_inter', 'user_graph_wo_inter'])
+def test_ablation_oracle_matches_reference_golden(kind, case):
+    """The restatement of the five ablation encoders (reference graphEncoders.py:201-842) against the outputs of the
+    unmodified reference classes: bit-for-bit (same torch ops, same order, one thread)."""
+    from tests.helpers import ablation_inputs, load_ablation_golden
+    torch.set_num_threads(1)
+    cfg, sd, batch = ablation_inputs(kind, case)
+    z, meta = load_ablation_golden(kind, case)
+    check_hashes(meta, sd, batch)
+    order = ('news_graph_embeddings', 'news_graph', 'news_graph_mask', 'user_news_embedding', 'user_graph',
+             'user_category_mask', 'user_category_indices')
+    for tag, dt in (('ref32_', torch.float32), ('ref64_', torch.float64)):
+        P = O.cast_params(sd, dt)
+        a = [batch[k].to(dt) if batch[k].is_floating_point() else batch[k] for k in order]
+        with torch.no_grad():
+            cn, cu = O.ablation_inference(kind, P, *a, torch.from_numpy(z[tag + 'c_n0']))
+            fn, fu = O.ablation_forward(kind, P, *a)
+        got = {'news_ctx': cn, 'user_ctx': cu, 'fwd_news_ctx': fn, 'fwd_user_ctx': fu, 'logits': O.logits(cn, cu)}
+        for k, v in got.items():
+            assert np.array_equal(v.numpy(), z[tag + k]), '%s%s differs from the reference (rel %.3e)' % (
+                tag, k, rel_err(v.numpy(), z[tag + k]))
