@@ -9,6 +9,10 @@ synthetic MIND-small-dev-sized corpus (BASELINE.json configs[1]; SURVEY.md secti
   value : pairs/s with the corpus resident in HBM (pair = (behaviour index, news id); gathers + encoder + logits)
   e2e   : pairs/s through scoring.score_host_batches with HOST (pinned) per-pair tensors, H2D + D2H inside the timing
           (both drivers stage batch k+1 on a side stream while batch k is encoded)
+  sustained : the same resident path run back to back for >= --sustained seconds (median SM clock / throttle reasons of
+          that window) next to the 20-step burst
+  train : BASELINE.json configs[2] -- fwd+bwd+clip+Adam on 64 behaviours x 5 candidates per GPU, DDP/NCCL gradient
+          all-reduce when N>1: samples/s, per-kernel table, CPU-oracle fwd+bwd baseline (N=1), 1-vs-N gradient equality (N>1)
 One JSON line on stdout (rank 0).
 """
 import argparse
@@ -31,7 +35,12 @@ WORKLOADS = {
     'mind_small_dev_n3_L3': (3, 2, 3, 65238, 73152, 37.5),       # BASELINE.json configs[1]
     'mind_small_dev_n5_L3': (5, 2, 3, 65238, 73152, 37.5),       # the reference's argparse default (config.py:53)
     'wide_n8_L7': (8, 2, 7, 65238, 73152, 37.5),                 # BASELINE.json configs[3]
+    # BASELINE.json configs[4] at FULL size (scale factor 1.0): 161 013 news, 2.37 M behaviours, ~8.8e7 pairs in total.
+    # Every rank holds the whole news side and generates + holds only ITS contiguous 1/N shard of the behaviours (their
+    # [N_beh,68,68] graphs are built on the device from 200 B/behaviour of category ids).
+    'mind_large_8gpu': (3, 2, 3, 161013, 2370000, 37.0),
 }
+SHARDED_WORKLOADS = ('mind_large_8gpu',)
 
 
 def algorithmic_bytes_per_pair(n_n, n_u, L, H=50, C=18):
@@ -92,24 +101,40 @@ class ClockSampler(threading.Thread):
         except Exception:
             pass
 
-    def stop(self):
-        self._stop_flag = True
-        if self.proc is not None:
-            self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace('.', '').isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace('.', '').isdigit()]
+    def mark(self):
+        """Index of the next sample (windows of the sample list: stats(lo, hi))."""
+        return len(self.rows)
+
+    def stats(self, lo=0, hi=None):
+        rows = self.rows[lo:hi]
+        sm = [float(r[0]) for r in rows if len(r) >= 7 and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) >= 7 and r[1].replace('.', '').isdigit()]
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i] == 'Active' for r in self.rows)]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i] == 'Active' for r in rows)]
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
                 'reasons': reasons, 'samples': len(sm)}
 
+    def stop(self, lo=0, hi=None):
+        self._stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+        return self.stats(lo, hi)
 
-def build_workload(name, seed=0):
+
+def build_workload(name, seed=0, rank=0, world=1):
+    """-> (config, state_dict, corpus).  Sharded workloads generate only this rank's 1/world of the behaviours (same news
+    side on every rank); the others generate the whole corpus and shard the ordered pair list (scoring.shard_range)."""
     from digat_b200 import synth
     N, hops, L, n_news, n_beh, cand = WORKLOADS[name]
     cfg = synth.make_config(SAG_neighbors=N, SAG_hops=hops, graph_depth=L)
     sd = synth.make_state_dict(cfg, D=D, seed=seed)
-    corpus = synth.make_corpus(cfg, D=D, n_news=n_news, n_behaviors=n_beh, mean_candidates=cand, seed=seed)
+    if name in SHARDED_WORKLOADS:
+        per = (n_beh + world - 1) // world
+        mine = max(0, min(per, n_beh - rank * per))
+        corpus = synth.make_corpus(cfg, D=D, n_news=n_news, n_behaviors=mine, mean_candidates=cand, seed=seed,
+                                   behavior_seed=seed + rank, build_user_graph=False)
+    else:
+        corpus = synth.make_corpus(cfg, D=D, n_news=n_news, n_behaviors=n_beh, mean_candidates=cand, seed=seed)
     return cfg, sd, corpus
 
 
@@ -157,6 +182,28 @@ def run_reference_arm(args):
     }))
 
 
+def _dist_env():
+    return int(os.environ.get('RANK', '0')), int(os.environ.get('LOCAL_RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))
+
+
+def _max_over_ranks(ms, world, dev):
+    if world == 1:
+        return ms
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _peaks():
+    peaks = {}
+    pk = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(pk):
+        peaks = json.load(open(pk))
+    return (float(peaks.get('hbm_gbs', 6650.0)),
+            float(peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops', 1590.0))),
+            'measured (MEASURED_PEAKS.json)' if peaks else 'fallback (B200_PROFILING.md)')
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -167,34 +214,45 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--cpu-budget', type=float, default=12.0, help='seconds of CPU-oracle timing for cpu_baseline')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--sustained', type=float, default=5.0,
+                    help='seconds of back-to-back resident steps for the `sustained` sub-record (0 = skip)')
+    ap.add_argument('--no-train', action='store_true', help='score mode: skip the `train` sub-record')
+    ap.add_argument('--train-steps', type=int, default=20)
     ap.add_argument('--eager-train', action='store_true',
-                    help='train mode: run the step eagerly instead of replaying it as one CUDA graph')
+                    help='train: run the step eagerly instead of replaying it as one CUDA graph')
     ap.add_argument('--mode', default='score', choices=['score', 'train'],
-                    help="'score' = the headline metric; 'train' = fwd+bwd(+DDP all-reduce)+Adam step, samples/s")
+                    help="'score' = the headline metric (+ sustained + train sub-records); 'train' = only the training record "
+                         "(fwd+bwd(+DDP all-reduce)+clip+Adam step, samples/s) as the line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
 
     if args.impl == 'reference':
         run_reference_arm(args)
         return
-    if args.mode == 'train':
-        run_train(args)
-        return
 
-    rank = int(os.environ.get('RANK', '0'))
-    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank, local_rank, world = _dist_env()
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group('nccl', device_id=dev)
-
-    from digat_b200 import _lib, scoring
-    from digat_b200.graphEncoders import DIGAT
+        torch.distributed.init_process_group('nccl', device_id=dev)
+    from digat_b200 import _lib
     _lib.require_device(local_rank)           # fails loudly without the sm_100a library / device
 
-    cfg, sd, corpus = build_workload(args.workload)
+    if args.mode == 'train':
+        rec = train_record(args, rank, local_rank, world, dev, steps=args.steps, cpu_baseline=not args.no_cpu_baseline)
+        if rank == 0:
+            print(json.dumps(rec))
+    else:
+        run_score(args, rank, local_rank, world, dev)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def run_score(args, rank, local_rank, world, dev):
+    from digat_b200 import _lib, scoring
+    from digat_b200.graphEncoders import DIGAT
+
+    cfg, sd, corpus = build_workload(args.workload, rank=rank, world=world)
     enc = DIGAT(cfg, D)
     enc.load_state_dict(sd)
     enc = enc.to(dev).eval()
@@ -202,23 +260,18 @@ def main():
     scorer.cache_news_context()
 
     n_pairs = corpus.pair_behavior.shape[0]
-    lo, hi = scoring.shard_range(n_pairs, rank, world)           # contiguous shard of the ordered pair list
+    sharded = args.workload in SHARDED_WORKLOADS                 # this rank generated only its own behaviours
+    lo, hi = (0, n_pairs) if sharded else scoring.shard_range(n_pairs, rank, world)   # contiguous shard of the ordered pair list
     total_steps = args.warmup + args.steps
     assert (hi - lo) >= total_steps * args.batch, 'shard too small for steps*batch'
     pair_beh = torch.from_numpy(corpus.pair_behavior[lo:hi]).to(dev)
     pair_news = torch.from_numpy(corpus.pair_news[lo:hi]).to(dev)
+    n_batches = (hi - lo) // args.batch
 
     def barrier():
         if world > 1:
             torch.distributed.barrier()
         torch.cuda.synchronize()
-
-    def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        return float(t.item())
 
     # ---------------------------------------------------------------- resident path (value)
     def step_resident(s):
@@ -226,12 +279,12 @@ def main():
         return scorer.score_resident(pair_beh[a:a + args.batch], pair_news[a:a + args.batch])
 
     def index_batches(s0, s1):
-        return ((pair_beh[s * args.batch:(s + 1) * args.batch], pair_news[s * args.batch:(s + 1) * args.batch])
-                for s in range(s0, s1))
+        return ((pair_beh[(s % n_batches) * args.batch:(s % n_batches + 1) * args.batch],
+                 pair_news[(s % n_batches) * args.batch:(s % n_batches + 1) * args.batch]) for s in range(s0, s1))
 
-    # The clock sampler (an nvidia-smi process) is started BEFORE the warm-up and must have delivered its first sample
-    # before the timed region begins: its start-up (NVML initialisation) stalls kernel launches for tens of milliseconds,
-    # which used to land inside the first timed steps every few runs (seen as 2-3x slower `value` at unchanged `e2e`).
+    # The clock sampler is started BEFORE the warm-up and must have delivered its first sample before the timed region
+    # begins: its start-up (NVML initialisation) stalls kernel launches for tens of milliseconds, which used to land inside
+    # the first timed steps every few runs (seen as 2-3x slower `value` at unchanged `e2e`).
     sampler = ClockSampler(local_rank)
     sampler.start()
     scoring.score_resident_batches(scorer, index_batches(0, args.warmup))
@@ -246,6 +299,7 @@ def main():
     gc.freeze()
     barrier()
     _lib.reset_launch_count()
+    c_lo = sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     # the public pipelined driver: the flag kernels of batch k+1 are enqueued ahead of the encoder pass of batch k and
@@ -255,13 +309,13 @@ def main():
     e1.record()
     barrier()
     launches = _lib.launch_count()
-    ms_resident = max_over_ranks(e0.elapsed_time(e1))
+    ms_resident = _max_over_ranks(e0.elapsed_time(e1), world, dev)
     marks = [e0] + step_events
     step_ms = sorted(marks[k].elapsed_time(marks[k + 1]) for k in range(len(marks) - 1))
     scorer.check_index_errors()
 
     # ---------------------------------------------------------------- end-to-end path (host buffers)
-    host = [scoring.host_batch(corpus, np.arange(lo + s * args.batch, lo + (s + 1) * args.batch), pin=True)
+    host = [scoring.host_batch(corpus, np.arange(lo + s * args.batch, lo + (s + 1) * args.batch), pin=True, config=cfg)
             for s in range(total_steps)]
     h2d = int(sum(t.numel() * t.element_size() for t in host[0]))
     res = torch.empty((total_steps, args.batch), dtype=torch.float32).pin_memory()
@@ -273,44 +327,79 @@ def main():
     scoring.score_host_batches(scorer, host[args.warmup:total_steps], res[args.warmup:total_steps])
     e1.record()
     barrier()
-    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.stop()
+    ms_e2e = _max_over_ranks(e0.elapsed_time(e1), world, dev)
+    clocks = sampler.stats(c_lo, sampler.mark())
+    del host
+
+    # ---------------------------------------------------------------- sustained: >= --sustained seconds back to back
+    sustained = None
+    if args.sustained > 0:
+        per_step = ms_resident / args.steps * 1e-3
+        n_sus = max(args.steps, int(args.sustained / per_step * 1.05) + 1)          # same count on every rank
+        if world > 1:
+            t = torch.tensor([n_sus], device=dev, dtype=torch.int64)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            n_sus = int(t.item())
+        barrier()
+        s_lo = sampler.mark()
+        e0.record()
+        scoring.score_resident_batches(scorer, index_batches(0, n_sus))
+        e1.record()
+        barrier()
+        ms_sus = _max_over_ranks(e0.elapsed_time(e1), world, dev)
+        sustained = {'value': world * n_sus * args.batch / (ms_sus * 1e-3), 'unit': 'pairs/s', 'seconds': ms_sus * 1e-3,
+                     'steps': n_sus, 'ms_per_step': ms_sus / n_sus, 'clocks': sampler.stats(s_lo, sampler.mark()),
+                     'note': 'the resident path back to back over this rank\'s shard (cyclically); same driver as `value`'}
+    sampler.stop()
 
     # ---------------------------------------------------------------- per-kernel timing -> roofline (untimed pass)
     prof = _lib.start_profile()
+    prof_preps = []
     for s in range(args.warmup, min(total_steps, args.warmup + 3)):
-        step_resident(s)
+        a = s * args.batch
+        prep = scorer.prepare_resident(pair_beh[a:a + args.batch], pair_news[a:a + args.batch])
+        prof_preps.append(prep)
+        scorer.score_prepared(prep)
     torch.cuda.synchronize()
     kernels = _lib.stop_profile()
+    # what pruning keeps (for the layer kernel's efficiency figure): active user / news node rows per pair
+    act_u = float(np.mean([p['prune'][1].shape[0] if p['prune'] is not None else args.batch * (cfg.max_history_num + cfg.category_num)
+                           for p in prof_preps])) / args.batch
+    act_n = float(np.mean([p['prune_n'][1].shape[0] if p['prune_n'] is not None else args.batch * cfg.news_graph_size
+                           for p in prof_preps])) / args.batch
 
     pairs_total = world * args.steps * args.batch
     value = pairs_total / (ms_resident * 1e-3)
     e2e = pairs_total / (ms_e2e * 1e-3)
 
+    train = None
+    if not args.no_train and args.workload not in SHARDED_WORKLOADS:
+        del scorer, pair_beh, pair_news
+        torch.cuda.empty_cache()
+        train = train_record(args, rank, local_rank, world, dev, steps=args.train_steps,
+                             cpu_baseline=not args.no_cpu_baseline)
+
     if rank == 0:
-        peaks = {}
-        pk = os.path.join(ROOT, 'MEASURED_PEAKS.json')
-        if os.path.isfile(pk):
-            peaks = json.load(open(pk))
-        hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
-        tensor_peak = float(peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops', 1590.0)))
-        peak_src = 'measured (MEASURED_PEAKS.json)' if peaks else 'fallback (B200_PROFILING.md)'
+        hbm_peak, tensor_peak, peak_src = _peaks()
         n_n, n_u, L = cfg.news_graph_size, cfg.max_history_num + cfg.category_num, cfg.graph_depth
         b_alg = algorithmic_bytes_per_pair(n_n, n_u, L)
-        table = summarize_kernels(kernels, hbm_peak, tensor_peak)
+        table = summarize_kernels(kernels, hbm_peak, tensor_peak, active_rows={n_u: act_u, n_n: act_n})
         top = table[0] if table else None
         roofline = None
         if top:
             traffic, traffic_note = None, None
-            tj = os.path.join(ROOT, 'profiles', 'r1_traffic.json')      # DRAM bytes per launch from the ncu --set full captures
-            if os.path.isfile(tj):
-                ent = json.load(open(tj)).get(top['kernel'])
-                if ent:
-                    traffic, traffic_note = ent['bytes'], ent['launch'] + ' / ' + ent['capture']
+            for tj in ('r2_traffic.json', 'r1_traffic.json'):           # DRAM bytes per launch from the ncu --set full captures
+                tj = os.path.join(ROOT, 'profiles', tj)
+                if os.path.isfile(tj):
+                    ent = json.load(open(tj)).get(top['kernel'])
+                    if ent:
+                        traffic, traffic_note = ent['bytes'], ent['launch'] + ' / ' + ent['capture']
+                        break
             roofline = {'kernel': top['kernel'], 'bound': top['bound'], 'achieved': top['achieved'], 'peak': top['peak'],
                         'unit': top['unit'], 'frac': top['achieved'] / top['peak'], 'traffic': traffic,
                         'traffic_note': traffic_note,
                         'share_of_step': top['share'], 'peak_source': peak_src, 'avg_launch_ms': top['avg_ms']}
+        per_gpu = value / world                                   # one GPU's pairs/s against one GPU's HBM peak
         line = {
             'metric': 'impressions_scored_per_sec', 'value': value, 'unit': 'pairs/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_resident / args.steps,
@@ -318,7 +407,8 @@ def main():
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': args.workload, 'pairs_per_step_per_gpu': args.batch, 'SAG_neighbors': cfg.SAG_neighbors,
                        'SAG_hops': cfg.SAG_hops, 'news_graph_size': n_n, 'user_graph_size': n_u, 'graph_depth': L,
-                       'D': D, 'n_news': int(corpus.news_embeddings.shape[0]), 'n_pairs': int(n_pairs),
+                       'D': D, 'n_news': int(corpus.news_embeddings.shape[0]),
+                       'n_pairs': int(n_pairs) if not sharded else None,
                        'parallelism': 'pair-sharded x%d, no communication' % world,
                        'l2_policy': 'inputs larger than L2 (per-step intermediates ~%.1f GB)' %
                                     (args.batch * n_u * 3 * D * 4 / 1e9)},
@@ -327,50 +417,118 @@ def main():
             'gpu_launches': launches,
             'clocks': clocks,
             'roofline': roofline,
-            'roofline_path': {'bound': 'hbm', 'bytes_per_pair_alg': b_alg, 'achieved': value * b_alg / 1e9,
-                              'peak': hbm_peak, 'unit': 'GB/s', 'frac': value * b_alg / 1e9 / hbm_peak,
-                              'note': 'SURVEY 8(d) B_alg; the path is tensor/ALU-bound, see DESIGN.md'},
-            'kernels': table[:8],
+            'roofline_path': {'bound': 'hbm', 'bytes_per_pair_alg': b_alg, 'achieved': per_gpu * b_alg / 1e9,
+                              'peak': hbm_peak, 'unit': 'GB/s', 'frac': per_gpu * b_alg / 1e9 / hbm_peak, 'per': 'GPU',
+                              'note': 'SURVEY 8(d) B_alg per pair x ONE GPU\'s pairs/s over one GPU\'s measured HBM peak; '
+                                      'the path is tensor/ALU-bound, see DESIGN.md'},
+            'sustained': sustained,
+            'kernels': table[:10],
+            'active_rows_per_pair': {'user_graph': act_u, 'news_graph': act_n, 'dense': {'user_graph': n_u, 'news_graph': n_n}},
         }
+        if sharded:
+            line['config']['scale'] = ('1.0 of BASELINE configs[4]: %d news, %d behaviours over %d ranks (%d on this rank, '
+                                       '%d pairs)' % (WORKLOADS[args.workload][3], WORKLOADS[args.workload][4], world,
+                                                      corpus.history.shape[0], n_pairs))
         if not args.no_cpu_baseline and world == 1:
             pps, sec, cores, n = oracle_pairs_per_second(cfg, sd, corpus, 64, args.cpu_budget)
             line['cpu_baseline'] = {'value': pps, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port',
                                     'sample': '%d calls x 64 pairs of the same workload (%.1f s of CPU work), '
                                               'oracle/digat_oracle.py inference, torch CPU fp32' % (n, n * sec)}
+        if train is not None:
+            line['train'] = train
         print(json.dumps(line))
-    if world > 1:
-        torch.distributed.destroy_process_group()
 
 
-def run_train(args):
+# -------------------------------------------------------------------------------------------------- training record
+ORDER = ('news_graph_embeddings', 'news_graph', 'news_graph_mask', 'user_news_embedding', 'user_graph',
+         'user_category_mask', 'user_category_indices')
+
+
+def oracle_train_samples_per_second(cfg, sd, corpus, behaviours, news_num, budget_s):
+    """CPU baseline of a training step: fwd + bwd of the oracle port through torch autograd (all host cores), on
+    `behaviours` x `news_num` encoder rows (the Eq. (8) tensor autograd saves is 7.4 MB per row and layer)."""
+    from digat_b200 import synth
+    from oracle import digat_oracle as O
+    import torch.nn.functional as F
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    P = {k: v.clone().requires_grad_(True) for k, v in O.cast_params(sd).items()}
+    rows = behaviours * news_num
+    batch = synth.make_batch(corpus, np.arange(rows))
+    args = [batch[k] for k in ORDER]
+
+    def step():
+        for v in P.values():
+            v.grad = None
+        cn, cu = O.forward(P, *args)
+        logits = O.logits(cn, cu).view(behaviours, news_num)
+        (-F.log_softmax(logits, dim=1).select(1, 0)).mean().backward()
+    step()
+    n, t0 = 0, time.perf_counter()
+    while True:
+        step()
+        n += 1
+        el = time.perf_counter() - t0
+        if el >= budget_s:
+            break
+    return n * behaviours / el, el / n, cores, n, rows
+
+
+def ddp_gradient_check(dev, rank, world):
+    """What tests/ddp_worker.py computes: gradients after DDP's NCCL all-reduce over `world` ranks (8 rows each) against
+    single-process gradients on the union batch, max relative difference over all parameters (rank 0's view)."""
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    from digat_b200 import synth
+    from digat_b200.graphEncoders import DIGAT
+    cfg = synth.make_config(graph_depth=2, dropout_rate=0.0)
+    sd = synth.make_state_dict(cfg, seed=6)
+    corpus = synth.make_corpus(cfg, n_news=300, n_behaviors=8 * world, mean_candidates=3.0, seed=3)
+    batch = synth.make_batch(corpus, np.arange(8 * world))
+    m = DIGAT(cfg, D)
+    m.load_state_dict(sd)
+    m = m.to(dev).train()
+    ddp = DDP(m, device_ids=[dev.index])
+    b = [batch[k][rank * 8:(rank + 1) * 8].to(dev) for k in ORDER]
+    cn, cu = ddp(*b)
+    (cn * cu).sum(1).mean().backward()
+    torch.cuda.synchronize()
+    worst = 0.0
+    if rank == 0:
+        m1 = DIGAT(cfg, D)
+        m1.load_state_dict(sd)
+        m1 = m1.to(dev).train()
+        cn, cu = m1(*[batch[k].to(dev) for k in ORDER])
+        (cn * cu).sum(1).mean().backward()
+        torch.cuda.synchronize()
+        g = dict(m.named_parameters())
+        for k, v in m1.named_parameters():
+            a, r = g[k].grad.double(), v.grad.double()
+            worst = max(worst, float((a - r).abs().max() / r.abs().max().clamp_min(1e-30)))
+    torch.distributed.barrier()
+    return worst
+
+
+def train_record(args, rank, local_rank, world, dev, steps, cpu_baseline=True):
     """BASELINE.json configs[2]: DIGAT training fwd+bwd on synthetic MIND-shaped batches, per-GPU batch = 64 behaviours
     x (1 + 4 negatives) = 320 rows (reference config.py:31,34), dropout 0.2, DDP gradient all-reduce over NCCL when
     launched with N>1 ranks, clip-norm 1 + Adam step as reference trainer.py:98-105.  News-encoder excluded."""
     import torch.nn.functional as F
-    rank = int(os.environ.get('RANK', '0'))
-    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device('cuda', local_rank)
-    if world > 1:
-        torch.distributed.init_process_group('nccl', device_id=dev)
     from digat_b200 import _lib, synth
-    from digat_b200.graphEncoders import DIGAT
     from digat_b200.model import Model
-    _lib.require_device(local_rank)
-    N, hops, L = WORKLOADS[args.workload][:3]
+    workload = args.workload if args.workload not in SHARDED_WORKLOADS else 'mind_small_dev_n3_L3'
+    N, hops, L = WORKLOADS[workload][:3]
     cfg = synth.make_config(SAG_neighbors=N, SAG_hops=hops, graph_depth=L, dropout_rate=0.2)
     sd = synth.make_state_dict(cfg, D=D, seed=0)
     corpus = synth.make_corpus(cfg, D=D, n_news=20000, n_behaviors=4096, mean_candidates=8.0, seed=rank)
     model = Model(cfg, D)
     model.graph_encoder.load_state_dict(sd)
     model = model.to(dev).train()
-    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank]) if world > 1 else model
     # whole-step CUDA graph (digat_b200/training.py) on one GPU; the DDP step runs eagerly (capturing DDP's reducer +
     # NCCL all-reduce failed in this PyTorch build: capture_end reported an invalidated capture from the backward)
     graphed = world == 1 and not args.eager_train
     opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=graphed)
     bs, news_num = 64, 5
+    warmup = max(args.warmup, 3)
     rng = np.random.Generator(np.random.PCG64(rank))
     emb = torch.from_numpy(corpus.news_embeddings).to(dev)
     node = torch.from_numpy(corpus.news_node_ID.astype(np.int64)).to(dev)
@@ -383,15 +541,6 @@ def run_train(args):
         cand = torch.from_numpy(rng.integers(1, emb.shape[0], size=(bs, news_num))).to(dev)
         return (emb[hist[beh]], ug[beh], cm[beh], ci[beh], emb[node[cand]], ng[cand], nm[cand])
 
-    def step(inp):
-        logits = net.forward_embeddings(*inp) if world == 1 else net.module.forward_embeddings(*inp)
-        loss = (-F.log_softmax(logits, dim=1).select(1, 0)).mean()
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
-        opt.step()
-        return loss
-
     if world > 1:
         # DDP hooks fire on the wrapped module's forward: route forward_embeddings through it
         class _Fwd(torch.nn.Module):
@@ -402,23 +551,25 @@ def run_train(args):
             def forward(self, *a):
                 return self.m.forward_embeddings(*a)
         fwd = torch.nn.parallel.DistributedDataParallel(_Fwd(model), device_ids=[local_rank])
+    else:
+        fwd = model.forward_embeddings
 
-        def step(inp):  # noqa: F811
-            logits = fwd(*inp)
-            loss = (-F.log_softmax(logits, dim=1).select(1, 0)).mean()
-            opt.zero_grad(set_to_none=True)
-            loss.backward()
-            torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
-            opt.step()
-            return loss
+    def eager_step(inp):
+        logits = fwd(*inp)
+        loss = (-F.log_softmax(logits, dim=1).select(1, 0)).mean()
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        return loss
 
-    inputs = [make_step_inputs() for _ in range(args.warmup + args.steps)]
+    inputs = [make_step_inputs() for _ in range(warmup + steps)]
+    step = eager_step
     if graphed:
         from digat_b200.training import GraphedTrainStep
-        eager_step = step
-        gstep = GraphedTrainStep(lambda *a: eager_step(a), inputs[0])
+        gstep = GraphedTrainStep(lambda *a: eager_step(a), inputs[0], modules=(model,))
         step = lambda inp: gstep(*inp)                      # noqa: E731
-    for s_ in range(args.warmup):
+    for s_ in range(warmup):
         step(inputs[s_])
     if world > 1:
         torch.distributed.barrier()
@@ -426,39 +577,73 @@ def run_train(args):
     _lib.reset_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for s_ in range(args.warmup, args.warmup + args.steps):
+    for s_ in range(warmup, warmup + steps):
         loss = step(inputs[s_])
     e1.record()
     if world > 1:
         torch.distributed.barrier()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = _max_over_ranks(e0.elapsed_time(e1), world, dev)
+    launches_timed = _lib.launch_count()
+    final_loss = float(loss)
+
+    # per-kernel table: one eager step through the profiling hooks (CUDA events around every C-ABI call)
+    _lib.start_profile()
+    e0.record()
+    eager_step(inputs[warmup])
+    e1.record()
+    torch.cuda.synchronize()
+    recs = _lib.stop_profile()
+    eager_ms = e0.elapsed_time(e1)
+    agg = {}
+    for name, a, t in recs:
+        e = agg.setdefault(name, [0.0, 0])
+        e[0] += t
+        e[1] += 1
+    ours_ms = sum(v[0] for v in agg.values()) or 1.0
+    kernels = [{'kernel': k, 'ms_per_step': v[0], 'launches': v[1], 'share_of_our_kernels': v[0] / ours_ms}
+               for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])][:12]
+
+    grad_check = ddp_gradient_check(dev, rank, world) if world > 1 else None
+    rec = None
     if rank == 0:
-        print(json.dumps({
-            'metric': 'train_samples_per_sec', 'value': world * args.steps * bs / (ms * 1e-3), 'unit': 'samples/s',
-            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': args.workload + ':train', 'behaviours_per_gpu': bs, 'candidates': news_num,
-                       'rows_per_gpu': bs * news_num, 'dropout': 0.2, 'optimizer': 'Adam + clip_grad_norm 1',
-                       'execution': 'whole step replayed as one CUDA graph' if graphed else 'eager',
-                       'parallelism': 'DDP x%d, NCCL gradient all-reduce' % world},
-            'gpu_launches': _lib.launch_count(), 'final_loss': float(loss)}))
-    if world > 1:
-        torch.distributed.destroy_process_group()
+        n_params = sum(p.numel() for p in model.parameters())
+        rec = {'metric': 'train_samples_per_sec', 'value': world * steps * bs / (ms * 1e-3), 'unit': 'samples/s',
+               'n_gpus': world, 'steps': steps, 'warmup': warmup, 'ms_per_step': ms / steps,
+               'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+               'config': {'workload': workload + ':train', 'behaviours_per_gpu': bs, 'candidates': news_num,
+                          'rows_per_gpu': bs * news_num, 'dropout': 0.2, 'optimizer': 'Adam + clip_grad_norm 1',
+                          'execution': 'whole step replayed as one CUDA graph' if graphed else 'eager',
+                          'parallelism': 'DDP x%d, NCCL gradient all-reduce (%.1f MB fp32 per step)' % (world, n_params * 4 / 1e6)
+                                         if world > 1 else 'single GPU (no collective)'},
+               'gpu_launches': launches_timed if not graphed else sum(v[1] for v in agg.values()) * steps,
+               'gpu_launches_note': 'C-ABI kernel launches (replayed from the captured graph)' if graphed else 'C-ABI kernel launches',
+               'final_loss': final_loss,
+               'eager_step_ms': eager_ms, 'our_kernels_ms_per_step': ours_ms, 'kernels': kernels}
+        if grad_check is not None:
+            rec['ddp_vs_single_process_grad_rel_diff'] = grad_check
+        if cpu_baseline and world == 1:
+            sps, sec, cores, n, rows = oracle_train_samples_per_second(cfg, sd, corpus, 12, news_num, min(args.cpu_budget, 10.0))
+            rec['cpu_baseline'] = {'value': sps, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
+                                   'sample': '%d fwd+bwd steps of %d behaviours x %d candidates = %d encoder rows (%.1f s of CPU '
+                                             'work), oracle/digat_oracle.py under torch autograd, CPU fp32' % (n, 12, news_num, rows, n * sec)}
+    return rec
 
 
-def summarize_kernels(records, hbm_peak, tensor_peak):
-    """records: [(name, args, ms)] from _lib.stop_profile -> per-kernel-class share and roofline numbers."""
+def summarize_kernels(records, hbm_peak, tensor_peak, active_rows=None):
+    """records: [(name, args, ms)] from _lib.stop_profile -> per-kernel-class share and roofline numbers.
+    active_rows {n: mean node rows per graph that survive pruning}: the fused layer kernel gets a second figure,
+    `needed` = the bytes the PRUNED result needs (5 rows-worth of D floats per active node + the adjacency), next to the
+    dense-layout figure `achieved` (every node row counted, as SURVEY 8(d) defines B_alg)."""
     agg = {}
     for name, a, ms in records:
+        work2 = None
         if name == 'digat_graph_layer_fwd':
             B, n, Dd = a[6], a[7], a[8]
             key = '%s[n=%d]' % (name, n)
             work, bound = B * (5 * n * Dd * 4 + n * n + Dd * 4), 'hbm'
+            if a[19] and active_rows and n in active_rows:              # row_active given: pruned evaluation
+                work2 = B * (5 * active_rows[n] * Dd * 4 + n * n + Dd * 4)
         elif name == 'digat_linear_f32' or name == 'digat_linear_tf32x3':
             M, N, K = (a[7], a[8], a[9]) if name == 'digat_linear_f32' else (a[8], a[9], a[10])
             key = '%s[N=%d,K=%d,%s]' % (name, N, K, 'M>2048' if M > 2048 else 'M<=2048')
@@ -478,9 +663,10 @@ def summarize_kernels(records, hbm_peak, tensor_peak):
             key, work, bound = name, a[6] * (a[7] + a[8]) * a[9] * 4 * 2, 'hbm'
         else:
             key, work, bound = name, 0.0, 'hbm'
-        e = agg.setdefault(key, {'kernel': key, 'bound': bound, 'ms': 0.0, 'work': 0.0, 'launches': 0})
+        e = agg.setdefault(key, {'kernel': key, 'bound': bound, 'ms': 0.0, 'work': 0.0, 'work2': 0.0, 'launches': 0})
         e['ms'] += ms
         e['work'] += work
+        e['work2'] += work2 if work2 is not None else work
         e['launches'] += 1
     total = sum(e['ms'] for e in agg.values()) or 1.0
     out = []
@@ -489,8 +675,13 @@ def summarize_kernels(records, hbm_peak, tensor_peak):
             ach, peak, unit = e['work'] / (e['ms'] * 1e-3) / 1e9, hbm_peak, 'GB/s'
         else:
             ach, peak, unit = e['work'] / (e['ms'] * 1e-3) / 1e12, tensor_peak, 'TFLOP/s'
-        out.append({'kernel': e['kernel'], 'bound': e['bound'], 'share': e['ms'] / total, 'avg_ms': e['ms'] / e['launches'],
-                    'launches': e['launches'], 'achieved': ach, 'peak': peak, 'unit': unit, 'frac': ach / peak})
+        row = {'kernel': e['kernel'], 'bound': e['bound'], 'share': e['ms'] / total, 'avg_ms': e['ms'] / e['launches'],
+               'launches': e['launches'], 'achieved': ach, 'peak': peak, 'unit': unit, 'frac': ach / peak}
+        if e['work2'] != e['work']:
+            need = e['work2'] / (e['ms'] * 1e-3) / 1e9
+            row.update(needed_GBps=need, frac_needed=need / peak,
+                       note='achieved = dense-layout bytes; needed = bytes of the pruned result (active rows only)')
+        out.append(row)
     out.sort(key=lambda r: -r['share'])
     return out
 
