@@ -623,5 +623,13 @@ class DIGAT(GraphEncoder):
 
 
 # The reference keeps its five ablation encoders in the same module (graphEncoders.py:201-842) and model.py:20-29 looks
-# them up here by name: re-export them so that `from digat_b200 import graphEncoders` stays a one-line swap.
-from .ablation_encoders import (News_graph_wo_inter, Seq_SA, User_graph_wo_inter, wo_interaction, wo_SA)  # noqa: E402,F401
+# them up here by name (`graphEncoders.wo_SA(...)`): resolve them lazily (PEP 562; ablation_encoders imports this module) so
+# that `from digat_b200 import graphEncoders` stays a one-line swap.
+_ABLATIONS = ('wo_SA', 'Seq_SA', 'wo_interaction', 'News_graph_wo_inter', 'User_graph_wo_inter')
+
+
+def __getattr__(name):
+    if name in _ABLATIONS:
+        from . import ablation_encoders
+        return getattr(ablation_encoders, name)
+    raise AttributeError('module %r has no attribute %r' % (__name__, name))
