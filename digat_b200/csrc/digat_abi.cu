@@ -104,6 +104,10 @@ int digat_debug_set_layer_mode(int mode) {
 }
 
 int digat_debug_set_gemm_variant(int variant) {
+    if (variant == 6 || variant == 7) {          // 6 / 7: W multicast across CTA pairs off / on (persistent kernel)
+        g_tc_cluster = variant == 7;
+        return DIGAT_OK;
+    }
     g_tc_variant = variant;
     return DIGAT_OK;
 }

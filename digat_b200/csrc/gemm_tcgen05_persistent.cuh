@@ -10,10 +10,30 @@
 //   * the MMA warp starts the next tile as soon as the epilogue has released TMEM (tmem_empty barrier).
 // Warp roles (448 threads): 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2-5 = operand transform (A_lo),
 // 6-13 = epilogue (TMEM lane quarter = warp % 4, two warps per quarter split the columns).  Arithmetic is identical to gemm_tf32x3_kernel<BN,1,true>.
+// kCl = 2: two CTAs of a cluster work on the SAME N tile of two adjacent M blocks and share the W tile: each CTA loads
+// half of its rows and multicasts them into both CTAs' shared memory (cp.async.bulk.tensor ... .multicast::cluster), so
+// every SM pulls A + W/2 instead of A + W through L2 per k-block (38 KB -> 23 KB at BN = 240).  The main loop of the
+// single-CTA kernel sits at the L2 -> SM bandwidth of the chip (148 SMs x 38 KB per ~800 cycles = 7.0 KB/clk against the
+// ~6.3 KB/clk the L2 slices deliver), which is why fewer MMAs per k-block (the BF16-correction scheme) bought almost
+// nothing before.  Everything else (MMA, operand transform, epilogue, TMEM) stays per CTA; only the recycling of a stage is
+// coupled: its "empty" barrier counts the commits of BOTH CTAs (tcgen05.commit ... .multicast::cluster), because the
+// peer's TMA writes into this CTA's stage too.
 #pragma once
 #include "gemm_tcgen05.cuh"
+#include "gemm_tcgen05_pair.cuh"     // cluster_ctarank, cluster_sync_all, mbar_wait_cluster
 
 namespace digat {
+
+__device__ __forceinline__ void tma_load_2d_multicast(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                                      uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {   // arrives on `bar` in every CTA of the mask
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
 
 constexpr int kTcEpiWarps = 8;                  // two epilogue warps per TMEM lane quarter, each takes half of the columns
 constexpr int kTcPersistThreads = (2 + 4 + kTcEpiWarps) * 32;
@@ -38,7 +58,7 @@ struct TcPersistCfg {
 // truncation error).  bf16 MMAs run at twice the TF32 rate: per 16-wide k-block the tensor pipe does 2 TF32 MMAs + 2 BF16
 // MMAs = 4 TF32-MMA times instead of 6.  The stage keeps its size: A_lo (tf32) becomes two bf16 tiles of half the size,
 // W_lo (tf32) becomes the two bf16 planes of W (map_w2 = bf16(W_hi), map_w3 = bf16(W_lo); SWIZZLE_32B tiles).
-template <int BN, bool kBf16>
+template <int BN, bool kBf16, int kCl>
 __global__ void __launch_bounds__(kTcPersistThreads, 1)
 gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_whi,
                               const __grid_constant__ CUtensorMap map_wlo, const __grid_constant__ CUtensorMap map_w3,
@@ -62,8 +82,16 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
     const int nkb_all = (K + kTcBK - 1) / kTcBK;
     const int nkb = (nkb_all + gb.kbatches - 1) / gb.kbatches;          // k-blocks per split-K slice (tail slices read zeros)
     const int n_tiles_n = (N + BN - 1) / BN, n_tiles_m = (M + 127) / 128;
-    const int n_tiles_mn = n_tiles_n * n_tiles_m;
-    const int n_tiles = n_tiles_mn * gb.kbatches;                        // tile = slice * n_tiles_mn + (m block, n block)
+    // a "worker" is a CTA (kCl = 1) or a cluster of two CTAs that takes a PAIR of adjacent M blocks of one N tile
+    const int cl_rank = kCl == 2 ? (int)cluster_ctarank() : 0;
+    const int worker = kCl == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int n_workers = kCl == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int n_units_m = kCl == 2 ? (n_tiles_m + 1) / 2 : n_tiles_m;    // M blocks, or pairs of them
+    const int n_tiles_mn = n_tiles_n * n_units_m;
+    const int n_tiles = n_tiles_mn * gb.kbatches;                        // tile = slice * n_tiles_mn + (m unit, n block)
+    // (a cluster whose second M block lies past M computes zeros there and stores nothing)
+    auto tile_mb = [&](int t_mn) { const int u = t_mn / n_tiles_n; return kCl == 2 ? 2 * u + cl_rank : u; };
+    auto tile_nb = [&](int t_mn) { return t_mn % n_tiles_n; };
 
     auto a_hi = [&](int s) { return smem + (size_t)s * Cfg::STAGE_BYTES; };
     auto a_lo = [&](int s) { return smem + (size_t)s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
@@ -81,7 +109,7 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
         for (int s = 0; s < Cfg::STAGES; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&ready[s], kTcTransformThreads / 32);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], kCl);                          // kCl = 2: the peer's TMA writes this stage too
         }
         mbar_init(accum_full, 1);
         mbar_init(tmem_empty, kTcEpiWarps);
@@ -93,7 +121,8 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    if (kCl == 2) cluster_sync_all();            // both CTAs' barriers exist before any multicast load / remote commit
+    else __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
@@ -101,9 +130,9 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
             int it = 0;                                                    // k-blocks issued so far (all tiles)
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int tile = worker; tile < n_tiles; tile += n_workers) {
                 const int slice = tile / n_tiles_mn, t_mn = tile - slice * n_tiles_mn;
-                const int mb = t_mn / n_tiles_n, m0 = mb * 128, n0 = (t_mn - mb * n_tiles_n) * BN;
+                const int mb = tile_mb(t_mn), m0 = mb * 128, n0 = tile_nb(t_mn) * BN;
                 const int kb0 = slice * nkb;                               // first k-block of this split-K slice
                 if (n0 == 0 && gb.kbatches == 1) {                         // pull a later M block's A rows into L2
                     const int ahead = mb + kTcPrefetchBlocks;
@@ -114,12 +143,22 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
                 }
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % Cfg::STAGES;
-                    mbar_wait(&empty[s], ((it / Cfg::STAGES) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&full[s], Cfg::A_BYTES + 2 * Cfg::W_BYTES);
+                    if (kCl == 2) mbar_wait_cluster(&empty[s], ((it / Cfg::STAGES) & 1) ^ 1);   // BOTH CTAs are done with stage s
+                    else mbar_wait(&empty[s], ((it / Cfg::STAGES) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&full[s], Cfg::A_BYTES + 2 * Cfg::W_BYTES);      // own A + the whole W tile (both halves)
                     tma_load_2d(a_hi(s), &map_a, &full[s], (kb0 + kb) * kTcBK, m0);        // k past K arrives as zeros
-                    tma_load_2d(w_hi(s), &map_whi, &full[s], (kb0 + kb) * kTcBK, n0);
-                    tma_load_2d(w_lo(s), &map_wlo, &full[s], (kb0 + kb) * kTcBK, n0);      // kBf16: bf16(W_hi), half the bytes
-                    if (kBf16) tma_load_2d(w_b3(s), &map_w3, &full[s], (kb0 + kb) * kTcBK, n0);   // bf16(W_lo)
+                    if (kCl == 2) {
+                        // this CTA's half of the W rows, delivered to the same offsets of both CTAs (the maps' boxes are BN/2 rows)
+                        constexpr int HR = BN / 2;
+                        const int nr = n0 + cl_rank * HR;
+                        tma_load_2d_multicast(w_hi(s) + cl_rank * HR * kTcBK * 4, &map_whi, &full[s], (kb0 + kb) * kTcBK, nr, 3);
+                        tma_load_2d_multicast(w_lo(s) + cl_rank * HR * kTcBK * (kBf16 ? 2 : 4), &map_wlo, &full[s], (kb0 + kb) * kTcBK, nr, 3);
+                        if (kBf16) tma_load_2d_multicast(w_b3(s) + cl_rank * HR * kTcBK * 2, &map_w3, &full[s], (kb0 + kb) * kTcBK, nr, 3);
+                    } else {
+                        tma_load_2d(w_hi(s), &map_whi, &full[s], (kb0 + kb) * kTcBK, n0);
+                        tma_load_2d(w_lo(s), &map_wlo, &full[s], (kb0 + kb) * kTcBK, n0);      // kBf16: bf16(W_hi), half the bytes
+                        if (kBf16) tma_load_2d(w_b3(s), &map_w3, &full[s], (kb0 + kb) * kTcBK, n0);   // bf16(W_lo)
+                    }
                 }
             }
         }
@@ -129,7 +168,7 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
             constexpr uint32_t idesc = umma_idesc_tf32(128, BN);
             const uint32_t d_main = tmem_base, d_corr = tmem_base + (uint32_t)BN;
             int it = 0, j = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+            for (int tile = worker; tile < n_tiles; tile += n_workers, ++j) {
 #ifdef DIGAT_TC_TIMING
                 const long long t0 = clock64();
 #endif
@@ -172,7 +211,8 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
                             umma_tf32(d_corr, d_alo + koff, d_whi + koff, idesc, 1u);
                         }
                     }
-                    umma_commit(&empty[s]);
+                    if (kCl == 2) umma_commit_multicast(&empty[s], 3);    // frees stage s in both CTAs of the cluster
+                    else umma_commit(&empty[s]);
                 };
                 issue_raw(0, it);
                 for (int kb = 0; kb < nkb; ++kb) {
@@ -191,7 +231,7 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
         // ------------------------------------------------------------------ operand transform: A_lo = rna_tf32(A - trunc_tf32(A))
         const int t = threadIdx.x - 64;                                    // 0..127
         int it = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int tile = worker; tile < n_tiles; tile += n_workers) {
             for (int kb = 0; kb < nkb; ++kb, ++it) {
                 const int s = it % Cfg::STAGES;
                 mbar_wait(&full[s], (it / Cfg::STAGES) & 1);
@@ -237,9 +277,9 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
         float* stage = stage_base + ew * (32 * 20);
         const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
         int j = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+        for (int tile = worker; tile < n_tiles; tile += n_workers, ++j) {
             const int slice = tile / n_tiles_mn, t_mn = tile - slice * n_tiles_mn;
-            const int mb = t_mn / n_tiles_n, m0 = mb * 128, n0 = (t_mn - mb * n_tiles_n) * BN;
+            const int mb = tile_mb(t_mn), m0 = mb * 128, n0 = tile_nb(t_mn) * BN;
             float* __restrict__ Cs = C + (size_t)slice * (size_t)gb.c_batch_stride;       // this slice's output slab
             const int m = m0 + q * 32 + lane;
             const int32_t* orow = gb.out_rows;                             // ascending row scatter, or null
@@ -343,11 +383,55 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    if (kCl == 2) cluster_sync_all();            // the peer may still multicast into / commit onto this CTA's shared memory
+    else __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
                      :: "r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
     }
+}
+
+static int g_tc_cluster = 1;   // 1 = W multicast across CTA pairs for large M (default), 0 = off (digat_debug_set_gemm_variant 6 / 7)
+
+// Launch of one persistent instantiation; kCl = 2 goes through cudaLaunchKernelEx with a (2,1,1) cluster.
+template <int BN, bool kBf16, int kCl>
+int launch_tf32x3_persistent_inst(const CUtensorMap& ma, const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& m3,
+                                  const float* bias, float* C, int ldc, int M, int N, int K, GroupBias gb, int units, int sm_count,
+                                  cudaStream_t st) {
+    using Cfg = TcPersistCfg<BN>;
+    auto kernel = gemm_tf32x3_persistent_kernel<BN, kBf16, kCl>;
+    if (int rc_ = ensure_dynamic_smem(kernel, (size_t)Cfg::SMEM)) return rc_;
+    if (kCl == 1) {
+        const int grid = units < sm_count ? units : sm_count;
+        kernel<<<grid, kTcPersistThreads, Cfg::SMEM, st>>>(ma, mh, ml, m3, bias, C, ldc, M, N, K, gb);
+        return check_launch("digat_linear_tf32x3(persistent)");
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.blockDim = dim3(kTcPersistThreads);
+    cfg.dynamicSmemBytes = Cfg::SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    static int max_clusters[16] = {0};                                   // co-resident clusters of this instantiation, per device
+    int dev = 0;
+    DIGAT_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 16 && max_clusters[dev] == 0) {
+        cfg.gridDim = dim3(2 * (sm_count / 2));
+        int n = 0;
+        DIGAT_CUDA(cudaOccupancyMaxActiveClusters(&n, kernel, &cfg));
+        max_clusters[dev] = n > 0 ? n : -1;
+    }
+    int clusters = sm_count / 2;
+    if (dev >= 0 && dev < 16 && max_clusters[dev] > 0 && max_clusters[dev] < clusters) clusters = max_clusters[dev];
+    if (units < clusters) clusters = units;
+    cfg.gridDim = dim3(2 * clusters);
+    DIGAT_CUDA(cudaLaunchKernelEx(&cfg, kernel, ma, mh, ml, m3, bias, C, ldc, M, N, K, gb));
+    return check_launch("digat_linear_tf32x3(persistent, W multicast)");
 }
 
 template <int BN>
@@ -357,29 +441,32 @@ int launch_tf32x3_persistent(const float* A, int lda, const float* W_hi, const f
     using Cfg = TcPersistCfg<BN>;
     const DeviceInfo* di = device_info();
     if (!di) return fail(DIGAT_E_CUDA, "digat_linear_tf32x3: no CUDA device");
+    DIGAT_REQUIRE(N <= Cfg::MAX_N, "digat_linear_tf32x3(persistent): N=%d exceeds %d", N, Cfg::MAX_N);
+    const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + 127) / 128;
+    // W multicast pays when every SM streams many tiles (the kernel is then bound by L2 -> SM traffic); short problems and
+    // split-K weight gradients (few tiles per CTA) keep the independent CTAs
+    const bool cluster = g_tc_cluster != 0 && gb.kbatches == 1 && tiles_m >= 2 &&
+                         (long)tiles_n * tiles_m >= 4L * di->sm_count;
+    const int wbox = cluster ? BN / 2 : BN;                               // rows of one W box (a cluster CTA loads half a tile)
     CUtensorMap ma, mh, ml;
     int rc;
     if ((rc = make_tensor_map_2d(&ma, A, M, K, lda, 128, kTcBK, CU_TENSOR_MAP_SWIZZLE_64B)) != DIGAT_OK) return rc;
-    if ((rc = make_tensor_map_2d(&mh, W_hi, N, K, ldw, BN, kTcBK, CU_TENSOR_MAP_SWIZZLE_64B)) != DIGAT_OK) return rc;
+    if ((rc = make_tensor_map_2d(&mh, W_hi, N, K, ldw, wbox, kTcBK, CU_TENSOR_MAP_SWIZZLE_64B)) != DIGAT_OK) return rc;
     const bool bf16c = W_hb != nullptr && W_lb != nullptr;
     CUtensorMap m3 = mh;
     if (bf16c) {
-        if ((rc = make_tensor_map_2d_bf16(&ml, W_hb, N, K, ldw, BN, kTcBK, CU_TENSOR_MAP_SWIZZLE_32B)) != DIGAT_OK) return rc;
-        if ((rc = make_tensor_map_2d_bf16(&m3, W_lb, N, K, ldw, BN, kTcBK, CU_TENSOR_MAP_SWIZZLE_32B)) != DIGAT_OK) return rc;
+        if ((rc = make_tensor_map_2d_bf16(&ml, W_hb, N, K, ldw, wbox, kTcBK, CU_TENSOR_MAP_SWIZZLE_32B)) != DIGAT_OK) return rc;
+        if ((rc = make_tensor_map_2d_bf16(&m3, W_lb, N, K, ldw, wbox, kTcBK, CU_TENSOR_MAP_SWIZZLE_32B)) != DIGAT_OK) return rc;
     } else {
-        if ((rc = make_tensor_map_2d(&ml, W_lo, N, K, ldw, BN, kTcBK, CU_TENSOR_MAP_SWIZZLE_64B)) != DIGAT_OK) return rc;
+        if ((rc = make_tensor_map_2d(&ml, W_lo, N, K, ldw, wbox, kTcBK, CU_TENSOR_MAP_SWIZZLE_64B)) != DIGAT_OK) return rc;
     }
-    DIGAT_REQUIRE(N <= Cfg::MAX_N, "digat_linear_tf32x3(persistent): N=%d exceeds %d", N, Cfg::MAX_N);
-    const int tiles = ((N + BN - 1) / BN) * ((M + 127) / 128) * gb.kbatches;
-    const int grid = tiles < di->sm_count ? tiles : di->sm_count;
-    if (bf16c) {
-        if (int rc_ = ensure_dynamic_smem(gemm_tf32x3_persistent_kernel<BN, true>, (size_t)(Cfg::SMEM))) return rc_;
-        gemm_tf32x3_persistent_kernel<BN, true><<<grid, kTcPersistThreads, Cfg::SMEM, st>>>(ma, mh, ml, m3, bias, C, ldc, M, N, K, gb);
-    } else {
-        if (int rc_ = ensure_dynamic_smem(gemm_tf32x3_persistent_kernel<BN, false>, (size_t)(Cfg::SMEM))) return rc_;
-        gemm_tf32x3_persistent_kernel<BN, false><<<grid, kTcPersistThreads, Cfg::SMEM, st>>>(ma, mh, ml, m3, bias, C, ldc, M, N, K, gb);
+    const int units = tiles_n * (cluster ? (tiles_m + 1) / 2 : tiles_m) * gb.kbatches;
+    if (cluster) {
+        if (bf16c) return launch_tf32x3_persistent_inst<BN, true, 2>(ma, mh, ml, m3, bias, C, ldc, M, N, K, gb, units, di->sm_count, st);
+        return launch_tf32x3_persistent_inst<BN, false, 2>(ma, mh, ml, m3, bias, C, ldc, M, N, K, gb, units, di->sm_count, st);
     }
-    return check_launch("digat_linear_tf32x3(persistent)");
+    if (bf16c) return launch_tf32x3_persistent_inst<BN, true, 1>(ma, mh, ml, m3, bias, C, ldc, M, N, K, gb, units, di->sm_count, st);
+    return launch_tf32x3_persistent_inst<BN, false, 1>(ma, mh, ml, m3, bias, C, ldc, M, N, K, gb, units, di->sm_count, st);
 }
 
 }  // namespace digat

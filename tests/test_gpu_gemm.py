@@ -144,3 +144,68 @@ def test_linear_backward_other_embedding_dims(M, D):
     assert rel_err(Ac.grad.cpu().numpy(), A64.grad.numpy()) < 5e-6
     assert rel_err(Wc.grad.cpu().numpy(), W64.grad.numpy()) < 5e-6
     assert rel_err(bc.grad.cpu().numpy(), b64.grad.numpy()) < 2e-6
+
+
+@pytest.mark.parametrize('M,N,K', [(100000, 1200, 400), (77824, 400, 400), (136000 + 77, 1200, 400), (30000, 480, 96)])
+def test_w_multicast_cluster_kernel_is_bit_identical(M, N, K):
+    """The cluster variant of the persistent kernel (two CTAs share the W tile by TMA multicast) does the same arithmetic per
+    output element as independent CTAs: bit-identical, including the odd M-block tail, bias, row-group bias and row scatter."""
+    from digat_b200 import _lib
+    g = torch.Generator().manual_seed(M + N)
+    A = torch.randn(M, K, generator=g).cuda()
+    W = (torch.randn(N, K, generator=g) * 0.05).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    gcols = min(400, N)
+    gbias = torch.randn((2 * M + 67) // 68, gcols, generator=g).cuda()
+    rows = torch.sort(torch.randperm(2 * M, generator=g)[:M]).values.to(torch.int32).cuda()      # ascending scatter targets
+    hi, lo = _split(W)
+    st = torch.cuda.current_stream().cuda_stream
+    out = {}
+    try:
+        for variant in (6, 7):                                            # 6 = independent CTAs, 7 = W multicast
+            _lib.call('digat_debug_set_gemm_variant', variant)
+            C = torch.zeros((2 * M, N), device='cuda')
+            _lib.call('digat_linear_tf32x3', A.data_ptr(), K, hi.data_ptr(), lo.data_ptr(), K, bias.data_ptr(), C.data_ptr(), N,
+                      M, N, K, gbias.data_ptr(), 68, 0, gcols, gcols, rows.data_ptr(), st)
+            D = torch.zeros((M, N), device='cuda')
+            _lib.call('digat_linear_tf32x3', A.data_ptr(), K, hi.data_ptr(), lo.data_ptr(), K, bias.data_ptr(), D.data_ptr(), N,
+                      M, N, K, 0, 1, 0, 0, 0, 0, st)
+            torch.cuda.synchronize()
+            out[variant] = (C, D)
+    finally:
+        _lib.call('digat_debug_set_gemm_variant', 7)
+    assert torch.equal(out[6][0], out[7][0]) and torch.equal(out[6][1], out[7][1])
+    sel = torch.randperm(M, generator=g)[:256]
+    ref = A[sel].double().cpu() @ W.double().cpu().t() + bias.double().cpu()
+    assert rel_err(out[7][1][sel].cpu().numpy(), ref.numpy()) < 4e-6
+
+
+def test_bf16_correction_scheme_with_multicast_and_scatter():
+    """digat_linear_tf32_bf16c on the cluster kernel (the hot-path configuration): vs fp64, and cluster on == off."""
+    from digat_b200 import _lib
+    g = torch.Generator().manual_seed(9)
+    M, N, K = 120000, 1200, 400
+    A = torch.randn(M, K, generator=g).cuda()
+    W = (torch.randn(N, K, generator=g) * 0.05).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    hi, lo = _split(W)
+    hb = torch.empty(W.shape, dtype=torch.bfloat16, device='cuda')
+    lb = torch.empty_like(hb)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.call('digat_split_bf16', W.data_ptr(), hb.data_ptr(), lb.data_ptr(), W.numel(), st)
+    rows = torch.sort(torch.randperm(2 * M, generator=g)[:M]).values.to(torch.int32).cuda()
+    out = {}
+    try:
+        for variant in (6, 7):
+            _lib.call('digat_debug_set_gemm_variant', variant)
+            C = torch.zeros((2 * M, N), device='cuda')
+            _lib.call('digat_linear_tf32_bf16c', A.data_ptr(), K, hi.data_ptr(), hb.data_ptr(), lb.data_ptr(), K, b.data_ptr(),
+                      C.data_ptr(), N, M, N, K, 0, 1, 0, 0, 0, rows.data_ptr(), st)
+            torch.cuda.synchronize()
+            out[variant] = C
+    finally:
+        _lib.call('digat_debug_set_gemm_variant', 7)
+    assert torch.equal(out[6], out[7])
+    sel = torch.randperm(M, generator=g)[:256]
+    ref = A[sel].double().cpu() @ W.double().cpu().t() + b.double().cpu()
+    assert rel_err(out[7][rows[sel].long()].cpu().numpy(), ref.numpy()) < 4e-6
