@@ -104,8 +104,8 @@ int digat_debug_set_layer_mode(int mode) {
 }
 
 int digat_debug_set_gemm_variant(int variant) {
-    if (variant == 6 || variant == 7) {          // 6 / 7: W multicast across CTA pairs off / on (persistent kernel)
-        g_tc_cluster = variant == 7;
+    if (variant >= 6 && variant <= 8) {          // persistent kernel: 6 = independent CTAs, 7 = W multicast, 8 = 2-CTA MMA
+        g_tc_cluster = variant - 6;
         return DIGAT_OK;
     }
     g_tc_variant = variant;

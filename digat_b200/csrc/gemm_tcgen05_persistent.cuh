@@ -35,13 +35,24 @@ __device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t ct
                  :: "r"(smem_u32(bar)), "h"(cta_mask) : "memory");
 }
 
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+
 constexpr int kTcEpiWarps = 8;                  // two epilogue warps per TMEM lane quarter, each takes half of the columns
 constexpr int kTcPersistThreads = (2 + 4 + kTcEpiWarps) * 32;
 
-template <int BN>
+// kCl: 1 = independent CTAs; 2 = W multicast across a CTA pair (experiment); 3 = 2-CTA MMA (cta_group::2, M = 256): each
+// CTA of the pair loads and holds only HALF of the W tile, the leader CTA issues the MMAs for both
+template <int BN, int kCl = 1>
 struct TcPersistCfg {
     static constexpr int A_BYTES = 128 * kTcBK * 4;
-    static constexpr int W_BYTES = BN * kTcBK * 4;
+    static constexpr int W_ROWS = kCl == 3 ? BN / 2 : BN;                // W rows resident in this CTA's shared memory
+    static constexpr int W_BYTES = W_ROWS * kTcBK * 4;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
     static constexpr int MAX_N = 1280;                                   // bias vector kept in smem for the whole N
     static constexpr int GB_GROUPS = 16;                                 // row groups of one 128-row tile staged in smem
@@ -50,6 +61,7 @@ struct TcPersistCfg {
     static constexpr int TMEM_COLS = 2 * BN <= 256 ? 256 : 512;
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + EXTRA;
     static_assert(STAGES >= 3, "not enough shared memory for the pipeline");
+    static_assert(A_BYTES % 512 == 0 && W_BYTES % 512 == 0, "operand tiles must start on a swizzle-atom boundary");
 };
 
 // kBf16: the TF32+BF16 scheme.  The two correction products are ~2^-11 of the result, so they only need ~9 good bits:
@@ -64,7 +76,7 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
                               const __grid_constant__ CUtensorMap map_wlo, const __grid_constant__ CUtensorMap map_w3,
                               const float* __restrict__ bias,
                               float* __restrict__ C, int ldc, int M, int N, int K, GroupBias gb) {
-    using Cfg = TcPersistCfg<BN>;
+    using Cfg = TcPersistCfg<BN, kCl>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES);
@@ -83,14 +95,14 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
     const int nkb = (nkb_all + gb.kbatches - 1) / gb.kbatches;          // k-blocks per split-K slice (tail slices read zeros)
     const int n_tiles_n = (N + BN - 1) / BN, n_tiles_m = (M + 127) / 128;
     // a "worker" is a CTA (kCl = 1) or a cluster of two CTAs that takes a PAIR of adjacent M blocks of one N tile
-    const int cl_rank = kCl == 2 ? (int)cluster_ctarank() : 0;
-    const int worker = kCl == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-    const int n_workers = kCl == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-    const int n_units_m = kCl == 2 ? (n_tiles_m + 1) / 2 : n_tiles_m;    // M blocks, or pairs of them
+    const int cl_rank = kCl >= 2 ? (int)cluster_ctarank() : 0;
+    const int worker = kCl >= 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int n_workers = kCl >= 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int n_units_m = kCl >= 2 ? (n_tiles_m + 1) / 2 : n_tiles_m;    // M blocks, or pairs of them
     const int n_tiles_mn = n_tiles_n * n_units_m;
     const int n_tiles = n_tiles_mn * gb.kbatches;                        // tile = slice * n_tiles_mn + (m unit, n block)
     // (a cluster whose second M block lies past M computes zeros there and stores nothing)
-    auto tile_mb = [&](int t_mn) { const int u = t_mn / n_tiles_n; return kCl == 2 ? 2 * u + cl_rank : u; };
+    auto tile_mb = [&](int t_mn) { const int u = t_mn / n_tiles_n; return kCl >= 2 ? 2 * u + cl_rank : u; };
     auto tile_nb = [&](int t_mn) { return t_mn % n_tiles_n; };
 
     auto a_hi = [&](int s) { return smem + (size_t)s * Cfg::STAGE_BYTES; };
@@ -108,20 +120,27 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
         asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(&map_wlo)) : "memory");
         for (int s = 0; s < Cfg::STAGES; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&ready[s], kTcTransformThreads / 32);
-            mbar_init(&empty[s], kCl);                          // kCl = 2: the peer's TMA writes this stage too
+            // 2-CTA MMA: the leader's "ready" also counts one arrive forwarded from the peer (its 4 transform warps are done)
+            mbar_init(&ready[s], kTcTransformThreads / 32 + ((kCl == 3 && cl_rank == 0) ? 1 : 0));
+            mbar_init(&empty[s], kCl == 2 ? 2 : 1);             // kCl = 2: the peer's TMA writes this stage too
         }
         mbar_init(accum_full, 1);
-        mbar_init(tmem_empty, kTcEpiWarps);
+        mbar_init(tmem_empty, kCl == 3 ? 2 * kTcEpiWarps : kTcEpiWarps);   // 2-CTA MMA: the leader waits for both epilogues
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     :: "r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (kCl == 3) {            // both CTAs of the pair issue the 2-CTA allocation from the same logical warp
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                         :: "r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                         :: "r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    if (kCl == 2) cluster_sync_all();            // both CTAs' barriers exist before any multicast load / remote commit
+    if (kCl >= 2) cluster_sync_all();            // both CTAs' barriers exist before any multicast load / remote commit
     else __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
@@ -143,7 +162,7 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
                 }
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % Cfg::STAGES;
-                    if (kCl == 2) mbar_wait_cluster(&empty[s], ((it / Cfg::STAGES) & 1) ^ 1);   // BOTH CTAs are done with stage s
+                    if (kCl >= 2) mbar_wait_cluster(&empty[s], ((it / Cfg::STAGES) & 1) ^ 1);   // (arrivals come from the peer too)
                     else mbar_wait(&empty[s], ((it / Cfg::STAGES) & 1) ^ 1);
                     mbar_arrive_expect_tx(&full[s], Cfg::A_BYTES + 2 * Cfg::W_BYTES);      // own A + the whole W tile (both halves)
                     tma_load_2d(a_hi(s), &map_a, &full[s], (kb0 + kb) * kTcBK, m0);        // k past K arrives as zeros
@@ -155,16 +174,67 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
                         tma_load_2d_multicast(w_lo(s) + cl_rank * HR * kTcBK * (kBf16 ? 2 : 4), &map_wlo, &full[s], (kb0 + kb) * kTcBK, nr, 3);
                         if (kBf16) tma_load_2d_multicast(w_b3(s) + cl_rank * HR * kTcBK * 2, &map_w3, &full[s], (kb0 + kb) * kTcBK, nr, 3);
                     } else {
-                        tma_load_2d(w_hi(s), &map_whi, &full[s], (kb0 + kb) * kTcBK, n0);
-                        tma_load_2d(w_lo(s), &map_wlo, &full[s], (kb0 + kb) * kTcBK, n0);      // kBf16: bf16(W_hi), half the bytes
-                        if (kBf16) tma_load_2d(w_b3(s), &map_w3, &full[s], (kb0 + kb) * kTcBK, n0);   // bf16(W_lo)
+                        const int nr = kCl == 3 ? n0 + cl_rank * (BN / 2) : n0;                // 2-CTA MMA: this CTA's half of the W rows
+                        tma_load_2d(w_hi(s), &map_whi, &full[s], (kb0 + kb) * kTcBK, nr);
+                        tma_load_2d(w_lo(s), &map_wlo, &full[s], (kb0 + kb) * kTcBK, nr);      // kBf16: bf16(W_hi), half the bytes
+                        if (kBf16) tma_load_2d(w_b3(s), &map_w3, &full[s], (kb0 + kb) * kTcBK, nr);   // bf16(W_lo)
                     }
                 }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (raw A = hi operand, see gemm_tcgen05.cuh)
-        if (lane == 0) {
+        if (kCl == 3) {
+            if (lane == 0 && cl_rank == 0) {
+                // 2-CTA MMA, leader: one M = 256 instruction covers both CTAs' 128 rows; A and the two halves of W are read
+                // from both CTAs' shared memory, each CTA's accumulator rows land in its own TMEM.  A stage is issued when
+                // BOTH CTAs' transform warps are done with it (ready: 4 local arrives + 1 forwarded by the peer).
+                constexpr uint32_t idesc2 = umma_idesc_tf32(256, BN);
+                constexpr uint32_t idesc2h = umma_idesc_bf16(256, BN);
+                const uint32_t d_main = tmem_base, d_corr = tmem_base + (uint32_t)BN;
+                int it = 0, j = 0;
+                for (int tile = worker; tile < n_tiles; tile += n_workers, ++j) {
+                    if (j > 0) {
+                        mbar_wait_cluster(tmem_empty, (uint32_t)(j - 1) & 1u);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    }
+                    for (int kb = 0; kb < nkb; ++kb, ++it) {
+                        const int s = it % Cfg::STAGES;
+                        mbar_wait_cluster(&ready[s], (it / Cfg::STAGES) & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint64_t d_ahi = umma_desc_sw64(smem_u32(a_hi(s))), d_whi = umma_desc_sw64(smem_u32(w_hi(s)));
+#pragma unroll
+                        for (int k = 0; k < kTcBK / 8; ++k) {
+                            const uint64_t koff = (uint64_t)((k * 8 * 4) >> 4);
+                            umma_tf32_2cta(d_main, d_ahi + koff, d_whi + koff, idesc2, (kb > 0 || k > 0) ? 1u : 0u);
+                        }
+                        if (kBf16) {
+                            umma_bf16_2cta(d_corr, umma_desc_sw32(smem_u32(a_lo(s))), umma_desc_sw32(smem_u32(w_b3(s))), idesc2h, kb > 0 ? 1u : 0u);
+                            umma_bf16_2cta(d_corr, umma_desc_sw32(smem_u32(a_b2(s))), umma_desc_sw32(smem_u32(w_lo(s))), idesc2h, 1u);
+                        } else {
+                            const uint64_t d_alo = umma_desc_sw64(smem_u32(a_lo(s))), d_wlo = umma_desc_sw64(smem_u32(w_lo(s)));
+#pragma unroll
+                            for (int k = 0; k < kTcBK / 8; ++k) {
+                                const uint64_t koff = (uint64_t)((k * 8 * 4) >> 4);
+                                umma_tf32_2cta(d_corr, d_ahi + koff, d_wlo + koff, idesc2, (kb > 0 || k > 0) ? 1u : 0u);
+                                umma_tf32_2cta(d_corr, d_alo + koff, d_whi + koff, idesc2, 1u);
+                            }
+                        }
+                        umma_commit_2cta(&empty[s]);               // frees stage s in both CTAs
+                    }
+                    umma_commit_2cta(accum_full);                  // both CTAs' epilogues
+                }
+            } else if (lane == 0) {
+                // peer: this otherwise idle thread forwards "my 4 transform warps are done with stage s" as ONE remote arrive
+                int it = 0;
+                for (int tile = worker; tile < n_tiles; tile += n_workers)
+                    for (int kb = 0; kb < nkb; ++kb, ++it) {
+                        const int s = it % Cfg::STAGES;
+                        mbar_wait(&ready[s], (it / Cfg::STAGES) & 1);
+                        mbar_arrive_cluster(&ready[s], 0);
+                    }
+            }
+        } else if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_tf32(128, BN);
             const uint32_t d_main = tmem_base, d_corr = tmem_base + (uint32_t)BN;
             int it = 0, j = 0;
@@ -336,7 +406,8 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
             if (c_begin < c_end) {
                 issue_group(c_begin);
             } else if (lane == 0) {
-                mbar_arrive(tmem_empty);                               // nothing to drain for this warp (BN <= 128)
+                if (kCl == 3 && cl_rank == 1) mbar_arrive_cluster(tmem_empty, 0);
+                else mbar_arrive(tmem_empty);                          // nothing to drain for this warp (BN <= 128)
             }
 #pragma unroll 1
             for (int c = c_begin; c < c_end; c += 16) {
@@ -358,7 +429,10 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
                     // every accumulator column of this tile is in registers: hand TMEM back to the MMA warp
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(tmem_empty);
+                    if (lane == 0) {
+                        if (kCl == 3 && cl_rank == 1) mbar_arrive_cluster(tmem_empty, 0);   // the leader issues the next tile's MMAs
+                        else mbar_arrive(tmem_empty);
+                    }
                 }
                 __syncwarp();
 #pragma unroll
@@ -383,22 +457,30 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    if (kCl == 2) cluster_sync_all();            // the peer may still multicast into / commit onto this CTA's shared memory
+    if (kCl >= 2) cluster_sync_all();            // the peer may still multicast into / commit onto this CTA's shared memory
     else __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
-                     :: "r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+        if (kCl == 3)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;"
+                         :: "r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
+                         :: "r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
     }
 }
 
-static int g_tc_cluster = 1;   // 1 = W multicast across CTA pairs for large M (default), 0 = off (digat_debug_set_gemm_variant 6 / 7)
+// Measured (tools/gemm_bench.py, profiles/r2_gemm_variants.txt): multicast is correct (bit-identical) but NOT faster -- 206 vs
+// 214 TFLOP/s (3xTF32), 222 vs 220 (BF16 corrections) at M = 136k.  The full W tile still has to LAND in every SM's shared
+// memory: the bound is the ~48 B/clk each SM can take in from the fabric (38 KB per ~800-cycle k-block), not the L2 slices.
+// Only the 2-CTA MMA (each SM holds half of W) removes those bytes.  Kept as an experiment, off by default.
+static int g_tc_cluster = 0;   // 0 = independent CTAs, 1 = W multicast across CTA pairs, 2 = 2-CTA MMA (digat_debug_set_gemm_variant 6 / 7 / 8)
 
 // Launch of one persistent instantiation; kCl = 2 goes through cudaLaunchKernelEx with a (2,1,1) cluster.
 template <int BN, bool kBf16, int kCl>
 int launch_tf32x3_persistent_inst(const CUtensorMap& ma, const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& m3,
                                   const float* bias, float* C, int ldc, int M, int N, int K, GroupBias gb, int units, int sm_count,
                                   cudaStream_t st) {
-    using Cfg = TcPersistCfg<BN>;
+    using Cfg = TcPersistCfg<BN, kCl>;
     auto kernel = gemm_tf32x3_persistent_kernel<BN, kBf16, kCl>;
     if (int rc_ = ensure_dynamic_smem(kernel, (size_t)Cfg::SMEM)) return rc_;
     if (kCl == 1) {
@@ -445,7 +527,7 @@ int launch_tf32x3_persistent(const float* A, int lda, const float* W_hi, const f
     const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + 127) / 128;
     // W multicast pays when every SM streams many tiles (the kernel is then bound by L2 -> SM traffic); short problems and
     // split-K weight gradients (few tiles per CTA) keep the independent CTAs
-    const bool cluster = g_tc_cluster != 0 && gb.kbatches == 1 && tiles_m >= 2 &&
+    const bool cluster = g_tc_cluster != 0 && gb.kbatches == 1 && tiles_m >= 2 && (BN / 2) % 8 == 0 &&
                          (long)tiles_n * tiles_m >= 4L * di->sm_count;
     const int wbox = cluster ? BN / 2 : BN;                               // rows of one W box (a cluster CTA loads half a tile)
     CUtensorMap ma, mh, ml;
@@ -461,7 +543,11 @@ int launch_tf32x3_persistent(const float* A, int lda, const float* W_hi, const f
         if ((rc = make_tensor_map_2d(&ml, W_lo, N, K, ldw, wbox, kTcBK, CU_TENSOR_MAP_SWIZZLE_64B)) != DIGAT_OK) return rc;
     }
     const int units = tiles_n * (cluster ? (tiles_m + 1) / 2 : tiles_m) * gb.kbatches;
-    if (cluster) {
+    if (cluster && g_tc_cluster == 2) {          // 2-CTA MMA
+        if (bf16c) return launch_tf32x3_persistent_inst<BN, true, 3>(ma, mh, ml, m3, bias, C, ldc, M, N, K, gb, units, di->sm_count, st);
+        return launch_tf32x3_persistent_inst<BN, false, 3>(ma, mh, ml, m3, bias, C, ldc, M, N, K, gb, units, di->sm_count, st);
+    }
+    if (cluster) {                               // W multicast (experiment)
         if (bf16c) return launch_tf32x3_persistent_inst<BN, true, 2>(ma, mh, ml, m3, bias, C, ldc, M, N, K, gb, units, di->sm_count, st);
         return launch_tf32x3_persistent_inst<BN, false, 2>(ma, mh, ml, m3, bias, C, ldc, M, N, K, gb, units, di->sm_count, st);
     }

@@ -15,7 +15,7 @@ def run(M, N, K, bf16c, cluster, reps=20):
     hb = torch.empty(W.shape, dtype=torch.bfloat16, device='cuda'); lb = torch.empty_like(hb)
     _lib.call('digat_split_bf16', W.data_ptr(), hb.data_ptr(), lb.data_ptr(), W.numel(), st)
     C = torch.empty((M, N), device='cuda')
-    _lib.call('digat_debug_set_gemm_variant', 7 if cluster else 6)
+    _lib.call('digat_debug_set_gemm_variant', 6 + cluster)
     def call():
         if bf16c:
             _lib.call('digat_linear_tf32_bf16c', A.data_ptr(), K, hi.data_ptr(), hb.data_ptr(), lb.data_ptr(), K, 0, C.data_ptr(), N,
@@ -33,10 +33,10 @@ def run(M, N, K, bf16c, cluster, reps=20):
     ref = A[sel].double() @ W.double().t()
     err = float((C[sel].double() - ref).abs().max() / ref.abs().max())
     print('M=%d N=%d K=%d  %-8s %-10s  %.3f ms  %.1f TFLOP/s  err %.2e' % (M, N, K, 'bf16c' if bf16c else 'tf32x3',
-          'multicast' if cluster else 'single', ms, 2.0 * M * N * K / ms / 1e9, err))
+          ('single', 'multicast', '2-CTA MMA')[cluster], ms, 2.0 * M * N * K / ms / 1e9, err))
 
 for (M, N, K) in [(136000, 1200, 400), (278528, 1200, 400), (27000, 1200, 400), (77824, 400, 400), (40960, 400, 800)]:
     for bf16c in (False, True):
-        for cluster in (False, True):
+        for cluster in (0, 2):
             run(M, N, K, bf16c, cluster)
-_lib.call('digat_debug_set_gemm_variant', 7)
+_lib.call('digat_debug_set_gemm_variant', 6)
