@@ -40,10 +40,14 @@ namespace digat {
 #ifndef DIGAT_SPARSE_MINCTAS
 #define DIGAT_SPARSE_MINCTAS 2
 #endif
+#ifndef DIGAT_SPARSE_UNROLL
+#define DIGAT_SPARSE_UNROLL 4      // measured (tools/run_layer_variants.sh): 4 quads in flight 0.656 ms vs 0.683 (2); more warps are slower
+#endif
 constexpr int kSparseConsumers = 32 * DIGAT_SPARSE_WARPS; // consumer warps 0..W-1
 constexpr int kSparseThreads = kSparseConsumers + 32;     // + producer warp
 constexpr int kSparseBufs = DIGAT_SPARSE_BUFS;
 constexpr int kSparseDc1 = 32, kSparseDc3 = 64;
+constexpr int kSparseUnroll = DIGAT_SPARSE_UNROLL;      // feature quads of one edge in flight in the score loop
 
 struct SparseGeom {
     int nch1, nch3;
@@ -219,7 +223,7 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
             const uint32_t ko = koff + (mt >> 8) * (uint32_t)(kSparseDc1 * 4);
             const uint32_t ukey = ((uo >> 7) & 7u) << 4, kkey = ((ko >> 7) & 7u) << 4;
             uint64_t acc0 = 0ull, acc1 = 0ull;
-#pragma unroll 2
+#pragma unroll kSparseUnroll
             for (int q = 0; q < wq; ++q) {
                 const uint32_t qo = (uint32_t)q * 16u;
                 const float4 av = *reinterpret_cast<const float4*>(smem_raw + aoff + qo);

@@ -103,10 +103,13 @@ class PackedWeight:
 
 # rows below which the exact-fp32 CUDA-core GEMM is used (a 128-row tensor-core tile would be mostly padding)
 TENSOR_CORE_MIN_ROWS = 256
-# Large projections (persistent kernel, M >= BF16C_MIN_ROWS): the two correction products of the 3xTF32 scheme run as BF16
-# MMAs (digat_linear_tf32_bf16c: 4 instead of 6 TF32-MMA times per k-block; tests/test_gpu_benchpaths.py holds the L=7
-# golden case and the sampled bench batches to the same 1e-5 gate).  Switch off to get the pure 3xTF32 products everywhere.
-GEMM_BF16_CORRECTIONS = True
+# Optional: large projections (persistent kernel, dense row count >= BF16C_MIN_ROWS) run the two correction products of the
+# 3xTF32 scheme as BF16 MMAs (digat_linear_tf32_bf16c: 4 instead of 6 TF32-MMA times per k-block).  Validated (the L=7
+# golden case x64 and the sampled bench batches stay inside the 1e-5 gate with it on), but OFF by default: the GEMM is bound
+# by the bytes each SM takes in per k-block, not by the tensor pipe, so it buys 3.5 % on the GEMM (~1 % of a step,
+# profiles/r2_gemm_variants.txt) while a size-dependent scheme would end the bit-identity of the shared-user-graph and the
+# expanded scoring paths (their layer-0 projections have different row counts).
+GEMM_BF16_CORRECTIONS = False
 BF16C_MIN_ROWS = 16385
 
 
