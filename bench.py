@@ -523,9 +523,12 @@ def train_record(args, rank, local_rank, world, dev, steps, cpu_baseline=True):
     model = Model(cfg, D)
     model.graph_encoder.load_state_dict(sd)
     model = model.to(dev).train()
-    # whole-step CUDA graph (digat_b200/training.py) on one GPU; the DDP step runs eagerly (capturing DDP's reducer +
-    # NCCL all-reduce failed in this PyTorch build: capture_end reported an invalidated capture from the backward)
-    graphed = world == 1 and not args.eager_train
+    # Gradient exchange: by default ONE all-reduce (mean) of the flat gradient buffer (digat_b200/training.py::FlatGradients)
+    # inside the step, which -- unlike DDP's reducer hooks -- captures into the whole-step CUDA graph; --eager-train runs the
+    # reference's arrangement instead (torch DistributedDataParallel around the model, trainer.py:19, eager).
+    from digat_b200.training import FlatGradients, GraphedTrainStep, broadcast_parameters
+    use_ddp = world > 1 and args.eager_train
+    graphed = not args.eager_train
     opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=graphed)
     bs, news_num = 64, 5
     warmup = max(args.warmup, 3)
@@ -541,7 +544,7 @@ def train_record(args, rank, local_rank, world, dev, steps, cpu_baseline=True):
         cand = torch.from_numpy(rng.integers(1, emb.shape[0], size=(bs, news_num))).to(dev)
         return (emb[hist[beh]], ug[beh], cm[beh], ci[beh], emb[node[cand]], ng[cand], nm[cand])
 
-    if world > 1:
+    if use_ddp:
         # DDP hooks fire on the wrapped module's forward: route forward_embeddings through it
         class _Fwd(torch.nn.Module):
             def __init__(self, m):
@@ -551,24 +554,37 @@ def train_record(args, rank, local_rank, world, dev, steps, cpu_baseline=True):
             def forward(self, *a):
                 return self.m.forward_embeddings(*a)
         fwd = torch.nn.parallel.DistributedDataParallel(_Fwd(model), device_ids=[local_rank])
+        flat = None
     else:
         fwd = model.forward_embeddings
+        broadcast_parameters(model)
+        flat = FlatGradients(model.parameters())
 
     def eager_step(inp):
         logits = fwd(*inp)
         loss = (-F.log_softmax(logits, dim=1).select(1, 0)).mean()
-        opt.zero_grad(set_to_none=True)
+        if flat is None:
+            opt.zero_grad(set_to_none=True)
+        else:
+            flat.zero()
         loss.backward()
+        if flat is not None:
+            flat.all_reduce_mean()                                # NCCL all-reduce over NVLink (no-op on one GPU)
         torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
         opt.step()
         return loss
 
     inputs = [make_step_inputs() for _ in range(warmup + steps)]
     step = eager_step
+    capture_note = None
     if graphed:
-        from digat_b200.training import GraphedTrainStep
-        gstep = GraphedTrainStep(lambda *a: eager_step(a), inputs[0], modules=(model,))
-        step = lambda inp: gstep(*inp)                      # noqa: E731
+        try:
+            gstep = GraphedTrainStep(lambda *a: eager_step(a), inputs[0], modules=(model,), distributed=world > 1)
+            step = lambda inp: gstep(*inp)                      # noqa: E731
+        except Exception as exc:                                # capture refused (e.g. NCCL inside the graph): stay eager
+            graphed = False
+            capture_note = 'graph capture failed, ran eagerly: %s' % str(exc).splitlines()[0][:200]
+            torch.cuda.synchronize()
     for s_ in range(warmup):
         step(inputs[s_])
     if world > 1:
@@ -613,8 +629,11 @@ def train_record(args, rank, local_rank, world, dev, steps, cpu_baseline=True):
                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
                'config': {'workload': workload + ':train', 'behaviours_per_gpu': bs, 'candidates': news_num,
                           'rows_per_gpu': bs * news_num, 'dropout': 0.2, 'optimizer': 'Adam + clip_grad_norm 1',
-                          'execution': 'whole step replayed as one CUDA graph' if graphed else 'eager',
-                          'parallelism': 'DDP x%d, NCCL gradient all-reduce (%.1f MB fp32 per step)' % (world, n_params * 4 / 1e6)
+                          'execution': ('whole step (incl. the gradient all-reduce) replayed as one CUDA graph' if graphed
+                                        else 'eager') + ('; ' + capture_note if capture_note else ''),
+                          'parallelism': ('data parallel x%d, %s, %.1f MB fp32 per step' % (
+                              world, 'torch DistributedDataParallel (bucketed NCCL all-reduce)' if use_ddp
+                              else 'one NCCL all-reduce (mean) of the flat gradient buffer', n_params * 4 / 1e6))
                                          if world > 1 else 'single GPU (no collective)'},
                'gpu_launches': launches_timed if not graphed else sum(v[1] for v in agg.values()) * steps,
                'gpu_launches_note': 'C-ABI kernel launches (replayed from the captured graph)' if graphed else 'C-ABI kernel launches',

@@ -1,20 +1,68 @@
-"""Training helper: a whole training step (forward, backward kernels, gradient clipping, optimizer) captured once as a
-CUDA graph and replayed per batch.
+"""Training helpers: a whole training step (forward, backward kernels, gradient all-reduce, clipping, optimizer) captured
+once as a CUDA graph and replayed per batch.
 
 At the reference's batch size (64 behaviours x 5 candidates = 320 encoder rows, config.py:31,34) a step is ~300 short
 kernel launches plus PyTorch's autograd and optimizer bookkeeping: eager execution is bound by the host, not by the GPU.
 All shapes of a training step are fixed (no node pruning, no data-dependent launch parameters), so the step can be
 captured as it is.  Requirements: fixed batch shapes, an optimizer constructed with ``capturable=True``, and a step
-function without host synchronisation (``loss.item()`` belongs outside)."""
+function without host synchronisation (``loss.item()`` belongs outside).
+
+Data parallelism (reference trainer.py:19 wraps the model in DistributedDataParallel): ``FlatGradients`` lays every
+parameter's ``.grad`` out as a view into ONE flat buffer, so the gradient exchange of a step is a single
+``all_reduce(flat, AVG)`` over NCCL / NVLink -- the same result as DDP's bucketed all-reduce (mean over ranks), but one
+collective without autograd hooks, which (unlike DDP's reducer) captures into the step's CUDA graph.  21.2 MB at L=3: about
+0.1 ms on NVSwitch, so overlapping it with the backward (what DDP's buckets are for) would buy nothing here."""
 import torch
 
 
+class FlatGradients:
+    """Gives every parameter a persistent ``.grad`` that is a view into one flat fp32 buffer.
+
+    ``zero()`` replaces ``optimizer.zero_grad()`` (the views must stay in place: autograd then accumulates into them in
+    place), ``all_reduce_mean()`` averages the buffer over the process group (no-op for a single process)."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        dev = self.params[0].device
+        n = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero(self):
+        self.flat.zero_()
+
+    def all_reduce_mean(self, group=None):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            if dist.get_backend(group) == 'nccl':
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group)
+            else:                                           # gloo (CPU tests) has no AVG
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+                self.flat.div_(dist.get_world_size(group))
+
+
+def broadcast_parameters(module, src=0, group=None):
+    """What DDP does at construction: every rank starts from rank ``src``'s parameters and buffers."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t.data, src=src, group=group)
+        for m in module.modules():
+            if hasattr(m, 'invalidate_packed'):
+                m.invalidate_packed()
+
+
 class GraphedTrainStep:
-    def __init__(self, step_fn, example_inputs, warmup: int = 3, modules=()):
+    def __init__(self, step_fn, example_inputs, warmup: int = 3, modules=(), distributed: bool = False):
         """step_fn(*inputs) -> loss tensor; it must do zero_grad / backward / optimizer.step itself.
         NOTE: the ``warmup`` eager calls and the capture itself are real training steps on ``example_inputs``.
         modules: nn.Modules whose DIGAT encoders keep a packed copy of the weights for inference -- a replayed optimizer
-        step does not bump ``param._version``, so every replay invalidates those copies (DIGAT.invalidate_packed)."""
+        step does not bump ``param._version``, so every replay invalidates those copies (DIGAT.invalidate_packed).
+        distributed: the step contains NCCL collectives (FlatGradients.all_reduce_mean): capture in thread-local error mode
+        (NCCL's watchdog thread polls events while the capture is open)."""
         self._encoders = [m for mod in modules for m in mod.modules() if hasattr(m, 'invalidate_packed')]
         self.static_inputs = [x.clone() for x in example_inputs]
         cur = torch.cuda.current_stream()
@@ -26,7 +74,8 @@ class GraphedTrainStep:
         cur.wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        kw = {'capture_error_mode': 'thread_local'} if distributed else {}
+        with torch.cuda.graph(self.graph, **kw):
             self.static_loss = step_fn(*self.static_inputs)
 
     def __call__(self, *inputs):

@@ -105,3 +105,58 @@ def test_similar_to_csr_and_impression_offsets():
     # rank_lists / metrics on the same layout (host versions; the device versions are checked against them on the GPU)
     ranks = evaluate.rank_lists(np.array([0.1, 0.3, 0.3, 1.0, -1.0, 2.0], dtype=np.float32), imp)
     assert ranks == [[3, 1, 2], [1], [], [2, 1]]
+
+
+_GLOO_FLATGRAD_WORKER = r'''
+import os, sys
+import torch
+import torch.distributed as dist
+from torch.nn.parallel import DistributedDataParallel as DDP
+sys.path.insert(0, os.environ["DIGAT_ROOT"])
+from digat_b200.training import FlatGradients, broadcast_parameters
+
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+torch.manual_seed(100 + rank)                                # different initial weights per rank on purpose
+make = lambda: torch.nn.Sequential(torch.nn.Linear(12, 16), torch.nn.ReLU(), torch.nn.Linear(16, 3))
+ours = make()
+broadcast_parameters(ours)                                   # every rank now holds rank 0's weights
+ref = make()
+ref.load_state_dict(ours.state_dict())
+ddp = DDP(ref)
+g = torch.Generator().manual_seed(7)
+X = torch.randn(8 * world, 12, generator=g)
+Y = torch.randn(8 * world, 3, generator=g)
+xs, ys = X[rank * 8:(rank + 1) * 8], Y[rank * 8:(rank + 1) * 8]
+flat = FlatGradients(ours.parameters())
+for step in range(2):                                        # second pass: zero() + in-place accumulation into the views
+    flat.zero()
+    ((ours(xs) - ys) ** 2).mean().backward()
+    flat.all_reduce_mean()
+    ddp.zero_grad(set_to_none=True)
+    ((ddp(xs) - ys) ** 2).mean().backward()
+    for a, b in zip(ours.parameters(), ref.parameters()):
+        assert a.grad.data_ptr() >= flat.flat.data_ptr() and a.grad.data_ptr() < flat.flat.data_ptr() + flat.flat.numel() * 4
+        assert torch.allclose(a.grad, b.grad, rtol=1e-6, atol=1e-7), (step, (a.grad - b.grad).abs().max())
+# and both equal the single-process gradient on the union batch
+single = make()
+single.load_state_dict(ours.state_dict())
+((single(X) - Y) ** 2).mean().backward()
+for a, b in zip(ours.parameters(), single.parameters()):
+    assert torch.allclose(a.grad, b.grad, rtol=1e-5, atol=1e-6)
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_flat_gradient_all_reduce_equals_ddp_world_size_2_gloo(tmp_path):
+    """The N>1 training path (digat_b200/training.py): one all-reduce of the flat gradient buffer gives DDP's gradients
+    (reference trainer.py:19) and the single-process gradients of the union batch."""
+    script = tmp_path / 'worker.py'
+    script.write_text(_GLOO_FLATGRAD_WORKER)
+    env = dict(os.environ, DIGAT_ROOT=ROOT)
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2',
+                        '--master-addr', '127.0.0.1', '--master-port', '29533', str(script)],
+                       env=env, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count('ok') == 2
