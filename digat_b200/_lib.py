@@ -57,6 +57,9 @@ SIGNATURES = {
     'digat_build_user_graphs': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p],
     'digat_sag_bfs': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                       ctypes.c_double, c_void_p, c_void_p],
+    'digat_msa_attention_fwd': [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_int, c_int, c_void_p],
+    'digat_additive_pool_fwd': [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int,
+                                c_void_p],
     'digat_rank_impressions': [c_void_p, c_void_p, c_void_p, c_int64, c_void_p],
     'digat_impression_metrics': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p],
 }

@@ -13,6 +13,7 @@
 #include "context_bwd.cuh"
 #include "gemm_wgrad.cuh"
 #include "builders.cuh"
+#include "news_encoder.cuh"
 
 using namespace digat;
 
@@ -286,6 +287,16 @@ int digat_rank_impressions(const float* scores, const int64_t* offsets, int32_t*
 int digat_impression_metrics(const int32_t* ranks, const uint8_t* labels, const int64_t* offsets, double* out,
                              uint8_t* valid, int64_t n_imp, void* stream) {
     return launch_impression_metrics(ranks, labels, offsets, out, valid, n_imp, as_stream(stream));
+}
+
+int digat_msa_attention_fwd(const float* QKV, int ld, float* H, int ldh, int64_t n_titles, int T, int heads, int dk,
+                            void* stream) {
+    return launch_msa_attention(QKV, ld, H, ldh, n_titles, T, heads, dk, as_stream(stream));
+}
+
+int digat_additive_pool_fwd(const float* att_pre, int lda, const float* w2, const float* H, int ldh, const uint8_t* mask,
+                            float* out, int ldo, int64_t n_titles, int T, int A, int D, void* stream) {
+    return launch_additive_pool(att_pre, lda, w2, H, ldh, mask, out, ldo, n_titles, T, A, D, as_stream(stream));
 }
 
 }  // extern "C"

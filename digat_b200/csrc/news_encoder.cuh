@@ -1,0 +1,148 @@
+// News (title) encoder, MSA variant -- reference newsEncoders.py:58-82 + layers.py:50-115.
+//
+//   w  = word_embedding[title]                                  [titles, T, E]      (digat_gather_rows_i32)
+//   QKV = w [W_Q; W_K; W_V]^T + [b_Q; 0; b_V]                   [titles*T, 3*h*dk]   (projection GEMM, one launch)
+//   per head: A = Q K^T / sqrt(dk);  alpha = softmax_j(A);  O = alpha V;  H = relu(concat heads)      msa_attention_kernel
+//   att = tanh(H affine1^T + b1);  a_t = att_t . w2;  alpha = softmax_t(mask(a));  out = sum_t alpha_t H_t   (GEMM +) additive_pool_kernel
+//
+// msa_attention_kernel: a title has T <= 32 tokens, so ONE WARP owns one (title, head): lane i is query token i.  K_h and
+// V_h (T x dk floats each) sit in the warp's slice of shared memory and are read as broadcasts; the lane keeps its q row,
+// its T scores and its dk outputs in registers -- the softmax needs no shuffle at all.  The self-attention has no padding
+// mask (layers.py:88-97 applies none); padded tokens are masked only by the pooling afterwards.
+// HBM traffic per title: read T*3*h*dk*4, write T*h*dk*4 bytes (205 KB at T=32, h*dk=400): the kernel is HBM-bound.
+//
+// additive_pool_kernel: one CTA per title, a warp per token for the tanh / dot pass, then the masked softmax over the T
+// tokens and the weighted sum of the H rows (each read once from L2/DRAM).
+#pragma once
+#include "common.cuh"
+#include "tma.cuh"   // ensure_dynamic_smem
+
+namespace digat {
+
+constexpr int kMsaMaxT = 32;       // tokens per title (config.max_title_length, default 32)
+constexpr int kMsaMaxDk = 32;      // head dimension (config.MSA_head_dim, default 25)
+constexpr int kMsaWarps = 8;       // (title, head) pairs per CTA
+
+__global__ void __launch_bounds__(kMsaWarps * 32)
+msa_attention_kernel(const float* __restrict__ QKV, int ld, float* __restrict__ H, int ldh, int64_t n_titles, int T, int heads,
+                     int dk, float inv_scale_div) {
+    extern __shared__ float msa_smem[];                             // [kMsaWarps][2][T * dk]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t unit = (int64_t)blockIdx.x * kMsaWarps + warp;    // (title, head)
+    if (unit >= n_titles * heads) return;
+    const int64_t title = unit / heads;
+    const int head = (int)(unit - title * heads);
+    const int hd = heads * dk;
+    float* Ks = msa_smem + (size_t)warp * 2 * T * dk;
+    float* Vs = Ks + T * dk;
+    const float* base = QKV + (size_t)title * T * ld + head * dk;   // Q block; K at +hd, V at +2*hd
+    for (int e = lane; e < T * dk; e += 32) {
+        const int t = e / dk, d = e - t * dk;
+        Ks[e] = base[(size_t)t * ld + hd + d];
+        Vs[e] = base[(size_t)t * ld + 2 * hd + d];
+    }
+    float q[kMsaMaxDk];
+#pragma unroll
+    for (int d = 0; d < kMsaMaxDk; ++d) q[d] = (lane < T && d < dk) ? base[(size_t)lane * ld + d] : 0.f;
+    __syncwarp();
+    float s[kMsaMaxT];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < kMsaMaxT; ++j) {
+        float acc = 0.f;
+        if (j < T) {
+#pragma unroll
+            for (int d = 0; d < kMsaMaxDk; ++d)
+                if (d < dk) acc = fmaf(q[d], Ks[j * dk + d], acc);
+            acc = acc / inv_scale_div;                               // the reference divides by sqrt(dk) (layers.py:89)
+            mx = fmaxf(mx, acc);
+        }
+        s[j] = acc;
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMsaMaxT; ++j) {
+        s[j] = j < T ? expf(s[j] - mx) : 0.f;
+        sum += s[j];
+    }
+    float o[kMsaMaxDk];
+#pragma unroll
+    for (int d = 0; d < kMsaMaxDk; ++d) o[d] = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMsaMaxT; ++j) {
+        if (j < T) {
+            const float p = s[j] / sum;
+#pragma unroll
+            for (int d = 0; d < kMsaMaxDk; ++d)
+                if (d < dk) o[d] = fmaf(p, Vs[j * dk + d], o[d]);
+        }
+    }
+    if (lane < T) {
+        float* out = H + ((size_t)title * T + lane) * ldh + head * dk;
+#pragma unroll
+        for (int d = 0; d < kMsaMaxDk; ++d)
+            if (d < dk) out[d] = fmaxf(o[d], 0.f);                   // F.relu (newsEncoders.py:78)
+    }
+}
+
+inline int launch_msa_attention(const float* QKV, int ld, float* H, int ldh, int64_t n_titles, int T, int heads, int dk,
+                                cudaStream_t st) {
+    if (n_titles <= 0) return DIGAT_OK;
+    DIGAT_REQUIRE(QKV && H, "digat_msa_attention_fwd: null pointer");
+    DIGAT_REQUIRE(T >= 1 && T <= kMsaMaxT && dk >= 1 && dk <= kMsaMaxDk && heads >= 1,
+                  "digat_msa_attention_fwd: needs max_title_length <= %d and head_dim <= %d (T=%d, dk=%d)", kMsaMaxT, kMsaMaxDk, T, dk);
+    DIGAT_REQUIRE(ld >= 3 * heads * dk && ldh >= heads * dk, "digat_msa_attention_fwd: leading dimension too small");
+    const int64_t units = n_titles * heads;
+    const size_t smem = (size_t)kMsaWarps * 2 * T * dk * sizeof(float);
+    DIGAT_REQUIRE(units / kMsaWarps + 1 < (1LL << 31), "digat_msa_attention_fwd: too many titles for one launch");
+    if (int rc_ = ensure_dynamic_smem(msa_attention_kernel, smem)) return rc_;
+    msa_attention_kernel<<<(unsigned)((units + kMsaWarps - 1) / kMsaWarps), kMsaWarps * 32, smem, st>>>(
+        QKV, ld, H, ldh, n_titles, T, heads, dk, sqrtf((float)dk));
+    return check_launch("digat_msa_attention_fwd");
+}
+
+// out[title] = sum_t softmax_t(mask(att_t . w2)) H[title, t, :],  att = tanh(pre-activation rows of the affine1 GEMM)
+constexpr int kPoolThreads = 128;
+
+__global__ void __launch_bounds__(kPoolThreads)
+additive_pool_kernel(const float* __restrict__ att_pre, int lda, const float* __restrict__ w2, const float* __restrict__ H,
+                     int ldh, const uint8_t* __restrict__ mask, float* __restrict__ out, int ldo, int T, int A, int D) {
+    __shared__ float a_s[kMsaMaxT];
+    const int64_t title = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int t = warp; t < T; t += kPoolThreads / 32) {
+        const float* row = att_pre + ((size_t)title * T + t) * lda;
+        float acc = 0.f;
+        for (int c = lane; c < A; c += 32) acc = fmaf(tanhf(row[c]), w2[c], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) a_s[t] = mask[(size_t)title * T + t] != 0 ? acc : kNegFill;      // masked_fill(mask == 0, -1e9), layers.py:111
+    }
+    __syncthreads();
+    float mx = -INFINITY;
+    for (int t = 0; t < T; ++t) mx = fmaxf(mx, a_s[t]);
+    float sum = 0.f;
+    for (int t = 0; t < T; ++t) sum += expf(a_s[t] - mx);
+    for (int q = threadIdx.x; q < D / 4; q += kPoolThreads) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int t = 0; t < T; ++t) {
+            const float p = expf(a_s[t] - mx) / sum;
+            const float4 h = reinterpret_cast<const float4*>(H + ((size_t)title * T + t) * ldh)[q];
+            acc.x = fmaf(p, h.x, acc.x); acc.y = fmaf(p, h.y, acc.y); acc.z = fmaf(p, h.z, acc.z); acc.w = fmaf(p, h.w, acc.w);
+        }
+        reinterpret_cast<float4*>(out + (size_t)title * ldo)[q] = acc;
+    }
+}
+
+inline int launch_additive_pool(const float* att_pre, int lda, const float* w2, const float* H, int ldh, const uint8_t* mask,
+                                float* out, int ldo, int64_t n_titles, int T, int A, int D, cudaStream_t st) {
+    if (n_titles <= 0) return DIGAT_OK;
+    DIGAT_REQUIRE(att_pre && w2 && H && mask && out, "digat_additive_pool_fwd: null pointer");
+    DIGAT_REQUIRE(T >= 1 && T <= kMsaMaxT && A >= 1 && D >= 4 && (D & 3) == 0 && (ldh & 3) == 0 && (ldo & 3) == 0 &&
+                  lda >= A && ldh >= D && ldo >= D, "digat_additive_pool_fwd: bad sizes (T=%d, A=%d, D=%d)", T, A, D);
+    DIGAT_REQUIRE(aligned16(H) && aligned16(out), "digat_additive_pool_fwd: H / out must be 16-byte aligned");
+    DIGAT_REQUIRE(n_titles < (1LL << 31), "digat_additive_pool_fwd: too many titles for one launch");
+    additive_pool_kernel<<<(unsigned)n_titles, kPoolThreads, 0, st>>>(att_pre, lda, w2, H, ldh, mask, out, ldo, T, A, D);
+    return check_launch("digat_additive_pool_fwd");
+}
+
+}  // namespace digat

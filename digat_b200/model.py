@@ -1,7 +1,11 @@
-"""Drop-in for the graph-encoder half of reference model.py: ``Model.inference`` (model.py:87-90) and the logits of
-``Model.forward`` (model.py:73-77) on top of the sm_100a DIGAT encoder.  The news (text) encoder is outside the hot
-path: callers hand in news embeddings, exactly as reference util.compute_scores does after
-caching them (util.py:24-33)."""
+"""Drop-in for reference model.py: the ``graph_encoder`` string dispatch (model.py:18-31), ``Model.inference``
+(model.py:87-90), ``Model.forward`` (model.py:54-77) and its logits on top of the sm_100a encoders.
+
+The news (text) encoder is outside the north-star hot path: the scoring path works on news
+embeddings, exactly as reference util.compute_scores does after caching them (util.py:24-33) -- ``forward_embeddings`` is
+``forward`` from the point where the embeddings exist (and is what trains, through autograd_ops).  When the config carries
+the text-side fields (``vocabulary_size`` ...) the MSA news encoder (newsEncoders.py) is built too and
+``forward`` takes the reference's token tensors (inference only: the text encoder has no backward kernels)."""
 import torch
 import torch.nn as nn
 
@@ -14,6 +18,14 @@ class Model(nn.Module):
         from .ablation_encoders import ENCODERS                                 # the string dispatch of model.py:18-31
         if config.graph_encoder not in ENCODERS:
             raise Exception(config.graph_encoder + ' is not implemented')      # same wording as model.py:31
+        self.news_encoder = None
+        if hasattr(config, 'vocabulary_size'):                                  # text side available: model.py:11-16
+            from . import newsEncoders
+            if getattr(config, 'news_encoder', 'MSA') != 'MSA':
+                raise Exception(config.news_encoder + ' is not implemented')
+            self.news_encoder = newsEncoders.MSA(config)
+            news_embedding_dim = self.news_encoder.news_embedding_dim
+            self.max_title_length = config.max_title_length
         self.graph_encoder = ENCODERS[config.graph_encoder](config, news_embedding_dim)
         self.model_name = getattr(config, 'news_encoder', 'MSA') + '-' + config.graph_encoder
         self.max_history_num = config.max_history_num
@@ -24,7 +36,23 @@ class Model(nn.Module):
         self.user_graph_size = config.max_history_num + config.category_num
 
     def initialize(self):
+        if self.news_encoder is not None:
+            self.news_encoder.initialize()
         self.graph_encoder.initialize()
+
+    def forward(self, user_title_text, user_title_mask, user_graph, user_category_mask, user_category_indices,
+                news_title_text, news_title_mask, news_graph, news_graph_mask):
+        """Reference Model.forward (model.py:54-77) on token tensors; needs the news encoder (inference only)."""
+        if self.news_encoder is None:
+            raise RuntimeError('Model was built without the text-side config fields: use forward_embeddings')
+        bs, news_num = news_graph.shape[0], news_graph.shape[1]
+        T = self.max_title_length
+        cand = self.news_encoder(news_title_text.reshape(bs * news_num, self.news_graph_size, T),
+                                 news_title_mask.reshape(bs * news_num, self.news_graph_size, T))
+        hist = self.news_encoder(user_title_text, user_title_mask)
+        return self.forward_embeddings(hist, user_graph, user_category_mask, user_category_indices,
+                                       cand.view(bs, news_num, self.news_graph_size, self.news_embedding_dim),
+                                       news_graph, news_graph_mask)
 
     def inference(self, user_news_embedding, user_graph, user_category_mask, user_category_indices,
                   candidate_news_embedding, news_graph, news_graph_mask, c_n0):

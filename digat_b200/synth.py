@@ -129,6 +129,42 @@ def make_ablation_state_dict(kind, config, D=400, seed=0):
     return {k: torch.from_numpy(v) for k, v in sd.items()}
 
 
+def make_text_config(vocabulary_size=500, max_title_length=32, word_embedding_dim=300, MSA_head_num=16, MSA_head_dim=25,
+                     attention_dim=256, **kw):
+    """make_config plus the text-side fields of reference config.py (newsEncoders.MSA reads them)."""
+    return make_config(vocabulary_size=vocabulary_size, max_title_length=max_title_length,
+                       word_embedding_dim=word_embedding_dim, MSA_head_num=MSA_head_num, MSA_head_dim=MSA_head_dim,
+                       attention_dim=attention_dim, word_threshold=3, dataset='synthetic', **kw)
+
+
+def make_msa_state_dict(config, seed=0):
+    """Seeded trained-like state_dict of the MSA news encoder (names/shapes of reference newsEncoders.py:58-66)."""
+    rng = np.random.Generator(np.random.PCG64(seed + 311))
+    E, hd, A = config.word_embedding_dim, config.MSA_head_num * config.MSA_head_dim, config.attention_dim
+    sd = {'word_embedding.weight': rng.normal(0, 0.4, size=(config.vocabulary_size, E)).astype(np.float32)}
+    sd['word_embedding.weight'][0] = 0                                   # padding token
+    for k in ('W_K', 'W_Q', 'W_V'):
+        sd['multiheadSelfattention.%s.weight' % k] = _xavier(rng, hd, E)
+    sd['multiheadSelfattention.W_Q.bias'] = rng.normal(0, 0.05, size=hd).astype(np.float32)
+    sd['multiheadSelfattention.W_V.bias'] = rng.normal(0, 0.05, size=hd).astype(np.float32)
+    sd['attention.affine1.weight'] = _xavier(rng, A, hd, 5.0 / 3.0)
+    sd['attention.affine1.bias'] = rng.normal(0, 0.05, size=A).astype(np.float32)
+    sd['attention.affine2.weight'] = _xavier(rng, 1, A)
+    return {k: torch.from_numpy(v) for k, v in sd.items()}
+
+
+def make_titles(config, n_titles, seed=0):
+    """Token ids [n_titles, T] int64 (zero padded tail, a few empty titles) and their mask [n_titles, T] float (1 = token)."""
+    rng = np.random.Generator(np.random.PCG64(seed + 911))
+    T = config.max_title_length
+    length = rng.integers(1, T + 1, size=n_titles)
+    length[rng.random(n_titles) < 0.05] = 0                              # all-padding title (news 0 in the reference corpus)
+    tok = rng.integers(1, config.vocabulary_size, size=(n_titles, T)).astype(np.int64)
+    valid = np.arange(T)[None, :] < length[:, None]
+    tok[~valid] = 0
+    return torch.from_numpy(tok), torch.from_numpy(valid.astype(np.float32))
+
+
 @dataclass
 class Corpus:
     """Device-agnostic synthetic corpus: the arrays reference util.compute_scores reads from MIND_Corpus."""

@@ -31,7 +31,7 @@ extern "C" {
 #define DIGAT_E_CUDA        -2   /* a CUDA runtime/driver call or a launch failed */
 #define DIGAT_E_UNSUPPORTED -3   /* device is not sm_100 */
 
-#define DIGAT_ABI_VERSION 3
+#define DIGAT_ABI_VERSION 4
 
 int         digat_abi_version(void);
 const char* digat_last_error(void);
@@ -291,6 +291,23 @@ int digat_rank_impressions(const float* scores, const int64_t* offsets, int32_t*
  * valid [n_imp] u8: 1 = scored, 0 = empty impression (skipped, evaluate.py:70), 2 = one class only (sklearn raises). */
 int digat_impression_metrics(const int32_t* ranks, const uint8_t* labels, const int64_t* offsets, double* out,
                              uint8_t* valid, int64_t n_imp, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * News (title) encoder, MSA variant (reference newsEncoders.py:58-82, layers.py:50-115),
+ * inference.  Word embeddings are gathered with digat_gather_rows_i32 and the Q|K|V and affine1 projections are
+ * digat_linear_* calls; these two kernels do the rest.
+ * --------------------------------------------------------------------------------------------------------- */
+/* Multi-head self-attention over the T <= 32 tokens of each title + relu (layers.py:78-97, newsEncoders.py:78):
+ *   QKV [n_titles*T, ld]: columns [0,hd) = Q (bias included), [hd,2hd) = K, [2hd,3hd) = V (bias included), hd = heads*dk,
+ *   head h owns columns h*dk .. h*dk+dk of each block;  H [n_titles*T, ldh] = relu(softmax(Q_h K_h^T / sqrt(dk)) V_h).
+ * No padding mask (the reference applies none here).  dk <= 32. */
+int digat_msa_attention_fwd(const float* QKV, int ld, float* H, int ldh, int64_t n_titles, int T, int heads, int dk,
+                            void* stream);
+/* Additive attention pooling over the tokens of each title (layers.py:107-115):
+ *   a_t = tanh(att_pre[t]) . w2  (att_pre [n_titles*T, lda] = H affine1^T + b1, A columns; w2 [A] = affine2.weight),
+ *   alpha = softmax_t(mask[t] ? a_t : -1e9),  out[title] = sum_t alpha_t H[title, t, :]  (out [n_titles, ldo], D columns). */
+int digat_additive_pool_fwd(const float* att_pre, int lda, const float* w2, const float* H, int ldh, const uint8_t* mask,
+                            float* out, int ldo, int64_t n_titles, int T, int A, int D, void* stream);
 
 #ifdef __cplusplus
 }

@@ -12,6 +12,7 @@ Each function cites the reference lines it follows (paths relative to /root/refe
 * ``inference``          -- graphEncoders.py:189-198  + model.py:87-90 (logits)
 * ``forward``            -- graphEncoders.py:177-187  + model.py:73-77 (eval / p=0 semantics, dropout omitted)
 * ``gat_layer`` / ``ablation_inference`` / ``ablation_forward`` -- the five ablation encoders, graphEncoders.py:201-842
+* ``msa_news_encoder``   -- newsEncoders.py:58-82 + layers.py:50-115 (MSA title encoder, eval mode)
 * ``gather_*``           -- util.py:34-36, 65-67
 * ``rank_lists`` / ``metrics`` -- util.py:70-80 + evaluate.py:32-89
 * ``user_graph_loops``   -- MIND_corpus.py:143-176 (literal loops; integer oracle)
@@ -183,6 +184,27 @@ def ablation_forward(kind, P, news_graph_embeddings, news_graph, news_graph_mask
     """``forward`` (eval / p=0): the initial news context is computed instead of read from the cache."""
     c_n0 = None if kind == 'wo_SA' else news_graph_context(P, news_graph_embeddings, news_graph_mask)
     return ablation_inference(kind, P, news_graph_embeddings, news_graph, news_graph_mask, *user_args, c_n0)
+
+
+# ----------------------------------------------------------------------------- MSA news encoder (newsEncoders.py:58-82)
+def msa_news_encoder(P, title_text, title_mask, heads, dk):
+    """title_text [B, news_num, T] int64, title_mask [B, news_num, T] -> [B, news_num, heads*dk]; eval mode (no dropout).
+    Multi-head self-attention without padding mask (layers.py:78-97), relu, additive attention pooling (layers.py:107-115)."""
+    B, news_num, T = title_text.shape
+    n = B * news_num
+    mask = title_mask.view(n, T)
+    w = F.embedding(title_text, P['word_embedding.weight']).view(n, T, -1)
+    pre = 'multiheadSelfattention.'
+    Q = _lin(w, P[pre + 'W_Q.weight'], P[pre + 'W_Q.bias']).view(n, T, heads, dk).transpose(1, 2).contiguous().view(n * heads, T, dk)
+    K = _lin(w, P[pre + 'W_K.weight']).view(n, T, heads, dk).transpose(1, 2).contiguous().view(n * heads, T, dk)
+    V = _lin(w, P[pre + 'W_V.weight'], P[pre + 'W_V.bias']).view(n, T, heads, dk).transpose(1, 2).contiguous().view(n * heads, T, dk)
+    A = torch.bmm(Q, K.transpose(1, 2).contiguous()) / math.sqrt(float(dk))
+    out = torch.bmm(F.softmax(A, dim=2), V).view(n, heads, T, dk).transpose(1, 2).contiguous().view(n, T, heads * dk)
+    h = F.relu(out)
+    att = torch.tanh(_lin(h, P['attention.affine1.weight'], P['attention.affine1.bias']))
+    a = _lin(att, P['attention.affine2.weight']).squeeze(dim=2)
+    alpha = F.softmax(a.masked_fill(mask == 0, NEG_FILL), dim=1).unsqueeze(dim=1)
+    return torch.bmm(alpha, h).squeeze(dim=1).view(B, news_num, heads * dk)
 
 
 # ----------------------------------------------------------------------------- gathers (util.py:34-36, 65-67)

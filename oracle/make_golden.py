@@ -153,6 +153,43 @@ def make_ablation_cases(ge):
             print(kind, case, {k: v.shape for k, v in payload.items() if k != 'meta'})
 
 
+def msa_inputs():
+    cfg = synth.make_text_config()
+    sd = synth.make_msa_state_dict(cfg, seed=5)
+    tok, mask = synth.make_titles(cfg, 24, seed=2)
+    return cfg, sd, tok.view(4, 6, -1), mask.view(4, 6, -1)
+
+
+def make_msa_case():
+    """newsEncoders.MSA of the unmodified reference (eval mode).  Its constructor reads the preprocessed word-embedding pickle
+    from the working directory (newsEncoders.py:14-15): a temporary one is provided, then the seeded weights are loaded."""
+    import importlib
+    import pickle
+    import tempfile
+    cfg, sd, tok, mask = msa_inputs()
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        try:
+            with open('word_embedding-%s-%s-%s-%s.pkl' % (cfg.word_threshold, cfg.word_embedding_dim, cfg.max_title_length,
+                                                           cfg.dataset), 'wb') as f:
+                pickle.dump(torch.zeros(cfg.vocabulary_size, cfg.word_embedding_dim), f)
+            ne = importlib.import_module('newsEncoders')
+            payload = {'meta': np.frombuffer(json.dumps({('w:' + k): sha(v.numpy()) for k, v in sd.items()} |
+                                                        {'x:title_text': sha(tok.numpy()), 'x:title_mask': sha(mask.numpy())}).encode(),
+                                             dtype=np.uint8)}
+            for tag, dt in (('ref32_', torch.float32), ('ref64_', torch.float64)):
+                m = ne.MSA(cfg)
+                m.load_state_dict(sd)
+                m = m.to(dt).eval()
+                with torch.no_grad():
+                    payload[tag + 'news'] = m(tok, mask.to(dt)).numpy()
+        finally:
+            os.chdir(cwd)
+    np.savez_compressed(os.path.join(GOLDEN, 'news_encoder_msa.npz'), **payload)
+    print('news_encoder_msa', payload['ref32_news'].shape)
+
+
 def make_sag_case(sag):
     """construct_SAG.generate_news_graph on a seeded similarity table (integer golden vectors)."""
     rng = np.random.Generator(np.random.PCG64(7))
@@ -212,11 +249,13 @@ if __name__ == '__main__':
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(1)   # fixed reduction partitioning inside MKL/ATen -> reproducible fp32 vectors
     ge, layers, ev, sag = load_reference()
-    which = sys.argv[1:] or ['encoder', 'ablation', 'sag', 'metrics']
+    which = sys.argv[1:] or ['encoder', 'ablation', 'msa', 'sag', 'metrics']
     if 'encoder' in which:
         make_encoder_cases(ge)
     if 'ablation' in which:
         make_ablation_cases(ge)
+    if 'msa' in which:
+        make_msa_case()
     if 'sag' in which:
         make_sag_case(sag)
     if 'metrics' in which:

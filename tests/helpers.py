@@ -118,3 +118,11 @@ def ablation_inputs(kind, case):
 def load_ablation_golden(kind, case):
     z = np.load(os.path.join(GOLDEN, 'ablation_%s_%s.npz' % (kind, case)))
     return z, json.loads(bytes(z['meta']).decode())
+
+
+def msa_inputs():
+    """Same construction as oracle/make_golden.py::msa_inputs."""
+    cfg = synth.make_text_config()
+    sd = synth.make_msa_state_dict(cfg, seed=5)
+    tok, mask = synth.make_titles(cfg, 24, seed=2)
+    return cfg, sd, tok.view(4, 6, -1), mask.view(4, 6, -1)

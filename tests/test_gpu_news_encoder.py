@@ -1,0 +1,88 @@
+"""GPU parity of the MSA news (title) encoder (reference newsEncoders.py:58-82) against the
+golden vectors of the unmodified reference class, small (exact-fp32 GEMMs) and replicated (tcgen05 GEMMs, K = 300 with a
+partial last k-block), plus ragged cases against the CPU oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import digat_oracle as O
+from tests.helpers import GOLDEN, msa_inputs, rel_err, sha
+
+pytestmark = pytest.mark.gpu
+
+
+def _encoder(cfg, sd):
+    from digat_b200.newsEncoders import MSA
+    m = MSA(cfg)
+    m.load_state_dict(sd)
+    return m.cuda().eval()
+
+
+@pytest.mark.parametrize('rep', [1, 40])
+def test_msa_matches_reference_golden(rep):
+    cfg, sd, tok, mask = msa_inputs()
+    z = np.load(os.path.join(GOLDEN, 'news_encoder_msa.npz'))
+    meta = json.loads(bytes(z['meta']).decode())
+    assert meta['x:title_text'] == sha(tok.numpy()) and all(meta['w:' + k] == sha(v.numpy()) for k, v in sd.items())
+    m = _encoder(cfg, sd)
+    with torch.no_grad():
+        out = m(tok.cuda().repeat(rep, 1, 1), mask.cuda().repeat(rep, 1, 1))
+    torch.cuda.synchronize()
+    assert out.shape == (4 * rep, 6, 400)
+    got = out.cpu().numpy()
+    for r in (0, rep - 1):
+        e32 = rel_err(got[4 * r:4 * r + 4], z['ref32_news'])
+        assert e32 < 1e-5, 'x%d replica %d: rel err vs fp32 reference %.3e (vs fp64 %.3e)' % (
+            rep, r, e32, rel_err(got[4 * r:4 * r + 4], z['ref64_news']))
+
+
+@pytest.mark.parametrize('T,heads,dk,E,A,n', [(32, 16, 25, 300, 256, 700), (20, 4, 16, 100, 64, 33), (7, 2, 32, 52, 200, 5)])
+def test_msa_matches_oracle_other_shapes(T, heads, dk, E, A, n):
+    from digat_b200 import synth
+    cfg = synth.make_text_config(vocabulary_size=300, max_title_length=T, word_embedding_dim=E, MSA_head_num=heads,
+                                 MSA_head_dim=dk, attention_dim=A)
+    sd = synth.make_msa_state_dict(cfg, seed=T)
+    tok, mask = synth.make_titles(cfg, n, seed=T + 1)
+    m = _encoder(cfg, sd)
+    with torch.no_grad():
+        got = m(tok.cuda().view(1, n, T), mask.cuda().view(1, n, T)).cpu()
+        ref = O.msa_news_encoder(O.cast_params(sd, torch.float64), tok.view(1, n, T), mask.double().view(1, n, T), heads, dk)
+    assert rel_err(got.numpy(), ref.numpy()) < 1e-5
+
+
+def test_msa_feeds_the_graph_encoder_through_model_forward():
+    """reference Model.forward on token tensors (model.py:54-77): news encoder -> DIGAT -> logits, against the oracle."""
+    from digat_b200 import synth
+    from digat_b200.model import Model
+    cfg = synth.make_text_config(graph_depth=2)
+    model = Model(cfg)
+    assert model.news_encoder is not None and model.news_embedding_dim == 400
+    sd_g = synth.make_state_dict(cfg, seed=3)
+    sd_n = synth.make_msa_state_dict(cfg, seed=4)
+    model.graph_encoder.load_state_dict(sd_g)
+    model.news_encoder.load_state_dict(sd_n)
+    model = model.cuda().eval()
+    corpus = synth.make_corpus(cfg, n_news=60, n_behaviors=6, mean_candidates=3.0, seed=2)
+    bs, news_num, n_n, H, T = 3, 2, cfg.news_graph_size, 50, cfg.max_title_length
+    tok, mask = synth.make_titles(cfg, 60, seed=9)
+    beh = np.arange(bs)
+    cand = np.array([[5, 9], [11, 3], [7, 20]])
+    u_tok, u_mask = tok[corpus.history[beh]], mask[corpus.history[beh]]
+    n_tok, n_mask = tok[corpus.news_node_ID[cand]], mask[corpus.news_node_ID[cand]]
+    t = torch.from_numpy
+    ug, cm, ci = t(corpus.user_graph[beh]), t(corpus.user_category_mask[beh]), t(corpus.user_category_indices[beh])
+    ng, nm = t(corpus.news_graph[cand]), t(corpus.news_graph_mask[cand])
+    with torch.no_grad():
+        got = model(u_tok.cuda(), u_mask.cuda(), ug.cuda(), cm.cuda(), ci.cuda(), n_tok.cuda(), n_mask.cuda(), ng.cuda(),
+                    nm.cuda()).cpu()
+        Pn, Pg = O.cast_params(sd_n), O.cast_params(sd_g)
+        c_emb = O.msa_news_encoder(Pn, n_tok.view(bs * news_num, n_n, T), n_mask.view(bs * news_num, n_n, T), 16, 25)
+        u_emb = O.msa_news_encoder(Pn, u_tok, u_mask, 16, 25)
+        ex = lambda x: x.unsqueeze(1).expand(-1, news_num, *([-1] * (x.dim() - 1))).reshape(bs * news_num, *x.shape[1:])  # noqa: E731
+        cn, cu = O.forward(Pg, c_emb, ng.view(bs * news_num, n_n, n_n), nm.view(bs * news_num, n_n), ex(u_emb), ex(ug), ex(cm), ex(ci))
+        ref = O.logits(cn, cu).view(bs, news_num)
+    assert got.shape == (bs, news_num)
+    assert rel_err(got.numpy(), ref.numpy()) < 1e-5

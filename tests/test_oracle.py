@@ -127,3 +127,20 @@ def test_ablation_oracle_matches_reference_golden(kind, case):
         for k, v in got.items():
             assert np.array_equal(v.numpy(), z[tag + k]), '%s%s differs from the reference (rel %.3e)' % (
                 tag, k, rel_err(v.numpy(), z[tag + k]))
+
+
+def test_msa_news_encoder_oracle_matches_reference_golden():
+    """The MSA title encoder restatement (reference newsEncoders.py:58-82, layers.py:50-115) against the unmodified class."""
+    import json
+    from tests.helpers import msa_inputs, sha
+    torch.set_num_threads(1)
+    cfg, sd, tok, mask = msa_inputs()
+    z = np.load(os.path.join(GOLDEN, 'news_encoder_msa.npz'))
+    meta = json.loads(bytes(z['meta']).decode())
+    for k, v in sd.items():
+        assert meta['w:' + k] == sha(v.numpy())
+    assert meta['x:title_text'] == sha(tok.numpy()) and meta['x:title_mask'] == sha(mask.numpy())
+    for tag, dt in (('ref32_', torch.float32), ('ref64_', torch.float64)):
+        with torch.no_grad():
+            got = O.msa_news_encoder(O.cast_params(sd, dt), tok, mask.to(dt), cfg.MSA_head_num, cfg.MSA_head_dim)
+        assert np.array_equal(got.numpy(), z[tag + 'news']), rel_err(got.numpy(), z[tag + 'news'])
