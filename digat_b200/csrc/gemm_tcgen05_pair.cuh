@@ -40,11 +40,11 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
     for (uint32_t spin = 0; ; ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+            : "=r"(done) : "r"(addr), "r"(parity), "r"(kMbarSuspendHintNs) : "memory");
         if (done) return;
-        if (spin > (1u << 24)) {
+        if (spin > (1u << 20)) {
             printf("digat: cluster mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
             __trap();
         }

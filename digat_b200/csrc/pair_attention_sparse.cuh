@@ -52,6 +52,7 @@ constexpr int kSparseUnroll = DIGAT_SPARSE_UNROLL;      // feature quads of one 
 struct SparseGeom {
     int nch1, nch3;
     int G;                 // graphs per CTA: small graphs are batched into one block-diagonal graph of G*n nodes
+    int stagger_lo, stagger_hi;   // CTAs [lo, hi) (the second resident of every SM in the first wave) start late (experiment)
     int tile_floats;       // floats of one [G*n][32] tile rounded up to 1024 bytes (SWIZZLE_128B atoms stay aligned)
     int unit_floats;       // floats of one ring buffer = 2 tiles (>= the [G*n][64] h tile)
     size_t smem;
@@ -86,6 +87,8 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
     uint8_t* uniform_row = adj_s + ((NB * n + 15) & ~15);          // [NB] 1 = row without edges (uniform softmax)
     uint8_t* dead_row = uniform_row + NB;                          // [NB] 1 = pruned node (row_active == 0): no edges, Y = X
     int* pos_s = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(dead_row + NB) + 3) & ~(uintptr_t)3);   // [NB] compact row of each node
+    int* n_act_s = pos_s + NB;                                     // number of rows this CTA evaluates (not pruned)
+    uint8_t* act_list = reinterpret_cast<uint8_t*>(n_act_s + 1);   // [NB] their node indices, ascending: phase 3 walks THIS list
 
     if (tid == 0) {
         for (int i = 0; i < kSparseBufs; ++i) {
@@ -94,6 +97,12 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+#ifdef DIGAT_SPARSE_STAGGER
+    // The CTAs of a wave run in lockstep (same graph sizes): everyone streams P at the same time (DRAM-bound) and everyone
+    // builds its CSR / does its softmax at the same time (DRAM idle).  Delaying the second CTA of every SM once, in the first
+    // wave, by about half a graph puts the two residents of an SM out of phase for the rest of the launch.
+    if (blockIdx.x >= gridDim.y * 0 + (unsigned)g.stagger_lo && blockIdx.x < (unsigned)g.stagger_hi) __nanosleep(DIGAT_SPARSE_STAGGER);
+#endif
     __syncthreads();
     const int n_loads = g.nch1 + g.nch3;
 
@@ -175,6 +184,15 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
             run_e += __shfl_sync(0xffffffffu, ve, 31);
         }
         if (lane == 0) rowptr[0] = 0;
+        int run_a = 0;                                             // compact list of the evaluated rows (phase 3 assigns half
+        for (int base = 0; base < N; base += 32) {                 // warps to list entries, so pruned rows cost no pass)
+            const int i = base + lane;
+            const bool alive = i < N && dead_row[i] == 0;
+            const unsigned m = __ballot_sync(0xffffffffu, alive);
+            if (alive) act_list[run_a + __popc(m & ((1u << lane) - 1u))] = (uint8_t)i;
+            run_a += __popc(m);
+        }
+        if (lane == 0) *n_act_s = run_a;
     }
     consumer_sync();
     // CSR pass B: column / row index of every edge, zeroed scores
@@ -215,36 +233,79 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
         const uint32_t koff = uoff + (uint32_t)g.tile_floats * 4u;
         const uint32_t aoff = a_off + (uint32_t)c0 * 4u, k3off = k3_off + (uint32_t)c0 * 4u;
         mbar_wait(&full[buf], (uint32_t)(l / kSparseBufs) & 1u);
-        for (int e = tid; e < E; e += kSparseConsumers) {          // one edge per thread: all lanes busy for E >= 320
+        // One edge per thread; a thread that owns a second edge (E > 320) evaluates BOTH in the same pass over the feature
+        // quads -- their loads are independent, so the second edge rides in the latency shadow of the first (the loop is
+        // latency-bound: a second sequential pass used to double the time of every unit), and the a / k3 quads are shared.
+        for (int eb = warp * 32; eb < E; eb += 2 * kSparseConsumers) {        // warp-uniform trip count (__any_sync below)
             // rows are 128 bytes (all rows would start in bank 0): the tiles are loaded with SWIZZLE_128B, i.e. the 16-byte
             // chunk q of the 128-byte line L sits at chunk q ^ (L & 7) -- threads on different rows hit different banks
-            const uint32_t mt = meta[e];
-            const uint32_t uo = uoff + (mt & 255u) * (uint32_t)(kSparseDc1 * 4);
-            const uint32_t ko = koff + (mt >> 8) * (uint32_t)(kSparseDc1 * 4);
+            const int e = eb + lane, e2 = e + kSparseConsumers;
+            const bool one = e < E, two = e2 < E;                   // (a lane past E re-evaluates edge 0 and stores nothing)
+            const uint32_t mt = meta[one ? e : 0], mt2 = meta[two ? e2 : 0];
+            const uint32_t uo = uoff + (mt & 255u) * (uint32_t)(kSparseDc1 * 4), ko = koff + (mt >> 8) * (uint32_t)(kSparseDc1 * 4);
+            const uint32_t uo2 = uoff + (mt2 & 255u) * (uint32_t)(kSparseDc1 * 4), ko2 = koff + (mt2 >> 8) * (uint32_t)(kSparseDc1 * 4);
             const uint32_t ukey = ((uo >> 7) & 7u) << 4, kkey = ((ko >> 7) & 7u) << 4;
-            uint64_t acc0 = 0ull, acc1 = 0ull;
+            const uint32_t ukey2 = ((uo2 >> 7) & 7u) << 4, kkey2 = ((ko2 >> 7) & 7u) << 4;
+            uint64_t acc0 = 0ull, acc1 = 0ull, bcc0 = 0ull, bcc1 = 0ull;
+            if (!__any_sync(0xffffffffu, two)) {                    // no lane of this warp owns a second edge: plain loop
 #pragma unroll kSparseUnroll
-            for (int q = 0; q < wq; ++q) {
-                const uint32_t qo = (uint32_t)q * 16u;
-                const float4 av = *reinterpret_cast<const float4*>(smem_raw + aoff + qo);
-                const float4 k2 = *reinterpret_cast<const float4*>(smem_raw + ko + (qo ^ kkey));
-                const float4 u = *reinterpret_cast<const float4*>(smem_raw + uo + (qo ^ ukey));
-                uint64_t u01 = pack2(u.x, u.y), u23 = pack2(u.z, u.w);
-                if (kIndexed) {                                     // the staged tile is K1: U = fl(k3 + K1)
-                    const float4 kk = *reinterpret_cast<const float4*>(smem_raw + k3off + qo);
-                    u01 = add2(pack2(kk.x, kk.y), u01);
-                    u23 = add2(pack2(kk.z, kk.w), u23);
+                for (int q = 0; q < wq; ++q) {
+                    const uint32_t qo = (uint32_t)q * 16u;
+                    const float4 av = *reinterpret_cast<const float4*>(smem_raw + aoff + qo);
+                    const float4 k2 = *reinterpret_cast<const float4*>(smem_raw + ko + (qo ^ kkey));
+                    const float4 u = *reinterpret_cast<const float4*>(smem_raw + uo + (qo ^ ukey));
+                    uint64_t u01 = pack2(u.x, u.y), u23 = pack2(u.z, u.w);
+                    if (kIndexed) {
+                        const float4 kk = *reinterpret_cast<const float4*>(smem_raw + k3off + qo);
+                        u01 = add2(pack2(kk.x, kk.y), u01);
+                        u23 = add2(pack2(kk.z, kk.w), u23);
+                    }
+                    float s0, s1, s2, s3;
+                    unpack2(add2(u01, pack2(k2.x, k2.y)), s0, s1);
+                    unpack2(add2(u23, pack2(k2.z, k2.w)), s2, s3);
+                    acc0 = fma2(pack2(av.x, av.y), pack2(fmaxf(s0, 0.f), fmaxf(s1, 0.f)), acc0);
+                    acc1 = fma2(pack2(av.z, av.w), pack2(fmaxf(s2, 0.f), fmaxf(s3, 0.f)), acc1);
                 }
-                float s0, s1, s2, s3;
-                unpack2(add2(u01, pack2(k2.x, k2.y)), s0, s1);
-                unpack2(add2(u23, pack2(k2.z, k2.w)), s2, s3);
-                acc0 = fma2(pack2(av.x, av.y), pack2(fmaxf(s0, 0.f), fmaxf(s1, 0.f)), acc0);
-                acc1 = fma2(pack2(av.z, av.w), pack2(fmaxf(s2, 0.f), fmaxf(s3, 0.f)), acc1);
+            } else {
+#pragma unroll kSparseUnroll
+                for (int q = 0; q < wq; ++q) {
+                    const uint32_t qo = (uint32_t)q * 16u;
+                    const float4 av = *reinterpret_cast<const float4*>(smem_raw + aoff + qo);
+                    const float4 k2 = *reinterpret_cast<const float4*>(smem_raw + ko + (qo ^ kkey));
+                    const float4 u = *reinterpret_cast<const float4*>(smem_raw + uo + (qo ^ ukey));
+                    const float4 k2b = *reinterpret_cast<const float4*>(smem_raw + ko2 + (qo ^ kkey2));
+                    const float4 ub = *reinterpret_cast<const float4*>(smem_raw + uo2 + (qo ^ ukey2));
+                    uint64_t u01 = pack2(u.x, u.y), u23 = pack2(u.z, u.w);
+                    uint64_t v01 = pack2(ub.x, ub.y), v23 = pack2(ub.z, ub.w);
+                    if (kIndexed) {                                     // the staged tile is K1: U = fl(k3 + K1)
+                        const float4 kk = *reinterpret_cast<const float4*>(smem_raw + k3off + qo);
+                        const uint64_t k01 = pack2(kk.x, kk.y), k23 = pack2(kk.z, kk.w);
+                        u01 = add2(k01, u01);
+                        u23 = add2(k23, u23);
+                        v01 = add2(k01, v01);
+                        v23 = add2(k23, v23);
+                    }
+                    const uint64_t a01 = pack2(av.x, av.y), a23 = pack2(av.z, av.w);
+                    float s0, s1, s2, s3;
+                    unpack2(add2(u01, pack2(k2.x, k2.y)), s0, s1);
+                    unpack2(add2(u23, pack2(k2.z, k2.w)), s2, s3);
+                    acc0 = fma2(a01, pack2(fmaxf(s0, 0.f), fmaxf(s1, 0.f)), acc0);
+                    acc1 = fma2(a23, pack2(fmaxf(s2, 0.f), fmaxf(s3, 0.f)), acc1);
+                    unpack2(add2(v01, pack2(k2b.x, k2b.y)), s0, s1);
+                    unpack2(add2(v23, pack2(k2b.z, k2b.w)), s2, s3);
+                    bcc0 = fma2(a01, pack2(fmaxf(s0, 0.f), fmaxf(s1, 0.f)), bcc0);
+                    bcc1 = fma2(a23, pack2(fmaxf(s2, 0.f), fmaxf(s3, 0.f)), bcc1);
+                }
             }
             float a0, a1, b0, b1;
             unpack2(acc0, a0, a1);
             unpack2(acc1, b0, b1);
-            score[e] += (a0 + a1) + (b0 + b1);                     // each edge is owned by exactly one thread
+            if (one) score[e] += (a0 + a1) + (b0 + b1);            // each edge is owned by exactly one thread
+            if (two) {
+                unpack2(bcc0, a0, a1);
+                unpack2(bcc1, b0, b1);
+                score[e2] += (a0 + a1) + (b0 + b1);
+            }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[buf]);                   // this warp is done with the buffer
@@ -310,10 +371,15 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
     // whole unit (up to kXSlots passes of this warp) are requested one unit AHEAD and sit in registers meanwhile.
     constexpr int kXSlots = 4;
     constexpr int kRowPairStep = kSparseConsumers / 32;
+    const int n_act = *n_act_s;
+    auto row_of = [&](int slot) {                                  // node evaluated by this half warp in pass `slot`, or -1
+        const int k = 2 * (warp + slot * kRowPairStep) + sub;
+        return k < n_act ? (int)act_list[k] : -1;
+    };
     auto load_x = [&](int unit, int slot) {
         const int c0_ = unit * kSparseDc3;
-        const int i_ = 2 * (warp + slot * kRowPairStep) + sub;
-        return (unit < g.nch3 && i_ < N && dead_row[min(i_, N - 1)] == 0 && c0_ + 4 * half_lane < D)
+        const int i_ = row_of(slot);
+        return (unit < g.nch3 && i_ >= 0 && c0_ + 4 * half_lane < D)
                    ? ldg_stream(reinterpret_cast<const float4*>(p.X + ((size_t)src0 * n + i_) * D + c0_ + 4 * half_lane))
                    : make_float4(0.f, 0.f, 0.f, 0.f);
     };
@@ -337,9 +403,9 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
 #pragma unroll
         for (int sl = 0; sl < kMaxPasses; ++sl) {                   // slots >= kXSlots load their residual directly
             const int rp = warp + sl * kRowPairStep;
-            if (2 * rp >= N) break;
-            const int i = 2 * rp + sub;
-            if (i < N && half_lane < wq && dead_row[i] == 0) {          // pruned rows are neither read nor written
+            if (2 * rp >= n_act) break;
+            const int i = row_of(sl);
+            if (i >= 0 && half_lane < wq) {                             // pruned rows are not in the list: neither read nor written
                 const int q = half_lane;
                 const size_t yoff = ((size_t)b * n + i) * D + c0 + 4 * q;
                 float4 x;
@@ -400,7 +466,7 @@ inline void sparse_geometry(int n, int D, int G, SparseGeom* g) {
     g->tile_floats = ((NB * kSparseDc1 * 4 + 1023) / 1024) * 1024 / 4;
     g->unit_floats = 2 * g->tile_floats;
     g->smem = (size_t)kSparseBufs * g->unit_floats * 4 + (size_t)2 * kSparseBufs * 8 + (size_t)2 * D * 4 +
-              (size_t)NB * n * 4 + (size_t)(NB + 2) * 4 + (size_t)2 * NB * n + (size_t)((NB * n + 15) & ~15) + (size_t)2 * NB + (size_t)4 * NB + 64;
+              (size_t)NB * n * 4 + (size_t)(NB + 2) * 4 + (size_t)2 * NB * n + (size_t)((NB * n + 15) & ~15) + (size_t)2 * NB + (size_t)4 * NB + (size_t)NB + 8 + 64;
 }
 
 size_t graph_layer_fwd_sparse_smem(int n, int D) {
@@ -434,6 +500,8 @@ int launch_graph_layer_fwd_sparse(const PairAttnArgs& args, int n_src, cudaStrea
                   : sparse_graphs_per_cta(args.n, args.D, args.B, di->sm_count, (size_t)di->max_smem_optin);
     SparseGeom g;
     sparse_geometry(args.n, args.D, G, &g);
+    g.stagger_lo = di->sm_count;
+    g.stagger_hi = 2 * di->sm_count;
     DIGAT_REQUIRE(g.smem <= (size_t)di->max_smem_optin, "digat_graph_layer_fwd(sparse): needs %zu B shared memory", g.smem);
     CUtensorMap map1, map3;
     int rc;

@@ -21,18 +21,21 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+constexpr uint32_t kMbarSuspendHintNs = 20000u;
 // Bounded spin: a barrier that never completes traps (CUDA error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
     for (uint32_t spin = 0; ; ++spin) {
+        // suspend-time hint: the warp sleeps in hardware until the phase completes (or the hint expires) instead of
+        // re-issuing the poll -- the spin loops of waiting warps were 15 % of all issued instructions of the layer kernel
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+            : "=r"(done) : "r"(addr), "r"(parity), "r"(kMbarSuspendHintNs) : "memory");
         if (done) return;
-        if (spin > (1u << 24)) {
+        if (spin > (1u << 20)) {
             printf("digat: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
             __trap();
         }

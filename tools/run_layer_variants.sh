@@ -1,2 +1,2 @@
-echo "== baseline"; timeout 120 python tools/layer_bench.py 2>&1 | grep -E "rows|edges"
-for f in build_variants/*.so; do echo "== $f"; timeout 120 python tools/layer_bench.py $f 2>&1 | grep -E "all rows|active rows "; done
+echo "== baseline"; timeout 120 python tools/layer_bench.py 2>&1 | grep -E " rows "
+for f in build_variants/*.so; do echo "== $f"; timeout 120 python tools/layer_bench.py $f 2>&1 | grep -E " rows "; done
