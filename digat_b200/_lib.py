@@ -26,7 +26,8 @@ SIGNATURES = {
     'digat_debug_set_layer_mode': [c_int],
     'digat_graph_layer_fwd': [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                               c_void_p, ctypes.c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
-                              c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+                              c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    'digat_build_graph_csr': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p],
     'digat_gat_layer_fwd': [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     'digat_graph_layer_supports_row_active': [c_int, c_int, c_int],
     'digat_compact_lists': [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],

@@ -185,6 +185,73 @@ inline int launch_user_active_rows(const uint8_t* adj, const int32_t* adj_index,
     return check_launch("digat_user_active_rows");
 }
 
+// CSR of a graph's adjacency, restricted to the evaluated rows (row_active), in the form the edge-driven layer kernel uses:
+// rowptr[i+1] = end of row i's edge range (bit 15: the row has no edge at all -> uniform softmax over every node, the
+// reference's all -1e9 row), meta[e] = neighbour | row << 8.  Built ONCE per batch and graph; the layer kernel used to rebuild
+// it from the adjacency bytes in every layer and for every pair sharing the graph (12 % of its instructions, ~15k of ~80k
+// cycles per graph).  One CTA of four warps per graph, a warp per row (ballot + popc), one warp scan for the row pointers.
+__global__ void __launch_bounds__(128)
+graph_csr_kernel(const uint8_t* __restrict__ adj, const int32_t* __restrict__ adj_index, const uint8_t* __restrict__ row_active,
+                 uint16_t* __restrict__ rowptr_out, uint16_t* __restrict__ meta_out, int n) {
+    __shared__ int rp[130];
+    __shared__ uint8_t uni[128];
+    const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint8_t* a = adj + (adj_index != nullptr ? (size_t)adj_index[g] : (size_t)g) * n * n;
+    const uint8_t* act = row_active != nullptr ? row_active + (size_t)g * n : nullptr;
+    for (int i = warp; i < n; i += 4) {
+        const bool dead = act != nullptr && act[i] == 0;
+        int deg = 0;
+        if (!dead)
+            for (int j = lane; j < ((n + 31) & ~31); j += 32)
+                deg += __popc(__ballot_sync(0xffffffffu, j < n && a[i * n + j] != 0));
+        if (lane == 0) {
+            uni[i] = deg == 0 && !dead;
+            rp[i + 1] = dead ? 0 : (deg == 0 ? n : deg);
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        int run = 0;
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + lane;
+            int v = i < n ? rp[i + 1] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= o) v += t;
+            }
+            if (i < n) rp[i + 1] = run + v;
+            run += __shfl_sync(0xffffffffu, v, 31);
+        }
+        if (lane == 0) rp[0] = 0;
+    }
+    __syncthreads();
+    uint16_t* rpo = rowptr_out + (size_t)g * (n + 1);
+    uint16_t* mo = meta_out + (size_t)g * n * n;
+    for (int i = tid; i <= n; i += 128) rpo[i] = (uint16_t)(rp[i] | ((i > 0 && uni[i - 1]) ? 0x8000 : 0));
+    for (int i = warp; i < n; i += 4) {
+        if (rp[i + 1] == rp[i]) continue;
+        const int e0 = rp[i];
+        const bool u = uni[i] != 0;
+        int filled = 0;
+        for (int j = lane; j < ((n + 31) & ~31); j += 32) {
+            const bool on = j < n && (u || a[i * n + j] != 0);
+            const unsigned m = __ballot_sync(0xffffffffu, on);
+            if (on) mo[e0 + filled + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(j | (i << 8));
+            filled += __popc(m);
+        }
+    }
+}
+
+inline int launch_build_graph_csr(const uint8_t* adj, const int32_t* adj_index, const uint8_t* row_active, uint16_t* rowptr,
+                                  uint16_t* meta, int64_t G, int n, cudaStream_t st) {
+    if (G <= 0) return DIGAT_OK;
+    DIGAT_REQUIRE(adj && rowptr && meta, "digat_build_graph_csr: null pointer");
+    DIGAT_REQUIRE(n >= 1 && n <= 128 && G < (1LL << 31), "digat_build_graph_csr: n=%d outside [1,128]", n);
+    graph_csr_kernel<<<(unsigned)G, 128, 0, st>>>(adj, adj_index, row_active, rowptr, meta, n);
+    return check_launch("digat_build_graph_csr");
+}
+
 // Stream compaction of up to four flag lists laid out back to back in `flags` (their inclusive prefix sums in `csum`):
 // for list k covering flat positions [lo[k], lo[k] + size[k]) with base[k] set flags before it,
 //   pos_k[r] = csum[lo + r] - 1 - base        (rank of position r among the set flags of ITS list; valid where set)

@@ -117,10 +117,16 @@ int digat_graph_layer_fwd(const float* P, int ldp, const float* a, const uint8_t
                           int B, int n, int D, const uint8_t* drop_keep, float drop_scale, float* score_out,
                           float* alpha_out, uint8_t* relu_mask_out, const int32_t* px_index, int n_src,
                           const int32_t* adj_index, const float* k3, int ldk3, const uint8_t* row_active,
-                          float* Yc, const int32_t* row_pos, void* stream) {
+                          float* Yc, const int32_t* row_pos, const uint16_t* csr_rowptr, const uint16_t* csr_meta,
+                          const int32_t* csr_index, void* stream) {
     return launch_graph_layer_fwd(P, ldp, a, adj, X, Y, B, n, D, drop_keep, drop_scale, score_out, alpha_out,
                                   relu_mask_out, px_index, n_src, adj_index, k3, ldk3, row_active, Yc, row_pos,
-                                  as_stream(stream));
+                                  csr_rowptr, csr_meta, csr_index, as_stream(stream));
+}
+
+int digat_build_graph_csr(const uint8_t* adj, const int32_t* adj_index, const uint8_t* row_active, uint16_t* rowptr,
+                          uint16_t* meta, int64_t G, int n, void* stream) {
+    return launch_build_graph_csr(adj, adj_index, row_active, rowptr, meta, G, n, as_stream(stream));
 }
 
 int digat_gat_layer_fwd(const float* Hm, int ldh, const float* s12, const uint8_t* adj, const float* X, float* Y,

@@ -67,6 +67,11 @@ struct PairAttnArgs {
     // vanilla-GAT scores (ablation encoders, reference graphEncoders.py:498-500 / 515-517; edge-driven kernel only):
     // gat_s [B*n, 2], s_ij = gat_s[j][0] + gat_s[i][1] (= a1 . h_j + a2 . h_i).  P then holds h only (ldp >= D) and `a` is unused.
     const float* gat_s = nullptr;
+    // precomputed CSR (digat_build_graph_csr; edge-driven kernel with one graph per CTA): graph b uses record
+    // csr_index[b] (or b): rowptr [*, n+1] uint16, meta [*, n*n] uint16.  The adjacency bytes are then not read at all.
+    const uint16_t* csr_rowptr = nullptr;
+    const uint16_t* csr_meta = nullptr;
+    const int32_t* csr_index = nullptr;
 };
 
 __device__ __forceinline__ uint64_t pack2(float lo, float hi) {
@@ -408,8 +413,10 @@ inline int launch_graph_layer_fwd(const float* P, int ldp, const float* a, const
                                   int B, int n, int D, const uint8_t* drop_keep, float drop_scale, float* score_out,
                                   float* alpha_out, uint8_t* relu_mask_out, const int32_t* px_index, int n_src,
                                   const int32_t* adj_index, const float* k3, int ldk3, const uint8_t* row_active,
-                                  float* Yc, const int32_t* row_pos, cudaStream_t st) {
+                                  float* Yc, const int32_t* row_pos, const uint16_t* csr_rowptr, const uint16_t* csr_meta,
+                                  const int32_t* csr_index, cudaStream_t st) {
     if (B == 0) return DIGAT_OK;
+    DIGAT_REQUIRE((csr_rowptr == nullptr) == (csr_meta == nullptr), "digat_graph_layer_fwd: csr_rowptr and csr_meta go together");
     DIGAT_REQUIRE((Yc == nullptr) == (row_pos == nullptr) && (Yc == nullptr || (row_active != nullptr && aligned16(Yc))),
                   "digat_graph_layer_fwd: Yc, row_pos and row_active go together");
     DIGAT_REQUIRE(P && a && adj && X && Y, "digat_graph_layer_fwd: null pointer");
@@ -434,6 +441,9 @@ inline int launch_graph_layer_fwd(const float* P, int ldp, const float* a, const
     if ((rc = make_tensor_map_2d(&map3, P, src_graphs * n, 3 * D, ldp, g.R * n, g.dc3, CU_TENSOR_MAP_SWIZZLE_NONE)) != DIGAT_OK) return rc;
     PairAttnArgs args{P, ldp, a, adj, X, Y, B, n, D, drop_keep, drop_scale, score_out, alpha_out, relu_mask_out,
                       px_index, adj_index, k3, ldk3, row_active, Yc, row_pos};
+    args.csr_rowptr = csr_rowptr;
+    args.csr_meta = csr_meta;
+    args.csr_index = csr_index;
     const bool inference = !drop_keep && !score_out && !alpha_out && !relu_mask_out;
     // Inference takes the edge-driven kernel (small graphs are batched several per CTA); the dense kernel stays for
     // training and for graphs whose edge-driven working set does not fit one CTA (n > ~100 at D = 400).

@@ -135,6 +135,40 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
         if (gat_s == nullptr) reinterpret_cast<float4*>(a_s)[i] = reinterpret_cast<const float4*>(p.a)[i];
         if (kIndexed) reinterpret_cast<float4*>(k3_s)[i] = reinterpret_cast<const float4*>(p.k3 + (size_t)b * p.ldk3)[i];
     }
+    const bool have_csr = !kMulti && p.csr_rowptr != nullptr;
+    if (have_csr) {
+        // CSR built once per batch and graph (digat_build_graph_csr): two short loads instead of the ballot passes below
+        const size_t cg = p.csr_index != nullptr ? (size_t)p.csr_index[b] : (size_t)b;
+        const uint16_t* rp = p.csr_rowptr + cg * (n + 1);
+        for (int i = tid; i <= n; i += kSparseConsumers) {
+            const uint32_t raw = rp[i];
+            rowptr[i] = (int)(raw & 0x7fffu);
+            if (i > 0) uniform_row[i - 1] = (uint8_t)(raw >> 15);
+        }
+        if (p.Yc != nullptr)
+            for (int i = tid; i < N; i += kSparseConsumers) pos_s[i] = p.row_pos[(size_t)b * n + i];
+        consumer_sync();
+        const int Ec = rowptr[n];
+        const uint16_t* mg = p.csr_meta + cg * (size_t)n * n;              // (n*n*2 bytes per record: 8-byte aligned for even n)
+        for (int e = tid; e < Ec; e += kSparseConsumers) {
+            const uint32_t mt = mg[e];
+            meta[e] = (uint16_t)mt;
+            score[e] = gat_s == nullptr ? 0.f
+                                        : gat_s[((size_t)b * n + (mt & 255u)) * 2] + gat_s[((size_t)b * n + (mt >> 8)) * 2 + 1];
+        }
+        for (int i = tid; i < N; i += kSparseConsumers) dead_row[i] = rowptr[i + 1] == rowptr[i];
+        if (warp == 0) {
+            int run_a = 0;
+            for (int base = 0; base < N; base += 32) {
+                const int i = base + lane;
+                const bool alive = i < N && rowptr[i + 1] != rowptr[i];
+                const unsigned m = __ballot_sync(0xffffffffu, alive);
+                if (alive) act_list[run_a + __popc(m & ((1u << lane) - 1u))] = (uint8_t)i;
+                run_a += __popc(m);
+            }
+            if (lane == 0) *n_act_s = run_a;
+        }
+    } else {
     {
         // adjacency -> shared memory with independent 16-byte loads (one round trip) when the graph is 16-byte aligned
         // (the graphs of one CTA are consecutive in memory: several graphs per CTA only without adj_index)
@@ -215,6 +249,7 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
             }
             filled += __popc(m);
         }
+    }
     }
     const int E = rowptr[N];
     consumer_sync();

@@ -162,10 +162,26 @@ def linear(A, W, bias=None, relu=False, M=None, K=None, lda=None, out=None, grou
     return out
 
 
+def build_graph_csr(adj, row_active=None, adj_index=None, G=None):
+    """CSR records of G graphs for graph_layer_fwd(csr=...) (digat_build_graph_csr): built once per batch, reused by every
+    layer and by every pair that shares the graph.  adj [*,n,n] bool (read through adj_index [G] int32 when given),
+    row_active [G,n] uint8 or None.  Returns (rowptr [G,n+1] int16, meta [G,n*n] int16)."""
+    n = adj.shape[1]
+    if G is None:
+        G = adj.shape[0] if adj_index is None else adj_index.shape[0]
+    rowptr = torch.empty((G, n + 1), dtype=torch.int16, device=adj.device)
+    meta = torch.empty((G, n * n), dtype=torch.int16, device=adj.device)
+    _lib.call('digat_build_graph_csr', adj.data_ptr(), _ptr(adj_index), _ptr(row_active), rowptr.data_ptr(), meta.data_ptr(),
+              G, n, _stream())
+    return rowptr, meta
+
+
 def graph_layer_fwd(P, a, adj, X, drop_keep=None, drop_scale=1.0, score_out=None, alpha_out=None, relu_mask_out=None,
-                    px_index=None, adj_index=None, k3=None, B=None, row_active=None, compact_out=None, row_pos=None):
+                    px_index=None, adj_index=None, k3=None, B=None, row_active=None, compact_out=None, row_pos=None,
+                    csr=None):
     """P [B*n, 3D] = h | U | K2 with U = k3 + K1 (row-group bias of the projection GEMM).
-    Indexed mode (px_index, k3): P / X are per-behaviour tables shared by B pairs, k3 [B,D] is added in-kernel."""
+    Indexed mode (px_index, k3): P / X are per-behaviour tables shared by B pairs, k3 [B,D] is added in-kernel.
+    csr = (rowptr, meta, index or None) from build_graph_csr: the kernel loads the record instead of rebuilding it."""
     n_src, n, D = X.shape
     if B is None:
         B = n_src
@@ -173,7 +189,9 @@ def graph_layer_fwd(P, a, adj, X, drop_keep=None, drop_scale=1.0, score_out=None
     _lib.call('digat_graph_layer_fwd', P.data_ptr(), P.stride(0), a.data_ptr(), adj.data_ptr(), X.data_ptr(),
               Y.data_ptr(), B, n, D, _ptr(drop_keep), float(drop_scale), _ptr(score_out), _ptr(alpha_out),
               _ptr(relu_mask_out), _ptr(px_index), n_src, _ptr(adj_index), _ptr(k3),
-              0 if k3 is None else k3.stride(0), _ptr(row_active), _ptr(compact_out), _ptr(row_pos), _stream())
+              0 if k3 is None else k3.stride(0), _ptr(row_active), _ptr(compact_out), _ptr(row_pos),
+              0 if csr is None else csr[0].data_ptr(), 0 if csr is None else csr[1].data_ptr(),
+              0 if csr is None else _ptr(csr[2]), _stream())
     return Y
 
 
@@ -379,7 +397,7 @@ class DIGAT(GraphEncoder):
         return attention_pool_fwd(Fa.view(B, S, D), v2, cmask, resid=T, add_in=ctx_in), k3_next
 
     def _layer(self, w, g, i, X, adj, ctx_other, k3=None, share=None, adj_index=None, prune=None, A_c=None,
-               want_compact=False):
+               want_compact=False, csr=None, csr_last=None):
         """k3 [B,D] (possibly a column view): ffn3(context of the other graph) + bias, computed here when None.
         share [B] int32 (layer 0 of the scoring path): X [n_src,n,D] holds one graph per BEHAVIOUR and pair b uses
         graph share[b]; the projection then runs once per behaviour and k3 is added inside the fused kernel.
@@ -394,6 +412,7 @@ class DIGAT(GraphEncoder):
         kernel_act = act
         if prune is not None and len(prune) > 3 and not want_compact and share is None and i + 1 == self.graph_depth:
             kernel_act = prune[3]         # last layer: only the rows a context pools are evaluated (the rest stay neighbours)
+            csr = csr_last                # (its CSR record lists those rows only)
         Yc = None
         if prune is not None and want_compact:
             # capacity = every row (M_act changes from batch to batch: a fixed size lets the caching allocator reuse the block)
@@ -401,7 +420,7 @@ class DIGAT(GraphEncoder):
         if share is not None:
             P = linear(X, w[g, i, 'Wcat'], w[g, i, 'bcat'])                       # h | K1 | K2 per behaviour
             return graph_layer_fwd(P, w[g, i, 'a'], adj, X, px_index=share, adj_index=share, k3=k3, B=k3.shape[0],
-                                   row_active=act, compact_out=Yc, row_pos=pos if Yc is not None else None), Yc
+                                   row_active=act, compact_out=Yc, row_pos=pos if Yc is not None else None, csr=csr), Yc
         if prune is not None:
             M = rows.shape[0]
             if A_c is None:                                                       # first layer: gather the active rows
@@ -411,11 +430,26 @@ class DIGAT(GraphEncoder):
             P = torch.empty((X.shape[0] * n, w[g, i, 'Wcat'].w.shape[0]), device=X.device, dtype=torch.float32)
             linear(A_c, w[g, i, 'Wcat'], w[g, i, 'bcat'], out=P, group_bias=k3, group_rows=n, group_col0=D, c_rows=rows)
             return graph_layer_fwd(P, w[g, i, 'a'], adj, X, adj_index=adj_index, row_active=kernel_act, compact_out=Yc,
-                                   row_pos=pos if Yc is not None else None), Yc
+                                   row_pos=pos if Yc is not None else None, csr=csr), Yc
         P = linear(X, w[g, i, 'Wcat'], w[g, i, 'bcat'], group_bias=k3, group_rows=n, group_col0=D)   # h | k3+K1 | K2
-        return graph_layer_fwd(P, w[g, i, 'a'], adj, X, adj_index=adj_index), None
+        return graph_layer_fwd(P, w[g, i, 'a'], adj, X, adj_index=adj_index, csr=csr), None
 
     prune_user_nodes = True      # inference only; switch off to evaluate every node of every user graph
+    precompute_user_csr = True   # user-graph CSR records built once per batch (build_graph_csr) instead of in every layer launch
+
+    def _user_csr(self, Au, prune, share, first_rows):
+        """CSR records of the user graphs for all layers of one batch: (csr, csr_last) for _layer.  The records follow the
+        adjacency's granularity: one per behaviour when the pairs of an impression share it (share + first_rows: the first
+        pair of each behaviour supplies its pruning flags -- they depend on the behaviour only), else one per row."""
+        if not self.precompute_user_csr or Au.shape[1] > 128 or (share is not None and first_rows is None):
+            return None, None
+        pick = (lambda f: f.index_select(0, first_rows.long())) if share is not None else (lambda f: f)   # noqa: E731
+        act = None if prune is None else pick(prune[0])
+        csr = build_graph_csr(Au, act) + (share,)
+        csr_last = csr
+        if prune is not None and len(prune) > 3 and self.graph_depth > 1:
+            csr_last = build_graph_csr(Au, pick(prune[3])) + (share,)
+        return csr, csr_last
 
     # ---- pruning lists.  The flags are computed by kernels (no synchronisation); compact_flags turns any number of flag
     # arrays into index lists with ONE host synchronisation (a single nonzero() over their concatenation).
@@ -598,7 +632,7 @@ class DIGAT(GraphEncoder):
             return self._layer(w, 'user', index, _f32c(user_graph_embeddings, 'user_graph_embeddings'),
                                _boolc(user_graph, 'user_graph'), _f32c(news_graph_context, 'news_graph_context'))[0]
 
-    def _encode(self, w, Xn, An, Mn, Xu, Au, Mc, ci, c_n, share=None, lists=None):
+    def _encode(self, w, Xn, An, Mn, Xu, Au, Mc, ci, c_n, share=None, lists=None, first_rows=None):
         """The L-layer dual-graph schedule of graphEncoders.py:180-198 on prebuilt node tensors.
         Xu [B, H+C, D] already holds [history ; topic nodes]; c_n None = compute the initial news context.
         share [B] int32 (scoring path): Xu / Au / ci are per-BEHAVIOUR tables and pair b uses entry share[b]; the
@@ -613,6 +647,7 @@ class DIGAT(GraphEncoder):
             prune, prune_n, seg_prune = self._lists(self._user_flags(Au, Mc, ci, share), self._news_flags(An, Mn),
                                                     self._segment_flags(Mc))
         c_u, k3u = self._user_ctx(w, Xu, Mc, ci, c_n, 0, src_index=share, seg_prune=seg_prune)
+        csr_u, csr_u_last = self._user_csr(Au, prune, share, first_rows)
         if share is not None:
             ci = ci.index_select(0, share.long())      # [B,H] int64: from layer 1 on every pair owns its user nodes
         Ac_n = Ac_u = None                               # compact projection operands written by the previous layer
@@ -620,7 +655,8 @@ class DIGAT(GraphEncoder):
             more = i + 1 < self.graph_depth
             Xn_new, Ac_n = self._layer(w, 'news', i, Xn, An, c_u, prune=prune_n, A_c=Ac_n, want_compact=more)
             Xu, Ac_u = self._layer(w, 'user', i, Xu, Au, c_n, k3=k3u, share=share if i == 0 else None,
-                                   adj_index=share if i > 0 else None, prune=prune, A_c=Ac_u, want_compact=more)
+                                   adj_index=share if i > 0 else None, prune=prune, A_c=Ac_u, want_compact=more,
+                                   csr=csr_u, csr_last=csr_u_last)
             Xn = Xn_new
             c_n = self._news_ctx(w, Xn, Mn, ctx_in=c_n)
             c_u, k3u = self._user_ctx(w, Xu, Mc, ci, c_n, i + 1, ctx_in=c_u, seg_prune=seg_prune)

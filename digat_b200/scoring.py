@@ -155,6 +155,7 @@ class Scorer:
         enc, prep = self.enc, begun['prep']
         with torch.no_grad():
             comp = enc.compact_finish(begun['state'], 4)
+            prep['first_rows'] = None if begun['first'] is None else comp[0][0]   # first pair of every distinct behaviour
             if begun['kind'] == 'resident':
                 bl = begun['bl']
                 if begun['first'] is not None:
@@ -197,7 +198,8 @@ class Scorer:
             c0 = self.gather_rows(self.c_n0, prep['news'])
             cn, cu = self.enc._encode(w, Xn, prep['An'], prep['Mn'], Xu, prep['Au'], prep['Mc'], prep['ci'], c0,
                                       share=prep['share'],
-                                      lists=(prep['prune'], prep['prune_n'], prep['seg_prune']))
+                                      lists=(prep['prune'], prep['prune_n'], prep['seg_prune']),
+                                      first_rows=prep.get('first_rows'))
             return logits(cn, cu)
 
     def score_resident(self, beh_idx, news_idx, share_user_graphs=True):

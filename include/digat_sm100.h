@@ -31,7 +31,7 @@ extern "C" {
 #define DIGAT_E_CUDA        -2   /* a CUDA runtime/driver call or a launch failed */
 #define DIGAT_E_UNSUPPORTED -3   /* device is not sm_100 */
 
-#define DIGAT_ABI_VERSION 4
+#define DIGAT_ABI_VERSION 5
 
 int         digat_abi_version(void);
 const char* digat_last_error(void);
@@ -132,7 +132,17 @@ int digat_graph_layer_fwd(const float* P, int ldp, const float* a, const uint8_t
                           int B, int n, int D, const uint8_t* drop_keep, float drop_scale, float* score_out,
                           float* alpha_out, uint8_t* relu_mask_out, const int32_t* px_index, int n_src,
                           const int32_t* adj_index, const float* k3, int ldk3, const uint8_t* row_active,
-                          float* Yc, const int32_t* row_pos, void* stream);
+                          float* Yc, const int32_t* row_pos, const uint16_t* csr_rowptr, const uint16_t* csr_meta,
+                          const int32_t* csr_index, void* stream);
+/* CSR of each graph's adjacency restricted to its evaluated rows, built once per batch for digat_graph_layer_fwd's
+ * csr_rowptr / csr_meta / csr_index (each may be NULL there; with them the kernel does not read `adj` and skips its
+ * per-layer, per-pair CSR construction; edge-driven kernel with one graph per CTA, i.e. not the multi-graph news launches):
+ *   graph g reads adjacency adj[adj_index ? adj_index[g] : g] ([*,n,n] bool) and row_active [G,n] (NULL = every row);
+ *   rowptr [G, n+1] uint16: rowptr[i+1] & 0x7fff = end of row i's edge range (pruned rows are empty), bit 15 = row i has no
+ *   edge at all (its range lists every node: the reference's uniform softmax);  meta [G, n*n] uint16: neighbour | row << 8.
+ * In digat_graph_layer_fwd graph b uses record csr_index[b] (NULL: b): the pairs of one impression share one record. */
+int digat_build_graph_csr(const uint8_t* adj, const int32_t* adj_index, const uint8_t* row_active, uint16_t* rowptr,
+                          uint16_t* meta, int64_t G, int n, void* stream);
 /* Vanilla-GAT layer of the reference's ablation encoders (graphEncoders.py:494-503, 511-520, 640-649, 807-816:
  * wo_interaction, news_graph_wo_inter, user_graph_wo_inter), inference:
  *   Y = relu(softmax_j(mask(leaky_relu(a1 . h_j + a2 . h_i))) * h) + X

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), 'libdigat_sm100.so does not export ' + n
     bound = set(_lib.SIGNATURES) | {'digat_last_error'}
     assert set(names) == bound, 'ctypes SIGNATURES out of sync with the header: %s' % (set(names) ^ bound)
-    assert _lib.load().digat_abi_version() == 4
+    assert _lib.load().digat_abi_version() == 5
 
 
 def test_no_gpu_fails_loudly():
@@ -48,7 +48,7 @@ def test_invalid_arguments_return_error_codes():
     p = ctypes.addressof(buf)
     p = (p + 15) & ~15
     assert lib.digat_linear_f32(p, 6, p, 8, None, p, 8, 1, 1, 6, 0, None, 1, 0, 0, 0, None) == -1        # K not multiple of 4
-    assert lib.digat_graph_layer_fwd(p, 12, p, p, p, p, 1, 500, 4, None, 1.0, None, None, None, None, 0, None, None, 0, None, None, None, None) == -1   # n too large
+    assert lib.digat_graph_layer_fwd(p, 12, p, p, p, p, 1, 500, 4, None, 1.0, None, None, None, None, 0, None, None, 0, None, None, None, None, None, None, None) == -1   # n too large
     assert lib.digat_attention_pool_fwd(p, 8, 8, None, p, 8, p, None, p, 8, None, None, 1, 1000, 8, None) == -1
 
 

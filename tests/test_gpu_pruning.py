@@ -156,3 +156,52 @@ def test_news_active_rows_kernel_matches_rule():
               torch.cuda.current_stream().cuda_stream)
     assert np.array_equal(act.cpu().numpy(), want)
     assert want[9, n - 1] == 1 and 0.2 < want.mean() < 0.9
+
+
+def test_graph_csr_builder_matches_numpy():
+    """digat_build_graph_csr: row pointers (bit 15 = edge-less row -> uniform), edge records neighbour | row << 8, pruned
+    rows empty; records read through adj_index."""
+    from digat_b200.graphEncoders import build_graph_csr
+    rng = np.random.Generator(np.random.PCG64(12))
+    G, n = 9, 37
+    adj = rng.random((5, n, n)) < 0.15
+    adj[:, np.arange(n), np.arange(n)] = True
+    adj[2, 7, :] = False                                             # an edge-less row (cannot happen in reference data)
+    act = rng.random((G, n)) < 0.7
+    idx = rng.integers(0, 5, size=G).astype(np.int32)
+    rowptr, meta = build_graph_csr(torch.from_numpy(adj).cuda(), torch.from_numpy(act.astype(np.uint8)).cuda(),
+                                   torch.from_numpy(idx).cuda())
+    torch.cuda.synchronize()
+    rowptr, meta = rowptr.cpu().numpy().view(np.uint16), meta.cpu().numpy().view(np.uint16)
+    for g in range(G):
+        e = 0
+        assert rowptr[g, 0] == 0
+        for i in range(n):
+            cols = np.nonzero(adj[idx[g], i])[0] if act[g, i] else np.zeros(0, dtype=np.int64)
+            uniform = bool(act[g, i]) and len(cols) == 0
+            if uniform:
+                cols = np.arange(n)
+            assert np.array_equal(meta[g, e:e + len(cols)], (cols | (i << 8)).astype(np.uint16)), (g, i)
+            e += len(cols)
+            assert rowptr[g, i + 1] == (e | (0x8000 if uniform else 0)), (g, i)
+
+
+def test_precomputed_csr_is_bit_identical_to_in_kernel_csr():
+    from tests.test_gpu_scoring import _setup
+    cfg, sd, corpus, scorer = _setup(n_beh=50, seed=4)
+    beh = torch.from_numpy(corpus.pair_behavior).cuda()
+    news = torch.from_numpy(corpus.pair_news).cuda()
+    out = {}
+    for on in (True, False):
+        scorer.enc.precompute_user_csr = on
+        out[on] = (scorer.score_resident(beh, news), scorer.score_resident(beh, news, share_user_graphs=False))
+    scorer.enc.precompute_user_csr = True
+    assert torch.equal(out[True][0], out[False][0]) and torch.equal(out[True][1], out[False][1])
+    assert torch.equal(out[True][0], out[True][1])
+    m, b = _encoder('default_n3_L3')                                     # the module API on per-row adjacencies (no sharing)
+    args = [b[k].repeat(64, *([1] * (b[k].dim() - 1))) for k in ORDER]
+    res = {}
+    for on in (True, False):
+        m.precompute_user_csr = on
+        res[on] = m.forward(*args)
+    assert torch.equal(res[True][0], res[False][0]) and torch.equal(res[True][1], res[False][1])
