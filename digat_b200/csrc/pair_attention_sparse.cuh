@@ -401,91 +401,128 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
     const long long t3 = clock64();
 #endif
     // ---------------------------------------------------------------------- phase 3: Y = relu(sum_{j in N(i)} alpha_ij h_j) + X
-    const int half_lane = lane & 15, sub = lane >> 4;              // two rows per warp pass, 16 feature quads each
-    // Residual rows: a pass over a row's few neighbours is far shorter than a DRAM round trip, so the x values of a
-    // whole unit (up to kXSlots passes of this warp) are requested one unit AHEAD and sit in registers meanwhile.
-    constexpr int kXSlots = 4;
+    // Two rows per warp pass, 16 lanes per row.  The h units (64 features each, one ring buffer) are consumed in PAIRS: a lane
+    // owns quad q of unit A and quad q of unit B, so the per-neighbour bookkeeping (alpha, neighbour index, loop control) and
+    // the per-row bookkeeping (row pointers, addresses) are paid once per 128 features -- this phase was 35 % of the kernel's
+    // instructions with one unit at a time.
+    const int half_lane = lane & 15, sub = lane >> 4;
+    // Residual rows: a pass over a row's few neighbours is far shorter than a DRAM round trip, so the x values of the next
+    // unit pair (up to kXSlots passes of this warp) are requested one iteration AHEAD and sit in registers meanwhile.
+    constexpr int kXSlots = 2;
     constexpr int kRowPairStep = kSparseConsumers / 32;
     const int n_act = *n_act_s;
     auto row_of = [&](int slot) {                                  // node evaluated by this half warp in pass `slot`, or -1
         const int k = 2 * (warp + slot * kRowPairStep) + sub;
         return k < n_act ? (int)act_list[k] : -1;
     };
-    auto load_x = [&](int unit, int slot) {
+    auto load_x = [&](int unit, int slot) {                        // quad of this lane in h unit `unit` of the row of pass `slot`
         const int c0_ = unit * kSparseDc3;
         const int i_ = row_of(slot);
         return (unit < g.nch3 && i_ >= 0 && c0_ + 4 * half_lane < D)
                    ? ldg_stream(reinterpret_cast<const float4*>(p.X + ((size_t)src0 * n + i_) * D + c0_ + 4 * half_lane))
                    : make_float4(0.f, 0.f, 0.f, 0.f);
     };
-    float4 xq[kXSlots];
+    float4 xqa[kXSlots], xqb[kXSlots];
 #pragma unroll
-    for (int sl = 0; sl < kXSlots; ++sl) xq[sl] = load_x(0, sl);
-    for (int l = g.nch1; l < n_loads; ++l) {
-        const int buf = l % kSparseBufs;
+    for (int sl = 0; sl < kXSlots; ++sl) {
+        xqa[sl] = load_x(0, sl);
+        xqb[sl] = load_x(1, sl);
+    }
+    for (int l = g.nch1; l < n_loads; l += 2) {
+        const bool pair = l + 1 < n_loads;                          // the last iteration may hold a single unit
+        const int bufa = l % kSparseBufs, bufb = (l + 1) % kSparseBufs;
         const int unit = l - g.nch1;
         const int c0 = unit * kSparseDc3;
-        const int wq = min(kSparseDc3, D - c0) >> 2;
-        const float* Hs0 = ring + buf * g.unit_floats;
-        float4 xcur[kXSlots];
+        const int wqa = min(kSparseDc3, D - c0) >> 2;
+        const int wqb = pair ? (min(kSparseDc3, D - c0 - kSparseDc3) >> 2) : 0;
+        const float* Ha = ring + bufa * g.unit_floats + 4 * half_lane;
+        const float* Hb = ring + bufb * g.unit_floats + 4 * half_lane;
+        float4 xa[kXSlots], xb[kXSlots];
 #pragma unroll
         for (int sl = 0; sl < kXSlots; ++sl) {
-            xcur[sl] = xq[sl];
-            xq[sl] = load_x(unit + 1, sl);                          // next unit's rows: in flight during this unit
+            xa[sl] = xqa[sl];
+            xb[sl] = xqb[sl];
+            xqa[sl] = load_x(unit + 2, sl);                         // next pair's rows: in flight during this one
+            xqb[sl] = load_x(unit + 3, sl);
         }
-        mbar_wait(&full[buf], (uint32_t)(l / kSparseBufs) & 1u);
+        mbar_wait(&full[bufa], (uint32_t)(l / kSparseBufs) & 1u);
+        if (pair) mbar_wait(&full[bufb], (uint32_t)((l + 1) / kSparseBufs) & 1u);
+        const bool on_a = half_lane < wqa, on_b = half_lane < wqb;
         constexpr int kMaxPasses = (kPairMaxNodes / 2 + kRowPairStep - 1) / kRowPairStep;
 #pragma unroll
         for (int sl = 0; sl < kMaxPasses; ++sl) {                   // slots >= kXSlots load their residual directly
             const int rp = warp + sl * kRowPairStep;
             if (2 * rp >= n_act) break;
             const int i = row_of(sl);
-            if (i >= 0 && half_lane < wq) {                             // pruned rows are not in the list: neither read nor written
-                const int q = half_lane;
-                const size_t yoff = ((size_t)b * n + i) * D + c0 + 4 * q;
-                float4 x;
-                if (sl < kXSlots) x = xcur[sl < kXSlots ? sl : 0];
-                else x = ldg_stream(reinterpret_cast<const float4*>(p.X + ((size_t)src0 * n + i) * D + c0 + 4 * q));
-                const float* Hs = Hs0 + 4 * q;
-                uint64_t o01 = 0ull, o23 = 0ull;
+            if (i >= 0 && on_a) {                                   // pruned rows are not in the list: neither read nor written
+                const size_t xoff = ((size_t)src0 * n + i) * D + c0 + 4 * half_lane;
+                const size_t yoff = ((size_t)b * n + i) * D + c0 + 4 * half_lane;
+                float4 x0, x1 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (sl < kXSlots) {
+                    x0 = xa[sl < kXSlots ? sl : 0];
+                    x1 = xb[sl < kXSlots ? sl : 0];
+                } else {
+                    x0 = ldg_stream(reinterpret_cast<const float4*>(p.X + xoff));
+                    if (on_b) x1 = ldg_stream(reinterpret_cast<const float4*>(p.X + xoff + kSparseDc3));
+                }
+                uint64_t o01 = 0ull, o23 = 0ull, p01 = 0ull, p23 = 0ull;
                 const int e1 = rowptr[i + 1];
                 int e = rowptr[i];
-                for (; e + 4 <= e1; e += 4) {                                               // 4 neighbours in flight
-                    float al[4];
-                    float4 h[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        al[u] = score[e + u];                                               // broadcast within the half warp
-                        h[u] = *reinterpret_cast<const float4*>(Hs + (meta[e + u] & 255u) * kSparseDc3);
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const uint64_t aa = pack2(al[u], al[u]);
-                        o01 = fma2(aa, pack2(h[u].x, h[u].y), o01);
-                        o23 = fma2(aa, pack2(h[u].z, h[u].w), o23);
-                    }
+                for (; e + 2 <= e1; e += 2) {                                               // 2 neighbours x 2 units in flight
+                    const float al0 = score[e], al1 = score[e + 1];                         // broadcast within the half warp
+                    const uint32_t j0 = (meta[e] & 255u) * kSparseDc3, j1 = (meta[e + 1] & 255u) * kSparseDc3;
+                    const float4 h0 = *reinterpret_cast<const float4*>(Ha + j0);
+                    const float4 h1 = *reinterpret_cast<const float4*>(Ha + j1);
+                    const float4 k0 = *reinterpret_cast<const float4*>(Hb + j0);            // (a stale / unused buffer when !on_b)
+                    const float4 k1 = *reinterpret_cast<const float4*>(Hb + j1);
+                    const uint64_t a0 = pack2(al0, al0), a1 = pack2(al1, al1);
+                    o01 = fma2(a0, pack2(h0.x, h0.y), o01);
+                    o23 = fma2(a0, pack2(h0.z, h0.w), o23);
+                    p01 = fma2(a0, pack2(k0.x, k0.y), p01);
+                    p23 = fma2(a0, pack2(k0.z, k0.w), p23);
+                    o01 = fma2(a1, pack2(h1.x, h1.y), o01);
+                    o23 = fma2(a1, pack2(h1.z, h1.w), o23);
+                    p01 = fma2(a1, pack2(k1.x, k1.y), p01);
+                    p23 = fma2(a1, pack2(k1.z, k1.w), p23);
                 }
-                for (; e < e1; ++e) {
+                if (e < e1) {
                     const float al = score[e];
-                    const float4 h = *reinterpret_cast<const float4*>(Hs + (meta[e] & 255u) * kSparseDc3);
+                    const uint32_t j0 = (meta[e] & 255u) * kSparseDc3;
+                    const float4 h = *reinterpret_cast<const float4*>(Ha + j0);
+                    const float4 k = *reinterpret_cast<const float4*>(Hb + j0);
                     const uint64_t aa = pack2(al, al);
                     o01 = fma2(aa, pack2(h.x, h.y), o01);
                     o23 = fma2(aa, pack2(h.z, h.w), o23);
+                    p01 = fma2(aa, pack2(k.x, k.y), p01);
+                    p23 = fma2(aa, pack2(k.z, k.w), p23);
                 }
                 float4 y;
                 unpack2(o01, y.x, y.y);
                 unpack2(o23, y.z, y.w);
-                y.x = fmaxf(y.x, 0.f) + x.x;
-                y.y = fmaxf(y.y, 0.f) + x.y;
-                y.z = fmaxf(y.z, 0.f) + x.z;
-                y.w = fmaxf(y.w, 0.f) + x.w;
+                y.x = fmaxf(y.x, 0.f) + x0.x;
+                y.y = fmaxf(y.y, 0.f) + x0.y;
+                y.z = fmaxf(y.z, 0.f) + x0.z;
+                y.w = fmaxf(y.w, 0.f) + x0.w;
                 stg_stream(reinterpret_cast<float4*>(p.Y + yoff), y);
-                if (p.Yc != nullptr)                                        // compact copy for the next layer's projection
-                    *reinterpret_cast<float4*>(p.Yc + (size_t)pos_s[i] * D + c0 + 4 * q) = y;
+                float* yc = p.Yc != nullptr ? p.Yc + (size_t)pos_s[i] * D + c0 + 4 * half_lane : nullptr;
+                if (yc != nullptr) *reinterpret_cast<float4*>(yc) = y;      // compact copy for the next layer's projection
+                if (on_b) {
+                    unpack2(p01, y.x, y.y);
+                    unpack2(p23, y.z, y.w);
+                    y.x = fmaxf(y.x, 0.f) + x1.x;
+                    y.y = fmaxf(y.y, 0.f) + x1.y;
+                    y.z = fmaxf(y.z, 0.f) + x1.z;
+                    y.w = fmaxf(y.w, 0.f) + x1.w;
+                    stg_stream(reinterpret_cast<float4*>(p.Y + yoff + kSparseDc3), y);
+                    if (yc != nullptr) *reinterpret_cast<float4*>(yc + kSparseDc3) = y;
+                }
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[buf]);
+        if (lane == 0) {
+            mbar_arrive(&empty[bufa]);
+            if (pair) mbar_arrive(&empty[bufb]);
+        }
     }
 #ifdef DIGAT_TC_TIMING
     if (tid == 0 && (b % 1000) == 7)
