@@ -208,6 +208,8 @@ int digat_news_gate_fwd(const float* z, const float* lg, const float* ctx_in, fl
  * cmask [B,n_seg] bool optional (inference): the mask the user-level attention applies to T afterwards
  * (graphEncoders.py:132).  Segments with cmask == 0 get a softmax weight of exactly 0 there, so their history rows are
  * not read and T[b,k] = 0 -- unless every segment of row b is masked (uniform weights: everything is evaluated).
+ * (With Tc, the rows T[b,k] of masked segments are left UNWRITTEN instead: the caller then evaluates featureAffine and the
+ * user-level pooling on the visible segments only and nothing reads them.)
  * Tc [M_live, D] + seg_pos [B*n_seg] int32 optional (with cmask): the evaluated segments (cmask != 0, or all of a
  * fully masked row) are also written to Tc[seg_pos[b*n_seg + k]], the compact operand of the featureAffine GEMM. */
 int digat_topic_segment_fwd(const float* Xu, int64_t strideX, const float* v, int ldv, const int64_t* cidx,
