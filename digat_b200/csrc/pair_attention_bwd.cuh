@@ -317,14 +317,22 @@ graph_layer_bwd_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_co
 }
 
 inline void pair_bwd_geometry(int n, int D, PairBwdGeom* g) {
+    g->nt = (n + 3) / 4;
+    g->ldm = ((n + 7) / 8) * 8 + 4;
+    // Feature chunk: 68 (68/4 = 17 odd: conflict-free row interleave), shrunk in steps of 8 (dc/4 stays odd) until TWO CTAs fit
+    // an SM.  At n = 68, dc = 68 the kernel needed 118.8 KB: one CTA per SM, so a training batch of 320 graphs ran in three
+    // waves on 148 SMs (ncu: 670 us); with dc = 60 (109.6 KB) the 296 slots take it in one wave plus a short tail.
+    const size_t two_per_sm = (size_t)113 * 1024;
     int dc = 68;
     if (dc > D) dc = D;
-    g->nt = (n + 3) / 4;
-    g->dc = dc;
-    g->nch = (D + dc - 1) / dc;
-    g->ldm = ((n + 7) / 8) * 8 + 4;
-    g->tile_floats = ((n * dc * 4 + 127) / 128) * 128 / 4;
-    g->smem = (size_t)4 * g->tile_floats * 4 + (size_t)2 * D * 4 + (size_t)2 * n * g->ldm * 4 + 16;
+    for (;;) {
+        g->dc = dc;
+        g->nch = (D + dc - 1) / dc;
+        g->tile_floats = ((n * dc * 4 + 127) / 128) * 128 / 4;
+        g->smem = (size_t)4 * g->tile_floats * 4 + (size_t)2 * D * 4 + (size_t)2 * n * g->ldm * 4 + 16;
+        if (g->smem <= two_per_sm || dc <= 36 || dc >= D) break;
+        dc -= 8;
+    }
 }
 
 inline int launch_graph_layer_bwd(const float* P, int ldp, const float* a, const uint8_t* adj, const float* score,
