@@ -129,6 +129,7 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
     // ---------------------------------------------------------------------- consumers: setup (overlaps the first loads)
 #ifdef DIGAT_TC_TIMING
     const long long t0 = clock64();
+    long long ta = t0, wait1 = 0, wait3 = 0;
 #endif
     const float* __restrict__ gat_s = p.gat_s;                     // vanilla-GAT scores: no phase-1 loads (g.nch1 == 0)
     for (int i = tid; i < D / 4; i += kSparseConsumers) {
@@ -187,7 +188,7 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
     }
     consumer_sync();
 #ifdef DIGAT_TC_TIMING
-    const long long ta = clock64();
+    ta = clock64();
 #endif
     // CSR pass A: degrees (a row without edges becomes a full row with uniform weights; a pruned row has no edges)
     for (int i = warp; i < N; i += kSparseConsumers / 32) {        // row i of the block-diagonal graph = adjacency row i, n columns
@@ -267,7 +268,13 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
         const uint32_t uoff = (uint32_t)(buf * g.unit_floats) * 4u;            // the ring starts at dynamic smem offset 0
         const uint32_t koff = uoff + (uint32_t)g.tile_floats * 4u;
         const uint32_t aoff = a_off + (uint32_t)c0 * 4u, k3off = k3_off + (uint32_t)c0 * 4u;
+#ifdef DIGAT_TC_TIMING
+        const long long tw0 = clock64();
+#endif
         mbar_wait(&full[buf], (uint32_t)(l / kSparseBufs) & 1u);
+#ifdef DIGAT_TC_TIMING
+        wait1 += clock64() - tw0;
+#endif
         // One edge per thread; a thread that owns a second edge (E > 320) evaluates BOTH in the same pass over the feature
         // quads -- their loads are independent, so the second edge rides in the latency shadow of the first (the loop is
         // latency-bound: a second sequential pass used to double the time of every unit), and the a / k3 quads are shared.
@@ -445,8 +452,14 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
             xqa[sl] = load_x(unit + 2, sl);                         // next pair's rows: in flight during this one
             xqb[sl] = load_x(unit + 3, sl);
         }
+#ifdef DIGAT_TC_TIMING
+        const long long tw0 = clock64();
+#endif
         mbar_wait(&full[bufa], (uint32_t)(l / kSparseBufs) & 1u);
         if (pair) mbar_wait(&full[bufb], (uint32_t)((l + 1) / kSparseBufs) & 1u);
+#ifdef DIGAT_TC_TIMING
+        wait3 += clock64() - tw0;
+#endif
         const bool on_a = half_lane < wqa, on_b = half_lane < wqb;
         constexpr int kMaxPasses = (kPairMaxNodes / 2 + kRowPairStep - 1) / kRowPairStep;
 #pragma unroll
@@ -526,7 +539,8 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
     }
 #ifdef DIGAT_TC_TIMING
     if (tid == 0 && (b % 1000) == 7)
-        printf("graph %d E=%d: setup %lld (loads %lld), phase1 %lld, softmax %lld, phase3 %lld\n", b, E, t1 - t0, ta - t0, t2 - t1, t3 - t2, clock64() - t3);
+        printf("graph %d E=%d n_act=%d csr=%d: setup %lld (loads %lld), phase1 %lld (waiting on TMA %lld), softmax %lld, phase3 %lld (waiting %lld)\n",
+               b, E, n_act, (int)have_csr, t1 - t0, ta - t0, t2 - t1, wait1, t3 - t2, clock64() - t3, wait3);
 #endif
 }
 

@@ -31,7 +31,12 @@ print('B=%d n=%d edges/graph %.0f active rows/graph %.1f active edges/graph %.0f
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 
-def bench(row_active, iters=10):
+from digat_b200.graphEncoders import build_graph_csr
+
+
+def bench(row_active, iters=10, csr=None):
+    if csr is not None:
+        return bench_csr(row_active, iters, csr)
     Y = graph_layer_fwd(P, a, adj, X, row_active=row_active)
     torch.cuda.synchronize()
     ts = []
@@ -46,6 +51,21 @@ def bench(row_active, iters=10):
     return Y, float(np.median(ts))
 
 
+def bench_csr(row_active, iters, csr):
+    Y = graph_layer_fwd(P, a, adj, X, row_active=row_active, csr=csr)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        graph_layer_fwd(P, a, adj, X, row_active=row_active, csr=csr)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return Y, float(np.median(ts))
+
+
 Y0, t0 = bench(None)
 Y1, t1 = bench(act)
 alg = B * (5 * n * D * 4 + n * n + D * 4)
@@ -53,6 +73,9 @@ print('all rows    : %.4f ms  %.0f GB/s algorithmic' % (t0, alg / t0 / 1e6))
 print('active rows : %.4f ms  %.0f GB/s algorithmic' % (t1, alg / t1 / 1e6))
 k = act != 0
 print('active rows identical:', bool(torch.equal(Y0[k], Y1[k])))
+csr = build_graph_csr(adj, act) + (None,)
+Y2, t2 = bench(act, csr=csr)
+print('active rows, precomputed CSR : %.4f ms  %.0f GB/s algorithmic; identical: %s' % (t2, alg / t2 / 1e6, bool(torch.equal(Y2[k], Y1[k]))))
 _lib.call('digat_debug_set_layer_mode', 1)
 Yd = graph_layer_fwd(P, a, adj, X)
 _lib.call('digat_debug_set_layer_mode', 0)
