@@ -35,7 +35,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done) : "r"(addr), "r"(parity), "r"(kMbarSuspendHintNs) : "memory");
         if (done) return;
-        if (spin > (1u << 20)) {
+        if (spin > (1u << 23)) {
             printf("digat: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
             __trap();
         }
