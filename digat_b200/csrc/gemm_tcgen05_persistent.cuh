@@ -85,7 +85,8 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
     uint64_t* empty = bars + 2 * Cfg::STAGES;               // [STAGES] MMAs reading the stage have retired
     uint64_t* accum_full = bars + 3 * Cfg::STAGES;          // accumulators of the current tile complete
     uint64_t* tmem_empty = accum_full + 1;                  // epilogue has drained the accumulators
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+    uint64_t* peer_full = tmem_empty + 1;                   // [STAGES] 2-CTA MMA, leader only: the PEER's TMA bytes of the stage landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(peer_full + Cfg::STAGES);
     float* bias_s = reinterpret_cast<float*>(smem + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES + 512);   // [N]
     float* stage_base = bias_s + Cfg::MAX_N;                // [4 warps][32][20]
     float* gb_s = stage_base + kTcEpiWarps * 32 * 20;       // [GB_GROUPS][BN] row-group bias slice of the current tile
@@ -123,6 +124,7 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
             // 2-CTA MMA: the leader's "ready" also counts one arrive forwarded from the peer (its 4 transform warps are done)
             mbar_init(&ready[s], kTcTransformThreads / 32 + ((kCl == 3 && cl_rank == 0) ? 1 : 0));
             mbar_init(&empty[s], kCl == 2 ? 2 : 1);             // kCl = 2: the peer's TMA writes this stage too
+            mbar_init(&peer_full[s], 1);
         }
         mbar_init(accum_full, 1);
         mbar_init(tmem_empty, kCl == 3 ? 2 * kTcEpiWarps : kTcEpiWarps);   // 2-CTA MMA: the leader waits for both epilogues
@@ -187,8 +189,10 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
         if (kCl == 3) {
             if (lane == 0 && cl_rank == 0) {
                 // 2-CTA MMA, leader: one M = 256 instruction covers both CTAs' 128 rows; A and the two halves of W are read
-                // from both CTAs' shared memory, each CTA's accumulator rows land in its own TMEM.  A stage is issued when
-                // BOTH CTAs' transform warps are done with it (ready: 4 local arrives + 1 forwarded by the peer).
+                // from both CTAs' shared memory, each CTA's accumulator rows land in its own TMEM.  As in the single-CTA kernel
+                // the products that need no transformed operand (raw A x W_hi, raw A x W_lo) are issued as soon as BOTH CTAs'
+                // TMA bytes of the stage have landed (own `full`, the peer's forwarded as `peer_full`); only the A_lo products
+                // wait for both CTAs' transform warps (`ready`: 4 local arrives + 1 forwarded), one stage later.
                 constexpr uint32_t idesc2 = umma_idesc_tf32(256, BN);
                 constexpr uint32_t idesc2h = umma_idesc_bf16(256, BN);
                 const uint32_t d_main = tmem_base, d_corr = tmem_base + (uint32_t)BN;
@@ -198,40 +202,61 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
                         mbar_wait_cluster(tmem_empty, (uint32_t)(j - 1) & 1u);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     }
-                    for (int kb = 0; kb < nkb; ++kb, ++it) {
-                        const int s = it % Cfg::STAGES;
-                        mbar_wait_cluster(&ready[s], (it / Cfg::STAGES) & 1);
+                    auto issue_raw = [&](int kb, int g) {
+                        const int s = g % Cfg::STAGES;
+                        mbar_wait(&full[s], (g / Cfg::STAGES) & 1);
+                        mbar_wait_cluster(&peer_full[s], (g / Cfg::STAGES) & 1);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint64_t d_ahi = umma_desc_sw64(smem_u32(a_hi(s))), d_whi = umma_desc_sw64(smem_u32(w_hi(s)));
+                        const uint64_t d_ahi = umma_desc_sw64(smem_u32(a_hi(s)));
+                        const uint64_t d_whi = umma_desc_sw64(smem_u32(w_hi(s))), d_wlo = umma_desc_sw64(smem_u32(w_lo(s)));
 #pragma unroll
                         for (int k = 0; k < kTcBK / 8; ++k) {
                             const uint64_t koff = (uint64_t)((k * 8 * 4) >> 4);
-                            umma_tf32_2cta(d_main, d_ahi + koff, d_whi + koff, idesc2, (kb > 0 || k > 0) ? 1u : 0u);
+                            const uint32_t first = (kb > 0 || k > 0) ? 1u : 0u;
+                            umma_tf32_2cta(d_main, d_ahi + koff, d_whi + koff, idesc2, first);
+                            if (!kBf16) umma_tf32_2cta(d_corr, d_ahi + koff, d_wlo + koff, idesc2, first);
                         }
+                    };
+                    auto issue_lo = [&](int g) {
+                        const int s = g % Cfg::STAGES;
+                        mbar_wait_cluster(&ready[s], (g / Cfg::STAGES) & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         if (kBf16) {
-                            umma_bf16_2cta(d_corr, umma_desc_sw32(smem_u32(a_lo(s))), umma_desc_sw32(smem_u32(w_b3(s))), idesc2h, kb > 0 ? 1u : 0u);
+                            const uint32_t first = (g - it) > 0 ? 1u : 0u;
+                            umma_bf16_2cta(d_corr, umma_desc_sw32(smem_u32(a_lo(s))), umma_desc_sw32(smem_u32(w_b3(s))), idesc2h, first);
                             umma_bf16_2cta(d_corr, umma_desc_sw32(smem_u32(a_b2(s))), umma_desc_sw32(smem_u32(w_lo(s))), idesc2h, 1u);
                         } else {
-                            const uint64_t d_alo = umma_desc_sw64(smem_u32(a_lo(s))), d_wlo = umma_desc_sw64(smem_u32(w_lo(s)));
+                            const uint64_t d_alo = umma_desc_sw64(smem_u32(a_lo(s))), d_whi = umma_desc_sw64(smem_u32(w_hi(s)));
 #pragma unroll
                             for (int k = 0; k < kTcBK / 8; ++k) {
                                 const uint64_t koff = (uint64_t)((k * 8 * 4) >> 4);
-                                umma_tf32_2cta(d_corr, d_ahi + koff, d_wlo + koff, idesc2, (kb > 0 || k > 0) ? 1u : 0u);
                                 umma_tf32_2cta(d_corr, d_alo + koff, d_whi + koff, idesc2, 1u);
                             }
                         }
                         umma_commit_2cta(&empty[s]);               // frees stage s in both CTAs
+                    };
+                    issue_raw(0, it);
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        if (kb + 1 < nkb) issue_raw(kb + 1, it + kb + 1);
+                        issue_lo(it + kb);
                     }
+                    it += nkb;
                     umma_commit_2cta(accum_full);                  // both CTAs' epilogues
                 }
-            } else if (lane == 0) {
-                // peer: this otherwise idle thread forwards "my 4 transform warps are done with stage s" as ONE remote arrive
+            } else if (cl_rank == 1 && lane < 2) {
+                // peer: two otherwise idle threads forward its per-stage events to the leader as ONE remote arrive each --
+                // lane 0 "my TMA bytes have landed" (full -> peer_full), lane 1 "my transform warps are done" (ready -> ready)
                 int it = 0;
                 for (int tile = worker; tile < n_tiles; tile += n_workers)
                     for (int kb = 0; kb < nkb; ++kb, ++it) {
                         const int s = it % Cfg::STAGES;
-                        mbar_wait(&ready[s], (it / Cfg::STAGES) & 1);
-                        mbar_arrive_cluster(&ready[s], 0);
+                        if (lane == 0) {
+                            mbar_wait(&full[s], (it / Cfg::STAGES) & 1);
+                            mbar_arrive_cluster(&peer_full[s], 0);
+                        } else {
+                            mbar_wait(&ready[s], (it / Cfg::STAGES) & 1);
+                            mbar_arrive_cluster(&ready[s], 0);
+                        }
                     }
             }
         } else if (lane == 0) {
