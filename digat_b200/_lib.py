@@ -27,7 +27,7 @@ SIGNATURES = {
     'digat_graph_layer_fwd': [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                               c_void_p, ctypes.c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                               c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
-    'digat_build_graph_csr': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p],
+    'digat_build_graph_csr': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p],
     'digat_gat_layer_fwd': [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     'digat_graph_layer_supports_row_active': [c_int, c_int, c_int],
     'digat_compact_lists': [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
@@ -45,6 +45,9 @@ SIGNATURES = {
                                c_void_p, c_void_p],
     'digat_graph_layer_bwd': [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_float, c_void_p,
                               c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p],
+    'digat_graph_layer_bwd_csr': [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  ctypes.c_float, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p],
+    'digat_graph_layer_csr_training_supported': [c_int, c_int],
     'digat_attention_pool_bwd': [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                  c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     'digat_topic_segment_bwd': [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -105,7 +108,7 @@ def require_device(device_index: int):
     _device_ok[device_index] = True
 
 
-_NON_KERNEL = ('digat_graph_layer_supports_row_active', 'digat_abi_version', 'digat_device_check', 'digat_debug_set_gemm_variant', 'digat_debug_set_layer_mode',
+_NON_KERNEL = ('digat_graph_layer_supports_row_active', 'digat_graph_layer_csr_training_supported', 'digat_abi_version', 'digat_device_check', 'digat_debug_set_gemm_variant', 'digat_debug_set_layer_mode',
                'digat_reduce_workspace_floats')
 _launches = 0
 _profile = None      # list of (name, args, start_event, end_event) while bench.py's per-kernel pass is running

@@ -12,7 +12,10 @@ import torch.nn.functional as F
 from torch.autograd import Function
 
 from . import _lib
-from .graphEncoders import PackedWeight, _ptr, _stream, attention_pool_fwd, graph_layer_fwd, linear
+from .graphEncoders import PackedWeight, _ptr, _stream, attention_pool_fwd, build_graph_csr, graph_layer_fwd, linear
+
+# Training walks each graph's edges (CSR + transpose built once per step) instead of all n^2 pairs; False = dense kernels.
+TRAIN_EDGE_DRIVEN = True
 
 
 def _workspace(M, N, K, device):
@@ -113,19 +116,22 @@ def lin(A, W, bias=None, group_bias=None, group_rows=1, group_col0=0):
 
 
 class GraphLayerFn(Function):
-    """Fused Eq. (8) layer; backward recomputes the [n,n,D] relu mask instead of storing it (digat_graph_layer_bwd)."""
+    """Fused Eq. (8) layer; backward recomputes the [n,n,D] relu mask instead of storing it.  With csr = (rowptr, meta,
+    colptr, cedge) from build_graph_csr(transpose=True) both directions are edge-driven (digat_graph_layer_fwd with
+    per-edge score / alpha + digat_graph_layer_bwd_csr); without it the dense [B,n,n] kernels run."""
 
     @staticmethod
-    def forward(ctx, P, a, adj, X, drop_keep, drop_scale):
+    def forward(ctx, P, a, adj, X, drop_keep, drop_scale, csr=None):
         B, n, D = X.shape
         P, a, X = P.contiguous(), a.contiguous(), X.contiguous()
         score = torch.empty((B, n, n), device=X.device, dtype=torch.float32)
         alpha = torch.empty((B, n, n), device=X.device, dtype=torch.float32)
         rmask = torch.empty((B, n, D), device=X.device, dtype=torch.uint8)
         Y = graph_layer_fwd(P, a, adj, X, drop_keep=drop_keep, drop_scale=drop_scale, score_out=score,
-                            alpha_out=alpha, relu_mask_out=rmask)
+                            alpha_out=alpha, relu_mask_out=rmask, csr=None if csr is None else (csr[0], csr[1], None))
         ctx.save_for_backward(P, a, adj, score, alpha, rmask)
         ctx.drop = (drop_keep, float(drop_scale))
+        ctx.csr = csr
         return Y
 
     @staticmethod
@@ -137,10 +143,16 @@ class GraphLayerFn(Function):
         G = dY * rmask                                    # dZ = dY * 1[Z > 0]
         dP = torch.empty_like(P)
         da_part = torch.empty((B, D), device=P.device, dtype=torch.float32)
-        _lib.call('digat_graph_layer_bwd', P.data_ptr(), P.stride(0), a.data_ptr(), adj.data_ptr(), score.data_ptr(),
-                  alpha.data_ptr(), _ptr(keep), scale, G.data_ptr(), dP.data_ptr(), dP.stride(0), da_part.data_ptr(),
-                  B, n, D, _stream())
-        return dP, colsum(da_part), None, dY, None, None
+        if ctx.csr is not None:
+            rowptr, meta, colptr, cedge = ctx.csr
+            _lib.call('digat_graph_layer_bwd_csr', P.data_ptr(), P.stride(0), a.data_ptr(), rowptr.data_ptr(), meta.data_ptr(),
+                      colptr.data_ptr(), cedge.data_ptr(), score.data_ptr(), alpha.data_ptr(), _ptr(keep), scale, G.data_ptr(),
+                      dP.data_ptr(), dP.stride(0), da_part.data_ptr(), B, n, D, _stream())
+        else:
+            _lib.call('digat_graph_layer_bwd', P.data_ptr(), P.stride(0), a.data_ptr(), adj.data_ptr(), score.data_ptr(),
+                      alpha.data_ptr(), _ptr(keep), scale, G.data_ptr(), dP.data_ptr(), dP.stride(0), da_part.data_ptr(),
+                      B, n, D, _stream())
+        return dP, colsum(da_part), None, dY, None, None, None
 
 
 class AttentionPoolFn(Function):
@@ -235,6 +247,14 @@ def encode_with_grad(enc, Xn, An, Mn, Xh, Au, Mc, ci):
             return AttentionPoolFn.apply(drop(torch.relu(Fa) + T, p), v2, Mc, None)
         return AttentionPoolFn.apply(Fa, v2, Mc, T)
 
+    def train_csr(adj):
+        n = adj.shape[1]
+        if not TRAIN_EDGE_DRIVEN or not _lib.load().digat_graph_layer_csr_training_supported(n, D):
+            return None
+        return build_graph_csr(adj, transpose=True)
+
+    csr_of = {'news': train_csr(An), 'user': train_csr(Au)}          # once per step: every layer walks the same edges
+
     def layer(g, i, X, adj, ctx_other):
         n = X.shape[1]
         W = getattr(enc, g + '_graph_attention_W')[i]
@@ -247,7 +267,7 @@ def encode_with_grad(enc, Xn, An, Mn, Xh, Au, Mc, ci):
         P = lin(Xd.reshape(B * n, D), torch.cat([W.weight, f1.weight, f2.weight], 0), torch.cat([W.bias, zeros2D], 0),
                 group_bias=k3, group_rows=n, group_col0=D)
         keep = (torch.rand((B, n, n), device=dev) >= p) if p > 0 else None
-        return GraphLayerFn.apply(P, av.weight.reshape(D), adj, Xd, keep, 1.0 / (1.0 - p) if p > 0 else 1.0)
+        return GraphLayerFn.apply(P, av.weight.reshape(D), adj, Xd, keep, 1.0 / (1.0 - p) if p > 0 else 1.0, csr_of[g])
 
     topic = drop(enc.topic_node_embedding.unsqueeze(0).expand(B, -1, -1), p / 2)
     Xu = torch.cat([Xh, topic], 1)

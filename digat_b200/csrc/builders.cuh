@@ -192,23 +192,30 @@ inline int launch_user_active_rows(const uint8_t* adj, const int32_t* adj_index,
 // cycles per graph).  One CTA of four warps per graph, a warp per row (ballot + popc), one warp scan for the row pointers.
 __global__ void __launch_bounds__(128)
 graph_csr_kernel(const uint8_t* __restrict__ adj, const int32_t* __restrict__ adj_index, const uint8_t* __restrict__ row_active,
-                 uint16_t* __restrict__ rowptr_out, uint16_t* __restrict__ meta_out, int n) {
+                 uint16_t* __restrict__ rowptr_out, uint16_t* __restrict__ meta_out, uint16_t* __restrict__ colptr_out,
+                 uint16_t* __restrict__ cedge_out, int n) {
+    extern __shared__ uint16_t eid[];            // [n*n] edge id of (i,j) or 0xFFFF (only when the transpose is requested)
     __shared__ int rp[130];
+    __shared__ int cp[130];
     __shared__ uint8_t uni[128];
     const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint8_t* a = adj + (adj_index != nullptr ? (size_t)adj_index[g] : (size_t)g) * n * n;
     const uint8_t* act = row_active != nullptr ? row_active + (size_t)g * n : nullptr;
+    const bool want_t = colptr_out != nullptr;
+    const int n32 = (n + 31) & ~31;
     for (int i = warp; i < n; i += 4) {
         const bool dead = act != nullptr && act[i] == 0;
         int deg = 0;
         if (!dead)
-            for (int j = lane; j < ((n + 31) & ~31); j += 32)
+            for (int j = lane; j < n32; j += 32)
                 deg += __popc(__ballot_sync(0xffffffffu, j < n && a[i * n + j] != 0));
         if (lane == 0) {
             uni[i] = deg == 0 && !dead;
             rp[i + 1] = dead ? 0 : (deg == 0 ? n : deg);
         }
     }
+    if (want_t)
+        for (int e = tid; e < n * n; e += 128) eid[e] = 0xFFFFu;
     __syncthreads();
     if (warp == 0) {
         int run = 0;
@@ -234,21 +241,67 @@ graph_csr_kernel(const uint8_t* __restrict__ adj, const int32_t* __restrict__ ad
         const int e0 = rp[i];
         const bool u = uni[i] != 0;
         int filled = 0;
-        for (int j = lane; j < ((n + 31) & ~31); j += 32) {
+        for (int j = lane; j < n32; j += 32) {
             const bool on = j < n && (u || a[i * n + j] != 0);
             const unsigned m = __ballot_sync(0xffffffffu, on);
-            if (on) mo[e0 + filled + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(j | (i << 8));
+            if (on) {
+                const int e = e0 + filled + __popc(m & ((1u << lane) - 1u));
+                mo[e] = (uint16_t)(j | (i << 8));
+                if (want_t) eid[i * n + j] = (uint16_t)e;
+            }
+            filled += __popc(m);
+        }
+    }
+    if (!want_t) return;
+    // transpose (CSC): the edges of column j in ascending row order, as ids into the CSR arrays (the backward pass sums
+    // over the incoming edges of a node: dh_j, dU_j)
+    __syncthreads();
+    for (int j = warp; j < n; j += 4) {
+        int cnt = 0;
+        for (int i = lane; i < n32; i += 32)
+            cnt += __popc(__ballot_sync(0xffffffffu, i < n && eid[i * n + j] != 0xFFFFu));
+        if (lane == 0) cp[j + 1] = cnt;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        int run = 0;
+        for (int base = 0; base < n; base += 32) {
+            const int j = base + lane;
+            int v = j < n ? cp[j + 1] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= o) v += t;
+            }
+            if (j < n) cp[j + 1] = run + v;
+            run += __shfl_sync(0xffffffffu, v, 31);
+        }
+        if (lane == 0) cp[0] = 0;
+    }
+    __syncthreads();
+    uint16_t* cpo = colptr_out + (size_t)g * (n + 1);
+    uint16_t* ceo = cedge_out + (size_t)g * n * n;
+    for (int j = tid; j <= n; j += 128) cpo[j] = (uint16_t)cp[j];
+    for (int j = warp; j < n; j += 4) {
+        int filled = 0;
+        for (int i = lane; i < n32; i += 32) {
+            const uint16_t e = i < n ? eid[i * n + j] : (uint16_t)0xFFFFu;
+            const bool on = e != 0xFFFFu;
+            const unsigned m = __ballot_sync(0xffffffffu, on);
+            if (on) ceo[cp[j] + filled + __popc(m & ((1u << lane) - 1u))] = e;
             filled += __popc(m);
         }
     }
 }
 
 inline int launch_build_graph_csr(const uint8_t* adj, const int32_t* adj_index, const uint8_t* row_active, uint16_t* rowptr,
-                                  uint16_t* meta, int64_t G, int n, cudaStream_t st) {
+                                  uint16_t* meta, uint16_t* colptr, uint16_t* cedge, int64_t G, int n, cudaStream_t st) {
     if (G <= 0) return DIGAT_OK;
     DIGAT_REQUIRE(adj && rowptr && meta, "digat_build_graph_csr: null pointer");
+    DIGAT_REQUIRE((colptr == nullptr) == (cedge == nullptr), "digat_build_graph_csr: colptr and cedge go together");
     DIGAT_REQUIRE(n >= 1 && n <= 128 && G < (1LL << 31), "digat_build_graph_csr: n=%d outside [1,128]", n);
-    graph_csr_kernel<<<(unsigned)G, 128, 0, st>>>(adj, adj_index, row_active, rowptr, meta, n);
+    const size_t smem = colptr != nullptr ? (size_t)n * n * sizeof(uint16_t) : 0;
+    graph_csr_kernel<<<(unsigned)G, 128, smem, st>>>(adj, adj_index, row_active, rowptr, meta, colptr, cedge, n);
     return check_launch("digat_build_graph_csr");
 }
 

@@ -10,6 +10,7 @@
 #include "context.cuh"
 #include "gather.cuh"
 #include "pair_attention_bwd.cuh"
+#include "pair_attention_sparse_bwd.cuh"
 #include "context_bwd.cuh"
 #include "gemm_wgrad.cuh"
 #include "builders.cuh"
@@ -125,8 +126,8 @@ int digat_graph_layer_fwd(const float* P, int ldp, const float* a, const uint8_t
 }
 
 int digat_build_graph_csr(const uint8_t* adj, const int32_t* adj_index, const uint8_t* row_active, uint16_t* rowptr,
-                          uint16_t* meta, int64_t G, int n, void* stream) {
-    return launch_build_graph_csr(adj, adj_index, row_active, rowptr, meta, G, n, as_stream(stream));
+                          uint16_t* meta, uint16_t* colptr, uint16_t* cedge, int64_t G, int n, void* stream) {
+    return launch_build_graph_csr(adj, adj_index, row_active, rowptr, meta, colptr, cedge, G, n, as_stream(stream));
 }
 
 int digat_gat_layer_fwd(const float* Hm, int ldh, const float* s12, const uint8_t* adj, const float* X, float* Y,
@@ -225,6 +226,16 @@ int digat_graph_layer_bwd(const float* P, int ldp, const float* a, const uint8_t
     return launch_graph_layer_bwd(P, ldp, a, adj, score, alpha, drop_keep, drop_scale, G, dP, lddp, da_partial, B, n, D,
                                   as_stream(stream));
 }
+
+int digat_graph_layer_bwd_csr(const float* P, int ldp, const float* a, const uint16_t* csr_rowptr, const uint16_t* csr_meta,
+                              const uint16_t* csc_colptr, const uint16_t* csc_edge, const float* edge_score,
+                              const float* edge_alpha, const uint8_t* drop_keep, float drop_scale, const float* G, float* dP,
+                              int lddp, float* da_partial, int B, int n, int D, void* stream) {
+    return launch_graph_layer_bwd_csr(P, ldp, a, csr_rowptr, csr_meta, csc_colptr, csc_edge, edge_score, edge_alpha, drop_keep,
+                                      drop_scale, G, dP, lddp, da_partial, B, n, D, as_stream(stream));
+}
+
+int digat_graph_layer_csr_training_supported(int n, int D) { return graph_layer_csr_training_supported(n, D); }
 
 int digat_attention_pool_bwd(const float* F, int64_t strideF, int ldf, const float* resid_F, const float* v,
                              const uint8_t* mask, const float* alpha, const float* dout, int ldg, float* dF,

@@ -445,11 +445,17 @@ inline int launch_graph_layer_fwd(const float* P, int ldp, const float* a, const
     args.csr_meta = csr_meta;
     args.csr_index = csr_index;
     const bool inference = !drop_keep && !score_out && !alpha_out && !relu_mask_out;
-    // Inference takes the edge-driven kernel (small graphs are batched several per CTA); the dense kernel stays for
-    // training and for graphs whose edge-driven working set does not fit one CTA (n > ~100 at D = 400).
+    // Inference takes the edge-driven kernel (small graphs are batched several per CTA); the dense kernel stays for graphs
+    // whose edge-driven working set does not fit one CTA (n > ~100 at D = 400) and for training WITHOUT a precomputed CSR.
+    // Training with csr_rowptr / csr_meta also takes the edge-driven kernel: score_out / alpha_out are then PER-EDGE arrays in
+    // CSR order ([B, n*n] capacity each) for digat_graph_layer_bwd_csr, not dense [B,n,n] matrices.
     const bool sparse_fits = graph_layer_fwd_sparse_smem(n, D) <= (size_t)di->max_smem_optin;
-    if (inference && g_layer_mode != 1 && (sparse_fits || g_layer_mode == 2))
+    const bool sparse_train = !inference && csr_rowptr != nullptr && px_index == nullptr && g_layer_mode != 1 && sparse_fits;
+    if ((inference && g_layer_mode != 1 && (sparse_fits || g_layer_mode == 2)) || sparse_train)
         return launch_graph_layer_fwd_sparse(args, n_src, st);
+    if (!inference && csr_rowptr != nullptr)
+        return fail(DIGAT_E_UNSUPPORTED, "digat_graph_layer_fwd: training with a CSR needs the edge-driven kernel (not indexed, "
+                    "working set within one SM); query digat_graph_layer_csr_training_supported first");
     if (row_active != nullptr)
         return fail(DIGAT_E_UNSUPPORTED, "digat_graph_layer_fwd: row_active needs the edge-driven kernel (inference, one graph "
                     "per CTA); query digat_graph_layer_supports_row_active first");

@@ -358,30 +358,48 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
 #endif
 
     // ---------------------------------------------------------------------- phase 2: softmax over each row's edges
+    // Training extras (one graph per CTA, precomputed CSR): the raw score s_e and the softmax weight alpha_e of every edge go
+    // out in CSR order (score_out / alpha_out [B, n*n], what the edge-driven backward reads), and the dropout on the attention
+    // weights (graphEncoders.py:152/172) is applied here: alpha~_e = alpha_e * keep[i,j] * scale.
+    const bool train_out = !kMulti && p.alpha_out != nullptr;
+    float* __restrict__ e_alpha = train_out ? p.alpha_out + (size_t)b * n * n : nullptr;
+    float* __restrict__ e_score = (train_out && p.score_out != nullptr) ? p.score_out + (size_t)b * n * n : nullptr;
+    const uint8_t* __restrict__ keep_g = (!kMulti && p.drop_keep != nullptr) ? p.drop_keep + (size_t)b * n * n : nullptr;
+    auto finish_edge = [&](int e, float s_raw, float al) {           // store alpha~ for phase 3, the raw values for the backward
+        if (e_score != nullptr) e_score[e] = s_raw;
+        if (e_alpha != nullptr) e_alpha[e] = al;
+        if (keep_g != nullptr) {
+            const uint32_t mt = meta[e];
+            al = keep_g[(mt >> 8) * n + (mt & 255u)] != 0 ? al * p.drop_scale : 0.f;
+        }
+        score[e] = al;
+    };
     for (int i = warp; i < N; i += kSparseConsumers / 32) {
         const int e0 = rowptr[i], deg = rowptr[i + 1] - e0;
         if (deg == 0) continue;                                    // pruned row
         const bool uni = uniform_row[i] != 0;
         if (deg <= 32) {                                           // the common case: one edge per lane
-            float m = -INFINITY;
+            float m = -INFINITY, s = 0.f;
             if (lane < deg) {
-                const float s = score[e0 + lane];
+                s = score[e0 + lane];
                 m = uni ? kNegFill : (s > 0.f ? s : s * kLeakySlope);
             }
             const float mx1 = warp_max(m);
             const float ex = lane < deg ? expf(m - mx1) : 0.f;
             const float sum1 = warp_sum(ex);
-            if (lane < deg) score[e0 + lane] = ex / sum1;
+            if (lane < deg) finish_edge(e0 + lane, s, ex / sum1);
             continue;
         }
-        float v[kPairMaxNodes / 32];
+        float v[kPairMaxNodes / 32], sr[kPairMaxNodes / 32];
         float mx = -INFINITY;
 #pragma unroll
         for (int k = 0; k < kPairMaxNodes / 32; ++k) {
             const int t = lane + 32 * k;
             float m = -INFINITY;
+            sr[k] = 0.f;
             if (t < deg) {
                 const float s = score[e0 + t];
+                sr[k] = s;
                 m = uni ? kNegFill : (s > 0.f ? s : s * kLeakySlope);
             }
             v[k] = m;
@@ -399,7 +417,7 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
 #pragma unroll
         for (int k = 0; k < kPairMaxNodes / 32; ++k) {
             const int t = lane + 32 * k;
-            if (t < deg) score[e0 + t] = v[k] / sum;
+            if (t < deg) finish_edge(e0 + t, sr[k], v[k] / sum);
         }
     }
     consumer_sync();
@@ -512,6 +530,8 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
                 float4 y;
                 unpack2(o01, y.x, y.y);
                 unpack2(o23, y.z, y.w);
+                if (p.relu_mask_out != nullptr)                             // training: 1[alpha~ h > 0] for the backward
+                    *reinterpret_cast<uchar4*>(p.relu_mask_out + yoff) = make_uchar4(y.x > 0.f, y.y > 0.f, y.z > 0.f, y.w > 0.f);
                 y.x = fmaxf(y.x, 0.f) + x0.x;
                 y.y = fmaxf(y.y, 0.f) + x0.y;
                 y.z = fmaxf(y.z, 0.f) + x0.z;
@@ -522,6 +542,8 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
                 if (on_b) {
                     unpack2(p01, y.x, y.y);
                     unpack2(p23, y.z, y.w);
+                    if (p.relu_mask_out != nullptr)
+                        *reinterpret_cast<uchar4*>(p.relu_mask_out + yoff + kSparseDc3) = make_uchar4(y.x > 0.f, y.y > 0.f, y.z > 0.f, y.w > 0.f);
                     y.x = fmaxf(y.x, 0.f) + x1.x;
                     y.y = fmaxf(y.y, 0.f) + x1.y;
                     y.z = fmaxf(y.z, 0.f) + x1.z;
@@ -582,7 +604,8 @@ int launch_graph_layer_fwd_sparse(const PairAttnArgs& args, int n_src, cudaStrea
     const DeviceInfo* di = device_info();
     if (!di) return fail(DIGAT_E_CUDA, "digat_graph_layer_fwd: no CUDA device");
     const bool indexed = args.px_index != nullptr;
-    const int G = (indexed || args.adj_index != nullptr) ? 1
+    const bool training = args.alpha_out != nullptr || args.drop_keep != nullptr || args.relu_mask_out != nullptr;
+    const int G = (indexed || args.adj_index != nullptr || training) ? 1
                   : sparse_graphs_per_cta(args.n, args.D, args.B, di->sm_count, (size_t)di->max_smem_optin);
     SparseGeom g;
     sparse_geometry(args.n, args.D, G, &g);

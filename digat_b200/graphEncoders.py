@@ -162,18 +162,21 @@ def linear(A, W, bias=None, relu=False, M=None, K=None, lda=None, out=None, grou
     return out
 
 
-def build_graph_csr(adj, row_active=None, adj_index=None, G=None):
+def build_graph_csr(adj, row_active=None, adj_index=None, G=None, transpose=False):
     """CSR records of G graphs for graph_layer_fwd(csr=...) (digat_build_graph_csr): built once per batch, reused by every
     layer and by every pair that shares the graph.  adj [*,n,n] bool (read through adj_index [G] int32 when given),
-    row_active [G,n] uint8 or None.  Returns (rowptr [G,n+1] int16, meta [G,n*n] int16)."""
+    row_active [G,n] uint8 or None.  Returns (rowptr [G,n+1] int16, meta [G,n*n] int16); with transpose=True also
+    (colptr [G,n+1], cedge [G,n*n]), the column-major view the training backward walks."""
     n = adj.shape[1]
     if G is None:
         G = adj.shape[0] if adj_index is None else adj_index.shape[0]
     rowptr = torch.empty((G, n + 1), dtype=torch.int16, device=adj.device)
     meta = torch.empty((G, n * n), dtype=torch.int16, device=adj.device)
+    colptr = torch.empty((G, n + 1), dtype=torch.int16, device=adj.device) if transpose else None
+    cedge = torch.empty((G, n * n), dtype=torch.int16, device=adj.device) if transpose else None
     _lib.call('digat_build_graph_csr', adj.data_ptr(), _ptr(adj_index), _ptr(row_active), rowptr.data_ptr(), meta.data_ptr(),
-              G, n, _stream())
-    return rowptr, meta
+              _ptr(colptr), _ptr(cedge), G, n, _stream())
+    return (rowptr, meta, colptr, cedge) if transpose else (rowptr, meta)
 
 
 def graph_layer_fwd(P, a, adj, X, drop_keep=None, drop_scale=1.0, score_out=None, alpha_out=None, relu_mask_out=None,

@@ -31,7 +31,7 @@ extern "C" {
 #define DIGAT_E_CUDA        -2   /* a CUDA runtime/driver call or a launch failed */
 #define DIGAT_E_UNSUPPORTED -3   /* device is not sm_100 */
 
-#define DIGAT_ABI_VERSION 5
+#define DIGAT_ABI_VERSION 6
 
 int         digat_abi_version(void);
 const char* digat_last_error(void);
@@ -140,9 +140,14 @@ int digat_graph_layer_fwd(const float* P, int ldp, const float* a, const uint8_t
  *   graph g reads adjacency adj[adj_index ? adj_index[g] : g] ([*,n,n] bool) and row_active [G,n] (NULL = every row);
  *   rowptr [G, n+1] uint16: rowptr[i+1] & 0x7fff = end of row i's edge range (pruned rows are empty), bit 15 = row i has no
  *   edge at all (its range lists every node: the reference's uniform softmax);  meta [G, n*n] uint16: neighbour | row << 8.
- * In digat_graph_layer_fwd graph b uses record csr_index[b] (NULL: b): the pairs of one impression share one record. */
+ * In digat_graph_layer_fwd graph b uses record csr_index[b] (NULL: b): the pairs of one impression share one record.
+ * Transpose for the training backward (both NULL, or both given): colptr [G, n+1] uint16 = start of column j's range,
+ * cedge [G, n*n] uint16 = the CSR positions of the edges (i, j) ending in node j, rows ascending.
+ * Training (score_out / alpha_out / relu_mask_out given) with a CSR: score_out and alpha_out are then PER EDGE, in
+ * CSR order ([B, n*n] capacity, entries past rowptr[n] untouched) instead of dense [B,n,n]; they feed
+ * digat_graph_layer_bwd_csr. */
 int digat_build_graph_csr(const uint8_t* adj, const int32_t* adj_index, const uint8_t* row_active, uint16_t* rowptr,
-                          uint16_t* meta, int64_t G, int n, void* stream);
+                          uint16_t* meta, uint16_t* colptr, uint16_t* cedge, int64_t G, int n, void* stream);
 /* Vanilla-GAT layer of the reference's ablation encoders (graphEncoders.py:494-503, 511-520, 640-649, 807-816:
  * wo_interaction, news_graph_wo_inter, user_graph_wo_inter), inference:
  *   Y = relu(softmax_j(mask(leaky_relu(a1 . h_j + a2 . h_i))) * h) + X
@@ -254,6 +259,17 @@ int digat_add_inplace(const float* x, float* y, int64_t count, void* stream);
 int digat_graph_layer_bwd(const float* P, int ldp, const float* a, const uint8_t* adj, const float* score,
                           const float* alpha, const uint8_t* drop_keep, float drop_scale, const float* G,
                           float* dP, int lddp, float* da_partial, int B, int n, int D, void* stream);
+/* The same backward, edge-driven: only the E edges of each graph are evaluated (a masked pair has alpha = 0 and
+ * ds = 0), through the CSR and its transpose of digat_build_graph_csr (no adj_index / row_active: training evaluates
+ * every graph and row) and the per-edge edge_score / edge_alpha [B, n*n] the forward wrote when it was given the
+ * same CSR.  drop_keep stays the dense [B,n,n] mask.  Outputs as digat_graph_layer_bwd (every row of dP is written). */
+int digat_graph_layer_bwd_csr(const float* P, int ldp, const float* a, const uint16_t* csr_rowptr, const uint16_t* csr_meta,
+                              const uint16_t* csc_colptr, const uint16_t* csc_edge, const float* edge_score,
+                              const float* edge_alpha, const uint8_t* drop_keep, float drop_scale, const float* G, float* dP,
+                              int lddp, float* da_partial, int B, int n, int D, void* stream);
+/* 1 when graphs of n nodes and width D can train through the CSR pair (digat_graph_layer_fwd with a CSR and training
+ * outputs + digat_graph_layer_bwd_csr): both working sets fit one SM.  0: use the dense [B,n,n] score / alpha path. */
+int digat_graph_layer_csr_training_supported(int n, int D);
 
 /* Backward of digat_attention_pool_fwd.  alpha [B,m] saved by the forward; dout [B, ldg].
  * out: dF [B,m,D] dense (w.r.t. F; masked by F > 0 when resid_F is given), dresid [B,m,D] (only with resid_F),

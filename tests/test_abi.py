@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), 'libdigat_sm100.so does not export ' + n
     bound = set(_lib.SIGNATURES) | {'digat_last_error'}
     assert set(names) == bound, 'ctypes SIGNATURES out of sync with the header: %s' % (set(names) ^ bound)
-    assert _lib.load().digat_abi_version() == 5
+    assert _lib.load().digat_abi_version() == 6
 
 
 def test_no_gpu_fails_loudly():

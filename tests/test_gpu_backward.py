@@ -35,8 +35,10 @@ def _oracle_grads(sd, batch, dtype, wn, wu):
     return g, float(loss)
 
 
-@pytest.mark.parametrize('N,L,rows', [(3, 2, 12), (5, 1, 6)])
-def test_encoder_gradients_match_oracle(N, L, rows):
+@pytest.mark.parametrize('N,L,rows,edge_driven', [(3, 2, 12, True), (5, 1, 6, True), (3, 2, 12, False)])
+def test_encoder_gradients_match_oracle(N, L, rows, edge_driven, monkeypatch):
+    from digat_b200 import autograd_ops
+    monkeypatch.setattr(autograd_ops, 'TRAIN_EDGE_DRIVEN', edge_driven)
     from digat_b200 import synth
     from digat_b200.graphEncoders import DIGAT
     cfg = synth.make_config(SAG_neighbors=N, SAG_hops=2, graph_depth=L, dropout_rate=0.0)
@@ -76,16 +78,24 @@ def test_encoder_gradients_match_oracle(N, L, rows):
     assert not bad, 'gradients beyond %.0e of the fp64 oracle: %s' % (GRAD_TOL, bad)
 
 
-def test_graph_layer_dropout_mask_injection():
-    """alpha~ = alpha * keep / (1-p) inside the fused kernel, forward and backward, against plain torch with the SAME mask."""
+@pytest.mark.parametrize('edge_driven,n,D,density,p', [(False, 26, 400, 0.4, 0.2), (True, 26, 400, 0.4, 0.2),
+                                                        (True, 68, 400, 0.12, 0.2), (True, 68, 400, 1.0, 0.0),
+                                                        (True, 7, 36, 0.3, 0.5), (True, 33, 200, 0.2, 0.0)])
+def test_graph_layer_dropout_mask_injection(edge_driven, n, D, density, p):
+    """alpha~ = alpha * keep / (1-p) inside the fused kernel, forward and backward, against plain torch with the SAME mask;
+    dense [B,n,n] kernels and the edge-driven pair (CSR forward with per-edge outputs + digat_graph_layer_bwd_csr)."""
+    from digat_b200 import _lib
     from digat_b200.autograd_ops import GraphLayerFn
+    from digat_b200.graphEncoders import build_graph_csr
     g = torch.Generator().manual_seed(3)
-    B, n, D, p = 5, 26, 400, 0.2
+    B = 5
     P = (torch.randn(B * n, 3 * D, generator=g) * 0.5)
     a = torch.randn(D, generator=g) * 0.1
     X = torch.randn(B, n, D, generator=g)
-    adj = (torch.rand(B, n, n, generator=g) < 0.4) | torch.eye(n, dtype=torch.bool)
-    keep = torch.rand(B, n, n, generator=g) >= p
+    adj = (torch.rand(B, n, n, generator=g) < density) | torch.eye(n, dtype=torch.bool)
+    adj[1, n // 2, :] = False                    # an edge-less row: uniform weights, no gradient into the scores
+    adj[2, :, 0] = False                         # a node nobody attends to: dh, dU of that node are exactly zero
+    keep = (torch.rand(B, n, n, generator=g) >= p) if p > 0 else None
     dY = torch.randn(B, n, D, generator=g)
 
     def ref(P, a, X, dtype):
@@ -94,16 +104,23 @@ def test_graph_layer_dropout_mask_injection():
         s = (torch.relu(U.unsqueeze(1) + K2.unsqueeze(2)) * a).sum(-1)
         e = torch.nn.functional.leaky_relu(s, 0.2)
         al = torch.softmax(e.masked_fill(adj == 0, -1e9), dim=2)
-        al = al * keep.to(dtype) / (1 - p)
+        if keep is not None:
+            al = al * keep.to(dtype) / (1 - p)
         Y = torch.relu(torch.bmm(al, h)) + X
         Y.backward(dY.to(dtype))
         return Y.detach(), P.grad, a.grad, X.grad
 
     Y64, dP64, da64, dX64 = ref(P, a, X, torch.float64)
     Pc, ac, Xc = P.cuda().requires_grad_(True), a.cuda().requires_grad_(True), X.cuda().requires_grad_(True)
-    Y = GraphLayerFn.apply(Pc, ac, adj.cuda(), Xc, keep.cuda(), 1.0 / (1 - p))
+    csr = None
+    if edge_driven:
+        assert _lib.load().digat_graph_layer_csr_training_supported(n, D) == 1
+        csr = build_graph_csr(adj.cuda(), transpose=True)
+    Y = GraphLayerFn.apply(Pc, ac, adj.cuda(), Xc, None if keep is None else keep.cuda(), 1.0 / (1 - p), csr)
     Y.backward(dY.cuda())
     torch.cuda.synchronize()
+    if edge_driven:
+        assert float(Pc.grad.view(B, n, 3 * D)[2, 0, :2 * D].abs().max()) == 0.0
     assert rel_err(Y.detach().cpu().numpy(), Y64.numpy()) < 1e-5
     assert rel_err(Pc.grad.cpu().numpy(), dP64.numpy()) < 1e-4
     assert rel_err(ac.grad.cpu().numpy(), da64.numpy()) < 1e-4

@@ -186,6 +186,32 @@ def test_graph_csr_builder_matches_numpy():
             assert rowptr[g, i + 1] == (e | (0x8000 if uniform else 0)), (g, i)
 
 
+def test_graph_csr_transpose_lists_incoming_edges():
+    """colptr / cedge of digat_build_graph_csr: column j's range holds the CSR positions of the edges (i, j), rows ascending
+    (what digat_graph_layer_bwd_csr walks for dh_j and dU_j)."""
+    from digat_b200.graphEncoders import build_graph_csr
+    rng = np.random.Generator(np.random.PCG64(13))
+    for G, n, dens in ((6, 68, 0.1), (3, 128, 0.3), (4, 5, 0.5), (2, 33, 1.0)):
+        adj = rng.random((G, n, n)) < dens
+        adj[:, np.arange(n), np.arange(n)] = True
+        adj[0, n // 2, :] = False                                    # edge-less row: listed with every node (uniform softmax)
+        if n > 2:
+            adj[G - 1, :, 1] = False                                 # a node without incoming edges
+        rowptr, meta, colptr, cedge = build_graph_csr(torch.from_numpy(adj).cuda(), transpose=True)
+        torch.cuda.synchronize()
+        rowptr, meta = rowptr.cpu().numpy().view(np.uint16), meta.cpu().numpy().view(np.uint16)
+        colptr, cedge = colptr.cpu().numpy().view(np.uint16), cedge.cpu().numpy().view(np.uint16)
+        for g in range(G):
+            E = int(rowptr[g, n] & 0x7fff)
+            rows, cols = meta[g, :E] >> 8, meta[g, :E] & 255
+            assert colptr[g, 0] == 0 and colptr[g, n] == E
+            for j in range(n):
+                want = np.nonzero(cols == j)[0]                      # CSR order is row-major, so ascending ids = ascending rows
+                got = cedge[g, colptr[g, j]:colptr[g, j + 1]]
+                assert np.array_equal(got, want.astype(np.uint16)), (n, g, j)
+                assert np.all(np.diff(rows[got].astype(np.int64)) > 0)
+
+
 def test_precomputed_csr_is_bit_identical_to_in_kernel_csr():
     from tests.test_gpu_scoring import _setup
     cfg, sd, corpus, scorer = _setup(n_beh=50, seed=4)
