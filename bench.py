@@ -526,10 +526,11 @@ def train_record(args, rank, local_rank, world, dev, steps, cpu_baseline=True):
     # Gradient exchange: by default ONE all-reduce (mean) of the flat gradient buffer (digat_b200/training.py::FlatGradients)
     # inside the step, which -- unlike DDP's reducer hooks -- captures into the whole-step CUDA graph; --eager-train runs the
     # reference's arrangement instead (torch DistributedDataParallel around the model, trainer.py:19, eager).
-    from digat_b200.training import FlatGradients, GraphedTrainStep, broadcast_parameters
+    from digat_b200.training import FlatAdam, GraphedTrainStep, broadcast_parameters
     use_ddp = world > 1 and args.eager_train
     graphed = not args.eager_train
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=graphed)
+    # optimizer: the flat clip + Adam kernels (digat_b200/training.py::FlatAdam); the DDP arm keeps torch.optim.Adam
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4) if use_ddp else None
     bs, news_num = 64, 5
     warmup = max(args.warmup, 3)
     rng = np.random.Generator(np.random.PCG64(rank))
@@ -558,20 +559,21 @@ def train_record(args, rank, local_rank, world, dev, steps, cpu_baseline=True):
     else:
         fwd = model.forward_embeddings
         broadcast_parameters(model)
-        flat = FlatGradients(model.parameters())
+        flat = FlatAdam(model.parameters(), lr=1e-4, max_norm=1.0)
 
     def eager_step(inp):
         logits = fwd(*inp)
         loss = (-F.log_softmax(logits, dim=1).select(1, 0)).mean()
         if flat is None:
             opt.zero_grad(set_to_none=True)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+            opt.step()
         else:
-            flat.zero()
-        loss.backward()
-        if flat is not None:
+            flat.zero_grad()
+            loss.backward()
             flat.all_reduce_mean()                                # NCCL all-reduce over NVLink (no-op on one GPU)
-        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
-        opt.step()
+            flat.step()                                           # clip_grad_norm 1 + Adam, two launches
         return loss
 
     inputs = [make_step_inputs() for _ in range(warmup + steps)]
@@ -628,7 +630,7 @@ def train_record(args, rank, local_rank, world, dev, steps, cpu_baseline=True):
                'n_gpus': world, 'steps': steps, 'warmup': warmup, 'ms_per_step': ms / steps,
                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
                'config': {'workload': workload + ':train', 'behaviours_per_gpu': bs, 'candidates': news_num,
-                          'rows_per_gpu': bs * news_num, 'dropout': 0.2, 'optimizer': 'Adam + clip_grad_norm 1',
+                          'rows_per_gpu': bs * news_num, 'dropout': 0.2, 'optimizer': 'Adam + clip_grad_norm 1' + (' (torch.optim)' if use_ddp else ' (flat buffers, 2 kernel launches)'),
                           'execution': ('whole step (incl. the gradient all-reduce) replayed as one CUDA graph' if graphed
                                         else 'eager') + ('; ' + capture_note if capture_note else ''),
                           'parallelism': ('data parallel x%d, %s, %.1f MB fp32 per step' % (

@@ -48,6 +48,9 @@ SIGNATURES = {
     'digat_graph_layer_bwd_csr': [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   ctypes.c_float, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p],
     'digat_graph_layer_csr_training_supported': [c_int, c_int],
+    'digat_grad_sumsq': [c_void_p, c_int64, c_void_p, c_void_p, c_void_p],
+    'digat_adam_clip_step': [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p] + [ctypes.c_float] * 6
+                            + [c_void_p],
     'digat_attention_pool_bwd': [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                  c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     'digat_topic_segment_bwd': [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -50,7 +50,7 @@ def _planes(W, transposed):
     return hit[0]
 
 
-WGRAD_TC_MIN_ROWS = 256      # contraction lengths below this keep the exact-fp32 CUDA-core wgrad kernel
+WGRAD_TC_MIN_ROWS = 2048     # shorter contractions keep the exact-fp32 CUDA-core wgrad kernel (measured faster up to M ~ 2k: no transposes)
 WGRAD_SLICE = 512            # rows per split-K slice: 64 truncating accumulate steps per accumulator
 
 

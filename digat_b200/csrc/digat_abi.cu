@@ -15,6 +15,7 @@
 #include "gemm_wgrad.cuh"
 #include "builders.cuh"
 #include "news_encoder.cuh"
+#include "optimizer.cuh"
 
 using namespace digat;
 
@@ -108,6 +109,10 @@ int digat_debug_set_layer_mode(int mode) {
 int digat_debug_set_gemm_variant(int variant) {
     if (variant >= 6 && variant <= 8) {          // persistent kernel: 6 = independent CTAs, 7 = W multicast, 8 = 2-CTA MMA
         g_tc_cluster = variant - 6;
+        return DIGAT_OK;
+    }
+    if (variant >= 10 && variant <= 13) {        // tile width of the few-hundred-row GEMMs: 128 (off), 64, 32, 16
+        g_tc_small_bn = 128 >> (variant - 10);
         return DIGAT_OK;
     }
     g_tc_variant = variant;
@@ -233,6 +238,17 @@ int digat_graph_layer_bwd_csr(const float* P, int ldp, const float* a, const uin
                               int lddp, float* da_partial, int B, int n, int D, void* stream) {
     return launch_graph_layer_bwd_csr(P, ldp, a, csr_rowptr, csr_meta, csc_colptr, csc_edge, edge_score, edge_alpha, drop_keep,
                                       drop_scale, G, dP, lddp, da_partial, B, n, D, as_stream(stream));
+}
+
+int digat_grad_sumsq(const float* g, int64_t n, float* partials, float* step_counter, void* stream) {
+    return launch_grad_sumsq(g, n, partials, step_counter, as_stream(stream));
+}
+
+int digat_adam_clip_step(float* p, float* g, float* m, float* v, int64_t n, const float* partials, const float* step_counter,
+                         float* grad_norm_out, float max_norm, float lr, float beta1, float beta2, float eps,
+                         float weight_decay, void* stream) {
+    return launch_adam_clip_step(p, g, m, v, n, partials, step_counter, grad_norm_out, max_norm, lr, beta1, beta2, eps,
+                                 weight_decay, as_stream(stream));
 }
 
 int digat_graph_layer_csr_training_supported(int n, int D) { return graph_layer_csr_training_supported(n, D); }

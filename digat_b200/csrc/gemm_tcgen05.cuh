@@ -141,7 +141,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(&map_wlo)) : "memory");
         for (int s = 0; s < Cfg::STAGES; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&ready[s], kTcTransformThreads);
+            mbar_init(&ready[s], kTcTransformThreads / 32);      // one arrival per transform warp
             mbar_init(&empty[s], 1);
         }
         mbar_init(accum_full, 1);
@@ -240,7 +240,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             const long long t_issued = clock64();
             mbar_wait(accum_full, 0);
             const long long t_done = clock64();
-            if (blockIdx.x == 2 && (blockIdx.y % 997) == 5)
+            if (blockIdx.x == 2 && ((blockIdx.y % 997) == 5 || (gridDim.y < 6 && blockIdx.y == 1)))
                 printf("tile(%d,%d): first MMA issued +%lld, all issued +%lld, accum done +%lld\n", blockIdx.x, blockIdx.y,
                        t_first - t_start, t_issued - t_start, t_done - t_start);
 #endif
@@ -265,7 +265,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 lo[idx] = vl;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
-            mbar_arrive(&ready[s]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ready[s]);       // (128 per-thread arrivals serialised on the barrier: ~0.3 us per k-block)
         }
         // epilogue: this warp may touch TMEM lanes [32*(warp%4), +32).  Software-pipelined over 16-column groups: the
         // TMEM loads (and the row-group-bias loads) of group c+1 are in flight while group c is finished and stored.
@@ -341,7 +342,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         }
     }
 #ifdef DIGAT_TC_TIMING
-    if (threadIdx.x == 64 && blockIdx.x == 2 && (blockIdx.y % 997) == 5)
+    if (threadIdx.x == 64 && blockIdx.x == 2 && ((blockIdx.y % 997) == 5 || (gridDim.y < 6 && blockIdx.y == 1)))
         printf("tile(%d,%d): epilogue done +%lld\n", blockIdx.x, blockIdx.y, clock64() - t_start);
 #endif
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -392,6 +393,7 @@ inline int launch_tf32x3_cfg(const float* A, int lda, const float* W_hi, const f
 }
 
 static int g_tc_variant = 0;   // experiment switch (digat_debug_set_gemm_variant)
+static int g_tc_small_bn = 32, g_tc_small_rows = 1024;   // tile width for GEMMs of at most g_tc_small_rows rows (variants 10..13)
 
 template <int BN>
 int launch_tf32x3_pair(const float* A, int lda, const float* W_hi, const float* W_lo, int ldw, const float* bias,
@@ -435,6 +437,14 @@ inline int launch_linear_tf32x3(const float* A, int lda, const float* W_hi, cons
         return launch_tf32x3_persistent<208>(A, lda, W_hi, W_lo, ldw, bias, C, ldc, M, N, K, gb, st);
     if (variant == 3 && N % 240 == 0)                    // 2-CTA (cta_group::2) 256 x 240 tiles
         return launch_tf32x3_pair<240>(A, lda, W_hi, W_lo, ldw, bias, C, ldc, M, N, K, gb, st);
+    // a few hundred rows (the context projections of a training step, M = batch): three 128-row tiles x N/128 columns
+    // would occupy a dozen SMs, each pulling its whole A panel and 2 W planes through one SM's ingest; narrow tiles
+    // spread the same MMAs over N/32 times as many SMs (results are bit-identical: the k order per element is unchanged)
+    if ((variant == 0 || variant == 4) && M <= g_tc_small_rows && g_tc_small_bn != 128) {
+        if (g_tc_small_bn == 64) return launch_tf32x3_cfg<64, 1, true>(A, lda, W_hi, W_lo, ldw, bias, C, ldc, M, N, K, gb, st);
+        if (g_tc_small_bn == 16) return launch_tf32x3_cfg<16, 1, true>(A, lda, W_hi, W_lo, ldw, bias, C, ldc, M, N, K, gb, st);
+        return launch_tf32x3_cfg<32, 1, true>(A, lda, W_hi, W_lo, ldw, bias, C, ldc, M, N, K, gb, st);
+    }
     // small problems (few tiles) and odd widths: 128-wide tiles, two CTAs per SM (measured 1.45x faster at M = 4096);
     // the last N tile may be partial.  Large M keeps the 240-wide tile (fewer re-reads of A: measured 185 vs 158 TFLOP/s).
     if (variant == 2 || N % 80 != 0 || ((variant == 0 || variant == 4) && (!big || (N % 240 != 0 && N % 160 != 0))))

@@ -138,13 +138,26 @@ __global__ void groupsum_kernel(const float* __restrict__ in, int ld, float* __r
     *reinterpret_cast<float4*>(out + (size_t)b * cols + 4 * q) = s;
 }
 
-inline int wgrad_splits(int M) {
-    int s = (M + 2047) / 2048;
-    return s < 1 ? 1 : (s > 64 ? 64 : s);
+// Slices of the M reduction rows.  Enough CTAs to cover the SMs twice when the output has few tiles (the context
+// projections of a training step: a 400 x 400 weight gradient contracted over 320 rows is 16 tiles -- one slice would
+// leave 132 SMs idle for 40 serial k-steps), at least one slice per 2048 rows, at least 8 rows per slice, at most 64.
+inline int reduce_splits(int M, int64_t tiles) {
+    int64_t s = (296 + tiles - 1) / tiles;
+    const int64_t lo = (M + 2047) / 2048, hi = M / 8 < 1 ? 1 : (M / 8 > 64 ? 64 : M / 8);
+    if (s < lo) s = lo;
+    if (s > hi) s = hi;
+    return (int)(s < 1 ? 1 : s);
 }
+inline int wgrad_splits(int M, int N, int K) {
+    return reduce_splits(M, (int64_t)((N + kWgTile - 1) / kWgTile) * ((K + kWgTile - 1) / kWgTile));
+}
+inline int colsum_splits(int M, int N) { return reduce_splits(M, (N / 4 + 31) / 32); }
 
-// workspace floats needed by launch_linear_wgrad / launch_colsum
-inline int64_t wgrad_workspace_floats(int M, int N, int K) { return (int64_t)wgrad_splits(M) * N * K; }
+// workspace floats needed by launch_linear_wgrad (M, N, K) / launch_colsum (M, N, 1)
+inline int64_t wgrad_workspace_floats(int M, int N, int K) {
+    const int64_t a = (int64_t)wgrad_splits(M, N, K) * N * K, b = K == 1 ? (int64_t)colsum_splits(M, N) * N : 0;
+    return a > b ? a : b;
+}
 
 inline int launch_linear_wgrad(const float* dC, int lddc, const float* A, int lda, float* dW, float* workspace,
                                int M, int N, int K, cudaStream_t st) {
@@ -153,7 +166,7 @@ inline int launch_linear_wgrad(const float* dC, int lddc, const float* A, int ld
                   "digat_linear_wgrad: N, K, lddc, lda must be multiples of 4");
     DIGAT_REQUIRE(aligned16(dC) && aligned16(A) && aligned16(dW) && aligned16(workspace),
                   "digat_linear_wgrad: pointers must be 16-byte aligned");
-    const int splits = wgrad_splits(M);
+    const int splits = wgrad_splits(M, N, K);
     const int rows = ((M + splits - 1) / splits + kWgBK - 1) / kWgBK * kWgBK;
     dim3 grid((K + kWgTile - 1) / kWgTile, (N + kWgTile - 1) / kWgTile, splits);
     gemm_wgrad_kernel<<<grid, kWgThreads, 0, st>>>(dC, lddc, A, lda, workspace, M, N, K, rows);
@@ -166,7 +179,7 @@ inline int launch_colsum(const float* in, int ld, float* out, float* workspace, 
     DIGAT_REQUIRE(in && out && workspace, "digat_colsum: null pointer");
     DIGAT_REQUIRE(M > 0 && N > 0 && (N & 3) == 0 && (ld & 3) == 0 && aligned16(in) && aligned16(out) && aligned16(workspace),
                   "digat_colsum: N, ld must be multiples of 4 and pointers 16-byte aligned");
-    const int splits = wgrad_splits(M);
+    const int splits = colsum_splits(M, N);
     const int rows = (M + splits - 1) / splits;
     dim3 grid((N / 4 + 31) / 32, splits);
     colsum_kernel<<<grid, 256, 0, st>>>(in, ld, workspace, M, N, rows);

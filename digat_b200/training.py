@@ -44,6 +44,56 @@ class FlatGradients:
                 self.flat.div_(dist.get_world_size(group))
 
 
+class FlatAdam:
+    """Clip-by-global-norm + Adam (reference trainer.py:98-105: ``clip_grad_norm_`` then ``optim.Adam.step``) over flat buffers,
+    two kernel launches per step (digat_grad_sumsq, digat_adam_clip_step) instead of PyTorch's per-parameter kernels.
+
+    Parameters are re-pointed (``p.data``) into ONE flat fp32 buffer, their ``.grad`` into another (FlatGradients), and the two
+    moment buffers are flat too.  The step counter lives on the device, so the whole step captures into a CUDA graph.
+    ``weight_decay`` is torch.optim.Adam's L2 term and applies to every parameter (the reference's default is 0, config.py:36;
+    its bias / LayerNorm exemption list matches no parameter of this encoder except the biases)."""
+
+    def __init__(self, params, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_norm=1.0):
+        from . import _lib
+        self._lib = _lib
+        self.grads = FlatGradients(params)
+        self.params = self.grads.params
+        dev = self.params[0].device
+        if dev.type != 'cuda':
+            raise RuntimeError('FlatAdam needs CUDA parameters (digat_b200 has no CPU fallback)')
+        _lib.require_device(dev.index if dev.index is not None else torch.cuda.current_device())
+        n = self.grads.flat.numel()
+        self.flat_params = torch.empty(n, dtype=torch.float32, device=dev)
+        off = 0
+        with torch.no_grad():
+            for p in self.params:
+                view = self.flat_params[off:off + p.numel()].view_as(p)
+                view.copy_(p.data)
+                p.data = view
+                off += p.numel()
+        self.exp_avg = torch.zeros_like(self.flat_params)
+        self.exp_avg_sq = torch.zeros_like(self.flat_params)
+        self.partials = torch.zeros(1024, dtype=torch.float32, device=dev)
+        self.step_count = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.grad_norm = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.lr, self.betas, self.eps, self.weight_decay, self.max_norm = lr, betas, eps, weight_decay, max_norm
+
+    def zero_grad(self):
+        self.grads.zero()
+
+    def all_reduce_mean(self, group=None):
+        self.grads.all_reduce_mean(group)
+
+    def step(self):
+        stream = torch.cuda.current_stream().cuda_stream
+        g, n = self.grads.flat, self.grads.flat.numel()
+        self._lib.call('digat_grad_sumsq', g.data_ptr(), n, self.partials.data_ptr(), self.step_count.data_ptr(), stream)
+        self._lib.call('digat_adam_clip_step', self.flat_params.data_ptr(), g.data_ptr(), self.exp_avg.data_ptr(),
+                       self.exp_avg_sq.data_ptr(), n, self.partials.data_ptr(), self.step_count.data_ptr(),
+                       self.grad_norm.data_ptr(), float(self.max_norm or 0.0), float(self.lr), float(self.betas[0]),
+                       float(self.betas[1]), float(self.eps), float(self.weight_decay), stream)
+
+
 def broadcast_parameters(module, src=0, group=None):
     """What DDP does at construction: every rank starts from rank ``src``'s parameters and buffers."""
     import torch.distributed as dist
@@ -58,7 +108,7 @@ def broadcast_parameters(module, src=0, group=None):
 class GraphedTrainStep:
     def __init__(self, step_fn, example_inputs, warmup: int = 3, modules=(), distributed: bool = False):
         """step_fn(*inputs) -> loss tensor; it must do zero_grad / backward / optimizer.step itself.
-        NOTE: the ``warmup`` eager calls and the capture itself are real training steps on ``example_inputs``.
+        NOTE: the ``warmup`` eager calls are real training steps on ``example_inputs`` (the capture itself executes nothing).
         modules: nn.Modules whose DIGAT encoders keep a packed copy of the weights for inference -- a replayed optimizer
         step does not bump ``param._version``, so every replay invalidates those copies (DIGAT.invalidate_packed).
         distributed: the step contains NCCL collectives (FlatGradients.all_reduce_mean): capture in thread-local error mode

@@ -271,6 +271,18 @@ int digat_graph_layer_bwd_csr(const float* P, int ldp, const float* a, const uin
  * outputs + digat_graph_layer_bwd_csr): both working sets fit one SM.  0: use the dense [B,n,n] score / alpha path. */
 int digat_graph_layer_csr_training_supported(int n, int D);
 
+/* Optimizer step of reference trainer.py:98-105 (nn.utils.clip_grad_norm_ + optim.Adam.step) over FLAT fp32 buffers of n
+ * elements (parameters, gradients, exp_avg, exp_avg_sq laid out in the same order), two launches:
+ *   digat_grad_sumsq      partials [1024] = fixed-chunk partial sums of g^2; step_counter[0] += 1 (device-side Adam step
+ *                         count, so a CUDA-graph replay advances it; may be NULL)
+ *   digat_adam_clip_step  norm = sqrt(sum partials) (-> grad_norm_out[0], may be NULL); g *= min(1, max_norm / (norm + 1e-6))
+ *                         when max_norm > 0 (written back); then torch.optim.Adam's update with L2 weight_decay and the
+ *                         bias corrections 1 - beta^step_counter[0]. */
+int digat_grad_sumsq(const float* g, int64_t n, float* partials, float* step_counter, void* stream);
+int digat_adam_clip_step(float* p, float* g, float* m, float* v, int64_t n, const float* partials, const float* step_counter,
+                         float* grad_norm_out, float max_norm, float lr, float beta1, float beta2, float eps,
+                         float weight_decay, void* stream);
+
 /* Backward of digat_attention_pool_fwd.  alpha [B,m] saved by the forward; dout [B, ldg].
  * out: dF [B,m,D] dense (w.r.t. F; masked by F > 0 when resid_F is given), dresid [B,m,D] (only with resid_F),
  *      dv [B,D]. */
