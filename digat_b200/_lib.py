@@ -14,6 +14,7 @@ SIGNATURES = {
     'digat_device_check': [c_void_p],
     'digat_linear_f32': [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                          c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    'digat_gemm_f32_small': [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     'digat_split_tf32': [c_void_p, c_void_p, c_void_p, c_int64, c_void_p],
     'digat_linear_tf32x3': [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                             c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],

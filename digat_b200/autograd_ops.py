@@ -78,15 +78,52 @@ def wgrad(dC, A):
     return dW
 
 
+SMALL_GEMM_ROWS = 1024       # products with at most this many rows run on the exact-fp32 CUDA-core kernel (digat_gemm_f32_small)
+
+
+def _rows16(x):
+    """x usable as a strided operand (unit inner stride, 16-byte aligned rows) -- else a contiguous copy."""
+    if x.stride(1) == 1 and (x.stride(0) & 3) == 0 and (x.data_ptr() & 15) == 0 and x.stride(0) >= x.shape[1]:
+        return x
+    return x.contiguous()
+
+
+def _small_gemm(L, l_trans, R, r_trans, ldr, bias, I, J, C):
+    out = torch.empty((I, J), device=L.device, dtype=torch.float32)
+    _lib.call('digat_gemm_f32_small', L.data_ptr(), L.stride(0), int(l_trans), R.data_ptr(), ldr, int(r_trans), _ptr(bias),
+              out.data_ptr(), J, I, J, C, _stream())
+    return out
+
+
+def _weight_layout(W):
+    """W [N,K] as stored: (tensor to point at, 'nk' if rows of K are contiguous, 'kn' if W is the transposed view of a
+    row-major [K,N] matrix, leading dimension).  The context keys enter as ``K.weight.t()``: no copy is made of them."""
+    if W.stride(1) == 1 and (W.stride(0) & 3) == 0 and (W.data_ptr() & 15) == 0:
+        return W, 'nk', W.stride(0)
+    if W.stride(0) == 1 and (W.stride(1) & 3) == 0 and (W.data_ptr() & 15) == 0:
+        return W, 'kn', W.stride(1)
+    W = W.contiguous()
+    return W, 'nk', W.stride(0)
+
+
 class LinearFn(Function):
-    """out = A W^T (+bias) (+row-group bias); dA by the tcgen05 GEMM against W^T, dW by the exact-fp32 wgrad GEMM."""
+    """out = A W^T (+bias) (+row-group bias).  Few-hundred-row products (the context projections): all three directions on the
+    exact-fp32 CUDA-core kernel, operands read in place.  Large ones: dA by the tcgen05 GEMM against W^T, dW by split-K."""
 
     @staticmethod
     def forward(ctx, A, W, bias, group_bias, group_rows, group_col0):
-        A = A.contiguous()
-        ctx.save_for_backward(A, W)
+        M, K = A.shape
+        N = W.shape[0]
+        ctx.small = M <= SMALL_GEMM_ROWS and group_bias is None and (K & 3) == 0 and (N & 3) == 0
         ctx.has_bias = bias is not None
         ctx.group = None if group_bias is None else (group_rows, group_col0, group_bias.shape[1])
+        if ctx.small:
+            A = _rows16(A)
+            ctx.save_for_backward(A, W)
+            Wt, lay, ldw = _weight_layout(W)
+            return _small_gemm(A, False, Wt, lay == 'nk', ldw, None if bias is None else bias.contiguous(), M, N, K)
+        A = A.contiguous()
+        ctx.save_for_backward(A, W)
         return linear(A, _planes(W, False), None if bias is None else bias.contiguous(),
                       group_bias=None if group_bias is None else group_bias.contiguous(), group_rows=group_rows,
                       group_col0=group_col0)
@@ -94,10 +131,20 @@ class LinearFn(Function):
     @staticmethod
     def backward(ctx, dC):
         A, W = ctx.saved_tensors
-        dC = dC.contiguous()
         M, K = A.shape
         N = W.shape[0]
         dA = dW = db = dg = None
+        if ctx.small:
+            dC = _rows16(dC)
+            if ctx.needs_input_grad[0]:
+                Wt, lay, ldw = _weight_layout(W)
+                dA = _small_gemm(dC, False, Wt, lay == 'kn', ldw, None, M, K, N)
+            if ctx.needs_input_grad[1]:
+                dW = _small_gemm(dC, True, A, False, A.stride(0), None, N, K, M)
+            if ctx.has_bias and ctx.needs_input_grad[2]:
+                db = colsum(dC)
+            return dA, dW, db, None, None, None
+        dC = dC.contiguous()
         if ctx.needs_input_grad[0]:
             dA = linear(dC, _planes(W, True))
         if ctx.needs_input_grad[1]:

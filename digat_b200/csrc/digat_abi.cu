@@ -2,6 +2,7 @@
 // One translation unit: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_small.cuh"
 #include "gemm_tcgen05.cuh"
 #include "gemm_tcgen05_pair.cuh"
 #include "gemm_tcgen05_persistent.cuh"
@@ -46,6 +47,11 @@ int digat_linear_f32(const float* A, int lda, const float* W, int ldw, const flo
                      int group_cols, int group_ld, void* stream) {
     return launch_linear_f32(A, lda, W, ldw, bias, C, ldc, M, N, K, relu,
                              GroupBias{group_bias, group_rows, group_col0, group_cols, group_ld}, as_stream(stream));
+}
+
+int digat_gemm_f32_small(const float* L, int ldl, int l_trans, const float* R, int ldr, int r_trans, const float* bias,
+                         float* out, int ldo, int I, int J, int C, void* stream) {
+    return launch_gemm_f32_small(L, ldl, l_trans, R, ldr, r_trans, bias, out, ldo, I, J, C, as_stream(stream));
 }
 
 int digat_split_tf32(const float* W, float* W_hi, float* W_lo, int64_t count, void* stream) {

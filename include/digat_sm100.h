@@ -54,6 +54,14 @@ int digat_linear_f32(const float* A, int lda, const float* W, int ldw, const flo
                      const float* group_bias, int group_rows, int group_col0, int group_cols, int group_ld,
                      void* stream);
 
+/* Exact-fp32 CUDA-core product for the few-hundred-row projections of a training step (context queries / keys / gates,
+ * k3): out[I,J] = sum_c L(i,c) R(c,j) (+ bias[j]), no operand copies, sums in c order (deterministic).
+ *   l_trans = 0: L stored [I][C] (ldl >= C)      l_trans = 1: L stored [C][I] (ldl >= I)
+ *   r_trans = 0: R stored [C][J] (ldr >= J)      r_trans = 1: R stored [J][C] (ldr >= C)
+ * forward C = A W^T: (L, R) = (A, W) with r_trans;  dgrad dA = dC W: (dC, W);  wgrad dW = dC^T A: (dC, A) with l_trans.
+ * J, the leading dimensions and each operand's contiguous dimension must be multiples of 4. */
+int digat_gemm_f32_small(const float* L, int ldl, int l_trans, const float* R, int ldr, int r_trans, const float* bias,
+                         float* out, int ldo, int I, int J, int C, void* stream);
 /* Splits W into the two TF32 planes used by digat_linear_tf32x3: hi = rna_tf32(W), lo = rna_tf32(W - hi). */
 int digat_split_tf32(const float* W, float* W_hi, float* W_lo, int64_t count, void* stream);
 

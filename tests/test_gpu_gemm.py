@@ -213,3 +213,36 @@ def test_bf16_correction_scheme_with_multicast_and_scatter():
     sel = torch.randperm(M, generator=g)[:256]
     ref = A[sel].double().cpu() @ W.double().cpu().t() + b.double().cpu()
     assert rel_err(out[7][rows[sel].long()].cpu().numpy(), ref.numpy()) < 4e-6
+
+
+@pytest.mark.parametrize('M,N,K', [(320, 400, 400), (320, 800, 400), (7, 36, 52), (1, 4, 4), (1000, 400, 1200), (33, 400, 68)])
+def test_small_exact_fp32_gemm_three_products(M, N, K):
+    """digat_gemm_f32_small: forward (A W^T + bias), dgrad (dC W) and wgrad (dC^T A) read their operands in place -- strided
+    slices and the transposed view of a key matrix included -- and match fp64 to fp32 rounding of a K-term sum."""
+    from digat_b200.autograd_ops import lin
+    g = torch.Generator().manual_seed(M + N + K)
+    wide = torch.randn(M, K + 8, generator=g)
+    A = wide[:, 4:4 + K]                                   # strided rows (lda = K + 8), 16-byte aligned start
+    W = torch.randn(N, K, generator=g) * 0.2
+    Kw = torch.randn(K, N, generator=g) * 0.2              # a key matrix applied as lin(q, Kw.t())
+    bias = torch.randn(N, generator=g)
+    dC = torch.randn(M, N, generator=g)
+    for weight, use_bias in ((W, True), (Kw.t(), False)):
+        A64, W64 = A.double().requires_grad_(True), weight.double().requires_grad_(True)
+        b64 = bias.double().requires_grad_(True)
+        ref = A64 @ W64.t() + (b64 if use_bias else 0)
+        ref.backward(dC.double())
+        wide_c = wide.cuda().requires_grad_(True)
+        Wc = (W.cuda() if weight is W else Kw.cuda()).requires_grad_(True)
+        bc = bias.cuda().requires_grad_(True)
+        out = lin(wide_c[:, 4:4 + K], Wc if weight is W else Wc.t(), bc if use_bias else None)
+        out.backward(dC.cuda())
+        torch.cuda.synchronize()
+        tol = 4e-7 * max(K, M, N) ** 0.5 + 2e-7
+        assert rel_err(out.detach().cpu().numpy(), ref.detach().numpy()) < tol
+        assert rel_err(wide_c.grad[:, 4:4 + K].cpu().numpy(), A64.grad.numpy()) < tol
+        wg = Wc.grad if weight is W else Wc.grad.t()
+        assert rel_err(wg.cpu().numpy(), W64.grad.numpy()) < tol
+        if use_bias:
+            assert rel_err(bc.grad.cpu().numpy(), b64.grad.numpy()) < tol
+        assert float(wide_c.grad[:, :4].abs().max()) == 0.0

@@ -54,6 +54,12 @@ def main():
         t_simt = timeit(lambda: _lib.call('digat_linear_f32', A.data_ptr(), K, W.data_ptr(), K, 0, C.data_ptr(), N, M, N, K, 0,
                                           0, 1, 0, 0, 0, _stream()))
         t_split = timeit(lambda: PackedWeight(W))
+        out = torch.empty(M, N, device='cuda'); dA = torch.empty(M, K, device='cuda'); dW = torch.empty(N, K, device='cuda')
+        sg = lambda L, ldl, lt, R, ldr, rt, o, ldo, I, J, Cc: _lib.call('digat_gemm_f32_small', L.data_ptr(), ldl, lt, R.data_ptr(), ldr, rt, 0, o.data_ptr(), ldo, I, J, Cc, _stream())  # noqa: E731
+        t_sf = timeit(lambda: sg(A, K, 0, W, K, 1, out, N, M, N, K))
+        t_sd = timeit(lambda: sg(dC, N, 0, W, K, 0, dA, K, M, K, N))
+        t_sw = timeit(lambda: sg(dC, N, 1, A, K, 0, dW, K, N, K, M))
+        print('small fp32 kernel: fwd %.1f us  dgrad %.1f us  wgrad %.1f us' % (t_sf, t_sd, t_sw))
         old = autograd_ops.WGRAD_TC_MIN_ROWS
         autograd_ops.WGRAD_TC_MIN_ROWS = 256
         t_wg_tc = timeit(lambda: autograd_ops.wgrad(dC, A))
