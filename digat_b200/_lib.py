@@ -47,7 +47,8 @@ SIGNATURES = {
     'digat_graph_layer_bwd': [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_float, c_void_p,
                               c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p],
     'digat_graph_layer_bwd_csr': [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                  ctypes.c_float, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p],
+                                  ctypes.c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                  c_int, c_void_p],
     'digat_graph_layer_csr_training_supported': [c_int, c_int],
     'digat_grad_sumsq': [c_void_p, c_int64, c_void_p, c_void_p, c_void_p],
     'digat_adam_clip_step': [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p] + [ctypes.c_float] * 6
@@ -59,6 +60,7 @@ SIGNATURES = {
     'digat_reduce_workspace_floats': [c_int, c_int, c_int, c_void_p],
     'digat_linear_wgrad': [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     'digat_colsum': [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p],
+    'digat_transpose_f32': [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     'digat_groupsum': [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     'digat_logits': [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
     'digat_add_inplace': [c_void_p, c_void_p, c_int64, c_void_p],

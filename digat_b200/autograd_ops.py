@@ -56,7 +56,7 @@ WGRAD_SLICE = 512            # rows per split-K slice: 64 truncating accumulate 
 
 def wgrad(dC, A):
     """dW[N,K] = dC[M,N]^T A[M,K].  Long contractions run on the tensor cores: both operands are transposed so that the
-    contraction index is contiguous (K-major), A^T is split into its TF32 planes, digat_linear_tf32x3_splitk writes one
+    contraction index is contiguous (digat_transpose_f32; A^T directly as its TF32 planes), digat_linear_tf32x3_splitk writes one
     partial product per slice of WGRAD_SLICE rows and digat_colsum adds the slabs in slice order (deterministic)."""
     M, K = A.shape
     N = dC.shape[1]
@@ -66,11 +66,14 @@ def wgrad(dC, A):
         _lib.call('digat_linear_wgrad', dC.data_ptr(), dC.stride(0), A.data_ptr(), A.stride(0), dW.data_ptr(),
                   ws.data_ptr(), M, N, K, _stream())
         return dW
-    dCt = dC.t().contiguous()                                    # [N, M]
-    At = PackedWeight(A.t().contiguous())                        # [K, M] + TF32 planes
+    dCt = torch.empty((N, M), device=A.device, dtype=torch.float32)
+    At_hi = torch.empty((K, M), device=A.device, dtype=torch.float32)
+    At_lo = torch.empty((K, M), device=A.device, dtype=torch.float32)
+    _lib.call('digat_transpose_f32', dC.data_ptr(), dC.stride(0), dCt.data_ptr(), 0, M, M, N, _stream())
+    _lib.call('digat_transpose_f32', A.data_ptr(), A.stride(0), At_hi.data_ptr(), At_lo.data_ptr(), M, M, K, _stream())
     S = (M + WGRAD_SLICE - 1) // WGRAD_SLICE
     out = dW if S == 1 else torch.empty((S, N, K), device=A.device, dtype=torch.float32)
-    _lib.call('digat_linear_tf32x3_splitk', dCt.data_ptr(), M, At.hi.data_ptr(), At.lo.data_ptr(), M, out.data_ptr(), K,
+    _lib.call('digat_linear_tf32x3_splitk', dCt.data_ptr(), M, At_hi.data_ptr(), At_lo.data_ptr(), M, out.data_ptr(), K,
               N, K, M, S, N * K, _stream())
     if S > 1:
         ws = _workspace(S, N * K, 1, A.device)
@@ -194,12 +197,68 @@ class GraphLayerFn(Function):
             rowptr, meta, colptr, cedge = ctx.csr
             _lib.call('digat_graph_layer_bwd_csr', P.data_ptr(), P.stride(0), a.data_ptr(), rowptr.data_ptr(), meta.data_ptr(),
                       colptr.data_ptr(), cedge.data_ptr(), score.data_ptr(), alpha.data_ptr(), _ptr(keep), scale, G.data_ptr(),
-                      dP.data_ptr(), dP.stride(0), da_part.data_ptr(), B, n, D, _stream())
+                      0, dP.data_ptr(), dP.stride(0), da_part.data_ptr(), 0, 0, B, n, D, _stream())
         else:
             _lib.call('digat_graph_layer_bwd', P.data_ptr(), P.stride(0), a.data_ptr(), adj.data_ptr(), score.data_ptr(),
                       alpha.data_ptr(), _ptr(keep), scale, G.data_ptr(), dP.data_ptr(), dP.stride(0), da_part.data_ptr(),
                       B, n, D, _stream())
         return dP, colsum(da_part), None, dY, None, None, None
+
+
+class ProjectedGraphLayerFn(Function):
+    """One graph-attention layer as ONE autograd node: the projection P = [h | U | K2] = Xd [W; f1; f2]^T + [b; 0; 0] with
+    the row-group bias k3 on U, then the fused Eq. (8) layer with residual Xd.  Fusing the two lets the edge-driven backward
+    kernel hand over what the projection's backward would otherwise re-read the [B*n, 3D] gradient for: the bias gradient
+    (per-graph column sums of dh) and dk3 (per-graph column sums of dU); the relu mask is applied in that kernel too."""
+
+    @staticmethod
+    def forward(ctx, Xd, W, Wb, f1w, f2w, k3, a, adj, drop_keep, drop_scale, csr):
+        B, n, D = Xd.shape
+        Xd = Xd.contiguous()
+        Wcat = torch.cat([W, f1w, f2w], 0)
+        bcat = torch.cat([Wb, Wb.new_zeros(2 * D)], 0)
+        a = a.contiguous()
+        P = linear(Xd.view(B * n, D), _planes(Wcat, False), bcat, group_bias=k3.contiguous(), group_rows=n, group_col0=D)
+        score = torch.empty((B, n, n), device=Xd.device, dtype=torch.float32)
+        alpha = torch.empty((B, n, n), device=Xd.device, dtype=torch.float32)
+        rmask = torch.empty((B, n, D), device=Xd.device, dtype=torch.uint8)
+        Y = graph_layer_fwd(P, a, adj, Xd, drop_keep=drop_keep, drop_scale=drop_scale, score_out=score, alpha_out=alpha,
+                            relu_mask_out=rmask, csr=None if csr is None else (csr[0], csr[1], None))
+        ctx.save_for_backward(Xd, Wcat, P, a, adj, score, alpha, rmask)
+        ctx.drop = (drop_keep, float(drop_scale))
+        ctx.csr = csr
+        return Y
+
+    @staticmethod
+    def backward(ctx, dY):
+        Xd, Wcat, P, a, adj, score, alpha, rmask = ctx.saved_tensors
+        keep, scale = ctx.drop
+        B, n, D = Xd.shape
+        dev = Xd.device
+        dY = dY.contiguous()
+        dP = torch.empty_like(P)
+        da_part = torch.empty((B, D), device=dev, dtype=torch.float32)
+        if ctx.csr is not None:
+            rowptr, meta, colptr, cedge = ctx.csr
+            dh_sum = torch.empty((B, D), device=dev, dtype=torch.float32)
+            dk3 = torch.empty((B, D), device=dev, dtype=torch.float32)
+            _lib.call('digat_graph_layer_bwd_csr', P.data_ptr(), P.stride(0), a.data_ptr(), rowptr.data_ptr(), meta.data_ptr(),
+                      colptr.data_ptr(), cedge.data_ptr(), score.data_ptr(), alpha.data_ptr(), _ptr(keep), scale, dY.data_ptr(),
+                      rmask.data_ptr(), dP.data_ptr(), dP.stride(0), da_part.data_ptr(), dh_sum.data_ptr(), dk3.data_ptr(),
+                      B, n, D, _stream())
+            dWb = colsum(dh_sum)
+        else:
+            G = dY * rmask
+            _lib.call('digat_graph_layer_bwd', P.data_ptr(), P.stride(0), a.data_ptr(), adj.data_ptr(), score.data_ptr(),
+                      alpha.data_ptr(), _ptr(keep), scale, G.data_ptr(), dP.data_ptr(), dP.stride(0), da_part.data_ptr(),
+                      B, n, D, _stream())
+            dWb = colsum(dP[:, :D])
+            dk3 = torch.empty((B, D), device=dev, dtype=torch.float32)
+            _lib.call('digat_groupsum', dP.data_ptr(), dP.stride(0), dk3.data_ptr(), B, n, D, D, _stream())
+        dXd = linear(dP, _planes(Wcat, True)).view(B, n, D)
+        dXd += dY                                                      # the residual path
+        dWcat = wgrad(dP, Xd.view(B * n, D))
+        return dXd, dWcat[:D], dWb, dWcat[D:2 * D], dWcat[2 * D:], dk3, colsum(da_part), None, None, None, None
 
 
 class AttentionPoolFn(Function):
@@ -273,7 +332,6 @@ def encode_with_grad(enc, Xn, An, Mn, Xh, Au, Mc, ci):
     cand_Kt, ua_Kt, un_Kt = cand.K.weight.t(), ua.K.weight.t(), enc.user_news_K.weight.t()
     uq_W = torch.cat([enc.user_news_Q.weight, ua.Q.weight], 0)
     uq_b = torch.cat([enc.user_news_Q.bias, ua.Q.bias], 0)
-    zeros2D = torch.zeros(2 * D, device=dev)
 
     def news_ctx(X):
         l = X[:, 0, :]
@@ -311,10 +369,9 @@ def encode_with_grad(enc, Xn, An, Mn, Xh, Au, Mc, ci):
         av = getattr(enc, g + '_graph_attention_a')[i]
         Xd = drop(X, p / 2)                                        # the residual uses the DROPPED input (:145,153)
         k3 = lin(ctx_other, f3.weight, f3.bias)
-        P = lin(Xd.reshape(B * n, D), torch.cat([W.weight, f1.weight, f2.weight], 0), torch.cat([W.bias, zeros2D], 0),
-                group_bias=k3, group_rows=n, group_col0=D)
         keep = (torch.rand((B, n, n), device=dev) >= p) if p > 0 else None
-        return GraphLayerFn.apply(P, av.weight.reshape(D), adj, Xd, keep, 1.0 / (1.0 - p) if p > 0 else 1.0, csr_of[g])
+        return ProjectedGraphLayerFn.apply(Xd, W.weight, W.bias, f1.weight, f2.weight, k3, av.weight.reshape(D), adj, keep,
+                                           1.0 / (1.0 - p) if p > 0 else 1.0, csr_of[g])
 
     topic = drop(enc.topic_node_embedding.unsqueeze(0).expand(B, -1, -1), p / 2)
     Xu = torch.cat([Xh, topic], 1)

@@ -240,10 +240,11 @@ int digat_graph_layer_bwd(const float* P, int ldp, const float* a, const uint8_t
 
 int digat_graph_layer_bwd_csr(const float* P, int ldp, const float* a, const uint16_t* csr_rowptr, const uint16_t* csr_meta,
                               const uint16_t* csc_colptr, const uint16_t* csc_edge, const float* edge_score,
-                              const float* edge_alpha, const uint8_t* drop_keep, float drop_scale, const float* G, float* dP,
-                              int lddp, float* da_partial, int B, int n, int D, void* stream) {
+                              const float* edge_alpha, const uint8_t* drop_keep, float drop_scale, const float* G,
+                              const uint8_t* relu_mask, float* dP, int lddp, float* da_partial, float* dh_sum, float* du_sum,
+                              int B, int n, int D, void* stream) {
     return launch_graph_layer_bwd_csr(P, ldp, a, csr_rowptr, csr_meta, csc_colptr, csc_edge, edge_score, edge_alpha, drop_keep,
-                                      drop_scale, G, dP, lddp, da_partial, B, n, D, as_stream(stream));
+                                      drop_scale, G, relu_mask, dP, lddp, da_partial, dh_sum, du_sum, B, n, D, as_stream(stream));
 }
 
 int digat_grad_sumsq(const float* g, int64_t n, float* partials, float* step_counter, void* stream) {
@@ -285,6 +286,10 @@ int digat_linear_wgrad(const float* dC, int lddc, const float* A, int lda, float
 
 int digat_colsum(const float* in, int ld, float* out, float* workspace, int M, int N, void* stream) {
     return launch_colsum(in, ld, out, workspace, M, N, as_stream(stream));
+}
+
+int digat_transpose_f32(const float* in, int ld_in, float* out, float* out_lo, int ld_out, int rows, int cols, void* stream) {
+    return launch_transpose(in, ld_in, out, out_lo, ld_out, rows, cols, as_stream(stream));
 }
 
 int digat_groupsum(const float* in, int ld, float* out, int groups, int rows, int col0, int cols, void* stream) {

@@ -175,16 +175,102 @@ inline int launch_linear_wgrad(const float* dC, int lddc, const float* A, int ld
     return check_launch("digat_linear_wgrad");
 }
 
-inline int launch_colsum(const float* in, int ld, float* out, float* workspace, int M, int N, cudaStream_t st) {
+// out[n] = sum_m in[m, n] in ONE launch for a few hundred rows (bias gradients of the context projections, the per-graph
+// partials of an attention-vector gradient): 32 row lanes x 8 column quads per CTA, every lane's loads independent, the 32
+// lane sums added in lane order.  (Two launches -- slices, then their sum -- cost 16 us for a [320 x 400] matrix.)
+constexpr int kColsumSmallRows = 2048;
+__global__ void __launch_bounds__(256)
+colsum_small_kernel(const float* __restrict__ in, int ld, float* __restrict__ out, int M, int N, int accumulate) {
+    __shared__ float4 s_acc[32][8];
+    const int cq = threadIdx.x & 7, rl = threadIdx.x >> 3;
+    const int col = (blockIdx.x * 8 + cq) * 4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col < N) {
+#pragma unroll 8
+        for (int m = rl; m < M; m += 32) {
+            const float4 v = *reinterpret_cast<const float4*>(in + (size_t)m * ld + col);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+    }
+    s_acc[rl][cq] = s;
+    __syncthreads();
+    if (rl == 0 && col < N) {
+#pragma unroll
+        for (int r = 1; r < 32; ++r) {
+            const float4 v = s_acc[r][cq];
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        float4* dst = reinterpret_cast<float4*>(out + col);
+        if (accumulate) {
+            const float4 o = *dst;
+            s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+        }
+        *dst = s;
+    }
+}
+
+inline int launch_colsum(const float* in, int ld, float* out, float* workspace, int M, int N, cudaStream_t st,
+                         int accumulate = 0) {
     DIGAT_REQUIRE(in && out && workspace, "digat_colsum: null pointer");
     DIGAT_REQUIRE(M > 0 && N > 0 && (N & 3) == 0 && (ld & 3) == 0 && aligned16(in) && aligned16(out) && aligned16(workspace),
                   "digat_colsum: N, ld must be multiples of 4 and pointers 16-byte aligned");
+    if (M <= kColsumSmallRows && N <= 65536) {
+        colsum_small_kernel<<<(N / 4 + 7) / 8, 256, 0, st>>>(in, ld, out, M, N, accumulate);
+        return check_launch("digat_colsum");
+    }
+    DIGAT_REQUIRE(!accumulate, "digat_colsum: accumulate is supported for at most %d rows", kColsumSmallRows);
     const int splits = colsum_splits(M, N);
     const int rows = (M + splits - 1) / splits;
     dim3 grid((N / 4 + 31) / 32, splits);
-    colsum_kernel<<<grid, 256, 0, st>>>(in, ld, workspace, M, N, rows);
-    reduce_partials_kernel<<<(unsigned)((N / 4 + 255) / 256), 256, 0, st>>>(workspace, out, splits, N);
+    colsum_kernel<<<grid, 256, 0, st>>>(in, ld, splits == 1 ? out : workspace, M, N, rows);     // one slice: no second pass
+    if (splits > 1) reduce_partials_kernel<<<(unsigned)((N / 4 + 255) / 256), 256, 0, st>>>(workspace, out, splits, N);
     return check_launch("digat_colsum");
+}
+
+// out[c, r] = in[r, c] (32 x 32 tiles through shared memory, both sides coalesced); with out_lo the transposed matrix is
+// written as its two TF32 planes (hi = rna_tf32(x), lo = rna_tf32(x - hi)) -- the operands of the split-K weight-gradient
+// GEMM, whose contraction index (the rows of dC and A) must be the contiguous one.
+__global__ void __launch_bounds__(256)
+transpose_kernel(const float* __restrict__ in, int ld_in, float* __restrict__ out, float* __restrict__ out_lo, int ld_out,
+                 int rows, int cols) {
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r = r0 + ty + 8 * k, c = c0 + tx;
+        tile[ty + 8 * k][tx] = (r < rows && c < cols) ? in[(size_t)r * ld_in + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = c0 + ty + 8 * k, r = r0 + tx;
+        if (c < cols && r < rows) {
+            const float x = tile[tx][ty + 8 * k];
+            if (out_lo != nullptr) {
+                uint32_t h;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+                const float hf = __uint_as_float(h);
+                uint32_t l;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(x - hf));
+                out[(size_t)c * ld_out + r] = hf;
+                out_lo[(size_t)c * ld_out + r] = __uint_as_float(l);
+            } else {
+                out[(size_t)c * ld_out + r] = x;
+            }
+        }
+    }
+}
+
+inline int launch_transpose(const float* in, int ld_in, float* out, float* out_lo, int ld_out, int rows, int cols,
+                            cudaStream_t st) {
+    if (rows <= 0 || cols <= 0) return DIGAT_OK;
+    DIGAT_REQUIRE(in && out, "digat_transpose_f32: null pointer");
+    DIGAT_REQUIRE(ld_in >= cols && ld_out >= rows, "digat_transpose_f32: leading dimension too small");
+    dim3 grid((rows + 31) / 32, (cols + 31) / 32);
+    DIGAT_REQUIRE(grid.y <= 65535, "digat_transpose_f32: too many columns (%d)", cols);
+    transpose_kernel<<<grid, 256, 0, st>>>(in, ld_in, out, out_lo, ld_out, rows, cols);
+    return check_launch("digat_transpose_f32");
 }
 
 inline int launch_groupsum(const float* in, int ld, float* out, int groups, int rows, int col0, int cols, cudaStream_t st) {

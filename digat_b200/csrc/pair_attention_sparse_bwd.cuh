@@ -10,10 +10,12 @@
 //   pass C  (U, K2 tiles)  x_ed = U_jd + K2_id  (the forward's IEEE add on the same operands: the same relu mask)
 //                          dK2_id = a_d sum_{e in row i}    ds_e 1[x_ed > 0]      8 lanes per node, its ROW
 //                          dU_jd  = a_d sum_{e in column j} ds_e 1[x_ed > 0]      8 lanes per node, its COLUMN
-//                          da_d  += sum_e ds_e relu(x_ed)                          per-CTA shared-memory accumulation
+//                          da_d   = sum_e ds_e relu(x_ed)                          per-graph partial [B,D]
+// Optional extras for the fused projection+layer backward: the saved relu mask of Z is applied to the staged dY tile (no
+// separate G = dY * mask pass), and the per-graph column sums of dh and dU come out as [B,D] arrays (the bias gradient is
+// their sum over graphs; sum_j dU_j IS dk3) so that nobody has to re-read the [B*n, 3D] dP for them.
 // Same skeleton as the forward: one CTA per graph, a producer warp streams [n][32]-feature tile pairs through a TMA ring
-// (SWIZZLE_128B), consumer warps synchronise through the ring's mbarriers.  All sums run in a fixed order except da (float
-// atomics inside the CTA, as in the dense kernel).
+// (SWIZZLE_128B), consumer warps synchronise through the ring's mbarriers.  Every sum runs in a fixed order (deterministic).
 #pragma once
 #include "common.cuh"
 #include "tma.cuh"
@@ -27,6 +29,8 @@ constexpr int kSbwdDc = 32;
 
 struct SparseBwdArgs {
     const float* P; int ldp; const float* a; const float* G;
+    const uint8_t* relu_mask;      // [B,n,D] or null: G is dY and the saved mask of Z > 0 is applied to the staged tile
+    float* dh_sum; float* du_sum;  // [B,D] each or null: per-graph column sums of dh (-> bias gradient) and dU (= dk3)
     const uint16_t* rowptr; const uint16_t* meta; const uint16_t* colptr; const uint16_t* cedge;
     const float* e_score; const float* e_alpha; const uint8_t* drop_keep; float drop_scale;
     float* dP; int lddp; float* da_partial;
@@ -52,8 +56,8 @@ graph_layer_bwd_sparse_kernel(const __grid_constant__ CUtensorMap mapG, const __
     uint64_t* full = reinterpret_cast<uint64_t*>(ring + kSbwdBufs * unit_floats);
     uint64_t* empty = full + kSbwdMaxBufs;
     float* a_s = reinterpret_cast<float*>(empty + kSbwdMaxBufs);               // [D]
-    float* da_s = a_s + D;                                                  // [D]
-    float* alt = da_s + D;                                                  // [n*n] alpha~ per edge
+    float* parts = a_s + D;                                                 // [2 parities][3 kinds][warps][32] column-sum partials
+    float* alt = parts + 2 * 3 * (kSparseConsumers / 32) * kSbwdDc;         // [n*n] alpha~ per edge
     float* dal = alt + n * n;                                               // [n*n] dalpha~ per edge, later ds
     int* rowptr = reinterpret_cast<int*>(dal + n * n);                      // [n+1]
     int* colptr = rowptr + (n + 1);                                         // [n+1]
@@ -92,7 +96,7 @@ graph_layer_bwd_sparse_kernel(const __grid_constant__ CUtensorMap mapG, const __
     }
 
     // ---------------------------------------------------------------------- setup: CSR + transpose, alpha~, zeroed accumulators
-    for (int i = tid; i < D; i += kSparseConsumers) { a_s[i] = p.a[i]; da_s[i] = 0.f; }
+    for (int i = tid; i < D; i += kSparseConsumers) a_s[i] = p.a[i];
     {
         const uint16_t* rp = p.rowptr + (size_t)b * (n + 1);
         const uint16_t* cp = p.colptr + (size_t)b * (n + 1);
@@ -129,6 +133,29 @@ graph_layer_bwd_sparse_kernel(const __grid_constant__ CUtensorMap mapG, const __
         return ro + ((q * 16u) ^ (((ro >> 7) & 7u) << 4));
     };
 
+    // Per-graph column sums (dh -> bias gradient, dU -> dk3, da) without atomics: a thread sums its nodes, the four node
+    // groups of a warp are folded with shuffles, lanes 0..7 park the warp's float4 in `parts`, and after a consumer barrier
+    // eight threads add the ten warps in order.  `parts` alternates by unit parity, so one barrier per unit is enough.
+    constexpr int kWarps = kSparseConsumers / 32;
+    auto park = [&](int parity, int kind, float4 v) {
+        v.x += __shfl_xor_sync(0xffffffffu, v.x, 8);  v.y += __shfl_xor_sync(0xffffffffu, v.y, 8);
+        v.z += __shfl_xor_sync(0xffffffffu, v.z, 8);  v.w += __shfl_xor_sync(0xffffffffu, v.w, 8);
+        v.x += __shfl_xor_sync(0xffffffffu, v.x, 16); v.y += __shfl_xor_sync(0xffffffffu, v.y, 16);
+        v.z += __shfl_xor_sync(0xffffffffu, v.z, 16); v.w += __shfl_xor_sync(0xffffffffu, v.w, 16);
+        if (lane < 8) *reinterpret_cast<float4*>(parts + ((parity * 3 + kind) * kWarps + warp) * kSbwdDc + 4 * lane) = v;
+    };
+    auto fold = [&](int parity, int kind, float* dst, int c0, int wq) {       // call after consumer_sync(); tid < 8 writes
+        if (tid < wq) {
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) {
+                const float4 v = *reinterpret_cast<const float4*>(parts + ((parity * 3 + kind) * kWarps + w) * kSbwdDc + 4 * tid);
+                t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+            }
+            *reinterpret_cast<float4*>(dst + (size_t)b * D + c0 + 4 * tid) = t;
+        }
+    };
+
     // ---------------------------------------------------------------------- pass A: dalpha~ per edge, dh per node
     for (int l = 0; l < g.nch; ++l) {
         const int buf = l % kSbwdBufs;
@@ -136,6 +163,20 @@ graph_layer_bwd_sparse_kernel(const __grid_constant__ CUtensorMap mapG, const __
         const int wq = min(kSbwdDc, D - c0) >> 2;
         const uint32_t goff = (uint32_t)(buf * unit_floats) * 4u, hoff = goff + (uint32_t)g.tile_floats * 4u;
         mbar_wait(&full[buf], (uint32_t)(l / kSbwdBufs) & 1u);
+        if (p.relu_mask != nullptr) {                               // G = dY * 1[Z > 0], applied to the staged dY tile
+            const uint8_t* mk = p.relu_mask + (size_t)b * n * D + c0;
+            for (int idx = tid; idx < n * 8; idx += kSparseConsumers) {
+                const int row = idx >> 3, q = idx & 7;
+                if (q < wq) {
+                    const uchar4 m = *reinterpret_cast<const uchar4*>(mk + (size_t)row * D + 4 * q);
+                    float4* cell = reinterpret_cast<float4*>(smem_raw + swz(goff, row, q));
+                    float4 v = *cell;
+                    v.x = m.x ? v.x : 0.f; v.y = m.y ? v.y : 0.f; v.z = m.z ? v.z : 0.f; v.w = m.w ? v.w : 0.f;
+                    *cell = v;
+                }
+            }
+            consumer_sync();
+        }
         for (int e = tid; e < E; e += kSparseConsumers) {
             const uint32_t mt = meta[e];
             float acc = 0.f;
@@ -147,6 +188,7 @@ graph_layer_bwd_sparse_kernel(const __grid_constant__ CUtensorMap mapG, const __
             }
             dal[e] += acc;
         }
+        float4 dh_tot = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int j = warp * 4 + grp; j < n; j += kNodeStep) {       // dh_j = sum over the incoming edges (column j)
             if (q8 < wq) {
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -157,10 +199,17 @@ graph_layer_bwd_sparse_kernel(const __grid_constant__ CUtensorMap mapG, const __
                     acc.x = fmaf(al, gi.x, acc.x); acc.y = fmaf(al, gi.y, acc.y); acc.z = fmaf(al, gi.z, acc.z); acc.w = fmaf(al, gi.w, acc.w);
                 }
                 *reinterpret_cast<float4*>(p.dP + ((size_t)b * n + j) * p.lddp + c0 + 4 * q8) = acc;
+                dh_tot.x += acc.x; dh_tot.y += acc.y; dh_tot.z += acc.z; dh_tot.w += acc.w;
             }
         }
+        if (p.relu_mask != nullptr) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // our writes, then TMA's
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[buf]);
+        if (p.dh_sum != nullptr) {
+            park(l & 1, 0, dh_tot);
+            consumer_sync();
+            fold(l & 1, 0, p.dh_sum, c0, wq);
+        }
     }
     consumer_sync();
 
@@ -198,6 +247,7 @@ graph_layer_bwd_sparse_kernel(const __grid_constant__ CUtensorMap mapG, const __
         const int wq = min(kSbwdDc, D - c0) >> 2;
         const uint32_t uoff = (uint32_t)(buf * unit_floats) * 4u, koff = uoff + (uint32_t)g.tile_floats * 4u;
         mbar_wait(&full[buf], (uint32_t)(l / kSbwdBufs) & 1u);
+        float4 da_tot = make_float4(0.f, 0.f, 0.f, 0.f), du_tot = make_float4(0.f, 0.f, 0.f, 0.f);
         if (q8 < wq) {
             const float4 av = *reinterpret_cast<const float4*>(a_s + c0 + 4 * q8);
             float4 da_acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -216,10 +266,7 @@ graph_layer_bwd_sparse_kernel(const __grid_constant__ CUtensorMap mapG, const __
                 *reinterpret_cast<float4*>(p.dP + ((size_t)b * n + i) * p.lddp + 2 * D + c0 + 4 * q8) =
                     make_float4(av.x * acc.x, av.y * acc.y, av.z * acc.z, av.w * acc.w);
             }
-            atomicAdd(&da_s[c0 + 4 * q8 + 0], da_acc.x);
-            atomicAdd(&da_s[c0 + 4 * q8 + 1], da_acc.y);
-            atomicAdd(&da_s[c0 + 4 * q8 + 2], da_acc.z);
-            atomicAdd(&da_s[c0 + 4 * q8 + 3], da_acc.w);
+            da_tot = da_acc;
             for (int j = warp * 4 + grp; j < n; j += kNodeStep) {
                 const float4 u = *reinterpret_cast<const float4*>(smem_raw + swz(uoff, j, q8));
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -232,21 +279,25 @@ graph_layer_bwd_sparse_kernel(const __grid_constant__ CUtensorMap mapG, const __
                     if (__fadd_rn(u.z, k2.z) > 0.f) acc.z += ds;
                     if (__fadd_rn(u.w, k2.w) > 0.f) acc.w += ds;
                 }
-                *reinterpret_cast<float4*>(p.dP + ((size_t)b * n + j) * p.lddp + D + c0 + 4 * q8) =
-                    make_float4(av.x * acc.x, av.y * acc.y, av.z * acc.z, av.w * acc.w);
+                const float4 du = make_float4(av.x * acc.x, av.y * acc.y, av.z * acc.z, av.w * acc.w);
+                *reinterpret_cast<float4*>(p.dP + ((size_t)b * n + j) * p.lddp + D + c0 + 4 * q8) = du;
+                du_tot.x += du.x; du_tot.y += du.y; du_tot.z += du.z; du_tot.w += du.w;
             }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[buf]);
+        park(l & 1, 2, da_tot);
+        if (p.du_sum != nullptr) park(l & 1, 1, du_tot);
+        consumer_sync();
+        fold(l & 1, 2, p.da_partial, c0, wq);
+        if (p.du_sum != nullptr) fold(l & 1, 1, p.du_sum, c0, wq);
     }
-    consumer_sync();
-    for (int i = tid; i < D; i += kSparseConsumers) p.da_partial[(size_t)b * D + i] = da_s[i];
 }
 
 inline void sparse_bwd_geometry(int n, int D, SparseBwdGeom* g) {
     g->nch = (D + kSbwdDc - 1) / kSbwdDc;
     g->tile_floats = ((n * kSbwdDc * 4 + 1023) / 1024) * 1024 / 4;
-    const size_t rest = (size_t)2 * kSbwdMaxBufs * 8 + (size_t)2 * D * 4 + (size_t)2 * n * n * 4 + (size_t)2 * (n + 1) * 4 +
+    const size_t rest = (size_t)2 * kSbwdMaxBufs * 8 + (size_t)D * 4 + (size_t)2 * 3 * (kSparseConsumers / 32) * kSbwdDc * 4 + (size_t)2 * n * n * 4 + (size_t)2 * (n + 1) * 4 +
                         (size_t)2 * n * n * 2 + (size_t)n + 64;
     const size_t unit = (size_t)2 * g->tile_floats * 4;
     constexpr size_t kTwoPerSm = 113 * 1024;                       // two CTAs per SM (228 KB, 1 KB reserved per CTA)
@@ -256,8 +307,9 @@ inline void sparse_bwd_geometry(int n, int D, SparseBwdGeom* g) {
 
 inline int launch_graph_layer_bwd_csr(const float* P, int ldp, const float* a, const uint16_t* rowptr, const uint16_t* meta,
                                       const uint16_t* colptr, const uint16_t* cedge, const float* e_score, const float* e_alpha,
-                                      const uint8_t* drop_keep, float drop_scale, const float* G, float* dP, int lddp,
-                                      float* da_partial, int B, int n, int D, cudaStream_t st) {
+                                      const uint8_t* drop_keep, float drop_scale, const float* G, const uint8_t* relu_mask,
+                                      float* dP, int lddp, float* da_partial, float* dh_sum, float* du_sum, int B, int n, int D,
+                                      cudaStream_t st) {
     if (B == 0) return DIGAT_OK;
     DIGAT_REQUIRE(P && a && rowptr && meta && colptr && cedge && e_score && e_alpha && G && dP && da_partial,
                   "digat_graph_layer_bwd_csr: null pointer");
@@ -278,7 +330,10 @@ inline int launch_graph_layer_bwd_csr(const float* P, int ldp, const float* a, c
     int rc;
     if ((rc = make_tensor_map_2d(&mapG, G, (int64_t)B * n, D, D, n, kSbwdDc, CU_TENSOR_MAP_SWIZZLE_128B)) != DIGAT_OK) return rc;
     if ((rc = make_tensor_map_2d(&mapP, P, (int64_t)B * n, 3 * D, ldp, n, kSbwdDc, CU_TENSOR_MAP_SWIZZLE_128B)) != DIGAT_OK) return rc;
-    SparseBwdArgs args{P, ldp, a, G, rowptr, meta, colptr, cedge, e_score, e_alpha, drop_keep, drop_scale, dP, lddp, da_partial, B, n, D};
+    DIGAT_REQUIRE(aligned16(da_partial) && (!dh_sum || aligned16(dh_sum)) && (!du_sum || aligned16(du_sum)),
+                  "digat_graph_layer_bwd_csr: da_partial / dh_sum / du_sum must be 16-byte aligned");
+    SparseBwdArgs args{P, ldp, a, G, relu_mask, dh_sum, du_sum, rowptr, meta, colptr, cedge, e_score, e_alpha, drop_keep, drop_scale,
+                       dP, lddp, da_partial, B, n, D};
     if (int rc_ = ensure_dynamic_smem(graph_layer_bwd_sparse_kernel, g.smem)) return rc_;
     graph_layer_bwd_sparse_kernel<<<B, kSparseThreads, g.smem, st>>>(mapG, mapP, args, g);
     return check_launch("digat_graph_layer_bwd_csr");

@@ -270,11 +270,16 @@ int digat_graph_layer_bwd(const float* P, int ldp, const float* a, const uint8_t
 /* The same backward, edge-driven: only the E edges of each graph are evaluated (a masked pair has alpha = 0 and
  * ds = 0), through the CSR and its transpose of digat_build_graph_csr (no adj_index / row_active: training evaluates
  * every graph and row) and the per-edge edge_score / edge_alpha [B, n*n] the forward wrote when it was given the
- * same CSR.  drop_keep stays the dense [B,n,n] mask.  Outputs as digat_graph_layer_bwd (every row of dP is written). */
+ * same CSR.  drop_keep stays the dense [B,n,n] mask.  Outputs as digat_graph_layer_bwd (every row of dP is written).
+ * Optional (NULL = off): relu_mask [B,n,D] -- G is then the raw dY and the forward's saved mask is applied in-kernel;
+ * dh_sum, du_sum [B,D] -- per-graph column sums of the dh and dU blocks of dP (sum over graphs of dh_sum = the gradient of
+ * the projection bias; du_sum = dk3, the gradient of the row-group bias), so nothing re-reads dP for them.
+ * All sums run in a fixed order (deterministic). */
 int digat_graph_layer_bwd_csr(const float* P, int ldp, const float* a, const uint16_t* csr_rowptr, const uint16_t* csr_meta,
                               const uint16_t* csc_colptr, const uint16_t* csc_edge, const float* edge_score,
-                              const float* edge_alpha, const uint8_t* drop_keep, float drop_scale, const float* G, float* dP,
-                              int lddp, float* da_partial, int B, int n, int D, void* stream);
+                              const float* edge_alpha, const uint8_t* drop_keep, float drop_scale, const float* G,
+                              const uint8_t* relu_mask, float* dP, int lddp, float* da_partial, float* dh_sum, float* du_sum,
+                              int B, int n, int D, void* stream);
 /* 1 when graphs of n nodes and width D can train through the CSR pair (digat_graph_layer_fwd with a CSR and training
  * outputs + digat_graph_layer_bwd_csr): both working sets fit one SM.  0: use the dense [B,n,n] score / alpha path. */
 int digat_graph_layer_csr_training_supported(int n, int D);
@@ -311,6 +316,11 @@ int digat_linear_wgrad(const float* dC, int lddc, const float* A, int lda, float
                        int M, int N, int K, void* stream);
 /* out[n] = sum_m in[m, n] (bias gradients); workspace: digat_reduce_workspace_floats(M, N, 1) floats. */
 int digat_colsum(const float* in, int ld, float* out, float* workspace, int M, int N, void* stream);
+/* out[c, r] = in[r, c] for an fp32 matrix of `rows` x `cols` (ld_in >= cols, ld_out >= rows).  With out_lo != NULL the
+ * transposed matrix is written as its TF32 planes: out = rna_tf32(x), out_lo = rna_tf32(x - out) (digat_split_tf32 of the
+ * transpose in one pass).  Operand preparation of the split-K weight gradient: dW = dC^T A contracts over the ROWS of dC and
+ * A, and digat_linear_tf32x3_splitk wants the contraction index contiguous. */
+int digat_transpose_f32(const float* in, int ld_in, float* out, float* out_lo, int ld_out, int rows, int cols, void* stream);
 /* out[g, c] = sum_{r < rows} in[(g*rows + r), col0 + c] -- gradient of the GEMMs' row-group bias (dk3). */
 int digat_groupsum(const float* in, int ld, float* out, int groups, int rows, int col0, int cols, void* stream);
 

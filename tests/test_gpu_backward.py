@@ -220,3 +220,46 @@ def test_train_mode_with_dropout_runs_and_is_stochastic():
         e1, _ = m(*b)
         e2, _ = m(*b)
     assert torch.equal(e1, e2)
+
+
+@pytest.mark.parametrize('n,D,p', [(68, 400, 0.2), (13, 400, 0.0), (7, 36, 0.5)])
+def test_edge_driven_backward_extras_match_the_plain_call(n, D, p):
+    """digat_graph_layer_bwd_csr with the in-kernel relu mask and the per-graph column sums: dP bit-identical to the call that
+    gets G = dY * mask precomputed, dh_sum / du_sum = the column sums of the dh / dU blocks of dP per graph, and the whole
+    call repeatable bit for bit (no atomics)."""
+    from digat_b200 import _lib
+    from digat_b200.graphEncoders import _ptr, _stream, build_graph_csr, graph_layer_fwd
+    g = torch.Generator().manual_seed(n)
+    B = 6
+    P = (torch.randn(B * n, 3 * D, generator=g) * 0.5).cuda()
+    a = (torch.randn(D, generator=g) * 0.1).cuda()
+    X = torch.randn(B, n, D, generator=g).cuda()
+    adj = ((torch.rand(B, n, n, generator=g) < 0.2) | torch.eye(n, dtype=torch.bool)).cuda()
+    keep = (torch.rand(B, n, n, generator=g) >= p).cuda() if p > 0 else None
+    scale = 1.0 / (1 - p) if p > 0 else 1.0
+    dY = torch.randn(B, n, D, generator=g).cuda()
+    csr = build_graph_csr(adj, transpose=True)
+    score = torch.empty(B, n * n, device='cuda')
+    alpha = torch.empty(B, n * n, device='cuda')
+    rmask = torch.empty(B, n, D, device='cuda', dtype=torch.uint8)
+    graph_layer_fwd(P, a, adj, X, drop_keep=keep, drop_scale=scale, score_out=score, alpha_out=alpha, relu_mask_out=rmask,
+                    csr=(csr[0], csr[1], None))
+
+    def run(G, mask, sums):
+        dP = torch.empty_like(P)
+        da = torch.empty(B, D, device='cuda')
+        dh = torch.empty(B, D, device='cuda') if sums else None
+        du = torch.empty(B, D, device='cuda') if sums else None
+        _lib.call('digat_graph_layer_bwd_csr', P.data_ptr(), P.stride(0), a.data_ptr(), csr[0].data_ptr(), csr[1].data_ptr(),
+                  csr[2].data_ptr(), csr[3].data_ptr(), score.data_ptr(), alpha.data_ptr(), _ptr(keep), scale, G.data_ptr(),
+                  _ptr(mask), dP.data_ptr(), dP.stride(0), da.data_ptr(), _ptr(dh), _ptr(du), B, n, D, _stream())
+        torch.cuda.synchronize()
+        return dP, da, dh, du
+    dP0, da0, _, _ = run((dY * rmask).contiguous(), None, False)
+    dP1, da1, dh, du = run(dY, rmask, True)
+    dP2, da2, dh2, du2 = run(dY, rmask, True)
+    assert torch.equal(dP0, dP1) and torch.equal(da0, da1)
+    assert torch.equal(dP1, dP2) and torch.equal(da1, da2) and torch.equal(dh, dh2) and torch.equal(du, du2)
+    blocks = dP1.view(B, n, 3 * D).double()
+    for got, want in ((dh, blocks[:, :, :D].sum(1)), (du, blocks[:, :, D:2 * D].sum(1))):
+        assert rel_err(got.cpu().numpy(), want.cpu().numpy()) < 1e-6
