@@ -24,14 +24,18 @@ def _workspace(M, N, K, device):
     return torch.empty(int(n.item()), device=device, dtype=torch.float32)
 
 
-def colsum(x2d):
+def colsum(x2d, bufs=None):
+    """bufs = (out, workspace) allocated by colsum_bufs (side-stream launches), else allocated here."""
     M, N = x2d.shape
-    out = torch.empty(N, device=x2d.device, dtype=torch.float32)
+    out, ws = bufs if bufs is not None else colsum_bufs(M, N, x2d.device)
     if M == 0:
         return out.zero_()
-    ws = _workspace(M, N, 1, x2d.device)
     _lib.call('digat_colsum', x2d.data_ptr(), x2d.stride(0), out.data_ptr(), ws.data_ptr(), M, N, _stream())
     return out
+
+
+def colsum_bufs(M, N, device):
+    return torch.empty(N, device=device, dtype=torch.float32), _workspace(max(M, 1), N, 1, device)
 
 
 # Kernel-layout copies (TF32 planes of W for the forward, of W^T for dgrad) of the weights of ONE training step.  A weight
@@ -54,31 +58,80 @@ WGRAD_TC_MIN_ROWS = 2048     # shorter contractions keep the exact-fp32 CUDA-cor
 WGRAD_SLICE = 512            # rows per split-K slice: 64 truncating accumulate steps per accumulator
 
 
+# Independent kernels of one backward node (dgrad / wgrad / bias sums) are issued on a second stream and joined before the
+# node returns: in the captured training step they become parallel graph branches, so the latency-bound small products overlap
+# instead of queueing behind each other.  Every buffer a side-stream kernel touches is allocated on the MAIN stream before the
+# fork (the caching allocator ties a block to the stream that was current when it was allocated).
+PARALLEL_BACKWARD = True
+_SIDE_STREAMS = {}
+
+
+class _Fork:
+    """with _Fork() as f: <launches on the side stream>  ...  f.join() on the main stream."""
+
+    def __init__(self, enabled=True):
+        self.enabled = enabled and PARALLEL_BACKWARD
+
+    def __enter__(self):
+        if self.enabled:
+            self.cur = torch.cuda.current_stream()
+            key = self.cur.device_index
+            side = _SIDE_STREAMS.get(key)
+            if side is None:
+                side = _SIDE_STREAMS[key] = torch.cuda.Stream(device=self.cur.device)
+            self.side = side
+            side.wait_stream(self.cur)
+            self.ctx = torch.cuda.stream(side)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.enabled:
+            self.ctx.__exit__(*exc)
+        return False
+
+    def join(self):
+        if self.enabled:
+            self.cur.wait_stream(self.side)
+
+
+class _WgradPlan:
+    """Buffers of wgrad(dC, A), allocated up front so that the launches can run on a side stream."""
+
+    def __init__(self, M, N, K, device):
+        self.M, self.N, self.K = M, N, K
+        self.dW = torch.empty((N, K), device=device, dtype=torch.float32)
+        self.tensor_path = not (M < WGRAD_TC_MIN_ROWS or (M & 3) != 0 or K > 1280 or (K & 15) != 0 or (N & 3) != 0)
+        if not self.tensor_path:
+            self.ws = _workspace(M, N, K, device)
+            return
+        self.dCt = torch.empty((N, M), device=device, dtype=torch.float32)
+        self.At_hi = torch.empty((K, M), device=device, dtype=torch.float32)
+        self.At_lo = torch.empty((K, M), device=device, dtype=torch.float32)
+        self.S = (M + WGRAD_SLICE - 1) // WGRAD_SLICE
+        self.out = self.dW if self.S == 1 else torch.empty((self.S, N, K), device=device, dtype=torch.float32)
+        self.ws = _workspace(self.S, N * K, 1, device) if self.S > 1 else None
+
+    def run(self, dC, A):
+        M, N, K = self.M, self.N, self.K
+        if not self.tensor_path:
+            _lib.call('digat_linear_wgrad', dC.data_ptr(), dC.stride(0), A.data_ptr(), A.stride(0), self.dW.data_ptr(),
+                      self.ws.data_ptr(), M, N, K, _stream())
+            return self.dW
+        _lib.call('digat_transpose_f32', dC.data_ptr(), dC.stride(0), self.dCt.data_ptr(), 0, M, M, N, _stream())
+        _lib.call('digat_transpose_f32', A.data_ptr(), A.stride(0), self.At_hi.data_ptr(), self.At_lo.data_ptr(), M, M, K, _stream())
+        _lib.call('digat_linear_tf32x3_splitk', self.dCt.data_ptr(), M, self.At_hi.data_ptr(), self.At_lo.data_ptr(), M,
+                  self.out.data_ptr(), K, N, K, M, self.S, N * K, _stream())
+        if self.S > 1:
+            _lib.call('digat_colsum', self.out.data_ptr(), N * K, self.dW.data_ptr(), self.ws.data_ptr(), self.S, N * K, _stream())
+        return self.dW
+
+
 def wgrad(dC, A):
     """dW[N,K] = dC[M,N]^T A[M,K].  Long contractions run on the tensor cores: both operands are transposed so that the
     contraction index is contiguous (digat_transpose_f32; A^T directly as its TF32 planes), digat_linear_tf32x3_splitk writes one
     partial product per slice of WGRAD_SLICE rows and digat_colsum adds the slabs in slice order (deterministic)."""
-    M, K = A.shape
-    N = dC.shape[1]
-    dW = torch.empty((N, K), device=A.device, dtype=torch.float32)
-    if M < WGRAD_TC_MIN_ROWS or (M & 3) != 0 or K > 1280 or (K & 15) != 0 or (N & 3) != 0:
-        ws = _workspace(M, N, K, A.device)
-        _lib.call('digat_linear_wgrad', dC.data_ptr(), dC.stride(0), A.data_ptr(), A.stride(0), dW.data_ptr(),
-                  ws.data_ptr(), M, N, K, _stream())
-        return dW
-    dCt = torch.empty((N, M), device=A.device, dtype=torch.float32)
-    At_hi = torch.empty((K, M), device=A.device, dtype=torch.float32)
-    At_lo = torch.empty((K, M), device=A.device, dtype=torch.float32)
-    _lib.call('digat_transpose_f32', dC.data_ptr(), dC.stride(0), dCt.data_ptr(), 0, M, M, N, _stream())
-    _lib.call('digat_transpose_f32', A.data_ptr(), A.stride(0), At_hi.data_ptr(), At_lo.data_ptr(), M, M, K, _stream())
-    S = (M + WGRAD_SLICE - 1) // WGRAD_SLICE
-    out = dW if S == 1 else torch.empty((S, N, K), device=A.device, dtype=torch.float32)
-    _lib.call('digat_linear_tf32x3_splitk', dCt.data_ptr(), M, At_hi.data_ptr(), At_lo.data_ptr(), M, out.data_ptr(), K,
-              N, K, M, S, N * K, _stream())
-    if S > 1:
-        ws = _workspace(S, N * K, 1, A.device)
-        _lib.call('digat_colsum', out.data_ptr(), N * K, dW.data_ptr(), ws.data_ptr(), S, N * K, _stream())
-    return dW
+    return _WgradPlan(A.shape[0], dC.shape[1], A.shape[1], A.device).run(dC, A)
 
 
 SMALL_GEMM_ROWS = 1024       # products with at most this many rows run on the exact-fp32 CUDA-core kernel (digat_gemm_f32_small)
@@ -91,8 +144,9 @@ def _rows16(x):
     return x.contiguous()
 
 
-def _small_gemm(L, l_trans, R, r_trans, ldr, bias, I, J, C):
-    out = torch.empty((I, J), device=L.device, dtype=torch.float32)
+def _small_gemm(L, l_trans, R, r_trans, ldr, bias, I, J, C, out=None):
+    if out is None:
+        out = torch.empty((I, J), device=L.device, dtype=torch.float32)
     _lib.call('digat_gemm_f32_small', L.data_ptr(), L.stride(0), int(l_trans), R.data_ptr(), ldr, int(r_trans), _ptr(bias),
               out.data_ptr(), J, I, J, C, _stream())
     return out
@@ -137,23 +191,34 @@ class LinearFn(Function):
         M, K = A.shape
         N = W.shape[0]
         dA = dW = db = dg = None
+        want_db = ctx.has_bias and ctx.needs_input_grad[2]
         if ctx.small:
             dC = _rows16(dC)
+            dev = dC.device
+            if ctx.needs_input_grad[1]:
+                dW = torch.empty((N, K), device=dev, dtype=torch.float32)
+            db_bufs = colsum_bufs(M, N, dev) if want_db else None
+            with _Fork(ctx.needs_input_grad[0]) as side:               # weight / bias gradients beside the dgrad product
+                if dW is not None:
+                    _small_gemm(dC, True, A, False, A.stride(0), None, N, K, M, out=dW)
+                if want_db:
+                    db = colsum(dC, db_bufs)
             if ctx.needs_input_grad[0]:
                 Wt, lay, ldw = _weight_layout(W)
                 dA = _small_gemm(dC, False, Wt, lay == 'kn', ldw, None, M, K, N)
-            if ctx.needs_input_grad[1]:
-                dW = _small_gemm(dC, True, A, False, A.stride(0), None, N, K, M)
-            if ctx.has_bias and ctx.needs_input_grad[2]:
-                db = colsum(dC)
+            side.join()
             return dA, dW, db, None, None, None
         dC = dC.contiguous()
+        plan = _WgradPlan(M, N, K, A.device) if ctx.needs_input_grad[1] else None
+        db_bufs = colsum_bufs(M, N, A.device) if want_db else None
+        with _Fork(ctx.needs_input_grad[0]) as side:
+            if plan is not None:
+                dW = plan.run(dC, A)
+            if want_db:
+                db = colsum(dC, db_bufs)
         if ctx.needs_input_grad[0]:
             dA = linear(dC, _planes(W, True))
-        if ctx.needs_input_grad[1]:
-            dW = wgrad(dC, A)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = colsum(dC)
+        side.join()
         if ctx.group is not None and ctx.needs_input_grad[3]:
             rows, col0, cols = ctx.group
             dg = torch.empty((M // rows, cols), device=A.device, dtype=torch.float32)
@@ -255,10 +320,15 @@ class ProjectedGraphLayerFn(Function):
             dWb = colsum(dP[:, :D])
             dk3 = torch.empty((B, D), device=dev, dtype=torch.float32)
             _lib.call('digat_groupsum', dP.data_ptr(), dP.stride(0), dk3.data_ptr(), B, n, D, D, _stream())
+        plan = _WgradPlan(B * n, 3 * D, D, dev)
+        da_bufs = colsum_bufs(B, D, dev)
+        with _Fork() as side:                                          # weight gradients beside the dgrad product
+            dWcat = plan.run(dP, Xd.view(B * n, D))
+            da = colsum(da_part, da_bufs)
         dXd = linear(dP, _planes(Wcat, True)).view(B, n, D)
         dXd += dY                                                      # the residual path
-        dWcat = wgrad(dP, Xd.view(B * n, D))
-        return dXd, dWcat[:D], dWb, dWcat[D:2 * D], dWcat[2 * D:], dk3, colsum(da_part), None, None, None, None
+        side.join()
+        return dXd, dWcat[:D], dWb, dWcat[D:2 * D], dWcat[2 * D:], dk3, da, None, None, None, None
 
 
 class AttentionPoolFn(Function):
