@@ -63,7 +63,9 @@ WGRAD_SLICE = 512            # rows per split-K slice: 64 truncating accumulate 
 # instead of queueing behind each other.  Every buffer a side-stream kernel touches is allocated on the MAIN stream before the
 # fork (the caching allocator ties a block to the stream that was current when it was allocated).
 PARALLEL_BACKWARD = True
+PARALLEL_BRANCHES = True     # encode_with_grad: the small-row chain (contexts, news layer) beside the user layer (second stream)
 _SIDE_STREAMS = {}
+_BRANCH_STREAMS = {}
 
 
 class _Fork:
@@ -75,7 +77,7 @@ class _Fork:
     def __enter__(self):
         if self.enabled:
             self.cur = torch.cuda.current_stream()
-            key = self.cur.device_index
+            key = (self.cur.device_index, self.cur.cuda_stream)          # one helper stream per forking stream
             side = _SIDE_STREAMS.get(key)
             if side is None:
                 side = _SIDE_STREAMS[key] = torch.cuda.Stream(device=self.cur.device)
@@ -447,10 +449,37 @@ def encode_with_grad(enc, Xn, An, Mn, Xh, Au, Mc, ci):
     Xu = torch.cat([Xh, topic], 1)
     c_n = news_ctx(Xn)
     c_u = user_ctx(Xu, c_n)
+    main = torch.cuda.current_stream()
+    branch = None
+    if PARALLEL_BRANCHES:
+        branch = _BRANCH_STREAMS.get(main.device_index)
+        if branch is None:
+            branch = _BRANCH_STREAMS[main.device_index] = torch.cuda.Stream(device=main.device)
+    if branch is None:
+        for i in range(L):
+            Xn_new = layer('news', i, Xn, An, c_u)
+            Xu = layer('user', i, Xu, Au, c_n)
+            Xn = Xn_new
+            c_n = c_n + news_ctx(Xn)
+            c_u = c_u + user_ctx(Xu, c_n)
+        return c_n, c_u
+    # Two streams.  The user layer of iteration i (tens of thousands of rows: the big GEMMs and the layer kernel) needs only
+    # X_u and c_n of iteration i; everything else -- the user context of the previous iteration's outputs, the news layer that
+    # needs it, the news context -- is a chain of small, latency-bound launches (a few hundred or thousand rows) that runs
+    # beside it on a second stream.  Autograd replays each node on its forward stream, so the backward forks the same way, and
+    # in the captured step the two become parallel graph branches.  Same arithmetic as the sequential order above.
     for i in range(L):
-        Xn_new = layer('news', i, Xn, An, c_u)
-        Xu = layer('user', i, Xu, Au, c_n)
-        Xn = Xn_new
-        c_n = c_n + news_ctx(Xn)
-        c_u = c_u + user_ctx(Xu, c_n)
+        branch.wait_stream(main)
+        with torch.cuda.stream(branch):
+            if i > 0:
+                c_u = c_u + user_ctx(Xu, c_n)                      # context of the previous iteration's user graph
+            Xn_new = layer('news', i, Xn, An, c_u)
+            c_n_new = c_n + news_ctx(Xn_new)
+        Xu_new = layer('user', i, Xu, Au, c_n)
+        main.wait_stream(branch)
+        for t in (Xn_new, c_n_new, c_u):
+            t.record_stream(main)
+        Xu_new.record_stream(branch)
+        Xn, c_n, Xu = Xn_new, c_n_new, Xu_new
+    c_u = c_u + user_ctx(Xu, c_n)
     return c_n, c_u
