@@ -246,3 +246,39 @@ def test_small_exact_fp32_gemm_three_products(M, N, K):
         if use_bias:
             assert rel_err(bc.grad.cpu().numpy(), b64.grad.numpy()) < tol
         assert float(wide_c.grad[:, :4].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('rows,cols', [(21760, 400), (680, 1200), (33, 7), (1, 5), (4, 4096)])
+def test_transpose_and_tf32_planes(rows, cols):
+    """digat_transpose_f32: the transposed matrix bit for bit; with out_lo the TF32 planes of the transpose are exactly
+    digat_split_tf32 of it (hi + lo reproduces x to 2^-21 relative)."""
+    from digat_b200 import _lib
+    from digat_b200.graphEncoders import PackedWeight, _stream
+    g = torch.Generator().manual_seed(rows + cols)
+    wide = torch.randn(rows, cols + 4, generator=g).cuda()
+    x = wide[:, :cols]                                       # strided source rows
+    t = torch.empty(cols, rows, device='cuda')
+    _lib.call('digat_transpose_f32', x.data_ptr(), x.stride(0), t.data_ptr(), 0, rows, rows, cols, _stream())
+    hi, lo = torch.empty(cols, rows, device='cuda'), torch.empty(cols, rows, device='cuda')
+    _lib.call('digat_transpose_f32', x.data_ptr(), x.stride(0), hi.data_ptr(), lo.data_ptr(), rows, rows, cols, _stream())
+    torch.cuda.synchronize()
+    want = x.t().contiguous()
+    assert torch.equal(t, want)
+    if cols % 16 == 0 and rows % 4 == 0:
+        ref = PackedWeight(want)
+        assert torch.equal(hi, ref.hi) and torch.equal(lo, ref.lo)
+    assert float(((hi.double() + lo.double()) - want.double()).abs().max()) <= 2.0 ** -21 * float(want.abs().max())
+
+
+@pytest.mark.parametrize('M,N,ld', [(320, 400, 400), (320, 400, 1200), (1, 4, 4), (2048, 1200, 1200), (2049, 400, 400),
+                                    (21760, 1200, 1200), (43, 480000, 480000)])
+def test_colsum_paths(M, N, ld):
+    """digat_colsum: the single-launch kernel (<= 2048 rows), the sliced two-launch path and its one-slice shortcut."""
+    from digat_b200.autograd_ops import colsum
+    g = torch.Generator().manual_seed(M)
+    x = torch.randn(M, ld, generator=g).cuda()[:, :N]
+    got = colsum(x)
+    torch.cuda.synchronize()
+    want = x.double().sum(0)
+    assert rel_err(got.cpu().numpy(), want.cpu().numpy()) < 2e-6
+    assert torch.equal(got, colsum(x))                       # deterministic
