@@ -55,6 +55,7 @@ SIGNATURES = {
                             + [c_void_p],
     'digat_attention_pool_bwd': [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                  c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    'digat_news_gate_bwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
     'digat_topic_segment_bwd': [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_int, c_int, c_int, c_int, c_int, c_void_p],
     'digat_reduce_workspace_floats': [c_int, c_int, c_int, c_void_p],

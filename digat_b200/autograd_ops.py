@@ -360,6 +360,33 @@ class AttentionPoolFn(Function):
         return dF, dv, None, dres
 
 
+class NewsGateFn(Function):
+    """ctx_out = ctx_in + sigmoid(z) * l + (1 - sigmoid(z)) * g with lg = [l | g]  (graphEncoders.py:112-113, 185): one kernel
+    each way instead of sigmoid / mul / rsub / mul / add / add and their autograd nodes."""
+
+    @staticmethod
+    def forward(ctx, z, lg, ctx_in):
+        z, lg = z.contiguous(), lg.contiguous()
+        B, D = z.shape
+        out = torch.empty((B, D), device=z.device, dtype=torch.float32)
+        _lib.call('digat_news_gate_fwd', z.data_ptr(), lg.data_ptr(), 0 if ctx_in is None else ctx_in.contiguous().data_ptr(),
+                  out.data_ptr(), B, D, _stream())
+        ctx.save_for_backward(z, lg)
+        ctx.has_ctx = ctx_in is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        z, lg = ctx.saved_tensors
+        B, D = z.shape
+        dout = dout.contiguous()
+        dz = torch.empty_like(z)
+        dlg = torch.empty_like(lg)
+        _lib.call('digat_news_gate_bwd', z.data_ptr(), lg.data_ptr(), dout.data_ptr(), dz.data_ptr(), dlg.data_ptr(), B, D,
+                  _stream())
+        return dz, dlg, dout if ctx.has_ctx else None
+
+
 class TopicSegmentFn(Function):
     @staticmethod
     def forward(ctx, Xu, v, cidx, H, S, err_flag):
@@ -405,14 +432,15 @@ def encode_with_grad(enc, Xn, An, Mn, Xh, Au, Mc, ci):
     uq_W = torch.cat([enc.user_news_Q.weight, ua.Q.weight], 0)
     uq_b = torch.cat([enc.user_news_Q.bias, ua.Q.bias], 0)
 
-    def news_ctx(X):
+    def news_ctx(X, c_prev=None):
+        """c_prev + gated news context (graphEncoders.py:104-113, 185)."""
         l = X[:, 0, :]
         q = lin(l, cand.Q.weight, cand.Q.bias)
         v = lin(q, cand_Kt)
         g = AttentionPoolFn.apply(X, v, Mn, None)
-        z = drop(lin(torch.cat([l, g], 1), enc.news_graph_W.weight, enc.news_graph_W.bias), p / 2)
-        gate = torch.sigmoid(z)
-        return gate * l + (1 - gate) * g
+        lg = torch.cat([l, g], 1)
+        z = drop(lin(lg, enc.news_graph_W.weight, enc.news_graph_W.bias), p / 2)
+        return NewsGateFn.apply(z, lg, c_prev)
 
     def user_ctx(Xu, c_n):
         qq = lin(c_n, uq_W, uq_b)
@@ -460,7 +488,7 @@ def encode_with_grad(enc, Xn, An, Mn, Xh, Au, Mc, ci):
             Xn_new = layer('news', i, Xn, An, c_u)
             Xu = layer('user', i, Xu, Au, c_n)
             Xn = Xn_new
-            c_n = c_n + news_ctx(Xn)
+            c_n = news_ctx(Xn, c_n)
             c_u = c_u + user_ctx(Xu, c_n)
         return c_n, c_u
     # Two streams.  The user layer of iteration i (tens of thousands of rows: the big GEMMs and the layer kernel) needs only
@@ -474,7 +502,7 @@ def encode_with_grad(enc, Xn, An, Mn, Xh, Au, Mc, ci):
             if i > 0:
                 c_u = c_u + user_ctx(Xu, c_n)                      # context of the previous iteration's user graph
             Xn_new = layer('news', i, Xn, An, c_u)
-            c_n_new = c_n + news_ctx(Xn_new)
+            c_n_new = news_ctx(Xn_new, c_n)
         Xu_new = layer('user', i, Xu, Au, c_n)
         main.wait_stream(branch)
         for t in (Xn_new, c_n_new, c_u):

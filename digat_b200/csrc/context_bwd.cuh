@@ -204,4 +204,43 @@ inline int launch_topic_segment_bwd(const float* Xu, int64_t strideX, const floa
     return check_launch("digat_topic_segment_bwd");
 }
 
+// ---------------------------------------------------------------------------------------------- news gate backward
+// out = ctx_in + s l + (1 - s) g with s = sigmoid(z)  (graphEncoders.py:112-113):
+//   dz = dout (l - g) s (1 - s),  dl = dout s,  dg = dout (1 - s);  d ctx_in = dout (the caller passes it on).
+__global__ void news_gate_bwd_kernel(const float4* __restrict__ z, const float4* __restrict__ lg, const float4* __restrict__ dout,
+                                     float4* __restrict__ dz, float4* __restrict__ dlg, int B, int Dq) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * Dq) return;
+    const int b = (int)(i / Dq), q = (int)(i % Dq);
+    const float4 zz = z[i], d = dout[i];
+    const float4 l = lg[(size_t)b * 2 * Dq + q];
+    const float4 g = lg[(size_t)b * 2 * Dq + Dq + q];
+    float4 oz, ol, og;
+    auto one = [](float zv, float lv, float gv, float dv, float& z_, float& l_, float& g_) {
+        const float s = 1.f / (1.f + expf(-zv));
+        z_ = dv * (lv - gv) * (s * (1.f - s));
+        l_ = dv * s;
+        g_ = dv * (1.f - s);
+    };
+    one(zz.x, l.x, g.x, d.x, oz.x, ol.x, og.x); one(zz.y, l.y, g.y, d.y, oz.y, ol.y, og.y);
+    one(zz.z, l.z, g.z, d.z, oz.z, ol.z, og.z); one(zz.w, l.w, g.w, d.w, oz.w, ol.w, og.w);
+    dz[i] = oz;
+    dlg[(size_t)b * 2 * Dq + q] = ol;
+    dlg[(size_t)b * 2 * Dq + Dq + q] = og;
+}
+
+inline int launch_news_gate_bwd(const float* z, const float* lg, const float* dout, float* dz, float* dlg, int B, int D,
+                                cudaStream_t st) {
+    if (B <= 0) return DIGAT_OK;
+    DIGAT_REQUIRE(z && lg && dout && dz && dlg, "digat_news_gate_bwd: null pointer");
+    DIGAT_REQUIRE(D >= 4 && (D & 3) == 0, "digat_news_gate_bwd: D must be a multiple of 4");
+    DIGAT_REQUIRE(aligned16(z) && aligned16(lg) && aligned16(dout) && aligned16(dz) && aligned16(dlg),
+                  "digat_news_gate_bwd: pointers must be 16-byte aligned");
+    const int64_t total = (int64_t)B * (D / 4);
+    news_gate_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<const float4*>(z), reinterpret_cast<const float4*>(lg), reinterpret_cast<const float4*>(dout),
+        reinterpret_cast<float4*>(dz), reinterpret_cast<float4*>(dlg), B, D / 4);
+    return check_launch("digat_news_gate_bwd");
+}
+
 }  // namespace digat

@@ -267,6 +267,10 @@ int digat_attention_pool_bwd(const float* F, int64_t strideF, int ldf, const flo
                                      as_stream(stream));
 }
 
+int digat_news_gate_bwd(const float* z, const float* lg, const float* dout, float* dz, float* dlg, int B, int D, void* stream) {
+    return launch_news_gate_bwd(z, lg, dout, dz, dlg, B, D, as_stream(stream));
+}
+
 int digat_topic_segment_bwd(const float* Xu, int64_t strideX, const float* v, const int64_t* cidx, const float* alpha,
                             const float* dT, float* dXu, float* dv, int B, int H, int n_seg, int n_u, int D,
                             void* stream) {

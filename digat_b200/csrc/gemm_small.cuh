@@ -17,10 +17,12 @@ constexpr int kSgT = 32, kSgC = 64, kSgGroups = 8, kSgThreads = 32 * kSgGroups;
 constexpr int kSgPitch = kSgT + 4;   // tile row pitch: float4-aligned rows
 constexpr int kSgCg = kSgC / kSgGroups;   // contraction steps of a chunk per warp
 constexpr int kSgAhead = 2;          // chunks in flight from global memory (registers): 2 x 16 KB per CTA
-constexpr int kSgLoads = kSgC * kSgT / 4 / 128;   // float4 per loader thread, operand and chunk
+constexpr int kSgLoaders = kSgThreads / 2;         // threads per operand
+constexpr int kSgLoads = kSgC * kSgT / 4 / kSgLoaders;   // float4 per loader thread, operand and chunk
 
 // One WARP computes the whole 32 x 32 tile (8 x 4 outputs per lane) for its share of the contraction: warp g takes the
-// c-steps [4g, 4g + 4) of every chunk, and the eight partial tiles are added in warp order at the end (deterministic).
+// c-steps [8g, 8g + 8) of every 64-deep chunk, and the eight partial tiles are added by a fixed pairwise tree at the end
+// (deterministic).  (Sixteen warps, four per scheduler, were slower: 10.6 vs 9.5 us for [320 x 400 x 400].)
 // Why this shape: the product is bound by shared-memory reads, not FMAs -- with 2 x 4 outputs per thread every c-step cost
 // 6 LSU cycles per warp for 8 FMA instructions (measured 33 cycles per c-step and tile, 4x the FMA time); 8 x 4 outputs
 // read 12 floats for 32 FMAs.  It is also latency-bound from global memory (a chunk's math takes ~0.1 us, a load ~0.7 us):
@@ -30,58 +32,59 @@ __global__ void __launch_bounds__(kSgThreads)
 gemm_small_f32_kernel(const float* __restrict__ L, int ldl, const float* __restrict__ R, int ldr,
                       const float* __restrict__ bias, float* __restrict__ out, int ldo, int I, int J, int C) {
     __shared__ __align__(16) float tiles[2 * 2 * kSgC * kSgPitch];        // L and R chunks, double-buffered; then the partial tiles
-    static_assert(sizeof(float4) * (kSgGroups - 1) * 8 * 32 <= sizeof(float) * 2 * 2 * kSgC * kSgPitch, "partials must fit the tiles");
+    static_assert(sizeof(float4) * (kSgGroups / 2) * 8 * 32 <= sizeof(float) * 2 * 2 * kSgC * kSgPitch, "partials must fit the tiles");
     float (*Ls)[kSgC][kSgPitch] = reinterpret_cast<float (*)[kSgC][kSgPitch]>(tiles);
     float (*Rs)[kSgC][kSgPitch] = reinterpret_cast<float (*)[kSgC][kSgPitch]>(tiles + 2 * kSgC * kSgPitch);
     float4 (*red)[8][32] = reinterpret_cast<float4 (*)[8][32]>(tiles);
     const int tid = threadIdx.x, grp = tid >> 5, lane = tid & 31;
     const int i0 = blockIdx.y * kSgT, j0 = blockIdx.x * kSgT;
     const int ti = lane >> 3, tj = lane & 7;               // outputs (i0 + 8 ti + {0..7}, j0 + 4 tj + {0..3})
-    // loaders: threads 0..127 own L's 256 float4 of a chunk (two each), threads 128..255 R's.  An operand whose contiguous
+    // loaders: the first half of the CTA owns L's 512 float4 of a chunk (four each), the second half R's.  An operand whose contiguous
     // dimension is c is transposed on the way into shared memory: lanes take 32 different rows, so the four scalar stores
     // of a float4 hit 32 different banks; the other layout is copied quad for quad.
-    const bool isR = tid >= 128;
-    const int e = tid & 127;
+    const bool isR = tid >= kSgLoaders;
+    const int e = tid % kSgLoaders;
     const bool transposing = isR ? R_T : !L_T;
     // element t of a thread: (row, quad) of the [32 rows x kSgC] (c contiguous, transposed on store) or [kSgC x 32] tile
     int lr[kSgLoads], lq[kSgLoads];
 #pragma unroll
     for (int t = 0; t < kSgLoads; ++t) {
-        const int f = e + t * 128;
+        const int f = e + t * kSgLoaders;
         lr[t] = transposing ? (f & 31) : (f >> 3);
         lq[t] = transposing ? (f >> 5) * 4 : (f & 7) * 4;
     }
     float4 rv[kSgAhead][kSgLoads];
 
+    // Loads are UNCONDITIONAL (clamped addresses) and zeroed at store time when out of range: a guarded load compiles to a
+    // branch that waits for the load it skips over, which made every prefetch synchronous (22 % of the stall samples sat on
+    // those branches and on the first store behind them).
+    const float* base = isR ? R : L;
+    const int ld = isR ? ldr : ldl;
+    const int fixed0 = isR ? j0 : i0, fixedN = isR ? J : I;       // the tile's own dimension (rows of L / columns of R)
+    auto in_range = [&](int t, int c0) {
+        const int r = lr[t], q = lq[t];
+        return transposing ? (fixed0 + r < fixedN && c0 + q < C) : (c0 + r < C && fixed0 + q < fixedN);
+    };
     auto gload = [&](float4 (&v)[kSgLoads], int c0) {
 #pragma unroll
         for (int t = 0; t < kSgLoads; ++t) {
             const int r = lr[t], q = lq[t];
-            v[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (!isR) {
-                if (L_T) {   // stored [c][i]: row = c, quad along i
-                    if (c0 + r < C && i0 + q < I) v[t] = *reinterpret_cast<const float4*>(L + (size_t)(c0 + r) * ldl + i0 + q);
-                } else {     // stored [i][c]: row = i, quad along c
-                    if (i0 + r < I && c0 + q < C) v[t] = *reinterpret_cast<const float4*>(L + (size_t)(i0 + r) * ldl + c0 + q);
-                }
-            } else {
-                if (R_T) {   // stored [j][c]: row = j, quad along c
-                    if (j0 + r < J && c0 + q < C) v[t] = *reinterpret_cast<const float4*>(R + (size_t)(j0 + r) * ldr + c0 + q);
-                } else {     // stored [c][j]: row = c, quad along j
-                    if (c0 + r < C && j0 + q < J) v[t] = *reinterpret_cast<const float4*>(R + (size_t)(c0 + r) * ldr + j0 + q);
-                }
-            }
+            // transposing: stored [tile dim][c] -> row = fixed0 + r, quad along c;   else stored [c][tile dim]
+            const int row = transposing ? min(fixed0 + r, fixedN - 1) : min(c0 + r, C - 1);
+            const int col = transposing ? min(c0 + q, (C - 4) & ~3) : min(fixed0 + q, fixedN - 4);
+            v[t] = __ldg(reinterpret_cast<const float4*>(base + (size_t)row * ld + col));
         }
     };
-    auto sstore = [&](int buf, const float4 (&v)[kSgLoads]) {
+    auto sstore = [&](int buf, const float4 (&v)[kSgLoads], int c0) {
         float (*dst)[kSgPitch] = isR ? Rs[buf] : Ls[buf];
 #pragma unroll
         for (int t = 0; t < kSgLoads; ++t) {
             const int r = lr[t], q = lq[t];
+            const float4 x = in_range(t, c0) ? v[t] : make_float4(0.f, 0.f, 0.f, 0.f);
             if (transposing) {
-                dst[q + 0][r] = v[t].x; dst[q + 1][r] = v[t].y; dst[q + 2][r] = v[t].z; dst[q + 3][r] = v[t].w;
+                dst[q + 0][r] = x.x; dst[q + 1][r] = x.y; dst[q + 2][r] = x.z; dst[q + 3][r] = x.w;
             } else {
-                *reinterpret_cast<float4*>(&dst[r][q]) = v[t];
+                *reinterpret_cast<float4*>(&dst[r][q]) = x;
             }
         }
     };
@@ -93,8 +96,8 @@ gemm_small_f32_kernel(const float* __restrict__ L, int ldl, const float* __restr
         for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
     const int chunks = (C + kSgC - 1) / kSgC;
 #pragma unroll
-    for (int t = 0; t < kSgAhead; ++t) gload(rv[t], t * kSgC);           // (beyond C: zeros, never stored)
-    sstore(0, rv[0]);
+    for (int t = 0; t < kSgAhead; ++t) gload(rv[t], t * kSgC);           // (beyond C: clamped reads, never stored)
+    sstore(0, rv[0], 0);
     __syncthreads();
     gload(rv[0], kSgAhead * kSgC);
     for (int ch0 = 0; ch0 < chunks; ch0 += kSgAhead) {
@@ -124,27 +127,32 @@ gemm_small_f32_kernel(const float* __restrict__ L, int ldl, const float* __restr
                     }
                 }
                 if (ch + 1 < chunks) {
-                    sstore(buf ^ 1, rv[(u + 1) % kSgAhead]);              // chunk ch + 1, loaded kSgAhead chunks ago
+                    sstore(buf ^ 1, rv[(u + 1) % kSgAhead], (ch + 1) * kSgC);   // chunk ch + 1, loaded kSgAhead chunks ago
                     __syncthreads();
                     gload(rv[(u + 1) % kSgAhead], (ch + 1 + kSgAhead) * kSgC);
                 }
             }
         }
     }
-    __syncthreads();                 // the tiles are dead: their memory now holds the partial tiles
-    if (grp > 0) {
+    // the tiles are dead: their memory now holds partial tiles.  Pairwise tree in a fixed order: warps [h, 2h) park, warps
+    // [0, h) add their partner, h = 4, 2, 1 (deterministic).
 #pragma unroll
-        for (int a = 0; a < 8; ++a) red[grp - 1][a][lane] = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
-    }
-    __syncthreads();
-    if (grp > 0) return;
+    for (int h = kSgGroups / 2; h >= 1; h >>= 1) {
+        __syncthreads();
+        if (grp >= h && grp < 2 * h) {
 #pragma unroll
-    for (int g = 0; g < kSgGroups - 1; ++g)
-#pragma unroll
-        for (int a = 0; a < 8; ++a) {
-            const float4 v = red[g][a][lane];
-            acc[a][0] += v.x; acc[a][1] += v.y; acc[a][2] += v.z; acc[a][3] += v.w;
+            for (int a = 0; a < 8; ++a) red[grp - h][a][lane] = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
         }
+        __syncthreads();
+        if (grp < h) {
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+                const float4 v = red[grp][a][lane];
+                acc[a][0] += v.x; acc[a][1] += v.y; acc[a][2] += v.z; acc[a][3] += v.w;
+            }
+        }
+    }
+    if (grp > 0) return;
     const int j = j0 + 4 * tj;
     if (j < J) {                     // J % 4 == 0: a quad is entirely inside or outside
         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -303,6 +303,9 @@ int digat_attention_pool_bwd(const float* F, int64_t strideF, int ldf, const flo
                              const uint8_t* mask, const float* alpha, const float* dout, int ldg,
                              float* dF, float* dresid, float* dv, int B, int m, int D, void* stream);
 
+/* Backward of digat_news_gate_fwd (out = ctx_in + s l + (1-s) g, s = sigmoid(z); lg = [l | g], [B, 2D]):
+ * dz [B,D] = dout (l - g) s (1 - s),  dlg [B,2D] = [dout s | dout (1 - s)];  the gradient of ctx_in is dout itself. */
+int digat_news_gate_bwd(const float* z, const float* lg, const float* dout, float* dz, float* dlg, int B, int D, void* stream);
 /* Backward of digat_topic_segment_fwd.  alpha [B,H] saved by the forward; dT [B,n_seg,D].
  * out: dXu [B,n_u,D] (rows >= H are written as zeros: topic nodes are not pooled), dv [B,D]. */
 int digat_topic_segment_bwd(const float* Xu, int64_t strideX, const float* v, const int64_t* cidx,
