@@ -63,7 +63,9 @@ __device__ __forceinline__ void consumer_sync() {         // named barrier over 
 }
 
 // kMulti: several small graphs per CTA (block-diagonal); false keeps every index a function of n alone (one graph per CTA)
-template <bool kIndexed, bool kMulti>
+// kTrain: the training extras (per-edge score / alpha, attention dropout, relu mask) are compiled in only for the
+// instantiation the training path launches -- with them in the inference kernels the layer ran 5 % slower.
+template <bool kIndexed, bool kMulti, bool kTrain = false>
 __global__ void __launch_bounds__(kSparseThreads, DIGAT_SPARSE_MINCTAS)
 graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map3,
                               PairAttnArgs p, SparseGeom g) {
@@ -361,10 +363,10 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
     // Training extras (one graph per CTA, precomputed CSR): the raw score s_e and the softmax weight alpha_e of every edge go
     // out in CSR order (score_out / alpha_out [B, n*n], what the edge-driven backward reads), and the dropout on the attention
     // weights (graphEncoders.py:152/172) is applied here: alpha~_e = alpha_e * keep[i,j] * scale.
-    const bool train_out = !kMulti && p.alpha_out != nullptr;
+    const bool train_out = kTrain && p.alpha_out != nullptr;
     float* __restrict__ e_alpha = train_out ? p.alpha_out + (size_t)b * n * n : nullptr;
     float* __restrict__ e_score = (train_out && p.score_out != nullptr) ? p.score_out + (size_t)b * n * n : nullptr;
-    const uint8_t* __restrict__ keep_g = (!kMulti && p.drop_keep != nullptr) ? p.drop_keep + (size_t)b * n * n : nullptr;
+    const uint8_t* __restrict__ keep_g = (kTrain && p.drop_keep != nullptr) ? p.drop_keep + (size_t)b * n * n : nullptr;
     auto finish_edge = [&](int e, float s_raw, float al) {           // store alpha~ for phase 3, the raw values for the backward
         if (e_score != nullptr) e_score[e] = s_raw;
         if (e_alpha != nullptr) e_alpha[e] = al;
@@ -530,7 +532,7 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
                 float4 y;
                 unpack2(o01, y.x, y.y);
                 unpack2(o23, y.z, y.w);
-                if (p.relu_mask_out != nullptr)                             // training: 1[alpha~ h > 0] for the backward
+                if (kTrain && p.relu_mask_out != nullptr)                   // training: 1[alpha~ h > 0] for the backward
                     *reinterpret_cast<uchar4*>(p.relu_mask_out + yoff) = make_uchar4(y.x > 0.f, y.y > 0.f, y.z > 0.f, y.w > 0.f);
                 y.x = fmaxf(y.x, 0.f) + x0.x;
                 y.y = fmaxf(y.y, 0.f) + x0.y;
@@ -542,7 +544,7 @@ graph_layer_fwd_sparse_kernel(const __grid_constant__ CUtensorMap map1, const __
                 if (on_b) {
                     unpack2(p01, y.x, y.y);
                     unpack2(p23, y.z, y.w);
-                    if (p.relu_mask_out != nullptr)
+                    if (kTrain && p.relu_mask_out != nullptr)
                         *reinterpret_cast<uchar4*>(p.relu_mask_out + yoff + kSparseDc3) = make_uchar4(y.x > 0.f, y.y > 0.f, y.z > 0.f, y.w > 0.f);
                     y.x = fmaxf(y.x, 0.f) + x1.x;
                     y.y = fmaxf(y.y, 0.f) + x1.y;
@@ -623,6 +625,9 @@ int launch_graph_layer_fwd_sparse(const PairAttnArgs& args, int n_src, cudaStrea
     if (indexed) {
         if (int rc_ = ensure_dynamic_smem(graph_layer_fwd_sparse_kernel<true, false>, (size_t)(g.smem))) return rc_;
         graph_layer_fwd_sparse_kernel<true, false><<<grid, kSparseThreads, g.smem, st>>>(map1, map3, args, g);
+    } else if (training) {
+        if (int rc_ = ensure_dynamic_smem(graph_layer_fwd_sparse_kernel<false, false, true>, (size_t)(g.smem))) return rc_;
+        graph_layer_fwd_sparse_kernel<false, false, true><<<grid, kSparseThreads, g.smem, st>>>(map1, map3, args, g);
     } else if (G == 1) {
         if (int rc_ = ensure_dynamic_smem(graph_layer_fwd_sparse_kernel<false, false>, (size_t)(g.smem))) return rc_;
         graph_layer_fwd_sparse_kernel<false, false><<<grid, kSparseThreads, g.smem, st>>>(map1, map3, args, g);
