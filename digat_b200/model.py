@@ -21,9 +21,13 @@ class Model(nn.Module):
         self.news_encoder = None
         if hasattr(config, 'vocabulary_size'):                                  # text side available: model.py:11-16
             from . import newsEncoders
-            if getattr(config, 'news_encoder', 'MSA') != 'MSA':
-                raise Exception(config.news_encoder + ' is not implemented')
-            self.news_encoder = newsEncoders.MSA(config)
+            kind = getattr(config, 'news_encoder', 'MSA')           # reference model.py:10-15
+            if kind == 'MSA':
+                self.news_encoder = newsEncoders.MSA(config)
+            elif kind == 'CNN':
+                self.news_encoder = newsEncoders.CNN(config)
+            else:
+                raise Exception(kind + ' is not implemented')
             news_embedding_dim = self.news_encoder.news_embedding_dim
             self.max_title_length = config.max_title_length
         self.graph_encoder = ENCODERS[config.graph_encoder](config, news_embedding_dim)

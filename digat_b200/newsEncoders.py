@@ -11,7 +11,8 @@ Inference only (``torch.no_grad``): in the reference's evaluation this encoder r
   attention + relu   digat_msa_attention_fwd          one warp per (title, head), lane = query token
   affine1            projection GEMM                  [titles*T, A]
   tanh . w2, masked softmax over tokens, weighted sum   digat_additive_pool_fwd
-The CNN encoder (newsEncoders.py:27-55) is not implemented (the reference's default and published setting is MSA)."""
+The CNN encoder (newsEncoders.py:27-55; cnn_method 'naive' and 'group3') is an im2col gather + ONE GEMM with a relu epilogue
++ the same pooling (class CNN below)."""
 import math
 import os
 import pickle
@@ -153,6 +154,126 @@ class MSA(NewsEncoder):
         return out.view(B, news_num, hd)
 
 
+class Conv1D(nn.Module):
+    """Parameter container with the names of reference layers.py:7-26 ('naive' and 'group3'; 'group5' cannot run in the
+    reference either: layers.py:43-48 concatenates its padding column along the channel dimension)."""
+
+    def __init__(self, cnn_method, in_channels, cnn_kernel_num, cnn_window_size):
+        super().__init__()
+        if cnn_method not in ('naive', 'group3'):
+            raise Exception("cnn_method %r is not implemented on the sm_100a path ('naive' and 'group3' are)" % cnn_method)
+        self.cnn_method, self.in_channels = cnn_method, in_channels
+        if cnn_method == 'naive':
+            if cnn_window_size % 2 != 1:
+                raise Exception('cnn_window_size must be odd (same-length output, reference padding (window-1)//2)')
+            self.conv = nn.Conv1d(in_channels, cnn_kernel_num, kernel_size=cnn_window_size, padding=(cnn_window_size - 1) // 2)
+            self.window = cnn_window_size
+        else:
+            assert cnn_kernel_num % 3 == 0
+            self.conv1 = nn.Conv1d(in_channels, cnn_kernel_num // 3, kernel_size=1, padding=0)
+            self.conv2 = nn.Conv1d(in_channels, cnn_kernel_num // 3, kernel_size=3, padding=1)
+            self.conv3 = nn.Conv1d(in_channels, cnn_kernel_num // 3, kernel_size=5, padding=2)
+            self.window = 5
+
+    def initialize(self):
+        pass
+
+    def packed(self):
+        """One [kernels, window * E] matrix acting on the im2col rows [x[t-pad] | ... | x[t+pad]] (+ its bias): a window-w
+        convolution occupies the w central column blocks, zero elsewhere -- the 'group3' concatenation is ONE product."""
+        convs = [self.conv] if self.cnn_method == 'naive' else [self.conv1, self.conv2, self.conv3]
+        E, W = self.in_channels, self.window
+        rows = []
+        for c in convs:
+            w = c.weight.detach().float()                      # [out, E, k]
+            k = w.shape[2]
+            full = w.new_zeros((w.shape[0], W, E))
+            lo = (W - k) // 2
+            full[:, lo:lo + k, :] = w.permute(0, 2, 1)
+            rows.append(full.reshape(w.shape[0], W * E))
+        return torch.cat(rows, 0).contiguous(), torch.cat([c.bias.detach().float() for c in convs], 0).contiguous()
+
+
 class CNN(NewsEncoder):
+    """Drop-in for the CNN news encoder of reference newsEncoders.py:27-55, inference only:
+      word embeddings   digat_gather_rows_i32, once per window offset, straight into the column blocks of the im2col matrix
+                        [titles*T, window*E] (positions outside the title read an appended zero row = Conv1d's zero padding)
+      conv + relu       ONE projection GEMM against the packed kernels (relu in its epilogue)
+      attention pooling affine1 GEMM + digat_additive_pool_fwd, as in MSA."""
+
     def __init__(self, config):
-        raise Exception('CNN news encoder is not implemented on the sm_100a path (use --news_encoder=MSA)')
+        super().__init__(config)
+        self.max_sentence_length = config.max_title_length
+        self.cnn_kernel_num = config.cnn_kernel_num
+        self.conv = Conv1D(config.cnn_method, config.word_embedding_dim, config.cnn_kernel_num, config.cnn_window_size)
+        self.news_embedding_dim = config.cnn_kernel_num
+        self.attention = Attention(self.news_embedding_dim, config.attention_dim)
+        if self.news_embedding_dim % 4 != 0 or config.word_embedding_dim % 4 != 0:
+            raise Exception('word_embedding_dim and cnn_kernel_num must be multiples of 4 for the sm_100a kernels')
+        self._packed = self._packed_key = None
+
+    def initialize(self):
+        super().initialize()
+        self.conv.initialize()
+        self.attention.initialize()
+
+    def invalidate_packed(self):
+        self._packed = self._packed_key = None
+
+    def train(self, mode: bool = True):
+        self.invalidate_packed()
+        return super().train(mode)
+
+    def _weights(self):
+        params = list(self.parameters())
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if self._packed is not None and key == self._packed_key:
+            return self._packed
+        dev = params[0].device
+        if dev.type != 'cuda':
+            raise RuntimeError('CNN parameters must live on a CUDA device (digat_b200 has no CPU fallback)')
+        _lib.require_device(dev.index if dev.index is not None else torch.cuda.current_device())
+        with torch.no_grad():
+            table = self.word_embedding.weight.detach().float()
+            conv_W, conv_b = self.conv.packed()
+            w = {'table': torch.cat([table, table.new_zeros((1, table.shape[1]))], 0).contiguous(),   # + the zero-padding row
+                 'conv_W': PackedWeight(conv_W), 'conv_b': conv_b,
+                 'a1_W': PackedWeight(self.attention.affine1.weight.detach().float().contiguous()),
+                 'a1_b': self.attention.affine1.bias.detach().float().contiguous(),
+                 'w2': self.attention.affine2.weight.detach().float().reshape(-1).contiguous()}
+        self._packed, self._packed_key = w, key
+        return w
+
+    def forward(self, title_text, title_mask):
+        """title_text [B, news_num, T] integer token ids, title_mask [B, news_num, T] -> [B, news_num, cnn_kernel_num]."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise RuntimeError('CNN news encoder: the sm_100a path is inference-only (run under torch.no_grad())')
+        if not title_text.is_cuda:
+            raise RuntimeError('title_text must be a CUDA tensor (digat_b200 has no CPU fallback)')
+        w = self._weights()
+        B, news_num, T = title_text.shape
+        if T != self.max_sentence_length:
+            raise RuntimeError('title length %d != max_title_length %d' % (T, self.max_sentence_length))
+        n_titles, E, Fk, W = B * news_num, self.word_embedding_dim, self.news_embedding_dim, self.conv.window
+        pad, V = (W - 1) // 2, w['table'].shape[0] - 1
+        dev = title_text.device
+        with torch.no_grad():
+            tok = title_text.reshape(n_titles, T).to(torch.int32)
+            mask = title_mask.reshape(n_titles, T)
+            mask = (mask != 0).contiguous() if mask.dtype != torch.bool else mask.contiguous()
+            err = torch.zeros(1, dtype=torch.int32, device=dev)
+            bad = ((tok < 0) | (tok >= V)).any()                          # the appended zero row must not be reachable by a token
+            padded = torch.nn.functional.pad(tok, (pad, pad), value=V)    # index V = the zero row
+            X = torch.empty((n_titles * T, W * E), device=dev, dtype=torch.float32)
+            for k in range(W):
+                idx = padded[:, k:k + T].contiguous()
+                _lib.call('digat_gather_rows_i32', w['table'].data_ptr(), V + 1, idx.data_ptr(), X.data_ptr() + 4 * k * E, W * E,
+                          n_titles * T, E, err.data_ptr(), _stream())
+            H = linear(X, w['conv_W'], w['conv_b'], relu=True)                           # [titles*T, kernels]
+            att = linear(H, w['a1_W'], w['a1_b'])                                        # tanh in the pooling kernel
+            out = torch.empty((n_titles, Fk), device=dev, dtype=torch.float32)
+            _lib.call('digat_additive_pool_fwd', att.data_ptr(), att.stride(0), w['w2'].data_ptr(), H.data_ptr(), Fk,
+                      mask.data_ptr(), out.data_ptr(), Fk, n_titles, T, att.shape[1], Fk, _stream())
+            if int(err.item()) != 0 or bool(bad):
+                raise RuntimeError('token id out of range in title_text (reference: nn.Embedding raises)')
+        return out.view(B, news_num, Fk)

@@ -13,6 +13,8 @@ The invariants of the reference's data pipeline are kept:
 from dataclasses import dataclass
 from types import SimpleNamespace
 
+import math
+
 import numpy as np
 import torch
 
@@ -130,11 +132,36 @@ def make_ablation_state_dict(kind, config, D=400, seed=0):
 
 
 def make_text_config(vocabulary_size=500, max_title_length=32, word_embedding_dim=300, MSA_head_num=16, MSA_head_dim=25,
-                     attention_dim=256, **kw):
-    """make_config plus the text-side fields of reference config.py (newsEncoders.MSA reads them)."""
+                     attention_dim=256, cnn_method='naive', cnn_kernel_num=400, cnn_window_size=3, **kw):
+    """make_config plus the text-side fields of reference config.py (newsEncoders.MSA / CNN read them; config.py:43-45)."""
     return make_config(vocabulary_size=vocabulary_size, max_title_length=max_title_length,
                        word_embedding_dim=word_embedding_dim, MSA_head_num=MSA_head_num, MSA_head_dim=MSA_head_dim,
-                       attention_dim=attention_dim, word_threshold=3, dataset='synthetic', **kw)
+                       attention_dim=attention_dim, cnn_method=cnn_method, cnn_kernel_num=cnn_kernel_num,
+                       cnn_window_size=cnn_window_size, word_threshold=3, dataset='synthetic', **kw)
+
+
+def make_cnn_state_dict(config, seed=0):
+    """Seeded trained-like state_dict of the CNN news encoder (names/shapes of reference newsEncoders.py:27-34, layers.py:7-26)."""
+    rng = np.random.Generator(np.random.PCG64(seed + 523))
+    E, Fk, A = config.word_embedding_dim, config.cnn_kernel_num, config.attention_dim
+    sd = {'word_embedding.weight': rng.normal(0, 0.4, size=(config.vocabulary_size, E)).astype(np.float32)}
+    sd['word_embedding.weight'][0] = 0                                   # padding token
+
+    def conv(name, out_ch, window):
+        bound = 1.0 / math.sqrt(E * window)
+        sd['conv.%s.weight' % name] = rng.uniform(-bound, bound, size=(out_ch, E, window)).astype(np.float32)
+        sd['conv.%s.bias' % name] = rng.uniform(-bound, bound, size=out_ch).astype(np.float32)
+    if config.cnn_method == 'naive':
+        conv('conv', Fk, config.cnn_window_size)
+    elif config.cnn_method == 'group3':
+        for name, window in (('conv1', 1), ('conv2', 3), ('conv3', 5)):
+            conv(name, Fk // 3, window)
+    else:
+        raise ValueError('cnn_method %r' % config.cnn_method)
+    sd['attention.affine1.weight'] = _xavier(rng, A, Fk, 5.0 / 3.0)
+    sd['attention.affine1.bias'] = rng.normal(0, 0.05, size=A).astype(np.float32)
+    sd['attention.affine2.weight'] = _xavier(rng, 1, A)
+    return {k: torch.from_numpy(v) for k, v in sd.items()}
 
 
 def make_msa_state_dict(config, seed=0):

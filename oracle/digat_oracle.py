@@ -207,6 +207,30 @@ def msa_news_encoder(P, title_text, title_mask, heads, dk):
     return torch.bmm(alpha, h).squeeze(dim=1).view(B, news_num, heads * dk)
 
 
+def cnn_news_encoder(P, title_text, title_mask, method='naive'):
+    """CNN news encoder, eval mode (newsEncoders.py:41-54): word embeddings, Conv1D + relu (layers.py:36-41; 'naive' = one
+    nn.Conv1d with padding (window-1)//2, 'group3' = windows 1/3/5 concatenated over the channels), additive attention pooling
+    (layers.py:107-115).  title_text [B, news_num, T] int64 -> [B, news_num, cnn_kernel_num]."""
+    B, news_num, T = title_text.shape
+    n = B * news_num
+    mask = title_mask.view(n, T)
+    w = F.embedding(title_text, P['word_embedding.weight']).view(n, T, -1).permute(0, 2, 1)
+
+    def conv(name, pad):
+        return F.conv1d(w, P['conv.%s.weight' % name], P['conv.%s.bias' % name], padding=pad)
+    if method == 'naive':
+        c = conv('conv', (P['conv.conv.weight'].shape[2] - 1) // 2)
+    elif method == 'group3':
+        c = torch.cat([conv('conv1', 0), conv('conv2', 1), conv('conv3', 2)], dim=1)
+    else:
+        raise ValueError(method)
+    h = F.relu(c).permute(0, 2, 1)
+    att = torch.tanh(_lin(h, P['attention.affine1.weight'], P['attention.affine1.bias']))
+    a = _lin(att, P['attention.affine2.weight']).squeeze(dim=2)
+    alpha = F.softmax(a.masked_fill(mask == 0, NEG_FILL), dim=1).unsqueeze(dim=1)
+    return torch.bmm(alpha, h).squeeze(dim=1).view(B, news_num, -1)
+
+
 # ----------------------------------------------------------------------------- gathers (util.py:34-36, 65-67)
 def gather_sag_nodes(news_table, news_node_ID):
     n_news, n_n = news_node_ID.shape

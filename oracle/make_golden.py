@@ -245,17 +245,57 @@ def make_metric_case(ev):
     print('metrics', m)
 
 
+def cnn_inputs(method):
+    cfg = synth.make_text_config(cnn_method=method, cnn_kernel_num=384 if method == 'group3' else 400)
+    sd = synth.make_cnn_state_dict(cfg, seed=6)
+    tok, mask = synth.make_titles(cfg, 24, seed=3)
+    return cfg, sd, tok.view(4, 6, -1), mask.view(4, 6, -1)
+
+
+def make_cnn_cases():
+    """newsEncoders.CNN of the unmodified reference (eval mode), cnn_method naive and group3 (group5 cannot run in the
+    reference: layers.py:43-48 concatenates its padding column along the channel dimension)."""
+    import importlib
+    import pickle
+    import tempfile
+    for method in ('naive', 'group3'):
+        cfg, sd, tok, mask = cnn_inputs(method)
+        cwd = os.getcwd()
+        with tempfile.TemporaryDirectory() as tmp:
+            os.chdir(tmp)
+            try:
+                with open('word_embedding-%s-%s-%s-%s.pkl' % (cfg.word_threshold, cfg.word_embedding_dim, cfg.max_title_length,
+                                                               cfg.dataset), 'wb') as f:
+                    pickle.dump(torch.zeros(cfg.vocabulary_size, cfg.word_embedding_dim), f)
+                ne = importlib.import_module('newsEncoders')
+                payload = {'meta': np.frombuffer(json.dumps({('w:' + k): sha(v.numpy()) for k, v in sd.items()} |
+                                                            {'x:title_text': sha(tok.numpy()), 'x:title_mask': sha(mask.numpy())}).encode(),
+                                                 dtype=np.uint8)}
+                for tag, dt in (('ref32_', torch.float32), ('ref64_', torch.float64)):
+                    m = ne.CNN(cfg)
+                    m.load_state_dict(sd)
+                    m = m.to(dt).eval()
+                    with torch.no_grad():
+                        payload[tag + 'news'] = m(tok, mask.to(dt)).numpy()
+            finally:
+                os.chdir(cwd)
+        np.savez_compressed(os.path.join(GOLDEN, 'news_encoder_cnn_%s.npz' % method), **payload)
+        print('news_encoder_cnn', method, payload['ref32_news'].shape)
+
+
 if __name__ == '__main__':
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(1)   # fixed reduction partitioning inside MKL/ATen -> reproducible fp32 vectors
     ge, layers, ev, sag = load_reference()
-    which = sys.argv[1:] or ['encoder', 'ablation', 'msa', 'sag', 'metrics']
+    which = sys.argv[1:] or ['encoder', 'ablation', 'msa', 'cnn', 'sag', 'metrics']
     if 'encoder' in which:
         make_encoder_cases(ge)
     if 'ablation' in which:
         make_ablation_cases(ge)
     if 'msa' in which:
         make_msa_case()
+    if 'cnn' in which:
+        make_cnn_cases()
     if 'sag' in which:
         make_sag_case(sag)
     if 'metrics' in which:

@@ -126,3 +126,11 @@ def msa_inputs():
     sd = synth.make_msa_state_dict(cfg, seed=5)
     tok, mask = synth.make_titles(cfg, 24, seed=2)
     return cfg, sd, tok.view(4, 6, -1), mask.view(4, 6, -1)
+
+
+def cnn_inputs(method):
+    """Same construction as oracle/make_golden.py::cnn_inputs."""
+    cfg = synth.make_text_config(cnn_method=method, cnn_kernel_num=384 if method == 'group3' else 400)
+    sd = synth.make_cnn_state_dict(cfg, seed=6)
+    tok, mask = synth.make_titles(cfg, 24, seed=3)
+    return cfg, sd, tok.view(4, 6, -1), mask.view(4, 6, -1)

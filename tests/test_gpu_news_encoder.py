@@ -86,3 +86,49 @@ def test_msa_feeds_the_graph_encoder_through_model_forward():
         ref = O.logits(cn, cu).view(bs, news_num)
     assert got.shape == (bs, news_num)
     assert rel_err(got.numpy(), ref.numpy()) < 1e-5
+
+
+@pytest.mark.parametrize('method,rep', [('naive', 1), ('naive', 30), ('group3', 1)])
+def test_cnn_matches_reference_golden(method, rep):
+    """CNN news encoder (reference newsEncoders.py:27-55): im2col gather + one GEMM with relu + additive pooling against the
+    unmodified reference class, cnn_method naive (window 3) and group3 (windows 1/3/5 as one packed window-5 product)."""
+    from digat_b200.newsEncoders import CNN
+    from tests.helpers import cnn_inputs
+    cfg, sd, tok, mask = cnn_inputs(method)
+    z = np.load(os.path.join(GOLDEN, 'news_encoder_cnn_%s.npz' % method))
+    meta = json.loads(bytes(z['meta']).decode())
+    assert meta['x:title_text'] == sha(tok.numpy()) and all(meta['w:' + k] == sha(v.numpy()) for k, v in sd.items())
+    m = CNN(cfg)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    with torch.no_grad():
+        out = m(tok.cuda().repeat(rep, 1, 1), mask.cuda().repeat(rep, 1, 1))
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    assert got.shape == (4 * rep, 6, cfg.cnn_kernel_num)
+    for r in (0, rep - 1):
+        e32 = rel_err(got[4 * r:4 * r + 4], z['ref32_news'])
+        assert e32 < 1e-5, 'x%d replica %d: rel err vs fp32 reference %.3e (vs fp64 %.3e)' % (
+            rep, r, e32, rel_err(got[4 * r:4 * r + 4], z['ref64_news']))
+
+
+@pytest.mark.parametrize('method,T,E,Fk,A,window,n', [('naive', 20, 100, 64, 64, 5, 33), ('naive', 7, 52, 48, 200, 1, 5),
+                                                      ('group3', 12, 60, 96, 32, 3, 9)])
+def test_cnn_matches_oracle_other_shapes(method, T, E, Fk, A, window, n):
+    from digat_b200 import synth
+    from digat_b200.newsEncoders import CNN
+    cfg = synth.make_text_config(vocabulary_size=300, max_title_length=T, word_embedding_dim=E, attention_dim=A,
+                                 cnn_method=method, cnn_kernel_num=Fk, cnn_window_size=window)
+    sd = synth.make_cnn_state_dict(cfg, seed=T)
+    tok, mask = synth.make_titles(cfg, n, seed=T + 1)
+    m = CNN(cfg)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    with torch.no_grad():
+        got = m(tok.cuda().view(1, n, T), mask.cuda().view(1, n, T)).cpu()
+        ref = O.cnn_news_encoder(O.cast_params(sd, torch.float64), tok.view(1, n, T), mask.double().view(1, n, T), method)
+    assert rel_err(got.numpy(), ref.numpy()) < 1e-5
+    bad = tok.clone().view(1, n, T)
+    bad[0, 0, 0] = 300                                       # == vocabulary_size: the zero-padding row is not a token
+    with pytest.raises(RuntimeError):
+        m(bad.cuda(), mask.cuda().view(1, n, T))
