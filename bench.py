@@ -301,12 +301,19 @@ def run_score(args, rank, local_rank, world, dev):
     _lib.reset_launch_count()
     c_lo = sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    profile_range = os.environ.get('DIGAT_PROFILE_RANGE') == '1'     # `ncu --profile-from-start off`: exactly the timed steps
+    if profile_range:
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
     e0.record()
     # the public pipelined driver: the flag kernels of batch k+1 are enqueued ahead of the encoder pass of batch k and
     # the host waits for their counts (the only synchronisation of a step) while that pass runs
     step_events = []
     scoring.score_resident_batches(scorer, index_batches(args.warmup, total_steps), events=step_events)
     e1.record()
+    if profile_range:
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
     barrier()
     launches = _lib.launch_count()
     ms_resident = _max_over_ranks(e0.elapsed_time(e1), world, dev)

@@ -14,7 +14,7 @@ for st in $STAGES; do
     bench)   timeout 600 python bench.py --steps 20 --warmup 3 > $OUT/${TAG}_bench_n3.json 2> $OUT/${TAG}_bench_n3.err; tail -c 600 $OUT/${TAG}_bench_n3.json ;;
     bench_all) for w in mind_small_dev_n5_L3 wide_n8_L7; do timeout 600 python bench.py --steps 20 --warmup 3 --no-train --workload $w > $OUT/${TAG}_bench_$w.json 2> $OUT/${TAG}_bench_$w.err; done ;;
     train)   timeout 600 python bench.py --mode train --steps 20 --warmup 3 > $OUT/${TAG}_bench_train.json 2> $OUT/${TAG}_bench_train.err; cat $OUT/${TAG}_bench_train.json ;;
-    launches) timeout 900 $NCU --metrics gpu__time_duration.sum -s 800 -c 330 --csv --log-file $OUT/${TAG}_launches.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-train --sustained 0 > $OUT/${TAG}_launches.log 2>&1 ;;
+    launches) DIGAT_PROFILE_RANGE=1 timeout 900 $NCU --profile-from-start off --metrics gpu__time_duration.sum --csv --log-file $OUT/${TAG}_launches.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-train --sustained 0 > $OUT/${TAG}_launches.log 2>&1 ;;
     ncu_gather) timeout 900 $NCU --set full --import-source on -k regex:"gather_rows_kernel|build_user_nodes_kernel|logits_kernel|compact_lists|active_rows" -s 40 -c 14 -o $OUT/${TAG}_ncu_gather -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_gather.log 2>&1 ;;
     ncu_bwd) timeout 900 $NCU --set full --import-source on -k regex:"graph_layer_bwd_kernel|attention_pool_bwd|topic_segment_bwd|gemm_wgrad|colsum|groupsum" -s 60 -c 14 -o $OUT/${TAG}_ncu_bwd -f python bench.py --mode train --eager-train --steps 2 --warmup 3 > $OUT/${TAG}_ncu_bwd.log 2>&1
              timeout 900 $NCU --set full --import-source on -k regex:"gemm_tf32x3_persistent" -s 30 -c 4 -o $OUT/${TAG}_ncu_wgrad -f python bench.py --mode train --eager-train --steps 2 --warmup 3 > $OUT/${TAG}_ncu_wgrad.log 2>&1 ;;
