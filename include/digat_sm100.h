@@ -100,7 +100,9 @@ int digat_linear_tf32x3_splitk(const float* A, int lda, const float* W_hi, const
                                float* C, int ldc, int M, int N, int K, int kbatches, int64_t c_batch_stride,
                                void* stream);
 
-/* Tuning/experiment switch for digat_linear_tf32x3 tile variants (0 = default).  Not part of the reference path. */
+/* Tuning/experiment switch for digat_linear_tf32x3 (0 = default).  Not part of the reference path.
+ * 0-4: tile variants of the non-persistent kernel; 6/7/8: persistent kernel as independent CTAs (default) / W multicast over a
+ * CTA pair / 2-CTA MMA; 10-13: tile width of GEMMs with at most 1024 rows = 128 (off) / 64 / 32 (default) / 16. */
 int digat_debug_set_gemm_variant(int variant);
 /* digat_graph_layer_fwd kernel choice: 0 = auto (edge-driven kernel when a CTA owns one graph and no training extras are
  * requested, dense kernel otherwise), 1 = always dense, 2 = always edge-driven (inference).  For tests / profiling. */
