@@ -259,7 +259,8 @@ class GraphLayerFn(Function):
         dY = dY.contiguous()
         G = dY * rmask                                    # dZ = dY * 1[Z > 0]
         dP = torch.empty_like(P)
-        da_part = torch.empty((B, D), device=P.device, dtype=torch.float32)
+        parts = _lib.load().digat_graph_layer_bwd_csr_parts() if ctx.csr is not None else 1
+        da_part = torch.empty((B * parts, D), device=P.device, dtype=torch.float32)
         if ctx.csr is not None:
             rowptr, meta, colptr, cedge = ctx.csr
             _lib.call('digat_graph_layer_bwd_csr', P.data_ptr(), P.stride(0), a.data_ptr(), rowptr.data_ptr(), meta.data_ptr(),
@@ -304,16 +305,19 @@ class ProjectedGraphLayerFn(Function):
         dev = Xd.device
         dY = dY.contiguous()
         dP = torch.empty_like(P)
-        da_part = torch.empty((B, D), device=dev, dtype=torch.float32)
+        parts = _lib.load().digat_graph_layer_bwd_csr_parts() if ctx.csr is not None else 1
+        da_part = torch.empty((B * parts, D), device=dev, dtype=torch.float32)
         if ctx.csr is not None:
             rowptr, meta, colptr, cedge = ctx.csr
-            dh_sum = torch.empty((B, D), device=dev, dtype=torch.float32)
-            dk3 = torch.empty((B, D), device=dev, dtype=torch.float32)
+            dh_sum = torch.empty((B * parts, D), device=dev, dtype=torch.float32)     # per-warp partials (see the header)
+            du_sum = torch.empty((B * parts, D), device=dev, dtype=torch.float32)
             _lib.call('digat_graph_layer_bwd_csr', P.data_ptr(), P.stride(0), a.data_ptr(), rowptr.data_ptr(), meta.data_ptr(),
                       colptr.data_ptr(), cedge.data_ptr(), score.data_ptr(), alpha.data_ptr(), _ptr(keep), scale, dY.data_ptr(),
-                      rmask.data_ptr(), dP.data_ptr(), dP.stride(0), da_part.data_ptr(), dh_sum.data_ptr(), dk3.data_ptr(),
+                      rmask.data_ptr(), dP.data_ptr(), dP.stride(0), da_part.data_ptr(), dh_sum.data_ptr(), du_sum.data_ptr(),
                       B, n, D, _stream())
             dWb = colsum(dh_sum)
+            dk3 = torch.empty((B, D), device=dev, dtype=torch.float32)
+            _lib.call('digat_groupsum', du_sum.data_ptr(), D, dk3.data_ptr(), B, parts, 0, D, _stream())
         else:
             G = dY * rmask
             _lib.call('digat_graph_layer_bwd', P.data_ptr(), P.stride(0), a.data_ptr(), adj.data_ptr(), score.data_ptr(),
@@ -323,7 +327,7 @@ class ProjectedGraphLayerFn(Function):
             dk3 = torch.empty((B, D), device=dev, dtype=torch.float32)
             _lib.call('digat_groupsum', dP.data_ptr(), dP.stride(0), dk3.data_ptr(), B, n, D, D, _stream())
         plan = _WgradPlan(B * n, 3 * D, D, dev)
-        da_bufs = colsum_bufs(B, D, dev)
+        da_bufs = colsum_bufs(B * parts, D, dev)
         with _Fork() as side:                                          # weight gradients beside the dgrad product
             dWcat = plan.run(dP, Xd.view(B * n, D))
             da = colsum(da_part, da_bufs)

@@ -258,6 +258,8 @@ int digat_adam_clip_step(float* p, float* g, float* m, float* v, int64_t n, cons
                                  weight_decay, as_stream(stream));
 }
 
+int digat_graph_layer_bwd_csr_parts(void) { return kSbwdParts; }
+
 int digat_graph_layer_csr_training_supported(int n, int D) { return graph_layer_csr_training_supported(n, D); }
 
 int digat_attention_pool_bwd(const float* F, int64_t strideF, int ldf, const float* resid_F, const float* v,

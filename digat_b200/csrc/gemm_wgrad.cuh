@@ -178,7 +178,7 @@ inline int launch_linear_wgrad(const float* dC, int lddc, const float* A, int ld
 // out[n] = sum_m in[m, n] in ONE launch for a few hundred rows (bias gradients of the context projections, the per-graph
 // partials of an attention-vector gradient): 32 row lanes x 8 column quads per CTA, every lane's loads independent, the 32
 // lane sums added in lane order.  (Two launches -- slices, then their sum -- cost 16 us for a [320 x 400] matrix.)
-constexpr int kColsumSmallRows = 2048;
+constexpr int kColsumSmallRows = 4096;
 __global__ void __launch_bounds__(256)
 colsum_small_kernel(const float* __restrict__ in, int ld, float* __restrict__ out, int M, int N, int accumulate) {
     __shared__ float4 s_acc[32][8];

@@ -10,10 +10,11 @@
 //   pass C  (U, K2 tiles)  x_ed = U_jd + K2_id  (the forward's IEEE add on the same operands: the same relu mask)
 //                          dK2_id = a_d sum_{e in row i}    ds_e 1[x_ed > 0]      8 lanes per node, its ROW
 //                          dU_jd  = a_d sum_{e in column j} ds_e 1[x_ed > 0]      8 lanes per node, its COLUMN
-//                          da_d   = sum_e ds_e relu(x_ed)                          per-graph partial [B,D]
+//                          da_d   = sum_e ds_e relu(x_ed)                          per-warp partials [B*10, D]
 // Optional extras for the fused projection+layer backward: the saved relu mask of Z is applied to the staged dY tile (no
-// separate G = dY * mask pass), and the per-graph column sums of dh and dU come out as [B,D] arrays (the bias gradient is
-// their sum over graphs; sum_j dU_j IS dk3) so that nobody has to re-read the [B*n, 3D] dP for them.
+// separate G = dY * mask pass), and the column sums of dh and dU come out as per-warp partials [B*10, D] (the bias gradient
+// is their sum over all rows; the sum over a graph's 10 rows of the dU partials IS dk3) so that nobody has to re-read the
+// [B*n, 3D] dP for them.
 // Same skeleton as the forward: one CTA per graph, a producer warp streams [n][32]-feature tile pairs through a TMA ring
 // (SWIZZLE_128B), consumer warps synchronise through the ring's mbarriers.  Every sum runs in a fixed order (deterministic).
 #pragma once
@@ -26,11 +27,12 @@ namespace digat {
 
 constexpr int kSbwdMaxBufs = 3;
 constexpr int kSbwdDc = 32;
+constexpr int kSbwdParts = 10;        // rows per graph of da_partial / dh_sum / du_sum: one per consumer warp
 
 struct SparseBwdArgs {
     const float* P; int ldp; const float* a; const float* G;
     const uint8_t* relu_mask;      // [B,n,D] or null: G is dY and the saved mask of Z > 0 is applied to the staged tile
-    float* dh_sum; float* du_sum;  // [B,D] each or null: per-graph column sums of dh (-> bias gradient) and dU (= dk3)
+    float* dh_sum; float* du_sum;  // [B*kSbwdParts, D] each or null: per-warp column sums of dh (-> bias gradient) and dU (-> dk3)
     const uint16_t* rowptr; const uint16_t* meta; const uint16_t* colptr; const uint16_t* cedge;
     const float* e_score; const float* e_alpha; const uint8_t* drop_keep; float drop_scale;
     float* dP; int lddp; float* da_partial;
@@ -56,8 +58,7 @@ graph_layer_bwd_sparse_kernel(const __grid_constant__ CUtensorMap mapG, const __
     uint64_t* full = reinterpret_cast<uint64_t*>(ring + kSbwdBufs * unit_floats);
     uint64_t* empty = full + kSbwdMaxBufs;
     float* a_s = reinterpret_cast<float*>(empty + kSbwdMaxBufs);               // [D]
-    float* parts = a_s + D;                                                 // [2 parities][3 kinds][warps][32] column-sum partials
-    float* alt = parts + 2 * 3 * (kSparseConsumers / 32) * kSbwdDc;         // [n*n] alpha~ per edge
+    float* alt = a_s + D;                                                   // [n*n] alpha~ per edge
     float* dal = alt + n * n;                                               // [n*n] dalpha~ per edge, later ds
     int* rowptr = reinterpret_cast<int*>(dal + n * n);                      // [n+1]
     int* colptr = rowptr + (n + 1);                                         // [n+1]
@@ -133,27 +134,18 @@ graph_layer_bwd_sparse_kernel(const __grid_constant__ CUtensorMap mapG, const __
         return ro + ((q * 16u) ^ (((ro >> 7) & 7u) << 4));
     };
 
-    // Per-graph column sums (dh -> bias gradient, dU -> dk3, da) without atomics: a thread sums its nodes, the four node
-    // groups of a warp are folded with shuffles, lanes 0..7 park the warp's float4 in `parts`, and after a consumer barrier
-    // eight threads add the ten warps in order.  `parts` alternates by unit parity, so one barrier per unit is enough.
+    // Per-graph column sums (dh -> bias gradient, dU -> dk3, da) without atomics and without a barrier: a thread sums its
+    // nodes, the four node groups of a warp are folded with shuffles and lanes 0..7 write the WARP's partial to row
+    // b * kSbwdParts + warp of the output; the caller adds the kSbwdParts rows of a graph (digat_groupsum) or all rows
+    // (digat_colsum).  (Folding the warps here cost a barrier over all consumer warps per unit: 30 % of the stall samples.)
     constexpr int kWarps = kSparseConsumers / 32;
-    auto park = [&](int parity, int kind, float4 v) {
+    static_assert(kWarps == kSbwdParts, "partial rows per graph");
+    auto park = [&](float* dst, int c0, int wq, float4 v) {
         v.x += __shfl_xor_sync(0xffffffffu, v.x, 8);  v.y += __shfl_xor_sync(0xffffffffu, v.y, 8);
         v.z += __shfl_xor_sync(0xffffffffu, v.z, 8);  v.w += __shfl_xor_sync(0xffffffffu, v.w, 8);
         v.x += __shfl_xor_sync(0xffffffffu, v.x, 16); v.y += __shfl_xor_sync(0xffffffffu, v.y, 16);
         v.z += __shfl_xor_sync(0xffffffffu, v.z, 16); v.w += __shfl_xor_sync(0xffffffffu, v.w, 16);
-        if (lane < 8) *reinterpret_cast<float4*>(parts + ((parity * 3 + kind) * kWarps + warp) * kSbwdDc + 4 * lane) = v;
-    };
-    auto fold = [&](int parity, int kind, float* dst, int c0, int wq) {       // call after consumer_sync(); tid < 8 writes
-        if (tid < wq) {
-            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int w = 0; w < kWarps; ++w) {
-                const float4 v = *reinterpret_cast<const float4*>(parts + ((parity * 3 + kind) * kWarps + w) * kSbwdDc + 4 * tid);
-                t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
-            }
-            *reinterpret_cast<float4*>(dst + (size_t)b * D + c0 + 4 * tid) = t;
-        }
+        if (lane < wq) *reinterpret_cast<float4*>(dst + ((size_t)b * kWarps + warp) * D + c0 + 4 * lane) = v;   // wq <= 8
     };
 
     // ---------------------------------------------------------------------- pass A: dalpha~ per edge, dh per node
@@ -205,11 +197,7 @@ graph_layer_bwd_sparse_kernel(const __grid_constant__ CUtensorMap mapG, const __
         if (p.relu_mask != nullptr) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // our writes, then TMA's
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[buf]);
-        if (p.dh_sum != nullptr) {
-            park(l & 1, 0, dh_tot);
-            consumer_sync();
-            fold(l & 1, 0, p.dh_sum, c0, wq);
-        }
+        if (p.dh_sum != nullptr) park(p.dh_sum, c0, wq, dh_tot);
     }
     consumer_sync();
 
@@ -286,18 +274,15 @@ graph_layer_bwd_sparse_kernel(const __grid_constant__ CUtensorMap mapG, const __
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[buf]);
-        park(l & 1, 2, da_tot);
-        if (p.du_sum != nullptr) park(l & 1, 1, du_tot);
-        consumer_sync();
-        fold(l & 1, 2, p.da_partial, c0, wq);
-        if (p.du_sum != nullptr) fold(l & 1, 1, p.du_sum, c0, wq);
+        park(p.da_partial, c0, wq, da_tot);
+        if (p.du_sum != nullptr) park(p.du_sum, c0, wq, du_tot);
     }
 }
 
 inline void sparse_bwd_geometry(int n, int D, SparseBwdGeom* g) {
     g->nch = (D + kSbwdDc - 1) / kSbwdDc;
     g->tile_floats = ((n * kSbwdDc * 4 + 1023) / 1024) * 1024 / 4;
-    const size_t rest = (size_t)2 * kSbwdMaxBufs * 8 + (size_t)D * 4 + (size_t)2 * 3 * (kSparseConsumers / 32) * kSbwdDc * 4 + (size_t)2 * n * n * 4 + (size_t)2 * (n + 1) * 4 +
+    const size_t rest = (size_t)2 * kSbwdMaxBufs * 8 + (size_t)D * 4 + (size_t)2 * n * n * 4 + (size_t)2 * (n + 1) * 4 +
                         (size_t)2 * n * n * 2 + (size_t)n + 64;
     const size_t unit = (size_t)2 * g->tile_floats * 4;
     constexpr size_t kTwoPerSm = 113 * 1024;                       // two CTAs per SM (228 KB, 1 KB reserved per CTA)

@@ -272,16 +272,20 @@ int digat_graph_layer_bwd(const float* P, int ldp, const float* a, const uint8_t
 /* The same backward, edge-driven: only the E edges of each graph are evaluated (a masked pair has alpha = 0 and
  * ds = 0), through the CSR and its transpose of digat_build_graph_csr (no adj_index / row_active: training evaluates
  * every graph and row) and the per-edge edge_score / edge_alpha [B, n*n] the forward wrote when it was given the
- * same CSR.  drop_keep stays the dense [B,n,n] mask.  Outputs as digat_graph_layer_bwd (every row of dP is written).
+ * same CSR.  drop_keep stays the dense [B,n,n] mask.  dP as in digat_graph_layer_bwd (every row is written).
+ * da_partial is [B * PARTS, D] here, PARTS = digat_graph_layer_bwd_csr_parts(): row b * PARTS + w holds the partial of
+ * consumer warp w of graph b (digat_colsum over all rows finishes da) -- folding the warps inside the kernel would cost a
+ * CTA-wide barrier per feature chunk.
  * Optional (NULL = off): relu_mask [B,n,D] -- G is then the raw dY and the forward's saved mask is applied in-kernel;
- * dh_sum, du_sum [B,D] -- per-graph column sums of the dh and dU blocks of dP (sum over graphs of dh_sum = the gradient of
- * the projection bias; du_sum = dk3, the gradient of the row-group bias), so nothing re-reads dP for them.
- * All sums run in a fixed order (deterministic). */
+ * dh_sum, du_sum [B * PARTS, D] -- column sums of the dh and dU blocks of dP in the same per-warp layout: digat_colsum of
+ * dh_sum = the gradient of the projection bias, digat_groupsum of du_sum over each graph's PARTS rows = dk3 (the gradient of
+ * the row-group bias), so nothing re-reads dP for them.  All sums run in a fixed order (deterministic). */
 int digat_graph_layer_bwd_csr(const float* P, int ldp, const float* a, const uint16_t* csr_rowptr, const uint16_t* csr_meta,
                               const uint16_t* csc_colptr, const uint16_t* csc_edge, const float* edge_score,
                               const float* edge_alpha, const uint8_t* drop_keep, float drop_scale, const float* G,
                               const uint8_t* relu_mask, float* dP, int lddp, float* da_partial, float* dh_sum, float* du_sum,
                               int B, int n, int D, void* stream);
+int digat_graph_layer_bwd_csr_parts(void);
 /* 1 when graphs of n nodes and width D can train through the CSR pair (digat_graph_layer_fwd with a CSR and training
  * outputs + digat_graph_layer_bwd_csr): both working sets fit one SM.  0: use the dense [B,n,n] score / alpha path. */
 int digat_graph_layer_csr_training_supported(int n, int D);

@@ -270,10 +270,10 @@ def test_transpose_and_tf32_planes(rows, cols):
     assert float(((hi.double() + lo.double()) - want.double()).abs().max()) <= 2.0 ** -21 * float(want.abs().max())
 
 
-@pytest.mark.parametrize('M,N,ld', [(320, 400, 400), (320, 400, 1200), (1, 4, 4), (2048, 1200, 1200), (2049, 400, 400),
+@pytest.mark.parametrize('M,N,ld', [(320, 400, 400), (320, 400, 1200), (1, 4, 4), (2048, 1200, 1200), (3200, 400, 400), (4097, 400, 400),
                                     (21760, 1200, 1200), (43, 480000, 480000)])
 def test_colsum_paths(M, N, ld):
-    """digat_colsum: the single-launch kernel (<= 2048 rows), the sliced two-launch path and its one-slice shortcut."""
+    """digat_colsum: the single-launch kernel (<= 4096 rows), the sliced two-launch path and its one-slice shortcut."""
     from digat_b200.autograd_ops import colsum
     g = torch.Generator().manual_seed(M)
     x = torch.randn(M, ld, generator=g).cuda()[:, :N]
