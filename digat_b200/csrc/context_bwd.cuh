@@ -133,21 +133,41 @@ topic_segment_bwd_kernel(SegBwdArgs p) {
         s_al[tid] = p.alpha[(size_t)b * H + tid];
     }
     __syncthreads();
-    for (int t = 0; t < H; ++t) {
-        const float* drow = dT + (size_t)s_seg[t] * D;
-        float part = 0.f;
+    // Rows are handled five at a time: their loads are independent, so one memory round trip covers five rows (a training
+    // batch is a few hundred CTAs -- the kernel is latency-bound, and one row per trip cost 47 us for 25 MB).
+    constexpr int kRows = 5;
+    for (int t0 = 0; t0 < H; t0 += kRows) {
+        float4 x[kRows][kCtxMaxQuads], d[kRows][kCtxMaxQuads];
 #pragma unroll
-        for (int c = 0; c < kCtxMaxQuads; ++c) {
-            const int q = tid + c * kCtxThreads;
-            if (q < nq) {
-                const float4 x = reinterpret_cast<const float4*>(Xh + (size_t)t * D)[q];
-                const float4 d = reinterpret_cast<const float4*>(drow)[q];
-                part = fmaf(x.x, d.x, part); part = fmaf(x.y, d.y, part);
-                part = fmaf(x.z, d.z, part); part = fmaf(x.w, d.w, part);
+        for (int u = 0; u < kRows; ++u) {
+            const int t = min(t0 + u, H - 1);                                  // the tail repeats the last row (result unused)
+            const float* drow = dT + (size_t)s_seg[t] * D;
+#pragma unroll
+            for (int c = 0; c < kCtxMaxQuads; ++c) {
+                const int q = tid + c * kCtxThreads;
+                x[u][c] = q < nq ? reinterpret_cast<const float4*>(Xh + (size_t)t * D)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+                d[u][c] = q < nq ? reinterpret_cast<const float4*>(drow)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
-        part = warp_sum(part);
-        if (lane == 0) s_part[t][warp] = part;
+        float part[kRows];
+#pragma unroll
+        for (int u = 0; u < kRows; ++u) {
+            part[u] = 0.f;
+#pragma unroll
+            for (int c = 0; c < kCtxMaxQuads; ++c) {
+                part[u] = fmaf(x[u][c].x, d[u][c].x, part[u]); part[u] = fmaf(x[u][c].y, d[u][c].y, part[u]);
+                part[u] = fmaf(x[u][c].z, d[u][c].z, part[u]); part[u] = fmaf(x[u][c].w, d[u][c].w, part[u]);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int u = 0; u < kRows; ++u) part[u] += __shfl_xor_sync(0xffffffffu, part[u], o);
+        if (lane == 0) {
+#pragma unroll
+            for (int u = 0; u < kRows; ++u)
+                if (t0 + u < H) s_part[t0 + u][warp] = part[u];
+        }
     }
     __syncthreads();
     if (tid < H) {
@@ -172,16 +192,26 @@ topic_segment_bwd_kernel(SegBwdArgs p) {
         const float4 vv = reinterpret_cast<const float4*>(p.v + (size_t)b * D)[q];
         float4 dv = make_float4(0.f, 0.f, 0.f, 0.f);
         float* dX = p.dXu + (size_t)b * p.n_u * D;
-        for (int t = 0; t < H; ++t) {
-            const float4 x = reinterpret_cast<const float4*>(Xh + (size_t)t * D)[q];
-            const float4 d = reinterpret_cast<const float4*>(dT + (size_t)s_seg[t] * D)[q];
-            const float al = s_al[t], ds = s_ds[t];
-            float4 o;
-            o.x = fmaf(al, d.x, ds * vv.x); o.y = fmaf(al, d.y, ds * vv.y);
-            o.z = fmaf(al, d.z, ds * vv.z); o.w = fmaf(al, d.w, ds * vv.w);
-            dv.x = fmaf(ds, x.x, dv.x); dv.y = fmaf(ds, x.y, dv.y);
-            dv.z = fmaf(ds, x.z, dv.z); dv.w = fmaf(ds, x.w, dv.w);
-            reinterpret_cast<float4*>(dX + (size_t)t * D)[q] = o;
+        for (int t0 = 0; t0 < H; t0 += kRows) {
+            float4 x[kRows], d[kRows];
+#pragma unroll
+            for (int u = 0; u < kRows; ++u) {
+                const int t = min(t0 + u, H - 1);
+                x[u] = reinterpret_cast<const float4*>(Xh + (size_t)t * D)[q];
+                d[u] = reinterpret_cast<const float4*>(dT + (size_t)s_seg[t] * D)[q];
+            }
+#pragma unroll
+            for (int u = 0; u < kRows; ++u) {
+                const int t = t0 + u;
+                if (t >= H) break;
+                const float al = s_al[t], ds = s_ds[t];
+                float4 o;
+                o.x = fmaf(al, d[u].x, ds * vv.x); o.y = fmaf(al, d[u].y, ds * vv.y);
+                o.z = fmaf(al, d[u].z, ds * vv.z); o.w = fmaf(al, d[u].w, ds * vv.w);
+                dv.x = fmaf(ds, x[u].x, dv.x); dv.y = fmaf(ds, x[u].y, dv.y);
+                dv.z = fmaf(ds, x[u].z, dv.z); dv.w = fmaf(ds, x[u].w, dv.w);
+                reinterpret_cast<float4*>(dX + (size_t)t * D)[q] = o;
+            }
         }
         for (int t = H; t < p.n_u; ++t)
             reinterpret_cast<float4*>(dX + (size_t)t * D)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
