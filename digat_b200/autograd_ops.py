@@ -462,7 +462,23 @@ def encode_with_grad(enc, Xn, An, Mn, Xh, Au, Mc, ci):
             return None
         return build_graph_csr(adj, transpose=True)
 
-    csr_of = {'news': train_csr(An), 'user': train_csr(Au)}          # once per step: every layer walks the same edges
+    main = torch.cuda.current_stream()
+    branch = None
+    if PARALLEL_BRANCHES:
+        branch = _BRANCH_STREAMS.get(main.device_index)
+        if branch is None:
+            branch = _BRANCH_STREAMS[main.device_index] = torch.cuda.Stream(device=main.device)
+    # CSR + transpose of both graph families, once per step (every layer walks the same edges); on the second stream they are
+    # built beside the initial contexts
+    if branch is None:
+        csr_of = {'news': train_csr(An), 'user': train_csr(Au)}
+    else:
+        branch.wait_stream(main)
+        with torch.cuda.stream(branch):
+            csr_of = {'news': train_csr(An), 'user': train_csr(Au)}
+        for c in csr_of.values():
+            for t in (c or ()):
+                t.record_stream(main)
 
     def layer(g, i, X, adj, ctx_other):
         n = X.shape[1]
@@ -481,12 +497,8 @@ def encode_with_grad(enc, Xn, An, Mn, Xh, Au, Mc, ci):
     Xu = torch.cat([Xh, topic], 1)
     c_n = news_ctx(Xn)
     c_u = user_ctx(Xu, c_n)
-    main = torch.cuda.current_stream()
-    branch = None
-    if PARALLEL_BRANCHES:
-        branch = _BRANCH_STREAMS.get(main.device_index)
-        if branch is None:
-            branch = _BRANCH_STREAMS[main.device_index] = torch.cuda.Stream(device=main.device)
+    if branch is not None:
+        main.wait_stream(branch)                                   # the CSR records
     if branch is None:
         for i in range(L):
             Xn_new = layer('news', i, Xn, An, c_u)

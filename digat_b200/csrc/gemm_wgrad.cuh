@@ -175,37 +175,44 @@ inline int launch_linear_wgrad(const float* dC, int lddc, const float* A, int ld
     return check_launch("digat_linear_wgrad");
 }
 
-// out[n] = sum_m in[m, n] in ONE launch for a few hundred rows (bias gradients of the context projections, the per-graph
-// partials of an attention-vector gradient): 32 row lanes x 8 column quads per CTA, every lane's loads independent, the 32
-// lane sums added in lane order.  (Two launches -- slices, then their sum -- cost 16 us for a [320 x 400] matrix.)
+// out[n] = sum_m in[m, n] in ONE launch for up to a few thousand rows (bias gradients of the context projections, the per-warp
+// partials of the layer backward): 128 row lanes x 8 column quads per CTA, every lane's loads independent, the lanes added in a
+// fixed order (warp shuffles, then the 32 warps).  (Two launches -- slices, then their sum -- cost 16 us for a [320 x 400] matrix.)
 constexpr int kColsumSmallRows = 4096;
-__global__ void __launch_bounds__(256)
+constexpr int kColsumSmallThreads = 1024;             // 128 row lanes x 8 column quads
+__global__ void __launch_bounds__(kColsumSmallThreads)
 colsum_small_kernel(const float* __restrict__ in, int ld, float* __restrict__ out, int M, int N, int accumulate) {
-    __shared__ float4 s_acc[32][8];
-    const int cq = threadIdx.x & 7, rl = threadIdx.x >> 3;
+    __shared__ float4 s_acc[kColsumSmallThreads / 32][8];
+    const int cq = threadIdx.x & 7, rl = threadIdx.x >> 3, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int col = (blockIdx.x * 8 + cq) * 4;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     if (col < N) {
 #pragma unroll 8
-        for (int m = rl; m < M; m += 32) {
+        for (int m = rl; m < M; m += kColsumSmallThreads / 8) {
             const float4 v = *reinterpret_cast<const float4*>(in + (size_t)m * ld + col);
             s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
         }
     }
-    s_acc[rl][cq] = s;
+    // the four row lanes of a warp, then the 32 warps, in a fixed order
+    s.x += __shfl_xor_sync(0xffffffffu, s.x, 8);  s.y += __shfl_xor_sync(0xffffffffu, s.y, 8);
+    s.z += __shfl_xor_sync(0xffffffffu, s.z, 8);  s.w += __shfl_xor_sync(0xffffffffu, s.w, 8);
+    s.x += __shfl_xor_sync(0xffffffffu, s.x, 16); s.y += __shfl_xor_sync(0xffffffffu, s.y, 16);
+    s.z += __shfl_xor_sync(0xffffffffu, s.z, 16); s.w += __shfl_xor_sync(0xffffffffu, s.w, 16);
+    if (lane < 8) s_acc[warp][lane] = s;
     __syncthreads();
-    if (rl == 0 && col < N) {
+    if (threadIdx.x < 8 && col < N) {
+        float4 t = s_acc[0][cq];
 #pragma unroll
-        for (int r = 1; r < 32; ++r) {
-            const float4 v = s_acc[r][cq];
-            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        for (int w = 1; w < kColsumSmallThreads / 32; ++w) {
+            const float4 v = s_acc[w][cq];
+            t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
         }
         float4* dst = reinterpret_cast<float4*>(out + col);
         if (accumulate) {
             const float4 o = *dst;
-            s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+            t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
         }
-        *dst = s;
+        *dst = t;
     }
 }
 
@@ -215,7 +222,7 @@ inline int launch_colsum(const float* in, int ld, float* out, float* workspace, 
     DIGAT_REQUIRE(M > 0 && N > 0 && (N & 3) == 0 && (ld & 3) == 0 && aligned16(in) && aligned16(out) && aligned16(workspace),
                   "digat_colsum: N, ld must be multiples of 4 and pointers 16-byte aligned");
     if (M <= kColsumSmallRows && N <= 65536) {
-        colsum_small_kernel<<<(N / 4 + 7) / 8, 256, 0, st>>>(in, ld, out, M, N, accumulate);
+        colsum_small_kernel<<<(N / 4 + 7) / 8, kColsumSmallThreads, 0, st>>>(in, ld, out, M, N, accumulate);
         return check_launch("digat_colsum");
     }
     DIGAT_REQUIRE(!accumulate, "digat_colsum: accumulate is supported for at most %d rows", kColsumSmallRows);
