@@ -12,8 +12,9 @@ util.py:39-50) on the same sm_100a kernels as DIGAT.  Same class names, construc
   User_graph_wo_inter  (:698-842)  news graph the DIGAT layer, user graph vanilla GAT
 
 A vanilla-GAT layer is a degenerate Eq. (8): ``digat_gat_layer_fwd`` runs the edge-driven layer kernel with the edge score
-formed by one add of two per-node dot products, streaming h only.  Inference only (``torch.no_grad`` / eval): the
-training path (autograd_ops.py) covers ``DIGAT``; asking these classes for gradients raises.  Node pruning is off here
+formed by one add of two per-node dot products, streaming h only.  ``wo_SA`` and ``Seq_SA`` consist of the DIGAT layer and
+contexts only and TRAIN through the same autograd nodes (autograd_ops.encode_with_grad with their schedule); the three
+vanilla-GAT variants are inference only (no GAT-layer backward kernel): asking them for gradients raises.  Node pruning is off here
 (every node is projected and evaluated): these are not the benchmarked path."""
 import torch
 import torch.nn as nn
@@ -185,7 +186,7 @@ class _AblationEncoder(DIGAT):
         if torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters())
                                         or any(t.requires_grad for t in tensors)):
             raise RuntimeError('%s: the sm_100a path of the ablation encoders is inference-only (run under torch.no_grad(); '
-                               'training is implemented for graph_encoder=DIGAT)' % type(self).__name__)
+                               'training is implemented for graph_encoder=DIGAT, wo_SA and Seq_SA)' % type(self).__name__)
 
     def compute_news_graph_embeddings(self, index, news_graph_embeddings, news_graph, user_graph_context=None):
         w = self._weights()
@@ -212,8 +213,17 @@ class _AblationEncoder(DIGAT):
             return self._run(w, Xn, An, Mn, self._user_nodes(w, Xh), Au, Mc, ci,
                              _f32c(news_graph_context, 'news_graph_context'))
 
+    TRAIN_SCHEDULE = None        # name of the autograd_ops.encode_with_grad schedule, for the encoders that can train
+
     def forward(self, news_graph_embeddings, news_graph, news_graph_mask, user_news_embedding, user_graph,
                 user_category_mask, user_category_indices):
+        wants_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters())
+                                                  or news_graph_embeddings.requires_grad or user_news_embedding.requires_grad)
+        if wants_grad and self.TRAIN_SCHEDULE is not None:
+            from . import autograd_ops   # training path: the DIGAT layer / context autograd nodes in this encoder's schedule
+            args = self._check_inputs(news_graph_embeddings, news_graph, news_graph_mask, user_news_embedding, user_graph,
+                                      user_category_mask, user_category_indices)
+            return autograd_ops.encode_with_grad(self, *args, schedule=self.TRAIN_SCHEDULE)
         self._no_grad_only(news_graph_embeddings, user_news_embedding)
         w = self._weights()
         Xn, An, Mn, Xh, Au, Mc, ci = self._check_inputs(news_graph_embeddings, news_graph, news_graph_mask,
@@ -229,6 +239,7 @@ class wo_SA(_AblationEncoder):
     NEWS_LAYER = None
     USER_LAYER = 'digat'
     USER_K3_FROM_CONTEXT = False
+    TRAIN_SCHEDULE = 'wo_SA'
 
     def compute_news_graph_context(self, news_graph_embeddings, news_graph_mask):
         raise Exception('wo_SA has no news-graph context (reference graphEncoders.py:201-295)')
@@ -251,6 +262,7 @@ class Seq_SA(_AblationEncoder):
     NEWS_CONTEXT = True
     NEWS_LAYER = None
     USER_LAYER = 'digat'
+    TRAIN_SCHEDULE = 'Seq_SA'
 
     def compute_news_sequence_context(self, news_graph_embeddings, news_graph_mask):
         """util.py:48 calls this instead of compute_news_graph_context (same arithmetic, reference :342-347)."""

@@ -417,8 +417,11 @@ class TopicSegmentFn(Function):
         return dXu, dv, None, None, None, None
 
 
-def encode_with_grad(enc, Xn, An, Mn, Xh, Au, Mc, ci):
-    """Reference DIGAT.forward (graphEncoders.py:177-187) with autograd; dropout active iff enc.training."""
+def encode_with_grad(enc, Xn, An, Mn, Xh, Au, Mc, ci, schedule='digat'):
+    """Reference DIGAT.forward (graphEncoders.py:177-187) with autograd; dropout active iff enc.training.
+    schedule: 'digat' (the dual-graph schedule), or one of the two ablations built from the same pieces --
+    'wo_SA' (graphEncoders.py:277-284: the candidate's own embedding drives L user layers, one user context at the end) and
+    'Seq_SA' (:388-396: a fixed news-sequence context, user layers and contexts as DIGAT)."""
     D, L, H, S = enc.news_embedding_dim, enc.graph_depth, enc.max_history_num, enc.category_num
     p = enc.dropout_rate if enc.training else 0.0
     B = Xn.shape[0]
@@ -431,8 +434,9 @@ def encode_with_grad(enc, Xn, An, Mn, Xh, Au, Mc, ci):
         return F.dropout(x, rate, True) if rate > 0 else x
 
     # differentiable packing of the parameters (same layout as DIGAT._weights)
-    cand, ua = enc.candidate_attention, enc.userAttention
-    cand_Kt, ua_Kt, un_Kt = cand.K.weight.t(), ua.K.weight.t(), enc.user_news_K.weight.t()
+    cand, ua = getattr(enc, 'candidate_attention', None), enc.userAttention          # (wo_SA has no news context)
+    cand_Kt = None if cand is None else cand.K.weight.t()
+    ua_Kt, un_Kt = ua.K.weight.t(), enc.user_news_K.weight.t()
     uq_W = torch.cat([enc.user_news_Q.weight, ua.Q.weight], 0)
     uq_b = torch.cat([enc.user_news_Q.bias, ua.Q.bias], 0)
 
@@ -470,7 +474,10 @@ def encode_with_grad(enc, Xn, An, Mn, Xh, Au, Mc, ci):
             branch = _BRANCH_STREAMS[main.device_index] = torch.cuda.Stream(device=main.device)
     # CSR + transpose of both graph families, once per step (every layer walks the same edges); on the second stream they are
     # built beside the initial contexts
-    if branch is None:
+    if schedule != 'digat':
+        branch = None
+        csr_of = {'user': train_csr(Au)}
+    elif branch is None:
         csr_of = {'news': train_csr(An), 'user': train_csr(Au)}
     else:
         branch.wait_stream(main)
@@ -493,6 +500,22 @@ def encode_with_grad(enc, Xn, An, Mn, Xh, Au, Mc, ci):
         return ProjectedGraphLayerFn.apply(Xd, W.weight, W.bias, f1.weight, f2.weight, k3, av.weight.reshape(D), adj, keep,
                                            1.0 / (1.0 - p) if p > 0 else 1.0, csr_of[g])
 
+    if schedule != 'digat':                                        # single-graph ablations: sequential on the current stream
+        topic = drop(enc.topic_node_embedding.unsqueeze(0).expand(B, -1, -1), p / 2)
+        Xu = torch.cat([Xh, topic], 1)
+        if schedule == 'wo_SA':
+            cand_vec = Xn[:, 0, :]
+            for i in range(L):
+                Xu = layer('user', i, Xu, Au, cand_vec)
+            return cand_vec, user_ctx(Xu, cand_vec)
+        if schedule != 'Seq_SA':
+            raise ValueError('unknown schedule %r' % (schedule,))
+        c_n = news_ctx(Xn)                                          # compute_news_sequence_context: the same gate (:342-347)
+        c_u = user_ctx(Xu, c_n)
+        for i in range(L):
+            Xu = layer('user', i, Xu, Au, c_n)
+            c_u = c_u + user_ctx(Xu, c_n)
+        return c_n, c_u
     topic = drop(enc.topic_node_embedding.unsqueeze(0).expand(B, -1, -1), p / 2)
     Xu = torch.cat([Xh, topic], 1)
     c_n = news_ctx(Xn)
