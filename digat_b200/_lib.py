@@ -51,6 +51,10 @@ SIGNATURES = {
                                   c_int, c_void_p],
     'digat_graph_layer_csr_training_supported': [c_int, c_int],
     'digat_graph_layer_bwd_csr_parts': [],
+    'digat_gat_layer_train_fwd': [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+                                  ctypes.c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    'digat_gat_layer_bwd_csr': [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                ctypes.c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p],
     'digat_grad_sumsq': [c_void_p, c_int64, c_void_p, c_void_p, c_void_p],
     'digat_adam_clip_step': [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p] + [ctypes.c_float] * 6
                             + [c_void_p],

@@ -12,9 +12,9 @@ util.py:39-50) on the same sm_100a kernels as DIGAT.  Same class names, construc
   User_graph_wo_inter  (:698-842)  news graph the DIGAT layer, user graph vanilla GAT
 
 A vanilla-GAT layer is a degenerate Eq. (8): ``digat_gat_layer_fwd`` runs the edge-driven layer kernel with the edge score
-formed by one add of two per-node dot products, streaming h only.  ``wo_SA`` and ``Seq_SA`` consist of the DIGAT layer and
-contexts only and TRAIN through the same autograd nodes (autograd_ops.encode_with_grad with their schedule); the three
-vanilla-GAT variants are inference only (no GAT-layer backward kernel): asking them for gradients raises.  Node pruning is off here
+formed by one add of two per-node dot products, streaming h only.  All five TRAIN through autograd_ops.encode_with_grad
+(``forward`` with gradients enabled): ``wo_SA`` / ``Seq_SA`` as their own schedules of the DIGAT layer and contexts, the
+vanilla-GAT layers through GATLayerFn (digat_gat_layer_train_fwd / digat_gat_layer_bwd_csr); ``inference`` is a no-grad path.  Node pruning is off here
 (every node is projected and evaluated): these are not the benchmarked path."""
 import torch
 import torch.nn as nn
@@ -186,7 +186,7 @@ class _AblationEncoder(DIGAT):
         if torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters())
                                         or any(t.requires_grad for t in tensors)):
             raise RuntimeError('%s: the sm_100a path of the ablation encoders is inference-only (run under torch.no_grad(); '
-                               'training is implemented for graph_encoder=DIGAT, wo_SA and Seq_SA)' % type(self).__name__)
+                               'training goes through forward())' % type(self).__name__)
 
     def compute_news_graph_embeddings(self, index, news_graph_embeddings, news_graph, user_graph_context=None):
         w = self._weights()
@@ -282,18 +282,21 @@ class wo_interaction(_AblationEncoder):
     """Reference graphEncoders.py:410-548: both graphs vanilla GAT."""
     NEWS_LAYER = 'gat'
     USER_LAYER = 'gat'
+    TRAIN_SCHEDULE = 'digat'     # the dual-graph schedule; the layer kinds come from NEWS_LAYER / USER_LAYER
 
 
 class News_graph_wo_inter(_AblationEncoder):
     """Reference graphEncoders.py:551-695."""
     NEWS_LAYER = 'gat'
     USER_LAYER = 'digat'
+    TRAIN_SCHEDULE = 'digat'
 
 
 class User_graph_wo_inter(_AblationEncoder):
     """Reference graphEncoders.py:698-842."""
     NEWS_LAYER = 'digat'
     USER_LAYER = 'gat'
+    TRAIN_SCHEDULE = 'digat'
 
 
 ENCODERS = {'DIGAT': DIGAT, 'wo_SA': wo_SA, 'Seq_SA': Seq_SA, 'wo_interaction': wo_interaction,

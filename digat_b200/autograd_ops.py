@@ -100,10 +100,10 @@ class _Fork:
 class _WgradPlan:
     """Buffers of wgrad(dC, A), allocated up front so that the launches can run on a side stream."""
 
-    def __init__(self, M, N, K, device):
+    def __init__(self, M, N, K, device, force_simt=False):
         self.M, self.N, self.K = M, N, K
         self.dW = torch.empty((N, K), device=device, dtype=torch.float32)
-        self.tensor_path = not (M < WGRAD_TC_MIN_ROWS or (M & 3) != 0 or K > 1280 or (K & 15) != 0 or (N & 3) != 0)
+        self.tensor_path = not (force_simt or M < WGRAD_TC_MIN_ROWS or (M & 3) != 0 or K > 1280 or (K & 15) != 0 or (N & 3) != 0)
         if not self.tensor_path:
             self.ws = _workspace(M, N, K, device)
             return
@@ -173,7 +173,8 @@ class LinearFn(Function):
     def forward(ctx, A, W, bias, group_bias, group_rows, group_col0):
         M, K = A.shape
         N = W.shape[0]
-        ctx.small = M <= SMALL_GEMM_ROWS and group_bias is None and (K & 3) == 0 and (N & 3) == 0
+        # (N < 16: the two attention columns of a vanilla-GAT layer over all node rows -- too thin for a tensor-core tile)
+        ctx.small = (M <= SMALL_GEMM_ROWS or N < 16) and group_bias is None and (K & 3) == 0 and (N & 3) == 0
         ctx.has_bias = bias is not None
         ctx.group = None if group_bias is None else (group_rows, group_col0, group_bias.shape[1])
         if ctx.small:
@@ -197,11 +198,15 @@ class LinearFn(Function):
         if ctx.small:
             dC = _rows16(dC)
             dev = dC.device
+            tall = M > SMALL_GEMM_ROWS                                 # thin-and-tall: the contraction needs row slices
+            plan = _WgradPlan(M, N, K, dev, force_simt=True) if (tall and ctx.needs_input_grad[1]) else None
             if ctx.needs_input_grad[1]:
-                dW = torch.empty((N, K), device=dev, dtype=torch.float32)
+                dW = plan.dW if plan is not None else torch.empty((N, K), device=dev, dtype=torch.float32)
             db_bufs = colsum_bufs(M, N, dev) if want_db else None
             with _Fork(ctx.needs_input_grad[0]) as side:               # weight / bias gradients beside the dgrad product
-                if dW is not None:
+                if plan is not None:
+                    plan.run(dC, A)
+                elif dW is not None:
                     _small_gemm(dC, True, A, False, A.stride(0), None, N, K, M, out=dW)
                 if want_db:
                     db = colsum(dC, db_bufs)
@@ -335,6 +340,44 @@ class ProjectedGraphLayerFn(Function):
         dXd += dY                                                      # the residual path
         side.join()
         return dXd, dWcat[:D], dWb, dWcat[D:2 * D], dWcat[2 * D:], dk3, da, None, None, None, None
+
+
+class GATLayerFn(Function):
+    """Vanilla-GAT layer of the ablation encoders (reference graphEncoders.py:494-503): Y = relu(softmax(mask(leaky_relu(s1_j +
+    s2_i))) h) + X, edge-driven both ways (digat_gat_layer_train_fwd / digat_gat_layer_bwd_csr).  s12 [B*n, >=2]: column 0 =
+    a1.h (neighbour term), column 1 = a2.h (query term); wider inputs (zero-padded weights) are read through their first two."""
+
+    @staticmethod
+    def forward(ctx, h, s12, adj, X, drop_keep, drop_scale, csr):
+        B, n, D = X.shape
+        h, X = h.contiguous(), X.contiguous()
+        s2 = s12[:, :2].contiguous()
+        score = torch.empty((B, n * n), device=X.device, dtype=torch.float32)
+        alpha = torch.empty((B, n * n), device=X.device, dtype=torch.float32)
+        rmask = torch.empty((B, n, D), device=X.device, dtype=torch.uint8)
+        Y = torch.empty((B, n, D), device=X.device, dtype=torch.float32)
+        _lib.call('digat_gat_layer_train_fwd', h.data_ptr(), h.stride(0), s2.data_ptr(), adj.data_ptr(), X.data_ptr(), Y.data_ptr(),
+                  B, n, D, _ptr(drop_keep), float(drop_scale), score.data_ptr(), alpha.data_ptr(), rmask.data_ptr(),
+                  csr[0].data_ptr(), csr[1].data_ptr(), _stream())
+        ctx.save_for_backward(h, score, alpha, rmask)
+        ctx.extra = (drop_keep, float(drop_scale), csr, s12.shape[1], (B, n, D))
+        return Y
+
+    @staticmethod
+    def backward(ctx, dY):
+        h, score, alpha, rmask = ctx.saved_tensors
+        keep, scale, csr, s_cols, (B, n, D) = ctx.extra
+        dY = dY.contiguous()
+        dh = torch.empty_like(h)
+        ds12 = torch.zeros((B * n, s_cols), device=h.device, dtype=torch.float32)
+        ds2 = ds12 if s_cols == 2 else torch.empty((B * n, 2), device=h.device, dtype=torch.float32)
+        rowptr, meta, colptr, cedge = csr
+        _lib.call('digat_gat_layer_bwd_csr', h.data_ptr(), h.stride(0), rowptr.data_ptr(), meta.data_ptr(), colptr.data_ptr(),
+                  cedge.data_ptr(), score.data_ptr(), alpha.data_ptr(), _ptr(keep), scale, dY.data_ptr(), rmask.data_ptr(),
+                  dh.data_ptr(), dh.stride(0), ds2.data_ptr(), B, n, D, _stream())
+        if s_cols != 2:
+            ds12[:, :2] = ds2
+        return dh, ds12, None, dY, None, None, None
 
 
 class AttentionPoolFn(Function):
@@ -500,6 +543,24 @@ def encode_with_grad(enc, Xn, An, Mn, Xh, Au, Mc, ci, schedule='digat'):
         return ProjectedGraphLayerFn.apply(Xd, W.weight, W.bias, f1.weight, f2.weight, k3, av.weight.reshape(D), adj, keep,
                                            1.0 / (1.0 - p) if p > 0 else 1.0, csr_of[g])
 
+    def gat_layer(g, i, X, adj, ctx_other=None):
+        """Vanilla-GAT layer (reference :494-503 / :511-520): h = W x + b, s1 = a1.h, s2 = a2.h per node, edge-driven layer."""
+        n = X.shape[1]
+        W = getattr(enc, g + '_graph_attention_W')[i]
+        a1 = getattr(enc, g + '_graph_attention_a1')[i]
+        a2 = getattr(enc, g + '_graph_attention_a2')[i]
+        if csr_of[g] is None:
+            raise RuntimeError('vanilla-GAT training needs the edge-driven kernels (graph of %d nodes does not fit)' % n)
+        Xd = drop(X, p / 2)
+        h = lin(Xd.reshape(B * n, D), W.weight, W.bias)
+        a12 = torch.cat([a1.weight, a2.weight, a1.weight.new_zeros((2, D))], 0)       # [4, D]: zero rows keep the GEMM shapes legal
+        s12 = lin(h, a12)
+        keep = (torch.rand((B, n, n), device=dev) >= p) if p > 0 else None
+        return GATLayerFn.apply(h, s12, adj, Xd, keep, 1.0 / (1.0 - p) if p > 0 else 1.0, csr_of[g])
+
+    news_layer = gat_layer if getattr(enc, 'NEWS_LAYER', 'digat') == 'gat' else layer
+    user_layer = gat_layer if getattr(enc, 'USER_LAYER', 'digat') == 'gat' else layer
+
     if schedule != 'digat':                                        # single-graph ablations: sequential on the current stream
         topic = drop(enc.topic_node_embedding.unsqueeze(0).expand(B, -1, -1), p / 2)
         Xu = torch.cat([Xh, topic], 1)
@@ -524,8 +585,8 @@ def encode_with_grad(enc, Xn, An, Mn, Xh, Au, Mc, ci, schedule='digat'):
         main.wait_stream(branch)                                   # the CSR records
     if branch is None:
         for i in range(L):
-            Xn_new = layer('news', i, Xn, An, c_u)
-            Xu = layer('user', i, Xu, Au, c_n)
+            Xn_new = news_layer('news', i, Xn, An, c_u)
+            Xu = user_layer('user', i, Xu, Au, c_n)
             Xn = Xn_new
             c_n = news_ctx(Xn, c_n)
             c_u = c_u + user_ctx(Xu, c_n)
@@ -540,9 +601,9 @@ def encode_with_grad(enc, Xn, An, Mn, Xh, Au, Mc, ci, schedule='digat'):
         with torch.cuda.stream(branch):
             if i > 0:
                 c_u = c_u + user_ctx(Xu, c_n)                      # context of the previous iteration's user graph
-            Xn_new = layer('news', i, Xn, An, c_u)
+            Xn_new = news_layer('news', i, Xn, An, c_u)
             c_n_new = news_ctx(Xn_new, c_n)
-        Xu_new = layer('user', i, Xu, Au, c_n)
+        Xu_new = user_layer('user', i, Xu, Au, c_n)
         main.wait_stream(branch)
         for t in (Xn_new, c_n_new, c_u):
             t.record_stream(main)

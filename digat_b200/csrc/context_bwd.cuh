@@ -118,8 +118,11 @@ struct SegBwdArgs {
 //   dXh_t = alpha_t dT_{c(t)} + ds_t v ;  dv = sum_t ds_t Xh_t
 __global__ void __launch_bounds__(kCtxThreads)
 topic_segment_bwd_kernel(SegBwdArgs p) {
-    __shared__ float s_part[kCtxMaxItems][kCtxWarps];
-    __shared__ float s_da[kCtxMaxItems];
+    // dalpha_t and the segment means are kept in DOUBLE: ds_t = alpha_t (dalpha_t - sum_k alpha_k dalpha_k) cancels when the
+    // history rows of a segment are alike (after smoothing graph layers they are), and an fp32 dot product's 1e-7 then shows up
+    // as 3e-5 in the gradients of user_news_K / user_news_Q (measured on the vanilla-GAT ablation, torch's fp32 autograd: 1e-6)
+    __shared__ double s_part[kCtxMaxItems][kCtxWarps];
+    __shared__ double s_da[kCtxMaxItems];
     __shared__ float s_ds[kCtxMaxItems];
     __shared__ float s_al[kCtxMaxItems];
     __shared__ int s_seg[kCtxMaxItems];
@@ -149,14 +152,14 @@ topic_segment_bwd_kernel(SegBwdArgs p) {
                 d[u][c] = q < nq ? reinterpret_cast<const float4*>(drow)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
-        float part[kRows];
+        double part[kRows];
 #pragma unroll
         for (int u = 0; u < kRows; ++u) {
-            part[u] = 0.f;
+            part[u] = 0.0;
 #pragma unroll
             for (int c = 0; c < kCtxMaxQuads; ++c) {
-                part[u] = fmaf(x[u][c].x, d[u][c].x, part[u]); part[u] = fmaf(x[u][c].y, d[u][c].y, part[u]);
-                part[u] = fmaf(x[u][c].z, d[u][c].z, part[u]); part[u] = fmaf(x[u][c].w, d[u][c].w, part[u]);
+                part[u] += (double)x[u][c].x * d[u][c].x + (double)x[u][c].y * d[u][c].y +
+                           (double)x[u][c].z * d[u][c].z + (double)x[u][c].w * d[u][c].w;
             }
         }
 #pragma unroll
@@ -171,7 +174,7 @@ topic_segment_bwd_kernel(SegBwdArgs p) {
     }
     __syncthreads();
     if (tid < H) {
-        float s = 0.f;
+        double s = 0.0;
 #pragma unroll
         for (int w = 0; w < kCtxWarps; ++w) s += s_part[tid][w];
         s_da[tid] = s;
@@ -179,10 +182,10 @@ topic_segment_bwd_kernel(SegBwdArgs p) {
     __syncthreads();
     if (tid < H) {
         const int me = s_seg[tid];
-        float tt = 0.f;
+        double tt = 0.0;
         for (int t = 0; t < H; ++t)
-            if (s_seg[t] == me) tt = fmaf(s_al[t], s_da[t], tt);
-        s_ds[tid] = s_al[tid] * (s_da[tid] - tt) / sqrtf((float)D);
+            if (s_seg[t] == me) tt += (double)s_al[t] * s_da[t];
+        s_ds[tid] = (float)((double)s_al[tid] * (s_da[tid] - tt) / sqrt((double)D));
     }
     __syncthreads();
 #pragma unroll

@@ -260,6 +260,24 @@ int digat_adam_clip_step(float* p, float* g, float* m, float* v, int64_t n, cons
 
 int digat_graph_layer_bwd_csr_parts(void) { return kSbwdParts; }
 
+int digat_gat_layer_train_fwd(const float* Hm, int ldh, const float* s12, const uint8_t* adj, const float* X, float* Y,
+                              int B, int n, int D, const uint8_t* drop_keep, float drop_scale, float* edge_score,
+                              float* edge_alpha, uint8_t* relu_mask, const uint16_t* csr_rowptr, const uint16_t* csr_meta,
+                              void* stream) {
+    return launch_gat_layer_train_fwd(Hm, ldh, s12, adj, X, Y, B, n, D, drop_keep, drop_scale, edge_score, edge_alpha, relu_mask,
+                                      csr_rowptr, csr_meta, as_stream(stream));
+}
+
+int digat_gat_layer_bwd_csr(const float* Hm, int ldh, const uint16_t* csr_rowptr, const uint16_t* csr_meta,
+                            const uint16_t* csc_colptr, const uint16_t* csc_edge, const float* edge_score, const float* edge_alpha,
+                            const uint8_t* drop_keep, float drop_scale, const float* dY, const uint8_t* relu_mask, float* dH,
+                            int lddh, float* ds12, int B, int n, int D, void* stream) {
+    if (B > 0 && ds12 == nullptr) return fail(DIGAT_E_INVALID, "digat_gat_layer_bwd_csr: null ds12");
+    return launch_graph_layer_bwd_csr(Hm, ldh, nullptr, csr_rowptr, csr_meta, csc_colptr, csc_edge, edge_score, edge_alpha,
+                                      drop_keep, drop_scale, dY, relu_mask, dH, lddh, nullptr, nullptr, nullptr, B, n, D,
+                                      as_stream(stream), ds12);
+}
+
 int digat_graph_layer_csr_training_supported(int n, int D) { return graph_layer_csr_training_supported(n, D); }
 
 int digat_attention_pool_bwd(const float* F, int64_t strideF, int ldf, const float* resid_F, const float* v,

@@ -660,4 +660,29 @@ inline int launch_gat_layer_fwd(const float* Hm, int ldh, const float* s12, cons
     return launch_graph_layer_fwd_sparse(args, B, st);
 }
 
+// Training forward of the vanilla-GAT layer: the same launch with the attention dropout and the per-edge score / alpha / relu
+// mask outputs of the edge-driven training path (precomputed CSR required), for digat_gat_layer_bwd_csr.
+inline int launch_gat_layer_train_fwd(const float* Hm, int ldh, const float* s12, const uint8_t* adj, const float* X, float* Y,
+                                      int B, int n, int D, const uint8_t* drop_keep, float drop_scale, float* edge_score,
+                                      float* edge_alpha, uint8_t* relu_mask, const uint16_t* csr_rowptr, const uint16_t* csr_meta,
+                                      cudaStream_t st) {
+    if (B == 0) return DIGAT_OK;
+    DIGAT_REQUIRE(Hm && s12 && adj && X && Y && edge_score && edge_alpha && relu_mask && csr_rowptr && csr_meta,
+                  "digat_gat_layer_train_fwd: null pointer");
+    DIGAT_REQUIRE(B >= 0 && n >= 1 && n <= kPairMaxNodes, "digat_gat_layer_train_fwd: n=%d outside [1,%d]", n, kPairMaxNodes);
+    DIGAT_REQUIRE(D >= 4 && (D & 3) == 0 && D <= 1024, "digat_gat_layer_train_fwd: D=%d must be a multiple of 4 in [4,1024]", D);
+    DIGAT_REQUIRE((ldh & 3) == 0 && ldh >= D, "digat_gat_layer_train_fwd: ldh=%d must be a multiple of 4 and >= D", ldh);
+    DIGAT_REQUIRE(aligned16(Hm) && aligned16(X) && aligned16(Y), "digat_gat_layer_train_fwd: pointers must be 16-byte aligned");
+    const DeviceInfo* di = device_info();
+    if (!di) return fail(DIGAT_E_CUDA, "digat_gat_layer_train_fwd: no CUDA device");
+    DIGAT_REQUIRE(graph_layer_fwd_sparse_smem(n, D) <= (size_t)di->max_smem_optin,
+                  "digat_gat_layer_train_fwd: a graph of %d nodes x %d features does not fit one CTA", n, D);
+    PairAttnArgs args{Hm, ldh, nullptr, adj, X, Y, B, n, D, drop_keep, drop_scale, edge_score, edge_alpha, relu_mask,
+                      nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr};
+    args.gat_s = s12;
+    args.csr_rowptr = csr_rowptr;
+    args.csr_meta = csr_meta;
+    return launch_graph_layer_fwd_sparse(args, B, st);
+}
+
 }  // namespace digat

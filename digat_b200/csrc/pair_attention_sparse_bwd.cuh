@@ -33,6 +33,8 @@ struct SparseBwdArgs {
     const float* P; int ldp; const float* a; const float* G;
     const uint8_t* relu_mask;      // [B,n,D] or null: G is dY and the saved mask of Z > 0 is applied to the staged tile
     float* dh_sum; float* du_sum;  // [B*kSbwdParts, D] each or null: per-warp column sums of dh (-> bias gradient) and dU (-> dk3)
+    float* gat_ds12;               // [B*n, 2] or null.  Non-null = vanilla-GAT layer (e_ij = leaky_relu(s1_j + s2_i)): P holds h only,
+                                   // pass C is replaced by ds1_j = sum over column j of ds_e, ds2_i = sum over row i of ds_e
     const uint16_t* rowptr; const uint16_t* meta; const uint16_t* colptr; const uint16_t* cedge;
     const float* e_score; const float* e_alpha; const uint8_t* drop_keep; float drop_scale;
     float* dP; int lddp; float* da_partial;
@@ -74,7 +76,8 @@ graph_layer_bwd_sparse_kernel(const __grid_constant__ CUtensorMap mapG, const __
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const int n_loads = 2 * g.nch;
+    const bool gat = p.gat_ds12 != nullptr;
+    const int n_loads = gat ? g.nch : 2 * g.nch;
 
     if (warp == kSparseConsumers / 32) {
         // ------------------------------------------------------------------ producer: (G, h) chunks, then (U, K2) chunks
@@ -97,7 +100,8 @@ graph_layer_bwd_sparse_kernel(const __grid_constant__ CUtensorMap mapG, const __
     }
 
     // ---------------------------------------------------------------------- setup: CSR + transpose, alpha~, zeroed accumulators
-    for (int i = tid; i < D; i += kSparseConsumers) a_s[i] = p.a[i];
+    if (!gat)
+        for (int i = tid; i < D; i += kSparseConsumers) a_s[i] = p.a[i];
     {
         const uint16_t* rp = p.rowptr + (size_t)b * (n + 1);
         const uint16_t* cp = p.colptr + (size_t)b * (n + 1);
@@ -228,6 +232,17 @@ graph_layer_bwd_sparse_kernel(const __grid_constant__ CUtensorMap mapG, const __
     }
     consumer_sync();
 
+    if (gat) {
+        // vanilla GAT: the score of edge (i, j) is s1_j + s2_i, so its gradient goes to two per-node scalars
+        for (int node = tid; node < n; node += kSparseConsumers) {
+            float d1 = 0.f, d2 = 0.f;
+            for (int ce = colptr[node]; ce < colptr[node + 1]; ++ce) d1 += dal[cedge[ce]];
+            for (int e = rowptr[node]; e < rowptr[node + 1]; ++e) d2 += dal[e];
+            *reinterpret_cast<float2*>(p.gat_ds12 + ((size_t)b * n + node) * 2) = make_float2(d1, d2);
+        }
+        return;
+    }
+
     // ---------------------------------------------------------------------- pass C: dK2 (rows), dU (columns), da
     for (int l = g.nch; l < n_loads; ++l) {
         const int buf = l % kSbwdBufs;
@@ -294,15 +309,17 @@ inline int launch_graph_layer_bwd_csr(const float* P, int ldp, const float* a, c
                                       const uint16_t* colptr, const uint16_t* cedge, const float* e_score, const float* e_alpha,
                                       const uint8_t* drop_keep, float drop_scale, const float* G, const uint8_t* relu_mask,
                                       float* dP, int lddp, float* da_partial, float* dh_sum, float* du_sum, int B, int n, int D,
-                                      cudaStream_t st) {
+                                      cudaStream_t st, float* gat_ds12 = nullptr) {
     if (B == 0) return DIGAT_OK;
-    DIGAT_REQUIRE(P && a && rowptr && meta && colptr && cedge && e_score && e_alpha && G && dP && da_partial,
+    const bool gat = gat_ds12 != nullptr;
+    const int pc = gat ? D : 3 * D;                                   // columns of P / dP: h only for a vanilla-GAT layer
+    DIGAT_REQUIRE(P && rowptr && meta && colptr && cedge && e_score && e_alpha && G && dP && (gat || (a && da_partial)),
                   "digat_graph_layer_bwd_csr: null pointer");
     DIGAT_REQUIRE(B >= 0 && n >= 1 && n <= kPairMaxNodes, "digat_graph_layer_bwd_csr: n=%d outside [1,%d]", n, kPairMaxNodes);
     DIGAT_REQUIRE(D >= 4 && (D & 3) == 0 && D <= 1024, "digat_graph_layer_bwd_csr: D=%d must be a multiple of 4 in [4,1024]", D);
-    DIGAT_REQUIRE((ldp & 3) == 0 && ldp >= 3 * D && (lddp & 3) == 0 && lddp >= 3 * D,
-                  "digat_graph_layer_bwd_csr: ldp / lddp must be multiples of 4 and >= 3D");
-    DIGAT_REQUIRE(aligned16(P) && aligned16(a) && aligned16(G) && aligned16(dP),
+    DIGAT_REQUIRE((ldp & 3) == 0 && ldp >= pc && (lddp & 3) == 0 && lddp >= pc,
+                  "digat_graph_layer_bwd_csr: ldp / lddp must be multiples of 4 and >= 3D (D for a vanilla-GAT layer)");
+    DIGAT_REQUIRE(aligned16(P) && (gat || aligned16(a)) && aligned16(G) && aligned16(dP) && (!gat || (reinterpret_cast<uintptr_t>(gat_ds12) & 7) == 0),
                   "digat_graph_layer_bwd_csr: pointers must be 16-byte aligned");
     SparseBwdGeom g;
     sparse_bwd_geometry(n, D, &g);
@@ -314,11 +331,11 @@ inline int launch_graph_layer_bwd_csr(const float* P, int ldp, const float* a, c
     CUtensorMap mapG, mapP;
     int rc;
     if ((rc = make_tensor_map_2d(&mapG, G, (int64_t)B * n, D, D, n, kSbwdDc, CU_TENSOR_MAP_SWIZZLE_128B)) != DIGAT_OK) return rc;
-    if ((rc = make_tensor_map_2d(&mapP, P, (int64_t)B * n, 3 * D, ldp, n, kSbwdDc, CU_TENSOR_MAP_SWIZZLE_128B)) != DIGAT_OK) return rc;
-    DIGAT_REQUIRE(aligned16(da_partial) && (!dh_sum || aligned16(dh_sum)) && (!du_sum || aligned16(du_sum)),
+    if ((rc = make_tensor_map_2d(&mapP, P, (int64_t)B * n, pc, ldp, n, kSbwdDc, CU_TENSOR_MAP_SWIZZLE_128B)) != DIGAT_OK) return rc;
+    DIGAT_REQUIRE((gat || aligned16(da_partial)) && (!dh_sum || aligned16(dh_sum)) && (!du_sum || aligned16(du_sum)),
                   "digat_graph_layer_bwd_csr: da_partial / dh_sum / du_sum must be 16-byte aligned");
-    SparseBwdArgs args{P, ldp, a, G, relu_mask, dh_sum, du_sum, rowptr, meta, colptr, cedge, e_score, e_alpha, drop_keep, drop_scale,
-                       dP, lddp, da_partial, B, n, D};
+    SparseBwdArgs args{P, ldp, a, G, relu_mask, dh_sum, du_sum, gat_ds12, rowptr, meta, colptr, cedge, e_score, e_alpha, drop_keep,
+                       drop_scale, dP, lddp, da_partial, B, n, D};
     if (int rc_ = ensure_dynamic_smem(graph_layer_bwd_sparse_kernel, g.smem)) return rc_;
     graph_layer_bwd_sparse_kernel<<<B, kSparseThreads, g.smem, st>>>(mapG, mapP, args, g);
     return check_launch("digat_graph_layer_bwd_csr");

@@ -286,6 +286,22 @@ int digat_graph_layer_bwd_csr(const float* P, int ldp, const float* a, const uin
                               const uint8_t* relu_mask, float* dP, int lddp, float* da_partial, float* dh_sum, float* du_sum,
                               int B, int n, int D, void* stream);
 int digat_graph_layer_bwd_csr_parts(void);
+/* Training pair of the vanilla-GAT layer (digat_gat_layer_fwd: e_ij = leaky_relu(s12[j,0] + s12[i,1]), Y = relu(alpha~ h) + X),
+ * edge-driven like the pair above; the CSR and its transpose come from digat_build_graph_csr:
+ *   digat_gat_layer_train_fwd  as digat_gat_layer_fwd, plus the attention dropout (drop_keep [B,n,n] or NULL, drop_scale) and
+ *                              the outputs the backward needs: edge_score / edge_alpha [B, n*n] in CSR order, relu_mask [B,n,D]
+ *   digat_gat_layer_bwd_csr    dY [B,n,D] (raw: the relu mask is applied in-kernel) -> dH [B*n, lddh] (gradient of h through the
+ *                              aggregation) and ds12 [B*n, 2] (ds1_j = sum over the edges entering j of ds_e, ds2_i = sum over
+ *                              row i of ds_e); the gradient of X through the residual is dY itself.  The caller adds
+ *                              ds12 [a1; a2] to dH and forms da1 / da2 (the backward of its s12 = h [a1; a2]^T product). */
+int digat_gat_layer_train_fwd(const float* Hm, int ldh, const float* s12, const uint8_t* adj, const float* X, float* Y,
+                              int B, int n, int D, const uint8_t* drop_keep, float drop_scale, float* edge_score,
+                              float* edge_alpha, uint8_t* relu_mask, const uint16_t* csr_rowptr, const uint16_t* csr_meta,
+                              void* stream);
+int digat_gat_layer_bwd_csr(const float* Hm, int ldh, const uint16_t* csr_rowptr, const uint16_t* csr_meta,
+                            const uint16_t* csc_colptr, const uint16_t* csc_edge, const float* edge_score, const float* edge_alpha,
+                            const uint8_t* drop_keep, float drop_scale, const float* dY, const uint8_t* relu_mask, float* dH,
+                            int lddh, float* ds12, int B, int n, int D, void* stream);
 /* 1 when graphs of n nodes and width D can train through the CSR pair (digat_graph_layer_fwd with a CSR and training
  * outputs + digat_graph_layer_bwd_csr): both working sets fit one SM.  0: use the dense [B,n,n] score / alpha path. */
 int digat_graph_layer_csr_training_supported(int n, int D);

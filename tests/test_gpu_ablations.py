@@ -56,21 +56,24 @@ def test_ablation_encoder_matches_reference_golden(kind, case, rep):
     assert torch.equal(lm, lg)
 
 
-def test_ablation_encoders_refuse_to_train():
-    from digat_b200 import synth
+def test_ablation_inference_entry_point_refuses_gradients():
+    """`inference` (the cached-context scoring entry point) is a no-grad path; training goes through `forward`."""
     from digat_b200.ablation_encoders import wo_interaction
     cfg, sd, batch = ablation_inputs('wo_interaction', 'n3_L2')
     enc = wo_interaction(cfg, 400)
     enc.load_state_dict(sd)
     enc = enc.cuda().train()
     with pytest.raises(RuntimeError):
-        enc(*[batch[k].cuda() for k in ORDER])
+        enc.inference(*[batch[k].cuda() for k in ORDER], torch.zeros(batch['news_graph'].shape[0], 400, device='cuda'))
 
 
-@pytest.mark.parametrize('kind,case', [('wo_SA', 'n3_L2'), ('Seq_SA', 'n3_L2'), ('Seq_SA', 'n5_L3')])
+@pytest.mark.parametrize('kind,case', [('wo_SA', 'n3_L2'), ('Seq_SA', 'n3_L2'), ('Seq_SA', 'n5_L3'), ('wo_interaction', 'n3_L2'),
+                                       ('wo_interaction', 'n5_L3'), ('news_graph_wo_inter', 'n3_L2'),
+                                       ('user_graph_wo_inter', 'n5_L3')])
 def test_trainable_ablations_gradients_match_oracle(kind, case):
-    """wo_SA and Seq_SA are built from the DIGAT layer and contexts only: their training forward + backward (p = 0, train mode)
-    against the fp64 autograd of the oracle restatement, every parameter and both embedding inputs."""
+    """Training forward + backward of the ablation encoders (p = 0, train mode) against the fp64 autograd of the oracle
+    restatement, every parameter and both embedding inputs: wo_SA / Seq_SA (DIGAT layer and contexts only) and the three
+    vanilla-GAT variants (digat_gat_layer_train_fwd / digat_gat_layer_bwd_csr)."""
     from oracle import digat_oracle as O
     from digat_b200.ablation_encoders import ENCODERS
     cfg, sd, batch = ablation_inputs(kind, case)
@@ -91,6 +94,7 @@ def test_trainable_ablations_gradients_match_oracle(kind, case):
         grads['in:news'], grads['in:hist'] = b['news_graph_embeddings'].grad, b['user_news_embedding'].grad
         return grads, float(loss)
     ref64, l64 = oracle(torch.float64)
+    ref32, _ = oracle(torch.float32)                         # the reference arithmetic's own fp32 error, per tensor
     enc = ENCODERS[kind](cfg, 400)
     enc.load_state_dict(sd)
     enc = enc.cuda().train()
@@ -104,15 +108,20 @@ def test_trainable_ablations_gradients_match_oracle(kind, case):
     assert abs(float(loss) - l64) / abs(l64) < 1e-5
     ours = {k: v.grad for k, v in enc.named_parameters()}
     ours['in:news'], ours['in:hist'] = b['news_graph_embeddings'].grad, b['user_news_embedding'].grad
-    worst = 0.0
+    worst, bad = 0.0, []
     for k, want in ref64.items():
         if want is None:                                     # a parameter this schedule does not touch
             assert ours[k] is None or float(ours[k].abs().max()) == 0.0
             continue
         assert ours[k] is not None, 'no gradient for ' + k
-        worst = max(worst, rel_err(ours[k].cpu().numpy(), want.numpy()))
-        assert rel_err(ours[k].cpu().numpy(), want.numpy()) < 2e-5, k
+        e64, eref = rel_err(ours[k].cpu().numpy(), want.numpy()), rel_err(ref32[k].numpy(), want.numpy())
+        worst = max(worst, e64)
+        print('   grad %-42s ours vs fp64 %.2e   oracle fp32 vs fp64 %.2e' % (k, e64, eref))
+        # gate: 2e-5, or four times the fp32 error of the reference arithmetic itself where that is larger (three stacked
+        # vanilla-GAT layers on 3 rows are that ill-conditioned: the torch fp32 oracle is off by 1e-5 there)
+        bad = bad + [(k, e64, eref)] if e64 >= max(2e-5, 4 * eref) else bad
     print('%s %s: worst gradient rel err vs fp64 %.3e' % (kind, case, worst))
+    assert not bad, bad
     # dropout on: runs, finite, stochastic
     cfg.dropout_rate = 0.2
     enc2 = ENCODERS[kind](cfg, 400)
