@@ -185,8 +185,8 @@ class _AblationEncoder(DIGAT):
     def _no_grad_only(self, *tensors):
         if torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters())
                                         or any(t.requires_grad for t in tensors)):
-            raise RuntimeError('%s: the sm_100a path of the ablation encoders is inference-only (run under torch.no_grad(); '
-                               'training goes through forward())' % type(self).__name__)
+            raise RuntimeError('%s: this entry point is a no-grad path (run it under torch.no_grad(); training goes through '
+                               'forward())' % type(self).__name__)
 
     def compute_news_graph_embeddings(self, index, news_graph_embeddings, news_graph, user_graph_context=None):
         w = self._weights()
