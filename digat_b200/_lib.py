@@ -76,6 +76,11 @@ SIGNATURES = {
     'digat_msa_attention_fwd': [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_int, c_int, c_void_p],
     'digat_additive_pool_fwd': [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int,
                                 c_void_p],
+    'digat_msa_attention_bwd': [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_int, c_int,
+                                c_void_p],
+    'digat_additive_pool_bwd': [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p,
+                                c_int, c_void_p, c_int64, c_int, c_int, c_int, c_void_p],
+    'digat_scatter_add_rows': [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p],
     'digat_rank_impressions': [c_void_p, c_void_p, c_void_p, c_int64, c_void_p],
     'digat_impression_metrics': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p],
 }

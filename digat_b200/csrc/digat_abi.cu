@@ -348,6 +348,23 @@ int digat_sag_bfs(const int64_t* sim_off, const int32_t* sim_idx, const double* 
                           err_flag, as_stream(stream));
 }
 
+int digat_msa_attention_bwd(const float* QKV, int ld, const float* H, int ldh, const float* dH, int lddh, float* dQKV, int ldd,
+                            int64_t n_titles, int T, int heads, int dk, void* stream) {
+    return launch_msa_attention_bwd(QKV, ld, H, ldh, dH, lddh, dQKV, ldd, n_titles, T, heads, dk, as_stream(stream));
+}
+
+int digat_additive_pool_bwd(const float* att_pre, int lda, const float* w2, const float* H, int ldh, const uint8_t* mask,
+                            const float* dout, int ldo, float* dH, int lddh, float* datt, int ldda, float* dw2_part,
+                            int64_t n_titles, int T, int A, int D, void* stream) {
+    return launch_additive_pool_bwd(att_pre, lda, w2, H, ldh, mask, dout, ldo, dH, lddh, datt, ldda, dw2_part, n_titles, T, A, D,
+                                    as_stream(stream));
+}
+
+int digat_scatter_add_rows(float* dtable, int64_t n_table, const int32_t* idx, const float* src, int64_t lds, int64_t rows, int D,
+                           void* stream) {
+    return launch_scatter_add_rows(dtable, n_table, idx, src, lds, rows, D, as_stream(stream));
+}
+
 int digat_rank_impressions(const float* scores, const int64_t* offsets, int32_t* ranks, int64_t n_imp, void* stream) {
     return launch_rank_impressions(scores, offsets, ranks, n_imp, as_stream(stream));
 }

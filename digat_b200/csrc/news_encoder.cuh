@@ -145,4 +145,234 @@ inline int launch_additive_pool(const float* att_pre, int lda, const float* w2, 
     return check_launch("digat_additive_pool_fwd");
 }
 
+// ------------------------------------------------------------------------------------------------ backward (training)
+// msa_attention_bwd_kernel: one warp per (title, head), as the forward.  The T x T attention matrix is recomputed from the
+// saved Q | K | V rows; lane i owns query row i (p_i., d p_i., dS_i. in registers -> dQ_i), writes its rows of P and dS to the
+// warp's shared-memory slice, and then owns key row i for the transposed sums dK_i = sum_q dS[q][i] Q_q, dV_i = sum_q P[q][i] dO_q.
+// dO = dH * 1[H > 0] (the relu of newsEncoders.py:78) is applied while staging.
+constexpr int kMsaBwdWarps = 4;
+
+__global__ void __launch_bounds__(kMsaBwdWarps * 32)
+msa_attention_bwd_kernel(const float* __restrict__ QKV, int ld, const float* __restrict__ H, int ldh, const float* __restrict__ dH,
+                         int lddh, float* __restrict__ dQKV, int ldd, int64_t n_titles, int T, int heads, int dk, float scale_div) {
+    extern __shared__ float msa_smem[];                             // per warp: Q, K, V, dO [T*dk] each, P, dS [T][33] each
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t unit = (int64_t)blockIdx.x * kMsaBwdWarps + warp;
+    if (unit >= n_titles * heads) return;
+    const int64_t title = unit / heads;
+    const int head = (int)(unit - title * heads);
+    const int hd = heads * dk;
+    float* Qs = msa_smem + (size_t)warp * (4 * T * dk + 2 * T * 33);
+    float* Ks = Qs + T * dk;
+    float* Vs = Ks + T * dk;
+    float* dOs = Vs + T * dk;
+    float* Ps = dOs + T * dk;
+    float* dSs = Ps + T * 33;
+    const float* base = QKV + (size_t)title * T * ld + head * dk;
+    for (int e = lane; e < T * dk; e += 32) {
+        const int t = e / dk, d = e - t * dk;
+        Qs[e] = base[(size_t)t * ld + d];
+        Ks[e] = base[(size_t)t * ld + hd + d];
+        Vs[e] = base[(size_t)t * ld + 2 * hd + d];
+        const size_t hrow = (size_t)title * T + t;
+        dOs[e] = H[hrow * ldh + head * dk + d] > 0.f ? dH[hrow * lddh + head * dk + d] : 0.f;
+    }
+    __syncwarp();
+    const int i = lane;
+    if (i < T) {
+        float q[kMsaMaxDk], go[kMsaMaxDk], dq[kMsaMaxDk];
+#pragma unroll
+        for (int d = 0; d < kMsaMaxDk; ++d) {
+            q[d] = d < dk ? Qs[i * dk + d] : 0.f;
+            go[d] = d < dk ? dOs[i * dk + d] : 0.f;
+            dq[d] = 0.f;
+        }
+        float pr[kMsaMaxT], dp[kMsaMaxT];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < kMsaMaxT; ++j) {
+            float acc = 0.f, g = 0.f;
+            if (j < T) {
+#pragma unroll
+                for (int d = 0; d < kMsaMaxDk; ++d)
+                    if (d < dk) {
+                        acc = fmaf(q[d], Ks[j * dk + d], acc);
+                        g = fmaf(go[d], Vs[j * dk + d], g);
+                    }
+                acc = acc / scale_div;
+                mx = fmaxf(mx, acc);
+            }
+            pr[j] = acc;
+            dp[j] = g;
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < kMsaMaxT; ++j) {
+            pr[j] = j < T ? expf(pr[j] - mx) : 0.f;
+            sum += pr[j];
+        }
+        float delta = 0.f;
+#pragma unroll
+        for (int j = 0; j < kMsaMaxT; ++j) {
+            pr[j] = pr[j] / sum;
+            delta = fmaf(pr[j], dp[j], delta);
+        }
+#pragma unroll
+        for (int j = 0; j < kMsaMaxT; ++j) {
+            if (j < T) {
+                const float ds = pr[j] * (dp[j] - delta) / scale_div;
+                Ps[i * 33 + j] = pr[j];
+                dSs[i * 33 + j] = ds;
+#pragma unroll
+                for (int d = 0; d < kMsaMaxDk; ++d)
+                    if (d < dk) dq[d] = fmaf(ds, Ks[j * dk + d], dq[d]);
+            }
+        }
+        float* out = dQKV + ((size_t)title * T + i) * ldd + head * dk;
+#pragma unroll
+        for (int d = 0; d < kMsaMaxDk; ++d)
+            if (d < dk) out[d] = dq[d];
+    }
+    __syncwarp();
+    if (i < T) {                                                    // lane i now owns KEY / VALUE row i
+        float gk[kMsaMaxDk], gv[kMsaMaxDk];
+#pragma unroll
+        for (int d = 0; d < kMsaMaxDk; ++d) gk[d] = gv[d] = 0.f;
+        for (int qr = 0; qr < T; ++qr) {
+            const float ds = dSs[qr * 33 + i], p = Ps[qr * 33 + i];
+#pragma unroll
+            for (int d = 0; d < kMsaMaxDk; ++d)
+                if (d < dk) {
+                    gk[d] = fmaf(ds, Qs[qr * dk + d], gk[d]);
+                    gv[d] = fmaf(p, dOs[qr * dk + d], gv[d]);
+                }
+        }
+        float* out = dQKV + ((size_t)title * T + i) * ldd + head * dk;
+#pragma unroll
+        for (int d = 0; d < kMsaMaxDk; ++d)
+            if (d < dk) {
+                out[hd + d] = gk[d];
+                out[2 * hd + d] = gv[d];
+            }
+    }
+}
+
+inline int launch_msa_attention_bwd(const float* QKV, int ld, const float* H, int ldh, const float* dH, int lddh, float* dQKV,
+                                    int ldd, int64_t n_titles, int T, int heads, int dk, cudaStream_t st) {
+    if (n_titles <= 0) return DIGAT_OK;
+    DIGAT_REQUIRE(QKV && H && dH && dQKV, "digat_msa_attention_bwd: null pointer");
+    DIGAT_REQUIRE(T >= 1 && T <= kMsaMaxT && dk >= 1 && dk <= kMsaMaxDk && heads >= 1,
+                  "digat_msa_attention_bwd: needs max_title_length <= %d and head_dim <= %d (T=%d, dk=%d)", kMsaMaxT, kMsaMaxDk, T, dk);
+    DIGAT_REQUIRE(ld >= 3 * heads * dk && ldd >= 3 * heads * dk && ldh >= heads * dk && lddh >= heads * dk,
+                  "digat_msa_attention_bwd: leading dimension too small");
+    const int64_t units = n_titles * heads;
+    const size_t smem = (size_t)kMsaBwdWarps * (4 * T * dk + 2 * T * 33) * sizeof(float);
+    DIGAT_REQUIRE(units / kMsaBwdWarps + 1 < (1LL << 31), "digat_msa_attention_bwd: too many titles for one launch");
+    if (int rc_ = ensure_dynamic_smem(msa_attention_bwd_kernel, smem)) return rc_;
+    msa_attention_bwd_kernel<<<(unsigned)((units + kMsaBwdWarps - 1) / kMsaBwdWarps), kMsaBwdWarps * 32, smem, st>>>(
+        QKV, ld, H, ldh, dH, lddh, dQKV, ldd, n_titles, T, heads, dk, sqrtf((float)dk));
+    return check_launch("digat_msa_attention_bwd");
+}
+
+// Backward of additive_pool_kernel (layers.py:107-115).  One CTA per title:
+//   alpha recomputed;  dalpha_t = dout . H_t;  da_t = alpha_t (dalpha_t - sum_k alpha_k dalpha_k)   (0 on masked tokens)
+//   dH_t (through the weighted sum) = alpha_t dout;  datt_pre[t, c] = da_t w2[c] (1 - tanh^2);  dw2_part[title, c] = sum_t da_t tanh
+// (the gradient through the affine1 GEMM reaches H via the caller's autograd and is added to dH there).
+__global__ void __launch_bounds__(kPoolThreads)
+additive_pool_bwd_kernel(const float* __restrict__ att_pre, int lda, const float* __restrict__ w2, const float* __restrict__ H,
+                         int ldh, const uint8_t* __restrict__ mask, const float* __restrict__ dout, int ldo,
+                         float* __restrict__ dH, int lddh, float* __restrict__ datt, int ldda, float* __restrict__ dw2_part,
+                         int T, int A, int D) {
+    __shared__ float a_s[kMsaMaxT], al_s[kMsaMaxT], ds_s[kMsaMaxT];
+    __shared__ double da_s[kMsaMaxT];      // dalpha_t in double: alpha_t (dalpha_t - sum alpha dalpha) cancels (cf. topic_segment_bwd)
+    const int64_t title = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* go = dout + (size_t)title * ldo;
+    for (int t = warp; t < T; t += kPoolThreads / 32) {
+        const float* row = att_pre + ((size_t)title * T + t) * lda;
+        const float* hrow = H + ((size_t)title * T + t) * ldh;
+        float acc = 0.f;
+        double g = 0.0;
+        for (int c = lane; c < A; c += 32) acc = fmaf(tanhf(row[c]), w2[c], acc);
+        for (int d = lane; d < D; d += 32) g += (double)go[d] * hrow[d];
+        acc = warp_sum(acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+        if (lane == 0) {
+            a_s[t] = mask[(size_t)title * T + t] != 0 ? acc : kNegFill;
+            da_s[t] = g;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < T) {
+        float mx = -INFINITY;
+        for (int t = 0; t < T; ++t) mx = fmaxf(mx, a_s[t]);
+        float sum = 0.f;
+        for (int t = 0; t < T; ++t) sum += expf(a_s[t] - mx);
+        al_s[threadIdx.x] = expf(a_s[threadIdx.x] - mx) / sum;
+    }
+    __syncthreads();
+    if (threadIdx.x < T) {
+        double tt = 0.0;
+        for (int t = 0; t < T; ++t) tt += (double)al_s[t] * da_s[t];
+        // a masked token's score is the constant fill value: no gradient (masked_fill), whatever alpha it ends up with
+        ds_s[threadIdx.x] = mask[(size_t)title * T + threadIdx.x] != 0 ? (float)((double)al_s[threadIdx.x] * (da_s[threadIdx.x] - tt)) : 0.f;
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < D / 4; q += kPoolThreads) {
+        const float4 g = reinterpret_cast<const float4*>(go)[q];
+        for (int t = 0; t < T; ++t) {
+            const float p = al_s[t];
+            reinterpret_cast<float4*>(dH + ((size_t)title * T + t) * lddh)[q] = make_float4(p * g.x, p * g.y, p * g.z, p * g.w);
+        }
+    }
+    for (int c = threadIdx.x; c < A; c += kPoolThreads) {
+        const float w = w2[c];
+        float acc = 0.f;
+        for (int t = 0; t < T; ++t) {
+            const float th = tanhf(att_pre[((size_t)title * T + t) * lda + c]);
+            const float ds = ds_s[t];
+            datt[((size_t)title * T + t) * ldda + c] = ds * w * (1.f - th * th);
+            acc = fmaf(ds, th, acc);
+        }
+        dw2_part[(size_t)title * A + c] = acc;
+    }
+}
+
+inline int launch_additive_pool_bwd(const float* att_pre, int lda, const float* w2, const float* H, int ldh, const uint8_t* mask,
+                                    const float* dout, int ldo, float* dH, int lddh, float* datt, int ldda, float* dw2_part,
+                                    int64_t n_titles, int T, int A, int D, cudaStream_t st) {
+    if (n_titles <= 0) return DIGAT_OK;
+    DIGAT_REQUIRE(att_pre && w2 && H && mask && dout && dH && datt && dw2_part, "digat_additive_pool_bwd: null pointer");
+    DIGAT_REQUIRE(T >= 1 && T <= kMsaMaxT && A >= 1 && D >= 4 && (D & 3) == 0 && (ldh & 3) == 0 && (ldo & 3) == 0 && (lddh & 3) == 0 &&
+                  lda >= A && ldda >= A && ldh >= D && ldo >= D && lddh >= D, "digat_additive_pool_bwd: bad sizes (T=%d, A=%d, D=%d)", T, A, D);
+    DIGAT_REQUIRE(aligned16(dout) && aligned16(dH), "digat_additive_pool_bwd: dout / dH must be 16-byte aligned");
+    DIGAT_REQUIRE(n_titles < (1LL << 31), "digat_additive_pool_bwd: too many titles for one launch");
+    additive_pool_bwd_kernel<<<(unsigned)n_titles, kPoolThreads, 0, st>>>(att_pre, lda, w2, H, ldh, mask, dout, ldo, dH, lddh, datt,
+                                                                          ldda, dw2_part, T, A, D);
+    return check_launch("digat_additive_pool_bwd");
+}
+
+// dtable[idx[r], :] += src[r, :]   (backward of the embedding gather; float atomics, like torch's embedding backward)
+__global__ void scatter_add_rows_kernel(float* __restrict__ dtable, int64_t n_table, const int32_t* __restrict__ idx,
+                                        const float* __restrict__ src, int64_t lds, int64_t rows, int D) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * D) return;
+    const int64_t r = i / D;
+    const int d = (int)(i - r * D);
+    const int64_t t = idx[r];
+    if (t < 0 || t >= n_table) return;                              // (the forward gather reports out-of-range ids)
+    atomicAdd(dtable + t * D + d, src[r * lds + d]);
+}
+
+inline int launch_scatter_add_rows(float* dtable, int64_t n_table, const int32_t* idx, const float* src, int64_t lds, int64_t rows,
+                                   int D, cudaStream_t st) {
+    if (rows <= 0) return DIGAT_OK;
+    DIGAT_REQUIRE(dtable && idx && src && D >= 1 && lds >= D, "digat_scatter_add_rows: null pointer or bad sizes");
+    const int64_t total = rows * D;
+    DIGAT_REQUIRE((total + 255) / 256 < (1LL << 31), "digat_scatter_add_rows: too many elements for one launch");
+    scatter_add_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dtable, n_table, idx, src, lds, rows, D);
+    return check_launch("digat_scatter_add_rows");
+}
+
 }  // namespace digat

@@ -46,7 +46,8 @@ class Model(nn.Module):
 
     def forward(self, user_title_text, user_title_mask, user_graph, user_category_mask, user_category_indices,
                 news_title_text, news_title_mask, news_graph, news_graph_mask):
-        """Reference Model.forward (model.py:54-77) on token tensors; needs the news encoder (inference only)."""
+        """Reference Model.forward (model.py:54-77) on token tensors; needs the news encoder.  With gradients enabled both encoders
+        run their training paths (end-to-end, as reference trainer.py)."""
         if self.news_encoder is None:
             raise RuntimeError('Model was built without the text-side config fields: use forward_embeddings')
         bs, news_num = news_graph.shape[0], news_graph.shape[1]

@@ -2,9 +2,10 @@
 (SURVEY.md section 8(f) row 4): same class / parameter names and shapes (``word_embedding.weight``,
 ``multiheadSelfattention.W_{Q,K,V}``, ``attention.affine{1,2}``), same ``forward(title_text, title_mask)``.
 
-Inference only (``torch.no_grad``): in the reference's evaluation this encoder runs once over all news
-(util.compute_scores, util.py:24-33) and its output is the cached embedding table the graph encoder reads.  Training it
-(reference model.py:68-69) needs its backward kernels, which are not written: asking for gradients raises.
+In the reference's evaluation this encoder runs once over all news (util.compute_scores, util.py:24-33) and its output is the
+cached embedding table the graph encoder reads: that is the no-grad path below.  With gradients enabled (reference
+model.py:68-69 trains it end to end) ``forward`` runs the same kernels as autograd nodes with their backward kernels
+(digat_msa_attention_bwd, digat_additive_pool_bwd, digat_scatter_add_rows; projections through autograd_ops.lin).
 
   word embeddings    digat_gather_rows_i32            [titles*T, E]
   Q | K | V          ONE projection GEMM              [titles*T, 3*h*dk]   (stacked weight, biases of Q and V)
@@ -22,6 +23,105 @@ import torch.nn as nn
 
 from . import _lib
 from .graphEncoders import PackedWeight, _ptr, _stream, linear
+
+
+# ------------------------------------------------------------------------------------------------ training path
+# Autograd nodes over the backward kernels of news_encoder.cuh; the projections go through autograd_ops.lin (tcgen05 /
+# exact-fp32 GEMMs with their dgrad and wgrad), dropout masks come from torch like in the graph encoder's training path.
+class _EmbeddingFn(torch.autograd.Function):
+    """rows = table[idx] (digat_gather_rows_i32, optionally into a column block of a wider matrix); the backward scatter-adds
+    into a zeroed table-shaped gradient (digat_scatter_add_rows, float atomics like torch's embedding backward)."""
+
+    @staticmethod
+    def forward(ctx, table, idx, err):
+        rows, E = idx.numel(), table.shape[1]
+        out = torch.empty((rows, E), device=table.device, dtype=torch.float32)
+        _lib.call('digat_gather_rows_i32', table.data_ptr(), table.shape[0], idx.data_ptr(), out.data_ptr(), E, rows, E,
+                  err.data_ptr(), _stream())
+        ctx.save_for_backward(idx)
+        ctx.shape = tuple(table.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (idx,) = ctx.saved_tensors
+        dout = dout.contiguous()
+        dtable = torch.zeros(ctx.shape, device=dout.device, dtype=torch.float32)
+        _lib.call('digat_scatter_add_rows', dtable.data_ptr(), ctx.shape[0], idx.data_ptr(), dout.data_ptr(), dout.stride(0),
+                  idx.numel(), ctx.shape[1], _stream())
+        return dtable, None, None
+
+
+class _MsaAttentionFn(torch.autograd.Function):
+    """H = relu(multi-head self-attention) from the stacked Q | K | V rows (digat_msa_attention_fwd / _bwd)."""
+
+    @staticmethod
+    def forward(ctx, qkv, n_titles, T, heads, dk):
+        qkv = qkv.contiguous()
+        hd = heads * dk
+        H = torch.empty((n_titles * T, hd), device=qkv.device, dtype=torch.float32)
+        _lib.call('digat_msa_attention_fwd', qkv.data_ptr(), qkv.stride(0), H.data_ptr(), hd, n_titles, T, heads, dk, _stream())
+        ctx.save_for_backward(qkv, H)
+        ctx.dims = (n_titles, T, heads, dk)
+        return H
+
+    @staticmethod
+    def backward(ctx, dH):
+        qkv, H = ctx.saved_tensors
+        n_titles, T, heads, dk = ctx.dims
+        dH = dH.contiguous()
+        dqkv = torch.empty_like(qkv)
+        _lib.call('digat_msa_attention_bwd', qkv.data_ptr(), qkv.stride(0), H.data_ptr(), H.stride(0), dH.data_ptr(), dH.stride(0),
+                  dqkv.data_ptr(), dqkv.stride(0), n_titles, T, heads, dk, _stream())
+        return dqkv, None, None, None, None
+
+
+class _AdditivePoolFn(torch.autograd.Function):
+    """out[title] = sum_t softmax_t(mask(tanh(att_pre_t) . w2)) H_t  (digat_additive_pool_fwd / _bwd)."""
+
+    @staticmethod
+    def forward(ctx, att_pre, w2, H, mask, n_titles, T):
+        att_pre, w2, H = att_pre.contiguous(), w2.contiguous(), H.contiguous()
+        D, A = H.shape[1], att_pre.shape[1]
+        out = torch.empty((n_titles, D), device=H.device, dtype=torch.float32)
+        _lib.call('digat_additive_pool_fwd', att_pre.data_ptr(), A, w2.data_ptr(), H.data_ptr(), D, mask.data_ptr(),
+                  out.data_ptr(), D, n_titles, T, A, D, _stream())
+        ctx.save_for_backward(att_pre, w2, H, mask)
+        ctx.dims = (n_titles, T)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        from .autograd_ops import colsum
+        att_pre, w2, H, mask = ctx.saved_tensors
+        n_titles, T = ctx.dims
+        D, A = H.shape[1], att_pre.shape[1]
+        dout = dout.contiguous()
+        dH = torch.empty_like(H)
+        datt = torch.empty_like(att_pre)
+        dw2_part = torch.empty((n_titles, A), device=H.device, dtype=torch.float32)
+        _lib.call('digat_additive_pool_bwd', att_pre.data_ptr(), A, w2.data_ptr(), H.data_ptr(), D, mask.data_ptr(),
+                  dout.data_ptr(), dout.stride(0), dH.data_ptr(), D, datt.data_ptr(), A, dw2_part.data_ptr(), n_titles, T, A, D,
+                  _stream())
+        return datt, colsum(dw2_part), dH, None, None, None
+
+
+def _train_prologue(enc, title_text, title_mask):
+    if not title_text.is_cuda:
+        raise RuntimeError('title_text must be a CUDA tensor (digat_b200 has no CPU fallback)')
+    dev = title_text.device
+    _lib.require_device(dev.index if dev.index is not None else torch.cuda.current_device())
+    B, news_num, T = title_text.shape
+    if T != enc.max_sentence_length:
+        raise RuntimeError('title length %d != max_title_length %d' % (T, enc.max_sentence_length))
+    n_titles = B * news_num
+    mask = title_mask.reshape(n_titles, T)
+    mask = (mask != 0).contiguous() if mask.dtype != torch.bool else mask.contiguous()
+    return B, news_num, T, n_titles, mask, torch.zeros(1, dtype=torch.int32, device=dev)
+
+
+def _wants_grad(enc):
+    return torch.is_grad_enabled() and any(p.requires_grad for p in enc.parameters())
 
 
 class MultiHeadAttention(nn.Module):
@@ -122,8 +222,8 @@ class MSA(NewsEncoder):
 
     def forward(self, title_text, title_mask):
         """title_text [B, news_num, T] integer token ids, title_mask [B, news_num, T] -> [B, news_num, h*dk]."""
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise RuntimeError('MSA news encoder: the sm_100a path is inference-only (run under torch.no_grad())')
+        if _wants_grad(self):
+            return self._forward_train(title_text, title_mask)
         if not title_text.is_cuda:
             raise RuntimeError('title_text must be a CUDA tensor (digat_b200 has no CPU fallback)')
         w = self._weights()
@@ -152,6 +252,31 @@ class MSA(NewsEncoder):
             if int(err.item()) != 0:
                 raise RuntimeError('token id out of range in title_text (reference: nn.Embedding raises)')
         return out.view(B, news_num, hd)
+
+
+def _msa_forward_train(self, title_text, title_mask):
+    """newsEncoders.py:71-82 with autograd: dropout on the word embeddings (train mode), Q | K | V as ONE projection, the
+    attention and pooling kernels with their backward kernels; gradients reach every parameter incl. the embedding table."""
+    from .autograd_ops import lin
+    import torch.nn.functional as F
+    B, news_num, T, n_titles, mask, err = _train_prologue(self, title_text, title_mask)
+    m = self.multiheadSelfattention
+    tok = title_text.reshape(-1).to(torch.int32).contiguous()
+    emb = _EmbeddingFn.apply(self.word_embedding.weight, tok, err)
+    if self.training and self.dropout_rate > 0:
+        emb = F.dropout(emb, self.dropout_rate, True)
+    qkv_W = torch.cat([m.W_Q.weight, m.W_K.weight, m.W_V.weight], 0)
+    qkv_b = torch.cat([m.W_Q.bias, torch.zeros_like(m.W_Q.bias), m.W_V.bias], 0)
+    qkv = lin(emb, qkv_W, qkv_b)
+    H = _MsaAttentionFn.apply(qkv, n_titles, T, m.h, m.d_k)
+    att = lin(H, self.attention.affine1.weight, self.attention.affine1.bias)
+    out = _AdditivePoolFn.apply(att, self.attention.affine2.weight.reshape(-1), H, mask, n_titles, T)
+    if int(err.item()) != 0:
+        raise RuntimeError('token id out of range in title_text (reference: nn.Embedding raises)')
+    return out.view(B, news_num, self.news_embedding_dim)
+
+
+MSA._forward_train = _msa_forward_train
 
 
 class Conv1D(nn.Module):
@@ -246,8 +371,8 @@ class CNN(NewsEncoder):
 
     def forward(self, title_text, title_mask):
         """title_text [B, news_num, T] integer token ids, title_mask [B, news_num, T] -> [B, news_num, cnn_kernel_num]."""
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise RuntimeError('CNN news encoder: the sm_100a path is inference-only (run under torch.no_grad())')
+        if _wants_grad(self):
+            return self._forward_train(title_text, title_mask)
         if not title_text.is_cuda:
             raise RuntimeError('title_text must be a CUDA tensor (digat_b200 has no CPU fallback)')
         w = self._weights()
@@ -277,3 +402,44 @@ class CNN(NewsEncoder):
             if int(err.item()) != 0 or bool(bad):
                 raise RuntimeError('token id out of range in title_text (reference: nn.Embedding raises)')
         return out.view(B, news_num, Fk)
+
+
+def _conv_packed_train(conv):
+    """Conv1D.packed() built from the live parameters with differentiable torch ops (permute / pad / cat)."""
+    convs = [conv.conv] if conv.cnn_method == 'naive' else [conv.conv1, conv.conv2, conv.conv3]
+    E, W = conv.in_channels, conv.window
+    rows = []
+    for c in convs:
+        k = c.weight.shape[2]
+        lo = (W - k) // 2
+        full = torch.nn.functional.pad(c.weight.permute(0, 2, 1), (0, 0, lo, W - k - lo))      # [out, W, E], zero blocks outside
+        rows.append(full.reshape(c.weight.shape[0], W * E))
+    return torch.cat(rows, 0), torch.cat([c.bias for c in convs], 0)
+
+
+def _cnn_forward_train(self, title_text, title_mask):
+    """newsEncoders.py:41-54 with autograd: dropout on the word embeddings and on the relu'd convolution output (train mode)."""
+    from .autograd_ops import lin
+    import torch.nn.functional as F
+    B, news_num, T, n_titles, mask, err = _train_prologue(self, title_text, title_mask)
+    W, V = self.conv.window, self.word_embedding.weight.shape[0]
+    pad = (W - 1) // 2
+    tok = title_text.reshape(n_titles, T).to(torch.int32)
+    if bool(((tok < 0) | (tok >= V)).any()):
+        raise RuntimeError('token id out of range in title_text (reference: nn.Embedding raises)')
+    emb = _EmbeddingFn.apply(self.word_embedding.weight, tok.reshape(-1).contiguous(), err)
+    if self.training and self.dropout_rate > 0:
+        emb = F.dropout(emb, self.dropout_rate, True)
+    # im2col [titles*T, W*E]: token t's row holds x[t-pad] | ... | x[t+pad], zeros outside the title (Conv1d's zero padding)
+    x = F.pad(emb.view(n_titles, T, -1), (0, 0, pad, pad))
+    X = torch.cat([x[:, k:k + T, :] for k in range(W)], 2).reshape(n_titles * T, -1)
+    conv_W, conv_b = _conv_packed_train(self.conv)
+    H = torch.relu(lin(X, conv_W, conv_b))
+    if self.training and self.dropout_rate > 0:
+        H = F.dropout(H, self.dropout_rate, True)
+    att = lin(H, self.attention.affine1.weight, self.attention.affine1.bias)
+    out = _AdditivePoolFn.apply(att, self.attention.affine2.weight.reshape(-1), H, mask, n_titles, T)
+    return out.view(B, news_num, self.news_embedding_dim)
+
+
+CNN._forward_train = _cnn_forward_train

@@ -367,6 +367,20 @@ int digat_build_user_graphs(const int32_t* hist_cat, const int32_t* hist_len, ui
 int digat_sag_bfs(const int64_t* sim_off, const int32_t* sim_idx, const double* sim_cos, int32_t* node_id,
                   uint8_t* graph, uint8_t* mask, int n_news, int top_M, int hop, int n_nodes, double threshold,
                   int32_t* err_flag, void* stream);
+/* Backward kernels of the news encoders (training from token tensors, reference model.py:54-77 + autograd):
+ *   digat_msa_attention_bwd  QKV, H as the forward saw / wrote them; dH [titles*T, lddh] -> dQKV [titles*T, ldd] (= dQ | dK | dV;
+ *                            the relu mask H > 0 is applied to dH in-kernel, the T x T attention is recomputed)
+ *   digat_additive_pool_bwd  dout [titles, ldo] -> dH (through the weighted sum only: alpha_t dout), datt [titles*T, ldda]
+ *                            (gradient of the pre-tanh affine1 rows), dw2_part [titles, A] (digat_colsum over the titles = dw2)
+ *   digat_scatter_add_rows   dtable[idx[r], :] += src[r, :] -- the embedding gather's backward (float atomics, as torch's) */
+int digat_msa_attention_bwd(const float* QKV, int ld, const float* H, int ldh, const float* dH, int lddh, float* dQKV, int ldd,
+                            int64_t n_titles, int T, int heads, int dk, void* stream);
+int digat_additive_pool_bwd(const float* att_pre, int lda, const float* w2, const float* H, int ldh, const uint8_t* mask,
+                            const float* dout, int ldo, float* dH, int lddh, float* datt, int ldda, float* dw2_part,
+                            int64_t n_titles, int T, int A, int D, void* stream);
+int digat_scatter_add_rows(float* dtable, int64_t n_table, const int32_t* idx, const float* src, int64_t lds, int64_t rows, int D,
+                           void* stream);
+
 /* ranks[p] = 1-based position of pair p inside its impression under a STABLE descending sort of the scores
  * (reference util.py:70-80).  offsets [n_imp+1] int64 delimit the impressions in the ordered pair list. */
 int digat_rank_impressions(const float* scores, const int64_t* offsets, int32_t* ranks, int64_t n_imp, void* stream);
