@@ -5,7 +5,7 @@ The news (text) encoder is outside the north-star hot path
 embeddings, exactly as reference util.compute_scores does after caching them (util.py:24-33) -- ``forward_embeddings`` is
 ``forward`` from the point where the embeddings exist (and is what trains, through autograd_ops).  When the config carries
 the text-side fields (``vocabulary_size`` ...) the MSA news encoder (newsEncoders.py) is built too and
-``forward`` takes the reference's token tensors (inference only: the text encoder has no backward kernels)."""
+``forward`` takes the reference's token tensors (with gradients enabled both encoders run their training paths)."""
 import torch
 import torch.nn as nn
 

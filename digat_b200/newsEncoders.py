@@ -320,7 +320,7 @@ class Conv1D(nn.Module):
 
 
 class CNN(NewsEncoder):
-    """Drop-in for the CNN news encoder of reference newsEncoders.py:27-55, inference only:
+    """Drop-in for the CNN news encoder of reference newsEncoders.py:27-55 (no-grad path; training: _cnn_forward_train):
       word embeddings   digat_gather_rows_i32, once per window offset, straight into the column blocks of the im2col matrix
                         [titles*T, window*E] (positions outside the title read an appended zero row = Conv1d's zero padding)
       conv + relu       ONE projection GEMM against the packed kernels (relu in its epilogue)
