@@ -566,7 +566,7 @@ def train_record(args, rank, local_rank, world, dev, steps, cpu_baseline=True):
     else:
         fwd = model.forward_embeddings
         broadcast_parameters(model)
-        flat = FlatAdam(model.parameters(), lr=1e-4, max_norm=1.0)
+        flat = FlatAdam(model.parameters(), lr=1e-4, max_norm=1.0, modules=(model,))
 
     def eager_step(inp):
         logits = fwd(*inp)

@@ -53,8 +53,11 @@ class FlatAdam:
     ``weight_decay`` is torch.optim.Adam's L2 term and applies to every parameter (the reference's default is 0, config.py:36;
     its bias / LayerNorm exemption list matches no parameter of this encoder except the biases)."""
 
-    def __init__(self, params, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_norm=1.0):
+    def __init__(self, params, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_norm=1.0, modules=()):
+        """modules: nn.Modules whose encoders keep packed inference copies of the weights (DIGAT / MSA / CNN ``invalidate_packed``):
+        the update kernel writes the parameters in place without bumping ``param._version``, so every step invalidates them."""
         from . import _lib
+        self._packed_owners = [m for mod in modules for m in mod.modules() if hasattr(m, 'invalidate_packed')]
         self._lib = _lib
         self.grads = FlatGradients(params)
         self.params = self.grads.params
@@ -92,6 +95,8 @@ class FlatAdam:
                        self.exp_avg_sq.data_ptr(), n, self.partials.data_ptr(), self.step_count.data_ptr(),
                        self.grad_norm.data_ptr(), float(self.max_norm or 0.0), float(self.lr), float(self.betas[0]),
                        float(self.betas[1]), float(self.eps), float(self.weight_decay), stream)
+        for m in self._packed_owners:
+            m.invalidate_packed()
 
 
 def broadcast_parameters(module, src=0, group=None):

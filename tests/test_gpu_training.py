@@ -111,3 +111,36 @@ def test_graphed_step_with_flat_adam_trains_like_eager_torch():
         worst = max(worst, float((a.detach() - b.detach()).abs().max()) / max(float(b.detach().abs().max()), 1e-12))
     print('worst parameter drift after 10 steps: %.3e' % worst)
     assert worst < 1e-3      # measured 5.8e-5 (Adam turns 1e-6 gradient differences into sign-level update differences on near-zero gradients)
+
+
+def test_flat_adam_step_invalidates_packed_inference_weights():
+    """The update kernel writes parameters in place without bumping their version counters: FlatAdam(modules=...) drops the
+    encoders' packed inference copies after every step, so a no-grad forward right after a step sees the NEW weights."""
+    from oracle import digat_oracle as O
+    from digat_b200 import synth
+    from digat_b200.graphEncoders import DIGAT
+    from digat_b200.training import FlatAdam
+    from tests.test_gpu_backward import ORDER, _batch
+    from tests.helpers import rel_err
+    cfg = synth.make_config(graph_depth=2, dropout_rate=0.0)
+    sd = synth.make_state_dict(cfg, seed=2)
+    batch = _batch(cfg, 6, seed=5)
+    m = DIGAT(cfg, 400)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()                                        # stays in eval mode throughout (no train()/eval() switch to help)
+    b = [batch[k].cuda() for k in ORDER]
+    with torch.no_grad():
+        before = m(*b)[1].clone()
+    flat = FlatAdam(m.parameters(), lr=1e-2, max_norm=0.0, modules=(m,))
+    flat.zero_grad()
+    cn, cu = m(*b)
+    (cn * cu).sum().backward()
+    flat.step()
+    with torch.no_grad():
+        after = m(*b)[1]
+    torch.cuda.synchronize()
+    P = {k: v.detach().double().cpu() for k, v in m.state_dict().items()}
+    bb = {k: (v.double() if v.is_floating_point() else v) for k, v in batch.items()}
+    ref = O.forward(P, *[bb[k] for k in ORDER])[1]
+    assert not torch.allclose(before, after)
+    assert rel_err(after.cpu().numpy(), ref.numpy()) < 1e-5
