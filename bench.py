@@ -220,9 +220,10 @@ def main():
     ap.add_argument('--train-steps', type=int, default=20)
     ap.add_argument('--eager-train', action='store_true',
                     help='train: run the step eagerly instead of replaying it as one CUDA graph')
-    ap.add_argument('--mode', default='score', choices=['score', 'train'],
+    ap.add_argument('--mode', default='score', choices=['score', 'train', 'train_tokens'],
                     help="'score' = the headline metric (+ sustained + train sub-records); 'train' = only the training record "
-                         "(fwd+bwd(+DDP all-reduce)+clip+Adam step, samples/s) as the line")
+                         "(fwd+bwd(+DDP all-reduce)+clip+Adam step, samples/s) as the line; 'train_tokens' = the same step from "
+                         "TOKEN tensors, MSA news encoder included (reference Model.forward, model.py:54-77), eager, one GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
 
@@ -242,6 +243,9 @@ def main():
         rec = train_record(args, rank, local_rank, world, dev, steps=args.steps, cpu_baseline=not args.no_cpu_baseline)
         if rank == 0:
             print(json.dumps(rec))
+    elif args.mode == 'train_tokens':
+        if rank == 0:
+            print(json.dumps(train_tokens_record(args, dev, steps=args.steps)))
     else:
         run_score(args, rank, local_rank, world, dev)
     if world > 1:
@@ -656,6 +660,69 @@ def train_record(args, rank, local_rank, world, dev, steps, cpu_baseline=True):
                                    'sample': '%d fwd+bwd steps of %d behaviours x %d candidates = %d encoder rows (%.1f s of CPU '
                                              'work), oracle/digat_oracle.py under torch autograd, CPU fp32' % (n, 12, news_num, rows, n * sec)}
     return rec
+
+
+def train_tokens_record(args, dev, steps):
+    """End-to-end training step of the reference from TOKEN tensors (model.py:54-77, trainer.py:86-105): MSA news encoder over the
+    64 x 50 history titles and the 320 x n_n candidate-graph titles of a step, then the graph encoder, loss, backward through both,
+    clip + Adam (FlatAdam).  Not part of BASELINE's metric (SURVEY 8(d) excludes the news encoder): an extra record.  Eager (the
+    news encoder's training path reads an error flag on the host), one GPU."""
+    import torch.nn.functional as F
+    from digat_b200 import _lib, synth
+    from digat_b200.model import Model
+    from digat_b200.training import FlatAdam
+    workload = args.workload if args.workload not in SHARDED_WORKLOADS else 'mind_small_dev_n3_L3'
+    N, hops, L = WORKLOADS[workload][:3]
+    cfg = synth.make_text_config(vocabulary_size=40000, SAG_neighbors=N, SAG_hops=hops, graph_depth=L, dropout_rate=0.2)
+    model = Model(cfg)
+    model.graph_encoder.load_state_dict(synth.make_state_dict(cfg, D=D, seed=0))
+    model.news_encoder.load_state_dict(synth.make_msa_state_dict(cfg, seed=1))
+    model = model.to(dev).train()
+    corpus = synth.make_corpus(cfg, D=D, n_news=20000, n_behaviors=4096, mean_candidates=8.0, seed=0)
+    tok, mask = synth.make_titles(cfg, 20000, seed=2)
+    tok, mask = tok.to(dev), mask.to(dev)
+    flat = FlatAdam(model.parameters(), lr=1e-4, max_norm=1.0, modules=(model,))
+    bs, news_num = 64, 5
+    rng = np.random.Generator(np.random.PCG64(0))
+    node = torch.from_numpy(corpus.news_node_ID.astype(np.int64)).to(dev)
+    ng, nm = torch.from_numpy(corpus.news_graph).to(dev), torch.from_numpy(corpus.news_graph_mask).to(dev)
+    hist = torch.from_numpy(corpus.history.astype(np.int64)).to(dev)
+    ug, cm, ci = (torch.from_numpy(x).to(dev) for x in (corpus.user_graph, corpus.user_category_mask, corpus.user_category_indices))
+
+    def inputs():
+        beh = torch.from_numpy(rng.integers(0, hist.shape[0], size=bs)).to(dev)
+        cand = torch.from_numpy(rng.integers(1, tok.shape[0], size=(bs, news_num))).to(dev)
+        return (tok[hist[beh]], mask[hist[beh]], ug[beh], cm[beh], ci[beh], tok[node[cand]], mask[node[cand]], ng[cand], nm[cand])
+
+    def step(inp):
+        logits = model(*inp)
+        loss = (-F.log_softmax(logits, dim=1).select(1, 0)).mean()
+        flat.zero_grad()
+        loss.backward()
+        flat.step()
+        return loss
+    warmup = max(args.warmup, 3)
+    batches = [inputs() for _ in range(warmup + steps)]
+    for i in range(warmup):
+        step(batches[i])
+    torch.cuda.synchronize()
+    _lib.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(warmup, warmup + steps):
+        loss = step(batches[i])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    titles = bs * cfg.max_history_num + bs * news_num * cfg.news_graph_size
+    return {'metric': 'train_samples_per_sec_from_tokens', 'value': steps * bs / (ms * 1e-3), 'unit': 'samples/s', 'n_gpus': 1,
+            'steps': steps, 'warmup': warmup, 'ms_per_step': ms / steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': workload + ':train_tokens', 'behaviours_per_gpu': bs, 'candidates': news_num,
+                       'titles_per_step': titles, 'tokens_per_title': cfg.max_title_length, 'vocabulary': cfg.vocabulary_size,
+                       'news_encoder': 'MSA 16 x 25, word_embedding_dim 300', 'dropout': 0.2,
+                       'optimizer': 'Adam + clip_grad_norm 1 (flat buffers)', 'execution': 'eager'},
+            'gpu_launches': _lib.launch_count(), 'final_loss': float(loss)}
 
 
 def summarize_kernels(records, hbm_peak, tensor_peak, active_rows=None):
