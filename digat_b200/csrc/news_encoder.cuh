@@ -155,37 +155,39 @@ constexpr int kMsaBwdWarps = 4;
 __global__ void __launch_bounds__(kMsaBwdWarps * 32)
 msa_attention_bwd_kernel(const float* __restrict__ QKV, int ld, const float* __restrict__ H, int ldh, const float* __restrict__ dH,
                          int lddh, float* __restrict__ dQKV, int ldd, int64_t n_titles, int T, int heads, int dk, float scale_div) {
-    extern __shared__ float msa_smem[];                             // per warp: Q, K, V, dO [T*dk] each, P, dS [T][33] each
+    extern __shared__ __align__(16) float msa_smem[];               // per warp: Q, K, V, dO [T][dkp] each, P, dS [T][33] each
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t unit = (int64_t)blockIdx.x * kMsaBwdWarps + warp;
     if (unit >= n_titles * heads) return;
     const int64_t title = unit / heads;
     const int head = (int)(unit - title * heads);
     const int hd = heads * dk;
-    float* Qs = msa_smem + (size_t)warp * (4 * T * dk + 2 * T * 33);
-    float* Ks = Qs + T * dk;
-    float* Vs = Ks + T * dk;
-    float* dOs = Vs + T * dk;
-    float* Ps = dOs + T * dk;
+    const int dkp = (dk + 3) & ~3, nq = dkp >> 2;                   // rows padded to float4s (zeros): every broadcast read is an LDS.128
+    float* Qs = msa_smem + (size_t)warp * ((4 * T * dkp + 2 * T * 33 + 3) & ~3);       // 16-byte aligned slices
+    float* Ks = Qs + T * dkp;
+    float* Vs = Ks + T * dkp;
+    float* dOs = Vs + T * dkp;
+    float* Ps = dOs + T * dkp;
     float* dSs = Ps + T * 33;
     const float* base = QKV + (size_t)title * T * ld + head * dk;
-    for (int e = lane; e < T * dk; e += 32) {
-        const int t = e / dk, d = e - t * dk;
-        Qs[e] = base[(size_t)t * ld + d];
-        Ks[e] = base[(size_t)t * ld + hd + d];
-        Vs[e] = base[(size_t)t * ld + 2 * hd + d];
+    for (int e = lane; e < T * dkp; e += 32) {
+        const int t = e / dkp, d = e - t * dkp;
+        const bool in = d < dk;
         const size_t hrow = (size_t)title * T + t;
-        dOs[e] = H[hrow * ldh + head * dk + d] > 0.f ? dH[hrow * lddh + head * dk + d] : 0.f;
+        Qs[e] = in ? base[(size_t)t * ld + d] : 0.f;
+        Ks[e] = in ? base[(size_t)t * ld + hd + d] : 0.f;
+        Vs[e] = in ? base[(size_t)t * ld + 2 * hd + d] : 0.f;
+        dOs[e] = (in && H[hrow * ldh + head * dk + d] > 0.f) ? dH[hrow * lddh + head * dk + d] : 0.f;
     }
     __syncwarp();
     const int i = lane;
     if (i < T) {
-        float q[kMsaMaxDk], go[kMsaMaxDk], dq[kMsaMaxDk];
+        float4 q[kMsaMaxDk / 4], go[kMsaMaxDk / 4], dq[kMsaMaxDk / 4];
 #pragma unroll
-        for (int d = 0; d < kMsaMaxDk; ++d) {
-            q[d] = d < dk ? Qs[i * dk + d] : 0.f;
-            go[d] = d < dk ? dOs[i * dk + d] : 0.f;
-            dq[d] = 0.f;
+        for (int d4 = 0; d4 < kMsaMaxDk / 4; ++d4) {
+            q[d4] = d4 < nq ? reinterpret_cast<const float4*>(Qs + i * dkp)[d4] : make_float4(0.f, 0.f, 0.f, 0.f);
+            go[d4] = d4 < nq ? reinterpret_cast<const float4*>(dOs + i * dkp)[d4] : make_float4(0.f, 0.f, 0.f, 0.f);
+            dq[d4] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         float pr[kMsaMaxT], dp[kMsaMaxT];
         float mx = -INFINITY;
@@ -193,11 +195,14 @@ msa_attention_bwd_kernel(const float* __restrict__ QKV, int ld, const float* __r
         for (int j = 0; j < kMsaMaxT; ++j) {
             float acc = 0.f, g = 0.f;
             if (j < T) {
+                const float4* kr = reinterpret_cast<const float4*>(Ks + j * dkp);
+                const float4* vr = reinterpret_cast<const float4*>(Vs + j * dkp);
 #pragma unroll
-                for (int d = 0; d < kMsaMaxDk; ++d)
-                    if (d < dk) {
-                        acc = fmaf(q[d], Ks[j * dk + d], acc);
-                        g = fmaf(go[d], Vs[j * dk + d], g);
+                for (int d4 = 0; d4 < kMsaMaxDk / 4; ++d4)
+                    if (d4 < nq) {
+                        const float4 k = kr[d4], v = vr[d4];
+                        acc = fmaf(q[d4].x, k.x, acc); acc = fmaf(q[d4].y, k.y, acc); acc = fmaf(q[d4].z, k.z, acc); acc = fmaf(q[d4].w, k.w, acc);
+                        g = fmaf(go[d4].x, v.x, g); g = fmaf(go[d4].y, v.y, g); g = fmaf(go[d4].z, v.z, g); g = fmaf(go[d4].w, v.w, g);
                     }
                 acc = acc / scale_div;
                 mx = fmaxf(mx, acc);
@@ -223,37 +228,56 @@ msa_attention_bwd_kernel(const float* __restrict__ QKV, int ld, const float* __r
                 const float ds = pr[j] * (dp[j] - delta) / scale_div;
                 Ps[i * 33 + j] = pr[j];
                 dSs[i * 33 + j] = ds;
+                const float4* kr = reinterpret_cast<const float4*>(Ks + j * dkp);
 #pragma unroll
-                for (int d = 0; d < kMsaMaxDk; ++d)
-                    if (d < dk) dq[d] = fmaf(ds, Ks[j * dk + d], dq[d]);
+                for (int d4 = 0; d4 < kMsaMaxDk / 4; ++d4)
+                    if (d4 < nq) {
+                        const float4 k = kr[d4];
+                        dq[d4].x = fmaf(ds, k.x, dq[d4].x); dq[d4].y = fmaf(ds, k.y, dq[d4].y);
+                        dq[d4].z = fmaf(ds, k.z, dq[d4].z); dq[d4].w = fmaf(ds, k.w, dq[d4].w);
+                    }
             }
         }
         float* out = dQKV + ((size_t)title * T + i) * ldd + head * dk;
 #pragma unroll
-        for (int d = 0; d < kMsaMaxDk; ++d)
-            if (d < dk) out[d] = dq[d];
+        for (int d4 = 0; d4 < kMsaMaxDk / 4; ++d4) {
+            const float v4[4] = {dq[d4].x, dq[d4].y, dq[d4].z, dq[d4].w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (4 * d4 + c < dk) out[4 * d4 + c] = v4[c];
+        }
     }
     __syncwarp();
     if (i < T) {                                                    // lane i now owns KEY / VALUE row i
-        float gk[kMsaMaxDk], gv[kMsaMaxDk];
+        float4 gk[kMsaMaxDk / 4], gv[kMsaMaxDk / 4];
 #pragma unroll
-        for (int d = 0; d < kMsaMaxDk; ++d) gk[d] = gv[d] = 0.f;
+        for (int d4 = 0; d4 < kMsaMaxDk / 4; ++d4) gk[d4] = gv[d4] = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int qr = 0; qr < T; ++qr) {
             const float ds = dSs[qr * 33 + i], p = Ps[qr * 33 + i];
+            const float4* qrow = reinterpret_cast<const float4*>(Qs + qr * dkp);
+            const float4* grow = reinterpret_cast<const float4*>(dOs + qr * dkp);
 #pragma unroll
-            for (int d = 0; d < kMsaMaxDk; ++d)
-                if (d < dk) {
-                    gk[d] = fmaf(ds, Qs[qr * dk + d], gk[d]);
-                    gv[d] = fmaf(p, dOs[qr * dk + d], gv[d]);
+            for (int d4 = 0; d4 < kMsaMaxDk / 4; ++d4)
+                if (d4 < nq) {
+                    const float4 qq = qrow[d4], gg = grow[d4];
+                    gk[d4].x = fmaf(ds, qq.x, gk[d4].x); gk[d4].y = fmaf(ds, qq.y, gk[d4].y);
+                    gk[d4].z = fmaf(ds, qq.z, gk[d4].z); gk[d4].w = fmaf(ds, qq.w, gk[d4].w);
+                    gv[d4].x = fmaf(p, gg.x, gv[d4].x); gv[d4].y = fmaf(p, gg.y, gv[d4].y);
+                    gv[d4].z = fmaf(p, gg.z, gv[d4].z); gv[d4].w = fmaf(p, gg.w, gv[d4].w);
                 }
         }
         float* out = dQKV + ((size_t)title * T + i) * ldd + head * dk;
 #pragma unroll
-        for (int d = 0; d < kMsaMaxDk; ++d)
-            if (d < dk) {
-                out[hd + d] = gk[d];
-                out[2 * hd + d] = gv[d];
-            }
+        for (int d4 = 0; d4 < kMsaMaxDk / 4; ++d4) {
+            const float k4[4] = {gk[d4].x, gk[d4].y, gk[d4].z, gk[d4].w};
+            const float v4[4] = {gv[d4].x, gv[d4].y, gv[d4].z, gv[d4].w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (4 * d4 + c < dk) {
+                    out[hd + 4 * d4 + c] = k4[c];
+                    out[2 * hd + 4 * d4 + c] = v4[c];
+                }
+        }
     }
 }
 
@@ -266,7 +290,8 @@ inline int launch_msa_attention_bwd(const float* QKV, int ld, const float* H, in
     DIGAT_REQUIRE(ld >= 3 * heads * dk && ldd >= 3 * heads * dk && ldh >= heads * dk && lddh >= heads * dk,
                   "digat_msa_attention_bwd: leading dimension too small");
     const int64_t units = n_titles * heads;
-    const size_t smem = (size_t)kMsaBwdWarps * (4 * T * dk + 2 * T * 33) * sizeof(float);
+    const int dkp = (dk + 3) & ~3;
+    const size_t smem = (size_t)kMsaBwdWarps * ((4 * T * dkp + 2 * T * 33 + 3) & ~3) * sizeof(float);
     DIGAT_REQUIRE(units / kMsaBwdWarps + 1 < (1LL << 31), "digat_msa_attention_bwd: too many titles for one launch");
     if (int rc_ = ensure_dynamic_smem(msa_attention_bwd_kernel, smem)) return rc_;
     msa_attention_bwd_kernel<<<(unsigned)((units + kMsaBwdWarps - 1) / kMsaBwdWarps), kMsaBwdWarps * 32, smem, st>>>(
