@@ -26,20 +26,21 @@ constexpr int kMsaWarps = 8;       // (title, head) pairs per CTA
 __global__ void __launch_bounds__(kMsaWarps * 32)
 msa_attention_kernel(const float* __restrict__ QKV, int ld, float* __restrict__ H, int ldh, int64_t n_titles, int T, int heads,
                      int dk, float inv_scale_div) {
-    extern __shared__ float msa_smem[];                             // [kMsaWarps][2][T * dk]
+    extern __shared__ __align__(16) float msa_smem[];               // [kMsaWarps][2][T * dkp], rows padded to float4s (zeros)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t unit = (int64_t)blockIdx.x * kMsaWarps + warp;    // (title, head)
     if (unit >= n_titles * heads) return;
     const int64_t title = unit / heads;
     const int head = (int)(unit - title * heads);
     const int hd = heads * dk;
-    float* Ks = msa_smem + (size_t)warp * 2 * T * dk;
-    float* Vs = Ks + T * dk;
+    const int dkp = (dk + 3) & ~3, nq = dkp >> 2;                   // every broadcast read of a K / V row is an LDS.128
+    float* Ks = msa_smem + (size_t)warp * 2 * T * dkp;
+    float* Vs = Ks + T * dkp;
     const float* base = QKV + (size_t)title * T * ld + head * dk;   // Q block; K at +hd, V at +2*hd
-    for (int e = lane; e < T * dk; e += 32) {
-        const int t = e / dk, d = e - t * dk;
-        Ks[e] = base[(size_t)t * ld + hd + d];
-        Vs[e] = base[(size_t)t * ld + 2 * hd + d];
+    for (int e = lane; e < T * dkp; e += 32) {
+        const int t = e / dkp, d = e - t * dkp;
+        Ks[e] = d < dk ? base[(size_t)t * ld + hd + d] : 0.f;
+        Vs[e] = d < dk ? base[(size_t)t * ld + 2 * hd + d] : 0.f;
     }
     float q[kMsaMaxDk];
 #pragma unroll
@@ -51,9 +52,14 @@ msa_attention_kernel(const float* __restrict__ QKV, int ld, float* __restrict__ 
     for (int j = 0; j < kMsaMaxT; ++j) {
         float acc = 0.f;
         if (j < T) {
+            const float4* kr = reinterpret_cast<const float4*>(Ks + j * dkp);
 #pragma unroll
-            for (int d = 0; d < kMsaMaxDk; ++d)
-                if (d < dk) acc = fmaf(q[d], Ks[j * dk + d], acc);
+            for (int d4 = 0; d4 < kMsaMaxDk / 4; ++d4)
+                if (d4 < nq) {                                       // (same ascending-d fma chain as a scalar loop: q is 0 past dk)
+                    const float4 k = kr[d4];
+                    acc = fmaf(q[4 * d4 + 0], k.x, acc); acc = fmaf(q[4 * d4 + 1], k.y, acc);
+                    acc = fmaf(q[4 * d4 + 2], k.z, acc); acc = fmaf(q[4 * d4 + 3], k.w, acc);
+                }
             acc = acc / inv_scale_div;                               // the reference divides by sqrt(dk) (layers.py:89)
             mx = fmaxf(mx, acc);
         }
@@ -72,9 +78,14 @@ msa_attention_kernel(const float* __restrict__ QKV, int ld, float* __restrict__ 
     for (int j = 0; j < kMsaMaxT; ++j) {
         if (j < T) {
             const float p = s[j] / sum;
+            const float4* vr = reinterpret_cast<const float4*>(Vs + j * dkp);
 #pragma unroll
-            for (int d = 0; d < kMsaMaxDk; ++d)
-                if (d < dk) o[d] = fmaf(p, Vs[j * dk + d], o[d]);
+            for (int d4 = 0; d4 < kMsaMaxDk / 4; ++d4)
+                if (d4 < nq) {
+                    const float4 v = vr[d4];
+                    o[4 * d4 + 0] = fmaf(p, v.x, o[4 * d4 + 0]); o[4 * d4 + 1] = fmaf(p, v.y, o[4 * d4 + 1]);
+                    o[4 * d4 + 2] = fmaf(p, v.z, o[4 * d4 + 2]); o[4 * d4 + 3] = fmaf(p, v.w, o[4 * d4 + 3]);
+                }
         }
     }
     if (lane < T) {
@@ -93,7 +104,7 @@ inline int launch_msa_attention(const float* QKV, int ld, float* H, int ldh, int
                   "digat_msa_attention_fwd: needs max_title_length <= %d and head_dim <= %d (T=%d, dk=%d)", kMsaMaxT, kMsaMaxDk, T, dk);
     DIGAT_REQUIRE(ld >= 3 * heads * dk && ldh >= heads * dk, "digat_msa_attention_fwd: leading dimension too small");
     const int64_t units = n_titles * heads;
-    const size_t smem = (size_t)kMsaWarps * 2 * T * dk * sizeof(float);
+    const size_t smem = (size_t)kMsaWarps * 2 * T * ((dk + 3) & ~3) * sizeof(float);
     DIGAT_REQUIRE(units / kMsaWarps + 1 < (1LL << 31), "digat_msa_attention_fwd: too many titles for one launch");
     if (int rc_ = ensure_dynamic_smem(msa_attention_kernel, smem)) return rc_;
     msa_attention_kernel<<<(unsigned)((units + kMsaWarps - 1) / kMsaWarps), kMsaWarps * 32, smem, st>>>(
@@ -390,12 +401,30 @@ __global__ void scatter_add_rows_kernel(float* __restrict__ dtable, int64_t n_ta
     atomicAdd(dtable + t * D + d, src[r * lds + d]);
 }
 
+// the same with one 16-byte reduction per quad (red.global.add.v4.f32, sm_90+): D, lds multiples of 4, 16-byte aligned bases
+__global__ void scatter_add_rows_v4_kernel(float* __restrict__ dtable, int64_t n_table, const int32_t* __restrict__ idx,
+                                           const float* __restrict__ src, int64_t lds, int64_t rows, int Dq) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * Dq) return;
+    const int64_t r = i / Dq;
+    const int q = (int)(i - r * Dq);
+    const int64_t t = idx[r];
+    if (t < 0 || t >= n_table) return;
+    const float4 v = *reinterpret_cast<const float4*>(src + r * lds + 4 * q);
+    atomicAdd(reinterpret_cast<float4*>(dtable + t * (int64_t)(4 * Dq)) + q, v);
+}
+
 inline int launch_scatter_add_rows(float* dtable, int64_t n_table, const int32_t* idx, const float* src, int64_t lds, int64_t rows,
                                    int D, cudaStream_t st) {
     if (rows <= 0) return DIGAT_OK;
     DIGAT_REQUIRE(dtable && idx && src && D >= 1 && lds >= D, "digat_scatter_add_rows: null pointer or bad sizes");
     const int64_t total = rows * D;
     DIGAT_REQUIRE((total + 255) / 256 < (1LL << 31), "digat_scatter_add_rows: too many elements for one launch");
+    if ((D & 3) == 0 && (lds & 3) == 0 && aligned16(dtable) && aligned16(src)) {
+        const int64_t quads = rows * (D / 4);
+        scatter_add_rows_v4_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, st>>>(dtable, n_table, idx, src, lds, rows, D / 4);
+        return check_launch("digat_scatter_add_rows");
+    }
     scatter_add_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dtable, n_table, idx, src, lds, rows, D);
     return check_launch("digat_scatter_add_rows");
 }
